@@ -1,0 +1,41 @@
+"""Named parity cases shared by oracle/make_golden.py and tests/ (TEST INFRASTRUCTURE ONLY).
+
+Each case is (config, steps, noise_kind, oracle kwargs).  The first five are the
+BASELINE.json configurations; the rest cover the reference's other
+views / masks / noises / reward modes and its edge cases (tasks "-1" and multi-digit,
+keep_objects_num=False terminal-by-exhaustion, V=5 and V=9, transparent observation).
+"""
+from maexp_b200.config import baseline_config, make_config
+
+_THREE = dict(name="three_rooms", SIZE_X=25, SIZE_Y=25)
+
+
+def cases():
+    c = {}
+    c["cfg1_simple_mlp"] = (baseline_config(1), 60, None, {})
+    c["cfg2_four_rooms_transition_flip_sharedmean"] = (baseline_config(2), 60, None, {})
+    c["cfg3_three_rooms"] = (baseline_config(3), 60, None, {})
+    c["cfg4_four_rectangle_merged_types"] = (baseline_config(4), 40, None, {})
+    c["cfg5_four_rooms_n8"] = (baseline_config(5), 230, None, {})
+    c["simple_views_v5"] = (make_config(agent_view_method="simple", object_view_method="simple", visible_range=5),
+                            40, None, {})
+    c["indtrans_t2_v9_tasks"] = (make_config(
+        agent_view_method="individual_transition", past_step=2, object_view_method="object_types", type_objects=2,
+        agent_tasks=["01", "10", "0", "1", "-1", "01", "0", "1"], visible_range=9,
+        flip_noise_probabilities=[0.2, 0.1, 0.05, 0.02]), 40, None, {})
+    c["relative_transparent"] = (make_config(observation_area_mask="relative", transparent_observation=True,
+                                             num_agents=4), 40, None, {})
+    c["sensing_dist"] = (make_config(observation_noise="sensing_dist", num_agents=3), 30, "normal", {})
+    c["threshold_sensing_dist"] = (make_config(observation_noise="threshold_sensing_dist", num_agents=3,
+                                               noise_threshold_ratio=0.7), 30, "normal", {})
+    c["flat"] = (make_config(observation_noise="flat", num_agents=3), 30, "normal", {})
+    c["merged_flip_three_rooms"] = (make_config(observation_noise="flip", observation_area_mask="merged",
+                                                num_agents=3, map=_THREE), 40, None, {})
+    c["no_keep_small"] = (make_config(keep_objects_num=False, num_objects=3, num_agents=6, max_episode_length=400,
+                                      map=dict(name="simple", SIZE_X=10, SIZE_Y=10),
+                                      init_xys=[[1, 1], [-1, 1], [1, -1], [-1, -1], [2, 2], [-2, -2]]),
+                          300, None, {})
+    c["shared_max_reference_compat"] = (make_config(environment="shared_max_reward", num_agents=5,
+                                                    shuffle_init_xys=False), 60, None,
+                                        {"shared_max_is_mean": True})
+    return c
