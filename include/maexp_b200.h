@@ -1,0 +1,137 @@
+/* maexp_b200 — C-ABI of the B200-native MAEXP hot path (libmaexp_b200.so).
+ *
+ * The reference (Yoshi-0921/MAEXP) is pure Python and has NO FFI of its own
+ * (SURVEY.md §2.1, §8b).  This boundary is therefore introduced *underneath* the reference's
+ * Python plugin surface; each entry point names the reference interface it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  Unless a name ends in
+ * `_host`, every data pointer is a DEVICE pointer owned by the caller (normally a torch
+ * tensor); the library owns only its opaque handles.  Calls are asynchronous on the given
+ * CUDA stream (passed as void* = cudaStream_t).  Return value: 0 ok, <0 error, text via
+ * maexp_last_error().  One host thread per handle; one process per GPU.
+ */
+#ifndef MAEXP_B200_H
+#define MAEXP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAEXP_MAX_AGENTS 16
+#define MAEXP_MAX_TYPES 4
+#define MAEXP_MAX_RINGS 4
+
+/* agent_view_method (core/handlers/observations/agents/__init__.py:22-46) */
+enum { MAEXP_AV_DEFAULT = 0, MAEXP_AV_SIMPLE = 1, MAEXP_AV_INDIVIDUAL = 2, MAEXP_AV_TRANSITION = 3, MAEXP_AV_INDIVIDUAL_TRANSITION = 4 };
+/* object_view_method (core/handlers/observations/objects/__init__.py:18-35) */
+enum { MAEXP_OV_DEFAULT = 0, MAEXP_OV_SIMPLE = 1, MAEXP_OV_TYPES = 2 };
+/* observation_area_mask (core/handlers/observations/__init__.py:21-28, masks/__init__.py:26-43) */
+enum { MAEXP_MASK_LOCAL = 0, MAEXP_MASK_RELATIVE = 1, MAEXP_MASK_MERGED = 2 };
+/* observation_noise (core/handlers/observations/noises/__init__.py:34-69) */
+enum { MAEXP_NOISE_NONE = 0, MAEXP_NOISE_FLIP = 1, MAEXP_NOISE_DIST = 2, MAEXP_NOISE_THRESHOLD_DIST = 3, MAEXP_NOISE_FLAT = 4 };
+/* environment (core/environments/__init__.py:37-71; shared_reward_environment.py:15-28) */
+enum { MAEXP_REWARD_DEFAULT = 0, MAEXP_REWARD_SHARED_MEAN = 1, MAEXP_REWARD_SHARED_MAX = 2 };
+
+typedef struct {
+    int32_t num_envs;            /* E environments resident on this GPU */
+    int32_t num_agents;          /* config.num_agents, N <= 16 */
+    int32_t type_objects;        /* config.type_objects, T <= 4 */
+    int32_t size_x, size_y;      /* map.SIZE_X / SIZE_Y (Y <= 32: grid rows are 32-bit) */
+    int32_t visible_range;       /* 5, 7 or 9 */
+    int32_t past_step;           /* transition views only */
+    int32_t agent_view, object_view, area_mask, noise, reward_mode;
+    int32_t max_episode_length;
+    int32_t num_objects;
+    int32_t keep_objects_num;
+    int32_t shuffle_init_xys;
+    int32_t shared_max_is_mean;  /* 1: reproduce the reference's "max" class, which takes the mean */
+    int32_t auto_reset;          /* 1: an env whose done[0] fired is reset by the NEXT step call */
+    int32_t num_destinations;    /* M canonical destination masks in maexp_tables.destination */
+    int32_t random_destinations; /* 1: three_rooms_map.py:42-55 (shuffle the M masks, choice per agent) */
+    uint32_t seed;
+    uint32_t first_global_env_id;/* envs are keyed globally so that shards reproduce a single-GPU run */
+    int32_t init_xys[MAEXP_MAX_AGENTS][2];   /* INDEX-space cells (abstract_map.py:44-53 applied by the host) */
+    int32_t task_mask[MAEXP_MAX_AGENTS];     /* -1 for agent_tasks "-1" (default_environment.py:201-202) */
+    int32_t task_order[MAEXP_MAX_AGENTS][MAEXP_MAX_TYPES]; /* digits of agent_tasks[i] in order, -1 terminated */
+    float flip_noise_range[MAEXP_MAX_RINGS]; /* fp32 0.5/(p-1), flip_observation_noise.py:28 */
+    float std_distribution[MAEXP_MAX_RINGS];
+    float noise_threshold[MAEXP_MAX_RINGS];  /* fp32(std*ratio), dist_observation_noise.py:60,66 */
+} maexp_env_cfg;
+
+/* Static per-map tables in the REFERENCE's layout, HOST pointers; packed to bit rows and
+ * uploaded once by maexp_env_create.  Replaces the numpy attributes of AbstractMap
+ * (core/maps/abstract_map.py:20-24,78) and generate_local_area_mask's return value
+ * (core/handlers/observations/masks/local_area_mask.py:50-97). */
+typedef struct {
+    const int8_t *wall;          /* [X,Y] */
+    const int8_t *objects_area;  /* [T,X,Y] */
+    const int8_t *noise_area;    /* [X,Y] */
+    const int8_t *destination;   /* [M,X,Y] */
+    const int8_t *los;           /* [X,Y,V,V] 1 visible, 0 hidden */
+} maexp_tables;
+
+/* Per-call outputs (device pointers, any may be NULL).  obs / obs_rel point at ONE slot of the
+ * device-resident replay ring: fp32 [E, N, slot_floats], slot_floats = maexp_env_slot_floats()
+ * (C*V*V rounded up to a multiple of 4 so that every agent slot is 16-byte aligned). */
+typedef struct {
+    float *obs;            /* state[view] of observation_handler.py:95-105 (noisy one for merged) */
+    float *obs_rel;        /* merged only: the "relative" key (merged_observtion_handler.py:41-47) */
+    float *rewards;        /* [E,N] fp32 (shared modes: fp32 of the float64 mean) */
+    uint8_t *dones;        /* [E,N] default_environment.py:233-237, evaluated per agent */
+    uint8_t *was_reset;    /* [E] 1: this call reset the env instead of stepping it */
+    int32_t *coordinates;  /* [E,N,12] local_area_mask.py:18-47 key order */
+    int8_t *positions;     /* [E,N,2] index-space positions after the call ("agents" key) */
+    int8_t *objects;       /* [E,N,T,X,Y] objects_matrix snapshot at agent i's observation time */
+    uint8_t *destination;  /* [E,N] selected destination mask per agent ("destination" key = table row) */
+} maexp_obs_out;
+
+typedef struct maexp_env maexp_env;
+
+/* generate_map + generate_world + generate_environment + generate_observation_handler
+ * (core/maps/__init__.py:25, core/worlds/__init__.py:19, core/environments/__init__.py:37,
+ * core/handlers/observations/__init__.py:21) for E batched environments. */
+int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tables, maexp_env **out);
+void maexp_env_destroy(maexp_env *env);
+int maexp_env_channels(const maexp_env *env);     /* ObservationHandler.get_channel, observation_handler.py:55-61 */
+int maexp_env_slot_floats(const maexp_env *env);
+
+/* DefaultEnvironment.reset (default_environment.py:64-116) for every env with env_mask[e] != 0
+ * (NULL: all).  noise_tape: optional fp32 [E,N,C*V*V] injected draws (NULL: on-chip Philox). */
+int maexp_env_reset(maexp_env *env, uint32_t tick, const uint8_t *env_mask, const float *noise_tape,
+                    const maexp_obs_out *out, void *stream);
+
+/* DefaultEnvironment.step(action_n, order) (default_environment.py:153-175) →
+ * AbstractWorld.step (core/worlds/abstract_world.py:39-78) → reward_ind / done_ind /
+ * observation_ind interleaved per agent → ObservationHandler.step.  Shared-reward subclasses:
+ * shared_reward_environment.py:15-28.
+ * actions int8 [E,N] in {0..4} (NULL: uniform random policy {0..3}, abstract_agent.py:31-34);
+ * order uint8 [E,N] permutation (NULL: Philox Fisher-Yates, abstract_trainer.py:66). */
+int maexp_env_step(maexp_env *env, uint32_t tick, const int8_t *actions, const uint8_t *order,
+                   const float *noise_tape, const maexp_obs_out *out, void *stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies actions in, steps, copies rewards /
+ * dones / was_reset out and synchronises.  Observations stay in the device ring slot `obs`. */
+int maexp_env_step_host(maexp_env *env, uint32_t tick, const int8_t *actions_host, float *obs_ring_slot,
+                        float *rewards_host, uint8_t *dones_host, uint8_t *was_reset_host, void *stream);
+
+/* State taps: map.agents_matrix / objects_matrix / destination_area_matrix and the env counters
+ * (default_environment.py:65-69) in the reference's dtypes.  Device pointers, may be NULL. */
+int maexp_env_get_state(maexp_env *env, int8_t *pos /*[E,N,2]*/, int8_t *objects /*[E,T,X,Y]*/,
+                        int32_t *counters /*[E,4] generated,completed,agents_collided,walls_collided*/,
+                        int32_t *steps /*[E]*/, int8_t *destination /*[E,N,X,Y]*/, void *stream);
+int maexp_env_set_state(maexp_env *env, const int8_t *pos /*[E,N,2]*/, const int8_t *objects /*[E,T,X,Y]*/,
+                        void *stream);
+/* number of env-steps (not resets) executed since creation, summed over envs; error flag of the
+ * bounded rejection sampler.  Synchronises the stream. */
+int maexp_env_stats(maexp_env *env, uint64_t *env_steps, uint64_t *resets, int32_t *error_flag, void *stream);
+
+const char *maexp_last_error(void);
+int maexp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,81 @@
+"""ctypes binding of libmaexp_b200.so (the C-ABI declared in include/maexp_b200.h).
+
+There is no CPU fallback: importing this module without the built CUDA library raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmaexp_b200.so")
+
+MAX_AGENTS, MAX_TYPES, MAX_RINGS = 16, 4, 4
+
+
+class MaexpError(RuntimeError):
+    pass
+
+
+class EnvCfg(C.Structure):
+    _fields_ = [
+        ("num_envs", C.c_int32), ("num_agents", C.c_int32), ("type_objects", C.c_int32),
+        ("size_x", C.c_int32), ("size_y", C.c_int32), ("visible_range", C.c_int32), ("past_step", C.c_int32),
+        ("agent_view", C.c_int32), ("object_view", C.c_int32), ("area_mask", C.c_int32), ("noise", C.c_int32),
+        ("reward_mode", C.c_int32), ("max_episode_length", C.c_int32), ("num_objects", C.c_int32),
+        ("keep_objects_num", C.c_int32), ("shuffle_init_xys", C.c_int32), ("shared_max_is_mean", C.c_int32),
+        ("auto_reset", C.c_int32), ("num_destinations", C.c_int32), ("random_destinations", C.c_int32),
+        ("seed", C.c_uint32), ("first_global_env_id", C.c_uint32),
+        ("init_xys", (C.c_int32 * 2) * MAX_AGENTS), ("task_mask", C.c_int32 * MAX_AGENTS),
+        ("task_order", (C.c_int32 * MAX_TYPES) * MAX_AGENTS),
+        ("flip_noise_range", C.c_float * MAX_RINGS), ("std_distribution", C.c_float * MAX_RINGS),
+        ("noise_threshold", C.c_float * MAX_RINGS),
+    ]
+
+
+class Tables(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("wall", "objects_area", "noise_area", "destination", "los")]
+
+
+class ObsOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates",
+                                           "positions", "objects", "destination")]
+
+
+# every symbol include/maexp_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "maexp_env_create": (C.c_int, [C.POINTER(EnvCfg), C.POINTER(Tables), C.POINTER(C.c_void_p)]),
+    "maexp_env_destroy": (None, [C.c_void_p]),
+    "maexp_env_channels": (C.c_int, [C.c_void_p]),
+    "maexp_env_slot_floats": (C.c_int, [C.c_void_p]),
+    "maexp_env_reset": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(ObsOut), C.c_void_p]),
+    "maexp_env_step": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ObsOut),
+                                 C.c_void_p]),
+    "maexp_env_step_host": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "maexp_env_get_state": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "maexp_env_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "maexp_env_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32),
+                                  C.c_void_p]),
+    "maexp_last_error": (C.c_char_p, []),
+    "maexp_version": (C.c_int, []),
+}
+
+_LIB = None
+
+
+def load():
+    """Load the CUDA library; raises MaexpError when it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise MaexpError(f"{LIB_PATH} is missing: run `python -m maexp_b200.build` (there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _LIB = lib
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise MaexpError(load().maexp_last_error().decode() or f"maexp error {rc}")

@@ -1,0 +1,170 @@
+"""Static gridworld maps (host side): walls, object areas, destination areas.
+
+Mirrors `generate_map` / `AbstractMap` of the reference (core/maps/__init__.py:25-61,
+core/maps/abstract_map.py:12-81).  The maps are pure data here: every map is a small
+declarative description (wall runs with gaps, area boxes) rasterised into the reference's
+int8 matrices, which the CUDA library then packs into bit rows (maexp_env_create).
+"""
+import numpy as np
+
+from ..utils.logging import initialize_logging
+
+logger = initialize_logging(__name__)
+
+
+class AbstractMap:
+    """Attribute-compatible with core/maps/abstract_map.py:12-81."""
+
+    #: (axis, line, cells) — wall cells on row/column `line`; axis "x": wall[cells, line], "y": wall[line, cells]
+    WALL_RUNS = ()
+    #: {type_objects: [(type, x0, x1, y0, y1), ...]} half-open boxes, negative = relative to SIZE
+    AREAS = {}
+    #: True: destination areas are redrawn at every reset from `destination_masks()`
+    RANDOM_DESTINATIONS = False
+
+    def __init__(self, config, size_x, size_y):
+        self.config = config
+        self.num_agents = config.num_agents
+        self.type_objects = config.type_objects
+        self.SIZE_X, self.SIZE_Y = int(size_x), int(size_y)
+        X, Y = self.SIZE_X, self.SIZE_Y
+        self.wall_matrix = np.zeros((X, Y), np.int8)
+        self.agents_matrix = np.zeros((self.num_agents, X, Y), np.int8)
+        self.objects_matrix = np.zeros((self.type_objects, X, Y), np.int8)
+        self.objects_area_matrix = np.zeros((self.type_objects, X, Y), np.int8)
+        self.destination_area_matrix = np.ones((self.num_agents, X, Y), np.int8)
+        self.locate_walls()
+        self.set_objects_area()
+        self.set_noise_area()
+
+    # ---- coordinate transforms, abstract_map.py:44-64
+    def coord2ind(self, position, size_x=None, size_y=None):
+        sx, sy = size_x or self.SIZE_X, size_y or self.SIZE_Y
+        return np.array([sx // 2 + position[0], sy // 2 - position[1]], dtype=np.int8)
+
+    def ind2coord(self, position, size_x=None, size_y=None):
+        sx, sy = size_x or self.SIZE_X, size_y or self.SIZE_Y
+        return np.array([position[0] - sx // 2, sy // 2 - position[1]], dtype=np.int8)
+
+    # ---- rasterisation
+    def _border(self):
+        self.wall_matrix[[0, self.SIZE_X - 1], :] = 1
+        self.wall_matrix[:, [0, self.SIZE_Y - 1]] = 1
+
+    def locate_walls(self):
+        self._border()
+        for axis, line, cells in self.WALL_RUNS:
+            cells = np.asarray(list(cells))
+            if axis == "x":
+                self.wall_matrix[cells, line] = 1
+            else:
+                self.wall_matrix[line, cells] = 1
+
+    def set_objects_area(self):
+        X, Y = self.SIZE_X, self.SIZE_Y
+        for t, x0, x1, y0, y1 in self._areas().get(self.type_objects, ()):
+            x1 = x1 if x1 > 0 else X + x1
+            y1 = y1 if y1 > 0 else Y + y1
+            self.objects_area_matrix[t, x0:x1, y0:y1] = 1
+
+    def _areas(self):
+        return self.AREAS
+
+    def set_noise_area(self):
+        self.noise_area_matrix = np.ones((self.SIZE_X, self.SIZE_Y), np.int8)
+
+    def destination_masks(self):
+        """Canonical destination masks [M, X, Y]; default: one all-ones mask (abstract_map.py:80-81)."""
+        return np.ones((1, self.SIZE_X, self.SIZE_Y), np.int8)
+
+    # ---- mutable-grid API kept for interface compatibility (state lives on the GPU)
+    def reset(self):
+        self.reset_agents()
+        self.reset_objects()
+        self.reset_destination_area()
+
+    def reset_agents(self):
+        self.agents_matrix = np.zeros_like(self.agents_matrix)
+
+    def reset_objects(self):
+        self.objects_matrix = np.zeros_like(self.objects_matrix)
+
+    def reset_destination_area(self):
+        self.destination_area_matrix = np.ones_like(self.destination_area_matrix)
+
+    def step(self):
+        pass
+
+
+class SimpleMap(AbstractMap):
+    """core/maps/simple_map.py:10-21"""
+
+    def _areas(self):
+        h = self.SIZE_X // 2
+        return {1: [(0, 1, -1, 1, -1)], 2: [(0, 1, h, 1, -1), (1, h, -1, 1, -1)]}
+
+
+_FOUR_ROOMS_RUN = (1, 2, 3, 7, 8, 9, 10, 13, 14, 15, 16, 20, 21, 22)
+
+
+class FourRoomsMap(AbstractMap):
+    """core/maps/four_rooms_map.py:11-42"""
+    WALL_RUNS = (("x", 10, _FOUR_ROOMS_RUN), ("x", 13, _FOUR_ROOMS_RUN),
+                 ("y", 10, _FOUR_ROOMS_RUN), ("y", 13, _FOUR_ROOMS_RUN))
+    AREAS = {1: [(0, 1, 10, 1, 10), (0, 1, 10, 14, -1), (0, 14, -1, 1, 10), (0, 14, -1, 14, -1)],
+             2: [(0, 1, 10, 1, 10), (0, 1, 10, 14, -1), (1, 14, -1, 1, 10), (1, 14, -1, 14, -1)]}
+
+
+class ThreeRoomsMap(AbstractMap):
+    """core/maps/three_rooms_map.py:13-55"""
+    WALL_RUNS = (("x", 10, (1, 2, 3, 7, 8, 9, 10)), ("x", 14, (1, 2, 3, 7, 8, 9, 10)),
+                 ("y", 10, (1, 2, 3, 7, 8, 9, 10, 14, 15, 16, 17, 21, 22, 23)),
+                 ("y", 14, (1, 2, 3, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 21, 22, 23)))
+    AREAS = {1: [(0, 1, 10, 1, 10), (0, 1, 10, 15, 24), (0, 15, 24, 1, 24)],
+             2: [(0, 1, 10, 1, 10), (0, 15, 24, 1, 24), (1, 1, 10, 15, 24), (1, 15, 24, 1, 24)]}
+    RANDOM_DESTINATIONS = True
+
+    def destination_masks(self):
+        # three_rooms_map.py:43-51: two copies of each half-plane plus the full map, in this order
+        X, Y, h = self.SIZE_X, self.SIZE_Y, self.SIZE_X // 2
+        m = np.ones((9, X, Y), np.int8)
+        m[0:2, :h, :] = 0
+        m[2:4, h:, :] = 0
+        m[4:6, :, :h] = 0
+        m[6:8, :, h:] = 0
+        return m
+
+
+class FourRectangleMap(AbstractMap):
+    """core/maps/four_rectangle.py:11-39"""
+    AREAS = {1: [(0, 1, 19, 1, 10), (0, 1, 19, 14, -1), (0, 21, -1, 1, 10), (0, 21, -1, 14, -1)],
+             2: [(0, 1, 19, 1, 10), (0, 1, 19, 14, -1), (1, 21, -1, 1, 10), (1, 21, -1, 14, -1)]}
+
+    def locate_walls(self):
+        self._border()
+        w = self.wall_matrix
+        w[[19, 20], :] = 1
+        w[19:21, 11:13] = 0
+        w[:, [10, 13]] = 1
+        for lo, hi in ((8, 12), (28, 32)):
+            w[lo:hi, 10] = 0
+            w[lo:hi, 13] = 0
+
+
+_REGISTRY = {
+    # name -> (class, fixed size or None for config.map.SIZE_X/SIZE_Y)  core/maps/__init__.py:26-39
+    "simple": (SimpleMap, None),
+    "four_rooms": (FourRoomsMap, (24, 24)),
+    "three_rooms": (ThreeRoomsMap, (25, 25)),
+    "four_rectangle": (FourRectangleMap, (40, 24)),
+}
+
+
+def generate_map(config):
+    name = config.map.name
+    if name not in _REGISTRY:
+        logger.warning(f"Unexpected map is given. config.map.name: {name}")
+        raise ValueError()
+    cls, size = _REGISTRY[name]
+    size_x, size_y = size if size else (config.map.SIZE_X, config.map.SIZE_Y)
+    return cls(config=config, size_x=size_x, size_y=size_y)

@@ -1,0 +1,174 @@
+"""Parity of the CUDA step + observation path (through the C-ABI) — bit-exact.
+
+1. against tests/golden/*.npz, i.e. the live reference's own outputs (E=1, injected draws);
+2. against the C oracle on batches of environments with on-chip Philox draws and auto-reset;
+3. at BASELINE.json's full size (65 536 envs x 8 agents) through size-independent invariants
+   plus an oracle check of a strided sample of environments.
+"""
+import numpy as np
+import pytest
+import torch
+
+from maexp_b200.config import Config, baseline_config, make_config
+from oracle.cases import cases
+from oracle.oracle import Oracle
+from tests import replay as rp
+from tests.cuda_backend import CudaBackend
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", rp.fixture_names())
+def test_cuda_replays_reference_fixture(name):
+    fix = rp.load(name)
+    b = CudaBackend(fix["config"], 1, first_global_env_id=fix["env_id"], **fix["oracle_kwargs"])
+    assert rp.replay(fix, b) == len(fix["ticks"])
+
+
+def _compare(a, b, keys, what):
+    for k in keys:
+        if a.get(k) is None:
+            continue
+        if not np.array_equal(a[k], b[k]):
+            idx = np.argwhere(a[k] != b[k])[0]
+            raise AssertionError(f"{what}: {k} differs at {idx.tolist()}: cuda {a[k][tuple(idx)]} oracle {b[k][tuple(idx)]}")
+
+
+BATCH_CASES = ["cfg1_simple_mlp", "cfg2_four_rooms_transition_flip_sharedmean", "cfg3_three_rooms",
+               "cfg4_four_rectangle_merged_types", "cfg5_four_rooms_n8", "indtrans_t2_v9_tasks",
+               "no_keep_small", "relative_transparent", "simple_views_v5"]
+
+
+@pytest.mark.parametrize("name", BATCH_CASES)
+@pytest.mark.parametrize("num_envs", [37, 300])
+def test_cuda_batch_matches_oracle(name, num_envs):
+    """Ragged batch sizes (not a multiple of the envs-per-warp / per-CTA tiling), Philox policy,
+    auto-reset across an episode boundary."""
+    cfg, _, _, okw = cases()[name]
+    cfg = cfg.merged_with(max_episode_length=12)
+    gid0 = 1000
+    cuda = CudaBackend(cfg, num_envs, first_global_env_id=gid0, auto_reset=True, extras=True, **okw)
+    orc = Oracle(cfg, num_envs, auto_reset=True, first_global_env_id=gid0, extras=True, **okw)
+    keys = ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates", "objects", "destination")
+    _compare(cuda.reset(0), orc.reset(0), keys, f"{name} reset")
+    for tick in range(1, 30):
+        a, b = cuda.step(tick), orc.step(tick, threads=4)
+        _compare(a, b, keys, f"{name} tick {tick}")
+        sa, sb = cuda.state(), orc.state()
+        _compare(sa, sb, ("pos", "objects", "counters", "steps", "destination"), f"{name} state tick {tick}")
+    st = cuda.env.stats()
+    assert st["error_flag"] == 0 and st["resets"] >= num_envs * 2  # initial reset + one auto-reset each
+
+
+def test_masked_reset_and_injected_actions():
+    cfg = baseline_config(5)
+    E = 64
+    cuda = CudaBackend(cfg, E, first_global_env_id=5, extras=True)
+    orc = Oracle(cfg, E, first_global_env_id=5, extras=True)
+    rng = np.random.default_rng(1)
+    keys = ("obs", "rewards", "dones", "objects")
+    _compare(cuda.reset(0), orc.reset(0), keys, "reset")
+    for tick in range(1, 20):
+        actions = rng.integers(0, 5, size=(E, 8)).astype(np.int8)
+        order = np.stack([rng.permutation(8) for _ in range(E)]).astype(np.uint8)
+        _compare(cuda.step(tick, actions, order), orc.step(tick, actions, order), keys, f"tick {tick}")
+        if tick % 7 == 0:
+            mask = (rng.random(E) < 0.3).astype(np.uint8)
+            a, b = cuda.reset(1000 + tick, env_mask=mask), orc.reset(1000 + tick, env_mask=mask)
+            sel = mask.astype(bool)
+            for k in keys:
+                assert np.array_equal(a[k][sel], b[k][sel]), (tick, k)
+            _compare(cuda.state(), orc.state(), ("pos", "objects", "counters", "steps"), f"masked reset {tick}")
+
+
+def test_full_size_invariants_and_sampled_oracle():
+    """BASELINE.json config 5 at full size: 65 536 envs x 8 agents on four_rooms."""
+    cfg = baseline_config(5)
+    E, N = 65536, 8
+    cuda = CudaBackend(cfg, E, first_global_env_id=0, auto_reset=True, extras=False)
+    env = cuda.env
+    wall = torch.as_tensor(env.map.wall_matrix.astype(np.int64), device=env.device)
+    out = cuda.out
+    env.reset(out, tick=0)
+    T = 12
+    for tick in range(1, T + 1):
+        env.step(out, tick=tick)
+        st = env.state()
+        pos = st["pos"].long()
+        # agents never stand on walls and never overlap (abstract_world.py:56-70)
+        assert int(wall[pos[..., 0], pos[..., 1]].sum()) == 0
+        key = pos[..., 0] * 64 + pos[..., 1]
+        assert int((key.sort(dim=1).values.diff(dim=1) == 0).sum()) == 0
+        # keep_objects_num: object count conserved (default_environment.py:214-215)
+        assert torch.equal(st["objects"].sum(dim=(1, 2, 3)), torch.full((E,), 25, device=env.device))
+        # objects never sit on walls, agents or outside their area; generated = 25 + completed
+        assert int((st["objects"][:, 0].long() * wall).sum()) == 0
+        assert torch.equal(st["counters"][:, 0], 25 + st["counters"][:, 1])
+        obs = env.view(out["obs"])
+        # area channel in {-1, 0}; centre cell: visible and occupied by the agent itself
+        assert bool(((obs[:, :, 2] == 0) | (obs[:, :, 2] == -1)).all())
+        assert bool((obs[:, :, 0, 3, 3] == 1).all()) and bool((obs[:, :, 2, 3, 3] == 0).all())
+        # hidden cells carry no agents / objects (default views multiply by the mask)
+        hidden = obs[:, :, 2] == -1
+        assert float(obs[:, :, 0][hidden].abs().sum()) == 0 and float(obs[:, :, 1][hidden].abs().sum()) == 0
+        # rewards in {-1, 0, 1}
+        r = out["rewards"]
+        assert bool(((r == 0) | (r == 1) | (r == -1)).all())
+    assert env.stats()["env_steps"] == E * T
+    # strided sample of envs re-run on the oracle (Philox keys are per global env id)
+    sample = np.arange(0, E, 4099)
+    for gid in sample:
+        orc = Oracle(cfg, 1, auto_reset=True, first_global_env_id=int(gid))
+        orc.reset(0)
+        for tick in range(1, T + 1):
+            o = orc.step(tick)
+        assert np.array_equal(o["obs"][0], env.view(out["obs"])[gid].cpu().numpy()), gid
+        assert np.array_equal(o["rewards"][0], out["rewards"][gid].cpu().numpy())
+        assert np.array_equal(orc.state()["objects"][0], env.state()["objects"][gid].cpu().numpy())
+
+
+def test_sharded_envs_equal_single_gpu_run():
+    """Two shards with first_global_env_id offsets reproduce one big batch."""
+    cfg = baseline_config(5)
+    whole = CudaBackend(cfg, 96, first_global_env_id=0, auto_reset=True, extras=False)
+    lo = CudaBackend(cfg, 48, first_global_env_id=0, auto_reset=True, extras=False)
+    hi = CudaBackend(cfg, 48, first_global_env_id=48, auto_reset=True, extras=False)
+    for b in (whole, lo, hi):
+        b.reset(0)
+    for tick in range(1, 10):
+        w, a, b = whole.step(tick), lo.step(tick), hi.step(tick)
+    assert np.array_equal(w["obs"], np.concatenate([a["obs"], b["obs"]]))
+    assert np.array_equal(w["rewards"], np.concatenate([a["rewards"], b["rewards"]]))
+
+
+def test_host_buffer_entry_point():
+    cfg = baseline_config(5)
+    E, N = 256, 8
+    b = CudaBackend(cfg, E, first_global_env_id=0, auto_reset=True, extras=False)
+    orc = Oracle(cfg, E, auto_reset=True, first_global_env_id=0)
+    b.reset(0), orc.reset(0)
+    rng = np.random.default_rng(3)
+    actions = torch.empty((E, N), dtype=torch.int8).pin_memory()
+    rewards = torch.empty((E, N), dtype=torch.float32).pin_memory()
+    dones = torch.empty((E, N), dtype=torch.uint8).pin_memory()
+    was_reset = torch.empty((E,), dtype=torch.uint8).pin_memory()
+    slot = b.env.new_slot()
+    for tick in range(1, 6):
+        a = rng.integers(0, 4, size=(E, N)).astype(np.int8)
+        actions.copy_(torch.from_numpy(a))
+        b.env.step_host(actions, slot, rewards, dones, was_reset, tick=tick)
+        # order is drawn on chip (Philox) in the host entry point
+        o = orc.step(tick, actions=a)
+        assert np.array_equal(rewards.numpy(), o["rewards"]) and np.array_equal(dones.numpy(), o["dones"])
+        assert np.array_equal(b.env.view(slot).cpu().numpy(), o["obs"])
+
+
+def test_unsupported_configs_fail_loudly():
+    from tests.cuda_backend import make_env
+    with pytest.raises(ValueError):
+        make_env(make_config(agent_view_method="self"), 1)
+    with pytest.raises(ValueError):
+        make_env(make_config(observation_noise="flip", visible_range=9), 1)  # needs 4 probabilities (§E-6)
+    with pytest.raises(ValueError):
+        make_env(make_config(map=dict(name="four_rooms", SIZE_X=24, SIZE_Y=24), type_objects=3,
+                             agent_tasks=["0"] * 8), 1)  # empty objects_area: reference spins forever (§E-8)
