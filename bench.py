@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Benchmark of the MAEXP hot path on B200: batched gridworld step + egocentric observation.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one `maexp_env_step` over the whole per-GPU batch (BASELINE.json configs[4]:
+four_rooms, 65 536 envs x 8 agents, V=7, C=3, random policy, auto-reset), observations written
+as fp32 into a rotating device-resident replay-ring slot.  Prints ONE JSON line (rank 0).
+
+`--impl reference` times the CPU implementation of the same path on the host cores.  The
+reference is pure Python and cannot travel to the GPU box, so this arm runs the C oracle port
+(oracle/maexp_oracle.c, pinned bit-exactly against the live reference in the build container)
+with all host threads — a much stronger baseline than the reference's own ~5.7 k agent-steps/s
+per core.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 65536
+RING_SLOTS = 8
+B_ALG = 744.0  # algorithmic bytes per agent-step for cfg5 (588 obs + 144 grid r/w + 12)
+METRIC, UNIT = "agent_steps_per_sec", "agent-steps/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of env_step_kernel<7,16,0> at this
+# workload, from profiles/ (ncu --set full); None until captured
+NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+
+
+def workload_config():
+    from maexp_b200.config import baseline_config
+    return baseline_config(5)
+
+
+def config_block(n_envs, extra=None):
+    c = {"workload": "BASELINE configs[4]: four_rooms 24x24, %d envs/GPU x 8 agents, V=7, C=3 (default views), "
+                     "25 objects kept, L=200 auto-reset, uniform random policy + move order from on-chip Philox"
+                     % n_envs,
+         "envs_per_gpu": n_envs, "agents": 8, "map": "four_rooms", "visible_range": 7, "channels": 3,
+         "ring_slots": RING_SLOTS,
+         "l2": "each step streams a fresh ring slot (310 MB at 65536 envs) > 126 MB L2; slots rotate"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the GPU phases run."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt, self.window = index, [], threading.Event(), [None, None]
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        nv = self.nv
+        t0, t1 = self.window
+        inside = [s for s in self.samples if t0 is not None and t0 <= s[0] <= t1] or self.samples[-3:]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        seen = sorted({n for _, _, r in inside for n, bit in names.items() if r & bit})
+        return {"sm_mhz": statistics.median(m for _, m, _ in inside), "sm_max_mhz": self.max_mhz, "reasons": seen,
+                "samples": len(inside)}
+
+
+def cpu_oracle_rate(n_envs, steps, warmup, threads):
+    """agent-steps/s of the C oracle port on the host cores (random policy, auto-reset)."""
+    from oracle.oracle import Oracle
+    cfg = workload_config()
+    o = Oracle(cfg, n_envs, auto_reset=True)
+    o.reset(0)
+    tick = 1
+    for _ in range(warmup):
+        o.step_nocopy(tick, threads=threads)
+        tick += 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step_nocopy(tick, threads=threads)
+        tick += 1
+    dt = time.perf_counter() - t0
+    return n_envs * 8 * steps / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_envs = 8192
+    steps = max(1, min(args.steps, 400))
+    rate, dt = cpu_oracle_rate(n_envs, steps, max(3, min(args.warmup, 10)), threads)
+    sample = "%d of the %d envs, %d steps, %.1f s" % (n_envs, ENVS_PER_GPU, steps, dt)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": config_block(ENVS_PER_GPU, {"reference_step": "bounded sample: %d envs per step" % n_envs}),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+
+    from maexp_b200.core.environments.batched import BatchedEnvironment
+    from maexp_b200.core.maps import generate_map
+    from maexp_b200.core.worlds import generate_world
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    E, N, K, W = args.envs, 8, args.steps, args.warmup
+    cfg = workload_config()
+    world_obj = generate_world(cfg, generate_map(cfg))
+    # envs are independent units: contiguous global ids per rank, no data-path collective
+    env = BatchedEnvironment(cfg, world_obj, E, device=dev, auto_reset=True, first_global_env_id=rank * E)
+    ring = torch.empty((RING_SLOTS, E, N, env.slot_floats), dtype=torch.float32, device=dev)
+    out = env.new_outputs()
+    outs = []
+    for s in range(RING_SLOTS):
+        o = dict(out)
+        o["obs"] = ring[s]
+        outs.append(o)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    tick = 0
+    env.reset(outs[0], tick=tick)
+    tick += 1
+    sampler.window[0] = time.perf_counter()
+    for _ in range(W):
+        env.step(outs[tick % RING_SLOTS], tick=tick)
+        tick += 1
+    before = env.stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        env.step(outs[tick % RING_SLOTS], tick=tick)
+        tick += 1
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    after = env.stats()
+    env_steps = after["env_steps"] - before["env_steps"]  # resets (1 in L+1 calls per env) are not counted
+
+    # ---- end to end through the host-buffer C-ABI entry point: pinned actions in, rewards/dones out
+    actions = torch.randint(0, 4, (E, N), dtype=torch.int8).pin_memory()
+    rewards = torch.empty((E, N), dtype=torch.float32).pin_memory()
+    dones = torch.empty((E, N), dtype=torch.uint8).pin_memory()
+    was_reset = torch.empty((E,), dtype=torch.uint8).pin_memory()
+    for _ in range(3):
+        env.step_host(actions, ring[tick % RING_SLOTS], rewards, dones, was_reset, tick=tick)
+        tick += 1
+    k2 = max(1, min(K, 200))
+    b2 = env.stats()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k2):
+        env.step_host(actions, ring[tick % RING_SLOTS], rewards, dones, was_reset, tick=tick)
+        tick += 1
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.window[1] = time.perf_counter()
+    e2e_steps = env.stats()["env_steps"] - b2["env_steps"]
+    sampler.stop()
+
+    vals = torch.tensor([ms, float(env_steps), e2e_s, float(e2e_steps)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        mx = vals.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_s = float(mx[0]), float(mx[2])
+        env_steps, e2e_steps = float(sm[1]), float(sm[3])
+    if rank == 0:
+        value = env_steps * N / (ms * 1e-3)
+        e2e = e2e_steps * N / e2e_s
+        peak, peak_src = peaks()
+        # dominant (only) kernel of the step: env_step_kernel; K launches back to back in the timed region
+        launch_s = ms * 1e-3 / K
+        per_launch_agent_steps = env_steps * N / K / world
+        achieved = B_ALG * per_launch_agent_steps / launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic", "config": config_block(E),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * N, "d2h_bytes_per_step": E * N * 5 + E,
+                    "steps": k2, "note": "maexp_env_step_host: pinned actions H2D, rewards+dones+was_reset D2H every "
+                                         "step, stream sync per step; observations stay in the device replay ring"},
+            "gpu_launches": K,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
+                         "kernel": "env_step_kernel", "algorithmic_bytes_per_agent_step": B_ALG,
+                         "launch_us": launch_s * 1e6},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_cpu, k_cpu = 8192, 150
+            rate, dt = cpu_oracle_rate(n_cpu, k_cpu, 3, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d of the %d envs, %d steps, %.1f s (C oracle port, pthreads)"
+                                              % (n_cpu, E, k_cpu, dt)}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: the BASELINE workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,12 +31,16 @@ def _deps():
 def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in _deps()):
         return LIB
-    objs = []
-    for src in sources():
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(CSRC, os.path.basename(src)[:-3] + ".o")
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         subprocess.check_call(cmd)
-        objs.append(obj)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
+        objs = list(pool.map(compile_one, sources()))
     subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"])
     return LIB
 
