@@ -39,7 +39,7 @@ typedef struct {
     int32_t num_envs;            /* E environments resident on this GPU */
     int32_t num_agents;          /* config.num_agents, N <= 16 */
     int32_t type_objects;        /* config.type_objects, T <= 4 */
-    int32_t size_x, size_y;      /* map.SIZE_X / SIZE_Y (Y <= 32: grid rows are 32-bit) */
+    int32_t size_x, size_y;      /* map.SIZE_X / SIZE_Y (Y + V/2 <= 32: grid rows are 32-bit) */
     int32_t visible_range;       /* 5, 7 or 9 */
     int32_t past_step;           /* transition views only */
     int32_t agent_view, object_view, area_mask, noise, reward_mode;
@@ -75,7 +75,7 @@ typedef struct {
 
 /* Per-call outputs (device pointers, any may be NULL).  obs / obs_rel point at ONE slot of the
  * device-resident replay ring: fp32 [E, N, slot_floats], slot_floats = maexp_env_slot_floats()
- * (C*V*V rounded up to a multiple of 4 so that every agent slot is 16-byte aligned). */
+ * (C*V*V rounded up to a multiple of 8 so that every agent slot starts on a 32-byte sector). */
 typedef struct {
     float *obs;            /* state[view] of observation_handler.py:95-105 (noisy one for merged) */
     float *obs_rel;        /* merged only: the "relative" key (merged_observtion_handler.py:41-47) */

@@ -109,6 +109,10 @@ struct maexp_env {
     EnvParams p;
     int V, epw;
     size_t smem_bytes;
+    int grid_ctas = 0;
+    KernelFn fn = nullptr;
+    int *work_counters = nullptr;  // ring of zeroed queue heads, one consumed per launch
+    unsigned launch_seq = 0;
     std::vector<void *> allocs;
     // pinned-free staging for the host-buffer entry point
     int8_t *d_actions = nullptr;
@@ -167,12 +171,11 @@ int launch(maexp_env *h, uint32_t tick, int force_reset, const uint8_t *env_mask
     p.noise_tape = noise_tape;
     if (out) p.out = *out;
     else memset(&p.out, 0, sizeof(p.out));
-    KernelFn fn = pick_kernel(h->V, h->epw, p.noise);
-    if (!fn) return fail("maexp: no kernel for this visible_range / noise");
-    const int envs_per_cta = h->epw * kWarpsPerCta;
-    const int grid = (p.E + envs_per_cta - 1) / envs_per_cta;
-    MAEXP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    fn<<<grid, kWarpsPerCta * 32, h->smem_bytes, stream>>>(p);
+    // work queue head for this launch; the slot half a ring away is re-zeroed for a later launch
+    const unsigned slot = h->launch_seq++ & 63u;
+    p.work_counter = h->work_counters + slot;
+    MAEXP_CUDA(cudaMemsetAsync(h->work_counters + ((slot + 32u) & 63u), 0, sizeof(int), stream));
+    h->fn<<<h->grid_ctas, kWarpsPerCta * 32, h->smem_bytes, stream>>>(p);
     MAEXP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -191,7 +194,8 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     if (E < 1) return fail("maexp_env_create: num_envs < 1");
     if (N < 1 || N > MAEXP_MAX_AGENTS) return fail("maexp_env_create: num_agents must be in 1..16");
     if (T < 1 || T > MAEXP_MAX_TYPES) return fail("maexp_env_create: type_objects must be in 1..4");
-    if (X < 3 || X > 255 || Y < 3 || Y > 32) return fail("maexp_env_create: map must satisfy 3<=X<=255, 3<=Y<=32");
+    if (X < 3 || X > 255 || Y < 3 || Y + cfg->visible_range / 2 > 32)
+        return fail("maexp_env_create: map must satisfy 3<=X<=255, 3<=Y and Y + visible_range/2 <= 32 (32-bit grid rows)");
     if (V != 5 && V != 7 && V != 9) return fail("maexp_env_create: visible_range must be 5, 7 or 9");
     if (M < 1 || M > 15) return fail("maexp_env_create: num_destinations must be in 1..15");
     if (!tb->wall || !tb->objects_area || !tb->noise_area || !tb->destination || !tb->los)
@@ -224,13 +228,18 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
         delete h;
         return fail("maexp_env_create: observation noise is undefined for observation_area_mask=relative (SURVEY.md appendix C)");
     }
-    p.slot_floats = (p.K + 3) & ~3;
+    int slot_align = 8;  // floats: agent slots start on 32-byte DRAM sectors (measured: 104 -> 90 us per step vs 16-byte alignment)
+    if (const char *a = getenv("MAEXP_SLOT_ALIGN")) { const int v = atoi(a); if (v == 4 || v == 8 || v == 16 || v == 32) slot_align = v; }
+    p.slot_floats = (p.K + slot_align - 1) / slot_align * slot_align;
     p.qps = p.slot_floats / 4;
     p.qps_magic = (uint32_t)((0x100000000ull + p.qps - 1) / p.qps);
     p.wpa = (p.K + 31) / 32;
-    p.ws = (p.wpa + 3) | 1;
-    p.gs = (T * X) | 1;
-    p.as = X | 1;
+    p.ws = (p.wpa + 4) | 1;
+    p.gs = (T * (X + 2 * (V / 2))) | 1;
+    p.tx_magic = (uint32_t)((0x100000000ull + (uint64_t)(T * X) - 1) / (uint64_t)(T * X));
+    p.as = (X + 2 * (V / 2)) | 1;
+    p.fast3 = (V <= 7) && (cfg->agent_view == MAEXP_AV_DEFAULT || cfg->agent_view == MAEXP_AV_SIMPLE) &&
+              (cfg->object_view == MAEXP_OV_DEFAULT || cfg->object_view == MAEXP_OV_SIMPLE);
     p.area_bit0 = (p.C - 1) * V * V;
     p.q_str = p.area_bit0 >> 2;
     p.q_tail = (p.K - 1) >> 2;
@@ -292,6 +301,7 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     rc |= dev_alloc(h, &p.past, (size_t)E * (p.P ? p.P : 1) * N);
     rc |= dev_alloc(h, &p.stats, 2);
     rc |= dev_alloc(h, &p.error_flag, 1);
+    rc |= dev_alloc(h, &h->work_counters, 64);
     rc |= dev_alloc(h, &h->d_actions, (size_t)E * N);
     rc |= dev_alloc(h, &h->d_rewards, (size_t)E * N);
     rc |= dev_alloc(h, &h->d_dones, (size_t)E * N);
@@ -302,8 +312,9 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    h->epw = 32;
-    while (h->epw > 8 && (E + h->epw - 1) / h->epw < sms * 24) h->epw >>= 1;
+    // envs per warp (one lane per env in the sequential phase).  Measured on B200 at E = 65536:
+    // 8 -> 119 us, 16 -> 89 us, 32 -> 93 us per step; small batches prefer more, shorter groups.
+    h->epw = (E >= 16 * sms * 8) ? 16 : 8;
     if (const char *force = getenv("MAEXP_EPW")) {
         const int v = atoi(force);
         if (v == 8 || v == 16 || v == 32) h->epw = v;
@@ -314,6 +325,20 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
         h->smem_bytes = env_smem_bytes(p, V, h->epw);
     }
     if (h->smem_bytes > 227 * 1024) { maexp_env_destroy(h); return fail("maexp_env_create: configuration needs more than 227 KB shared memory per CTA"); }
+    for (int i = 0; i < 32 * T * X; ++i)
+        if ((int)(((uint64_t)i * p.tx_magic) >> 32) != i / (T * X)) { maexp_env_destroy(h); return fail("maexp_env_create: internal magic division (TX)"); }
+    h->fn = pick_kernel(V, h->epw, p.noise);
+    if (!h->fn) { maexp_env_destroy(h); return fail("maexp_env_create: no kernel for this visible_range / noise"); }
+    if (cudaFuncSetAttribute(h->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess) {
+        maexp_env_destroy(h);
+        return fail("maexp_env_create: cannot reserve shared memory");
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->fn, kWarpsPerCta * 32, h->smem_bytes);
+    if (per_sm < 1) per_sm = 1;
+    const int groups = (E + h->epw - 1) / h->epw;
+    h->grid_ctas = per_sm * sms;  // persistent: exactly one resident wave
+    if (h->grid_ctas > (groups + kWarpsPerCta - 1) / kWarpsPerCta) h->grid_ctas = (groups + kWarpsPerCta - 1) / kWarpsPerCta;
     init_state_kernel<<<(E + 127) / 128, 128>>>(p);
     if (cudaDeviceSynchronize() != cudaSuccess) { maexp_env_destroy(h); return fail("maexp_env_create: init kernel failed"); }
     *out = h;

@@ -18,6 +18,7 @@ struct EnvParams {
     int q_str, q_tail, sub_str, sub_tail;  // phase-B quad classes (area channel offset, tail padding)
     uint32_t qps_magic;
     int agent_view, object_view, merged, noise, reward_mode, shared_max_is_mean;
+    int fast3;  // 3 channels (total agents, all objects, area) and V <= 7: compile-time bit assembly
     int L, num_objects, keep, shuffle_init, auto_reset, random_dest;
     uint32_t seed, gid0, tick;
     int force_reset;
@@ -35,6 +36,8 @@ struct EnvParams {
     uint8_t *dest_sel;
     uint16_t *past;
     unsigned long long *stats;  // [0] env-steps, [1] resets
+    int *work_counter;          // persistent-CTA work queue (groups of EPW envs), zeroed per launch
+    uint32_t tx_magic;          // ceil(2^32 / (T*X))
     int32_t *error_flag;
     // io
     const int8_t *actions;
@@ -47,6 +50,20 @@ struct EnvParams {
     int8_t no_task[MAEXP_MAX_AGENTS];
     float flip_range[MAEXP_MAX_RINGS], std_dist[MAEXP_MAX_RINGS], noise_thr[MAEXP_MAX_RINGS];
 };
+
+#ifndef MAEXP_ST
+#define MAEXP_ST 0
+#endif
+__device__ __forceinline__ void store_quad(float4 *ptr, const float4 &v) {
+#if MAEXP_ST == 0
+    __stcs(ptr, v);   // st.global.cs: streaming, evict-first
+#elif MAEXP_ST == 1
+    *ptr = v;         // default write-back policy
+#else
+    __stcg(ptr, v);   // st.global.cg: cache in L2 only
+#endif
+}
+#define MAEXP_STORE 1
 
 template <int V>
 struct Win {  // V*V-bit window mask, bit a*V+b  (a: x offset, b: y offset)
@@ -80,31 +97,44 @@ __device__ __forceinline__ uint64_t fisher_yates(uint64_t v, int n, uint32_t see
     return v;
 }
 
+// Appends V*V-bit channel masks to a bit stream in output order.  Pending bits live in a
+// register accumulator; completed 32-bit words are written once (no shared-memory RMW chain).
 template <int V>
-__device__ __forceinline__ void put_bits(uint32_t *w, int bit0, typename Win<V>::T m) {
-    const int i = bit0 >> 5, s = bit0 & 31;
-    if constexpr (V == 9) {
-        const unsigned __int128 v = m << s;  // 81 + 31 bits
-        w[i] |= (uint32_t)v;
-        w[i + 1] |= (uint32_t)(v >> 32);
-        w[i + 2] |= (uint32_t)(v >> 64);
-        w[i + 3] |= (uint32_t)(v >> 96);
-    } else {
-        w[i] |= (uint32_t)(m << s);
-        const uint64_t r = (m >> (31 - s)) >> 1;  // m >> (32 - s) without a 32-bit-wide shift
-        w[i + 1] |= (uint32_t)r;
-        w[i + 2] |= (uint32_t)(r >> 32);
+struct BitStream {
+    unsigned __int128 acc = 0;
+    int nbits = 0;
+    uint32_t *out;
+    __device__ __forceinline__ explicit BitStream(uint32_t *o) : out(o) {}
+    __device__ __forceinline__ void put(typename Win<V>::T m) {
+        acc |= (unsigned __int128)m << nbits;  // nbits < 32, V*V <= 81
+        nbits += V * V;
+        while (nbits >= 32) {
+            *out++ = (uint32_t)acc;
+            acc >>= 32;
+            nbits -= 32;
+        }
     }
-}
+    __device__ __forceinline__ void finish() {  // flush the tail and one zero word of slack
+        *out++ = (uint32_t)acc;
+        out[0] = 0u;
+        out[1] = 0u;
+    }
+};
 
 template <int V, int EPW, int NOISE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 : 6) env_step_kernel(const EnvParams p) {
+#ifndef MAEXP_MINB
+#define MAEXP_MINB 8
+#endif
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 : MAEXP_MINB) env_step_kernel(const EnvParams p) {
     constexpr int R = V / 2, VV = V * V;
     constexpr int LW = (V == 9) ? 2 : 1;
     using WinT = typename Win<V>::T;
     extern __shared__ __align__(16) uint32_t smem[];
 
     const int N = p.N, T = p.T, X = p.X, Y = p.Y, P = p.P, TX = T * X;
+    // Shared-memory bit rows are padded: R zero rows on both sides of x and every row shifted left by
+    // R bits, so window crops need no bounds checks and no signed shifts.
+    const int XP = X + 2 * R;
     // ---- shared memory carve-up (must match env_smem_bytes) ----
     float4 *s_lut = reinterpret_cast<float4 *>(smem);  // [4 classes][16 nibbles] → 4 fp32 values
     uint64_t *s_los = reinterpret_cast<uint64_t *>(smem + 256);
@@ -132,30 +162,42 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     }
     for (int i = threadIdx.x; i < X * Y * LW; i += blockDim.x) s_los[i] = p.los[i];
     for (int i = threadIdx.x; i < X; i += blockDim.x) {
-        s_wall[i] = p.wall[i];
-        s_noise[i] = p.noise_area[i];
+        s_wall[i] = p.wall[i] << R;
+        s_noise[i] = p.noise_area[i] << R;
     }
-    for (int i = threadIdx.x; i < TX; i += blockDim.x) s_area[i] = p.area[i];
-    for (int i = threadIdx.x; i < p.M * X; i += blockDim.x) s_dest[i] = p.dest[i];
+    for (int i = threadIdx.x; i < TX; i += blockDim.x) s_area[i] = p.area[i] << R;
+    for (int i = threadIdx.x; i < p.M * X; i += blockDim.x) s_dest[i] = p.dest[i] << R;
+    for (int i = threadIdx.x; i < kWarpsPerCta * per_warp_words; i += blockDim.x) s_warp0[i] = 0;  // zero padding
 
-    const int env0 = (blockIdx.x * kWarpsPerCta + warp) * EPW;
+    __syncthreads();
+
+    // Persistent CTAs: every warp pulls groups of EPW environments from a global queue, so the
+    // grid is sized to the machine (no partial last wave) and short groups keep warps busy.
+    const int num_groups = (p.E + EPW - 1) / EPW;
+    for (;;) {
+    int group = 0;
+    if (lane == 0) group = atomicAdd(p.work_counter, 1);
+    group = __shfl_sync(0xFFFFFFFFu, group, 0);
+    if (group >= num_groups) break;
+    const int env0 = group * EPW;
     const int nenv = min(EPW, p.E - env0);
-    if (nenv > 0) {  // coalesced stage-in of this warp's grids
+    {  // coalesced stage-in of this warp's grids (flat index, loads batched by the unroll)
         const uint32_t *src = p.obj + (size_t)env0 * TX;
+#pragma unroll 4
         for (int i = lane; i < nenv * TX; i += 32) {
-            const int e = i / TX, r = i - e * TX;
-            s_grid[e * p.gs + r] = src[i];
+            const int e = (int)__umulhi((uint32_t)i, p.tx_magic), r = i - e * TX;
+            const int t = (r >= X) + (r >= 2 * X) + (r >= 3 * X);
+            s_grid[e * p.gs + R + r + t * 2 * R] = src[i] << R;
         }
     }
-    __syncthreads();
-    if (nenv <= 0) return;
+    __syncwarp();
 
     // ---------------------------------------------------------------- phase A state (lane = env)
     const bool mine = lane < nenv;
     const int env = env0 + lane;
     const uint32_t gid = p.gid0 + (uint32_t)env;
-    uint32_t *grid = s_grid + lane * p.gs;
-    uint32_t *agrid = s_agrid + lane * p.as;
+    uint32_t *grid = s_grid + lane * p.gs + R;    // row (t, x) at grid[t * XP + x], x in [-R, X + R)
+    uint32_t *agrid = s_agrid + lane * p.as + R;  // row x at agrid[x]
     uint32_t *wv = s_w + lane * p.ws;
     uint16_t *mypos = s_pos + lane;  // agent k at mypos[k*EPW]
     int stepc = 0, nobj = 0;
@@ -166,7 +208,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     uint32_t attempt = 0;
     uint4 rw = make_uint4(0, 0, 0, 0);
 
-    auto agent_at = [&](int x, int y) { return (agrid[x] >> y) & 1u; };
+    auto agent_at = [&](int x, int y) { return (agrid[x] >> (y + R)) & 1u; };
     // default_environment.py:134-148, one accepted object; two uniforms per attempt
     auto spawn = [&](int t, uint32_t stream) {
         for (;;) {
@@ -178,12 +220,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             const uint32_t u1 = (attempt & 1u) ? rw.z : rw.x, u2 = (attempt & 1u) ? rw.w : rw.y;
             ++attempt;
             const int x = 1 + (int)scale(u1, (uint32_t)(X - 1)), y = 1 + (int)scale(u2, (uint32_t)(Y - 1));
-            const uint32_t bit = 1u << y;
+            const uint32_t bit = 1u << (y + R);
             bool ok = !(s_wall[x] & bit) && (s_area[t * X + x] & bit);
-            for (int t2 = 0; t2 < T; ++t2) ok = ok && !(grid[t2 * X + x] & bit);
+            for (int t2 = 0; t2 < T; ++t2) ok = ok && !(grid[t2 * XP + x] & bit);
             ok = ok && !agent_at(x, y);
             if (ok) {
-                grid[t * X + x] |= bit;
+                grid[t * XP + x] |= bit;
                 ++c_gen;
                 ++nobj;
                 return;
@@ -212,7 +254,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             // ------------------------------------------------ default_environment.py:64-116
             c_gen = c_done = c_ca = c_cw = 0;
             stepc = 0;
-            for (int r = 0; r < TX; ++r) grid[r] = 0;
+            for (int t = 0; t < T; ++t)
+                for (int x = 0; x < X; ++x) grid[t * XP + x] = 0;
             if (p.random_dest) {  // three_rooms_map.py:42-55
                 uint64_t perm = 0;
                 for (int k = 0; k < p.M; ++k) perm |= (uint64_t)k << (4 * k);
@@ -236,7 +279,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             }
             for (int k = 0; k < N; ++k) mypos[k * EPW] = p.init_xy[nib(perm, k)];
             for (int x = 0; x < X; ++x) agrid[x] = 0;
-            for (int k = 0; k < N; ++k) agrid[mypos[k * EPW] & 0xFF] |= 1u << (mypos[k * EPW] >> 8);
+            for (int k = 0; k < N; ++k) agrid[mypos[k * EPW] & 0xFF] |= 1u << ((mypos[k * EPW] >> 8) + R);
             attempt = 0;
             nobj = 0;
             for (int t = 0; t < T; ++t)
@@ -246,9 +289,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             attempt = 0;
         } else {
             // ------------------------------------------------ abstract_world.py:39-78
-            for (int r = 0; r < TX; ++r) nobj += __popc(grid[r]);
+            for (int t = 0; t < T; ++t)
+                for (int x = 0; x < X; ++x) nobj += __popc(grid[t * XP + x]);
             for (int x = 0; x < X; ++x) agrid[x] = 0;
-            for (int k = 0; k < N; ++k) agrid[mypos[k * EPW] & 0xFF] |= 1u << (mypos[k * EPW] >> 8);
+            for (int k = 0; k < N; ++k) agrid[mypos[k * EPW] & 0xFF] |= 1u << ((mypos[k * EPW] >> 8) + R);
             uint64_t acts = 0;  // 3 bits per agent
             if (p.actions) {
                 for (int k = 0; k < N; ++k) acts |= (uint64_t)(p.actions[(size_t)env * N + k] & 7) << (3 * k);
@@ -276,17 +320,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                 const int nx = (cur & 0xFF) + dx, ny = (cur >> 8) + dy;
                 bool move = true;
                 // another agent on the target cell (abstract_world.py:56-64; own cell excluded: only STAY hits it)
-                if ((dx | dy) != 0 && ((agrid[nx] >> ny) & 1u)) {
+                if ((dx | dy) != 0 && ((agrid[nx] >> (ny + R)) & 1u)) {
                     ca |= 1u << id;
                     move = false;
                 }
-                if (s_wall[nx] & (1u << ny)) {
+                if (s_wall[nx] & (1u << (ny + R))) {
                     cw |= 1u << id;
                     move = false;
                 }
                 if (move) {
-                    agrid[cur & 0xFF] &= ~(1u << (cur >> 8));
-                    agrid[nx] |= 1u << ny;
+                    agrid[cur & 0xFF] &= ~(1u << ((cur >> 8) + R));
+                    agrid[nx] |= 1u << (ny + R);
                     mypos[id * EPW] = (uint16_t)(nx | (ny << 8));
                 }
             }
@@ -304,12 +348,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                 // ---------------------------------------- default_environment.py:196-231
                 if (!p.no_task[i]) {
                     const int sel = p.random_dest ? (int)nib(dsel, i) : (i < p.M ? i : p.M - 1);
-                    const uint32_t bit = 1u << py;
+                    const uint32_t bit = 1u << (py + R);
                     for (int q = 0; q < MAEXP_MAX_TYPES && p.task_order[i][q] >= 0; ++q) {
                         const int t = p.task_order[i][q];
-                        if ((grid[t * X + px] & bit) && (s_dest[sel * X + px] & bit)) {
+                        if ((grid[t * XP + px] & bit) && (s_dest[sel * X + px] & bit)) {
                             rew_pos |= 1u << i;
-                            grid[t * X + px] &= ~bit;
+                            grid[t * XP + px] &= ~bit;
                             --nobj;
                             ++c_done;
                             if (p.keep) spawn(t, kStreamRespawn);
@@ -322,33 +366,47 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                 if (nobj == 0 || stepc == p.L - 1) done_bits |= 1u << i;
             }
             // -------------------------------------------- observation_handler.py:67-105, bits in output order
-            for (int w = 0; w < p.wpa + 3; ++w) wv[w] = 0;
             WinT los = s_los[(px * Y + py) * LW];
             if constexpr (V == 9) los |= (WinT)s_los[(px * Y + py) * LW + 1] << 64;
-            int ch = 0;
             auto win_bit = [&](uint16_t cell) -> WinT {  // cell → window bit or 0
                 const int a = (int)(cell & 0xFF) - px + R, b = (int)(cell >> 8) - py + R;
                 return (a >= 0 && a < V && b >= 0 && b < V) ? ((WinT)1 << (a * V + b)) : (WinT)0;
             };
-            const int av = p.agent_view;
-            if (av == MAEXP_AV_INDIVIDUAL || av == MAEXP_AV_INDIVIDUAL_TRANSITION)
-                for (int k = 0; k < N; ++k) put_bits<V>(wv, (ch++) * VV, win_bit(mypos[k * EPW]) & los);
-            auto row_window = [&](const uint32_t *rows) -> WinT {  // V x V crop of a bit-row grid around (px, py)
+            auto row_window = [&](const uint32_t *rows) -> WinT {  // V x V crop of a padded bit-row grid around (px, py)
                 WinT m = 0;
-                const int sh = py - R;
+                const uint32_t *r0 = rows + (px - R);
 #pragma unroll
-                for (int a = 0; a < V; ++a) {
-                    const int gx = px - R + a;
-                    uint32_t row = (gx >= 0 && gx < X) ? rows[gx] : 0u;
-                    row = sh >= 0 ? (row >> sh) : (row << (-sh));
-                    m |= (WinT)(row & ((1u << V) - 1u)) << (a * V);
-                }
+                for (int a = 0; a < V; ++a) m |= (WinT)((r0[a] >> py) & ((1u << V) - 1u)) << (a * V);
                 return m;
             };
+            bool done_fast = false;
+            if constexpr (V <= 7) {
+                if (p.fast3) {  // channels: total agents, all objects, area — assembled with compile-time shifts
+                    uint64_t A = row_window(agrid), O = 0;
+                    for (int t = 0; t < T; ++t) O |= row_window(grid + t * XP);
+                    if (p.agent_view == MAEXP_AV_DEFAULT) A &= los;
+                    if (p.object_view == MAEXP_OV_DEFAULT) O &= los;
+                    const unsigned __int128 lo = (unsigned __int128)A | ((unsigned __int128)O << VV) |
+                                                 ((unsigned __int128)los << (2 * VV));
+                    wv[0] = (uint32_t)lo;
+                    wv[1] = (uint32_t)(lo >> 32);
+                    wv[2] = (uint32_t)(lo >> 64);
+                    wv[3] = (uint32_t)(lo >> 96);
+                    constexpr int kHi = 128 - 2 * VV;
+                    wv[4] = kHi < 64 ? (uint32_t)(los >> (kHi < 64 ? kHi : 0)) : 0u;
+                    wv[5] = 0u;
+                    done_fast = true;
+                }
+            }
+            if (!done_fast) {
+            BitStream<V> bs(wv);
+            const int av = p.agent_view;
+            if (av == MAEXP_AV_INDIVIDUAL || av == MAEXP_AV_INDIVIDUAL_TRANSITION)
+                for (int k = 0; k < N; ++k) bs.put(win_bit(mypos[k * EPW]) & los);
             if (av != MAEXP_AV_INDIVIDUAL) {
                 WinT m = row_window(agrid);
                 if (av != MAEXP_AV_SIMPLE) m &= los;
-                put_bits<V>(wv, (ch++) * VV, m);
+                bs.put(m);
             }
             if (av == MAEXP_AV_TRANSITION || av == MAEXP_AV_INDIVIDUAL_TRANSITION)
                 for (int q = 0; q < P; ++q) {  // transition_agent_observation.py:47-57,81-94
@@ -360,19 +418,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                         const int ux = c & 0xFF, uy = c >> 8;
                         if (abs(ux - qx) <= R && abs(uy - qy) <= R) m |= win_bit(c);
                     }
-                    put_bits<V>(wv, (ch++) * VV, m);
+                    bs.put(m);
                 }
-            auto obj_window = [&](int t) -> WinT { return row_window(grid + t * X); };
+            auto obj_window = [&](int t) -> WinT { return row_window(grid + t * XP); };
             if (p.object_view == MAEXP_OV_TYPES) {
-                for (int t = 0; t < T; ++t) put_bits<V>(wv, (ch++) * VV, obj_window(t) & los);
+                for (int t = 0; t < T; ++t) bs.put(obj_window(t) & los);
             } else {
                 WinT m = 0;
                 for (int t = 0; t < T; ++t) m |= obj_window(t);
                 if (p.object_view == MAEXP_OV_DEFAULT) m &= los;
-                put_bits<V>(wv, (ch++) * VV, m);
+                bs.put(m);
             }
-            put_bits<V>(wv, ch * VV, los);  // observation_handler.py:107-108 (value = bit - 1)
-            gate = (s_noise[px] >> py) & 1u;
+            bs.put(los);  // observation_handler.py:107-108 (value = bit - 1)
+            bs.finish();
+            }
+            gate = (s_noise[px] >> (py + R)) & 1u;
 
             // -------------------------------------------- optional reference-format extras
             if (p.out.coordinates) {  // local_area_mask.py:18-47
@@ -388,8 +448,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             }
             if (p.out.objects) {
                 int8_t *o = p.out.objects + ((size_t)env * N + i) * TX * Y;
-                for (int r = 0; r < TX; ++r)
-                    for (int y = 0; y < Y; ++y) o[r * Y + y] = (int8_t)((grid[r] >> y) & 1u);
+                for (int t = 0; t < T; ++t)
+                    for (int x = 0; x < X; ++x)
+                        for (int y = 0; y < Y; ++y)
+                            o[(t * X + x) * Y + y] = (int8_t)((grid[t * XP + x] >> (y + R)) & 1u);
             }
         }
         if constexpr (NOISE != MAEXP_NOISE_NONE) {
@@ -398,31 +460,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
         __syncwarp();
 
         // ---------------------------------------------------------- phase B: expand + stream out
-        {
-            const int total = nenv * p.qps;
+        if (p.out.obs) {
+            const int qps = p.qps, ws = p.ws;
             const int env_stride = N * p.slot_floats;  // floats between consecutive envs in the slot
             const size_t base = ((size_t)env0 * N + i) * p.slot_floats;
-            float *dst = p.out.obs ? p.out.obs + base : nullptr;
-            float *dst_rel = (p.merged && p.out.obs_rel) ? p.out.obs_rel + base : nullptr;
+            float *const dst = p.out.obs + base;
+            float *const dst_rel = (p.merged && p.out.obs_rel) ? p.out.obs_rel + base : nullptr;
             const bool all_on = __all_sync(0xFFFFFFFFu, !mine || active);
-            for (int f = lane; f < total; f += 32) {
-                const int e = (int)__umulhi((uint32_t)f, p.qps_magic);
-                const int q = f - e * p.qps;
-                uint8_t flags = 3;
-                if (NOISE != MAEXP_NOISE_NONE || !all_on) flags = s_active[e];
-                if (!(flags & 1)) continue;
-                const uint32_t bits = (s_w[e * p.ws + (q >> 3)] >> ((q & 7) * 4)) & 0xFu;
-                const int cls = (q >= p.q_str) + (q > p.q_str) + (q == p.q_tail);
-                const float4 o = s_lut[cls * 16 + bits];
+            const bool check = (NOISE != MAEXP_NOISE_NONE) || !all_on;
+
+            // one quad (4 consecutive fp32 of the slot) of env e: table lookup, optional noise, 128-bit stores
+            auto emit = [&](int e, int q, uint32_t word, int sh, int lut_off) {
+                const float4 o = s_lut[lut_off + ((word >> sh) & 0xFu)];
                 const int off = e * env_stride + q * 4;
                 if constexpr (NOISE == MAEXP_NOISE_NONE) {
-                    if (dst) __stcs(reinterpret_cast<float4 *>(dst + off), o);
-                    if (dst_rel) __stcs(reinterpret_cast<float4 *>(dst_rel + off), o);
+                    store_quad(reinterpret_cast<float4 *>(dst + off), o);
+                    if (dst_rel) store_quad(reinterpret_cast<float4 *>(dst_rel + off), o);
                 } else {
-                    if (dst_rel) __stcs(reinterpret_cast<float4 *>(dst_rel + off), o);  // merged: relative stays clean
+                    if (dst_rel) store_quad(reinterpret_cast<float4 *>(dst_rel + off), o);  // merged: relative stays clean
                     float v[4] = {o.x, o.y, o.z, o.w};
                     const int k0 = q * 4;
-                    if (flags & 2) {
+                    if (s_active[e] & 2) {
                         float dr[4];
                         if (p.noise_tape) {
                             const float *t = p.noise_tape + ((size_t)(env0 + e) * N + i) * p.K + k0;
@@ -469,7 +527,41 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                             v[j] = x;
                         }
                     }
-                    if (dst) __stcs(reinterpret_cast<float4 *>(dst + off), make_float4(v[0], v[1], v[2], v[3]));
+                    store_quad(reinterpret_cast<float4 *>(dst + off), make_float4(v[0], v[1], v[2], v[3]));
+                }
+            };
+            auto quad_class = [&](int q) { return q > p.q_tail ? 0 : ((q >= p.q_str) + (q > p.q_str) + (q == p.q_tail)) * 16; };
+
+            // (1) full chunks: lane owns quad q = c*32 + lane of every env → per-lane constants hoisted,
+            //     each store instruction covers 512 contiguous bytes of one agent slot
+            const int nfull = qps >> 5;
+            for (int c = 0; c < nfull; ++c) {
+                const int q = c * 32 + lane;
+                const int sh = (q & 7) * 4, lut_off = quad_class(q);
+                const uint32_t *wq = s_w + (q >> 3);
+                if (NOISE == MAEXP_NOISE_NONE && !check && !dst_rel) {
+                    // hot path: running pointers, ~12 instructions per 16 bytes stored
+                    const float4 *lut = s_lut + lut_off;
+                    float *dp = dst + q * 4;
+#pragma unroll 4
+                    for (int e = 0; e < nenv; ++e, wq += ws, dp += env_stride)
+                        store_quad(reinterpret_cast<float4 *>(dp), lut[(*wq >> sh) & 0xFu]);
+                } else if (!check) {
+#pragma unroll 4
+                    for (int e = 0; e < nenv; ++e) emit(e, q, wq[e * ws], sh, lut_off);
+                } else {
+                    for (int e = 0; e < nenv; ++e)
+                        if (s_active[e] & 1) emit(e, q, wq[e * ws], sh, lut_off);
+                }
+            }
+            // (2) the qps % 32 trailing quads of all envs, flattened over (env, quad)
+            const int rem = qps & 31;
+            if (rem) {
+                const int q0 = nfull * 32;
+                for (int f = lane; f < nenv * rem; f += 32) {
+                    const int e = f / rem, q = q0 + (f - e * rem);
+                    if (check && !(s_active[e] & 1)) continue;
+                    emit(e, q, s_w[e * ws + (q >> 3)], (q & 7) * 4, quad_class(q));
                 }
             }
         }
@@ -524,11 +616,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     __syncwarp();
     {  // coalesced write-back of the grids
         uint32_t *dst = p.obj + (size_t)env0 * TX;
+#pragma unroll 4
         for (int i = lane; i < nenv * TX; i += 32) {
-            const int e = i / TX, r = i - e * TX;
-            if (s_active[e] & 1) dst[i] = s_grid[e * p.gs + r];
+            const int e = (int)__umulhi((uint32_t)i, p.tx_magic), r = i - e * TX;
+            const int t = (r >= X) + (r >= 2 * X) + (r >= 3 * X);
+            if (s_active[e] & 1) dst[i] = s_grid[e * p.gs + R + r + t * 2 * R] >> R;
         }
     }
+    __syncwarp();
+    }  // persistent group loop
 }
 
 
