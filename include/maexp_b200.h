@@ -86,6 +86,7 @@ typedef struct {
     int8_t *positions;     /* [E,N,2] index-space positions after the call ("agents" key) */
     int8_t *objects;       /* [E,N,T,X,Y] objects_matrix snapshot at agent i's observation time */
     uint8_t *destination;  /* [E,N] selected destination mask per agent ("destination" key = table row) */
+    int8_t *actions_taken; /* [E,N] the actions executed by this call (given or Philox-drawn); -1 on reset */
 } maexp_obs_out;
 
 typedef struct maexp_env maexp_env;
@@ -127,6 +128,95 @@ int maexp_env_set_state(maexp_env *env, const int8_t *pos /*[E,N,2]*/, const int
 /* number of env-steps (not resets) executed since creation, summed over envs; error flag of the
  * bounded rejection sampler.  Synchronises the stream. */
 int maexp_env_stats(maexp_env *env, uint64_t *env_steps, uint64_t *resets, int32_t *error_flag, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-resident replay ring (replaces ReplayBuffer / RLDataset / DataLoader collate:
+ * core/utils/buffer.py:36-63, core/utils/dataset.py:24-29, abstract_trainer.py:91-97).
+ * The ring is caller-owned device memory; slot s of every array is what one maexp_env_step /
+ * maexp_env_reset call wrote (obs, rewards, dones, was_reset) plus the actions that led to it.
+ * The transition (s -> s+1) of env e is valid iff was_reset[s+1][e] == 0. */
+typedef struct {
+    const float *obs;          /* [S,E,N,slot_floats] */
+    const int8_t *actions;     /* [S,E,N] action taken to reach slot s */
+    const float *rewards;      /* [S,E,N] */
+    const uint8_t *dones;      /* [S,E,N] */
+    const uint8_t *was_reset;  /* [S,E] */
+    int32_t num_slots;         /* S */
+    int32_t num_envs, num_agents, slot_floats;
+    int32_t head;              /* newest written slot */
+    int32_t count;             /* number of valid consecutive slots ending at head (>= 2) */
+} maexp_replay_view;
+
+typedef struct {
+    float *obs;        /* [N,B,slot_floats] state      */
+    float *next_obs;   /* [N,B,slot_floats] new_state  */
+    int32_t *actions;  /* [N,B] */
+    float *rewards;    /* [N,B] */
+    uint8_t *dones;    /* [N,B] */
+    int32_t *picked;   /* [B,2] (slot of the state, env) — may be NULL */
+} maexp_batch;
+
+/* Uniform sampling of `batch` whole-team transitions (np.random.choice in buffer.py:61; here with
+ * replacement — immaterial for batch << S*E) fused with the gather into per-agent batches.
+ * indices: optional int32 [B,2] (slot, env) injected picks (NULL: Philox keyed by seed/tick). */
+int maexp_replay_sample(const maexp_replay_view *ring, int32_t batch, uint32_t seed, uint32_t tick,
+                        const int32_t *indices, const maexp_batch *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Learner: G = num_agents independent value networks updated in grouped launches.
+ * generate_brain / generate_network / generate_optimizer / brain.learn
+ * (core/agents/brains/__init__.py:42-85, models/__init__.py:33-105, optimizers/__init__.py:17-42). */
+enum {
+    MAEXP_LEARNER_DQN_CONV_MLP = 0, /* brain dqn / da3_baseline + model conv_mlp: da3_brain.py:58-89, conv_mlp.py:21-66 */
+    MAEXP_LEARNER_C51 = 1,          /* categorical_dqn_brain.py:42-89, customs/categorical_dqn.py:28-79 */
+    MAEXP_LEARNER_QR = 2,           /* qr_dqn_brain.py:81-119, customs/qr_dqn.py:20-65 */
+    MAEXP_LEARNER_DQN_MLP = 3       /* model mlp on the flattened observation (mlp.py:14-34) */
+};
+enum { MAEXP_BUF_ONLINE = 0, MAEXP_BUF_TARGET = 1, MAEXP_BUF_GRADS = 2, MAEXP_BUF_SQUARE_AVG = 3, MAEXP_BUF_SUPPORT = 4 };
+
+typedef struct {
+    int32_t kind;
+    int32_t num_agents;      /* G */
+    int32_t batch_size;      /* B */
+    int32_t channels, visible_range, num_actions;
+    int32_t hidden;          /* model.hidden_layer_sizes[0] */
+    int32_t conv1_channels;  /* model.hidden_channels[0] */
+    int32_t conv2_channels;  /* model.output_channel */
+    int32_t num_atoms;       /* C51: model.num_atoms; QR: model.num_quantiles */
+    int32_t obs_stride;      /* floats between consecutive observations of a batch (>= C*V*V) */
+    float gamma;
+    float v_min, v_max, delta_z;  /* C51 support bounds; delta_z = fp32((V_max - V_min)/(num_atoms - 1)) */
+    float learning_rate, alpha, one_minus_alpha, eps;  /* optim.RMSprop, configs/opt/rmsprop.yaml */
+    float max_norm;          /* clip_grad_norm_: 0.1 (dqn, qr), 10 (c51) */
+} maexp_learner_cfg;
+
+typedef struct maexp_learner maexp_learner;
+
+int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out);
+void maexp_learner_destroy(maexp_learner *learner);
+/* parameters per agent, and the table (state_dict key, offset, count) that maps the flat fp32
+ * buffers to the reference's `agent{i}.pth` tensors (abstract_loop_handler.py:149-180) */
+int64_t maexp_learner_num_params(const maexp_learner *learner);
+int maexp_learner_num_tensors(const maexp_learner *learner);
+int maexp_learner_tensor(const maexp_learner *learner, int index, char *name, int name_len, int64_t *offset,
+                         int64_t *count);
+/* device buffers [G, num_params] (MAEXP_BUF_SUPPORT: [128] atoms z_j or tau_hat_j, written by the host) */
+float *maexp_learner_buffer(maexp_learner *learner, int which);
+/* hard_update (core/utils/updates.py:25-34) */
+int maexp_learner_sync_target(maexp_learner *learner, void *stream);
+/* brain.get_action's values: Q [G,batch,A] (C51: sum_j p_j z_j, QR: mean of quantiles) */
+int maexp_learner_q_values(maexp_learner *learner, const float *obs /*[G,batch,obs_stride]*/, int batch,
+                           int use_target, float *q_out, void *stream);
+/* forward(s), forward(s'), TD target / projection, loss [G] and gradients into MAEXP_BUF_GRADS */
+int maexp_learner_grads(maexp_learner *learner, const float *obs, const float *next_obs, const int32_t *actions,
+                        const float *rewards, const uint8_t *dones, float *loss_out, void *stream);
+/* grads *= grad_scale (1/world_size after an all-reduce), clip_grad_norm_, RMSprop step.
+ * active: optional uint8 [G], 0 skips the agent (agent_tasks "-1", abstract_trainer.py:49-51) */
+int maexp_learner_apply(maexp_learner *learner, float grad_scale, const uint8_t *active, float *grad_norm_out,
+                        void *stream);
+/* grads + apply on one GPU */
+int maexp_learner_update(maexp_learner *learner, const float *obs, const float *next_obs, const int32_t *actions,
+                         const float *rewards, const uint8_t *dones, float *loss_out, void *stream);
 
 const char *maexp_last_error(void);
 int maexp_version(void);

@@ -37,8 +37,27 @@ class Tables(C.Structure):
 
 class ObsOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates",
-                                           "positions", "objects", "destination")]
+                                           "positions", "objects", "destination", "actions_taken")]
 
+
+class ReplayView(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "actions", "rewards", "dones", "was_reset")] + \
+               [(n, C.c_int32) for n in ("num_slots", "num_envs", "num_agents", "slot_floats", "head", "count")]
+
+
+class Batch(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "next_obs", "actions", "rewards", "dones", "picked")]
+
+
+class LearnerCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("kind", "num_agents", "batch_size", "channels", "visible_range", "num_actions",
+                                          "hidden", "conv1_channels", "conv2_channels", "num_atoms", "obs_stride")] + \
+               [(n, C.c_float) for n in ("gamma", "v_min", "v_max", "delta_z", "learning_rate", "alpha",
+                                          "one_minus_alpha", "eps", "max_norm")]
+
+
+LEARNER_KINDS = {"dqn_conv_mlp": 0, "c51": 1, "qr": 2, "dqn_mlp": 3}
+BUF_ONLINE, BUF_TARGET, BUF_GRADS, BUF_SQUARE_AVG, BUF_SUPPORT = range(5)
 
 # every symbol include/maexp_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -55,6 +74,20 @@ SYMBOLS = {
     "maexp_env_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "maexp_env_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32),
                                   C.c_void_p]),
+    "maexp_replay_sample": (C.c_int, [C.POINTER(ReplayView), C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                      C.POINTER(Batch), C.c_void_p]),
+    "maexp_learner_create": (C.c_int, [C.POINTER(LearnerCfg), C.POINTER(C.c_void_p)]),
+    "maexp_learner_destroy": (None, [C.c_void_p]),
+    "maexp_learner_num_params": (C.c_int64, [C.c_void_p]),
+    "maexp_learner_num_tensors": (C.c_int, [C.c_void_p]),
+    "maexp_learner_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64)]),
+    "maexp_learner_buffer": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "maexp_learner_sync_target": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "maexp_learner_q_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "maexp_learner_grads": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
+    "maexp_learner_apply": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "maexp_learner_update": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
     "maexp_last_error": (C.c_char_p, []),
     "maexp_version": (C.c_int, []),
 }

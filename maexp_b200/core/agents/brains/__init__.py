@@ -1,0 +1,221 @@
+"""Brains: TD target, loss, clipping and optimizer step on the GPU (maexp_learner_* C-ABI).
+
+`LearnerGroup` updates G = num_agents independent networks in grouped launches; `generate_brain`
+keeps the reference's per-agent factory (core/agents/brains/__init__.py:42-85) on top of it.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .... import _lib
+from ...utils.logging import initialize_logging
+from ..models import build_reference_modules
+
+logger = initialize_logging(__name__)
+
+# brain name -> (learner kind for conv models, clip max_norm)      brains/*.py
+_BRAINS = {"dqn": ("dqn_conv_mlp", 0.1), "da3_baseline": ("dqn_conv_mlp", 0.1), "categorical_dqn": ("c51", 10.0),
+           "qr_dqn": ("qr", 0.1)}
+
+
+def learner_kind(config):
+    if config.brain not in _BRAINS:
+        logger.warning(f"Unexpected brain is given. config.brain: {config.brain}")
+        raise ValueError()
+    kind, max_norm = _BRAINS[config.brain]
+    if config.model.name == "mlp":
+        if kind != "dqn_conv_mlp":
+            raise ValueError("model=mlp is only defined for the dqn brain")
+        kind = "dqn_mlp"
+    elif config.model.name not in ("conv_mlp", "da3_baseline", "categorical_dqn", "qr_dqn"):
+        logger.warning(f"Unexpected network is given. config.model.name: {config.model.name}")
+        raise ValueError()
+    return kind, max_norm
+
+
+class LearnerGroup:
+    def __init__(self, config, obs_shape, act_size, num_agents, batch_size, obs_stride=None, device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise _lib.MaexpError("LearnerGroup needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
+        self.config, self.device = config, torch.device(device)
+        self.kind, max_norm = learner_kind(config)
+        C_, V = int(obs_shape[0]), int(obs_shape[1])
+        self.G, self.B, self.A, self.C, self.V = int(num_agents), int(batch_size), int(act_size), C_, V
+        self.K = C_ * V * V
+        self.obs_stride = int(obs_stride or (self.K + 7) // 8 * 8)
+        m, opt = config.model, config.opt
+        if opt.name != "rmsprop":
+            raise ValueError("only opt=rmsprop is implemented (all shipped configs use it)")
+        cfg = _lib.LearnerCfg()
+        cfg.kind = _lib.LEARNER_KINDS[self.kind]
+        cfg.num_agents, cfg.batch_size, cfg.channels, cfg.visible_range = self.G, self.B, C_, V
+        cfg.num_actions, cfg.hidden = self.A, int(m.hidden_layer_sizes[0])
+        cfg.conv1_channels = int(m.get("hidden_channels", [32])[0])
+        cfg.conv2_channels = int(m.get("output_channel", 64))
+        self.Z = int(m.num_atoms) if self.kind == "c51" else int(m.num_quantiles) if self.kind == "qr" else 1
+        cfg.num_atoms, cfg.obs_stride = self.Z, self.obs_stride
+        cfg.gamma = float(config.gamma)
+        if self.kind == "c51":
+            cfg.v_min, cfg.v_max = float(m.V_min), float(m.V_max)
+            cfg.delta_z = (float(m.V_max) - float(m.V_min)) / (self.Z - 1)  # python double -> fp32, as torch does
+        cfg.learning_rate, cfg.alpha, cfg.eps = float(opt.learning_rate), float(opt.alpha), float(opt.eps)
+        cfg.one_minus_alpha = 1.0 - float(opt.alpha)
+        cfg.max_norm = max_norm
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.maexp_learner_create(C.byref(cfg), C.byref(handle)))
+        self.h = handle
+        self.P = int(self.lib.maexp_learner_num_params(self.h))
+        self.table = []
+        for i in range(self.lib.maexp_learner_num_tensors(self.h)):
+            name, off, cnt = C.create_string_buffer(96), C.c_int64(), C.c_int64()
+            _lib.check(self.lib.maexp_learner_tensor(self.h, i, name, 96, C.byref(off), C.byref(cnt)))
+            self.table.append((name.value.decode(), off.value, cnt.value))
+        self.loss = torch.zeros((self.G,), dtype=torch.float32, device=self.device)
+        self.grad_norm = torch.zeros((self.G,), dtype=torch.float32, device=self.device)
+        self.q = torch.zeros((self.G, self.B, self.A), dtype=torch.float32, device=self.device)
+        # support / tau_hat vector exactly as the reference brains build it
+        if self.kind == "c51":  # categorical_dqn_brain.py:24-26
+            self._write_support(torch.linspace(float(m.V_min), float(m.V_max), self.Z))
+        elif self.kind == "qr":  # qr_dqn_brain.py:59-65
+            taus = torch.arange(0, self.Z + 1, dtype=torch.float32) / self.Z
+            self._write_support((taus[1:] + taus[:-1]) / 2.0)
+        # PyTorch default initialisation, target <- online (abstract_brain.py:33)
+        for g in range(self.G):
+            self.load_state_dict(g, build_reference_modules(config, obs_shape, act_size).state_dict())
+        self.synchronize()
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            self.lib.maexp_learner_destroy(h)
+
+    # ------------------------------------------------------------------ buffers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _buffer(self, which, count):
+        """Zero-copy torch view of a library-owned device buffer."""
+        ptr = self.lib.maexp_learner_buffer(self.h, which)
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+        return torch.as_tensor(_Holder(), device=self.device)
+
+    def params(self, which=_lib.BUF_ONLINE):
+        return self._buffer(which, self.G * self.P).view(self.G, self.P)
+
+    def _write_support(self, values):
+        self._buffer(_lib.BUF_SUPPORT, 128)[: values.numel()].copy_(values.to(self.device))
+
+    # ------------------------------------------------------------------ state dicts (agent{i}.pth compatible)
+    def state_dict(self, agent_id, which=_lib.BUF_ONLINE, shapes=None):
+        flat = self.params(which)[agent_id].detach().cpu()
+        shapes = shapes or self._shapes
+        return {name: flat[off:off + cnt].clone().view(shapes[name]) for name, off, cnt in self.table}
+
+    def load_state_dict(self, agent_id, state_dict, which=_lib.BUF_ONLINE):
+        """abstract_loop_handler.py:168-180: copy the matching keys."""
+        flat = self.params(which)[agent_id]
+        self._shapes = getattr(self, "_shapes", {})
+        for name, off, cnt in self.table:
+            if name in state_dict:
+                t = state_dict[name].detach().to(torch.float32)
+                assert t.numel() == cnt, (name, tuple(t.shape), cnt)
+                self._shapes[name] = tuple(t.shape)
+                flat[off:off + cnt].copy_(t.reshape(-1).to(self.device))
+
+    def synchronize(self):
+        """hard_update of every agent's target network (abstract_brain.py:37-38)."""
+        _lib.check(self.lib.maexp_learner_sync_target(self.h, self._stream()))
+
+    # ------------------------------------------------------------------ compute
+    def q_values(self, obs, use_target=False):
+        """obs fp32 [G, b, obs_stride] on the device -> Q [G, b, A]."""
+        b = obs.shape[1]
+        q = self.q if b == self.B else torch.empty((self.G, b, self.A), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.maexp_learner_q_values(self.h, C.c_void_p(obs.data_ptr()), b, int(use_target),
+                                                   C.c_void_p(q.data_ptr()), self._stream()))
+        return q
+
+    def grads(self, batch):
+        """Forward, TD target, loss [G] and gradients (kept in the library's grad buffer)."""
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(self.lib.maexp_learner_grads(self.h, p(batch["obs"]), p(batch["next_obs"]), p(batch["actions"]),
+                                                p(batch["rewards"]), p(batch["dones"]), p(self.loss), self._stream()))
+        return self.loss
+
+    def apply(self, grad_scale=1.0, active=None):
+        a = None if active is None else C.c_void_p(active.data_ptr())
+        _lib.check(self.lib.maexp_learner_apply(self.h, float(grad_scale), a, C.c_void_p(self.grad_norm.data_ptr()),
+                                                self._stream()))
+
+    def learn(self, batch, active=None, all_reduce=None):
+        """One update of every agent's network.  all_reduce: optional callable(grads_tensor) -> world size,
+        e.g. an NCCL all-reduce for the data-parallel learner (clip runs AFTER the reduce)."""
+        loss = self.grads(batch)
+        scale = 1.0
+        if all_reduce is not None:
+            scale = 1.0 / float(all_reduce(self.params(_lib.BUF_GRADS)))
+        self.apply(scale, active)
+        return loss
+
+
+class Brain:
+    """Single-agent brain with the reference's interface (abstract_brain.py:20-67)."""
+
+    def __init__(self, config, obs_shape, act_size):
+        self.config = config
+        self.device = torch.device("cuda:0")
+        self.group = LearnerGroup(config, obs_shape, act_size, 1, int(config.batch_size), device=self.device)
+        self.view = "local" if config.observation_area_mask in ("local", "merged") else "relative"
+
+    def _pack(self, x):
+        g = self.group
+        x = x.float().reshape(x.shape[0], -1).to(self.device)
+        out = torch.zeros((1, x.shape[0], g.obs_stride), dtype=torch.float32, device=self.device)
+        out[0, :, : g.K] = x
+        return out
+
+    @torch.no_grad()
+    def get_action(self, state):
+        q = self.group.q_values(self._pack(state[self.view].unsqueeze(0)))
+        return int(q[0, 0].argmax().item())
+
+    def learn(self, states_ind, actions_ind, rewards_ind, dones_ind, next_states_ind):
+        batch = {"obs": self._pack(states_ind[self.view]), "next_obs": self._pack(next_states_ind[self.view]),
+                 "actions": actions_ind.to(self.device).to(torch.int32).reshape(1, -1).contiguous(),
+                 "rewards": rewards_ind.float().to(self.device).reshape(1, -1).contiguous(),
+                 "dones": dones_ind.to(self.device).to(torch.uint8).reshape(1, -1).contiguous()}
+        loss = self.group.learn(batch)
+        return {"total_loss": loss[0].detach().cpu()}  # always a dict
+
+    def synchronize_network(self):
+        self.group.synchronize()
+
+    @property
+    def network(self):
+        return _StateDictView(self.group, _lib.BUF_ONLINE)
+
+    @property
+    def target_network(self):
+        return _StateDictView(self.group, _lib.BUF_TARGET)
+
+
+class _StateDictView:
+    def __init__(self, group, which):
+        self.group, self.which = group, which
+
+    def state_dict(self):
+        return self.group.state_dict(0, self.which)
+
+    def load_state_dict(self, sd):
+        self.group.load_state_dict(0, sd, self.which)
+
+
+def generate_brain(config, obs_shape, act_size):
+    """core/agents/brains/__init__.py:42-85 (dqn, da3_baseline, categorical_dqn, qr_dqn)."""
+    learner_kind(config)  # raises ValueError on unknown keys, as the reference does
+    return Brain(config=config, obs_shape=obs_shape, act_size=act_size)

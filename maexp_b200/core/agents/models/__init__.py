@@ -1,0 +1,64 @@
+"""Network *definitions* (host side): layer shapes, state_dict keys and default initialisation.
+
+The forward/backward arithmetic runs in the CUDA library (csrc/learner.cu); these torch modules
+only exist so that parameters are created with PyTorch's default initialisers in the reference's
+construction order and under the reference's state_dict keys
+(core/agents/models/convolution.py:14-55, mlp.py:14-34, customs/conv_mlp.py:21-52,
+customs/categorical_dqn.py:28-58, customs/qr_dqn.py:20-44), so `agent{i}.pth` files interchange.
+"""
+import torch
+from torch import nn
+
+
+class _Conv(nn.Module):
+    def __init__(self, config, input_channel, output_channel):
+        super().__init__()
+        m = config.model
+        self.conv_list = nn.ModuleList()
+        for ch, k, s in zip(m.hidden_channels, m.hidden_kernels, m.hidden_strides):
+            self.conv_list.append(nn.Conv2d(input_channel, ch, kernel_size=k, stride=s))
+            input_channel = ch
+        self.conv_post = nn.Conv2d(input_channel, output_channel, kernel_size=m.hidden_kernels[-1],
+                                   stride=m.hidden_strides[-1])
+
+
+class _MLP(nn.Module):
+    def __init__(self, config, input_size, output_size):
+        super().__init__()
+        self.fc_list = nn.ModuleList()
+        for size in config.model.hidden_layer_sizes:
+            self.fc_list.append(nn.Linear(input_size, size))
+            input_size = size
+        self.fc_post = nn.Linear(input_size, output_size)
+
+
+def conv_output_size(config, obs_shape):
+    """Flattened size of Conv's output (conv k2 s1 -> max_pool2d(2,2) -> conv k2 s1)."""
+    v = int(obs_shape[1])
+    h2 = (v - 1) // 2 - 1
+    return int(config.model.output_channel) * h2 * h2
+
+
+class _ConvHeads(nn.Module):
+    def __init__(self, config, obs_shape, heads):
+        super().__init__()
+        self.conv = _Conv(config, obs_shape[0], config.model.output_channel)
+        torch.randn(1, *obs_shape)  # the reference probes the conv with a random input here (conv_mlp.py:51)
+        d = conv_output_size(config, obs_shape)
+        for name, out in heads:
+            setattr(self, name, _MLP(config, d, out))
+
+
+def build_reference_modules(config, obs_shape, act_size):
+    name = config.model.name
+    if name == "mlp":  # the flattened observation feeds the MLP
+        return _MLP(config, int(obs_shape[0]) * int(obs_shape[1]) * int(obs_shape[2]), act_size)
+    if name in ("conv_mlp", "da3_baseline"):
+        return _ConvHeads(config, obs_shape, [("mlp", act_size)])
+    if name == "categorical_dqn":
+        z = int(config.model.num_atoms)
+        return _ConvHeads(config, obs_shape, [("fc_V", z), ("fc_A", act_size * z)])
+    if name == "qr_dqn":
+        z = int(config.model.num_quantiles)
+        return _ConvHeads(config, obs_shape, [("fc_V", z), ("fc_A", act_size * z)])
+    raise ValueError(name)

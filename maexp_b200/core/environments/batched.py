@@ -170,7 +170,7 @@ class BatchedEnvironment:
     def _out_struct(self, out):
         s = _lib.ObsOut()
         for name in ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates", "positions", "objects",
-                     "destination"):
+                     "destination", "actions_taken"):
             t = out.get(name)
             if t is not None:
                 assert t.is_cuda and t.is_contiguous()

@@ -1,0 +1,72 @@
+"""Device-resident replay ring (replaces core/utils/buffer.py:36-63 + core/utils/dataset.py:24-29).
+
+The reference keeps a deque of python Experience tuples and collates a batch per step; here
+every env step writes its observations, rewards, dones and actions straight into slot `head` of
+ring tensors in HBM, and `sample()` is one fused pick+gather launch (maexp_replay_sample).
+"""
+import ctypes as C
+
+import torch
+
+from ... import _lib
+from .logging import initialize_logging
+
+logger = initialize_logging(__name__)
+
+
+class DeviceReplayRing:
+    def __init__(self, env, num_slots):
+        self.lib = _lib.load()
+        self.env, self.S = env, int(num_slots)
+        E, N, d = env.E, env.N, env.device
+        self.obs = torch.zeros((self.S, E, N, env.slot_floats), dtype=torch.float32, device=d)
+        self.actions = torch.zeros((self.S, E, N), dtype=torch.int8, device=d)
+        self.rewards = torch.zeros((self.S, E, N), dtype=torch.float32, device=d)
+        self.dones = torch.zeros((self.S, E, N), dtype=torch.uint8, device=d)
+        self.was_reset = torch.ones((self.S, E), dtype=torch.uint8, device=d)
+        self.head, self.count = -1, 0
+
+    def __len__(self):
+        """Number of stored whole-team transitions (valid or not), as ReplayBuffer.__len__."""
+        return max(0, self.count - 1) * self.env.E
+
+    def next_outputs(self):
+        """Output dict for env.step / env.reset that targets the next ring slot; call commit() after."""
+        s = (self.head + 1) % self.S
+        return {"obs": self.obs[s], "rewards": self.rewards[s], "dones": self.dones[s],
+                "was_reset": self.was_reset[s], "actions_taken": self.actions[s]}
+
+    def commit(self):
+        self.head = (self.head + 1) % self.S
+        self.count = min(self.count + 1, self.S)
+
+    def new_batch(self, batch_size):
+        N, d, sf = self.env.N, self.env.device, self.env.slot_floats
+        return {"obs": torch.empty((N, batch_size, sf), dtype=torch.float32, device=d),
+                "next_obs": torch.empty((N, batch_size, sf), dtype=torch.float32, device=d),
+                "actions": torch.empty((N, batch_size), dtype=torch.int32, device=d),
+                "rewards": torch.empty((N, batch_size), dtype=torch.float32, device=d),
+                "dones": torch.empty((N, batch_size), dtype=torch.uint8, device=d),
+                "picked": torch.empty((batch_size, 2), dtype=torch.int32, device=d)}
+
+    def sample(self, batch, seed=0, tick=0, indices=None):
+        """Fills `batch` (from new_batch) with uniformly sampled transitions; indices: int32 [B,2]."""
+        B = batch["actions"].shape[1]
+        view = _lib.ReplayView(self.obs.data_ptr(), self.actions.data_ptr(), self.rewards.data_ptr(),
+                               self.dones.data_ptr(), self.was_reset.data_ptr(), self.S, self.env.E, self.env.N,
+                               self.env.slot_floats, self.head, self.count)
+        out = _lib.Batch(*[batch[k].data_ptr() for k in ("obs", "next_obs", "actions", "rewards", "dones", "picked")])
+        idx = None if indices is None else C.c_void_p(indices.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
+        _lib.check(self.lib.maexp_replay_sample(C.byref(view), B, seed & 0xFFFFFFFF, tick & 0xFFFFFFFF, idx,
+                                                C.byref(out), stream))
+        return batch
+
+
+def generate_buffer(config, env=None):
+    """core/utils/buffer.py:21-33.  `capacity` counts whole-team transitions, as in the reference."""
+    if config.buffer == "default":
+        slots = max(2, min(int(config.capacity) // max(1, env.E) + 1, 1 << 16))
+        return DeviceReplayRing(env, slots)
+    logger.warning(f"Unexpected buffer is given. config.buffer: {config.buffer}")
+    raise ValueError()

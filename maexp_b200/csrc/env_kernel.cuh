@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     int stepc = 0, nobj = 0;
     int c_gen = 0, c_done = 0, c_ca = 0, c_cw = 0;
     uint32_t ca = 0, cw = 0, rew_pos = 0, rew_neg = 0, done_bits = 0;
-    uint64_t dsel = 0;
+    uint64_t dsel = 0, acts_taken = 0;
     bool is_reset = false, active = false;
     uint32_t attempt = 0;
     uint4 rw = make_uint4(0, 0, 0, 0);
@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                         if (c * 4 + j < N) acts |= (uint64_t)(pick(w, j) >> 30) << (3 * (c * 4 + j));
                 }
             }
+            acts_taken = acts;
             uint64_t ord = 0;
             if (p.order) {
                 for (int k = 0; k < N; ++k) ord |= (uint64_t)(p.order[(size_t)env * N + k] & 15) << (4 * k);
@@ -595,6 +596,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                 p.out.positions[((size_t)env * N + k) * 2 + 0] = (int8_t)(mypos[k * EPW] & 0xFF);
                 p.out.positions[((size_t)env * N + k) * 2 + 1] = (int8_t)(mypos[k * EPW] >> 8);
             }
+            if (p.out.actions_taken)
+                p.out.actions_taken[(size_t)env * N + k] = is_reset ? (int8_t)-1 : (int8_t)((acts_taken >> (3 * k)) & 7);
             if (p.out.destination)
                 p.out.destination[(size_t)env * N + k] =
                     (uint8_t)(p.random_dest ? nib(dsel, k) : (k < p.M ? k : p.M - 1));

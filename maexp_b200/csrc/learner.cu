@@ -1,0 +1,855 @@
+// Data-parallel learner update for the per-agent value networks, sm_100a.
+//
+// Replaces (for G = num_agents independent networks at once, grouped in every launch):
+//   DA3Brain.learn / DQNBrain.learn   core/agents/brains/da3_brain.py:58-89, dqn_brain.py:20-49   (TD target + MSE)
+//   CategoricalDQNBrain.learn         core/agents/brains/categorical_dqn_brain.py:42-89           (C51 projection + CE)
+//   QRDQNBrain.learn                  core/agents/brains/qr_dqn_brain.py:15-51,81-119             (quantile Huber)
+//   Conv / MLP / ConvMLP / CategoricalDQN / QRDQN forward+backward
+//                                      core/agents/models/convolution.py:14-55, mlp.py:14-34,
+//                                      customs/conv_mlp.py:21-66, categorical_dqn.py:28-79, qr_dqn.py:20-65
+//   clip_grad_norm_ + optim.RMSprop   brains/*.py, core/agents/optimizers/__init__.py:28-33
+//   hard_update                        core/utils/updates.py:25-34
+//
+// Numerics: fp32 FMA-free SIMT arithmetic in a fixed summation order (deterministic).  The parity
+// bar is 1e-5 relative on losses and Q-values against torch fp32 eager, which
+// rules out TF32 tensor-core math at these sizes; the networks are 42k-140k parameters and the
+// update is launch-latency bound, so every layer is ONE grouped launch for
+// all agents and the whole update is CUDA-graph capturable (no host sync, no allocation).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/maexp_b200.h"
+
+namespace maexp {
+int fail(const std::string &msg);  // env.cu
+#define MAEXP_CUDA_L(call)                                                                        \
+    do {                                                                                          \
+        cudaError_t err__ = (call);                                                               \
+        if (err__ != cudaSuccess)                                                                 \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(err__));                   \
+    } while (0)
+
+// ------------------------------------------------------------------------------ grouped GEMM
+// C[g][m,n] (=|+=) epi( sum_k A[g][m,k] * B[g][k,n] + bias[g][n] ), arbitrary element strides.
+struct GemmArgs {
+    const float *A, *B, *bias, *aux;
+    float *C;
+    int M, N, K;
+    long long sam, sak, sbk, sbn, scm, scn;  // element strides
+    long long gA, gB, gC, gBias, gAux;       // per-group offsets
+    int relu;        // max(x, 0)
+    int accumulate;  // C += result
+    int mask_aux;    // result *= (aux[m,n] > 0)   (ReLU backward; aux uses C's strides)
+};
+
+constexpr int kTile = 64, kBK = 16;
+
+__global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
+    __shared__ float As[kBK][kTile + 4];
+    __shared__ float Bs[kBK][kTile + 4];
+    const int g = blockIdx.z;
+    const float *A = a.A + (size_t)g * a.gA, *B = a.B + (size_t)g * a.gB;
+    float *C = a.C + (size_t)g * a.gC;
+    const int m0 = blockIdx.y * kTile, n0 = blockIdx.x * kTile;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    const bool a_k_fast = a.sak == 1, b_n_fast = a.sbn == 1;
+    for (int k0 = 0; k0 < a.K; k0 += kBK) {
+        // load A tile [64 x 16] and B tile [16 x 64]; 4 elements per thread each, coalesced along the unit stride
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int idx = tid + r * 256;
+            int mm, kk;
+            if (a_k_fast) { kk = idx & 15; mm = idx >> 4; } else { mm = idx & 63; kk = idx >> 6; }
+            const int m = m0 + mm, k = k0 + kk;
+            As[kk][mm] = (m < a.M && k < a.K) ? A[(size_t)m * a.sam + (size_t)k * a.sak] : 0.0f;
+            int nn, kb;
+            if (b_n_fast) { nn = idx & 63; kb = idx >> 6; } else { kb = idx & 15; nn = idx >> 4; }
+            const int n = n0 + nn, k2 = k0 + kb;
+            Bs[kb][nn] = (n < a.N && k2 < a.K) ? B[(size_t)k2 * a.sbk + (size_t)n * a.sbn] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kBK; ++kk) {
+            float av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(av[i], bv[j]));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= a.N) continue;
+            float v = acc[i][j];
+            if (a.bias) v = __fadd_rn(v, a.bias[(size_t)g * a.gBias + n]);
+            if (a.relu) v = fmaxf(v, 0.0f);
+            const size_t ci = (size_t)m * a.scm + (size_t)n * a.scn;
+            if (a.mask_aux) v = (a.aux[(size_t)g * a.gAux + ci] > 0.0f) ? v : 0.0f;
+            if (a.accumulate) v = __fadd_rn(C[ci], v);
+            C[ci] = v;
+        }
+    }
+}
+
+// column sums: out[g][n] = sum_m X[g][m,n]  (bias gradients), one warp per column, fixed order
+__global__ void colsum_kernel(const float *X, float *out, int M, int N, long long gX, long long gOut) {
+    const int g = blockIdx.y, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= N) return;
+    const float *x = X + (size_t)g * gX + warp;
+    float s = 0.0f;
+    for (int m = lane; m < M; m += 32) s = __fadd_rn(s, x[(size_t)m * N]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = __fadd_rn(s, __shfl_down_sync(0xFFFFFFFFu, s, o));
+    if (lane == 0) out[(size_t)g * gOut + warp] = s;
+}
+
+// im2col for k=2, s=1: col[g][(b,oy,ox)][c*4 + ky*2 + kx] = src[g][b*sb + c*sc + (oy+ky)*sy + (ox+kx)*sx]
+__global__ void im2col_kernel(const float *src, float *col, int B, int Cn, int Ho, int Wo, long long sb, long long sc,
+                              long long sy, long long sx, long long gSrc, long long gCol) {
+    const int g = blockIdx.y;
+    const long long total = (long long)B * Ho * Wo * Cn * 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % (Cn * 4));
+        const long long row = i / (Cn * 4);
+        const int ox = (int)(row % Wo), oy = (int)((row / Wo) % Ho);
+        const long long b = row / ((long long)Wo * Ho);
+        const int c = kk >> 2, ky = (kk >> 1) & 1, kx = kk & 1;
+        col[(size_t)g * gCol + i] = src[(size_t)g * gSrc + b * sb + c * sc + (oy + ky) * sy + (ox + kx) * sx];
+    }
+}
+
+// F.max_pool2d(kernel 2, stride 2) on NHWC [B][H*W][F]; first maximum wins (strict >), index kept for backward
+__global__ void pool_fwd_kernel(const float *y, float *p, uint8_t *arg, int B, int H, int W, int F, long long gY,
+                                long long gP) {
+    const int g = blockIdx.y, Hp = H / 2, Wp = W / 2;
+    const long long total = (long long)B * Hp * Wp * F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F);
+        const long long cell = i / F;
+        const int px = (int)(cell % Wp), py = (int)((cell / Wp) % Hp);
+        const long long b = cell / ((long long)Wp * Hp);
+        const float *src = y + (size_t)g * gY + (size_t)b * H * W * F + f;
+        float best = src[((size_t)(2 * py) * W + 2 * px) * F];
+        int bi = 0;
+#pragma unroll
+        for (int d = 1; d < 4; ++d) {
+            const float v = src[((size_t)(2 * py + (d >> 1)) * W + 2 * px + (d & 1)) * F];
+            if (v > best) { best = v; bi = d; }
+        }
+        p[(size_t)g * gP + i] = best;
+        arg[(size_t)g * gP + i] = (uint8_t)bi;
+    }
+}
+
+__global__ void pool_bwd_kernel(const float *dp, const uint8_t *arg, float *dy, int B, int H, int W, int F, long long gY,
+                                long long gP) {
+    const int g = blockIdx.y, Hp = H / 2, Wp = W / 2;
+    const long long total = (long long)B * H * W * F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F);
+        const long long cell = i / F;
+        const int x = (int)(cell % W), yy = (int)((cell / W) % H);
+        const long long b = cell / ((long long)W * H);
+        float v = 0.0f;
+        const int py = yy >> 1, px = x >> 1;
+        if (py < Hp && px < Wp) {
+            const size_t pi = (size_t)g * gP + (((size_t)b * Hp + py) * Wp + px) * F + f;
+            if (arg[pi] == (uint8_t)(((yy & 1) << 1) | (x & 1))) v = dp[pi];
+        }
+        dy[(size_t)g * gY + i] = v;
+    }
+}
+
+// col2im (gather form) for k=2, s=1 on NHWC: dp[b][y][x][o] = sum over (ky,kx) of dcol[(b,y-ky,x-kx)][o*4+ky*2+kx]
+__global__ void col2im_kernel(const float *dcol, float *dp, int B, int Hp, int Wp, int F, long long gCol, long long gP) {
+    const int g = blockIdx.y, Ho = Hp - 1, Wo = Wp - 1;
+    const long long total = (long long)B * Hp * Wp * F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(i % F);
+        const long long cell = i / F;
+        const int x = (int)(cell % Wp), y = (int)((cell / Wp) % Hp);
+        const long long b = cell / ((long long)Wp * Hp);
+        float s = 0.0f;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int ky = d >> 1, kx = d & 1, qy = y - ky, qx = x - kx;
+            if (qy >= 0 && qy < Ho && qx >= 0 && qx < Wo)
+                s = __fadd_rn(s, dcol[(size_t)g * gCol + (((size_t)b * Ho + qy) * Wo + qx) * (F * 4) + o * 4 + d]);
+        }
+        dp[(size_t)g * gP + i] = s;
+    }
+}
+
+// NHWC [B][Q][F] <-> flattened NCHW [B][F*Q]  (out.view(B, -1) of conv_mlp.py:44)
+__global__ void nhwc_to_flat_kernel(const float *y, float *flat, int B, int Q, int F, long long gs, int inverse) {
+    const int g = blockIdx.y;
+    const long long total = (long long)B * Q * F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F);
+        const int q = (int)((i / F) % Q);
+        const long long b = i / ((long long)F * Q);
+        const size_t fi = (size_t)g * gs + (size_t)b * F * Q + (size_t)f * Q + q;
+        if (!inverse) flat[fi] = y[(size_t)g * gs + i];
+        else flat[(size_t)g * gs + i] = y[fi];  // here `y` is the flat gradient, `flat` the NHWC gradient
+    }
+}
+
+// ------------------------------------------------------------------------------ losses
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+
+// fixed-order mean over the batch of per-sample losses: one block per group
+__global__ void mean_kernel(const float *per_sample, float *loss, int B) {
+    __shared__ float part[256];
+    const int g = blockIdx.x;
+    float s = 0.0f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) s = __fadd_rn(s, per_sample[(size_t)g * B + b]);
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) part[threadIdx.x] = __fadd_rn(part[threadIdx.x], part[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[g] = __fdiv_rn(part[0], (float)B);
+}
+
+// DQN TD target + MSE (da3_brain.py:69-87): one thread per (group, sample)
+__global__ void dqn_loss_kernel(const float *q, const float *qn, const int32_t *act, const float *rew, const uint8_t *done,
+                                float gamma, int B, int A, float *dq, float *per_sample) {
+    const int g = blockIdx.y, b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const size_t i = (size_t)g * B + b;
+    const float *qs = q + i * A, *qt = qn + i * A;
+    float v = qt[0];
+    for (int a = 1; a < A; ++a) v = fmaxf(v, qt[a]);
+    const bool d = done[i] != 0;
+    if (d) v = 0.0f;
+    const float y = __fadd_rn(rew[i], __fmul_rn(__fmul_rn(gamma, d ? 0.0f : 1.0f), v));
+    const int a_taken = act[i];
+    const float diff = __fadd_rn(qs[a_taken], -y);
+    per_sample[i] = __fmul_rn(diff, diff);
+    for (int a = 0; a < A; ++a) dq[i * A + a] = (a == a_taken) ? __fdiv_rn(__fmul_rn(2.0f, diff), (float)B) : 0.0f;
+}
+
+// Distributional heads share the dueling combination  out[a][j] = V[j] + A[a][j] - mean_a A[a][j]
+// (categorical_dqn.py:60-63, qr_dqn.py:46-53).  One WARP per (group, sample); lanes stride over atoms.
+constexpr int kMaxAtomsPerLane = 4;  // up to 128 atoms / quantiles
+constexpr int kMaxActions = 8;
+
+struct DistArgs {
+    const float *v_s, *a_s;    // online(s):   V [G][B][Z], A [G][B][A*Z]
+    const float *v_n, *a_n;    // online(s'):  double-DQN action selection
+    const float *v_t, *a_t;    // target(s')
+    const int32_t *act;
+    const float *rew;
+    const float *support;      // C51: z_j ; QR: tau_hat_j
+    float *dv, *da;            // gradients w.r.t. raw head outputs of online(s)
+    float *per_sample;
+    int B, A, Z;
+    float gamma, v_min, v_max, delta_z;
+};
+
+__device__ __forceinline__ float dueling(const float *v, const float *adv, int A, int Z, int a, int j) {
+    float s = 0.0f;
+    for (int k = 0; k < A; ++k) s = __fadd_rn(s, adv[k * Z + j]);
+    const float mean = __fdiv_rn(s, (float)A);
+    return __fadd_rn(v[j], __fadd_rn(adv[a * Z + j], -mean));
+}
+
+// C51 (categorical_dqn_brain.py:51-87)
+__global__ void c51_loss_kernel(const DistArgs p, float *m_scratch) {
+    const int g = blockIdx.y, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= p.B) return;
+    const int A = p.A, Z = p.Z;
+    const size_t i = (size_t)g * p.B + warp;
+    const float *vs = p.v_s + i * Z, *as = p.a_s + i * A * Z;
+    const float *vn = p.v_n + i * Z, *an = p.a_n + i * A * Z;
+    const float *vt = p.v_t + i * Z, *at = p.a_t + i * A * Z;
+    const int a_taken = p.act[i];
+
+    // best action of the ONLINE net on s': argmax_a sum_j softmax(out[a])_j z_j, first maximum wins
+    int best = 0;
+    float best_q = 0.0f;
+    for (int a = 0; a < A; ++a) {
+        float l[kMaxAtomsPerLane], mx = -INFINITY;
+        for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+            const int j = lane + 32 * t;
+            l[t] = j < Z ? dueling(vn, an, A, Z, a, j) : -INFINITY;
+            mx = fmaxf(mx, l[t]);
+        }
+        mx = warp_max(mx);
+        float se = 0.0f, sq = 0.0f;
+        for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+            const int j = lane + 32 * t;
+            if (j < Z) {
+                const float e = expf(__fadd_rn(l[t], -mx));
+                se = __fadd_rn(se, e);
+                sq = __fadd_rn(sq, __fmul_rn(e, p.support[j]));
+            }
+        }
+        se = warp_sum(se);
+        sq = warp_sum(sq);
+        const float qv = __fdiv_rn(sq, se);
+        if (a == 0 || qv > best_q) { best_q = qv; best = a; }
+    }
+    // p' = softmax(target(s')[best])
+    float pt[kMaxAtomsPerLane], mx = -INFINITY;
+    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+        const int j = lane + 32 * t;
+        pt[t] = j < Z ? dueling(vt, at, A, Z, best, j) : -INFINITY;
+        mx = fmaxf(mx, pt[t]);
+    }
+    mx = warp_max(mx);
+    float se = 0.0f;
+    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+        const int j = lane + 32 * t;
+        pt[t] = j < Z ? expf(__fadd_rn(pt[t], -mx)) : 0.0f;
+        se = __fadd_rn(se, pt[t]);
+    }
+    se = warp_sum(se);
+    // projection onto the support: two scatter-adds per atom (index_add_, :80-81) into per-sample scratch
+    float *m = m_scratch + i * Z;
+    for (int j = lane; j < Z; j += 32) m[j] = 0.0f;
+    __syncwarp();
+    const float r = p.rew[i];
+    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+        const int j = lane + 32 * t;
+        if (j >= Z) continue;
+        const float prob = __fdiv_rn(pt[t], se);
+        float tz = __fadd_rn(r, __fmul_rn(p.gamma, p.support[j]));
+        tz = fminf(fmaxf(tz, p.v_min), p.v_max);
+        const float bb = __fdiv_rn(__fadd_rn(tz, -p.v_min), p.delta_z);
+        int lo = (int)floorf(bb), up = (int)ceilf(bb);
+        if (lo == up && lo > 0) lo -= 1;            // :73
+        if (lo == up && up < Z - 1) up += 1;        // :75
+        atomicAdd(&m[lo], __fmul_rn(prob, __fadd_rn((float)up, -bb)));
+        atomicAdd(&m[up], __fmul_rn(prob, __fadd_rn(bb, -(float)lo)));
+    }
+    __syncwarp();
+    // log_softmax(online(s)[a_taken]), loss and its gradient
+    float l[kMaxAtomsPerLane];
+    mx = -INFINITY;
+    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+        const int j = lane + 32 * t;
+        l[t] = j < Z ? dueling(vs, as, A, Z, a_taken, j) : -INFINITY;
+        mx = fmaxf(mx, l[t]);
+    }
+    mx = warp_max(mx);
+    float sum_e = 0.0f;
+    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+        const int j = lane + 32 * t;
+        if (j < Z) sum_e = __fadd_rn(sum_e, expf(__fadd_rn(l[t], -mx)));
+    }
+    sum_e = warp_sum(sum_e);
+    const float lse = __fadd_rn(mx, logf(sum_e));
+    float loss = 0.0f, msum = 0.0f;
+    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+        const int j = lane + 32 * t;
+        if (j < Z) {
+            loss = __fadd_rn(loss, __fmul_rn(m[j], __fadd_rn(l[t], -lse)));
+            msum = __fadd_rn(msum, m[j]);
+        }
+    }
+    loss = warp_sum(loss);
+    msum = warp_sum(msum);
+    if (lane == 0) p.per_sample[i] = -loss;
+    const float invB = __fdiv_rn(1.0f, (float)p.B);
+    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+        const int j = lane + 32 * t;
+        if (j >= Z) continue;
+        const float sm = expf(__fadd_rn(l[t], -lse));
+        const float gl = __fmul_rn(__fadd_rn(__fmul_rn(sm, msum), -m[j]), invB);  // d loss / d out[a_taken][j]
+        p.dv[i * Z + j] = gl;
+        const float shared = __fdiv_rn(gl, (float)A);
+        for (int k = 0; k < A; ++k)
+            p.da[i * A * Z + k * Z + j] = __fadd_rn(k == a_taken ? gl : 0.0f, -shared);
+    }
+}
+
+// QR-DQN (qr_dqn_brain.py:23-51,91-117): element-wise quantile Huber, kappa = 1
+__global__ void qr_loss_kernel(const DistArgs p) {
+    const int g = blockIdx.y, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= p.B) return;
+    const int A = p.A, Z = p.Z;
+    const size_t i = (size_t)g * p.B + warp;
+    const float *vs = p.v_s + i * Z, *as = p.a_s + i * A * Z;
+    const float *vn = p.v_n + i * Z, *an = p.a_n + i * A * Z;
+    const float *vt = p.v_t + i * Z, *at = p.a_t + i * A * Z;
+    const int a_taken = p.act[i];
+    int best = 0;
+    float best_q = 0.0f;
+    for (int a = 0; a < A; ++a) {  // argmax_a mean_j quantiles(s')[a][j] of the online net
+        float s = 0.0f;
+        for (int j = lane; j < Z; j += 32) s = __fadd_rn(s, dueling(vn, an, A, Z, a, j));
+        s = __fdiv_rn(warp_sum(s), (float)Z);
+        if (a == 0 || s > best_q) { best_q = s; best = a; }
+    }
+    const float r = p.rew[i], invB = __fdiv_rn(1.0f, (float)p.B);
+    float loss = 0.0f;
+    for (int j = lane; j < Z; j += 32) {
+        const float target = __fadd_rn(r, __fmul_rn(p.gamma, dueling(vt, at, A, Z, best, j)));
+        const float theta = dueling(vs, as, A, Z, a_taken, j);
+        const float delta = __fadd_rn(target, -theta);
+        const float ad = fabsf(delta);
+        const float huber = ad <= 1.0f ? __fmul_rn(0.5f, __fmul_rn(delta, delta)) : __fadd_rn(ad, -0.5f);
+        const float w = fabsf(__fadd_rn(p.support[j], delta < 0.0f ? -1.0f : 0.0f));
+        loss = __fadd_rn(loss, __fmul_rn(w, huber));
+        const float dh = ad <= 1.0f ? delta : (delta > 0.0f ? 1.0f : -1.0f);
+        const float gl = __fmul_rn(-__fmul_rn(w, dh), invB);  // d loss / d theta_j
+        p.dv[i * Z + j] = gl;
+        const float shared = __fdiv_rn(gl, (float)A);
+        for (int k = 0; k < A; ++k)
+            p.da[i * A * Z + k * Z + j] = __fadd_rn(k == a_taken ? gl : 0.0f, -shared);
+    }
+    loss = warp_sum(loss);
+    if (lane == 0) p.per_sample[i] = loss;
+}
+
+// greedy-policy values Q[g][b][a] from raw head outputs (get_action of the brains)
+__global__ void dist_q_kernel(const float *v, const float *adv, const float *support, int B, int Bmax, int A, int Z,
+                              int categorical, float *q) {
+    const int g = blockIdx.y, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const size_t i = (size_t)g * Bmax + warp;  // head outputs are strided by the maximum batch
+    for (int a = 0; a < A; ++a) {
+        float out;
+        if (categorical) {
+            float mx = -INFINITY;
+            for (int j = lane; j < Z; j += 32) mx = fmaxf(mx, dueling(v + i * Z, adv + i * A * Z, A, Z, a, j));
+            mx = warp_max(mx);
+            float se = 0.0f, sq = 0.0f;
+            for (int j = lane; j < Z; j += 32) {
+                const float e = expf(__fadd_rn(dueling(v + i * Z, adv + i * A * Z, A, Z, a, j), -mx));
+                se = __fadd_rn(se, e);
+                sq = __fadd_rn(sq, __fmul_rn(e, support[j]));
+            }
+            out = __fdiv_rn(warp_sum(sq), warp_sum(se));
+        } else {
+            float s = 0.0f;
+            for (int j = lane; j < Z; j += 32) s = __fadd_rn(s, dueling(v + i * Z, adv + i * A * Z, A, Z, a, j));
+            out = __fdiv_rn(warp_sum(s), (float)Z);
+        }
+        if (lane == 0) q[((size_t)g * B + warp) * A + a] = out;
+    }
+}
+
+// ------------------------------------------------------------------------------ optimizer
+// stage 1: per-block partial sums of squares (fixed order); stage 2 inside the apply kernel
+__global__ void sqnorm_partial_kernel(const float *grads, float *partial, long long P, float scale) {
+    __shared__ float part[256];
+    const int g = blockIdx.y;
+    const float *x = grads + (size_t)g * P;
+    float s = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        const float v = __fmul_rn(x[i], scale);
+        s = __fadd_rn(s, __fmul_rn(v, v));
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) part[threadIdx.x] = __fadd_rn(part[threadIdx.x], part[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)g * gridDim.x + blockIdx.x] = part[0];
+}
+
+// nn.utils.clip_grad_norm_(max_norm) + optim.RMSprop(lr, alpha, eps).step()  (optimizers/__init__.py:28-33)
+__global__ void clip_rmsprop_kernel(float *params, const float *grads, float *sq, const float *partial, int nparts,
+                                    long long P, float scale, float max_norm, float lr, float alpha, float one_minus_alpha, float eps,
+                                    const uint8_t *active, float *norm_out) {
+    const int g = blockIdx.y;
+    if (active && !active[g]) return;
+    float total = 0.0f;
+    for (int i = 0; i < nparts; ++i) total = __fadd_rn(total, partial[(size_t)g * nparts + i]);
+    const float norm = sqrtf(total);
+    const float coef = fminf(__fdiv_rn(max_norm, __fadd_rn(norm, 1e-6f)), 1.0f);
+    if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) norm_out[g] = norm;
+    float *p = params + (size_t)g * P, *s = sq + (size_t)g * P;
+    const float *gr = grads + (size_t)g * P;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = __fmul_rn(__fmul_rn(gr[i], scale), coef);
+        const float v = __fadd_rn(__fmul_rn(s[i], alpha), __fmul_rn(__fmul_rn(one_minus_alpha, gi), gi));
+        s[i] = v;
+        const float avg = __fadd_rn(sqrtf(v), eps);
+        p[i] = __fadd_rn(p[i], -__fmul_rn(lr, __fdiv_rn(gi, avg)));
+    }
+}
+
+}  // namespace maexp
+
+using namespace maexp;
+
+// --------------------------------------------------------------------------------- handle
+struct ParamEntry {
+    std::string name;
+    long long offset, count;
+};
+struct HeadLayout {
+    long long w1, b1, w2, b2;
+    int out;
+};
+
+struct maexp_learner {
+    maexp_learner_cfg cfg;
+    int G, B, C, V, A, H, F1, F2, Z, D;  // D = flattened conv output (or C*V*V for the plain MLP)
+    int H1, Hp, H2;                      // conv1 out side, pooled side, conv2 out side
+    bool has_conv, dist;
+    long long P;                         // parameters per agent
+    long long o_c1w, o_c1b, o_c2w, o_c2b;
+    std::vector<HeadLayout> heads;
+    std::vector<ParamEntry> table;
+    std::vector<void *> allocs;
+    float *online = nullptr, *target = nullptr, *grads = nullptr, *sq = nullptr;
+    float *support = nullptr;
+    // activations of the three passes (0: online(s) kept for backward, 1: online(s'), 2: target(s'))
+    struct Acts {
+        float *col1, *y1, *p, *col2, *y2, *flat, *h[2], *out[2];
+        uint8_t *arg;
+    } acts[3];
+    // backward workspace
+    float *d_out[2], *d_h, *d_flat, *d_y2, *d_col2, *d_p, *d_y1, *per_sample, *m_scratch, *partial, *q_tmp;
+    int nparts;
+};
+
+namespace {
+
+template <typename T>
+int lalloc(maexp_learner *h, T **ptr, size_t count) {
+    void *d = nullptr;
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    MAEXP_CUDA_L(cudaMalloc(&d, bytes));
+    MAEXP_CUDA_L(cudaMemset(d, 0, bytes));
+    h->allocs.push_back(d);
+    *ptr = static_cast<T *>(d);
+    return 0;
+}
+
+inline dim3 grid1d(long long total, int g, int threads = 256, int cap = 1024) {
+    long long blocks = (total + threads - 1) / threads;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return dim3((unsigned)blocks, (unsigned)g);
+}
+
+void gemm(cudaStream_t st, int G, const float *A, const float *Bm, float *C, const float *bias, int M, int N, int K,
+          long long sam, long long sak, long long sbk, long long sbn, long long scm, long long scn, long long gA,
+          long long gB, long long gC, long long gBias, int relu = 0, int accumulate = 0, const float *aux = nullptr,
+          long long gAux = 0) {
+    GemmArgs a;
+    a.A = A; a.B = Bm; a.C = C; a.bias = bias; a.aux = aux;
+    a.M = M; a.N = N; a.K = K;
+    a.sam = sam; a.sak = sak; a.sbk = sbk; a.sbn = sbn; a.scm = scm; a.scn = scn;
+    a.gA = gA; a.gB = gB; a.gC = gC; a.gBias = gBias; a.gAux = gAux;
+    a.relu = relu; a.accumulate = accumulate; a.mask_aux = aux != nullptr;
+    dim3 grid((N + kTile - 1) / kTile, (M + kTile - 1) / kTile, G);
+    gemm_kernel<<<grid, 256, 0, st>>>(a);
+}
+
+// forward of one network for all groups; obs [G][B][obs_stride] (C*V*V valid floats per row)
+void forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, maexp_learner::Acts &a) {
+    const int G = h->G, C = h->C, V = h->V, F1 = h->F1, F2 = h->F2, H = h->H, D = h->D;
+    const long long P = h->P, Bmax = h->B, stride = h->cfg.obs_stride;
+    const float *head_in = obs;
+    long long head_in_row = stride, head_in_g = (long long)B * stride;
+    if (h->has_conv) {
+        const int H1 = h->H1, Hp = h->Hp, H2 = h->H2;
+        const long long gcol1 = Bmax * H1 * H1 * C * 4, gy1 = Bmax * H1 * H1 * F1, gp = Bmax * Hp * Hp * F1;
+        const long long gcol2 = Bmax * H2 * H2 * F1 * 4, gy2 = Bmax * H2 * H2 * F2;
+        im2col_kernel<<<grid1d((long long)B * H1 * H1 * C * 4, G), 256, 0, st>>>(
+            obs, a.col1, B, C, H1, H1, stride, (long long)V * V, V, 1, (long long)B * stride, gcol1);
+        gemm(st, G, a.col1, params + h->o_c1w, a.y1, params + h->o_c1b, B * H1 * H1, F1, C * 4, C * 4, 1, 1, C * 4, F1, 1,
+             gcol1, P, gy1, P);
+        pool_fwd_kernel<<<grid1d((long long)B * Hp * Hp * F1, G), 256, 0, st>>>(a.y1, a.p, a.arg, B, H1, H1, F1, gy1, gp);
+        im2col_kernel<<<grid1d((long long)B * H2 * H2 * F1 * 4, G), 256, 0, st>>>(
+            a.p, a.col2, B, F1, H2, H2, (long long)Hp * Hp * F1, 1, (long long)Hp * F1, F1, gp, gcol2);
+        gemm(st, G, a.col2, params + h->o_c2w, a.y2, params + h->o_c2b, B * H2 * H2, F2, F1 * 4, F1 * 4, 1, 1, F1 * 4, F2,
+             1, gcol2, P, gy2, P);
+        nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, st>>>(a.y2, a.flat, B, H2 * H2, F2, gy2, 0);
+        head_in = a.flat;
+        head_in_row = D;
+        head_in_g = gy2;
+    }
+    for (size_t k = 0; k < h->heads.size(); ++k) {
+        const HeadLayout &hd = h->heads[k];
+        gemm(st, G, head_in, params + hd.w1, a.h[k], params + hd.b1, B, H, D, head_in_row, 1, 1, D, H, 1, head_in_g, P,
+             Bmax * H, P, /*relu=*/1);
+        gemm(st, G, a.h[k], params + hd.w2, a.out[k], params + hd.b2, B, hd.out, H, H, 1, 1, H, hd.out, 1, Bmax * H, P,
+             Bmax * hd.out, P);
+    }
+}
+
+// backward of the online net through the activations of pass 0; d_out[k] already filled
+void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
+    const int G = h->G, B = h->B, C = h->C, F1 = h->F1, F2 = h->F2, H = h->H, D = h->D;
+    const long long P = h->P, stride = h->cfg.obs_stride;
+    maexp_learner::Acts &a = h->acts[0];
+    const float *head_in = h->has_conv ? a.flat : obs;
+    const long long head_in_row = h->has_conv ? D : stride, head_in_g = h->has_conv ? (long long)B * D : (long long)B * stride;
+    for (size_t k = 0; k < h->heads.size(); ++k) {
+        const HeadLayout &hd = h->heads[k];
+        const int O = hd.out;
+        // dW2[O,H] = dOut^T h ; db2 ; dh = (dOut W2) * (h > 0)
+        gemm(st, G, h->d_out[k], a.h[k], h->grads + hd.w2, nullptr, O, H, B, 1, O, H, 1, H, 1, (long long)B * O,
+             (long long)B * H, P, 0);
+        colsum_kernel<<<dim3((O * 32 + 255) / 256, G), 256, 0, st>>>(h->d_out[k], h->grads + hd.b2, B, O, (long long)B * O, P);
+        gemm(st, G, h->d_out[k], h->online + hd.w2, h->d_h, nullptr, B, H, O, O, 1, H, 1, H, 1, (long long)B * O, P,
+             (long long)B * H, 0, 0, 0, a.h[k], (long long)B * H);
+        // dW1[H,D] = dh^T x ; db1 ; dflat (+)= dh W1
+        gemm(st, G, h->d_h, head_in, h->grads + hd.w1, nullptr, H, D, B, 1, H, head_in_row, 1, D, 1, (long long)B * H,
+             head_in_g, P, 0);
+        colsum_kernel<<<dim3((H * 32 + 255) / 256, G), 256, 0, st>>>(h->d_h, h->grads + hd.b1, B, H, (long long)B * H, P);
+        if (h->has_conv)
+            gemm(st, G, h->d_h, h->online + hd.w1, h->d_flat, nullptr, B, D, H, H, 1, D, 1, D, 1, (long long)B * H, P,
+                 (long long)B * D, 0, 0, /*accumulate=*/k > 0);
+    }
+    if (!h->has_conv) return;
+    const int H1 = h->H1, Hp = h->Hp, H2 = h->H2;
+    const long long gcol1 = (long long)B * H1 * H1 * C * 4, gy1 = (long long)B * H1 * H1 * F1, gp = (long long)B * Hp * Hp * F1;
+    const long long gcol2 = (long long)B * H2 * H2 * F1 * 4, gy2 = (long long)B * H2 * H2 * F2;
+    nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, st>>>(h->d_flat, h->d_y2, B, H2 * H2, F2, gy2, 1);
+    const int M2 = B * H2 * H2;
+    gemm(st, G, h->d_y2, a.col2, h->grads + h->o_c2w, nullptr, F2, F1 * 4, M2, 1, F2, F1 * 4, 1, F1 * 4, 1, gy2, gcol2, P, 0);
+    colsum_kernel<<<dim3((F2 * 32 + 255) / 256, G), 256, 0, st>>>(h->d_y2, h->grads + h->o_c2b, M2, F2, gy2, P);
+    gemm(st, G, h->d_y2, h->online + h->o_c2w, h->d_col2, nullptr, M2, F1 * 4, F2, F2, 1, F1 * 4, 1, F1 * 4, 1, gy2, P,
+         gcol2, 0);
+    col2im_kernel<<<grid1d((long long)B * Hp * Hp * F1, G), 256, 0, st>>>(h->d_col2, h->d_p, B, Hp, Hp, F1, gcol2, gp);
+    pool_bwd_kernel<<<grid1d((long long)B * H1 * H1 * F1, G), 256, 0, st>>>(h->d_p, a.arg, h->d_y1, B, H1, H1, F1, gy1, gp);
+    const int M1 = B * H1 * H1;
+    gemm(st, G, h->d_y1, a.col1, h->grads + h->o_c1w, nullptr, F1, C * 4, M1, 1, F1, C * 4, 1, C * 4, 1, gy1, gcol1, P, 0);
+    colsum_kernel<<<dim3((F1 * 32 + 255) / 256, G), 256, 0, st>>>(h->d_y1, h->grads + h->o_c1b, M1, F1, gy1, P);
+}
+
+}  // namespace
+
+extern "C" {
+
+int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
+    if (!cfg || !out) return fail("maexp_learner_create: null argument");
+    if (cfg->kind < MAEXP_LEARNER_DQN_CONV_MLP || cfg->kind > MAEXP_LEARNER_DQN_MLP)
+        return fail("maexp_learner_create: unknown kind");
+    if (cfg->num_agents < 1 || cfg->batch_size < 1) return fail("maexp_learner_create: bad num_agents / batch_size");
+    if (cfg->num_actions < 1 || cfg->num_actions > kMaxActions) return fail("maexp_learner_create: num_actions must be in 1..8");
+    maexp_learner *h = new maexp_learner();
+    h->cfg = *cfg;
+    h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
+    h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;
+    h->has_conv = cfg->kind != MAEXP_LEARNER_DQN_MLP;
+    h->dist = cfg->kind == MAEXP_LEARNER_C51 || cfg->kind == MAEXP_LEARNER_QR;
+    h->Z = h->dist ? cfg->num_atoms : 1;
+    if (h->dist && (h->Z < 1 || h->Z > 32 * kMaxAtomsPerLane)) { delete h; return fail("maexp_learner_create: num_atoms must be in 1..128"); }
+    if (cfg->obs_stride < h->C * h->V * h->V) { delete h; return fail("maexp_learner_create: obs_stride < C*V*V"); }
+    long long off = 0;
+    auto add = [&](const std::string &name, long long count) {
+        h->table.push_back({name, off, count});
+        const long long o = off;
+        off += count;
+        return o;
+    };
+    if (h->has_conv) {
+        h->H1 = h->V - 1; h->Hp = h->H1 / 2; h->H2 = h->Hp - 1;
+        if (h->H2 < 1) { delete h; return fail("maexp_learner_create: visible_range too small for the conv trunk"); }
+        h->D = h->F2 * h->H2 * h->H2;
+        // state_dict order of convolution.py:21-42
+        h->o_c1w = add("conv.conv_list.0.weight", (long long)h->F1 * h->C * 4);
+        h->o_c1b = add("conv.conv_list.0.bias", h->F1);
+        h->o_c2w = add("conv.conv_post.weight", (long long)h->F2 * h->F1 * 4);
+        h->o_c2b = add("conv.conv_post.bias", h->F2);
+    } else {
+        h->H1 = h->Hp = h->H2 = 0;
+        h->D = h->C * h->V * h->V;
+    }
+    auto add_head = [&](const std::string &prefix, int outn) {
+        HeadLayout hd;
+        hd.w1 = add(prefix + ".fc_list.0.weight", (long long)h->H * h->D);
+        hd.b1 = add(prefix + ".fc_list.0.bias", h->H);
+        hd.w2 = add(prefix + ".fc_post.weight", (long long)outn * h->H);
+        hd.b2 = add(prefix + ".fc_post.bias", outn);
+        hd.out = outn;
+        h->heads.push_back(hd);
+    };
+    if (h->dist) {
+        add_head("fc_V", h->Z);           // categorical_dqn.py:47-52, qr_dqn.py:37-42
+        add_head("fc_A", h->A * h->Z);
+    } else if (h->has_conv) {
+        add_head("mlp", h->A);            // conv_mlp.py:41
+    } else {
+        add_head("", h->A);               // mlp.py:19-26 (flattened observation)
+        for (auto &e : h->table) e.name = e.name.substr(1);
+    }
+    h->P = off;
+    const long long G = h->G, B = h->B, P = h->P;
+    int rc = 0;
+    rc |= lalloc(h, &h->online, G * P);
+    rc |= lalloc(h, &h->target, G * P);
+    rc |= lalloc(h, &h->grads, G * P);
+    rc |= lalloc(h, &h->sq, G * P);
+    rc |= lalloc(h, &h->support, 128);
+    for (int k = 0; k < 3; ++k) {
+        maexp_learner::Acts &a = h->acts[k];
+        memset(&a, 0, sizeof(a));
+        if (h->has_conv) {
+            rc |= lalloc(h, &a.col1, G * B * h->H1 * h->H1 * h->C * 4);
+            rc |= lalloc(h, &a.y1, G * B * h->H1 * h->H1 * h->F1);
+            rc |= lalloc(h, &a.p, G * B * h->Hp * h->Hp * h->F1);
+            rc |= lalloc(h, &a.arg, G * B * h->Hp * h->Hp * h->F1);
+            rc |= lalloc(h, &a.col2, G * B * h->H2 * h->H2 * h->F1 * 4);
+            rc |= lalloc(h, &a.y2, G * B * h->D);
+            rc |= lalloc(h, &a.flat, G * B * h->D);
+        }
+        for (size_t j = 0; j < h->heads.size(); ++j) {
+            rc |= lalloc(h, &a.h[j], G * B * h->H);
+            rc |= lalloc(h, &a.out[j], G * B * h->heads[j].out);
+        }
+    }
+    for (size_t j = 0; j < h->heads.size(); ++j) rc |= lalloc(h, &h->d_out[j], G * B * h->heads[j].out);
+    rc |= lalloc(h, &h->d_h, G * B * h->H);
+    if (h->has_conv) {
+        rc |= lalloc(h, &h->d_flat, G * B * h->D);
+        rc |= lalloc(h, &h->d_y2, G * B * h->D);
+        rc |= lalloc(h, &h->d_col2, G * B * h->H2 * h->H2 * h->F1 * 4);
+        rc |= lalloc(h, &h->d_p, G * B * h->Hp * h->Hp * h->F1);
+        rc |= lalloc(h, &h->d_y1, G * B * h->H1 * h->H1 * h->F1);
+    }
+    rc |= lalloc(h, &h->per_sample, G * B);
+    rc |= lalloc(h, &h->m_scratch, G * B * 128);
+    rc |= lalloc(h, &h->q_tmp, G * B * h->A);
+    h->nparts = 32;
+    rc |= lalloc(h, &h->partial, G * h->nparts);
+    if (rc) { maexp_learner_destroy(h); return -1; }
+    *out = h;
+    return 0;
+}
+
+void maexp_learner_destroy(maexp_learner *h) {
+    if (!h) return;
+    for (void *d : h->allocs) cudaFree(d);
+    delete h;
+}
+
+int64_t maexp_learner_num_params(const maexp_learner *h) { return h ? h->P : -1; }
+int maexp_learner_num_tensors(const maexp_learner *h) { return h ? (int)h->table.size() : -1; }
+int maexp_learner_tensor(const maexp_learner *h, int index, char *name, int name_len, int64_t *offset, int64_t *count) {
+    if (!h || index < 0 || index >= (int)h->table.size()) return fail("maexp_learner_tensor: bad index");
+    const ParamEntry &e = h->table[index];
+    if (name && name_len > 0) {
+        strncpy(name, e.name.c_str(), name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (offset) *offset = e.offset;
+    if (count) *count = e.count;
+    return 0;
+}
+
+float *maexp_learner_buffer(maexp_learner *h, int which) {
+    if (!h) return nullptr;
+    switch (which) {
+    case MAEXP_BUF_ONLINE: return h->online;
+    case MAEXP_BUF_TARGET: return h->target;
+    case MAEXP_BUF_GRADS: return h->grads;
+    case MAEXP_BUF_SQUARE_AVG: return h->sq;
+    case MAEXP_BUF_SUPPORT: return h->support;
+    }
+    return nullptr;
+}
+
+int maexp_learner_sync_target(maexp_learner *h, void *stream) {
+    if (!h) return fail("maexp_learner_sync_target: null handle");
+    MAEXP_CUDA_L(cudaMemcpyAsync(h->target, h->online, sizeof(float) * h->G * h->P, cudaMemcpyDeviceToDevice,
+                                 static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int use_target, float *q_out, void *stream) {
+    if (!h || !obs || !q_out) return fail("maexp_learner_q_values: null argument");
+    if (batch < 1 || batch > h->B) return fail("maexp_learner_q_values: batch must be in 1..batch_size");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    maexp_learner::Acts &a = h->acts[1];
+    forward(h, st, use_target ? h->target : h->online, obs, batch, a);
+    if (!h->dist) {
+        // heads are strided by the maximum batch: compact to [G][batch][A]
+        MAEXP_CUDA_L(cudaMemcpy2DAsync(q_out, sizeof(float) * batch * h->A, a.out[0], sizeof(float) * h->B * h->A,
+                                       sizeof(float) * batch * h->A, h->G, cudaMemcpyDeviceToDevice, st));
+    } else {
+        dist_q_kernel<<<dim3((batch * 32 + 255) / 256, h->G), 256, 0, st>>>(a.out[0], a.out[1], h->support, batch, h->B, h->A,
+                                                                            h->Z, h->cfg.kind == MAEXP_LEARNER_C51, q_out);
+    }
+    MAEXP_CUDA_L(cudaGetLastError());
+    return 0;
+}
+
+int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_obs, const int32_t *actions,
+                        const float *rewards, const uint8_t *dones, float *loss_out, void *stream) {
+    if (!h || !obs || !next_obs || !actions || !rewards || !dones) return fail("maexp_learner_grads: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int G = h->G, B = h->B, A = h->A, Z = h->Z;
+    forward(h, st, h->online, obs, B, h->acts[0]);
+    forward(h, st, h->target, next_obs, B, h->acts[2]);
+    if (!h->dist) {
+        dqn_loss_kernel<<<dim3((B + 127) / 128, G), 128, 0, st>>>(h->acts[0].out[0], h->acts[2].out[0], actions, rewards,
+                                                                  dones, h->cfg.gamma, B, A, h->d_out[0], h->per_sample);
+    } else {
+        forward(h, st, h->online, next_obs, B, h->acts[1]);  // double-DQN action selection by the online net
+        DistArgs p;
+        p.v_s = h->acts[0].out[0]; p.a_s = h->acts[0].out[1];
+        p.v_n = h->acts[1].out[0]; p.a_n = h->acts[1].out[1];
+        p.v_t = h->acts[2].out[0]; p.a_t = h->acts[2].out[1];
+        p.act = actions; p.rew = rewards; p.support = h->support;
+        p.dv = h->d_out[0]; p.da = h->d_out[1]; p.per_sample = h->per_sample;
+        p.B = B; p.A = A; p.Z = Z;
+        p.gamma = h->cfg.gamma; p.v_min = h->cfg.v_min; p.v_max = h->cfg.v_max; p.delta_z = h->cfg.delta_z;
+        const dim3 grid((B * 32 + 255) / 256, G);
+        if (h->cfg.kind == MAEXP_LEARNER_C51) c51_loss_kernel<<<grid, 256, 0, st>>>(p, h->m_scratch);
+        else qr_loss_kernel<<<grid, 256, 0, st>>>(p);
+    }
+    mean_kernel<<<G, 256, 0, st>>>(h->per_sample, loss_out ? loss_out : h->q_tmp, B);
+    backward(h, st, obs);
+    MAEXP_CUDA_L(cudaGetLastError());
+    return 0;
+}
+
+int maexp_learner_apply(maexp_learner *h, float grad_scale, const uint8_t *active, float *grad_norm_out, void *stream) {
+    if (!h) return fail("maexp_learner_apply: null handle");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    sqnorm_partial_kernel<<<dim3(h->nparts, h->G), 256, 0, st>>>(h->grads, h->partial, h->P, grad_scale);
+    clip_rmsprop_kernel<<<dim3(64, h->G), 256, 0, st>>>(h->online, h->grads, h->sq, h->partial, h->nparts, h->P, grad_scale,
+                                                        h->cfg.max_norm, h->cfg.learning_rate, h->cfg.alpha, h->cfg.one_minus_alpha, h->cfg.eps,
+                                                        active, grad_norm_out);
+    MAEXP_CUDA_L(cudaGetLastError());
+    return 0;
+}
+
+int maexp_learner_update(maexp_learner *h, const float *obs, const float *next_obs, const int32_t *actions,
+                         const float *rewards, const uint8_t *dones, float *loss_out, void *stream) {
+    if (maexp_learner_grads(h, obs, next_obs, actions, rewards, dones, loss_out, stream)) return -1;
+    return maexp_learner_apply(h, 1.0f, nullptr, nullptr, stream);
+}
+
+}  // extern "C"

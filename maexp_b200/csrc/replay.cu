@@ -1,0 +1,84 @@
+// Fused replay sampling + gather on the device-resident ring (sm_100a).
+//
+// Replaces ReplayBuffer.sample + RLDataset.__iter__ + DataLoader default collate
+// (core/utils/buffer.py:60-63, core/utils/dataset.py:24-29, abstract_trainer.py:93-97): one launch
+// picks `batch` whole-team transitions and writes the per-agent batches the learner consumes.
+// One warp per (sample, agent): the pick is recomputed per warp (a few Philox calls) so that no
+// second launch or index buffer is needed; rows are moved with 128-bit loads/stores.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/maexp_b200.h"
+#include "philox.cuh"
+
+namespace maexp {
+int fail(const std::string &msg);
+
+constexpr uint32_t kStreamReplay = 7;
+constexpr int kMaxRedraws = 64;
+
+__global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint32_t seed, uint32_t tick,
+                                     const int32_t *indices, const maexp_batch out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int N = r.num_agents;
+    if (warp >= batch * N) return;
+    const int b = warp / N, agent = warp - b * N;
+    int slot, env;
+    if (indices) {
+        slot = indices[2 * b];
+        env = indices[2 * b + 1];
+    } else {
+        // transition age a in [0, count-2]: state slot = head-1-a, next slot = head-a (mod S)
+        uint32_t d = 0;
+        for (;;) {
+            const uint4 w = philox4x32_10(seed, 0x52504C59u /*'RPLY'*/, tick, kStreamReplay, d, (uint32_t)b);
+            const int age = (int)scale(w.x, (uint32_t)(r.count - 1));
+            env = (int)scale(w.y, (uint32_t)r.num_envs);
+            slot = (r.head - 1 - age) % r.num_slots;
+            if (slot < 0) slot += r.num_slots;
+            const int nxt = (slot + 1) % r.num_slots;
+            if (!r.was_reset[(size_t)nxt * r.num_envs + env] || ++d >= (uint32_t)kMaxRedraws) break;
+        }
+    }
+    const int nxt = (slot + 1) % r.num_slots;
+    const size_t row = (size_t)r.num_envs * N * r.slot_floats;
+    const float4 *s0 = reinterpret_cast<const float4 *>(r.obs + (size_t)slot * row + ((size_t)env * N + agent) * r.slot_floats);
+    const float4 *s1 = reinterpret_cast<const float4 *>(r.obs + (size_t)nxt * row + ((size_t)env * N + agent) * r.slot_floats);
+    const size_t orow = ((size_t)agent * batch + b) * r.slot_floats;
+    float4 *d0 = reinterpret_cast<float4 *>(out.obs + orow), *d1 = reinterpret_cast<float4 *>(out.next_obs + orow);
+    for (int q = lane; q < r.slot_floats / 4; q += 32) {
+        d0[q] = __ldg(s0 + q);
+        d1[q] = __ldg(s1 + q);
+    }
+    if (lane == 0) {
+        const size_t m = ((size_t)nxt * r.num_envs + env) * N + agent, o = (size_t)agent * batch + b;
+        out.actions[o] = r.actions[m];
+        out.rewards[o] = r.rewards[m];
+        out.dones[o] = r.dones[m];
+        if (out.picked && agent == 0) {
+            out.picked[2 * b] = slot;
+            out.picked[2 * b + 1] = env;
+        }
+    }
+}
+}  // namespace maexp
+
+extern "C" int maexp_replay_sample(const maexp_replay_view *ring, int32_t batch, uint32_t seed, uint32_t tick,
+                                   const int32_t *indices, const maexp_batch *out, void *stream) {
+    using namespace maexp;
+    if (!ring || !out) return fail("maexp_replay_sample: null argument");
+    if (batch < 1) return fail("maexp_replay_sample: batch < 1");
+    if (!indices && ring->count < 2) return fail("maexp_replay_sample: the ring holds fewer than 2 slots");
+    if (ring->slot_floats % 4) return fail("maexp_replay_sample: slot_floats must be a multiple of 4");
+    if (!ring->obs || !ring->actions || !ring->rewards || !ring->dones || !ring->was_reset || !out->obs ||
+        !out->next_obs || !out->actions || !out->rewards || !out->dones)
+        return fail("maexp_replay_sample: null buffer");
+    const int warps = batch * ring->num_agents;
+    replay_sample_kernel<<<(warps * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(*ring, batch, seed, tick,
+                                                                                                 indices, *out);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("maexp_replay_sample: ") + cudaGetErrorString(e));
+    return 0;
+}

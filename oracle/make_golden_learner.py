@@ -1,0 +1,81 @@
+"""Writes tests/golden/learner_<brain>.npz from the LIVE reference brains (build container only).
+
+    python -m oracle.make_golden_learner
+
+For each brain: initial state_dict, a synthetic batch, the loss `brain.learn` returned, the
+network's Q-values before the update and the online weights after 2 updates.  TEST INFRASTRUCTURE.
+"""
+import os
+
+import numpy as np
+import torch
+
+from maexp_b200.config import baseline_config, make_config
+from oracle import ref_runner as rr
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+B = 32
+
+
+def configs():
+    c5, c3, c2 = baseline_config(5), baseline_config(3), baseline_config(2)
+    # the DQN that runs in shipped experiments is DA3BaselineBrain + ConvMLP; model.num_heads is
+    # only read to size a constant attention placeholder (da3_brain.py:107-113)
+    dqn = c2.merged_with(brain="da3_baseline", batch_size=B, observation_noise=False)
+    dqn["model"] = dict(dqn.model, name="da3_baseline", patch_size=1, num_heads=4)
+    return {"dqn_conv_mlp": (dqn, [7, 7, 7]), "c51": (c5.merged_with(batch_size=B), [3, 7, 7]),
+            "qr": (c3.merged_with(batch_size=B), [3, 7, 7])}
+
+
+def synthetic_batch(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    C, V, _ = shape
+    def obs():
+        x = (torch.rand((B, C, V, V), generator=g) < 0.15).float()
+        x[:, -1] = -(torch.rand((B, V, V), generator=g) < 0.3).float()
+        return x
+    return {"obs": obs(), "next_obs": obs(), "actions": torch.randint(0, 4, (B,), generator=g),
+            "rewards": torch.tensor(np.random.default_rng(seed).choice([-1.0, 0.0, 1.0], size=B, p=[0.2, 0.6, 0.2])),
+            "dones": torch.rand((B,), generator=g) < 0.1}
+
+
+def main():
+    rr._import_reference()
+    from core.agents.brains import generate_brain
+    os.makedirs(GOLDEN, exist_ok=True)
+    for kind, (cfg, shape) in configs().items():
+        torch.manual_seed(921)
+        brain = generate_brain(config=rr.to_dictconfig(cfg), obs_shape=shape, act_size=4)
+        # make the target differ from the online net, as it does between synchronisations
+        with torch.no_grad():
+            for p_ in brain.target_network.parameters():
+                p_.add_(0.01 * torch.randn_like(p_))
+        init = {k: v.detach().clone() for k, v in brain.network.state_dict().items()}
+        tgt = {k: v.detach().clone() for k, v in brain.target_network.state_dict().items()}
+        batch = synthetic_batch(shape, 7)
+        with torch.no_grad():
+            if kind == "c51":
+                from core.agents.models.customs.categorical_dqn import ApplySoftmax
+                q0 = torch.sum(brain.network({"local": batch["obs"].clone()}, ApplySoftmax.NORMAL) * brain.support, dim=2)
+            elif kind == "qr":
+                q0 = brain.network({"local": batch["obs"].clone()}).mean(dim=2)
+            else:
+                q0 = brain.network({"local": batch["obs"].clone()})
+        losses = []
+        for _ in range(2):
+            out = brain.learn({"local": batch["obs"].clone()}, batch["actions"].clone(), batch["rewards"].clone(),
+                              batch["dones"].clone(), {"local": batch["next_obs"].clone()})
+            losses.append(float(out["total_loss"] if isinstance(out, dict) else out))
+        final = {k: v.detach().clone() for k, v in brain.network.state_dict().items()}
+        arrays = {"init/" + k: v.numpy() for k, v in init.items()}
+        arrays.update({"target/" + k: v.numpy() for k, v in tgt.items()})
+        arrays.update({"final/" + k: v.numpy() for k, v in final.items()})
+        arrays.update({"batch/" + k: v.numpy() for k, v in batch.items()})
+        path = os.path.join(GOLDEN, f"learner_{kind}.npz")
+        np.savez_compressed(path, losses=np.array(losses, np.float64), q0=q0.numpy(), shape=np.array(shape),
+                            gamma=float(cfg.gamma), **arrays)
+        print(kind, losses, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

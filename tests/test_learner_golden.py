@@ -1,0 +1,38 @@
+"""Pins the torch fp32 learner oracle (oracle/torch_learner.py) against the live reference brains."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.torch_learner import TorchLearner
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KINDS = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLDEN, "learner_*.npz")))
+ATOMS = {"dqn_conv_mlp": 1, "c51": 51, "qr": 100}
+
+
+def load(kind):
+    z = np.load(os.path.join(GOLDEN, f"learner_{kind}.npz"))
+    part = lambda pre: {k[len(pre):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre)}
+    return {"init": part("init/"), "target": part("target/"), "final": part("final/"), "batch": part("batch/"),
+            "losses": z["losses"], "q0": torch.from_numpy(z["q0"]), "gamma": float(z["gamma"])}
+
+
+def make_oracle(kind, fix):
+    o = TorchLearner(kind, fix["init"], 4, fix["gamma"], 1e-3, 0.99, 1e-8, num_atoms=ATOMS[kind])
+    o.target = {k: v.clone() for k, v in fix["target"].items()}
+    return o
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_torch_oracle_matches_reference_brain(kind):
+    fix = load(kind)
+    o, b = make_oracle(kind, fix), fix["batch"]
+    assert torch.allclose(o.q_values(b["obs"]), fix["q0"], rtol=1e-6, atol=1e-6)
+    for want in fix["losses"]:
+        loss, _ = o.learn(b["obs"], b["next_obs"], b["actions"], b["rewards"], b["dones"])
+        assert abs(float(loss) - want) <= 1e-6 * max(1.0, abs(want)), (float(loss), want)
+    for k, v in fix["final"].items():
+        assert torch.allclose(o.sd[k].detach(), v, rtol=1e-5, atol=1e-6), k

@@ -1,0 +1,200 @@
+"""Parity of the CUDA learner and replay sampler (through the C-ABI).
+
+Tolerance (north_star): losses and Q-values within 1e-5 relative in fp32.  Updated weights are
+checked with a looser bound because RMSprop's first steps normalise every gradient to about
++-lr/sqrt(1-alpha), which amplifies last-bit differences of near-zero gradients.
+"""
+import numpy as np
+import pytest
+import torch
+
+from maexp_b200.config import Config, baseline_config
+from oracle.make_golden_learner import configs as golden_configs
+from oracle.torch_learner import TorchLearner
+from tests.test_learner_golden import ATOMS, KINDS, load
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def make_group(kind, shape, G, B):
+    from maexp_b200.core.agents.brains import LearnerGroup
+    cfg, _ = golden_configs()[kind]
+    return LearnerGroup(cfg.merged_with(batch_size=B), shape, 4, G, B)
+
+
+def pack(group, x):
+    """[G,B,C,V,V] dense -> [G,B,obs_stride] device rows (the replay sampler's layout)."""
+    G, B = x.shape[:2]
+    out = torch.zeros((G, B, group.obs_stride), dtype=torch.float32, device=group.device)
+    out[:, :, : group.K] = x.reshape(G, B, -1).to(group.device)
+    return out
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_cuda_learner_matches_reference_fixture(kind):
+    fix = load(kind)
+    b = fix["batch"]
+    shape = list(b["obs"].shape[1:])
+    g = make_group(kind, shape, 1, b["obs"].shape[0])
+    g.load_state_dict(0, fix["init"])
+    g.load_state_dict(0, fix["target"], which=1)
+    batch = {"obs": pack(g, b["obs"][None]), "next_obs": pack(g, b["next_obs"][None]),
+             "actions": b["actions"].to(torch.int32)[None].contiguous().cuda(),
+             "rewards": b["rewards"].float()[None].contiguous().cuda(),
+             "dones": b["dones"].to(torch.uint8)[None].contiguous().cuda()}
+    q = g.q_values(batch["obs"]).cpu()[0]
+    assert rel_err(q, fix["q0"]) < RTOL
+    for want in fix["losses"]:
+        loss = float(g.learn(batch).cpu()[0])
+        assert abs(loss - want) <= RTOL * abs(want), (loss, want)
+    got = g.state_dict(0)
+    bad = 0
+    total = 0
+    for k, v in fix["final"].items():
+        diff = (got[k] - v).abs()
+        bad += int((diff > 1e-4 + 1e-4 * v.abs()).sum())
+        total += v.numel()
+    assert bad <= total * 1e-3, (bad, total)
+
+
+@pytest.mark.parametrize("kind,B", [("dqn_conv_mlp", 32), ("c51", 256), ("qr", 256)])
+def test_cuda_learner_group_matches_torch_oracle(kind, B):
+    """G independent networks with different weights and batches, BASELINE batch sizes."""
+    G = 3
+    fix = load(kind)
+    shape = list(fix["batch"]["obs"].shape[1:])
+    C, V = shape[0], shape[1]
+    g = make_group(kind, shape, G, B)
+    gen = torch.Generator().manual_seed(11)
+    oracles, batches = [], []
+    for a in range(G):
+        sd = {k: v + 0.02 * torch.randn(v.shape, generator=gen) for k, v in fix["init"].items()}
+        tg = {k: v + 0.02 * torch.randn(v.shape, generator=gen) for k, v in fix["init"].items()}
+        g.load_state_dict(a, sd)
+        g.load_state_dict(a, tg, which=1)
+        o = TorchLearner(kind, sd, 4, fix["gamma"], 1e-3, 0.99, 1e-8, num_atoms=ATOMS[kind])
+        o.target = tg
+        oracles.append(o)
+        obs = (torch.rand((B, C, V, V), generator=gen) < 0.2).float()
+        nxt = (torch.rand((B, C, V, V), generator=gen) < 0.2).float()
+        obs[:, -1] -= 1
+        nxt[:, -1] -= 1
+        batches.append({"obs": obs, "next_obs": nxt, "actions": torch.randint(0, 4, (B,), generator=gen),
+                        "rewards": torch.randint(-1, 2, (B,), generator=gen).double(),
+                        "dones": torch.rand((B,), generator=gen) < 0.1})
+    batch = {"obs": pack(g, torch.stack([b["obs"] for b in batches])),
+             "next_obs": pack(g, torch.stack([b["next_obs"] for b in batches])),
+             "actions": torch.stack([b["actions"] for b in batches]).to(torch.int32).cuda(),
+             "rewards": torch.stack([b["rewards"] for b in batches]).float().cuda(),
+             "dones": torch.stack([b["dones"] for b in batches]).to(torch.uint8).cuda()}
+    q = g.q_values(batch["obs"]).cpu()
+    for a in range(G):
+        assert rel_err(q[a], oracles[a].q_values(batches[a]["obs"])) < RTOL
+    # gradients of the first update, then two full updates
+    loss = g.grads(batch).cpu()
+    grads = g.params(2).cpu()
+    for a in range(G):
+        o, b = oracles[a], batches[a]
+        o.opt.zero_grad()
+        want = o.loss(b["obs"], b["next_obs"], b["actions"], b["rewards"], b["dones"])
+        want.backward()
+        assert abs(float(loss[a]) - float(want.detach())) <= RTOL * abs(float(want.detach()))
+        for name, off, cnt in g.table:
+            ref = o.sd[name].grad.reshape(-1)
+            got = grads[a, off:off + cnt]
+            assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-8, (a, name)
+    for step in range(2):
+        loss = g.learn(batch).cpu()
+        for a in range(G):
+            b = batches[a]
+            want, norm = oracles[a].learn(b["obs"], b["next_obs"], b["actions"], b["rewards"], b["dones"])
+            assert abs(float(loss[a]) - float(want)) <= 2e-5 * abs(float(want)), (step, a, float(loss[a]), float(want))
+            assert abs(float(g.grad_norm.cpu()[a]) - float(norm)) <= 1e-4 * float(norm)
+
+
+def test_apply_scale_and_inactive_agents():
+    """grad_scale (1/world after an all-reduce) and the agent_tasks "-1" mask of abstract_trainer.py:49-51."""
+    kind, B, G = "dqn_conv_mlp", 32, 2
+    fix = load(kind)
+    b = fix["batch"]
+    g = make_group(kind, list(b["obs"].shape[1:]), G, B)
+    for a in range(G):
+        g.load_state_dict(a, fix["init"])
+    g.synchronize()
+    batch = {"obs": pack(g, torch.stack([b["obs"]] * G)), "next_obs": pack(g, torch.stack([b["next_obs"]] * G)),
+             "actions": torch.stack([b["actions"]] * G).to(torch.int32).cuda(),
+             "rewards": torch.stack([b["rewards"]] * G).float().cuda(),
+             "dones": torch.stack([b["dones"]] * G).to(torch.uint8).cuda()}
+    before = g.params().clone()
+    g.grads(batch)
+    g.params(2).mul_(4.0)  # as if four ranks had summed identical gradients
+    g.apply(grad_scale=0.25, active=torch.tensor([1, 0], dtype=torch.uint8, device="cuda"))
+    after = g.params()
+    assert torch.equal(after[1], before[1])  # inactive agent untouched
+    g2 = make_group(kind, list(b["obs"].shape[1:]), 1, B)
+    g2.load_state_dict(0, fix["init"])
+    g2.synchronize()
+    g2.learn({k: v[:1].contiguous() for k, v in batch.items()})
+    assert torch.allclose(after[0], g2.params()[0], rtol=0, atol=1e-7)
+
+
+def test_replay_ring_sampling():
+    from maexp_b200.core.utils.buffer import DeviceReplayRing
+    from tests.cuda_backend import make_env
+    cfg = baseline_config(5).merged_with(max_episode_length=7)
+    E, N, S, B = 48, 8, 16, 64
+    env = make_env(cfg, E, auto_reset=True)
+    ring = DeviceReplayRing(env, S)
+    env.reset(ring.next_outputs(), tick=0)
+    ring.commit()
+    for t in range(1, 23):  # wraps the ring, crosses two auto-resets
+        env.step(ring.next_outputs(), tick=t)
+        ring.commit()
+    assert ring.count == S and len(ring) == (S - 1) * E
+    batch = ring.new_batch(B)
+    # (1) injected picks: exact gather
+    rng = np.random.default_rng(0)
+    picks = np.stack([(ring.head - 1 - rng.integers(0, S - 1, B)) % S, rng.integers(0, E, B)], 1).astype(np.int32)
+    ring.sample(batch, indices=torch.from_numpy(picks).cuda())
+    torch.cuda.synchronize()
+    obs, act, rew, done = ring.obs.cpu(), ring.actions.cpu(), ring.rewards.cpu(), ring.dones.cpu()
+    for j, (s, e) in enumerate(picks):
+        n = (s + 1) % S
+        assert torch.equal(batch["obs"][:, j].cpu(), obs[s, e])
+        assert torch.equal(batch["next_obs"][:, j].cpu(), obs[n, e])
+        assert torch.equal(batch["actions"][:, j].cpu(), act[n, e].to(torch.int32))
+        assert torch.equal(batch["rewards"][:, j].cpu(), rew[n, e]) and torch.equal(batch["dones"][:, j].cpu(), done[n, e])
+    # (2) Philox picks: in range, never a transition into a reset slot, reproducible, tick-dependent
+    ring.sample(batch, seed=921, tick=5)
+    p1 = batch["picked"].cpu().clone()
+    was_reset = ring.was_reset.cpu()
+    ages = (ring.head - 1 - p1[:, 0]) % S
+    assert bool(((ages >= 0) & (ages <= S - 2)).all()) and bool(((p1[:, 1] >= 0) & (p1[:, 1] < E)).all())
+    assert int(was_reset[(p1[:, 0] + 1) % S, p1[:, 1]].sum()) == 0
+    assert bool((batch["actions"].cpu() >= 0).all())  # actions of reset slots are -1 and must never be sampled
+    ring.sample(batch, seed=921, tick=5)
+    assert torch.equal(batch["picked"].cpu(), p1)
+    ring.sample(batch, seed=921, tick=6)
+    assert not torch.equal(batch["picked"].cpu(), p1)
+
+
+def test_reference_style_brain_interface():
+    """generate_brain(...).learn / get_action with the reference's argument structure (E=1 style)."""
+    from maexp_b200.core.agents.brains import generate_brain
+    fix = load("c51")
+    b = fix["batch"]
+    cfg, shape = golden_configs()["c51"]
+    brain = generate_brain(cfg, shape, 4)
+    brain.network.load_state_dict(fix["init"])
+    brain.target_network.load_state_dict(fix["target"])
+    assert brain.get_action({"local": b["obs"][0].clone()}) == int(fix["q0"][0].argmax())
+    out = brain.learn({"local": b["obs"].clone()}, b["actions"].clone(), b["rewards"].clone(), b["dones"].clone(),
+                      {"local": b["next_obs"].clone()})
+    assert abs(float(out["total_loss"]) - fix["losses"][0]) <= RTOL * fix["losses"][0]
+    with pytest.raises(ValueError):
+        generate_brain(cfg.merged_with(brain="nope"), shape, 4)
