@@ -146,11 +146,36 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def learner_cpu_rate(batch_size, steps=8):
+    """updates/s of the torch fp32 restatement of CategoricalDQNBrain.learn on the host cores."""
+    import torch
+
+    from maexp_b200.core.agents.models import build_reference_modules
+    from oracle.torch_learner import TorchLearner
+    cfg = workload_config()
+    torch.manual_seed(0)
+    sd = build_reference_modules(cfg, [3, 7, 7], 4).state_dict()
+    o = TorchLearner("c51", sd, 4, float(cfg.gamma), 1e-3, 0.99, 1e-8, num_atoms=51)
+    B = batch_size
+    obs, nxt = torch.rand(B, 3, 7, 7).round(), torch.rand(B, 3, 7, 7).round()
+    act, rew, done = torch.randint(0, 4, (B,)), torch.randint(-1, 2, (B,)).double(), torch.rand(B) < 0.05
+    for _ in range(2):
+        o.learn(obs, nxt, act, rew, done)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.learn(obs, nxt, act, rew, done)
+    return steps / (time.perf_counter() - t0)
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
 
+    from maexp_b200 import _lib
+    from maexp_b200 import distributed as mdist
+    from maexp_b200.core.agents.brains import LearnerGroup
     from maexp_b200.core.environments.batched import BatchedEnvironment
     from maexp_b200.core.maps import generate_map
+    from maexp_b200.core.utils.buffer import DeviceReplayRing
     from maexp_b200.core.worlds import generate_world
 
     if not torch.cuda.is_available():
@@ -171,30 +196,30 @@ def run_ours(args, rank, local_rank, world):
     cfg = workload_config()
     world_obj = generate_world(cfg, generate_map(cfg))
     # envs are independent units: contiguous global ids per rank, no data-path collective
-    env = BatchedEnvironment(cfg, world_obj, E, device=dev, auto_reset=True, first_global_env_id=rank * E)
-    ring = torch.empty((RING_SLOTS, E, N, env.slot_floats), dtype=torch.float32, device=dev)
-    out = env.new_outputs()
-    outs = []
-    for s in range(RING_SLOTS):
-        o = dict(out)
-        o["obs"] = ring[s]
-        outs.append(o)
+    env = BatchedEnvironment(cfg, world_obj, E, device=dev, auto_reset=True,
+                             first_global_env_id=mdist.first_global_env_id(rank, E))
+    ring = DeviceReplayRing(env, RING_SLOTS)  # obs + actions + rewards + dones + was_reset rings in HBM
     sampler = ClockSampler(local_rank)
     sampler.start()
 
+    def step(tick):
+        env.step(ring.next_outputs(), tick=tick)
+        ring.commit()
+
     tick = 0
-    env.reset(outs[0], tick=tick)
+    env.reset(ring.next_outputs(), tick=tick)
+    ring.commit()
     tick += 1
     sampler.window[0] = time.perf_counter()
     for _ in range(W):
-        env.step(outs[tick % RING_SLOTS], tick=tick)
+        step(tick)
         tick += 1
     before = env.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
     for _ in range(K):
-        env.step(outs[tick % RING_SLOTS], tick=tick)
+        step(tick)
         tick += 1
     ev1.record()
     barrier()
@@ -208,29 +233,67 @@ def run_ours(args, rank, local_rank, world):
     dones = torch.empty((E, N), dtype=torch.uint8).pin_memory()
     was_reset = torch.empty((E,), dtype=torch.uint8).pin_memory()
     for _ in range(3):
-        env.step_host(actions, ring[tick % RING_SLOTS], rewards, dones, was_reset, tick=tick)
+        env.step_host(actions, ring.obs[tick % RING_SLOTS], rewards, dones, was_reset, tick=tick)
         tick += 1
     k2 = max(1, min(K, 200))
     b2 = env.stats()
     barrier()
     t0 = time.perf_counter()
     for _ in range(k2):
-        env.step_host(actions, ring[tick % RING_SLOTS], rewards, dones, was_reset, tick=tick)
+        env.step_host(actions, ring.obs[tick % RING_SLOTS], rewards, dones, was_reset, tick=tick)
         tick += 1
     barrier()
     e2e_s = time.perf_counter() - t0
-    sampler.window[1] = time.perf_counter()
     e2e_steps = env.stats()["env_steps"] - b2["env_steps"]
+
+    # ---- learner leg: fused replay sample + C51 update of the 8 per-agent networks (B = 256 per GPU),
+    #      forward/backward and clip+RMSprop replayed from CUDA graphs, NCCL gradient all-reduce when N > 1
+    for _ in range(3):  # refill the ring's meta arrays with ordinary steps after the host-entry steps
+        step(tick)
+        tick += 1
+    B = int(cfg.batch_size)
+    group = LearnerGroup(cfg, [3, 7, 7], 4, N, B, obs_stride=env.slot_floats, device=dev)
+    batch = ring.new_batch(B)
+    reduce_fn = mdist.make_grad_all_reduce(dist) if dist is not None else None
+    grads_view = group.params(_lib.BUF_GRADS)
+    ring.sample(batch, seed=921, tick=0)
+    group.learn(batch, all_reduce=reduce_fn)  # eager warm-up
+    torch.cuda.synchronize(dev)
+    g_grads, g_apply = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_grads):
+        group.grads(batch)
+    with torch.cuda.graph(g_apply):
+        group.apply(1.0 / world)
+
+    def update(t):
+        ring.sample(batch, seed=921, tick=t)
+        g_grads.replay()
+        if reduce_fn is not None:
+            reduce_fn(grads_view)
+        g_apply.replay()
+
+    for t in range(5):
+        update(t)
+    ku = max(10, min(K, 200))
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    u0.record()
+    for t in range(ku):
+        update(100 + t)
+    u1.record()
+    barrier()
+    upd_ms = u0.elapsed_time(u1)
+    loss = float(group.loss.mean())
+    sampler.window[1] = time.perf_counter()
     sampler.stop()
 
-    vals = torch.tensor([ms, float(env_steps), e2e_s, float(e2e_steps)], dtype=torch.float64, device=dev)
+    vals = [ms, e2e_s, upd_ms]
+    sums = [float(env_steps), float(e2e_steps)]
     if dist is not None:
-        mx = vals.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = vals.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, e2e_s = float(mx[0]), float(mx[2])
-        env_steps, e2e_steps = float(sm[1]), float(sm[3])
+        vals = mdist.max_over_ranks(dist, vals, dev)
+        sums = mdist.sum_over_ranks(dist, sums, dev)
+    ms, e2e_s, upd_ms = vals
+    env_steps, e2e_steps = sums
     if rank == 0:
         value = env_steps * N / (ms * 1e-3)
         e2e = e2e_steps * N / e2e_s
@@ -252,6 +315,12 @@ def run_ours(args, rank, local_rank, world):
                          "kernel": "env_step_kernel", "algorithmic_bytes_per_agent_step": B_ALG,
                          "launch_us": launch_s * 1e6},
             "clocks": sampler.summary(),
+            "learner": {"metric": "learner_updates_per_sec", "unit": "agent-network updates/s",
+                        "value": ku * N / (upd_ms * 1e-3), "ms_per_team_update": upd_ms / ku, "brain": "categorical_dqn",
+                        "agents": N, "batch_per_gpu": B, "global_batch": B * world, "steps": ku, "loss": loss,
+                        "note": "replay sample (1 launch) + forward/backward (CUDA graph) + "
+                                + ("NCCL all-reduce of the flat gradient buffer + " if world > 1 else "")
+                                + "clip+RMSprop (CUDA graph); all 8 agents' networks in grouped launches"},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -260,6 +329,10 @@ def run_ours(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d of the %d envs, %d steps, %.1f s (C oracle port, pthreads)"
                                               % (n_cpu, E, k_cpu, dt)}
+            line["learner"]["cpu_baseline"] = {"value": learner_cpu_rate(B), "unit": "agent-network updates/s",
+                                               "cores": threads, "kind": "port",
+                                               "sample": "torch fp32 restatement of CategoricalDQNBrain.learn, B=%d, "
+                                                         "8 updates of one network" % B}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
