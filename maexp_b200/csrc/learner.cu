@@ -49,35 +49,50 @@ struct GemmArgs {
 
 constexpr int kTile = 64, kBK = 16;
 
-__global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
+// Deterministic split-K: slice z of the K range accumulates into a dense partial tile
+// part[slice][g][M][N]; splitk_reduce_kernel then adds the slices in a fixed order and applies the
+// epilogue.  With ksplit == 1 the epilogue runs here and C is written directly.
+__global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a, int ksplit, int kslice, float *part) {
     __shared__ float As[kBK][kTile + 4];
     __shared__ float Bs[kBK][kTile + 4];
-    const int g = blockIdx.z;
+    const int g = blockIdx.z / ksplit, slice = blockIdx.z - g * ksplit;
     const float *A = a.A + (size_t)g * a.gA, *B = a.B + (size_t)g * a.gB;
-    float *C = a.C + (size_t)g * a.gC;
     const int m0 = blockIdx.y * kTile, n0 = blockIdx.x * kTile;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int kbeg = slice * kslice, kend = min(a.K, kbeg + kslice);
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
     const bool a_k_fast = a.sak == 1, b_n_fast = a.sbn == 1;
-    for (int k0 = 0; k0 < a.K; k0 += kBK) {
-        // load A tile [64 x 16] and B tile [16 x 64]; 4 elements per thread each, coalesced along the unit stride
+    // per-thread tile coordinates of the 4 A and 4 B elements it stages (coalesced along the unit stride)
+    int amm[4], akk[4], bnn[4], bkk[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int idx = tid + r * 256;
+        if (a_k_fast) { akk[r] = idx & 15; amm[r] = idx >> 4; } else { amm[r] = idx & 63; akk[r] = idx >> 6; }
+        if (b_n_fast) { bnn[r] = idx & 63; bkk[r] = idx >> 6; } else { bkk[r] = idx & 15; bnn[r] = idx >> 4; }
+    }
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const int idx = tid + r * 256;
-            int mm, kk;
-            if (a_k_fast) { kk = idx & 15; mm = idx >> 4; } else { mm = idx & 63; kk = idx >> 6; }
-            const int m = m0 + mm, k = k0 + kk;
-            As[kk][mm] = (m < a.M && k < a.K) ? A[(size_t)m * a.sam + (size_t)k * a.sak] : 0.0f;
-            int nn, kb;
-            if (b_n_fast) { nn = idx & 63; kb = idx >> 6; } else { kb = idx & 15; nn = idx >> 4; }
-            const int n = n0 + nn, k2 = k0 + kb;
-            Bs[kb][nn] = (n < a.N && k2 < a.K) ? B[(size_t)k2 * a.sbk + (size_t)n * a.sbn] : 0.0f;
+            const int m = m0 + amm[r], k = k0 + akk[r];
+            ra[r] = (m < a.M && k < kend) ? A[(size_t)m * a.sam + (size_t)k * a.sak] : 0.0f;
+            const int n = n0 + bnn[r], k2 = k0 + bkk[r];
+            rb[r] = (n < a.N && k2 < kend) ? B[(size_t)k2 * a.sbk + (size_t)n * a.sbn] : 0.0f;
+        }
+    };
+    fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += kBK) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            As[akk[r]][amm[r]] = ra[r];
+            Bs[bkk[r]][bnn[r]] = rb[r];
         }
         __syncthreads();
+        if (k0 + kBK < kend) fetch(k0 + kBK);  // next tile's loads overlap this tile's math
 #pragma unroll
         for (int kk = 0; kk < kBK; ++kk) {
             float av[4], bv[4];
@@ -92,6 +107,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
         }
         __syncthreads();
     }
+    float *C = a.C + (size_t)g * a.gC;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + ty * 4 + i;
@@ -101,6 +117,10 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
             const int n = n0 + tx * 4 + j;
             if (n >= a.N) continue;
             float v = acc[i][j];
+            if (ksplit > 1) {
+                part[(((size_t)slice * gridDim.z / ksplit + g) * a.M + m) * a.N + n] = v;
+                continue;
+            }
             if (a.bias) v = __fadd_rn(v, a.bias[(size_t)g * a.gBias + n]);
             if (a.relu) v = fmaxf(v, 0.0f);
             const size_t ci = (size_t)m * a.scm + (size_t)n * a.scn;
@@ -108,6 +128,23 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
             if (a.accumulate) v = __fadd_rn(C[ci], v);
             C[ci] = v;
         }
+    }
+}
+
+__global__ void splitk_reduce_kernel(const GemmArgs a, int ksplit, int G, const float *part) {
+    const int g = blockIdx.y;
+    const long long total = (long long)a.M * a.N;
+    float *C = a.C + (size_t)g * a.gC;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / a.N), n = (int)(i - (long long)m * a.N);
+        float v = 0.0f;
+        for (int s = 0; s < ksplit; ++s) v = __fadd_rn(v, part[((size_t)s * G + g) * total + i]);
+        if (a.bias) v = __fadd_rn(v, a.bias[(size_t)g * a.gBias + n]);
+        if (a.relu) v = fmaxf(v, 0.0f);
+        const size_t ci = (size_t)m * a.scm + (size_t)n * a.scn;
+        if (a.mask_aux) v = (a.aux[(size_t)g * a.gAux + ci] > 0.0f) ? v : 0.0f;
+        if (a.accumulate) v = __fadd_rn(C[ci], v);
+        C[ci] = v;
     }
 }
 
@@ -528,7 +565,7 @@ struct maexp_learner {
     std::vector<ParamEntry> table;
     std::vector<void *> allocs;
     float *online = nullptr, *target = nullptr, *grads = nullptr, *sq = nullptr;
-    float *support = nullptr;
+    float *support = nullptr, *ones = nullptr, *splitk_ws = nullptr;
     // activations of the three passes (0: online(s) kept for backward, 1: online(s'), 2: target(s'))
     struct Acts {
         float *col1, *y1, *p, *col2, *y2, *flat, *h[2], *out[2];
@@ -559,6 +596,9 @@ inline dim3 grid1d(long long total, int g, int threads = 256, int cap = 1024) {
     return dim3((unsigned)blocks, (unsigned)g);
 }
 
+constexpr long long kSplitWorkspaceFloats = 8ll << 20;  // 32 MB of partial tiles
+float *g_splitk_ws = nullptr;                            // set per call from the handle (single host thread)
+
 void gemm(cudaStream_t st, int G, const float *A, const float *Bm, float *C, const float *bias, int M, int N, int K,
           long long sam, long long sak, long long sbk, long long sbn, long long scm, long long scn, long long gA,
           long long gB, long long gC, long long gBias, int relu = 0, int accumulate = 0, const float *aux = nullptr,
@@ -569,8 +609,26 @@ void gemm(cudaStream_t st, int G, const float *A, const float *Bm, float *C, con
     a.sam = sam; a.sak = sak; a.sbk = sbk; a.sbn = sbn; a.scm = scm; a.scn = scn;
     a.gA = gA; a.gB = gB; a.gC = gC; a.gBias = gBias; a.gAux = gAux;
     a.relu = relu; a.accumulate = accumulate; a.mask_aux = aux != nullptr;
-    dim3 grid((N + kTile - 1) / kTile, (M + kTile - 1) / kTile, G);
-    gemm_kernel<<<grid, 256, 0, st>>>(a);
+    const int tm = (M + kTile - 1) / kTile, tn = (N + kTile - 1) / kTile;
+    // split K (powers of two, slices >= 64) until the grid covers two waves of 148 SMs; shapes only → deterministic
+    int ksplit = 1;
+    while ((long long)tm * tn * G * ksplit < 296 && K / (ksplit * 2) >= 64 &&
+           (long long)ksplit * 2 * G * M * N <= kSplitWorkspaceFloats && g_splitk_ws)
+        ksplit *= 2;
+    const int kslice = ((K + ksplit - 1) / ksplit + kBK - 1) / kBK * kBK;
+    dim3 grid(tn, tm, G * ksplit);
+    gemm_kernel<<<grid, 256, 0, st>>>(a, ksplit, kslice, g_splitk_ws);
+    if (ksplit > 1) {
+        const long long total = (long long)M * N;
+        splitk_reduce_kernel<<<dim3((unsigned)((total + 255) / 256 > 256 ? 256 : (total + 255) / 256), G), 256, 0, st>>>(
+            a, ksplit, G, g_splitk_ws);
+    }
+}
+
+// bias gradient: column sums as ones[1,M] x dY[M,N] through the split-K GEMM (fixed order)
+void colsum(cudaStream_t st, int G, const float *ones, const float *X, float *out, int M, int N, long long gX,
+            long long gOut) {
+    gemm(st, G, ones, X, out, nullptr, 1, N, M, 0, 0, N, 1, N, 1, 0, gX, gOut, 0);
 }
 
 // forward of one network for all groups; obs [G][B][obs_stride] (C*V*V valid floats per row)
@@ -619,13 +677,13 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
         // dW2[O,H] = dOut^T h ; db2 ; dh = (dOut W2) * (h > 0)
         gemm(st, G, h->d_out[k], a.h[k], h->grads + hd.w2, nullptr, O, H, B, 1, O, H, 1, H, 1, (long long)B * O,
              (long long)B * H, P, 0);
-        colsum_kernel<<<dim3((O * 32 + 255) / 256, G), 256, 0, st>>>(h->d_out[k], h->grads + hd.b2, B, O, (long long)B * O, P);
+        colsum(st, G, h->ones, h->d_out[k], h->grads + hd.b2, B, O, (long long)B * O, P);
         gemm(st, G, h->d_out[k], h->online + hd.w2, h->d_h, nullptr, B, H, O, O, 1, H, 1, H, 1, (long long)B * O, P,
              (long long)B * H, 0, 0, 0, a.h[k], (long long)B * H);
         // dW1[H,D] = dh^T x ; db1 ; dflat (+)= dh W1
         gemm(st, G, h->d_h, head_in, h->grads + hd.w1, nullptr, H, D, B, 1, H, head_in_row, 1, D, 1, (long long)B * H,
              head_in_g, P, 0);
-        colsum_kernel<<<dim3((H * 32 + 255) / 256, G), 256, 0, st>>>(h->d_h, h->grads + hd.b1, B, H, (long long)B * H, P);
+        colsum(st, G, h->ones, h->d_h, h->grads + hd.b1, B, H, (long long)B * H, P);
         if (h->has_conv)
             gemm(st, G, h->d_h, h->online + hd.w1, h->d_flat, nullptr, B, D, H, H, 1, D, 1, D, 1, (long long)B * H, P,
                  (long long)B * D, 0, 0, /*accumulate=*/k > 0);
@@ -637,14 +695,14 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
     nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, st>>>(h->d_flat, h->d_y2, B, H2 * H2, F2, gy2, 1);
     const int M2 = B * H2 * H2;
     gemm(st, G, h->d_y2, a.col2, h->grads + h->o_c2w, nullptr, F2, F1 * 4, M2, 1, F2, F1 * 4, 1, F1 * 4, 1, gy2, gcol2, P, 0);
-    colsum_kernel<<<dim3((F2 * 32 + 255) / 256, G), 256, 0, st>>>(h->d_y2, h->grads + h->o_c2b, M2, F2, gy2, P);
+    colsum(st, G, h->ones, h->d_y2, h->grads + h->o_c2b, M2, F2, gy2, P);
     gemm(st, G, h->d_y2, h->online + h->o_c2w, h->d_col2, nullptr, M2, F1 * 4, F2, F2, 1, F1 * 4, 1, F1 * 4, 1, gy2, P,
          gcol2, 0);
     col2im_kernel<<<grid1d((long long)B * Hp * Hp * F1, G), 256, 0, st>>>(h->d_col2, h->d_p, B, Hp, Hp, F1, gcol2, gp);
     pool_bwd_kernel<<<grid1d((long long)B * H1 * H1 * F1, G), 256, 0, st>>>(h->d_p, a.arg, h->d_y1, B, H1, H1, F1, gy1, gp);
     const int M1 = B * H1 * H1;
     gemm(st, G, h->d_y1, a.col1, h->grads + h->o_c1w, nullptr, F1, C * 4, M1, 1, F1, C * 4, 1, C * 4, 1, gy1, gcol1, P, 0);
-    colsum_kernel<<<dim3((F1 * 32 + 255) / 256, G), 256, 0, st>>>(h->d_y1, h->grads + h->o_c1b, M1, F1, gy1, P);
+    colsum(st, G, h->ones, h->d_y1, h->grads + h->o_c1b, M1, F1, gy1, P);
 }
 
 }  // namespace
@@ -712,6 +770,8 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     rc |= lalloc(h, &h->grads, G * P);
     rc |= lalloc(h, &h->sq, G * P);
     rc |= lalloc(h, &h->support, 128);
+    rc |= lalloc(h, &h->ones, 4);
+    rc |= lalloc(h, &h->splitk_ws, (size_t)kSplitWorkspaceFloats);
     for (int k = 0; k < 3; ++k) {
         maexp_learner::Acts &a = h->acts[k];
         memset(&a, 0, sizeof(a));
@@ -744,6 +804,8 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     h->nparts = 32;
     rc |= lalloc(h, &h->partial, G * h->nparts);
     if (rc) { maexp_learner_destroy(h); return -1; }
+    const float one = 1.0f;
+    if (cudaMemcpy(h->ones, &one, sizeof(one), cudaMemcpyHostToDevice) != cudaSuccess) { maexp_learner_destroy(h); return fail("maexp_learner_create: memcpy"); }
     *out = h;
     return 0;
 }
@@ -792,6 +854,7 @@ int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int us
     if (batch < 1 || batch > h->B) return fail("maexp_learner_q_values: batch must be in 1..batch_size");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     maexp_learner::Acts &a = h->acts[1];
+    g_splitk_ws = h->splitk_ws;
     forward(h, st, use_target ? h->target : h->online, obs, batch, a);
     if (!h->dist) {
         // heads are strided by the maximum batch: compact to [G][batch][A]
@@ -810,6 +873,7 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
     if (!h || !obs || !next_obs || !actions || !rewards || !dones) return fail("maexp_learner_grads: null argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int G = h->G, B = h->B, A = h->A, Z = h->Z;
+    g_splitk_ws = h->splitk_ws;
     forward(h, st, h->online, obs, B, h->acts[0]);
     forward(h, st, h->target, next_obs, B, h->acts[2]);
     if (!h->dist) {
