@@ -218,6 +218,21 @@ int maexp_learner_apply(maexp_learner *learner, float grad_scale, const uint8_t 
 int maexp_learner_update(maexp_learner *learner, const float *obs, const float *next_obs, const int32_t *actions,
                          const float *rewards, const uint8_t *dones, float *loss_out, void *stream);
 
+/* ObservationHandler.decode_relative_state (observation_handler.py:150-216): fp32 obs rows
+ * [rows, obs_stride] (C*V*V valid) + int8 index-space positions [rows,2] -> canvas [rows,C,X,Y]
+ * (0 everywhere, last channel -1, window∩map pasted).  only_area_plus_one = 1 writes
+ * canvas[:, -1:] + 1 -> [rows,1,X,Y], which is all the merged models read (conv_mlp.py:100-108). */
+int maexp_decode_relative(const float *obs, const int8_t *positions, float *canvas, int64_t rows, int channels,
+                          int visible_range, int size_x, int size_y, int obs_stride, int only_area_plus_one, void *stream);
+
+/* DefaultAgent.get_action for a chunk of environments (default_agent.py:12-19): with probability epsilon a
+ * uniform random action int(random()*A) (abstract_agent.py:31-34), else argmax_a Q.  q_values [G,batch,A];
+ * actions int8 [E,G] written at rows env_offset .. env_offset+batch; no_task uint8 [G]: agent_tasks "-1" agents
+ * always act randomly (abstract_trainer.py:70-72).  Draws: Philox keyed (seed, global env id, tick). */
+int maexp_select_actions(const float *q_values, int8_t *actions, int num_agents, int batch, int num_actions, int env_offset,
+                         float epsilon, uint32_t seed, uint32_t first_global_env_id, uint32_t tick, const uint8_t *no_task,
+                         void *stream);
+
 const char *maexp_last_error(void);
 int maexp_version(void);
 

@@ -88,6 +88,10 @@ SYMBOLS = {
     "maexp_learner_grads": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
     "maexp_learner_apply": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "maexp_learner_update": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
+    "maexp_decode_relative": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p]),
+    "maexp_select_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint32,
+                                       C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "maexp_last_error": (C.c_char_p, []),
     "maexp_version": (C.c_int, []),
 }

@@ -1,0 +1,98 @@
+"""`generate_environment` (core/environments/__init__.py:37-71) on top of the CUDA step kernel.
+
+`DefaultEnvironment` keeps the reference's single-environment interface — `reset() -> obs_n`,
+`step(action_n, order) -> (reward_n, done_n, obs_n)` with per-agent observation dicts
+(default_environment.py:64-175, observation_handler.py:95-105) — by driving a one-env
+`BatchedEnvironment`.  Training at scale uses `BatchedEnvironment` directly (see trainers).
+"""
+import numpy as np
+import torch
+
+from ..handlers.observations import generate_observation_handler
+from ..handlers.observations.masks import COORDINATE_KEYS
+from ..utils.logging import initialize_logging
+from .batched import BatchedEnvironment
+
+logger = initialize_logging(__name__)
+
+__all__ = ["BatchedEnvironment", "DefaultEnvironment", "SharedMeanRewardEnvironment", "SharedMaxRewardEnvironment",
+           "generate_environment"]
+
+
+class DefaultEnvironment:
+    reward_environment = "default"
+
+    def __init__(self, config, world, reference_compat=False):
+        self.config, self.world = config, world
+        self.num_agents = int(config.num_agents)
+        self.agents = list(range(self.num_agents))
+        self.observation_handler = generate_observation_handler(config=config, world=world)
+        self.action_space = [4 for _ in self.agents]  # default_environment.py:27
+        self.observation_space = [self.observation_handler.observation_space for _ in self.agents]
+        self.view_method = config.observation_area_mask
+        cfg = config if config.environment == self.reward_environment else config.merged_with(
+            environment=self.reward_environment)
+        self.batched = BatchedEnvironment(cfg, world, 1, auto_reset=False, shared_max_is_mean=reference_compat)
+        self.out = self.batched.new_outputs(extras=True)
+        self.current_step = 0
+        self.objects_generated = self.objects_completed = self.agents_collided = self.walls_collided = 0
+
+    # ---- reference structures
+    def _obs_n(self):
+        b, o = self.batched, self.out
+        torch.cuda.synchronize(b.device)
+        obs = b.view(o["obs"])[0].cpu()
+        rel = b.view(o["obs_rel"])[0].cpu() if b.merged else None
+        pos = o["positions"][0].cpu()
+        coords = o["coordinates"][0].cpu().numpy()
+        objects = o["objects"][0].cpu()
+        dest = torch.from_numpy(b.destination_masks[o["destination"][0].cpu().numpy().astype(np.int64)])
+        view = "local" if self.view_method in ("local", "merged") else "relative"
+        obs_n = []
+        for i in range(self.num_agents):
+            d = {view: obs[i], "coordinates": {k: int(v) for k, v in zip(COORDINATE_KEYS, coords[i])},
+                 "agents": pos.clone(), "objects": objects[i], "destination": dest[i]}
+            if rel is not None:
+                d["relative"] = rel[i]
+            obs_n.append(d)
+        st = b.state()
+        cnt = st["counters"][0].cpu().tolist()
+        self.objects_generated, self.objects_completed, self.agents_collided, self.walls_collided = cnt
+        self.current_step = int(st["steps"][0])
+        return obs_n
+
+    def reset(self):
+        self.batched.reset(self.out)
+        return self._obs_n()
+
+    def step(self, action_n, order):
+        dev = self.batched.device
+        actions = torch.as_tensor(np.asarray(action_n, np.int8).reshape(1, -1)).to(dev)
+        order = torch.as_tensor(np.asarray(order, np.uint8).reshape(1, -1)).to(dev)
+        self.batched.step(self.out, actions=actions, order=order)
+        obs_n = self._obs_n()
+        rewards = self.out["rewards"][0].cpu().tolist()
+        dones = [bool(d) for d in self.out["dones"][0].cpu().tolist()]
+        return rewards, dones, obs_n
+
+
+class SharedMeanRewardEnvironment(DefaultEnvironment):
+    """shared_reward_environment.py:15-20 (with the `order` argument the shipped class lacks)."""
+    reward_environment = "shared_mean_reward"
+
+
+class SharedMaxRewardEnvironment(DefaultEnvironment):
+    """shared_reward_environment.py:23-28.  The reference computes the MEAN here; pass reference_compat=True to
+    reproduce that, the default is the true maximum."""
+    reward_environment = "shared_max_reward"
+
+
+def generate_environment(config, world):
+    if config.environment == "default":
+        return DefaultEnvironment(config=config, world=world)
+    if config.environment == "shared_mean_reward":
+        return SharedMeanRewardEnvironment(config=config, world=world)
+    if config.environment == "shared_max_reward":
+        return SharedMaxRewardEnvironment(config=config, world=world)
+    logger.warning(f"Unexpected environment is given. config.environment: {config.environment}")
+    raise ValueError()

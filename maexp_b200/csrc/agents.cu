@@ -1,0 +1,87 @@
+// Learner-side observation decode and batched epsilon-greedy action selection (sm_100a).
+//
+//   maexp_decode_relative   ObservationHandler.decode_relative_state  (observation_handler.py:150-216):
+//                           pastes each V x V crop onto an [C, X, Y] canvas (0 everywhere, last channel -1);
+//                           the reference loops over the batch in Python.
+//   maexp_select_actions    DefaultAgent.get_action / get_random_action (default_agent.py:12-19,
+//                           abstract_agent.py:31-34) for every (env, agent) at once.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/maexp_b200.h"
+#include "philox.cuh"
+
+namespace maexp {
+int fail(const std::string &msg);
+constexpr uint32_t kStreamEpsilon = 8;
+
+// one thread per canvas element, coalesced along y; HBM-bound: writes 4*C*X*Y bytes per observation
+__global__ void decode_relative_kernel(const float *obs, const int8_t *pos, float *canvas, long long rows, int C, int V,
+                                       int X, int Y, int obs_stride, int only_area) {
+    const int R = V / 2, Cout = only_area ? 1 : C;
+    const long long total = rows * Cout * X * Y;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i % Y), x = (int)((i / Y) % X);
+        const int co = (int)((i / ((long long)X * Y)) % Cout);
+        const long long row = i / ((long long)Cout * X * Y);
+        const int c = only_area ? C - 1 : co;
+        const int px = pos[row * 2], py = pos[row * 2 + 1];
+        const int a = x - px + R, b = y - py + R;  // window cell of map cell (x, y); window∩map is what the slices copy
+        float v = (c == C - 1) ? -1.0f : 0.0f;
+        if (a >= 0 && a < V && b >= 0 && b < V) v = obs[row * obs_stride + ((long long)c * V + a) * V + b];
+        // merged models use canvas[:, -1:] + 1 (conv_mlp.py:100-108): 1 where visible
+        canvas[i] = only_area ? v + 1.0f : v;
+    }
+}
+
+__global__ void select_actions_kernel(const float *q, int8_t *actions, int G, int batch, int A, int env0, int num_envs_total,
+                                      float epsilon, uint32_t seed, uint32_t gid0, uint32_t tick, const uint8_t *no_task) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch * G) return;
+    const int e = i / G, k = i - e * G;
+    const uint4 w = philox4x32_10(seed, gid0 + (uint32_t)(env0 + e), tick, kStreamEpsilon, (uint32_t)k, 0);
+    int action;
+    if ((no_task && no_task[k]) || unit_float(w.x) < epsilon) {
+        action = (int)scale(w.y, (uint32_t)A);  // int(random() * act_size)
+    } else {
+        const float *row = q + ((size_t)k * batch + e) * A;
+        action = 0;
+        float best = row[0];
+        for (int a = 1; a < A; ++a)
+            if (row[a] > best) { best = row[a]; action = a; }  // argmax, first maximum
+    }
+    actions[(size_t)(env0 + e) * G + k] = (int8_t)action;
+    (void)num_envs_total;
+}
+}  // namespace maexp
+
+extern "C" {
+using namespace maexp;
+
+int maexp_decode_relative(const float *obs, const int8_t *positions, float *canvas, int64_t rows, int channels,
+                          int visible_range, int size_x, int size_y, int obs_stride, int only_area_plus_one, void *stream) {
+    if (!obs || !positions || !canvas) return fail("maexp_decode_relative: null argument");
+    if (rows < 1 || channels < 1) return fail("maexp_decode_relative: bad shape");
+    const long long total = (long long)rows * (only_area_plus_one ? 1 : channels) * size_x * size_y;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    decode_relative_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        obs, positions, canvas, rows, channels, visible_range, size_x, size_y, obs_stride, only_area_plus_one);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("maexp_decode_relative: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int maexp_select_actions(const float *q_values, int8_t *actions, int num_agents, int batch, int num_actions, int env_offset,
+                         float epsilon, uint32_t seed, uint32_t first_global_env_id, uint32_t tick, const uint8_t *no_task,
+                         void *stream) {
+    if (!q_values || !actions) return fail("maexp_select_actions: null argument");
+    select_actions_kernel<<<(batch * num_agents + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        q_values, actions, num_agents, batch, num_actions, env_offset, 0, epsilon, seed, first_global_env_id, tick, no_task);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("maexp_select_actions: ") + cudaGetErrorString(e));
+    return 0;
+}
+}

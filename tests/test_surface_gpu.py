@@ -1,0 +1,120 @@
+"""The reference-facing plugin surface on top of the kernels: single-env environment, decoders, actor, trainer."""
+import numpy as np
+import pytest
+import torch
+
+from maexp_b200.config import Config, baseline_config
+from oracle.oracle import Oracle
+from tests import replay as rp
+
+pytestmark = pytest.mark.gpu
+
+
+def _world(cfg):
+    from maexp_b200.core.maps import generate_map
+    from maexp_b200.core.worlds import generate_world
+    return generate_world(cfg, generate_map(cfg))
+
+
+def test_generate_environment_returns_reference_structures():
+    """env.reset()/env.step(action_n, order) as the reference's trainers call them, against a fixture of the
+    live reference (same actions and orders as the tape draws)."""
+    from maexp_b200.core.environments import generate_environment
+    from oracle import ref_runner as rr
+    fix = rp.load("cfg5_four_rooms_n8")
+    cfg = Config(fix["config"])
+    env = generate_environment(cfg, _world(cfg))
+    assert env.action_space == [4] * 8 and env.observation_space == [[3, 7, 7]] * 8
+    # the single-env wrapper keys its draws with global env id 0; compare against the oracle with the same id
+    orc = Oracle(cfg, 1, first_global_env_id=0, extras=True)
+    obs_n = env.reset()
+    want = orc.reset(0)
+    assert len(obs_n) == 8 and set(obs_n[0]) == {"local", "coordinates", "agents", "objects", "destination"}
+    for i in range(8):
+        assert np.array_equal(obs_n[i]["local"].numpy(), want["obs"][0, i])
+        assert np.array_equal(obs_n[i]["objects"].numpy(), want["objects"][0, i])
+        assert obs_n[i]["coordinates"]["map_x_max"] == want["coordinates"][0, i, 9]
+    rng = np.random.default_rng(0)
+    for tick in range(1, 25):
+        actions, order = rng.integers(0, 5, 8), rng.permutation(8)
+        rewards, dones, obs_n = env.step(list(actions), list(order))
+        want = orc.step(tick, actions=actions[None], order=order[None])
+        assert rewards == want["rewards"][0].tolist() and dones == [bool(d) for d in want["dones"][0]]
+        for i in range(8):
+            assert np.array_equal(obs_n[i]["local"].numpy(), want["obs"][0, i])
+            assert np.array_equal(obs_n[i]["agents"].numpy(), want["agents"][0, i])
+    assert env.objects_completed == int(orc.state()["counters"][0, 1]) and env.current_step == 24
+    with pytest.raises(ValueError):
+        generate_environment(cfg.merged_with(environment="nope"), _world(cfg))
+
+
+def test_decode_relative_state_matches_reference_semantics():
+    """observation_handler.py:150-216 restated in numpy on the oracle's coordinates."""
+    from maexp_b200.core.handlers.observations import ObservationHandler
+    cfg = baseline_config(4)  # four_rectangle 40x24, merged, C=11
+    orc = Oracle(cfg, 6, first_global_env_id=0, extras=True)
+    orc.reset(0)
+    out = orc.step(1)
+    B = 6 * 8
+    rel = torch.from_numpy(out["obs_rel"].reshape(B, 11, 7, 7)).cuda()
+    pos = torch.from_numpy(np.stack([out["agents"][e, i, i] for e in range(6) for i in range(8)])).cuda()
+    coords = out["coordinates"].reshape(B, 12)
+    want = np.zeros((B, 11, 40, 24), np.float32)
+    want[:, -1] -= 1
+    for b in range(B):
+        c = coords[b]
+        want[b, :, c[8]:c[9], c[10]:c[11]] = out["obs_rel"].reshape(B, 11, 7, 7)[b, :, c[0]:c[1], c[2]:c[3]]
+    got = ObservationHandler.decode_relative_state({"relative": rel, "positions": pos}, [40, 24])
+    assert np.array_equal(got.cpu().numpy(), want)
+    area = ObservationHandler.decode_relative_state({"relative": rel, "positions": pos}, [40, 24], only_area_plus_one=True)
+    assert np.array_equal(area.cpu().numpy(), want[:, -1:] + 1)
+    one = ObservationHandler.decode_relative_state({"relative": rel[3], "positions": pos[3]}, [40, 24])
+    assert np.array_equal(one.cpu().numpy(), want[3])
+
+
+def test_batched_actor_epsilon_greedy():
+    from maexp_b200.core.agents import BatchedActor
+    from maexp_b200.core.agents.brains import LearnerGroup
+    from tests.cuda_backend import make_env
+    cfg = baseline_config(5).merged_with(agent_tasks=["0"] * 7 + ["-1"])
+    env = make_env(cfg, 300, auto_reset=True)
+    out = env.new_outputs()
+    env.reset(out, tick=0)
+    learner = LearnerGroup(cfg, [3, 7, 7], 4, 8, 32, obs_stride=env.slot_floats)
+    actor = BatchedActor(cfg, env, learner, chunk=128)  # 300 envs -> chunks of 128, 128, 44
+    actor.refresh()
+    greedy = actor.act(out["obs"], 0.0, tick=1).clone()
+    q = torch.cat([learner_q for learner_q in [actor.group.q_values(out["obs"][e0:e0 + 100].transpose(0, 1).contiguous())
+                                               .clone() for e0 in (0, 100, 200)]], dim=1)  # [N, 300, A]
+    want = q.argmax(dim=2).transpose(0, 1).to(torch.int8)
+    assert torch.equal(greedy[:, :7], want[:, :7])  # epsilon = 0: argmax of the online net
+    rnd = actor.act(out["obs"], 1.0, tick=2)
+    assert int(rnd.min()) >= 0 and int(rnd.max()) <= 3
+    counts = torch.bincount(rnd.flatten().long(), minlength=4).float()
+    assert float(counts.min() / counts.sum()) > 0.2  # uniform over the four actions
+    a3 = actor.act(out["obs"], 0.0, tick=3)[:, 7].clone()
+    assert not torch.equal(a3, actor.act(out["obs"], 0.0, tick=4)[:, 7])  # the "-1" agent acts randomly
+
+
+def test_trainer_runs_and_saves_reference_compatible_checkpoints(tmp_path):
+    from maexp_b200.core.handlers.trainers import generate_trainer
+    from tests.cuda_backend import make_env
+    cfg = baseline_config(5).merged_with(max_episode_length=8, batch_size=32, populate_steps=4 * 64, capacity=64 * 16,
+                                         synchronize_frequency=1, epsilon_decay=0.5)
+    env = make_env(cfg, 64, auto_reset=True)
+    trainer = generate_trainer(cfg, env)
+    before = trainer.learner.params().clone()
+    hist = trainer.run(max_epochs=2)
+    assert len(hist) == 2 and hist[-1]["epsilon"] == 0.25 and np.isfinite(hist[-1]["loss"])
+    assert not torch.equal(trainer.learner.params(), before)  # networks were updated
+    assert torch.equal(trainer.learner.params(1), trainer.learner.params())  # target synchronised at episode end
+    assert trainer.env.stats()["env_steps"] > 0
+    trainer.save_state_dict(str(tmp_path))
+    sd = torch.load(str(tmp_path / "agent3.pth"))
+    assert set(sd) == {"conv.conv_list.0.weight", "conv.conv_list.0.bias", "conv.conv_post.weight", "conv.conv_post.bias",
+                       "fc_V.fc_list.0.weight", "fc_V.fc_list.0.bias", "fc_V.fc_post.weight", "fc_V.fc_post.bias",
+                       "fc_A.fc_list.0.weight", "fc_A.fc_list.0.bias", "fc_A.fc_post.weight", "fc_A.fc_post.bias"}
+    assert tuple(sd["fc_A.fc_post.weight"].shape) == (204, 128) and tuple(sd["conv.conv_post.weight"].shape) == (64, 32, 2, 2)
+    trainer.load_state_dict(str(tmp_path))
+    with pytest.raises(ValueError):
+        generate_trainer(cfg.merged_with(trainer="nope"), env)
