@@ -170,7 +170,8 @@ enum {
     MAEXP_LEARNER_DQN_CONV_MLP = 0, /* brain dqn / da3_baseline + model conv_mlp: da3_brain.py:58-89, conv_mlp.py:21-66 */
     MAEXP_LEARNER_C51 = 1,          /* categorical_dqn_brain.py:42-89, customs/categorical_dqn.py:28-79 */
     MAEXP_LEARNER_QR = 2,           /* qr_dqn_brain.py:81-119, customs/qr_dqn.py:20-65 */
-    MAEXP_LEARNER_DQN_MLP = 3       /* model mlp on the flattened observation (mlp.py:14-34) */
+    MAEXP_LEARNER_DQN_MLP = 3,      /* model mlp on the flattened observation (mlp.py:14-34) */
+    MAEXP_LEARNER_IQN = 4           /* iqn_brain.py:60-115, customs/iqn.py:21-162 (num_atoms = model.num_quantiles) */
 };
 enum { MAEXP_BUF_ONLINE = 0, MAEXP_BUF_TARGET = 1, MAEXP_BUF_GRADS = 2, MAEXP_BUF_SQUARE_AVG = 3, MAEXP_BUF_SUPPORT = 4 };
 
@@ -187,7 +188,8 @@ typedef struct {
     float gamma;
     float v_min, v_max, delta_z;  /* C51 support bounds; delta_z = fp32((V_max - V_min)/(num_atoms - 1)) */
     float learning_rate, alpha, one_minus_alpha, eps;  /* optim.RMSprop, configs/opt/rmsprop.yaml */
-    float max_norm;          /* clip_grad_norm_: 0.1 (dqn, qr), 10 (c51) */
+    float max_norm;          /* clip_grad_norm_: 0.1 (dqn, qr, iqn), 10 (c51) */
+    int32_t num_quantiles_dash, num_cosines;  /* IQN: model.num_quantiles_dash, model.num_cosines */
 } maexp_learner_cfg;
 
 typedef struct maexp_learner maexp_learner;
@@ -210,6 +212,14 @@ int maexp_learner_q_values(maexp_learner *learner, const float *obs /*[G,batch,o
 /* forward(s), forward(s'), TD target / projection, loss [G] and gradients into MAEXP_BUF_GRADS */
 int maexp_learner_grads(maexp_learner *learner, const float *obs, const float *next_obs, const int32_t *actions,
                         const float *rewards, const uint8_t *dones, float *loss_out, void *stream);
+/* IQN variants: taus fp32 [G,B,Nq] and tau_dashes [G,B,Nq'] are the per-sample quantile fractions
+ * (torch.rand in iqn_brain.py:74,87), tau_sel [G,Nq] the shared fractions of the action-selecting forward
+ * (customs/iqn.py:105-106).  Terminal states are not masked, as in the reference. */
+int maexp_learner_q_values_iqn(maexp_learner *learner, const float *obs, int batch, int use_target, const float *tau_sel,
+                               float *q_out, void *stream);
+int maexp_learner_grads_iqn(maexp_learner *learner, const float *obs, const float *next_obs, const int32_t *actions,
+                            const float *rewards, const uint8_t *dones, const float *taus, const float *tau_dashes,
+                            const float *tau_sel, float *loss_out, void *stream);
 /* grads *= grad_scale (1/world_size after an all-reduce), clip_grad_norm_, RMSprop step.
  * active: optional uint8 [G], 0 skips the agent (agent_tasks "-1", abstract_trainer.py:49-51) */
 int maexp_learner_apply(maexp_learner *learner, float grad_scale, const uint8_t *active, float *grad_norm_out,

@@ -53,10 +53,11 @@ class LearnerCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("kind", "num_agents", "batch_size", "channels", "visible_range", "num_actions",
                                           "hidden", "conv1_channels", "conv2_channels", "num_atoms", "obs_stride")] + \
                [(n, C.c_float) for n in ("gamma", "v_min", "v_max", "delta_z", "learning_rate", "alpha",
-                                          "one_minus_alpha", "eps", "max_norm")]
+                                          "one_minus_alpha", "eps", "max_norm")] + \
+               [(n, C.c_int32) for n in ("num_quantiles_dash", "num_cosines")]
 
 
-LEARNER_KINDS = {"dqn_conv_mlp": 0, "c51": 1, "qr": 2, "dqn_mlp": 3}
+LEARNER_KINDS = {"dqn_conv_mlp": 0, "c51": 1, "qr": 2, "dqn_mlp": 3, "iqn": 4}
 BUF_ONLINE, BUF_TARGET, BUF_GRADS, BUF_SQUARE_AVG, BUF_SUPPORT = range(5)
 
 # every symbol include/maexp_b200.h declares: name -> (restype, argtypes)
@@ -86,6 +87,8 @@ SYMBOLS = {
     "maexp_learner_sync_target": (C.c_int, [C.c_void_p, C.c_void_p]),
     "maexp_learner_q_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "maexp_learner_grads": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
+    "maexp_learner_q_values_iqn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "maexp_learner_grads_iqn": (C.c_int, [C.c_void_p] + [C.c_void_p] * 9 + [C.c_void_p]),
     "maexp_learner_apply": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "maexp_learner_update": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
     "maexp_decode_relative": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -16,7 +16,7 @@ logger = initialize_logging(__name__)
 
 # brain name -> (learner kind for conv models, clip max_norm)      brains/*.py
 _BRAINS = {"dqn": ("dqn_conv_mlp", 0.1), "da3_baseline": ("dqn_conv_mlp", 0.1), "categorical_dqn": ("c51", 10.0),
-           "qr_dqn": ("qr", 0.1)}
+           "qr_dqn": ("qr", 0.1), "iqn": ("iqn", 0.1)}
 
 
 def learner_kind(config):
@@ -28,7 +28,7 @@ def learner_kind(config):
         if kind != "dqn_conv_mlp":
             raise ValueError("model=mlp is only defined for the dqn brain")
         kind = "dqn_mlp"
-    elif config.model.name not in ("conv_mlp", "da3_baseline", "categorical_dqn", "qr_dqn"):
+    elif config.model.name not in ("conv_mlp", "da3_baseline", "categorical_dqn", "qr_dqn", "iqn"):
         logger.warning(f"Unexpected network is given. config.model.name: {config.model.name}")
         raise ValueError()
     return kind, max_norm
@@ -54,8 +54,11 @@ class LearnerGroup:
         cfg.num_actions, cfg.hidden = self.A, int(m.hidden_layer_sizes[0])
         cfg.conv1_channels = int(m.get("hidden_channels", [32])[0])
         cfg.conv2_channels = int(m.get("output_channel", 64))
-        self.Z = int(m.num_atoms) if self.kind == "c51" else int(m.num_quantiles) if self.kind == "qr" else 1
+        self.Z = int(m.num_atoms) if self.kind == "c51" else int(m.num_quantiles) if self.kind in ("qr", "iqn") else 1
         cfg.num_atoms, cfg.obs_stride = self.Z, self.obs_stride
+        if self.kind == "iqn":
+            self.Nd = int(m.num_quantiles_dash)
+            cfg.num_quantiles_dash, cfg.num_cosines = self.Nd, int(m.num_cosines)
         cfg.gamma = float(config.gamma)
         if self.kind == "c51":
             cfg.v_min, cfg.v_max = float(m.V_min), float(m.V_max)
@@ -132,10 +135,18 @@ class LearnerGroup:
         _lib.check(self.lib.maexp_learner_sync_target(self.h, self._stream()))
 
     # ------------------------------------------------------------------ compute
-    def q_values(self, obs, use_target=False):
-        """obs fp32 [G, b, obs_stride] on the device -> Q [G, b, A]."""
+    def q_values(self, obs, use_target=False, tau_sel=None):
+        """obs fp32 [G, b, obs_stride] on the device -> Q [G, b, A].  IQN: tau_sel [G, Nq] (drawn if None,
+        customs/iqn.py:105-106)."""
         b = obs.shape[1]
         q = self.q if b == self.B else torch.empty((self.G, b, self.A), dtype=torch.float32, device=self.device)
+        if self.kind == "iqn":
+            if tau_sel is None:
+                tau_sel = torch.rand((self.G, self.Z), device=self.device)
+            _lib.check(self.lib.maexp_learner_q_values_iqn(self.h, C.c_void_p(obs.data_ptr()), b, int(use_target),
+                                                           C.c_void_p(tau_sel.data_ptr()), C.c_void_p(q.data_ptr()),
+                                                           self._stream()))
+            return q
         _lib.check(self.lib.maexp_learner_q_values(self.h, C.c_void_p(obs.data_ptr()), b, int(use_target),
                                                    C.c_void_p(q.data_ptr()), self._stream()))
         return q
@@ -143,6 +154,16 @@ class LearnerGroup:
     def grads(self, batch):
         """Forward, TD target, loss [G] and gradients (kept in the library's grad buffer)."""
         p = lambda t: C.c_void_p(t.data_ptr())
+        if self.kind == "iqn":  # quantile fractions: injected for parity tests, else drawn like iqn_brain.py:74,87
+            d = self.device
+            taus = batch["taus"] if "taus" in batch else torch.rand((self.G, self.B, self.Z), device=d)
+            dash = batch["tau_dashes"] if "tau_dashes" in batch else torch.rand((self.G, self.B, self.Nd), device=d)
+            sel = batch["tau_sel"] if "tau_sel" in batch else torch.rand((self.G, self.Z), device=d)
+            self._taus_keep = (taus, dash, sel)
+            _lib.check(self.lib.maexp_learner_grads_iqn(self.h, p(batch["obs"]), p(batch["next_obs"]), p(batch["actions"]),
+                                                        p(batch["rewards"]), p(batch["dones"]), p(taus), p(dash), p(sel),
+                                                        p(self.loss), self._stream()))
+            return self.loss
         _lib.check(self.lib.maexp_learner_grads(self.h, p(batch["obs"]), p(batch["next_obs"]), p(batch["actions"]),
                                                 p(batch["rewards"]), p(batch["dones"]), p(self.loss), self._stream()))
         return self.loss

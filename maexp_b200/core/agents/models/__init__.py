@@ -49,6 +49,21 @@ class _ConvHeads(nn.Module):
             setattr(self, name, _MLP(config, d, out))
 
 
+class _IQN(nn.Module):
+    """Parameter layout and construction order of customs/iqn.py:35-67."""
+
+    def __init__(self, config, obs_shape, act_size):
+        super().__init__()
+        self.conv = _Conv(config, obs_shape[0], config.model.output_channel)
+        torch.randn(1, *obs_shape)  # customs/iqn.py:143
+        d = conv_output_size(config, obs_shape)
+        self.state_embedder = _MLP(config, d, d)
+        self.cosine_net = nn.Module()
+        self.cosine_net.net = nn.Sequential(nn.Linear(int(config.model.num_cosines), d), nn.ReLU(inplace=False))
+        self.fc_V = _MLP(config, d, 1)
+        self.fc_A = _MLP(config, d, act_size)
+
+
 def build_reference_modules(config, obs_shape, act_size):
     name = config.model.name
     if name == "mlp":  # SURVEY.md appendix E-2: the flattened observation feeds the MLP
@@ -61,4 +76,6 @@ def build_reference_modules(config, obs_shape, act_size):
     if name == "qr_dqn":
         z = int(config.model.num_quantiles)
         return _ConvHeads(config, obs_shape, [("fc_V", z), ("fc_A", act_size * z)])
+    if name == "iqn":
+        return _IQN(config, obs_shape, act_size)
     raise ValueError(name)

@@ -498,6 +498,132 @@ __global__ void dist_q_kernel(const float *v, const float *adv, const float *sup
     }
 }
 
+
+// ------------------------------------------------------------------------------ IQN pieces
+// CosineEmbeddingNetwork input (customs/iqn.py:32-40): cos(tau * (pi * k)), k = 1..ncos, fp32 products as torch forms them
+__global__ void iqn_cos_kernel(const float *taus, float *cosf_out, int B, int Nq, int ncos, int per_sample, long long gT,
+                               long long gC) {
+    const int g = blockIdx.y;
+    const long long total = (long long)B * Nq * ncos;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % ncos);
+        const long long r = i / ncos;
+        const int q = (int)(r % Nq);
+        const long long b = r / Nq;
+        const float tau = per_sample ? taus[(size_t)g * gT + b * Nq + q] : taus[(size_t)g * gT + q];
+        const float ipi = __fmul_rn(3.14159274101257324f, (float)(k + 1));
+        cosf_out[(size_t)g * gC + i] = cosf(__fmul_rn(tau, ipi));
+    }
+}
+
+// e[(b,q)][d] = psi[b][d] * phi[(b,q)][d]   (customs/iqn.py:123)
+__global__ void iqn_hadamard_fwd_kernel(const float *psi, const float *phi, float *e, int B, int Nq, int D, long long gPsi,
+                                        long long gRow) {
+    const int g = blockIdx.y;
+    const long long total = (long long)B * Nq * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const long long b = i / ((long long)D * Nq);
+        e[(size_t)g * gRow + i] = __fmul_rn(psi[(size_t)g * gPsi + b * D + d], phi[(size_t)g * gRow + i]);
+    }
+}
+
+// dphi = de * psi masked by relu (phi > 0); dpsi[b][d] = sum_q de[(b,q)][d] * phi[(b,q)][d]  (fixed order over q)
+__global__ void iqn_hadamard_bwd_kernel(const float *de, const float *psi, const float *phi, float *dphi, float *dpsi, int B,
+                                        int Nq, int D, long long gPsi, long long gRow) {
+    const int g = blockIdx.y;
+    const long long total = (long long)B * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const long long b = i / D;
+        const float ps = psi[(size_t)g * gPsi + i];
+        float acc = 0.0f;
+        for (int q = 0; q < Nq; ++q) {
+            const size_t r = (size_t)g * gRow + ((size_t)b * Nq + q) * D + d;
+            const float ph = phi[r], g_e = de[r];
+            acc = __fadd_rn(acc, __fmul_rn(g_e, ph));
+            dphi[r] = ph > 0.0f ? __fmul_rn(g_e, ps) : 0.0f;
+        }
+        dpsi[(size_t)g * gPsi + i] = acc;
+    }
+}
+
+struct IqnArgs {
+    const float *v0, *a0;  // online(s, taus):        V [G][B*Nq], A [G][B*Nq][A]
+    const float *v1, *a1;  // online(s', tau_sel):    action selection (iqn_brain.py:84-85, customs/iqn.py:88-94)
+    const float *v2, *a2;  // target(s', tau_dashes): [G][B*Nd], [G][B*Nd][A]
+    const float *taus;     // [G][B][Nq]
+    const int32_t *act;
+    const float *rew;
+    float *dv, *da, *per_sample;
+    int B, A, Nq, Nd;
+    long long gV, gA, gV2, gA2, gT;  // group strides
+    float gamma;
+};
+
+__device__ __forceinline__ float iqn_quantile(const float *v, const float *adv, int A, int r, int a) {
+    float s = 0.0f;
+    for (int k = 0; k < A; ++k) s = __fadd_rn(s, adv[(size_t)r * A + k]);
+    return __fadd_rn(v[r], __fadd_rn(adv[(size_t)r * A + a], -__fdiv_rn(s, (float)A)));  // customs/iqn.py:133-134
+}
+
+// IQNBrain.learn's loss (iqn_brain.py:23-50,73-113): pairwise quantile Huber, one warp per (group, sample)
+__global__ void iqn_loss_kernel(const IqnArgs p) {
+    const int g = blockIdx.y, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= p.B) return;
+    const int A = p.A, Nq = p.Nq, Nd = p.Nd, b = warp;
+    const float *v0 = p.v0 + (size_t)g * p.gV, *a0 = p.a0 + (size_t)g * p.gA;
+    const float *v1 = p.v1 + (size_t)g * p.gV, *a1 = p.a1 + (size_t)g * p.gA;
+    const float *v2 = p.v2 + (size_t)g * p.gV2, *a2 = p.a2 + (size_t)g * p.gA2;
+    const size_t sb = (size_t)g * p.B + b;
+    const int a_taken = p.act[sb];
+    int best = 0;
+    float best_q = 0.0f;
+    for (int a = 0; a < A; ++a) {  // q_values = quantiles.mean(dim=1); argmax, first maximum
+        float s = 0.0f;
+        for (int i = lane; i < Nq; i += 32) s = __fadd_rn(s, iqn_quantile(v1, a1, A, b * Nq + i, a));
+        s = __fdiv_rn(warp_sum(s), (float)Nq);
+        if (a == 0 || s > best_q) { best_q = s; best = a; }
+    }
+    const float r = p.rew[sb];
+    const float scale = __fdiv_rn(1.0f, __fmul_rn((float)Nd, (float)p.B));
+    float loss = 0.0f;
+    for (int i = lane; i < Nq; i += 32) {
+        const float theta = iqn_quantile(v0, a0, A, b * Nq + i, a_taken);
+        const float tau = p.taus[(size_t)g * p.gT + (size_t)b * Nq + i];
+        float grad = 0.0f;
+        for (int j = 0; j < Nd; ++j) {
+            const float target = __fadd_rn(r, __fmul_rn(p.gamma, iqn_quantile(v2, a2, A, b * Nd + j, best)));
+            const float delta = __fadd_rn(target, -theta);
+            const float ad = fabsf(delta);
+            const float hub = ad <= 1.0f ? __fmul_rn(0.5f, __fmul_rn(delta, delta)) : __fadd_rn(ad, -0.5f);
+            const float w = fabsf(__fadd_rn(tau, delta < 0.0f ? -1.0f : 0.0f));
+            loss = __fadd_rn(loss, __fmul_rn(w, hub));
+            const float dh = ad <= 1.0f ? delta : (delta > 0.0f ? 1.0f : -1.0f);
+            grad = __fadd_rn(grad, -__fmul_rn(w, dh));
+        }
+        const float gl = __fmul_rn(grad, scale);  // d loss / d theta_i
+        const size_t row = (size_t)b * Nq + i;
+        p.dv[(size_t)g * p.gV + row] = gl;
+        const float shared = __fdiv_rn(gl, (float)A);
+        for (int k = 0; k < A; ++k)
+            p.da[(size_t)g * p.gA + row * A + k] = __fadd_rn(k == a_taken ? gl : 0.0f, -shared);
+    }
+    loss = warp_sum(loss);
+    if (lane == 0) p.per_sample[sb] = __fdiv_rn(loss, (float)Nd);  // .sum(dim=1).mean(dim=1)
+}
+
+// Q[g][b][a] = mean over quantiles (customs/iqn.py:138-139)
+__global__ void iqn_q_kernel(const float *v, const float *adv, int B, int A, int Nq, long long gV, long long gA, float *q) {
+    const int g = blockIdx.y, b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int a = 0; a < A; ++a) {
+        float s = 0.0f;
+        for (int i = 0; i < Nq; ++i) s = __fadd_rn(s, iqn_quantile(v + (size_t)g * gV, adv + (size_t)g * gA, A, b * Nq + i, a));
+        q[((size_t)g * B + b) * A + a] = __fdiv_rn(s, (float)Nq);
+    }
+}
+
 // ------------------------------------------------------------------------------ optimizer
 // stage 1: per-block partial sums of squares (fixed order); stage 2 inside the apply kernel
 __global__ void sqnorm_partial_kernel(const float *grads, float *partial, long long P, float scale) {
@@ -558,7 +684,10 @@ struct maexp_learner {
     maexp_learner_cfg cfg;
     int G, B, C, V, A, H, F1, F2, Z, D;  // D = flattened conv output (or C*V*V for the plain MLP)
     int H1, Hp, H2;                      // conv1 out side, pooled side, conv2 out side
-    bool has_conv, dist;
+    bool has_conv, dist, iqn;
+    int Nq, Nd, ncos, rows_max;  // IQN: quantiles, target quantiles, cosines, B * max(Nq, Nd)
+    HeadLayout se;               // IQN state_embedder (customs/iqn.py:51-53)
+    long long o_cw, o_cb;        // IQN cosine_net.net.0
     long long P;                         // parameters per agent
     long long o_c1w, o_c1b, o_c2w, o_c2b;
     std::vector<HeadLayout> heads;
@@ -571,6 +700,10 @@ struct maexp_learner {
         float *col1, *y1, *p, *col2, *y2, *flat, *h[2], *out[2];
         uint8_t *arg;
     } acts[3];
+    struct IqnActs {
+        float *se_h, *psi, *cosf, *phi, *e, *hrow[2], *out[2];
+    } iq[3];
+    float *d_e = nullptr, *d_phi = nullptr, *d_psi = nullptr, *d_hrow = nullptr;
     // backward workspace
     float *d_out[2], *d_h, *d_flat, *d_y2, *d_col2, *d_p, *d_y1, *per_sample, *m_scratch, *partial, *q_tmp;
     int nparts;
@@ -631,64 +764,30 @@ void colsum(cudaStream_t st, int G, const float *ones, const float *X, float *ou
     gemm(st, G, ones, X, out, nullptr, 1, N, M, 0, 0, N, 1, N, 1, 0, gX, gOut, 0);
 }
 
-// forward of one network for all groups; obs [G][B][obs_stride] (C*V*V valid floats per row)
-void forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, maexp_learner::Acts &a) {
-    const int G = h->G, C = h->C, V = h->V, F1 = h->F1, F2 = h->F2, H = h->H, D = h->D;
+// ---- conv trunk: obs [G][B][obs_stride] -> a.flat [G][Bmax][D]
+void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, maexp_learner::Acts &a) {
+    const int G = h->G, C = h->C, V = h->V, F1 = h->F1, F2 = h->F2;
     const long long P = h->P, Bmax = h->B, stride = h->cfg.obs_stride;
-    const float *head_in = obs;
-    long long head_in_row = stride, head_in_g = (long long)B * stride;
-    if (h->has_conv) {
-        const int H1 = h->H1, Hp = h->Hp, H2 = h->H2;
-        const long long gcol1 = Bmax * H1 * H1 * C * 4, gy1 = Bmax * H1 * H1 * F1, gp = Bmax * Hp * Hp * F1;
-        const long long gcol2 = Bmax * H2 * H2 * F1 * 4, gy2 = Bmax * H2 * H2 * F2;
-        im2col_kernel<<<grid1d((long long)B * H1 * H1 * C * 4, G), 256, 0, st>>>(
-            obs, a.col1, B, C, H1, H1, stride, (long long)V * V, V, 1, (long long)B * stride, gcol1);
-        gemm(st, G, a.col1, params + h->o_c1w, a.y1, params + h->o_c1b, B * H1 * H1, F1, C * 4, C * 4, 1, 1, C * 4, F1, 1,
-             gcol1, P, gy1, P);
-        pool_fwd_kernel<<<grid1d((long long)B * Hp * Hp * F1, G), 256, 0, st>>>(a.y1, a.p, a.arg, B, H1, H1, F1, gy1, gp);
-        im2col_kernel<<<grid1d((long long)B * H2 * H2 * F1 * 4, G), 256, 0, st>>>(
-            a.p, a.col2, B, F1, H2, H2, (long long)Hp * Hp * F1, 1, (long long)Hp * F1, F1, gp, gcol2);
-        gemm(st, G, a.col2, params + h->o_c2w, a.y2, params + h->o_c2b, B * H2 * H2, F2, F1 * 4, F1 * 4, 1, 1, F1 * 4, F2,
-             1, gcol2, P, gy2, P);
-        nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, st>>>(a.y2, a.flat, B, H2 * H2, F2, gy2, 0);
-        head_in = a.flat;
-        head_in_row = D;
-        head_in_g = gy2;
-    }
-    for (size_t k = 0; k < h->heads.size(); ++k) {
-        const HeadLayout &hd = h->heads[k];
-        gemm(st, G, head_in, params + hd.w1, a.h[k], params + hd.b1, B, H, D, head_in_row, 1, 1, D, H, 1, head_in_g, P,
-             Bmax * H, P, /*relu=*/1);
-        gemm(st, G, a.h[k], params + hd.w2, a.out[k], params + hd.b2, B, hd.out, H, H, 1, 1, H, hd.out, 1, Bmax * H, P,
-             Bmax * hd.out, P);
-    }
+    const int H1 = h->H1, Hp = h->Hp, H2 = h->H2;
+    const long long gcol1 = Bmax * H1 * H1 * C * 4, gy1 = Bmax * H1 * H1 * F1, gp = Bmax * Hp * Hp * F1;
+    const long long gcol2 = Bmax * H2 * H2 * F1 * 4, gy2 = Bmax * H2 * H2 * F2;
+    im2col_kernel<<<grid1d((long long)B * H1 * H1 * C * 4, G), 256, 0, st>>>(
+        obs, a.col1, B, C, H1, H1, stride, (long long)V * V, V, 1, (long long)B * stride, gcol1);
+    gemm(st, G, a.col1, params + h->o_c1w, a.y1, params + h->o_c1b, B * H1 * H1, F1, C * 4, C * 4, 1, 1, C * 4, F1, 1,
+         gcol1, P, gy1, P);
+    pool_fwd_kernel<<<grid1d((long long)B * Hp * Hp * F1, G), 256, 0, st>>>(a.y1, a.p, a.arg, B, H1, H1, F1, gy1, gp);
+    im2col_kernel<<<grid1d((long long)B * H2 * H2 * F1 * 4, G), 256, 0, st>>>(
+        a.p, a.col2, B, F1, H2, H2, (long long)Hp * Hp * F1, 1, (long long)Hp * F1, F1, gp, gcol2);
+    gemm(st, G, a.col2, params + h->o_c2w, a.y2, params + h->o_c2b, B * H2 * H2, F2, F1 * 4, F1 * 4, 1, 1, F1 * 4, F2,
+         1, gcol2, P, gy2, P);
+    nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, st>>>(a.y2, a.flat, B, H2 * H2, F2, gy2, 0);
 }
 
-// backward of the online net through the activations of pass 0; d_out[k] already filled
-void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
-    const int G = h->G, B = h->B, C = h->C, F1 = h->F1, F2 = h->F2, H = h->H, D = h->D;
-    const long long P = h->P, stride = h->cfg.obs_stride;
+// ---- conv trunk backward from h->d_flat [G][B][D] (activations of pass 0)
+void trunk_backward(maexp_learner *h, cudaStream_t st) {
+    const int G = h->G, B = h->B, C = h->C, F1 = h->F1, F2 = h->F2;
+    const long long P = h->P;
     maexp_learner::Acts &a = h->acts[0];
-    const float *head_in = h->has_conv ? a.flat : obs;
-    const long long head_in_row = h->has_conv ? D : stride, head_in_g = h->has_conv ? (long long)B * D : (long long)B * stride;
-    for (size_t k = 0; k < h->heads.size(); ++k) {
-        const HeadLayout &hd = h->heads[k];
-        const int O = hd.out;
-        // dW2[O,H] = dOut^T h ; db2 ; dh = (dOut W2) * (h > 0)
-        gemm(st, G, h->d_out[k], a.h[k], h->grads + hd.w2, nullptr, O, H, B, 1, O, H, 1, H, 1, (long long)B * O,
-             (long long)B * H, P, 0);
-        colsum(st, G, h->ones, h->d_out[k], h->grads + hd.b2, B, O, (long long)B * O, P);
-        gemm(st, G, h->d_out[k], h->online + hd.w2, h->d_h, nullptr, B, H, O, O, 1, H, 1, H, 1, (long long)B * O, P,
-             (long long)B * H, 0, 0, 0, a.h[k], (long long)B * H);
-        // dW1[H,D] = dh^T x ; db1 ; dflat (+)= dh W1
-        gemm(st, G, h->d_h, head_in, h->grads + hd.w1, nullptr, H, D, B, 1, H, head_in_row, 1, D, 1, (long long)B * H,
-             head_in_g, P, 0);
-        colsum(st, G, h->ones, h->d_h, h->grads + hd.b1, B, H, (long long)B * H, P);
-        if (h->has_conv)
-            gemm(st, G, h->d_h, h->online + hd.w1, h->d_flat, nullptr, B, D, H, H, 1, D, 1, D, 1, (long long)B * H, P,
-                 (long long)B * D, 0, 0, /*accumulate=*/k > 0);
-    }
-    if (!h->has_conv) return;
     const int H1 = h->H1, Hp = h->Hp, H2 = h->H2;
     const long long gcol1 = (long long)B * H1 * H1 * C * 4, gy1 = (long long)B * H1 * H1 * F1, gp = (long long)B * Hp * Hp * F1;
     const long long gcol2 = (long long)B * H2 * H2 * F1 * 4, gy2 = (long long)B * H2 * H2 * F2;
@@ -705,13 +804,111 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
     colsum(st, G, h->ones, h->d_y1, h->grads + h->o_c1b, M1, F1, gy1, P);
 }
 
+// ---- MLP with one hidden ReLU layer on `rows` rows per group (mlp.py:28-34); buffers strided by rows_max
+struct MlpIn {
+    const float *x;
+    long long x_row, x_g;  // row stride and group stride of x
+    int rows;
+    long long rows_max;
+    int din;
+};
+
+void mlp_forward(maexp_learner *h, cudaStream_t st, const float *params, const HeadLayout &hd, const MlpIn &in, float *hbuf,
+                 float *out) {
+    const int G = h->G, H = h->H;
+    const long long P = h->P;
+    gemm(st, G, in.x, params + hd.w1, hbuf, params + hd.b1, in.rows, H, in.din, in.x_row, 1, 1, in.din, H, 1, in.x_g, P,
+         in.rows_max * H, P, /*relu=*/1);
+    gemm(st, G, hbuf, params + hd.w2, out, params + hd.b2, in.rows, hd.out, H, H, 1, 1, H, hd.out, 1, in.rows_max * H, P,
+         in.rows_max * hd.out, P);
+}
+
+// gradients of one MLP's parameters into h->grads; dx (optional, [rows][din], group stride rows_max*din) = or += dh W1
+void mlp_backward(maexp_learner *h, cudaStream_t st, const HeadLayout &hd, const MlpIn &in, const float *dout,
+                  const float *hbuf, float *dhbuf, float *dx, int accumulate_dx) {
+    const int G = h->G, H = h->H, O = hd.out, rows = in.rows;
+    const long long P = h->P, gO = in.rows_max * O, gH = in.rows_max * H;
+    gemm(st, G, dout, hbuf, h->grads + hd.w2, nullptr, O, H, rows, 1, O, H, 1, H, 1, gO, gH, P, 0);
+    colsum(st, G, h->ones, dout, h->grads + hd.b2, rows, O, gO, P);
+    gemm(st, G, dout, h->online + hd.w2, dhbuf, nullptr, rows, H, O, O, 1, H, 1, H, 1, gO, P, gH, 0, 0, 0, hbuf, gH);
+    gemm(st, G, dhbuf, in.x, h->grads + hd.w1, nullptr, H, in.din, rows, 1, H, in.x_row, 1, in.din, 1, gH, in.x_g, P, 0);
+    colsum(st, G, h->ones, dhbuf, h->grads + hd.b1, rows, H, gH, P);
+    if (dx)
+        gemm(st, G, dhbuf, h->online + hd.w1, dx, nullptr, rows, in.din, H, H, 1, in.din, 1, in.din, 1, gH, P,
+             in.rows_max * in.din, 0, 0, accumulate_dx);
+}
+
+// forward of one (non-IQN) network for all groups
+void forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, maexp_learner::Acts &a) {
+    MlpIn in;
+    if (h->has_conv) {
+        trunk_forward(h, st, params, obs, B, a);
+        in = {a.flat, h->D, (long long)h->B * h->D, B, h->B, h->D};
+    } else {
+        in = {obs, h->cfg.obs_stride, (long long)B * h->cfg.obs_stride, B, h->B, h->D};
+    }
+    for (size_t k = 0; k < h->heads.size(); ++k) mlp_forward(h, st, params, h->heads[k], in, a.h[k], a.out[k]);
+}
+
+// backward of the online net through the activations of pass 0; d_out[k] already filled
+void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
+    maexp_learner::Acts &a = h->acts[0];
+    const int B = h->B;
+    MlpIn in;
+    if (h->has_conv) in = {a.flat, h->D, (long long)B * h->D, B, B, h->D};
+    else in = {obs, h->cfg.obs_stride, (long long)B * h->cfg.obs_stride, B, B, h->D};
+    for (size_t k = 0; k < h->heads.size(); ++k)
+        mlp_backward(h, st, h->heads[k], in, h->d_out[k], a.h[k], h->d_h, h->has_conv ? h->d_flat : nullptr, k > 0);
+    if (h->has_conv) trunk_backward(h, st);
+}
+
+// ---- IQN (customs/iqn.py:88-139): quantiles of `nq` taus per sample; taus per sample [G][B][nq] or shared [G][nq]
+void iqn_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, const float *taus, int nq,
+                 int per_sample, int pass) {
+    maexp_learner::Acts &a = h->acts[pass];
+    maexp_learner::IqnActs &q = h->iq[pass];
+    const int G = h->G, D = h->D;
+    const long long P = h->P, Bmax = h->B, R = h->rows_max;
+    trunk_forward(h, st, params, obs, B, a);
+    const MlpIn se_in = {a.flat, D, Bmax * D, B, Bmax, D};
+    mlp_forward(h, st, params, h->se, se_in, q.se_h, q.psi);  // state_embedder
+    const int rows = B * nq;
+    iqn_cos_kernel<<<grid1d((long long)rows * h->ncos, G), 256, 0, st>>>(taus, q.cosf, B, nq, h->ncos, per_sample,
+                                                                         per_sample ? (long long)B * nq : (long long)nq,
+                                                                         R * h->ncos);
+    // phi = relu(cos W^T + b)   (cosine_net.net.0 + ReLU, customs/iqn.py:24)
+    gemm(st, G, q.cosf, params + h->o_cw, q.phi, params + h->o_cb, rows, D, h->ncos, h->ncos, 1, 1, h->ncos, D, 1,
+         R * h->ncos, P, R * D, P, /*relu=*/1);
+    iqn_hadamard_fwd_kernel<<<grid1d((long long)rows * D, G), 256, 0, st>>>(q.psi, q.phi, q.e, B, nq, D, Bmax * D, R * D);
+    const MlpIn e_in = {q.e, D, R * D, rows, R, D};
+    for (int k = 0; k < 2; ++k) mlp_forward(h, st, params, h->heads[k], e_in, q.hrow[k], q.out[k]);
+}
+
+void iqn_backward(maexp_learner *h, cudaStream_t st, int nq) {
+    maexp_learner::Acts &a = h->acts[0];
+    maexp_learner::IqnActs &q = h->iq[0];
+    const int G = h->G, B = h->B, D = h->D, rows = B * nq;
+    const long long P = h->P, R = h->rows_max;
+    const MlpIn e_in = {q.e, D, R * D, rows, R, D};
+    for (int k = 0; k < 2; ++k) mlp_backward(h, st, h->heads[k], e_in, h->d_out[k], q.hrow[k], h->d_hrow, h->d_e, k > 0);
+    iqn_hadamard_bwd_kernel<<<grid1d((long long)B * D, G), 256, 0, st>>>(h->d_e, q.psi, q.phi, h->d_phi, h->d_psi, B, nq, D,
+                                                                         (long long)B * D, R * D);
+    // cosine net: dW[D,ncos] = dphi^T cos ; db = colsum(dphi)
+    gemm(st, G, h->d_phi, q.cosf, h->grads + h->o_cw, nullptr, D, h->ncos, rows, 1, D, h->ncos, 1, h->ncos, 1, R * D,
+         R * h->ncos, P, 0);
+    colsum(st, G, h->ones, h->d_phi, h->grads + h->o_cb, rows, D, R * D, P);
+    const MlpIn se_in = {a.flat, D, (long long)B * D, B, B, D};
+    mlp_backward(h, st, h->se, se_in, h->d_psi, q.se_h, h->d_h, h->d_flat, 0);
+    trunk_backward(h, st);
+}
+
 }  // namespace
 
 extern "C" {
 
 int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (!cfg || !out) return fail("maexp_learner_create: null argument");
-    if (cfg->kind < MAEXP_LEARNER_DQN_CONV_MLP || cfg->kind > MAEXP_LEARNER_DQN_MLP)
+    if (cfg->kind < MAEXP_LEARNER_DQN_CONV_MLP || cfg->kind > MAEXP_LEARNER_IQN)
         return fail("maexp_learner_create: unknown kind");
     if (cfg->num_agents < 1 || cfg->batch_size < 1) return fail("maexp_learner_create: bad num_agents / batch_size");
     if (cfg->num_actions < 1 || cfg->num_actions > kMaxActions) return fail("maexp_learner_create: num_actions must be in 1..8");
@@ -721,6 +918,12 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;
     h->has_conv = cfg->kind != MAEXP_LEARNER_DQN_MLP;
     h->dist = cfg->kind == MAEXP_LEARNER_C51 || cfg->kind == MAEXP_LEARNER_QR;
+    h->iqn = cfg->kind == MAEXP_LEARNER_IQN;
+    h->Nq = h->iqn ? cfg->num_atoms : 0;
+    h->Nd = h->iqn ? cfg->num_quantiles_dash : 0;
+    h->ncos = h->iqn ? cfg->num_cosines : 0;
+    if (h->iqn && (h->Nq < 1 || h->Nd < 1 || h->ncos < 1)) { delete h; return fail("maexp_learner_create: IQN needs num_atoms (quantiles), num_quantiles_dash, num_cosines >= 1"); }
+    h->rows_max = h->B * (h->Nq > h->Nd ? h->Nq : h->Nd);
     h->Z = h->dist ? cfg->num_atoms : 1;
     if (h->dist && (h->Z < 1 || h->Z > 32 * kMaxAtomsPerLane)) { delete h; return fail("maexp_learner_create: num_atoms must be in 1..128"); }
     if (cfg->obs_stride < h->C * h->V * h->V) { delete h; return fail("maexp_learner_create: obs_stride < C*V*V"); }
@@ -753,7 +956,15 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         hd.out = outn;
         h->heads.push_back(hd);
     };
-    if (h->dist) {
+    if (h->iqn) {  // state_dict order of customs/iqn.py:43-67
+        add_head("state_embedder", h->D);
+        h->se = h->heads.back();
+        h->heads.pop_back();
+        h->o_cw = add("cosine_net.net.0.weight", (long long)h->D * h->ncos);
+        h->o_cb = add("cosine_net.net.0.bias", h->D);
+        add_head("fc_V", 1);
+        add_head("fc_A", h->A);
+    } else if (h->dist) {
         add_head("fc_V", h->Z);           // categorical_dqn.py:47-52, qr_dqn.py:37-42
         add_head("fc_A", h->A * h->Z);
     } else if (h->has_conv) {
@@ -789,7 +1000,26 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             rc |= lalloc(h, &a.out[j], G * B * h->heads[j].out);
         }
     }
-    for (size_t j = 0; j < h->heads.size(); ++j) rc |= lalloc(h, &h->d_out[j], G * B * h->heads[j].out);
+    const long long R = h->iqn ? h->rows_max : B;
+    for (size_t j = 0; j < h->heads.size(); ++j) rc |= lalloc(h, &h->d_out[j], G * R * h->heads[j].out);
+    if (h->iqn) {
+        for (int k = 0; k < 3; ++k) {
+            maexp_learner::IqnActs &q = h->iq[k];
+            rc |= lalloc(h, &q.se_h, G * B * h->H);
+            rc |= lalloc(h, &q.psi, G * B * h->D);
+            rc |= lalloc(h, &q.cosf, G * R * h->ncos);
+            rc |= lalloc(h, &q.phi, G * R * h->D);
+            rc |= lalloc(h, &q.e, G * R * h->D);
+            for (int j = 0; j < 2; ++j) {
+                rc |= lalloc(h, &q.hrow[j], G * R * h->H);
+                rc |= lalloc(h, &q.out[j], G * R * h->heads[j].out);
+            }
+        }
+        rc |= lalloc(h, &h->d_e, G * R * h->D);
+        rc |= lalloc(h, &h->d_phi, G * R * h->D);
+        rc |= lalloc(h, &h->d_psi, G * B * h->D);
+        rc |= lalloc(h, &h->d_hrow, G * R * h->H);
+    }
     rc |= lalloc(h, &h->d_h, G * B * h->H);
     if (h->has_conv) {
         rc |= lalloc(h, &h->d_flat, G * B * h->D);
@@ -852,6 +1082,7 @@ int maexp_learner_sync_target(maexp_learner *h, void *stream) {
 int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int use_target, float *q_out, void *stream) {
     if (!h || !obs || !q_out) return fail("maexp_learner_q_values: null argument");
     if (batch < 1 || batch > h->B) return fail("maexp_learner_q_values: batch must be in 1..batch_size");
+    if (h->iqn) return fail("maexp_learner_q_values: use maexp_learner_q_values_iqn for IQN");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     maexp_learner::Acts &a = h->acts[1];
     g_splitk_ws = h->splitk_ws;
@@ -872,6 +1103,7 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
                         const float *rewards, const uint8_t *dones, float *loss_out, void *stream) {
     if (!h || !obs || !next_obs || !actions || !rewards || !dones) return fail("maexp_learner_grads: null argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->iqn) return fail("maexp_learner_grads: use maexp_learner_grads_iqn for IQN");
     const int G = h->G, B = h->B, A = h->A, Z = h->Z;
     g_splitk_ws = h->splitk_ws;
     forward(h, st, h->online, obs, B, h->acts[0]);
@@ -895,6 +1127,50 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
     }
     mean_kernel<<<G, 256, 0, st>>>(h->per_sample, loss_out ? loss_out : h->q_tmp, B);
     backward(h, st, obs);
+    MAEXP_CUDA_L(cudaGetLastError());
+    return 0;
+}
+
+int maexp_learner_q_values_iqn(maexp_learner *h, const float *obs, int batch, int use_target, const float *tau_sel,
+                               float *q_out, void *stream) {
+    if (!h || !obs || !tau_sel || !q_out) return fail("maexp_learner_q_values_iqn: null argument");
+    if (!h->iqn) return fail("maexp_learner_q_values_iqn: not an IQN learner");
+    if (batch < 1 || batch > h->B) return fail("maexp_learner_q_values_iqn: batch must be in 1..batch_size");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    g_splitk_ws = h->splitk_ws;
+    iqn_forward(h, st, use_target ? h->target : h->online, obs, batch, tau_sel, h->Nq, /*per_sample=*/0, 1);
+    iqn_q_kernel<<<dim3((batch + 127) / 128, h->G), 128, 0, st>>>(h->iq[1].out[0], h->iq[1].out[1], batch, h->A, h->Nq,
+                                                                  h->rows_max, h->rows_max * h->A, q_out);
+    MAEXP_CUDA_L(cudaGetLastError());
+    return 0;
+}
+
+int maexp_learner_grads_iqn(maexp_learner *h, const float *obs, const float *next_obs, const int32_t *actions,
+                            const float *rewards, const uint8_t *dones, const float *taus, const float *tau_dashes,
+                            const float *tau_sel, float *loss_out, void *stream) {
+    if (!h || !obs || !next_obs || !actions || !rewards || !taus || !tau_dashes || !tau_sel)
+        return fail("maexp_learner_grads_iqn: null argument");
+    if (!h->iqn) return fail("maexp_learner_grads_iqn: not an IQN learner");
+    (void)dones;  // IQNBrain.learn never masks terminal states (iqn_brain.py:104-106)
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int G = h->G, B = h->B;
+    g_splitk_ws = h->splitk_ws;
+    iqn_forward(h, st, h->online, obs, B, taus, h->Nq, 1, 0);
+    iqn_forward(h, st, h->online, next_obs, B, tau_sel, h->Nq, 0, 1);
+    iqn_forward(h, st, h->target, next_obs, B, tau_dashes, h->Nd, 1, 2);
+    IqnArgs p;
+    p.v0 = h->iq[0].out[0]; p.a0 = h->iq[0].out[1];
+    p.v1 = h->iq[1].out[0]; p.a1 = h->iq[1].out[1];
+    p.v2 = h->iq[2].out[0]; p.a2 = h->iq[2].out[1];
+    p.taus = taus; p.act = actions; p.rew = rewards;
+    p.dv = h->d_out[0]; p.da = h->d_out[1]; p.per_sample = h->per_sample;
+    p.B = B; p.A = h->A; p.Nq = h->Nq; p.Nd = h->Nd;
+    p.gV = h->rows_max; p.gA = h->rows_max * h->A; p.gV2 = h->rows_max; p.gA2 = h->rows_max * h->A;
+    p.gT = (long long)B * h->Nq;
+    p.gamma = h->cfg.gamma;
+    iqn_loss_kernel<<<dim3((B * 32 + 255) / 256, G), 256, 0, st>>>(p);
+    mean_kernel<<<G, 256, 0, st>>>(h->per_sample, loss_out ? loss_out : h->q_tmp, B);
+    iqn_backward(h, st, h->Nq);
     MAEXP_CUDA_L(cudaGetLastError());
     return 0;
 }

@@ -23,8 +23,10 @@ def configs():
     # only read to size a constant attention placeholder (da3_brain.py:107-113)
     dqn = c2.merged_with(brain="da3_baseline", batch_size=B, observation_noise=False)
     dqn["model"] = dict(dqn.model, name="da3_baseline", patch_size=1, num_heads=4)
+    iqn = c3.merged_with(batch_size=B, brain="iqn")
+    iqn["model"] = dict(iqn.model, name="iqn", num_quantiles=4, num_quantiles_dash=4, num_cosines=4)
     return {"dqn_conv_mlp": (dqn, [7, 7, 7]), "c51": (c5.merged_with(batch_size=B), [3, 7, 7]),
-            "qr": (c3.merged_with(batch_size=B), [3, 7, 7])}
+            "qr": (c3.merged_with(batch_size=B), [3, 7, 7]), "iqn": (iqn, [3, 7, 7])}
 
 
 def synthetic_batch(shape, seed):
@@ -59,18 +61,36 @@ def main():
                 q0 = torch.sum(brain.network({"local": batch["obs"].clone()}, ApplySoftmax.NORMAL) * brain.support, dim=2)
             elif kind == "qr":
                 q0 = brain.network({"local": batch["obs"].clone()}).mean(dim=2)
+            elif kind == "iqn":
+                tau0 = torch.rand(1, 4)
+                q0 = brain.network({"local": batch["obs"].clone()}, external_taus=tau0)
             else:
                 q0 = brain.network({"local": batch["obs"].clone()})
-        losses = []
+        losses, drawn = [], []
+        real_rand = torch.rand
+
+        def recording_rand(*a, **kw):  # iqn_brain.py:74,87 and customs/iqn.py:106 draw their fractions with torch.rand
+            kw.pop("device", None)
+            t = real_rand(*a, **kw)
+            drawn.append(t.clone())
+            return t
         for _ in range(2):
+            torch.rand = recording_rand if kind == "iqn" else real_rand
             out = brain.learn({"local": batch["obs"].clone()}, batch["actions"].clone(), batch["rewards"].clone(),
                               batch["dones"].clone(), {"local": batch["next_obs"].clone()})
+            torch.rand = real_rand
             losses.append(float(out["total_loss"] if isinstance(out, dict) else out))
         final = {k: v.detach().clone() for k, v in brain.network.state_dict().items()}
         arrays = {"init/" + k: v.numpy() for k, v in init.items()}
         arrays.update({"target/" + k: v.numpy() for k, v in tgt.items()})
         arrays.update({"final/" + k: v.numpy() for k, v in final.items()})
         arrays.update({"batch/" + k: v.numpy() for k, v in batch.items()})
+        if kind == "iqn":  # per learn call: taus [B,N], tau_sel [1,N], tau_dashes [B,N']
+            assert len(drawn) == 6
+            for u in range(2):
+                arrays[f"taus/{u}/taus"], arrays[f"taus/{u}/sel"], arrays[f"taus/{u}/dash"] = (
+                    drawn[3 * u].numpy(), drawn[3 * u + 1].numpy(), drawn[3 * u + 2].numpy())
+            arrays["tau0"] = tau0.numpy()
         path = os.path.join(GOLDEN, f"learner_{kind}.npz")
         np.savez_compressed(path, losses=np.array(losses, np.float64), q0=q0.numpy(), shape=np.array(shape),
                             gamma=float(cfg.gamma), **arrays)

@@ -10,14 +10,19 @@ from oracle.torch_learner import TorchLearner
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KINDS = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLDEN, "learner_*.npz")))
-ATOMS = {"dqn_conv_mlp": 1, "c51": 51, "qr": 100}
+ATOMS = {"dqn_conv_mlp": 1, "c51": 51, "qr": 100, "iqn": 4}
 
 
 def load(kind):
     z = np.load(os.path.join(GOLDEN, f"learner_{kind}.npz"))
     part = lambda pre: {k[len(pre):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre)}
-    return {"init": part("init/"), "target": part("target/"), "final": part("final/"), "batch": part("batch/"),
-            "losses": z["losses"], "q0": torch.from_numpy(z["q0"]), "gamma": float(z["gamma"])}
+    fix = {"init": part("init/"), "target": part("target/"), "final": part("final/"), "batch": part("batch/"),
+           "losses": z["losses"], "q0": torch.from_numpy(z["q0"]), "gamma": float(z["gamma"])}
+    if kind == "iqn":  # the fractions the reference drew: per update (taus, tau_dashes, tau_sel), and q0's tau
+        fix["taus"] = [(torch.from_numpy(z[f"taus/{u}/taus"]), torch.from_numpy(z[f"taus/{u}/dash"]),
+                        torch.from_numpy(z[f"taus/{u}/sel"])) for u in range(2)]
+        fix["tau0"] = torch.from_numpy(z["tau0"])
+    return fix
 
 
 def make_oracle(kind, fix):
@@ -30,9 +35,11 @@ def make_oracle(kind, fix):
 def test_torch_oracle_matches_reference_brain(kind):
     fix = load(kind)
     o, b = make_oracle(kind, fix), fix["batch"]
-    assert torch.allclose(o.q_values(b["obs"]), fix["q0"], rtol=1e-6, atol=1e-6)
-    for want in fix["losses"]:
-        loss, _ = o.learn(b["obs"], b["next_obs"], b["actions"], b["rewards"], b["dones"])
+    q0 = o.q_values_iqn(b["obs"], fix["tau0"]) if kind == "iqn" else o.q_values(b["obs"])
+    assert torch.allclose(q0, fix["q0"], rtol=1e-6, atol=1e-6)
+    for u, want in enumerate(fix["losses"]):
+        loss, _ = o.learn(b["obs"], b["next_obs"], b["actions"], b["rewards"], b["dones"],
+                          taus=fix["taus"][u] if kind == "iqn" else None)
         assert abs(float(loss) - want) <= 1e-6 * max(1.0, abs(want)), (float(loss), want)
     for k, v in fix["final"].items():
         assert torch.allclose(o.sd[k].detach(), v, rtol=1e-5, atol=1e-6), k
