@@ -171,7 +171,8 @@ enum {
     MAEXP_LEARNER_C51 = 1,          /* categorical_dqn_brain.py:42-89, customs/categorical_dqn.py:28-79 */
     MAEXP_LEARNER_QR = 2,           /* qr_dqn_brain.py:81-119, customs/qr_dqn.py:20-65 */
     MAEXP_LEARNER_DQN_MLP = 3,      /* model mlp on the flattened observation (mlp.py:14-34) */
-    MAEXP_LEARNER_IQN = 4           /* iqn_brain.py:60-115, customs/iqn.py:21-162 (num_atoms = model.num_quantiles) */
+    MAEXP_LEARNER_IQN = 4,          /* iqn_brain.py:60-115, customs/iqn.py:21-162 (num_atoms = model.num_quantiles) */
+    MAEXP_LEARNER_DA3 = 5           /* brain da3 + model da3, local view: da3_brain.py:58-89, customs/da3.py:22-96, vit.py */
 };
 enum { MAEXP_BUF_ONLINE = 0, MAEXP_BUF_TARGET = 1, MAEXP_BUF_GRADS = 2, MAEXP_BUF_SQUARE_AVG = 3, MAEXP_BUF_SUPPORT = 4 };
 
@@ -190,6 +191,7 @@ typedef struct {
     float learning_rate, alpha, one_minus_alpha, eps;  /* optim.RMSprop, configs/opt/rmsprop.yaml */
     float max_norm;          /* clip_grad_norm_: 0.1 (dqn, qr, iqn), 10 (c51) */
     int32_t num_quantiles_dash, num_cosines;  /* IQN: model.num_quantiles_dash, model.num_cosines */
+    int32_t embed_dim, num_heads, mlp_hidden, block_loop;  /* DA3: model.embed_dim, num_heads, int(embed_dim*mlp_ratio), block_loop */
 } maexp_learner_cfg;
 
 typedef struct maexp_learner maexp_learner;

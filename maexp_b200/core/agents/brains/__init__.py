@@ -16,7 +16,7 @@ logger = initialize_logging(__name__)
 
 # brain name -> (learner kind for conv models, clip max_norm)      brains/*.py
 _BRAINS = {"dqn": ("dqn_conv_mlp", 0.1), "da3_baseline": ("dqn_conv_mlp", 0.1), "categorical_dqn": ("c51", 10.0),
-           "qr_dqn": ("qr", 0.1), "iqn": ("iqn", 0.1)}
+           "qr_dqn": ("qr", 0.1), "iqn": ("iqn", 0.1), "da3": ("da3", 0.1)}
 
 
 def learner_kind(config):
@@ -28,6 +28,12 @@ def learner_kind(config):
         if kind != "dqn_conv_mlp":
             raise ValueError("model=mlp is only defined for the dqn brain")
         kind = "dqn_mlp"
+    elif config.model.name == "da3" or kind == "da3":
+        if kind != "da3" or config.model.name != "da3":
+            raise ValueError("brain=da3 and model=da3 go together (da3_brain.py, customs/da3.py)")
+        if config.observation_area_mask == "merged" or int(config.model.patch_size) != 1 or \
+                config.model.get("attention") == "hard" or config.get("objects_channel"):
+            raise ValueError("DA3 is implemented for the local/relative view with patch_size=1 and soft attention")
     elif config.model.name not in ("conv_mlp", "da3_baseline", "categorical_dqn", "qr_dqn", "iqn"):
         logger.warning(f"Unexpected network is given. config.model.name: {config.model.name}")
         raise ValueError()
@@ -51,7 +57,11 @@ class LearnerGroup:
         cfg = _lib.LearnerCfg()
         cfg.kind = _lib.LEARNER_KINDS[self.kind]
         cfg.num_agents, cfg.batch_size, cfg.channels, cfg.visible_range = self.G, self.B, C_, V
-        cfg.num_actions, cfg.hidden = self.A, int(m.hidden_layer_sizes[0])
+        cfg.num_actions = self.A
+        cfg.hidden = int(m.hidden_layer_sizes[0]) if self.kind != "da3" else 0
+        if self.kind == "da3":
+            cfg.embed_dim, cfg.num_heads, cfg.block_loop = int(m.embed_dim), int(m.num_heads), int(m.block_loop)
+            cfg.mlp_hidden = int(int(m.embed_dim) * float(m.mlp_ratio))
         cfg.conv1_channels = int(m.get("hidden_channels", [32])[0])
         cfg.conv2_channels = int(m.get("output_channel", 64))
         self.Z = int(m.num_atoms) if self.kind == "c51" else int(m.num_quantiles) if self.kind in ("qr", "iqn") else 1

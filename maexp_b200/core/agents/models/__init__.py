@@ -64,6 +64,52 @@ class _IQN(nn.Module):
         self.fc_A = _MLP(config, d, act_size)
 
 
+class _Attention(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.qkv = nn.Linear(dim, dim * 3, bias=False)  # vit.py:111 (qkv_bias=False)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _VitMlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Block(nn.Module):
+    """vit.py:50-80 parameter layout."""
+
+    def __init__(self, dim, mlp_ratio):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = _Attention(dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = _VitMlp(dim, int(dim * mlp_ratio))
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, patch_size, in_chans, embed_dim):
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+
+class _DA3(nn.Module):
+    """Parameter layout and construction order of customs/da3.py:22-60."""
+
+    def __init__(self, config, obs_shape, act_size):
+        super().__init__()
+        m = config.model
+        tokens = (int(obs_shape[1]) // int(m.patch_size)) * (int(obs_shape[2]) // int(m.patch_size)) + 1
+        self.patch_embed = _PatchEmbed(int(m.patch_size), int(obs_shape[0]), int(m.embed_dim))
+        self.saliency_vector = nn.Parameter(torch.zeros(1, 1, int(m.embed_dim)))
+        self.pos_embed = nn.Parameter(torch.zeros(1, tokens, int(m.embed_dim)))
+        self.blocks = nn.ModuleList([_Block(int(m.embed_dim), float(m.mlp_ratio)) for _ in range(int(m.block_loop))])
+        self.norm = nn.LayerNorm(int(m.embed_dim))
+        self.drl_head = nn.Linear(int(m.embed_dim), act_size)
+
+
 def build_reference_modules(config, obs_shape, act_size):
     name = config.model.name
     if name == "mlp":  # SURVEY.md appendix E-2: the flattened observation feeds the MLP
@@ -78,4 +124,6 @@ def build_reference_modules(config, obs_shape, act_size):
         return _ConvHeads(config, obs_shape, [("fc_V", z), ("fc_A", act_size * z)])
     if name == "iqn":
         return _IQN(config, obs_shape, act_size)
+    if name == "da3":
+        return _DA3(config, obs_shape, act_size)
     raise ValueError(name)

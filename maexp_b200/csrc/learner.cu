@@ -624,6 +624,233 @@ __global__ void iqn_q_kernel(const float *v, const float *adv, int B, int A, int
     }
 }
 
+
+// ------------------------------------------------------------------------------ DA3 (ViT) pieces
+// patches[g][(b,pos)][c] = obs[g][b][c*VV + pos]   (PatchEmbed with patch_size 1 is a per-pixel linear map, vit.py:34-47)
+__global__ void da3_patch_gather_kernel(const float *obs, float *patches, int B, int C, int VV, long long stride,
+                                        long long gObs, long long gP) {
+    const int g = blockIdx.y;
+    const long long total = (long long)B * VV * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int pos = (int)((i / C) % VV);
+        const long long b = i / ((long long)C * VV);
+        patches[(size_t)g * gP + i] = obs[(size_t)g * gObs + b * stride + (long long)c * VV + pos];
+    }
+}
+
+// x0[b][t] = (t == 0 ? saliency_vector : tok[b][t-1]) + pos_embed[t]     (da3.py:77-83)
+__global__ void da3_tokens_kernel(const float *tok, const float *sal, const float *pos, float *x0, int B, int Tn, int E,
+                                  long long gTok, long long gX, long long P) {
+    const int g = blockIdx.y;
+    const long long total = (long long)B * Tn * E;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % E);
+        const int t = (int)((i / E) % Tn);
+        const long long b = i / ((long long)E * Tn);
+        const float base = t == 0 ? sal[(size_t)g * P + d] : tok[(size_t)g * gTok + (b * (Tn - 1) + (t - 1)) * E + d];
+        x0[(size_t)g * gX + i] = __fadd_rn(base, pos[(size_t)g * P + (size_t)t * E + d]);
+    }
+}
+
+// nn.LayerNorm(E), eps 1e-5, one warp per row; rows may be strided (final norm reads token 0 of every sample)
+__global__ void layernorm_fwd_kernel(const float *x, long long x_row, const float *gamma, const float *beta, float *y,
+                                     float *mean_out, float *rstd_out, int rows, int E, long long gX, long long gY,
+                                     long long gS, long long P) {
+    const int g = blockIdx.y, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float *xr = x + (size_t)g * gX + (size_t)warp * x_row;
+    float s = 0.0f;
+    for (int d = lane; d < E; d += 32) s = __fadd_rn(s, xr[d]);
+    const float mean = __fdiv_rn(warp_sum(s), (float)E);
+    float v = 0.0f;
+    for (int d = lane; d < E; d += 32) {
+        const float c = __fadd_rn(xr[d], -mean);
+        v = __fadd_rn(v, __fmul_rn(c, c));
+    }
+    const float var = __fdiv_rn(warp_sum(v), (float)E);
+    const float rstd = __fdiv_rn(1.0f, sqrtf(__fadd_rn(var, 1e-5f)));
+    for (int d = lane; d < E; d += 32) {
+        const float xh = __fmul_rn(__fadd_rn(xr[d], -mean), rstd);
+        y[(size_t)g * gY + (size_t)warp * E + d] = __fadd_rn(__fmul_rn(xh, gamma[(size_t)g * P + d]), beta[(size_t)g * P + d]);
+    }
+    if (lane == 0) {
+        mean_out[(size_t)g * gS + warp] = mean;
+        rstd_out[(size_t)g * gS + warp] = rstd;
+    }
+}
+
+// dx (+)= LN backward; gx = dy * xhat (for d gamma = column sum of gx, d beta = column sum of dy)
+__global__ void layernorm_bwd_kernel(const float *dy, const float *x, long long x_row, const float *gamma, const float *mean_in,
+                                     const float *rstd_in, float *dx, long long dx_row, int accumulate, float *gx, int rows,
+                                     int E, long long gDy, long long gX, long long gDx, long long gS, long long P) {
+    const int g = blockIdx.y, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float *xr = x + (size_t)g * gX + (size_t)warp * x_row, *dyr = dy + (size_t)g * gDy + (size_t)warp * E;
+    const float mean = mean_in[(size_t)g * gS + warp], rstd = rstd_in[(size_t)g * gS + warp];
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int d = lane; d < E; d += 32) {
+        const float xh = __fmul_rn(__fadd_rn(xr[d], -mean), rstd);
+        const float dg = __fmul_rn(dyr[d], gamma[(size_t)g * P + d]);
+        s1 = __fadd_rn(s1, dg);
+        s2 = __fadd_rn(s2, __fmul_rn(dg, xh));
+        gx[(size_t)g * gDy + (size_t)warp * E + d] = __fmul_rn(dyr[d], xh);
+    }
+    s1 = __fdiv_rn(warp_sum(s1), (float)E);
+    s2 = __fdiv_rn(warp_sum(s2), (float)E);
+    float *dxr = dx + (size_t)g * gDx + (size_t)warp * dx_row;
+    for (int d = lane; d < E; d += 32) {
+        const float xh = __fmul_rn(__fadd_rn(xr[d], -mean), rstd);
+        const float dg = __fmul_rn(dyr[d], gamma[(size_t)g * P + d]);
+        const float v = __fmul_rn(rstd, __fadd_rn(__fadd_rn(dg, -s1), -__fmul_rn(xh, s2)));
+        dxr[d] = accumulate ? __fadd_rn(dxr[d], v) : v;
+    }
+}
+
+constexpr int kMaxTokens = 96, kMaxHeadDim = 32;
+
+// Attention.forward (vit.py:116-132) for one (group, sample, head) per block; thread t owns query token t
+__global__ void __launch_bounds__(128) da3_attn_fwd_kernel(const float *qkv, float *probs, float *out, int B, int Tn, int E,
+                                                           int heads, float scale, long long gQ, long long gPr, long long gO) {
+    __shared__ float sk[kMaxTokens][kMaxHeadDim + 1], sv[kMaxTokens][kMaxHeadDim + 1];
+    const int g = blockIdx.z, b = blockIdx.y, h = blockIdx.x, dh = E / heads, t = threadIdx.x;
+    const float *base = qkv + (size_t)g * gQ + (size_t)b * Tn * 3 * E;
+    for (int i = threadIdx.x; i < Tn * dh; i += blockDim.x) {
+        const int u = i / dh, d = i - u * dh;
+        sk[u][d] = base[(size_t)u * 3 * E + E + h * dh + d];
+        sv[u][d] = base[(size_t)u * 3 * E + 2 * E + h * dh + d];
+    }
+    __syncthreads();
+    if (t >= Tn) return;
+    float q[kMaxHeadDim];
+    for (int d = 0; d < dh; ++d) q[d] = base[(size_t)t * 3 * E + h * dh + d];
+    float *pr = probs + (size_t)g * gPr + (((size_t)b * heads + h) * Tn + t) * Tn;
+    float mx = -INFINITY;
+    for (int u = 0; u < Tn; ++u) {
+        float s = 0.0f;
+        for (int d = 0; d < dh; ++d) s = __fadd_rn(s, __fmul_rn(q[d], sk[u][d]));
+        s = __fmul_rn(s, scale);
+        pr[u] = s;
+        mx = fmaxf(mx, s);
+    }
+    float se = 0.0f;
+    for (int u = 0; u < Tn; ++u) {
+        const float e = expf(__fadd_rn(pr[u], -mx));
+        pr[u] = e;
+        se = __fadd_rn(se, e);
+    }
+    float o[kMaxHeadDim];
+    for (int d = 0; d < dh; ++d) o[d] = 0.0f;
+    for (int u = 0; u < Tn; ++u) {
+        const float pu = __fdiv_rn(pr[u], se);
+        pr[u] = pu;
+        for (int d = 0; d < dh; ++d) o[d] = __fadd_rn(o[d], __fmul_rn(pu, sv[u][d]));
+    }
+    float *orow = out + (size_t)g * gO + ((size_t)b * Tn + t) * E + h * dh;
+    for (int d = 0; d < dh; ++d) orow[d] = o[d];
+}
+
+// backward of the attention core: d(out) -> d(qkv); two phases with a barrier, fixed summation order
+__global__ void __launch_bounds__(128) da3_attn_bwd_kernel(const float *qkv, const float *probs, const float *dout,
+                                                           float *dqkv, int B, int Tn, int E, int heads, float scale,
+                                                           long long gQ, long long gPr, long long gO) {
+    extern __shared__ float smem_attn[];
+    const int g = blockIdx.z, b = blockIdx.y, h = blockIdx.x, dh = E / heads, t = threadIdx.x;
+    float *sq = smem_attn;                  // [Tn][dh]
+    float *sk = sq + Tn * dh;               // [Tn][dh]
+    float *sv = sk + Tn * dh;               // [Tn][dh]
+    float *sdo = sv + Tn * dh;              // [Tn][dh]
+    float *sds = sdo + Tn * dh;             // [Tn][Tn]  dS
+    const float *base = qkv + (size_t)g * gQ + (size_t)b * Tn * 3 * E;
+    const float *dob = dout + (size_t)g * gO + (size_t)b * Tn * E;
+    for (int i = threadIdx.x; i < Tn * dh; i += blockDim.x) {
+        const int u = i / dh, d = i - u * dh;
+        sq[i] = base[(size_t)u * 3 * E + h * dh + d];
+        sk[i] = base[(size_t)u * 3 * E + E + h * dh + d];
+        sv[i] = base[(size_t)u * 3 * E + 2 * E + h * dh + d];
+        sdo[i] = dob[(size_t)u * E + h * dh + d];
+    }
+    __syncthreads();
+    const float *pr = probs + (size_t)g * gPr + (((size_t)b * heads + h) * Tn) * Tn;
+    float *dq_out = dqkv + (size_t)g * gQ + (size_t)b * Tn * 3 * E;
+    if (t < Tn) {
+        // dP[t,u] = dO_t . v_u ; dS = P * (dP - sum_u dP*P) ; dq_t = scale * sum_u dS[t,u] k_u
+        float dot = 0.0f;
+        for (int u = 0; u < Tn; ++u) {
+            float dp = 0.0f;
+            for (int d = 0; d < dh; ++d) dp = __fadd_rn(dp, __fmul_rn(sdo[t * dh + d], sv[u * dh + d]));
+            sds[t * Tn + u] = dp;
+            dot = __fadd_rn(dot, __fmul_rn(dp, pr[t * Tn + u]));
+        }
+        float dq[kMaxHeadDim];
+        for (int d = 0; d < dh; ++d) dq[d] = 0.0f;
+        for (int u = 0; u < Tn; ++u) {
+            const float ds = __fmul_rn(pr[t * Tn + u], __fadd_rn(sds[t * Tn + u], -dot));
+            sds[t * Tn + u] = ds;
+            for (int d = 0; d < dh; ++d) dq[d] = __fadd_rn(dq[d], __fmul_rn(ds, sk[u * dh + d]));
+        }
+        for (int d = 0; d < dh; ++d) dq_out[(size_t)t * 3 * E + h * dh + d] = __fmul_rn(dq[d], scale);
+    }
+    __syncthreads();
+    if (t < Tn) {
+        // key/value token u = t: dk_u = scale * sum_t' dS[t',u] q_t' ; dv_u = sum_t' P[t',u] dO_t'
+        const int u = t;
+        float dk[kMaxHeadDim], dv[kMaxHeadDim];
+        for (int d = 0; d < dh; ++d) dk[d] = dv[d] = 0.0f;
+        for (int tq = 0; tq < Tn; ++tq) {
+            const float ds = sds[tq * Tn + u], pu = pr[tq * Tn + u];
+            for (int d = 0; d < dh; ++d) {
+                dk[d] = __fadd_rn(dk[d], __fmul_rn(ds, sq[tq * dh + d]));
+                dv[d] = __fadd_rn(dv[d], __fmul_rn(pu, sdo[tq * dh + d]));
+            }
+        }
+        for (int d = 0; d < dh; ++d) {
+            dq_out[(size_t)u * 3 * E + E + h * dh + d] = __fmul_rn(dk[d], scale);
+            dq_out[(size_t)u * 3 * E + 2 * E + h * dh + d] = dv[d];
+        }
+    }
+}
+
+// nn.GELU() (exact erf form) forward / backward
+__global__ void gelu_fwd_kernel(const float *x, float *y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        y[i] = __fmul_rn(__fmul_rn(0.5f, v), __fadd_rn(1.0f, erff(__fmul_rn(v, 0.70710678118654752440f))));
+    }
+}
+__global__ void gelu_bwd_kernel(const float *x, const float *dy, float *dx, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        const float cdf = __fmul_rn(0.5f, __fadd_rn(1.0f, erff(__fmul_rn(v, 0.70710678118654752440f))));
+        const float pdf = __fmul_rn(0.39894228040143267794f, expf(__fmul_rn(-0.5f, __fmul_rn(v, v))));
+        dx[i] = __fmul_rn(dy[i], __fadd_rn(cdf, __fmul_rn(v, pdf)));
+    }
+}
+
+// dx2[b][t] = (t == 0) ? d_token0[b] : 0   (only the saliency token feeds the head, da3.py:90-91)
+__global__ void da3_scatter_token0_kernel(const float *dtok0, float *dx, int B, int Tn, int E, long long gT, long long gX) {
+    const int g = blockIdx.y;
+    const long long total = (long long)B * Tn * E;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % E);
+        const int t = (int)((i / E) % Tn);
+        const long long b = i / ((long long)E * Tn);
+        dx[(size_t)g * gX + i] = t == 0 ? dtok0[(size_t)g * gT + b * E + d] : 0.0f;
+    }
+}
+
+// rows t >= 1 of dx0 [B][Tn][E] -> dtok [B*(Tn-1)][E]
+__global__ void da3_token_rows_kernel(const float *dx0, float *dtok, int B, int Tn, int E, long long gX, long long gTok) {
+    const int g = blockIdx.y;
+    const long long total = (long long)B * (Tn - 1) * E;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % E);
+        const int t = (int)((i / E) % (Tn - 1));
+        const long long b = i / ((long long)E * (Tn - 1));
+        dtok[(size_t)g * gTok + i] = dx0[(size_t)g * gX + (b * Tn + t + 1) * E + d];
+    }
+}
+
 // ------------------------------------------------------------------------------ optimizer
 // stage 1: per-block partial sums of squares (fixed order); stage 2 inside the apply kernel
 __global__ void sqnorm_partial_kernel(const float *grads, float *partial, long long P, float scale) {
@@ -684,7 +911,11 @@ struct maexp_learner {
     maexp_learner_cfg cfg;
     int G, B, C, V, A, H, F1, F2, Z, D;  // D = flattened conv output (or C*V*V for the plain MLP)
     int H1, Hp, H2;                      // conv1 out side, pooled side, conv2 out side
-    bool has_conv, dist, iqn;
+    bool has_conv, dist, iqn, da3;
+    int E_, heads_, Fm, L_, Tn;   // DA3: embed_dim, num_heads, mlp hidden, block_loop, tokens
+    long long o_sal, o_pos, o_pew, o_peb, o_nfw, o_nfb, o_hw, o_hb;
+    struct BlockLayout { long long n1w, n1b, qkvw, projw, projb, n2w, n2b, f1w, f1b, f2w, f2b; };
+    std::vector<BlockLayout> blocks;
     int Nq, Nd, ncos, rows_max;  // IQN: quantiles, target quantiles, cosines, B * max(Nq, Nd)
     HeadLayout se;               // IQN state_embedder (customs/iqn.py:51-53)
     long long o_cw, o_cb;        // IQN cosine_net.net.0
@@ -704,6 +935,10 @@ struct maexp_learner {
         float *se_h, *psi, *cosf, *phi, *e, *hrow[2], *out[2];
     } iq[3];
     float *d_e = nullptr, *d_phi = nullptr, *d_psi = nullptr, *d_hrow = nullptr;
+    struct Da3Block { float *n1, *m1, *r1, *qkv, *probs, *ao, *x1, *n2, *m2, *r2, *f1, *g1, *x2; };
+    struct Da3Acts { float *patches, *tok, *x0, *nf, *mf, *rf, *q; std::vector<Da3Block> blk; } da[3];
+    float *da_dx = nullptr, *da_dx1 = nullptr, *da_dn = nullptr, *da_gx = nullptr, *da_dqkv = nullptr, *da_dao = nullptr,
+          *da_dg1 = nullptr, *da_df1 = nullptr, *da_dnf = nullptr, *da_dtok0 = nullptr, *da_dtok = nullptr;
     // backward workspace
     float *d_out[2], *d_h, *d_flat, *d_y2, *d_col2, *d_p, *d_y1, *per_sample, *m_scratch, *partial, *q_tmp;
     int nparts;
@@ -902,13 +1137,116 @@ void iqn_backward(maexp_learner *h, cudaStream_t st, int nq) {
     trunk_backward(h, st);
 }
 
+// ---- DA3 (customs/da3.py:22-96, vit.py): patch embedding, saliency token, pre-LN blocks, final LN, head
+inline void ln_fwd(maexp_learner *h, cudaStream_t st, const float *params, const float *x, long long x_row, long long gX,
+                   long long wo, long long bo, float *y, float *m, float *r, int rows, long long rows_max) {
+    layernorm_fwd_kernel<<<dim3((rows * 32 + 255) / 256, h->G), 256, 0, st>>>(x, x_row, params + wo, params + bo, y, m, r, rows,
+                                                                              h->E_, gX, rows_max * h->E_, rows_max, h->P);
+}
+
+void da3_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, int pass) {
+    maexp_learner::Da3Acts &a = h->da[pass];
+    const int G = h->G, C = h->C, VV = h->V * h->V, E = h->E_, Tn = h->Tn, Fm = h->Fm;
+    const long long P = h->P, Bmax = h->B, Rm = Bmax * Tn, R49 = Bmax * (Tn - 1);
+    const int rows = B * Tn, rows49 = B * (Tn - 1);
+    da3_patch_gather_kernel<<<grid1d((long long)rows49 * C, G), 256, 0, st>>>(obs, a.patches, B, C, VV, h->cfg.obs_stride,
+                                                                              (long long)B * h->cfg.obs_stride, R49 * C);
+    gemm(st, G, a.patches, params + h->o_pew, a.tok, params + h->o_peb, rows49, E, C, C, 1, 1, C, E, 1, R49 * C, P, R49 * E, P);
+    da3_tokens_kernel<<<grid1d((long long)rows * E, G), 256, 0, st>>>(a.tok, params + h->o_sal, params + h->o_pos, a.x0, B, Tn, E,
+                                                                      R49 * E, Rm * E, P);
+    const float *x = a.x0;
+    const float scale = 1.0f / sqrtf((float)(E / h->heads_));
+    for (int l = 0; l < h->L_; ++l) {
+        const maexp_learner::BlockLayout &w = h->blocks[l];
+        maexp_learner::Da3Block &k = a.blk[l];
+        ln_fwd(h, st, params, x, E, Rm * E, w.n1w, w.n1b, k.n1, k.m1, k.r1, rows, Rm);
+        gemm(st, G, k.n1, params + w.qkvw, k.qkv, nullptr, rows, 3 * E, E, E, 1, 1, E, 3 * E, 1, Rm * E, P, Rm * 3 * E, 0);
+        da3_attn_fwd_kernel<<<dim3(h->heads_, B, G), 128, 0, st>>>(k.qkv, k.probs, k.ao, B, Tn, E, h->heads_, scale, Rm * 3 * E,
+                                                                   Bmax * h->heads_ * Tn * Tn, Rm * E);
+        cudaMemcpyAsync(k.x1, x, sizeof(float) * (size_t)G * Rm * E, cudaMemcpyDeviceToDevice, st);
+        gemm(st, G, k.ao, params + w.projw, k.x1, params + w.projb, rows, E, E, E, 1, 1, E, E, 1, Rm * E, P, Rm * E, P, 0,
+             /*accumulate=*/1);
+        ln_fwd(h, st, params, k.x1, E, Rm * E, w.n2w, w.n2b, k.n2, k.m2, k.r2, rows, Rm);
+        gemm(st, G, k.n2, params + w.f1w, k.f1, params + w.f1b, rows, Fm, E, E, 1, 1, E, Fm, 1, Rm * E, P, Rm * Fm, P);
+        gelu_fwd_kernel<<<grid1d((long long)G * Rm * Fm, 1), 256, 0, st>>>(k.f1, k.g1, (long long)G * Rm * Fm);
+        cudaMemcpyAsync(k.x2, k.x1, sizeof(float) * (size_t)G * Rm * E, cudaMemcpyDeviceToDevice, st);
+        gemm(st, G, k.g1, params + w.f2w, k.x2, params + w.f2b, rows, E, Fm, Fm, 1, 1, Fm, E, 1, Rm * Fm, P, Rm * E, P, 0, 1);
+        x = k.x2;
+    }
+    // final LayerNorm on the saliency token only, then the head (da3.py:59-60,90-96)
+    layernorm_fwd_kernel<<<dim3((B * 32 + 255) / 256, G), 256, 0, st>>>(x, (long long)Tn * E, params + h->o_nfw, params + h->o_nfb,
+                                                                        a.nf, a.mf, a.rf, B, E, Rm * E, Bmax * E, Bmax, P);
+    gemm(st, G, a.nf, params + h->o_hw, a.q, params + h->o_hb, B, h->A, E, E, 1, 1, E, h->A, 1, Bmax * E, P, Bmax * h->A, P);
+}
+
+void da3_backward(maexp_learner *h, cudaStream_t st) {
+    maexp_learner::Da3Acts &a = h->da[0];
+    const int G = h->G, B = h->B, C = h->C, E = h->E_, Tn = h->Tn, Fm = h->Fm, A = h->A;
+    const long long P = h->P, Rm = (long long)B * Tn, R49 = (long long)B * (Tn - 1);
+    const int rows = B * Tn, rows49 = B * (Tn - 1);
+    const float *dq = h->d_out[0];
+    float *grads = h->grads;
+    const float *W = h->online;
+    const float scale = 1.0f / sqrtf((float)(E / h->heads_));
+    auto ln_bwd = [&](const float *dy, const float *x, long long x_row, long long gX, long long wo, const float *m,
+                      const float *r, float *dx, long long dx_row, long long gDx, int acc, int nrows, long long nrows_max) {
+        layernorm_bwd_kernel<<<dim3((nrows * 32 + 255) / 256, G), 256, 0, st>>>(dy, x, x_row, W + wo, m, r, dx, dx_row, acc,
+                                                                                h->da_gx, nrows, E, nrows_max * E, gX, gDx,
+                                                                                nrows_max, P);
+    };
+    // head
+    gemm(st, G, dq, a.nf, grads + h->o_hw, nullptr, A, E, B, 1, A, E, 1, E, 1, (long long)B * A, (long long)B * E, P, 0);
+    colsum(st, G, h->ones, dq, grads + h->o_hb, B, A, (long long)B * A, P);
+    gemm(st, G, dq, W + h->o_hw, h->da_dnf, nullptr, B, E, A, A, 1, E, 1, E, 1, (long long)B * A, P, (long long)B * E, 0);
+    const float *x_last = h->L_ ? a.blk[h->L_ - 1].x2 : a.x0;
+    ln_bwd(h->da_dnf, x_last, (long long)Tn * E, Rm * E, h->o_nfw, a.mf, a.rf, h->da_dtok0, E, (long long)B * E, 0, B, B);
+    colsum(st, G, h->ones, h->da_gx, grads + h->o_nfw, B, E, (long long)B * E, P);
+    colsum(st, G, h->ones, h->da_dnf, grads + h->o_nfb, B, E, (long long)B * E, P);
+    da3_scatter_token0_kernel<<<grid1d((long long)rows * E, G), 256, 0, st>>>(h->da_dtok0, h->da_dx, B, Tn, E, (long long)B * E,
+                                                                              Rm * E);
+    for (int l = h->L_ - 1; l >= 0; --l) {
+        const maexp_learner::BlockLayout &w = h->blocks[l];
+        maexp_learner::Da3Block &k = a.blk[l];
+        const float *x_in = l ? a.blk[l - 1].x2 : a.x0;
+        // mlp branch: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
+        gemm(st, G, h->da_dx, k.g1, grads + w.f2w, nullptr, E, Fm, rows, 1, E, Fm, 1, Fm, 1, Rm * E, Rm * Fm, P, 0);
+        colsum(st, G, h->ones, h->da_dx, grads + w.f2b, rows, E, Rm * E, P);
+        gemm(st, G, h->da_dx, W + w.f2w, h->da_dg1, nullptr, rows, Fm, E, E, 1, Fm, 1, Fm, 1, Rm * E, P, Rm * Fm, 0);
+        gelu_bwd_kernel<<<grid1d((long long)G * Rm * Fm, 1), 256, 0, st>>>(k.f1, h->da_dg1, h->da_df1, (long long)G * Rm * Fm);
+        gemm(st, G, h->da_df1, k.n2, grads + w.f1w, nullptr, Fm, E, rows, 1, Fm, E, 1, E, 1, Rm * Fm, Rm * E, P, 0);
+        colsum(st, G, h->ones, h->da_df1, grads + w.f1b, rows, Fm, Rm * Fm, P);
+        gemm(st, G, h->da_df1, W + w.f1w, h->da_dn, nullptr, rows, E, Fm, Fm, 1, E, 1, E, 1, Rm * Fm, P, Rm * E, 0);
+        ln_bwd(h->da_dn, k.x1, E, Rm * E, w.n2w, k.m2, k.r2, h->da_dx, E, Rm * E, /*accumulate=*/1, rows, Rm);
+        colsum(st, G, h->ones, h->da_gx, grads + w.n2w, rows, E, Rm * E, P);
+        colsum(st, G, h->ones, h->da_dn, grads + w.n2b, rows, E, Rm * E, P);
+        // attention branch: x1 = x_in + proj(attn(LN1(x_in)))        (da_dx now holds d x1)
+        gemm(st, G, h->da_dx, k.ao, grads + w.projw, nullptr, E, E, rows, 1, E, E, 1, E, 1, Rm * E, Rm * E, P, 0);
+        colsum(st, G, h->ones, h->da_dx, grads + w.projb, rows, E, Rm * E, P);
+        gemm(st, G, h->da_dx, W + w.projw, h->da_dao, nullptr, rows, E, E, E, 1, E, 1, E, 1, Rm * E, P, Rm * E, 0);
+        const size_t smem = sizeof(float) * (size_t)(4 * Tn * (E / h->heads_) + Tn * Tn);
+        da3_attn_bwd_kernel<<<dim3(h->heads_, B, G), 128, smem, st>>>(k.qkv, k.probs, h->da_dao, h->da_dqkv, B, Tn, E, h->heads_,
+                                                                      scale, Rm * 3 * E, (long long)B * h->heads_ * Tn * Tn, Rm * E);
+        gemm(st, G, h->da_dqkv, k.n1, grads + w.qkvw, nullptr, 3 * E, E, rows, 1, 3 * E, E, 1, E, 1, Rm * 3 * E, Rm * E, P, 0);
+        gemm(st, G, h->da_dqkv, W + w.qkvw, h->da_dn, nullptr, rows, E, 3 * E, 3 * E, 1, E, 1, E, 1, Rm * 3 * E, P, Rm * E, 0);
+        ln_bwd(h->da_dn, x_in, E, Rm * E, w.n1w, k.m1, k.r1, h->da_dx, E, Rm * E, 1, rows, Rm);
+        colsum(st, G, h->ones, h->da_gx, grads + w.n1w, rows, E, Rm * E, P);
+        colsum(st, G, h->ones, h->da_dn, grads + w.n1b, rows, E, Rm * E, P);
+    }
+    // embeddings: pos_embed, saliency_vector, patch projection (da_dx = d x0)
+    colsum(st, G, h->ones, h->da_dx, grads + h->o_pos, B, Tn * E, Rm * E, P);
+    gemm(st, G, h->ones, h->da_dx, grads + h->o_sal, nullptr, 1, E, B, 0, 0, (long long)Tn * E, 1, E, 1, 0, Rm * E, P, 0);
+    da3_token_rows_kernel<<<grid1d((long long)rows49 * E, G), 256, 0, st>>>(h->da_dx, h->da_dtok, B, Tn, E, Rm * E, R49 * E);
+    gemm(st, G, h->da_dtok, a.patches, grads + h->o_pew, nullptr, E, C, rows49, 1, E, C, 1, C, 1, R49 * E, R49 * C, P, 0);
+    colsum(st, G, h->ones, h->da_dtok, grads + h->o_peb, rows49, E, R49 * E, P);
+}
+
 }  // namespace
 
 extern "C" {
 
 int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (!cfg || !out) return fail("maexp_learner_create: null argument");
-    if (cfg->kind < MAEXP_LEARNER_DQN_CONV_MLP || cfg->kind > MAEXP_LEARNER_IQN)
+    if (cfg->kind < MAEXP_LEARNER_DQN_CONV_MLP || cfg->kind > MAEXP_LEARNER_DA3)
         return fail("maexp_learner_create: unknown kind");
     if (cfg->num_agents < 1 || cfg->batch_size < 1) return fail("maexp_learner_create: bad num_agents / batch_size");
     if (cfg->num_actions < 1 || cfg->num_actions > kMaxActions) return fail("maexp_learner_create: num_actions must be in 1..8");
@@ -916,7 +1254,8 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     h->cfg = *cfg;
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
     h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;
-    h->has_conv = cfg->kind != MAEXP_LEARNER_DQN_MLP;
+    h->da3 = cfg->kind == MAEXP_LEARNER_DA3;
+    h->has_conv = cfg->kind != MAEXP_LEARNER_DQN_MLP && !h->da3;
     h->dist = cfg->kind == MAEXP_LEARNER_C51 || cfg->kind == MAEXP_LEARNER_QR;
     h->iqn = cfg->kind == MAEXP_LEARNER_IQN;
     h->Nq = h->iqn ? cfg->num_atoms : 0;
@@ -934,7 +1273,35 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         off += count;
         return o;
     };
-    if (h->has_conv) {
+    if (h->da3) {
+        h->E_ = cfg->embed_dim; h->heads_ = cfg->num_heads; h->Fm = cfg->mlp_hidden; h->L_ = cfg->block_loop;
+        h->Tn = h->V * h->V + 1;
+        h->H1 = h->Hp = h->H2 = 0;
+        h->D = h->E_;
+        if (h->E_ < 1 || h->heads_ < 1 || h->E_ % h->heads_ || h->E_ / h->heads_ > kMaxHeadDim || h->Tn > kMaxTokens || h->Fm < 1 ||
+            h->L_ < 0 || (4 * h->Tn * (h->E_ / h->heads_) + h->Tn * h->Tn) * 4 > 48 * 1024) {
+            delete h;
+            return fail("maexp_learner_create: unsupported DA3 shape (tokens <= 96, head_dim <= 32, attention tile <= 48 KB)");
+        }
+        // own parameters first, then submodules in registration order (customs/da3.py:33-60)
+        h->o_sal = add("saliency_vector", h->E_);
+        h->o_pos = add("pos_embed", (long long)h->Tn * h->E_);
+        h->o_pew = add("patch_embed.proj.weight", (long long)h->E_ * h->C);
+        h->o_peb = add("patch_embed.proj.bias", h->E_);
+        for (int l = 0; l < h->L_; ++l) {
+            const std::string b = "blocks." + std::to_string(l) + ".";
+            maexp_learner::BlockLayout w;
+            w.n1w = add(b + "norm1.weight", h->E_); w.n1b = add(b + "norm1.bias", h->E_);
+            w.qkvw = add(b + "attn.qkv.weight", 3ll * h->E_ * h->E_);
+            w.projw = add(b + "attn.proj.weight", (long long)h->E_ * h->E_); w.projb = add(b + "attn.proj.bias", h->E_);
+            w.n2w = add(b + "norm2.weight", h->E_); w.n2b = add(b + "norm2.bias", h->E_);
+            w.f1w = add(b + "mlp.fc1.weight", (long long)h->Fm * h->E_); w.f1b = add(b + "mlp.fc1.bias", h->Fm);
+            w.f2w = add(b + "mlp.fc2.weight", (long long)h->E_ * h->Fm); w.f2b = add(b + "mlp.fc2.bias", h->E_);
+            h->blocks.push_back(w);
+        }
+        h->o_nfw = add("norm.weight", h->E_); h->o_nfb = add("norm.bias", h->E_);
+        h->o_hw = add("drl_head.weight", (long long)h->A * h->E_); h->o_hb = add("drl_head.bias", h->A);
+    } else if (h->has_conv) {
         h->H1 = h->V - 1; h->Hp = h->H1 / 2; h->H2 = h->Hp - 1;
         if (h->H2 < 1) { delete h; return fail("maexp_learner_create: visible_range too small for the conv trunk"); }
         h->D = h->F2 * h->H2 * h->H2;
@@ -956,7 +1323,9 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         hd.out = outn;
         h->heads.push_back(hd);
     };
-    if (h->iqn) {  // state_dict order of customs/iqn.py:43-67
+    if (h->da3) {
+        // no MLP heads: the drl_head is part of the layout above
+    } else if (h->iqn) {  // state_dict order of customs/iqn.py:43-67
         add_head("state_embedder", h->D);
         h->se = h->heads.back();
         h->heads.pop_back();
@@ -1001,6 +1370,35 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         }
     }
     const long long R = h->iqn ? h->rows_max : B;
+    if (h->da3) {
+        const long long Rm = B * h->Tn, R49 = B * (h->Tn - 1), E = h->E_;
+        for (int k = 0; k < 3; ++k) {
+            maexp_learner::Da3Acts &a = h->da[k];
+            rc |= lalloc(h, &a.patches, G * R49 * h->C);
+            rc |= lalloc(h, &a.tok, G * R49 * E);
+            rc |= lalloc(h, &a.x0, G * Rm * E);
+            rc |= lalloc(h, &a.nf, G * B * E);
+            rc |= lalloc(h, &a.mf, G * B);
+            rc |= lalloc(h, &a.rf, G * B);
+            rc |= lalloc(h, &a.q, G * B * h->A);
+            a.blk.resize(h->L_);
+            for (int l = 0; l < h->L_; ++l) {
+                maexp_learner::Da3Block &q = a.blk[l];
+                rc |= lalloc(h, &q.n1, G * Rm * E); rc |= lalloc(h, &q.m1, G * Rm); rc |= lalloc(h, &q.r1, G * Rm);
+                rc |= lalloc(h, &q.qkv, G * Rm * 3 * E);
+                rc |= lalloc(h, &q.probs, G * B * h->heads_ * h->Tn * h->Tn);
+                rc |= lalloc(h, &q.ao, G * Rm * E); rc |= lalloc(h, &q.x1, G * Rm * E);
+                rc |= lalloc(h, &q.n2, G * Rm * E); rc |= lalloc(h, &q.m2, G * Rm); rc |= lalloc(h, &q.r2, G * Rm);
+                rc |= lalloc(h, &q.f1, G * Rm * h->Fm); rc |= lalloc(h, &q.g1, G * Rm * h->Fm);
+                rc |= lalloc(h, &q.x2, G * Rm * E);
+            }
+        }
+        rc |= lalloc(h, &h->d_out[0], G * B * h->A);
+        rc |= lalloc(h, &h->da_dx, G * Rm * E); rc |= lalloc(h, &h->da_dn, G * Rm * E); rc |= lalloc(h, &h->da_gx, G * Rm * E);
+        rc |= lalloc(h, &h->da_dqkv, G * Rm * 3 * E); rc |= lalloc(h, &h->da_dao, G * Rm * E);
+        rc |= lalloc(h, &h->da_dg1, G * Rm * h->Fm); rc |= lalloc(h, &h->da_df1, G * Rm * h->Fm);
+        rc |= lalloc(h, &h->da_dnf, G * B * E); rc |= lalloc(h, &h->da_dtok0, G * B * E); rc |= lalloc(h, &h->da_dtok, G * R49 * E);
+    }
     for (size_t j = 0; j < h->heads.size(); ++j) rc |= lalloc(h, &h->d_out[j], G * R * h->heads[j].out);
     if (h->iqn) {
         for (int k = 0; k < 3; ++k) {
@@ -1086,6 +1484,13 @@ int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int us
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     maexp_learner::Acts &a = h->acts[1];
     g_splitk_ws = h->splitk_ws;
+    if (h->da3) {
+        da3_forward(h, st, use_target ? h->target : h->online, obs, batch, 1);
+        MAEXP_CUDA_L(cudaMemcpy2DAsync(q_out, sizeof(float) * batch * h->A, h->da[1].q, sizeof(float) * h->B * h->A,
+                                       sizeof(float) * batch * h->A, h->G, cudaMemcpyDeviceToDevice, st));
+        MAEXP_CUDA_L(cudaGetLastError());
+        return 0;
+    }
     forward(h, st, use_target ? h->target : h->online, obs, batch, a);
     if (!h->dist) {
         // heads are strided by the maximum batch: compact to [G][batch][A]
@@ -1106,6 +1511,16 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
     if (h->iqn) return fail("maexp_learner_grads: use maexp_learner_grads_iqn for IQN");
     const int G = h->G, B = h->B, A = h->A, Z = h->Z;
     g_splitk_ws = h->splitk_ws;
+    if (h->da3) {  // DA3Brain.learn: TD target + MSE on the attention network (da3_brain.py:58-89)
+        da3_forward(h, st, h->online, obs, B, 0);
+        da3_forward(h, st, h->target, next_obs, B, 2);
+        dqn_loss_kernel<<<dim3((B + 127) / 128, G), 128, 0, st>>>(h->da[0].q, h->da[2].q, actions, rewards, dones, h->cfg.gamma, B,
+                                                                  A, h->d_out[0], h->per_sample);
+        mean_kernel<<<G, 256, 0, st>>>(h->per_sample, loss_out ? loss_out : h->q_tmp, B);
+        da3_backward(h, st);
+        MAEXP_CUDA_L(cudaGetLastError());
+        return 0;
+    }
     forward(h, st, h->online, obs, B, h->acts[0]);
     forward(h, st, h->target, next_obs, B, h->acts[2]);
     if (!h->dist) {

@@ -25,7 +25,10 @@ def configs():
     dqn["model"] = dict(dqn.model, name="da3_baseline", patch_size=1, num_heads=4)
     iqn = c3.merged_with(batch_size=B, brain="iqn")
     iqn["model"] = dict(iqn.model, name="iqn", num_quantiles=4, num_quantiles_dash=4, num_cosines=4)
-    return {"dqn_conv_mlp": (dqn, [7, 7, 7]), "c51": (c5.merged_with(batch_size=B), [3, 7, 7]),
+    da3 = c5.merged_with(batch_size=B, brain="da3", agent_type="attention")
+    da3["model"] = dict(name="da3", embed_dim=64, patch_size=1, block_loop=1, num_heads=4, mlp_ratio=4.0,
+                        attention="soft", af_lambd=0.5)
+    return {"da3": (da3, [3, 7, 7]), "dqn_conv_mlp": (dqn, [7, 7, 7]), "c51": (c5.merged_with(batch_size=B), [3, 7, 7]),
             "qr": (c3.merged_with(batch_size=B), [3, 7, 7]), "iqn": (iqn, [3, 7, 7])}
 
 
@@ -48,6 +51,10 @@ def main():
     for kind, (cfg, shape) in configs().items():
         torch.manual_seed(921)
         brain = generate_brain(config=rr.to_dictconfig(cfg), obs_shape=shape, act_size=4)
+        if kind == "da3":  # zero-initialised embeddings (da3.py:41-44): perturb so the fixture exercises them
+            with torch.no_grad():
+                brain.network.saliency_vector.add_(0.02 * torch.randn_like(brain.network.saliency_vector))
+                brain.network.pos_embed.add_(0.02 * torch.randn_like(brain.network.pos_embed))
         # make the target differ from the online net, as it does between synchronisations
         with torch.no_grad():
             for p_ in brain.target_network.parameters():
@@ -61,6 +68,8 @@ def main():
                 q0 = torch.sum(brain.network({"local": batch["obs"].clone()}, ApplySoftmax.NORMAL) * brain.support, dim=2)
             elif kind == "qr":
                 q0 = brain.network({"local": batch["obs"].clone()}).mean(dim=2)
+            elif kind == "da3":
+                q0 = brain.network({"local": batch["obs"].clone()})
             elif kind == "iqn":
                 tau0 = torch.rand(1, 4)
                 q0 = brain.network({"local": batch["obs"].clone()}, external_taus=tau0)

@@ -10,7 +10,7 @@ from oracle.torch_learner import TorchLearner
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KINDS = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLDEN, "learner_*.npz")))
-ATOMS = {"dqn_conv_mlp": 1, "c51": 51, "qr": 100, "iqn": 4}
+ATOMS = {"dqn_conv_mlp": 1, "c51": 51, "qr": 100, "iqn": 4, "da3": 1}
 
 
 def load(kind):

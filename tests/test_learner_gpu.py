@@ -65,7 +65,7 @@ def test_cuda_learner_matches_reference_fixture(kind):
     assert bad <= total * 1e-3, (bad, total)
 
 
-@pytest.mark.parametrize("kind,B", [("dqn_conv_mlp", 32), ("c51", 256), ("qr", 256), ("iqn", 256)])
+@pytest.mark.parametrize("kind,B", [("dqn_conv_mlp", 32), ("c51", 256), ("qr", 256), ("iqn", 256), ("da3", 32)])
 def test_cuda_learner_group_matches_torch_oracle(kind, B):
     """G independent networks with different weights and batches, BASELINE batch sizes."""
     G = 3
