@@ -32,7 +32,7 @@ B_ALG = 744.0  # algorithmic bytes per agent-step for cfg5 (588 
 METRIC, UNIT = "agent_steps_per_sec", "agent-steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of env_step_kernel<7,16,0> at this
 # workload, from profiles/ (ncu --set full)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 283.3e6  # 8.87 MB read + 274.47 MB written (profiles/r1_env_step_kernel_ncu_full.csv)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 282.1e6  # 8.87 MB read + 273.25 MB written (profiles/r1_env_step_kernel_ncu_full.csv)
 
 
 def workload_config():

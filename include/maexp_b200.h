@@ -74,7 +74,7 @@ typedef struct {
 } maexp_tables;
 
 /* Per-call outputs (device pointers, any may be NULL).  obs / obs_rel point at ONE slot of the
- * device-resident replay ring: fp32 [E, N, slot_floats], slot_floats = maexp_env_slot_floats()
+ * device-resident replay ring, AGENT-MAJOR: fp32 [N, E, slot_floats], slot_floats = maexp_env_slot_floats()
  * (C*V*V rounded up to a multiple of 8 so that every agent slot starts on a 32-byte sector). */
 typedef struct {
     float *obs;            /* state[view] of observation_handler.py:95-105 (noisy one for merged) */
@@ -136,7 +136,7 @@ int maexp_env_stats(maexp_env *env, uint64_t *env_steps, uint64_t *resets, int32
  * maexp_env_reset call wrote (obs, rewards, dones, was_reset) plus the actions that led to it.
  * The transition (s -> s+1) of env e is valid iff was_reset[s+1][e] == 0. */
 typedef struct {
-    const float *obs;          /* [S,E,N,slot_floats] */
+    const float *obs;          /* [S,N,E,slot_floats] (agent-major slots, as maexp_env_step writes them) */
     const int8_t *actions;     /* [S,E,N] action taken to reach slot s */
     const float *rewards;      /* [S,E,N] */
     const uint8_t *dones;      /* [S,E,N] */

@@ -63,11 +63,11 @@ class BatchedActor:
         self.group.params().copy_(self.learner.params())
 
     def act(self, obs_slot, epsilon, tick):
-        """obs_slot fp32 [E, N, slot] (a ring slot) -> int8 actions [E, N] on the device."""
+        """obs_slot fp32 [N, E, slot] (an agent-major ring slot) -> int8 actions [E, N] on the device."""
         env, stream = self.env, C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
         for e0 in range(0, env.E, self.chunk):
             b = min(self.chunk, env.E - e0)
-            obs = obs_slot[e0:e0 + b].transpose(0, 1).contiguous()  # [N, b, slot]
+            obs = obs_slot[:, e0:e0 + b].contiguous()  # [N, b, slot]
             q = self.group.q_values(obs)
             _lib.check(self.lib.maexp_select_actions(C.c_void_p(q.data_ptr()), C.c_void_p(self.actions.data_ptr()),
                                                      env.N, b, 4, e0, float(epsilon), self.seed,

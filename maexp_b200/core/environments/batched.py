@@ -140,8 +140,8 @@ class BatchedEnvironment:
 
     # ------------------------------------------------------------------ buffers
     def new_slot(self):
-        """One replay-ring slot: fp32 [E, N, slot_floats] (slot_floats = C*V*V padded to 16 bytes)."""
-        return torch.empty((self.E, self.N, self.slot_floats), dtype=torch.float32, device=self.device)
+        """One replay-ring slot, agent-major: fp32 [N, E, slot_floats] (slot_floats = C*V*V padded to 32 bytes)."""
+        return torch.empty((self.N, self.E, self.slot_floats), dtype=torch.float32, device=self.device)
 
     def new_outputs(self, extras=False):
         d = self.device
@@ -160,8 +160,8 @@ class BatchedEnvironment:
         return o
 
     def view(self, slot):
-        """Dense [E, N, C, V, V] copy of a ring slot (drops the alignment padding)."""
-        return slot[..., :self.K].reshape(self.E, self.N, self.C, self.V, self.V)
+        """Dense env-major [E, N, C, V, V] copy of an (agent-major) ring slot, without the alignment padding."""
+        return slot[..., :self.K].reshape(self.N, self.E, self.C, self.V, self.V).transpose(0, 1).contiguous()
 
     @staticmethod
     def _p(t):

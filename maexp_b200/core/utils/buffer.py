@@ -19,7 +19,7 @@ class DeviceReplayRing:
         self.lib = _lib.load()
         self.env, self.S = env, int(num_slots)
         E, N, d = env.E, env.N, env.device
-        self.obs = torch.zeros((self.S, E, N, env.slot_floats), dtype=torch.float32, device=d)
+        self.obs = torch.zeros((self.S, N, E, env.slot_floats), dtype=torch.float32, device=d)  # agent-major slots
         self.actions = torch.zeros((self.S, E, N), dtype=torch.int8, device=d)
         self.rewards = torch.zeros((self.S, E, N), dtype=torch.float32, device=d)
         self.dones = torch.zeros((self.S, E, N), dtype=torch.uint8, device=d)

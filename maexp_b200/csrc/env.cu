@@ -70,7 +70,7 @@ __global__ void get_state_kernel(const EnvParams p, int8_t *pos, int8_t *objects
             const int sel = p.random_dest ? p.dest_sel[(size_t)env * N + k] : (k < p.M ? k : p.M - 1);
             for (int x = 0; x < X; ++x)
                 for (int y = 0; y < Y; ++y)
-                    destination[(((size_t)env * N + k) * X + x) * Y + y] = (int8_t)((p.dest[sel * X + x] >> y) & 1u);
+                    destination[(((size_t)env * N + k) * X + x) * Y + y] = (int8_t)((p.dest[sel * X + x] >> (y + p.R)) & 1u);
         }
 }
 
@@ -111,8 +111,6 @@ struct maexp_env {
     size_t smem_bytes;
     int grid_ctas = 0;
     KernelFn fn = nullptr;
-    int *work_counters = nullptr;  // ring of zeroed queue heads, one consumed per launch
-    unsigned launch_seq = 0;
     std::vector<void *> allocs;
     // pinned-free staging for the host-buffer entry point
     int8_t *d_actions = nullptr;
@@ -143,10 +141,10 @@ int upload(maexp_env *h, const Tp **ptr, const std::vector<Tp> &host) {
 }
 
 size_t env_smem_bytes(const EnvParams &p, int V, int epw) {
-    const int LW = (V == 9) ? 2 : 1;
-    size_t words = 256 + (size_t)p.X * p.Y * LW * 2 + p.X + p.X + (size_t)p.T * p.X + (size_t)p.M * p.X;
-    const size_t per_warp = (size_t)epw * p.gs + (size_t)epw * p.as + (size_t)epw * p.ws + ((size_t)p.N * epw + (size_t)p.P * p.N * epw + 1) / 2 +
-                            (epw + 3) / 4;
+    (void)V;
+    size_t words = 256;  // nibble -> float4 table; static map tables stay in global memory (read-only L1 path)
+    const size_t per_warp = (size_t)epw * p.gs + (size_t)epw * p.as + (size_t)epw * p.ws +
+                            ((size_t)p.N * epw + (size_t)p.P * p.N * epw + 1) / 2 + (epw + 3) / 4;
     words += per_warp * kWarpsPerCta;
     return words * 4;
 }
@@ -171,10 +169,6 @@ int launch(maexp_env *h, uint32_t tick, int force_reset, const uint8_t *env_mask
     p.noise_tape = noise_tape;
     if (out) p.out = *out;
     else memset(&p.out, 0, sizeof(p.out));
-    // work queue head for this launch; the slot half a ring away is re-zeroed for a later launch
-    const unsigned slot = h->launch_seq++ & 63u;
-    p.work_counter = h->work_counters + slot;
-    MAEXP_CUDA(cudaMemsetAsync(h->work_counters + ((slot + 32u) & 63u), 0, sizeof(int), stream));
     h->fn<<<h->grid_ctas, kWarpsPerCta * 32, h->smem_bytes, stream>>>(p);
     MAEXP_CUDA(cudaGetLastError());
     return 0;
@@ -210,6 +204,7 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     h->V = V;
     EnvParams &p = h->p;
     memset(&p, 0, sizeof(p));
+    p.R = V / 2;
     p.E = E; p.N = N; p.T = T; p.X = X; p.Y = Y; p.P = transition ? P : 0; p.M = M;
     int agent_ch = 1;
     switch (cfg->agent_view) {
@@ -271,7 +266,7 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
         for (int pl = 0; pl < planes; ++pl)
             for (int x = 0; x < X; ++x)
                 for (int y = 0; y < Y; ++y)
-                    if (src[((size_t)pl * X + x) * Y + y]) r[(size_t)pl * X + x] |= 1u << y;
+                    if (src[((size_t)pl * X + x) * Y + y]) r[(size_t)pl * X + x] |= 1u << (y + V / 2);  // pre-shifted by R
         return r;
     };
     const int LW = (V == 9) ? 2 : 1;
@@ -301,7 +296,6 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     rc |= dev_alloc(h, &p.past, (size_t)E * (p.P ? p.P : 1) * N);
     rc |= dev_alloc(h, &p.stats, 2);
     rc |= dev_alloc(h, &p.error_flag, 1);
-    rc |= dev_alloc(h, &h->work_counters, 64);
     rc |= dev_alloc(h, &h->d_actions, (size_t)E * N);
     rc |= dev_alloc(h, &h->d_rewards, (size_t)E * N);
     rc |= dev_alloc(h, &h->d_dones, (size_t)E * N);

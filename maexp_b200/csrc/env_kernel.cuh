@@ -14,6 +14,7 @@ constexpr int kRespawnCap = 1 << 16;  // the reference loop is 
 
 struct EnvParams {
     // shape
+    int R;  // V / 2: static bit rows are stored pre-shifted by R
     int E, N, T, X, Y, P, C, K, slot_floats, qps, wpa, ws, gs, as, area_bit0, M;
     int q_str, q_tail, sub_str, sub_tail;  // phase-B quad classes (area channel offset, tail padding)
     uint32_t qps_magic;
@@ -23,7 +24,8 @@ struct EnvParams {
     uint32_t seed, gid0, tick;
     int force_reset;
     const uint8_t *env_mask;
-    // static tables
+    // static tables, bit rows pre-shifted left by R = V/2 (see the padded shared-memory layout); read through the
+    // read-only L1 path: 6.6 KB shared by every CTA on an SM, no per-CTA staging
     const uint32_t *wall, *noise_area, *area, *dest;
     const uint64_t *los;
     // state
@@ -36,7 +38,6 @@ struct EnvParams {
     uint8_t *dest_sel;
     uint16_t *past;
     unsigned long long *stats;  // [0] env-steps, [1] resets
-    int *work_counter;          // persistent-CTA work queue (groups of EPW envs), zeroed per launch
     uint32_t tx_magic;          // ceil(2^32 / (T*X))
     int32_t *error_flag;
     // io
@@ -123,7 +124,7 @@ struct BitStream {
 
 template <int V, int EPW, int NOISE>
 #ifndef MAEXP_MINB
-#define MAEXP_MINB 8
+#define MAEXP_MINB 7
 #endif
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 : MAEXP_MINB) env_step_kernel(const EnvParams p) {
     constexpr int R = V / 2, VV = V * V;
@@ -137,12 +138,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     const int XP = X + 2 * R;
     // ---- shared memory carve-up (must match env_smem_bytes) ----
     float4 *s_lut = reinterpret_cast<float4 *>(smem);  // [4 classes][16 nibbles] → 4 fp32 values
-    uint64_t *s_los = reinterpret_cast<uint64_t *>(smem + 256);
-    uint32_t *s_wall = reinterpret_cast<uint32_t *>(s_los + (size_t)X * Y * LW);
-    uint32_t *s_noise = s_wall + X;
-    uint32_t *s_area = s_noise + X;
-    uint32_t *s_dest = s_area + TX;
-    uint32_t *s_warp0 = s_dest + p.M * X;
+    uint32_t *s_warp0 = smem + 256;
+    const uint32_t *const s_wall = p.wall, *const s_noise = p.noise_area, *const s_area = p.area, *const s_dest = p.dest;
+    const uint64_t *const s_los = p.los;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per_warp_words = EPW * p.gs + EPW * p.as + EPW * p.ws + (N * EPW + P * N * EPW + 1) / 2 + (EPW + 3) / 4;
     uint32_t *s_grid = s_warp0 + (size_t)warp * per_warp_words;
@@ -160,25 +158,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
         for (int j = 0; j < 4; ++j) v[j] = (float)((n >> j) & 1) - (float)((sub >> j) & 1);
         s_lut[threadIdx.x] = make_float4(v[0], v[1], v[2], v[3]);
     }
-    for (int i = threadIdx.x; i < X * Y * LW; i += blockDim.x) s_los[i] = p.los[i];
-    for (int i = threadIdx.x; i < X; i += blockDim.x) {
-        s_wall[i] = p.wall[i] << R;
-        s_noise[i] = p.noise_area[i] << R;
+    {  // zero the pad rows (x < 0, x >= X) of this warp's grids once; nothing writes them afterwards
+        const int planes = T + 1, per_env = planes * 2 * R;
+        for (int i = lane; i < EPW * per_env; i += 32) {
+            const int e = i / per_env, j = i - e * per_env, pl = j / (2 * R), r = j - pl * 2 * R;
+            const int x = r < R ? r : X + r;  // padded row index in [0, R) or [X+R, X+2R)
+            if (pl < T) s_grid[e * p.gs + pl * XP + x] = 0;
+            else s_agrid[e * p.as + x] = 0;
+        }
     }
-    for (int i = threadIdx.x; i < TX; i += blockDim.x) s_area[i] = p.area[i] << R;
-    for (int i = threadIdx.x; i < p.M * X; i += blockDim.x) s_dest[i] = p.dest[i] << R;
-    for (int i = threadIdx.x; i < kWarpsPerCta * per_warp_words; i += blockDim.x) s_warp0[i] = 0;  // zero padding
-
     __syncthreads();
 
-    // Persistent CTAs: every warp pulls groups of EPW environments from a global queue, so the
-    // grid is sized to the machine (no partial last wave) and short groups keep warps busy.
+    // One resident wave of CTAs; groups of EPW environments are dealt round-robin (all groups cost about the
+    // same, and at the benchmark size every warp owns exactly one group).
     const int num_groups = (p.E + EPW - 1) / EPW;
-    for (;;) {
-    int group = 0;
-    if (lane == 0) group = atomicAdd(p.work_counter, 1);
-    group = __shfl_sync(0xFFFFFFFFu, group, 0);
-    if (group >= num_groups) break;
+    for (int group = blockIdx.x * kWarpsPerCta + warp; group < num_groups; group += gridDim.x * kWarpsPerCta) {
     const int env0 = group * EPW;
     const int nenv = min(EPW, p.E - env0);
     {  // coalesced stage-in of this warp's grids (flat index, loads batched by the unroll)
@@ -221,7 +215,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             ++attempt;
             const int x = 1 + (int)scale(u1, (uint32_t)(X - 1)), y = 1 + (int)scale(u2, (uint32_t)(Y - 1));
             const uint32_t bit = 1u << (y + R);
-            bool ok = !(s_wall[x] & bit) && (s_area[t * X + x] & bit);
+            bool ok = !(__ldg(&s_wall[x]) & bit) && (__ldg(&s_area[t * X + x]) & bit);
             for (int t2 = 0; t2 < T; ++t2) ok = ok && !(grid[t2 * XP + x] & bit);
             ok = ok && !agent_at(x, y);
             if (ok) {
@@ -325,7 +319,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                     ca |= 1u << id;
                     move = false;
                 }
-                if (s_wall[nx] & (1u << (ny + R))) {
+                if (__ldg(&s_wall[nx]) & (1u << (ny + R))) {
                     cw |= 1u << id;
                     move = false;
                 }
@@ -339,6 +333,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     }
     __syncwarp();
 
+    const bool all_on = __all_sync(0xFFFFFFFFu, !mine || active);
     // ------------------------------------------------------------ per-agent interleave
     for (int i = 0; i < N; ++i) {
         bool gate = false;
@@ -352,7 +347,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                     const uint32_t bit = 1u << (py + R);
                     for (int q = 0; q < MAEXP_MAX_TYPES && p.task_order[i][q] >= 0; ++q) {
                         const int t = p.task_order[i][q];
-                        if ((grid[t * XP + px] & bit) && (s_dest[sel * X + px] & bit)) {
+                        if ((grid[t * XP + px] & bit) && (__ldg(&s_dest[sel * X + px]) & bit)) {
                             rew_pos |= 1u << i;
                             grid[t * XP + px] &= ~bit;
                             --nobj;
@@ -367,8 +362,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                 if (nobj == 0 || stepc == p.L - 1) done_bits |= 1u << i;
             }
             // -------------------------------------------- observation_handler.py:67-105, bits in output order
-            WinT los = s_los[(px * Y + py) * LW];
-            if constexpr (V == 9) los |= (WinT)s_los[(px * Y + py) * LW + 1] << 64;
+            WinT los = __ldg(&s_los[(px * Y + py) * LW]);
+            if constexpr (V == 9) los |= (WinT)__ldg(&s_los[(px * Y + py) * LW + 1]) << 64;
             auto win_bit = [&](uint16_t cell) -> WinT {  // cell → window bit or 0
                 const int a = (int)(cell & 0xFF) - px + R, b = (int)(cell >> 8) - py + R;
                 return (a >= 0 && a < V && b >= 0 && b < V) ? ((WinT)1 << (a * V + b)) : (WinT)0;
@@ -433,7 +428,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             bs.put(los);  // observation_handler.py:107-108 (value = bit - 1)
             bs.finish();
             }
-            gate = (s_noise[px] >> (py + R)) & 1u;
+            gate = (__ldg(&s_noise[px]) >> (py + R)) & 1u;
 
             // -------------------------------------------- optional reference-format extras
             if (p.out.coordinates) {  // local_area_mask.py:18-47
@@ -463,11 +458,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
         // ---------------------------------------------------------- phase B: expand + stream out
         if (p.out.obs) {
             const int qps = p.qps, ws = p.ws;
-            const int env_stride = N * p.slot_floats;  // floats between consecutive envs in the slot
-            const size_t base = ((size_t)env0 * N + i) * p.slot_floats;
+            // ring slot layout is agent-major [N][E][slot_floats]: agent i's slots of this group are one contiguous run
+            const int env_stride = p.slot_floats;
+            const size_t base = ((size_t)i * p.E + env0) * p.slot_floats;
             float *const dst = p.out.obs + base;
             float *const dst_rel = (p.merged && p.out.obs_rel) ? p.out.obs_rel + base : nullptr;
-            const bool all_on = __all_sync(0xFFFFFFFFu, !mine || active);
             const bool check = (NOISE != MAEXP_NOISE_NONE) || !all_on;
 
             // one quad (4 consecutive fp32 of the slot) of env e: table lookup, optional noise, 128-bit stores
@@ -555,14 +550,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                         if (s_active[e] & 1) emit(e, q, wq[e * ws], sh, lut_off);
                 }
             }
-            // (2) the qps % 32 trailing quads of all envs, flattened over (env, quad)
+            // (2) the qps % 32 trailing quads: lanes split as (env sub-index, quad) with a power-of-two quad
+            //     pitch, so a lane again owns a fixed quad and only the env advances
             const int rem = qps & 31;
             if (rem) {
-                const int q0 = nfull * 32;
-                for (int f = lane; f < nenv * rem; f += 32) {
-                    const int e = f / rem, q = q0 + (f - e * rem);
-                    if (check && !(s_active[e] & 1)) continue;
-                    emit(e, q, s_w[e * ws + (q >> 3)], (q & 7) * 4, quad_class(q));
+                int pitch = 1;
+                while (pitch < rem) pitch <<= 1;
+                const int r = lane & (pitch - 1), esub = lane / pitch, estep = 32 / pitch;
+                if (r < rem) {
+                    const int q = nfull * 32 + r;
+                    const int sh = (q & 7) * 4, lut_off = quad_class(q);
+                    const uint32_t *wq = s_w + esub * ws + (q >> 3);
+                    if (NOISE == MAEXP_NOISE_NONE && !check && !dst_rel) {
+                        const float4 *lut = s_lut + lut_off;
+                        float *dp = dst + esub * env_stride + q * 4;
+#pragma unroll 2
+                        for (int e = esub; e < nenv; e += estep, wq += estep * ws, dp += estep * env_stride)
+                            store_quad(reinterpret_cast<float4 *>(dp), lut[(*wq >> sh) & 0xFu]);
+                    } else {
+                        for (int e = esub; e < nenv; e += estep, wq += estep * ws)
+                            if (!check || (s_active[e] & 1)) emit(e, q, *wq, sh, lut_off);
+                    }
                 }
             }
         }

@@ -44,8 +44,9 @@ __global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint3
     }
     const int nxt = (slot + 1) % r.num_slots;
     const size_t row = (size_t)r.num_envs * N * r.slot_floats;
-    const float4 *s0 = reinterpret_cast<const float4 *>(r.obs + (size_t)slot * row + ((size_t)env * N + agent) * r.slot_floats);
-    const float4 *s1 = reinterpret_cast<const float4 *>(r.obs + (size_t)nxt * row + ((size_t)env * N + agent) * r.slot_floats);
+    // ring slots are agent-major: [S][N][E][slot_floats]
+    const float4 *s0 = reinterpret_cast<const float4 *>(r.obs + (size_t)slot * row + ((size_t)agent * r.num_envs + env) * r.slot_floats);
+    const float4 *s1 = reinterpret_cast<const float4 *>(r.obs + (size_t)nxt * row + ((size_t)agent * r.num_envs + env) * r.slot_floats);
     const size_t orow = ((size_t)agent * batch + b) * r.slot_floats;
     float4 *d0 = reinterpret_cast<float4 *>(out.obs + orow), *d1 = reinterpret_cast<float4 *>(out.next_obs + orow);
     for (int q = lane; q < r.slot_floats / 4; q += 32) {

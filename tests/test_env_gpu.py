@@ -117,14 +117,15 @@ def test_full_size_invariants_and_sampled_oracle():
     assert env.stats()["env_steps"] == E * T
     # strided sample of envs re-run on the oracle (Philox keys are per global env id)
     sample = np.arange(0, E, 4099)
+    final_obs, final_objects = env.view(out["obs"]), env.state()["objects"]
     for gid in sample:
         orc = Oracle(cfg, 1, auto_reset=True, first_global_env_id=int(gid))
         orc.reset(0)
         for tick in range(1, T + 1):
             o = orc.step(tick)
-        assert np.array_equal(o["obs"][0], env.view(out["obs"])[gid].cpu().numpy()), gid
+        assert np.array_equal(o["obs"][0], final_obs[gid].cpu().numpy()), gid
         assert np.array_equal(o["rewards"][0], out["rewards"][gid].cpu().numpy())
-        assert np.array_equal(orc.state()["objects"][0], env.state()["objects"][gid].cpu().numpy())
+        assert np.array_equal(orc.state()["objects"][0], final_objects[gid].cpu().numpy())
 
 
 def test_sharded_envs_equal_single_gpu_run():

@@ -182,8 +182,8 @@ def test_replay_ring_sampling():
     obs, act, rew, done = ring.obs.cpu(), ring.actions.cpu(), ring.rewards.cpu(), ring.dones.cpu()
     for j, (s, e) in enumerate(picks):
         n = (s + 1) % S
-        assert torch.equal(batch["obs"][:, j].cpu(), obs[s, e])
-        assert torch.equal(batch["next_obs"][:, j].cpu(), obs[n, e])
+        assert torch.equal(batch["obs"][:, j].cpu(), obs[s, :, e])
+        assert torch.equal(batch["next_obs"][:, j].cpu(), obs[n, :, e])
         assert torch.equal(batch["actions"][:, j].cpu(), act[n, e].to(torch.int32))
         assert torch.equal(batch["rewards"][:, j].cpu(), rew[n, e]) and torch.equal(batch["dones"][:, j].cpu(), done[n, e])
     # (2) Philox picks: in range, never a transition into a reset slot, reproducible, tick-dependent

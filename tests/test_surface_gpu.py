@@ -84,7 +84,7 @@ def test_batched_actor_epsilon_greedy():
     actor = BatchedActor(cfg, env, learner, chunk=128)  # 300 envs -> chunks of 128, 128, 44
     actor.refresh()
     greedy = actor.act(out["obs"], 0.0, tick=1).clone()
-    q = torch.cat([learner_q for learner_q in [actor.group.q_values(out["obs"][e0:e0 + 100].transpose(0, 1).contiguous())
+    q = torch.cat([learner_q for learner_q in [actor.group.q_values(out["obs"][:, e0:e0 + 100].contiguous())
                                                .clone() for e0 in (0, 100, 200)]], dim=1)  # [N, 300, A]
     want = q.argmax(dim=2).transpose(0, 1).to(torch.int8)
     assert torch.equal(greedy[:, :7], want[:, :7])  # epsilon = 0: argmax of the online net
