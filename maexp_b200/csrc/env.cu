@@ -149,11 +149,11 @@ size_t env_smem_bytes(const EnvParams &p, int V, int epw) {
     return words * 4;
 }
 
-KernelFn pick_kernel(int V, int epw, int noise) {
+KernelFn pick_kernel(int V, int epw, int noise, int nspec) {
     switch (V) {
-    case 5: return pick_v5(epw, noise);
-    case 7: return pick_v7(epw, noise);
-    case 9: return pick_v9(epw, noise);
+    case 5: return pick_v5(epw, noise, nspec);
+    case 7: return pick_v7(epw, noise, nspec);
+    case 9: return pick_v9(epw, noise, nspec);
     }
     return nullptr;
 }
@@ -321,7 +321,9 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     if (h->smem_bytes > 227 * 1024) { maexp_env_destroy(h); return fail("maexp_env_create: configuration needs more than 227 KB shared memory per CTA"); }
     for (int i = 0; i < 32 * T * X; ++i)
         if ((int)(((uint64_t)i * p.tx_magic) >> 32) != i / (T * X)) { maexp_env_destroy(h); return fail("maexp_env_create: internal magic division (TX)"); }
-    h->fn = pick_kernel(V, h->epw, p.noise);
+    int nspec = (N == 8 && T == 1 && !transition) ? 8 : 0;
+    if (getenv("MAEXP_NOSPEC")) nspec = 0;
+    h->fn = pick_kernel(V, h->epw, p.noise, nspec);
     if (!h->fn) { maexp_env_destroy(h); return fail("maexp_env_create: no kernel for this visible_range / noise"); }
     if (cudaFuncSetAttribute(h->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess) {
         maexp_env_destroy(h);

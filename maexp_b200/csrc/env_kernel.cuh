@@ -122,7 +122,7 @@ struct BitStream {
     }
 };
 
-template <int V, int EPW, int NOISE>
+template <int V, int EPW, int NOISE, int NSPEC>
 #ifndef MAEXP_MINB
 #define MAEXP_MINB 7
 #endif
@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     using WinT = typename Win<V>::T;
     extern __shared__ __align__(16) uint32_t smem[];
 
-    const int N = p.N, T = p.T, X = p.X, Y = p.Y, P = p.P, TX = T * X;
+    // NSPEC = 8: agents and object types are compile-time constants (N = 8, T = 1, no transition frames), so the
+    // per-agent loops unroll; NSPEC = 0: everything from the parameter block
+    const int N = NSPEC ? NSPEC : p.N, T = NSPEC ? 1 : p.T, X = p.X, Y = p.Y, P = NSPEC ? 0 : p.P, TX = T * X;
     // Shared-memory bit rows are padded: R zero rows on both sides of x and every row shifted left by
     // R bits, so window crops need no bounds checks and no signed shifts.
     const int XP = X + 2 * R;
@@ -642,27 +644,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
 using KernelFn = void (*)(const EnvParams);
 
 template <int V, int EPW>
-KernelFn pick_noise(int noise) {
+KernelFn pick_noise(int noise, int nspec) {
     switch (noise) {
-    case MAEXP_NOISE_NONE: return env_step_kernel<V, EPW, MAEXP_NOISE_NONE>;
-    case MAEXP_NOISE_FLIP: return env_step_kernel<V, EPW, MAEXP_NOISE_FLIP>;
-    case MAEXP_NOISE_DIST: return env_step_kernel<V, EPW, MAEXP_NOISE_DIST>;
-    case MAEXP_NOISE_THRESHOLD_DIST: return env_step_kernel<V, EPW, MAEXP_NOISE_THRESHOLD_DIST>;
-    case MAEXP_NOISE_FLAT: return env_step_kernel<V, EPW, MAEXP_NOISE_FLAT>;
+    case MAEXP_NOISE_NONE:
+        if (nspec == 8) return env_step_kernel<V, EPW, MAEXP_NOISE_NONE, 8>;
+        return env_step_kernel<V, EPW, MAEXP_NOISE_NONE, 0>;
+    case MAEXP_NOISE_FLIP: return env_step_kernel<V, EPW, MAEXP_NOISE_FLIP, 0>;
+    case MAEXP_NOISE_DIST: return env_step_kernel<V, EPW, MAEXP_NOISE_DIST, 0>;
+    case MAEXP_NOISE_THRESHOLD_DIST: return env_step_kernel<V, EPW, MAEXP_NOISE_THRESHOLD_DIST, 0>;
+    case MAEXP_NOISE_FLAT: return env_step_kernel<V, EPW, MAEXP_NOISE_FLAT, 0>;
     }
     return nullptr;
 }
 template <int V>
-KernelFn pick_epw(int epw, int noise) {
+KernelFn pick_epw(int epw, int noise, int nspec) {
     switch (epw) {
-    case 32: return pick_noise<V, 32>(noise);
-    case 16: return pick_noise<V, 16>(noise);
-    case 8: return pick_noise<V, 8>(noise);
+    case 32: return pick_noise<V, 32>(noise, nspec);
+    case 16: return pick_noise<V, 16>(noise, nspec);
+    case 8: return pick_noise<V, 8>(noise, nspec);
     }
     return nullptr;
 }
-KernelFn pick_v5(int epw, int noise);
-KernelFn pick_v7(int epw, int noise);
-KernelFn pick_v9(int epw, int noise);
+KernelFn pick_v5(int epw, int noise, int nspec);
+KernelFn pick_v7(int epw, int noise, int nspec);
+KernelFn pick_v9(int epw, int noise, int nspec);
 
 }  // namespace maexp
