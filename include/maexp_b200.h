@@ -141,6 +141,7 @@ typedef struct {
     const float *rewards;      /* [S,E,N] */
     const uint8_t *dones;      /* [S,E,N] */
     const uint8_t *was_reset;  /* [S,E] */
+    const int8_t *positions;   /* [S,E,N,2] index-space agent positions after the call (may be NULL) */
     int32_t num_slots;         /* S */
     int32_t num_envs, num_agents, slot_floats;
     int32_t head;              /* newest written slot */
@@ -154,6 +155,8 @@ typedef struct {
     float *rewards;    /* [N,B] */
     uint8_t *dones;    /* [N,B] */
     int32_t *picked;   /* [B,2] (slot of the state, env) — may be NULL */
+    int8_t *pos;       /* [N,B,2] observing agent's position in the state (relative / merged models) — may be NULL */
+    int8_t *next_pos;  /* [N,B,2] ... in the new state */
 } maexp_batch;
 
 /* Uniform sampling of `batch` whole-team transitions (np.random.choice in buffer.py:61; here with
@@ -192,6 +195,10 @@ typedef struct {
     float max_norm;          /* clip_grad_norm_: 0.1 (dqn, qr, iqn), 10 (c51) */
     int32_t num_quantiles_dash, num_cosines;  /* IQN: model.num_quantiles_dash, model.num_cosines */
     int32_t embed_dim, num_heads, mlp_hidden, block_loop;  /* DA3: model.embed_dim, num_heads, int(embed_dim*mlp_ratio), block_loop */
+    int32_t area_mask;        /* MAEXP_MASK_*: relative (conv_mlp on the decoded [C,X,Y] canvas, conv_mlp.py:56-66) and merged
+                                 (MergedConvMLP conv_mlp.py:69-108, MergedDA3 da3.py:99-225) need the observing agents' positions */
+    int32_t size_x, size_y;   /* map size for the relative canvas */
+    int32_t patch_size;       /* DA3 model.patch_size (only sizes the parent's unused parameters of MergedDA3) */
 } maexp_learner_cfg;
 
 typedef struct maexp_learner maexp_learner;
@@ -206,6 +213,9 @@ int maexp_learner_tensor(const maexp_learner *learner, int index, char *name, in
                          int64_t *count);
 /* device buffers [G, num_params] (MAEXP_BUF_SUPPORT: [128] atoms z_j or tau_hat_j, written by the host) */
 float *maexp_learner_buffer(maexp_learner *learner, int which);
+/* relative / merged models: index-space positions of the observing agent, int8 [G,B,2] for the state batch and for
+ * the next-state batch (maexp_batch.pos / next_pos); used by the following grads / q_values calls */
+int maexp_learner_bind_positions(maexp_learner *learner, const int8_t *pos, const int8_t *next_pos);
 /* hard_update (core/utils/updates.py:25-34) */
 int maexp_learner_sync_target(maexp_learner *learner, void *stream);
 /* brain.get_action's values: Q [G,batch,A] (C51: sum_j p_j z_j, QR: mean of quantiles) */

@@ -41,12 +41,12 @@ class ObsOut(C.Structure):
 
 
 class ReplayView(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("obs", "actions", "rewards", "dones", "was_reset")] + \
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "actions", "rewards", "dones", "was_reset", "positions")] + \
                [(n, C.c_int32) for n in ("num_slots", "num_envs", "num_agents", "slot_floats", "head", "count")]
 
 
 class Batch(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("obs", "next_obs", "actions", "rewards", "dones", "picked")]
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "next_obs", "actions", "rewards", "dones", "picked", "pos", "next_pos")]
 
 
 class LearnerCfg(C.Structure):
@@ -55,7 +55,7 @@ class LearnerCfg(C.Structure):
                [(n, C.c_float) for n in ("gamma", "v_min", "v_max", "delta_z", "learning_rate", "alpha",
                                           "one_minus_alpha", "eps", "max_norm")] + \
                [(n, C.c_int32) for n in ("num_quantiles_dash", "num_cosines", "embed_dim", "num_heads", "mlp_hidden",
-                                          "block_loop")]
+                                          "block_loop", "area_mask", "size_x", "size_y", "patch_size")]
 
 
 LEARNER_KINDS = {"dqn_conv_mlp": 0, "c51": 1, "qr": 2, "dqn_mlp": 3, "iqn": 4, "da3": 5}
@@ -85,6 +85,7 @@ SYMBOLS = {
     "maexp_learner_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64)]),
     "maexp_learner_buffer": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "maexp_learner_bind_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "maexp_learner_sync_target": (C.c_int, [C.c_void_p, C.c_void_p]),
     "maexp_learner_q_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "maexp_learner_grads": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),

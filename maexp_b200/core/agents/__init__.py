@@ -51,7 +51,7 @@ class BatchedActor:
         self.lib = _lib.load()
         self.env, self.learner = env, learner
         self.chunk = min(int(chunk), env.E)
-        self.group = LearnerGroup(config, [env.C, env.V, env.V], 4, env.N, self.chunk, obs_stride=env.slot_floats,
+        self.group = LearnerGroup(config, env.model_obs_shape, 4, env.N, self.chunk, obs_stride=env.slot_floats,
                                   device=env.device)
         self.actions = torch.zeros((env.E, env.N), dtype=torch.int8, device=env.device)
         self.no_task = torch.tensor([1 if str(t) == "-1" else 0 for t in list(config.agent_tasks)[:env.N]],
@@ -62,13 +62,17 @@ class BatchedActor:
         """Copy the learner's online parameters (the actor is a separate handle sized for acting batches)."""
         self.group.params().copy_(self.learner.params())
 
-    def act(self, obs_slot, epsilon, tick):
-        """obs_slot fp32 [N, E, slot] (an agent-major ring slot) -> int8 actions [E, N] on the device."""
+    def act(self, obs_slot, epsilon, tick, positions=None):
+        """obs_slot fp32 [N, E, slot] (an agent-major ring slot) -> int8 actions [E, N] on the device.
+        positions int8 [E, N, 2]: the step's agent cells, needed by the relative / merged models."""
         env, stream = self.env, C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
         for e0 in range(0, env.E, self.chunk):
             b = min(self.chunk, env.E - e0)
             obs = obs_slot[:, e0:e0 + b].contiguous()  # [N, b, slot]
-            q = self.group.q_values(obs)
+            pos = None
+            if self.group.area_mask != "local":
+                pos = positions[e0:e0 + b].transpose(0, 1).contiguous()  # [N, b, 2]
+            q = self.group.q_values(obs, pos=pos)
             _lib.check(self.lib.maexp_select_actions(C.c_void_p(q.data_ptr()), C.c_void_p(self.actions.data_ptr()),
                                                      env.N, b, 4, e0, float(epsilon), self.seed,
                                                      0, tick & 0xFFFFFFFF, C.c_void_p(self.no_task.data_ptr()), stream))

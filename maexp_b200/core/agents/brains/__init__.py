@@ -31,13 +31,22 @@ def learner_kind(config):
     elif config.model.name == "da3" or kind == "da3":
         if kind != "da3" or config.model.name != "da3":
             raise ValueError("brain=da3 and model=da3 go together (da3_brain.py, customs/da3.py)")
-        if config.observation_area_mask == "merged" or int(config.model.patch_size) != 1 or \
-                config.model.get("attention") == "hard" or config.get("objects_channel"):
-            raise ValueError("DA3 is implemented for the local/relative view with patch_size=1 and soft attention")
+        if config.observation_area_mask == "relative" or config.model.get("attention") == "hard" or \
+                config.get("objects_channel") or (config.observation_area_mask == "local" and int(config.model.patch_size) != 1):
+            raise ValueError("DA3 is implemented for the local view (patch_size=1) and the merged view, soft attention")
     elif config.model.name not in ("conv_mlp", "da3_baseline", "categorical_dqn", "qr_dqn", "iqn"):
         logger.warning(f"Unexpected network is given. config.model.name: {config.model.name}")
         raise ValueError()
+    if config.observation_area_mask != "local" and kind not in ("dqn_conv_mlp", "da3"):
+        raise ValueError("relative / merged views are implemented for the conv_mlp DQN and the merged DA3")
+    if config.observation_area_mask == "merged" and config.observation_noise:
+        # the merged models read the area channel of the NOISE-FREE "relative" key (merged_observtion_handler.py:26-29);
+        # the replay ring keeps only the noisy crop, so this combination is refused rather than approximated
+        raise ValueError("merged view with observation noise is not implemented in the learner")
     return kind, max_norm
+
+
+AREA_MASKS = {"local": 0, "relative": 1, "merged": 2}
 
 
 class LearnerGroup:
@@ -47,7 +56,7 @@ class LearnerGroup:
         self.lib = _lib.load()
         self.config, self.device = config, torch.device(device)
         self.kind, max_norm = learner_kind(config)
-        C_, V = int(obs_shape[0]), int(obs_shape[1])
+        C_, V = int(obs_shape[0]), int(config.visible_range)  # batches always hold the V x V crops
         self.G, self.B, self.A, self.C, self.V = int(num_agents), int(batch_size), int(act_size), C_, V
         self.K = C_ * V * V
         self.obs_stride = int(obs_stride or (self.K + 7) // 8 * 8)
@@ -58,7 +67,11 @@ class LearnerGroup:
         cfg.kind = _lib.LEARNER_KINDS[self.kind]
         cfg.num_agents, cfg.batch_size, cfg.channels, cfg.visible_range = self.G, self.B, C_, V
         cfg.num_actions = self.A
-        cfg.hidden = int(m.hidden_layer_sizes[0]) if self.kind != "da3" else 0
+        self.area_mask = config.observation_area_mask
+        cfg.area_mask = AREA_MASKS[self.area_mask]
+        cfg.size_x, cfg.size_y = int(config.map.SIZE_X), int(config.map.SIZE_Y)
+        cfg.patch_size = int(m.get("patch_size") or 1)
+        cfg.hidden = int(m.hidden_layer_sizes[0]) if (self.kind != "da3" or self.area_mask == "merged") else 0
         if self.kind == "da3":
             cfg.embed_dim, cfg.num_heads, cfg.block_loop = int(m.embed_dim), int(m.num_heads), int(m.block_loop)
             cfg.mlp_hidden = int(int(m.embed_dim) * float(m.mlp_ratio))
@@ -145,10 +158,18 @@ class LearnerGroup:
         _lib.check(self.lib.maexp_learner_sync_target(self.h, self._stream()))
 
     # ------------------------------------------------------------------ compute
-    def q_values(self, obs, use_target=False, tau_sel=None):
+    def bind_positions(self, pos, next_pos=None):
+        """int8 [G, b, 2] index-space positions of the observing agents (relative / merged models)."""
+        self._pos_keep = (pos, next_pos)
+        _lib.check(self.lib.maexp_learner_bind_positions(self.h, C.c_void_p(pos.data_ptr()),
+                                                         None if next_pos is None else C.c_void_p(next_pos.data_ptr())))
+
+    def q_values(self, obs, use_target=False, tau_sel=None, pos=None):
         """obs fp32 [G, b, obs_stride] on the device -> Q [G, b, A].  IQN: tau_sel [G, Nq] (drawn if None,
-        customs/iqn.py:105-106)."""
+        customs/iqn.py:105-106).  Relative / merged models: pos int8 [G, b, 2]."""
         b = obs.shape[1]
+        if pos is not None:
+            self.bind_positions(pos.contiguous())
         q = self.q if b == self.B else torch.empty((self.G, b, self.A), dtype=torch.float32, device=self.device)
         if self.kind == "iqn":
             if tau_sel is None:
@@ -164,6 +185,8 @@ class LearnerGroup:
     def grads(self, batch):
         """Forward, TD target, loss [G] and gradients (kept in the library's grad buffer)."""
         p = lambda t: C.c_void_p(t.data_ptr())
+        if self.area_mask != "local":
+            self.bind_positions(batch["pos"], batch["next_pos"])
         if self.kind == "iqn":  # quantile fractions: injected for parity tests, else drawn like iqn_brain.py:74,87
             d = self.device
             taus = batch["taus"] if "taus" in batch else torch.rand((self.G, self.B, self.Z), device=d)
@@ -210,9 +233,19 @@ class Brain:
         out[0, :, : g.K] = x
         return out
 
+    def _positions(self, state, batched):
+        """Observing agent's index-space cell from the `coordinates` dict (local_area_mask.py:18-47)."""
+        c = state["coordinates"]
+        r = int(self.config.visible_range) // 2
+        px = torch.as_tensor(c["map_x_min"]) - torch.as_tensor(c["obs_x_min"]) + r
+        py = torch.as_tensor(c["map_y_min"]) - torch.as_tensor(c["obs_y_min"]) + r
+        pos = torch.stack([px.reshape(-1), py.reshape(-1)], dim=1).to(torch.int8)
+        return pos.reshape(1, -1, 2).contiguous().to(self.device)
+
     @torch.no_grad()
     def get_action(self, state):
-        q = self.group.q_values(self._pack(state[self.view].unsqueeze(0)))
+        pos = self._positions(state, False) if self.group.area_mask != "local" else None
+        q = self.group.q_values(self._pack(state[self.view].unsqueeze(0)), pos=pos)
         return int(q[0, 0].argmax().item())
 
     def learn(self, states_ind, actions_ind, rewards_ind, dones_ind, next_states_ind):
@@ -220,6 +253,8 @@ class Brain:
                  "actions": actions_ind.to(self.device).to(torch.int32).reshape(1, -1).contiguous(),
                  "rewards": rewards_ind.float().to(self.device).reshape(1, -1).contiguous(),
                  "dones": dones_ind.to(self.device).to(torch.uint8).reshape(1, -1).contiguous()}
+        if self.group.area_mask != "local":
+            batch["pos"], batch["next_pos"] = self._positions(states_ind, True), self._positions(next_states_ind, True)
         loss = self.group.learn(batch)
         return {"total_loss": loss[0].detach().cpu()}  # always a dict
 

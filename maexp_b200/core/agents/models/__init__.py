@@ -34,9 +34,8 @@ class _MLP(nn.Module):
 
 def conv_output_size(config, obs_shape):
     """Flattened size of Conv's output (conv k2 s1 -> max_pool2d(2,2) -> conv k2 s1)."""
-    v = int(obs_shape[1])
-    h2 = (v - 1) // 2 - 1
-    return int(config.model.output_channel) * h2 * h2
+    h2, w2 = (int(obs_shape[1]) - 1) // 2 - 1, (int(obs_shape[2]) - 1) // 2 - 1
+    return int(config.model.output_channel) * h2 * w2
 
 
 class _ConvHeads(nn.Module):
@@ -62,6 +61,23 @@ class _IQN(nn.Module):
         self.cosine_net.net = nn.Sequential(nn.Linear(int(config.model.num_cosines), d), nn.ReLU(inplace=False))
         self.fc_V = _MLP(config, d, 1)
         self.fc_A = _MLP(config, d, act_size)
+
+
+class _MergedConvMLP(nn.Module):
+    """customs/conv_mlp.py:69-98: the parent's `conv` stays as unused parameters; `mlp` is replaced."""
+
+    def __init__(self, config, obs_shape, act_size):
+        super().__init__()
+        v = int(config.visible_range)
+        self.conv = _Conv(config, obs_shape[0], config.model.output_channel)
+        torch.randn(1, *obs_shape)
+        self.mlp = _MLP(config, conv_output_size(config, obs_shape), act_size)  # replaced below, as in the reference
+        self.local_conv = _Conv(config, obs_shape[0], config.model.output_channel)
+        self.relative_conv = _Conv(config, 1, config.model.output_channel)
+        torch.randn(1, obs_shape[0], v, v)
+        torch.randn(1, 1, *obs_shape[1:])
+        d = conv_output_size(config, [obs_shape[0], v, v]) + conv_output_size(config, [1, *obs_shape[1:]])
+        self.mlp = _MLP(config, d, act_size)
 
 
 class _Attention(nn.Module):
@@ -110,11 +126,31 @@ class _DA3(nn.Module):
         self.drl_head = nn.Linear(int(m.embed_dim), act_size)
 
 
+class _MergedDA3(_DA3):
+    """customs/da3.py:99-165: parent parameters (unused) + local ViT + relative conv / embedder + wide head."""
+
+    def __init__(self, config, obs_shape, act_size):
+        super().__init__(config, obs_shape, act_size)
+        m, v = config.model, int(config.visible_range)
+        self.local_patch_embed = _PatchEmbed(1, int(obs_shape[0]), int(m.embed_dim))
+        self.local_saliency_vector = nn.Parameter(torch.zeros(1, 1, int(m.embed_dim)))
+        self.local_pos_embed = nn.Parameter(torch.zeros(1, v * v + 1, int(m.embed_dim)))
+        self.local_blocks = nn.ModuleList([_Block(int(m.embed_dim), float(m.mlp_ratio)) for _ in range(int(m.block_loop))])
+        self.norm = nn.LayerNorm(int(m.embed_dim))
+        self.relative_conv = _Conv(config, 1, m.output_channel)
+        torch.randn(1, 1, *obs_shape[1:])
+        d = conv_output_size(config, [1, *obs_shape[1:]])
+        self.relative_state_embedder = _MLP(config, d, d)
+        self.drl_head = nn.Linear(int(m.embed_dim) + d, act_size)
+
+
 def build_reference_modules(config, obs_shape, act_size):
     name = config.model.name
     if name == "mlp":  # SURVEY.md appendix E-2: the flattened observation feeds the MLP
         return _MLP(config, int(obs_shape[0]) * int(obs_shape[1]) * int(obs_shape[2]), act_size)
     if name in ("conv_mlp", "da3_baseline"):
+        if config.observation_area_mask == "merged":
+            return _MergedConvMLP(config, obs_shape, act_size)
         return _ConvHeads(config, obs_shape, [("mlp", act_size)])
     if name == "categorical_dqn":
         z = int(config.model.num_atoms)
@@ -125,5 +161,7 @@ def build_reference_modules(config, obs_shape, act_size):
     if name == "iqn":
         return _IQN(config, obs_shape, act_size)
     if name == "da3":
+        if config.observation_area_mask == "merged":
+            return _MergedDA3(config, obs_shape, act_size)
         return _DA3(config, obs_shape, act_size)
     raise ValueError(name)

@@ -139,6 +139,14 @@ class BatchedEnvironment:
             self.lib.maexp_env_destroy(h)
 
     # ------------------------------------------------------------------ buffers
+    @property
+    def model_obs_shape(self):
+        """obs_shape the reference hands to generate_brain: [C,V,V], or [C,X,Y] for the relative / merged views
+        (observation_handler.py:60-70, merged_observtion_handler.py:37-39)."""
+        if self.config.observation_area_mask == "local":
+            return [self.C, self.V, self.V]
+        return [self.C, int(self.map.SIZE_X), int(self.map.SIZE_Y)]
+
     def new_slot(self):
         """One replay-ring slot, agent-major: fp32 [N, E, slot_floats] (slot_floats = C*V*V padded to 32 bytes)."""
         return torch.empty((self.N, self.E, self.slot_floats), dtype=torch.float32, device=self.device)

@@ -28,7 +28,7 @@ class DefaultTrainer:
             first_global_env_id=first_global_env_id)
         env = self.env
         self.buffer = generate_buffer(config, env)
-        self.learner = LearnerGroup(config, [env.C, env.V, env.V], 4, env.N, int(config.batch_size),
+        self.learner = LearnerGroup(config, env.model_obs_shape, 4, env.N, int(config.batch_size),
                                     obs_stride=env.slot_floats, device=env.device)
         self.actor = BatchedActor(config, env, self.learner)
         self.batch = self.buffer.new_batch(int(config.batch_size))
@@ -57,7 +57,8 @@ class DefaultTrainer:
         self.buffer.sample(self.batch, seed=int(self.config.seed), tick=self.tick)
         loss = self.learner.learn(self.batch, active=self.active, all_reduce=self.all_reduce)
         self.actor.refresh()
-        actions = self.actor.act(self.buffer.obs[self.buffer.head], self.epsilon, self.tick)
+        head = self.buffer.head
+        actions = self.actor.act(self.buffer.obs[head], self.epsilon, self.tick, positions=self.buffer.positions[head])
         out = self.buffer.next_outputs()
         self.env.step(out, actions=actions, tick=self._tick())
         self.buffer.commit()

@@ -24,6 +24,7 @@ class DeviceReplayRing:
         self.rewards = torch.zeros((self.S, E, N), dtype=torch.float32, device=d)
         self.dones = torch.zeros((self.S, E, N), dtype=torch.uint8, device=d)
         self.was_reset = torch.ones((self.S, E), dtype=torch.uint8, device=d)
+        self.positions = torch.zeros((self.S, E, N, 2), dtype=torch.int8, device=d)
         self.head, self.count = -1, 0
 
     def __len__(self):
@@ -34,7 +35,7 @@ class DeviceReplayRing:
         """Output dict for env.step / env.reset that targets the next ring slot; call commit() after."""
         s = (self.head + 1) % self.S
         return {"obs": self.obs[s], "rewards": self.rewards[s], "dones": self.dones[s],
-                "was_reset": self.was_reset[s], "actions_taken": self.actions[s]}
+                "was_reset": self.was_reset[s], "actions_taken": self.actions[s], "positions": self.positions[s]}
 
     def commit(self):
         self.head = (self.head + 1) % self.S
@@ -47,15 +48,18 @@ class DeviceReplayRing:
                 "actions": torch.empty((N, batch_size), dtype=torch.int32, device=d),
                 "rewards": torch.empty((N, batch_size), dtype=torch.float32, device=d),
                 "dones": torch.empty((N, batch_size), dtype=torch.uint8, device=d),
-                "picked": torch.empty((batch_size, 2), dtype=torch.int32, device=d)}
+                "picked": torch.empty((batch_size, 2), dtype=torch.int32, device=d),
+                "pos": torch.empty((N, batch_size, 2), dtype=torch.int8, device=d),
+                "next_pos": torch.empty((N, batch_size, 2), dtype=torch.int8, device=d)}
 
     def sample(self, batch, seed=0, tick=0, indices=None):
         """Fills `batch` (from new_batch) with uniformly sampled transitions; indices: int32 [B,2]."""
         B = batch["actions"].shape[1]
         view = _lib.ReplayView(self.obs.data_ptr(), self.actions.data_ptr(), self.rewards.data_ptr(),
-                               self.dones.data_ptr(), self.was_reset.data_ptr(), self.S, self.env.E, self.env.N,
+                               self.dones.data_ptr(), self.was_reset.data_ptr(), self.positions.data_ptr(), self.S, self.env.E, self.env.N,
                                self.env.slot_floats, self.head, self.count)
-        out = _lib.Batch(*[batch[k].data_ptr() for k in ("obs", "next_obs", "actions", "rewards", "dones", "picked")])
+        out = _lib.Batch(*[batch[k].data_ptr() for k in ("obs", "next_obs", "actions", "rewards", "dones", "picked", "pos",
+                                                         "next_pos")])
         idx = None if indices is None else C.c_void_p(indices.data_ptr())
         stream = C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
         _lib.check(self.lib.maexp_replay_sample(C.byref(view), B, seed & 0xFFFFFFFF, tick & 0xFFFFFFFF, idx,

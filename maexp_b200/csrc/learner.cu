@@ -251,6 +251,22 @@ __global__ void nhwc_to_flat_kernel(const float *y, float *flat, int B, int Q, i
     }
 }
 
+// NHWC [B][Q][F] <-> a slice of a wider feature row: flat[b*row + off + f*Q + q]  (concatenated embeddings of the
+// merged models, conv_mlp.py:87-98)
+__global__ void nhwc_flat_strided_kernel(const float *y, float *flat, int B, int Q, int F, long long gY, long long row,
+                                         long long off, long long gFlat, int inverse) {
+    const int g = blockIdx.y;
+    const long long total = (long long)B * Q * F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F);
+        const int q = (int)((i / F) % Q);
+        const long long b = i / ((long long)F * Q);
+        const size_t fi = (size_t)g * gFlat + (size_t)b * row + off + (size_t)f * Q + q;
+        if (!inverse) flat[fi] = y[(size_t)g * gY + i];
+        else flat[(size_t)g * gY + i] = y[fi];  // `y` is the gradient of the wide row, `flat` the NHWC gradient
+    }
+}
+
 // ------------------------------------------------------------------------------ losses
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -937,6 +953,20 @@ struct maexp_learner {
     float *d_e = nullptr, *d_phi = nullptr, *d_psi = nullptr, *d_hrow = nullptr;
     struct Da3Block { float *n1, *m1, *r1, *qkv, *probs, *ao, *x1, *n2, *m2, *r2, *f1, *g1, *x2; };
     struct Da3Acts { float *patches, *tok, *x0, *nf, *mf, *rf, *q; std::vector<Da3Block> blk; } da[3];
+    // generalized conv trunks (rectangular input, any source): relative / merged models
+    struct GTrunk {
+        int Cin, Hin, Win, H1, W1, Hp, Wp, H2, W2, D;
+        long long c1w, c1b, c2w, c2b;
+        struct A { float *col1, *y1, *p, *col2, *y2; uint8_t *arg; } a[3];
+        float *d_y2, *d_col2, *d_p, *d_y1;
+    } gt_rel, gt_loc;
+    int area_mask = 0, X = 0, Y = 0, Drel = 0, Dloc = 0;
+    bool merged_conv = false, relative_conv = false, merged_da3 = false;
+    HeadLayout rse;                 // MergedDA3 relative_state_embedder
+    const int8_t *pos = nullptr, *next_pos = nullptr;  // bound by maexp_learner_bind_positions
+    float *canvas[3] = {nullptr, nullptr, nullptr}, *feat[3] = {nullptr, nullptr, nullptr}, *d_feat = nullptr;
+    float *rel_flat[3] = {nullptr, nullptr, nullptr}, *rse_h[3] = {nullptr, nullptr, nullptr}, *rse_out[3] = {nullptr, nullptr, nullptr};
+    float *d_relsal = nullptr, *d_relflat = nullptr;
     float *da_dx = nullptr, *da_dx1 = nullptr, *da_dn = nullptr, *da_gx = nullptr, *da_dqkv = nullptr, *da_dao = nullptr,
           *da_dg1 = nullptr, *da_df1 = nullptr, *da_dnf = nullptr, *da_dtok0 = nullptr, *da_dtok = nullptr;
     // backward workspace
@@ -1144,7 +1174,8 @@ inline void ln_fwd(maexp_learner *h, cudaStream_t st, const float *params, const
                                                                               h->E_, gX, rows_max * h->E_, rows_max, h->P);
 }
 
-void da3_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, int pass) {
+void da3_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, int pass,
+                 bool with_head = true) {
     maexp_learner::Da3Acts &a = h->da[pass];
     const int G = h->G, C = h->C, VV = h->V * h->V, E = h->E_, Tn = h->Tn, Fm = h->Fm;
     const long long P = h->P, Bmax = h->B, Rm = Bmax * Tn, R49 = Bmax * (Tn - 1);
@@ -1176,10 +1207,11 @@ void da3_forward(maexp_learner *h, cudaStream_t st, const float *params, const f
     // final LayerNorm on the saliency token only, then the head (da3.py:59-60,90-96)
     layernorm_fwd_kernel<<<dim3((B * 32 + 255) / 256, G), 256, 0, st>>>(x, (long long)Tn * E, params + h->o_nfw, params + h->o_nfb,
                                                                         a.nf, a.mf, a.rf, B, E, Rm * E, Bmax * E, Bmax, P);
-    gemm(st, G, a.nf, params + h->o_hw, a.q, params + h->o_hb, B, h->A, E, E, 1, 1, E, h->A, 1, Bmax * E, P, Bmax * h->A, P);
+    if (with_head)
+        gemm(st, G, a.nf, params + h->o_hw, a.q, params + h->o_hb, B, h->A, E, E, 1, 1, E, h->A, 1, Bmax * E, P, Bmax * h->A, P);
 }
 
-void da3_backward(maexp_learner *h, cudaStream_t st) {
+void da3_backward(maexp_learner *h, cudaStream_t st, bool with_head = true) {
     maexp_learner::Da3Acts &a = h->da[0];
     const int G = h->G, B = h->B, C = h->C, E = h->E_, Tn = h->Tn, Fm = h->Fm, A = h->A;
     const long long P = h->P, Rm = (long long)B * Tn, R49 = (long long)B * (Tn - 1);
@@ -1194,10 +1226,11 @@ void da3_backward(maexp_learner *h, cudaStream_t st) {
                                                                                 h->da_gx, nrows, E, nrows_max * E, gX, gDx,
                                                                                 nrows_max, P);
     };
-    // head
-    gemm(st, G, dq, a.nf, grads + h->o_hw, nullptr, A, E, B, 1, A, E, 1, E, 1, (long long)B * A, (long long)B * E, P, 0);
-    colsum(st, G, h->ones, dq, grads + h->o_hb, B, A, (long long)B * A, P);
-    gemm(st, G, dq, W + h->o_hw, h->da_dnf, nullptr, B, E, A, A, 1, E, 1, E, 1, (long long)B * A, P, (long long)B * E, 0);
+    if (with_head) {  // drl_head; the merged model fills da_dnf from its own concatenated head
+        gemm(st, G, dq, a.nf, grads + h->o_hw, nullptr, A, E, B, 1, A, E, 1, E, 1, (long long)B * A, (long long)B * E, P, 0);
+        colsum(st, G, h->ones, dq, grads + h->o_hb, B, A, (long long)B * A, P);
+        gemm(st, G, dq, W + h->o_hw, h->da_dnf, nullptr, B, E, A, A, 1, E, 1, E, 1, (long long)B * A, P, (long long)B * E, 0);
+    }
     const float *x_last = h->L_ ? a.blk[h->L_ - 1].x2 : a.x0;
     ln_bwd(h->da_dnf, x_last, (long long)Tn * E, Rm * E, h->o_nfw, a.mf, a.rf, h->da_dtok0, E, (long long)B * E, 0, B, B);
     colsum(st, G, h->ones, h->da_gx, grads + h->o_nfw, B, E, (long long)B * E, P);
@@ -1240,6 +1273,134 @@ void da3_backward(maexp_learner *h, cudaStream_t st) {
     colsum(st, G, h->ones, h->da_dtok, grads + h->o_peb, rows49, E, R49 * E, P);
 }
 
+// ---- generalized conv trunk: src[g][b*sb + c*sc + y*sy + x*sx] -> flat slice [b*flat_row + flat_off + ...]
+void gtrunk_forward(maexp_learner *h, cudaStream_t st, const float *params, maexp_learner::GTrunk &t, int pass, const float *src,
+                    long long sb, long long sc, long long sy, long long sx, long long gSrc, int B, float *flat,
+                    long long flat_row, long long flat_off, long long gFlat) {
+    const int G = h->G, F1 = h->F1, F2 = h->F2;
+    const long long P = h->P, Bmax = h->B;
+    auto &a = t.a[pass];
+    const long long n1 = (long long)t.H1 * t.W1, np = (long long)t.Hp * t.Wp, n2 = (long long)t.H2 * t.W2;
+    const long long gcol1 = Bmax * n1 * t.Cin * 4, gy1 = Bmax * n1 * F1, gp = Bmax * np * F1, gcol2 = Bmax * n2 * F1 * 4,
+                    gy2 = Bmax * n2 * F2;
+    im2col_kernel<<<grid1d((long long)B * n1 * t.Cin * 4, G), 256, 0, st>>>(src, a.col1, B, t.Cin, t.H1, t.W1, sb, sc, sy, sx, gSrc,
+                                                                            gcol1);
+    gemm(st, G, a.col1, params + t.c1w, a.y1, params + t.c1b, (int)(B * n1), F1, t.Cin * 4, t.Cin * 4, 1, 1, t.Cin * 4, F1, 1,
+         gcol1, P, gy1, P);
+    pool_fwd_kernel<<<grid1d((long long)B * np * F1, G), 256, 0, st>>>(a.y1, a.p, a.arg, B, t.H1, t.W1, F1, gy1, gp);
+    im2col_kernel<<<grid1d((long long)B * n2 * F1 * 4, G), 256, 0, st>>>(a.p, a.col2, B, F1, t.H2, t.W2, np * F1, 1,
+                                                                         (long long)t.Wp * F1, F1, gp, gcol2);
+    gemm(st, G, a.col2, params + t.c2w, a.y2, params + t.c2b, (int)(B * n2), F2, F1 * 4, F1 * 4, 1, 1, F1 * 4, F2, 1, gcol2, P,
+         gy2, P);
+    nhwc_flat_strided_kernel<<<grid1d((long long)B * n2 * F2, G), 256, 0, st>>>(a.y2, flat, B, (int)n2, F2, gy2, flat_row, flat_off,
+                                                                                gFlat, 0);
+}
+
+void gtrunk_backward(maexp_learner *h, cudaStream_t st, maexp_learner::GTrunk &t, const float *dflat, long long dflat_row,
+                     long long dflat_off, long long gDflat) {
+    const int G = h->G, B = h->B, F1 = h->F1, F2 = h->F2;
+    const long long P = h->P;
+    auto &a = t.a[0];
+    const long long n1 = (long long)t.H1 * t.W1, np = (long long)t.Hp * t.Wp, n2 = (long long)t.H2 * t.W2;
+    const long long gcol1 = B * n1 * t.Cin * 4, gy1 = B * n1 * F1, gp = B * np * F1, gcol2 = B * n2 * F1 * 4, gy2 = B * n2 * F2;
+    nhwc_flat_strided_kernel<<<grid1d((long long)B * n2 * F2, G), 256, 0, st>>>(dflat, t.d_y2, B, (int)n2, F2, gy2, dflat_row,
+                                                                                dflat_off, gDflat, 1);
+    const int M2 = (int)(B * n2), M1 = (int)(B * n1);
+    gemm(st, G, t.d_y2, a.col2, h->grads + t.c2w, nullptr, F2, F1 * 4, M2, 1, F2, F1 * 4, 1, F1 * 4, 1, gy2, gcol2, P, 0);
+    colsum(st, G, h->ones, t.d_y2, h->grads + t.c2b, M2, F2, gy2, P);
+    gemm(st, G, t.d_y2, h->online + t.c2w, t.d_col2, nullptr, M2, F1 * 4, F2, F2, 1, F1 * 4, 1, F1 * 4, 1, gy2, P, gcol2, 0);
+    col2im_kernel<<<grid1d((long long)B * np * F1, G), 256, 0, st>>>(t.d_col2, t.d_p, B, t.Hp, t.Wp, F1, gcol2, gp);
+    pool_bwd_kernel<<<grid1d((long long)B * n1 * F1, G), 256, 0, st>>>(t.d_p, a.arg, t.d_y1, B, t.H1, t.W1, F1, gy1, gp);
+    gemm(st, G, t.d_y1, a.col1, h->grads + t.c1w, nullptr, F1, t.Cin * 4, M1, 1, F1, t.Cin * 4, 1, t.Cin * 4, 1, gy1, gcol1, P, 0);
+    colsum(st, G, h->ones, t.d_y1, h->grads + t.c1b, M1, F1, gy1, P);
+}
+
+// ---- relative / merged models (conv_mlp.py:56-108, da3.py:99-225): the relative branch reads the decoded canvas
+int decode_canvas(maexp_learner *h, cudaStream_t st, const float *obs, const int8_t *pos, int B, int pass, int only_area) {
+    if (!pos) return fail("maexp_learner: relative / merged models need maexp_learner_bind_positions");
+    return maexp_decode_relative(obs, pos, h->canvas[pass], (int64_t)h->G * B, h->C, h->V, h->X, h->Y, h->cfg.obs_stride, only_area, st);
+}
+
+int rel_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, const int8_t *pos, int B, int pass) {
+    const int V = h->V, C = h->C, X = h->X, Y = h->Y;
+    const long long Bmax = h->B;
+    if (h->relative_conv) {  // ConvMLP on the full canvas [C, X, Y] (conv_mlp.py:56-66)
+        if (decode_canvas(h, st, obs, pos, B, pass, 0)) return -1;
+        gtrunk_forward(h, st, params, h->gt_rel, pass, h->canvas[pass], (long long)C * X * Y, (long long)X * Y, Y, 1,
+                       (long long)B * C * X * Y, B, h->feat[pass], h->Drel, 0, Bmax * h->Drel);
+    } else {  // merged: conv(area canvas + 1) ++ conv(local)  (conv_mlp.py:87-108)
+        if (decode_canvas(h, st, obs, pos, B, pass, 1)) return -1;
+        const long long Dt = h->Drel + h->Dloc;
+        gtrunk_forward(h, st, params, h->gt_rel, pass, h->canvas[pass], (long long)X * Y, (long long)X * Y, Y, 1,
+                       (long long)B * X * Y, B, h->merged_da3 ? h->rel_flat[pass] : h->feat[pass],
+                       h->merged_da3 ? h->Drel : Dt, 0, Bmax * (h->merged_da3 ? h->Drel : Dt));
+        if (!h->merged_da3)
+            gtrunk_forward(h, st, params, h->gt_loc, pass, obs, h->cfg.obs_stride, (long long)V * V, V, 1,
+                           (long long)B * h->cfg.obs_stride, B, h->feat[pass], Dt, h->Drel, Bmax * Dt);
+    }
+    return 0;
+}
+
+int merged_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, const int8_t *pos, int B, int pass,
+                   float **q_out) {
+    const long long Bmax = h->B, P = h->P;
+    if (rel_forward(h, st, params, obs, pos, B, pass)) return -1;
+    if (!h->merged_da3) {
+        const int D = h->D;
+        const MlpIn in = {h->feat[pass], D, Bmax * D, B, Bmax, D};
+        mlp_forward(h, st, params, h->heads[0], in, h->acts[pass].h[0], h->acts[pass].out[0]);
+        *q_out = h->acts[pass].out[0];
+        return 0;
+    }
+    // MergedDA3: [relative_state_embedder(conv(area)), LN(local ViT)[:, 0]] -> drl_head   (da3.py:187-215)
+    const int E = h->E_, Dr = h->Drel, Dt = Dr + E;
+    const MlpIn rin = {h->rel_flat[pass], Dr, Bmax * Dr, B, Bmax, Dr};
+    mlp_forward(h, st, params, h->rse, rin, h->rse_h[pass], h->rse_out[pass]);
+    da3_forward(h, st, params, obs, B, pass, /*with_head=*/false);
+    for (int g = 0; g < h->G; ++g) {  // concatenate per group (2-D copies are graph-capturable)
+        cudaMemcpy2DAsync(h->feat[pass] + (size_t)g * Bmax * Dt, sizeof(float) * Dt, h->rse_out[pass] + (size_t)g * Bmax * Dr,
+                          sizeof(float) * Dr, sizeof(float) * Dr, B, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpy2DAsync(h->feat[pass] + (size_t)g * Bmax * Dt + Dr, sizeof(float) * Dt, h->da[pass].nf + (size_t)g * Bmax * E,
+                          sizeof(float) * E, sizeof(float) * E, B, cudaMemcpyDeviceToDevice, st);
+    }
+    gemm(st, h->G, h->feat[pass], params + h->o_hw, h->da[pass].q, params + h->o_hb, B, h->A, Dt, Dt, 1, 1, Dt, h->A, 1, Bmax * Dt, P,
+         Bmax * h->A, P);
+    *q_out = h->da[pass].q;
+    return 0;
+}
+
+void merged_backward(maexp_learner *h, cudaStream_t st) {
+    const int G = h->G, B = h->B, A = h->A;
+    const long long P = h->P;
+    if (!h->merged_da3) {
+        const int D = h->D;
+        const MlpIn in = {h->feat[0], D, (long long)B * D, B, B, D};
+        mlp_backward(h, st, h->heads[0], in, h->d_out[0], h->acts[0].h[0], h->d_h, h->d_feat, 0);
+        if (h->relative_conv) {
+            gtrunk_backward(h, st, h->gt_rel, h->d_feat, D, 0, (long long)B * D);
+        } else {
+            gtrunk_backward(h, st, h->gt_rel, h->d_feat, D, 0, (long long)B * D);
+            gtrunk_backward(h, st, h->gt_loc, h->d_feat, D, h->Drel, (long long)B * D);
+        }
+        return;
+    }
+    const int E = h->E_, Dr = h->Drel, Dt = Dr + E;
+    const float *dq = h->d_out[0];
+    gemm(st, G, dq, h->feat[0], h->grads + h->o_hw, nullptr, A, Dt, B, 1, A, Dt, 1, Dt, 1, (long long)B * A, (long long)B * Dt, P, 0);
+    colsum(st, G, h->ones, dq, h->grads + h->o_hb, B, A, (long long)B * A, P);
+    gemm(st, G, dq, h->online + h->o_hw, h->d_feat, nullptr, B, Dt, A, A, 1, Dt, 1, Dt, 1, (long long)B * A, P, (long long)B * Dt, 0);
+    for (int g = 0; g < G; ++g) {  // split the concatenated gradient
+        cudaMemcpy2DAsync(h->d_relsal + (size_t)g * B * Dr, sizeof(float) * Dr, h->d_feat + (size_t)g * B * Dt, sizeof(float) * Dt,
+                          sizeof(float) * Dr, B, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpy2DAsync(h->da_dnf + (size_t)g * B * E, sizeof(float) * E, h->d_feat + (size_t)g * B * Dt + Dr, sizeof(float) * Dt,
+                          sizeof(float) * E, B, cudaMemcpyDeviceToDevice, st);
+    }
+    const MlpIn rin = {h->rel_flat[0], Dr, (long long)B * Dr, B, B, Dr};
+    mlp_backward(h, st, h->rse, rin, h->d_relsal, h->rse_h[0], h->d_h, h->d_relflat, 0);
+    gtrunk_backward(h, st, h->gt_rel, h->d_relflat, Dr, 0, (long long)B * Dr);
+    da3_backward(h, st, /*with_head=*/false);
+}
+
 }  // namespace
 
 extern "C" {
@@ -1255,7 +1416,14 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
     h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;
     h->da3 = cfg->kind == MAEXP_LEARNER_DA3;
-    h->has_conv = cfg->kind != MAEXP_LEARNER_DQN_MLP && !h->da3;
+    h->area_mask = cfg->area_mask; h->X = cfg->size_x; h->Y = cfg->size_y;
+    h->relative_conv = cfg->kind == MAEXP_LEARNER_DQN_CONV_MLP && cfg->area_mask == MAEXP_MASK_RELATIVE;
+    h->merged_conv = cfg->kind == MAEXP_LEARNER_DQN_CONV_MLP && cfg->area_mask == MAEXP_MASK_MERGED;
+    h->merged_da3 = h->da3 && cfg->area_mask == MAEXP_MASK_MERGED;
+    const bool gmodel = h->relative_conv || h->merged_conv || h->merged_da3;
+    if (cfg->area_mask != MAEXP_MASK_LOCAL && !gmodel) { delete h; return fail("maexp_learner_create: relative / merged views are implemented for conv_mlp (dqn) and da3 (merged)"); }
+    if (gmodel && (h->X < 4 || h->Y < 4)) { delete h; return fail("maexp_learner_create: size_x / size_y missing for a relative / merged model"); }
+    h->has_conv = cfg->kind != MAEXP_LEARNER_DQN_MLP && !h->da3 && !gmodel;
     h->dist = cfg->kind == MAEXP_LEARNER_C51 || cfg->kind == MAEXP_LEARNER_QR;
     h->iqn = cfg->kind == MAEXP_LEARNER_IQN;
     h->Nq = h->iqn ? cfg->num_atoms : 0;
@@ -1273,6 +1441,27 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         off += count;
         return o;
     };
+    auto set_trunk = [&](maexp_learner::GTrunk &t, const std::string &prefix, int cin, int hin, int win) {
+        t.Cin = cin; t.Hin = hin; t.Win = win;
+        t.H1 = hin - 1; t.W1 = win - 1; t.Hp = t.H1 / 2; t.Wp = t.W1 / 2; t.H2 = t.Hp - 1; t.W2 = t.Wp - 1;
+        t.D = h->F2 * t.H2 * t.W2;
+        t.c1w = add(prefix + ".conv_list.0.weight", (long long)h->F1 * cin * 4);
+        t.c1b = add(prefix + ".conv_list.0.bias", h->F1);
+        t.c2w = add(prefix + ".conv_post.weight", (long long)h->F2 * h->F1 * 4);
+        t.c2b = add(prefix + ".conv_post.bias", h->F2);
+    };
+    if (h->relative_conv) {  // ConvMLP on the decoded [C, X, Y] canvas (conv_mlp.py:21-66)
+        set_trunk(h->gt_rel, "conv", h->C, h->X, h->Y);
+        h->Drel = h->gt_rel.D; h->Dloc = 0; h->D = h->Drel;
+        h->H1 = h->Hp = h->H2 = 0;
+    } else if (h->merged_conv) {  // MergedConvMLP (conv_mlp.py:69-108); the parent's `conv` keeps unused parameters
+        maexp_learner::GTrunk unused;
+        set_trunk(unused, "conv", h->C, h->X, h->Y);
+        set_trunk(h->gt_loc, "local_conv", h->C, h->V, h->V);
+        set_trunk(h->gt_rel, "relative_conv", 1, h->X, h->Y);
+        h->Drel = h->gt_rel.D; h->Dloc = h->gt_loc.D; h->D = h->Drel + h->Dloc;
+        h->H1 = h->Hp = h->H2 = 0;
+    }
     if (h->da3) {
         h->E_ = cfg->embed_dim; h->heads_ = cfg->num_heads; h->Fm = cfg->mlp_hidden; h->L_ = cfg->block_loop;
         h->Tn = h->V * h->V + 1;
@@ -1284,12 +1473,29 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             return fail("maexp_learner_create: unsupported DA3 shape (tokens <= 96, head_dim <= 32, attention tile <= 48 KB)");
         }
         // own parameters first, then submodules in registration order (customs/da3.py:33-60)
-        h->o_sal = add("saliency_vector", h->E_);
-        h->o_pos = add("pos_embed", (long long)h->Tn * h->E_);
-        h->o_pew = add("patch_embed.proj.weight", (long long)h->E_ * h->C);
-        h->o_peb = add("patch_embed.proj.bias", h->E_);
+        const std::string lp = h->merged_da3 ? "local_" : "";
+        if (h->merged_da3) {  // parameters the parent DA3.__init__ creates and MergedDA3 never uses (da3.py:99-103)
+            const int ps = cfg->patch_size > 0 ? cfg->patch_size : 1;
+            add("saliency_vector", h->E_);
+            add("pos_embed", (long long)((h->X / ps) * (h->Y / ps) + 1) * h->E_);
+            add("patch_embed.proj.weight", (long long)h->E_ * h->C * ps * ps);
+            add("patch_embed.proj.bias", h->E_);
+            for (int l = 0; l < h->L_; ++l) {
+                const std::string b = "blocks." + std::to_string(l) + ".";
+                add(b + "norm1.weight", h->E_); add(b + "norm1.bias", h->E_);
+                add(b + "attn.qkv.weight", 3ll * h->E_ * h->E_);
+                add(b + "attn.proj.weight", (long long)h->E_ * h->E_); add(b + "attn.proj.bias", h->E_);
+                add(b + "norm2.weight", h->E_); add(b + "norm2.bias", h->E_);
+                add(b + "mlp.fc1.weight", (long long)h->Fm * h->E_); add(b + "mlp.fc1.bias", h->Fm);
+                add(b + "mlp.fc2.weight", (long long)h->E_ * h->Fm); add(b + "mlp.fc2.bias", h->E_);
+            }
+        }
+        h->o_sal = add(lp + "saliency_vector", h->E_);
+        h->o_pos = add(lp + "pos_embed", (long long)h->Tn * h->E_);
+        h->o_pew = add(lp + "patch_embed.proj.weight", (long long)h->E_ * h->C);
+        h->o_peb = add(lp + "patch_embed.proj.bias", h->E_);
         for (int l = 0; l < h->L_; ++l) {
-            const std::string b = "blocks." + std::to_string(l) + ".";
+            const std::string b = lp + "blocks." + std::to_string(l) + ".";
             maexp_learner::BlockLayout w;
             w.n1w = add(b + "norm1.weight", h->E_); w.n1b = add(b + "norm1.bias", h->E_);
             w.qkvw = add(b + "attn.qkv.weight", 3ll * h->E_ * h->E_);
@@ -1300,7 +1506,13 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             h->blocks.push_back(w);
         }
         h->o_nfw = add("norm.weight", h->E_); h->o_nfb = add("norm.bias", h->E_);
-        h->o_hw = add("drl_head.weight", (long long)h->A * h->E_); h->o_hb = add("drl_head.bias", h->A);
+        if (h->merged_da3) {
+            set_trunk(h->gt_rel, "relative_conv", 1, h->X, h->Y);
+            h->Drel = h->gt_rel.D; h->Dloc = 0;
+        }
+        h->o_hw = add("drl_head.weight", (long long)h->A * (h->E_ + h->Drel)); h->o_hb = add("drl_head.bias", h->A);
+    } else if (gmodel) {
+        // layout set above
     } else if (h->has_conv) {
         h->H1 = h->V - 1; h->Hp = h->H1 / 2; h->H2 = h->Hp - 1;
         if (h->H2 < 1) { delete h; return fail("maexp_learner_create: visible_range too small for the conv trunk"); }
@@ -1323,8 +1535,17 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         hd.out = outn;
         h->heads.push_back(hd);
     };
-    if (h->da3) {
+    if (h->merged_da3) {  // relative_state_embedder: MLP(Drel -> H -> Drel)  (da3.py:160-162)
+        const int keepD = h->D;
+        h->D = h->Drel;
+        add_head("relative_state_embedder", h->Drel);
+        h->rse = h->heads.back();
+        h->heads.pop_back();
+        h->D = keepD;
+    } else if (h->da3) {
         // no MLP heads: the drl_head is part of the layout above
+    } else if (h->relative_conv || h->merged_conv) {
+        add_head("mlp", h->A);
     } else if (h->iqn) {  // state_dict order of customs/iqn.py:43-67
         add_head("state_embedder", h->D);
         h->se = h->heads.back();
@@ -1426,6 +1647,40 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         rc |= lalloc(h, &h->d_p, G * B * h->Hp * h->Hp * h->F1);
         rc |= lalloc(h, &h->d_y1, G * B * h->H1 * h->H1 * h->F1);
     }
+    if (gmodel) {
+        auto alloc_trunk = [&](maexp_learner::GTrunk &t) {
+            const long long n1 = (long long)t.H1 * t.W1, np = (long long)t.Hp * t.Wp, n2 = (long long)t.H2 * t.W2;
+            for (int k = 0; k < 3; ++k) {
+                rc |= lalloc(h, &t.a[k].col1, G * B * n1 * t.Cin * 4);
+                rc |= lalloc(h, &t.a[k].y1, G * B * n1 * h->F1);
+                rc |= lalloc(h, &t.a[k].p, G * B * np * h->F1);
+                rc |= lalloc(h, &t.a[k].arg, G * B * np * h->F1);
+                rc |= lalloc(h, &t.a[k].col2, G * B * n2 * h->F1 * 4);
+                rc |= lalloc(h, &t.a[k].y2, G * B * n2 * h->F2);
+            }
+            rc |= lalloc(h, &t.d_y2, G * B * n2 * h->F2);
+            rc |= lalloc(h, &t.d_col2, G * B * n2 * h->F1 * 4);
+            rc |= lalloc(h, &t.d_p, G * B * np * h->F1);
+            rc |= lalloc(h, &t.d_y1, G * B * n1 * h->F1);
+        };
+        alloc_trunk(h->gt_rel);
+        if (h->merged_conv) alloc_trunk(h->gt_loc);
+        const long long Dt = h->merged_da3 ? h->Drel + h->E_ : h->D;
+        for (int k = 0; k < 3; ++k) {
+            rc |= lalloc(h, &h->canvas[k], G * B * (h->relative_conv ? h->C : 1) * h->X * h->Y);
+            rc |= lalloc(h, &h->feat[k], G * B * Dt);
+            if (h->merged_da3) {
+                rc |= lalloc(h, &h->rel_flat[k], G * B * h->Drel);
+                rc |= lalloc(h, &h->rse_h[k], G * B * h->H);
+                rc |= lalloc(h, &h->rse_out[k], G * B * h->Drel);
+            }
+        }
+        rc |= lalloc(h, &h->d_feat, G * B * Dt);
+        if (h->merged_da3) {
+            rc |= lalloc(h, &h->d_relsal, G * B * h->Drel);
+            rc |= lalloc(h, &h->d_relflat, G * B * h->Drel);
+        }
+    }
     rc |= lalloc(h, &h->per_sample, G * B);
     rc |= lalloc(h, &h->m_scratch, G * B * 128);
     rc |= lalloc(h, &h->q_tmp, G * B * h->A);
@@ -1470,6 +1725,13 @@ float *maexp_learner_buffer(maexp_learner *h, int which) {
     return nullptr;
 }
 
+int maexp_learner_bind_positions(maexp_learner *h, const int8_t *pos, const int8_t *next_pos) {
+    if (!h) return fail("maexp_learner_bind_positions: null handle");
+    h->pos = pos;
+    h->next_pos = next_pos;
+    return 0;
+}
+
 int maexp_learner_sync_target(maexp_learner *h, void *stream) {
     if (!h) return fail("maexp_learner_sync_target: null handle");
     MAEXP_CUDA_L(cudaMemcpyAsync(h->target, h->online, sizeof(float) * h->G * h->P, cudaMemcpyDeviceToDevice,
@@ -1484,6 +1746,14 @@ int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int us
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     maexp_learner::Acts &a = h->acts[1];
     g_splitk_ws = h->splitk_ws;
+    if (h->relative_conv || h->merged_conv || h->merged_da3) {
+        float *q = nullptr;
+        if (merged_forward(h, st, use_target ? h->target : h->online, obs, h->pos, batch, 1, &q)) return -1;
+        MAEXP_CUDA_L(cudaMemcpy2DAsync(q_out, sizeof(float) * batch * h->A, q, sizeof(float) * h->B * h->A,
+                                       sizeof(float) * batch * h->A, h->G, cudaMemcpyDeviceToDevice, st));
+        MAEXP_CUDA_L(cudaGetLastError());
+        return 0;
+    }
     if (h->da3) {
         da3_forward(h, st, use_target ? h->target : h->online, obs, batch, 1);
         MAEXP_CUDA_L(cudaMemcpy2DAsync(q_out, sizeof(float) * batch * h->A, h->da[1].q, sizeof(float) * h->B * h->A,
@@ -1511,6 +1781,17 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
     if (h->iqn) return fail("maexp_learner_grads: use maexp_learner_grads_iqn for IQN");
     const int G = h->G, B = h->B, A = h->A, Z = h->Z;
     g_splitk_ws = h->splitk_ws;
+    if (h->relative_conv || h->merged_conv || h->merged_da3) {  // TD target + MSE on the relative / merged models
+        float *q0 = nullptr, *q2 = nullptr;
+        if (merged_forward(h, st, h->online, obs, h->pos, B, 0, &q0)) return -1;
+        if (merged_forward(h, st, h->target, next_obs, h->next_pos, B, 2, &q2)) return -1;
+        dqn_loss_kernel<<<dim3((B + 127) / 128, G), 128, 0, st>>>(q0, q2, actions, rewards, dones, h->cfg.gamma, B, A, h->d_out[0],
+                                                                  h->per_sample);
+        mean_kernel<<<G, 256, 0, st>>>(h->per_sample, loss_out ? loss_out : h->q_tmp, B);
+        merged_backward(h, st);
+        MAEXP_CUDA_L(cudaGetLastError());
+        return 0;
+    }
     if (h->da3) {  // DA3Brain.learn: TD target + MSE on the attention network (da3_brain.py:58-89)
         da3_forward(h, st, h->online, obs, B, 0);
         da3_forward(h, st, h->target, next_obs, B, 2);

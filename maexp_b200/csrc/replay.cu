@@ -58,6 +58,13 @@ __global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint3
         out.actions[o] = r.actions[m];
         out.rewards[o] = r.rewards[m];
         out.dones[o] = r.dones[m];
+        if (out.pos && r.positions) {
+            const size_t ps = (((size_t)slot * r.num_envs + env) * N + agent) * 2, pn = (((size_t)nxt * r.num_envs + env) * N + agent) * 2;
+            out.pos[o * 2] = r.positions[ps];
+            out.pos[o * 2 + 1] = r.positions[ps + 1];
+            out.next_pos[o * 2] = r.positions[pn];
+            out.next_pos[o * 2 + 1] = r.positions[pn + 1];
+        }
         if (out.picked && agent == 0) {
             out.picked[2 * b] = slot;
             out.picked[2 * b + 1] = env;

@@ -15,6 +15,8 @@ from oracle import ref_runner as rr
 
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 B = 32
+SIZE = (12, 10)  # map of the relative / merged fixtures
+VIEW = 5
 
 
 def configs():
@@ -28,13 +30,27 @@ def configs():
     da3 = c5.merged_with(batch_size=B, brain="da3", agent_type="attention")
     da3["model"] = dict(name="da3", embed_dim=64, patch_size=1, block_loop=1, num_heads=4, mlp_ratio=4.0,
                         attention="soft", af_lambd=0.5)
-    return {"da3": (da3, [3, 7, 7]), "dqn_conv_mlp": (dqn, [7, 7, 7]), "c51": (c5.merged_with(batch_size=B), [3, 7, 7]),
+    # relative / merged views on a small rectangular map (the models only read map.SIZE_X / SIZE_Y)
+    small = dict(hidden_channels=[8], output_channel=16, hidden_kernels=[2, 2], hidden_strides=[1, 1],
+                 conv_afs=["max_pool2d", "max_pool2d"], af_kernels=[2, 2], af_strides=[2, 2], hidden_layer_sizes=[32], fc_afs=["relu"])
+    def view(mask, name, brain, **extra):
+        c = c2.merged_with(brain=brain, batch_size=B, observation_noise=False, observation_area_mask=mask, visible_range=5)
+        c["map"] = dict(c.map, SIZE_X=SIZE[0], SIZE_Y=SIZE[1])
+        c["model"] = dict(small, name=name, patch_size=1, num_heads=2, **extra)
+        return c
+    rel = view("relative", "da3_baseline", "da3_baseline")
+    mconv = view("merged", "da3_baseline", "da3_baseline")
+    mda3 = view("merged", "da3", "da3", embed_dim=32, block_loop=1, mlp_ratio=4.0, attention="soft", af_lambd=0.5)
+    mda3["agent_type"] = "attention"
+    return {"relative_conv_mlp": (rel, [4, *SIZE]), "merged_conv_mlp": (mconv, [4, *SIZE]), "merged_da3": (mda3, [4, *SIZE]),
+            "da3": (da3, [3, 7, 7]), "dqn_conv_mlp": (dqn, [7, 7, 7]), "c51": (c5.merged_with(batch_size=B), [3, 7, 7]),
             "qr": (c3.merged_with(batch_size=B), [3, 7, 7]), "iqn": (iqn, [3, 7, 7])}
 
 
-def synthetic_batch(shape, seed):
+def synthetic_batch(shape, seed, V=None):
     g = torch.Generator().manual_seed(seed)
-    C, V, _ = shape
+    C = shape[0]
+    V = V or shape[1]
     def obs():
         x = (torch.rand((B, C, V, V), generator=g) < 0.15).float()
         x[:, -1] = -(torch.rand((B, V, V), generator=g) < 0.3).float()
@@ -44,6 +60,13 @@ def synthetic_batch(shape, seed):
             "dones": torch.rand((B,), generator=g) < 0.1}
 
 
+def ref_state(obs, pos):
+    """The dict the reference's relative / merged observation handlers hand to a brain."""
+    from oracle.torch_learner import coordinates
+    c = coordinates(pos, obs.shape[2], *SIZE)
+    return {"local": obs.clone(), "relative": obs.clone(), "coordinates": {k: torch.tensor(v) for k, v in c.items()}}
+
+
 def main():
     rr._import_reference()
     from core.agents.brains import generate_brain
@@ -51,6 +74,11 @@ def main():
     for kind, (cfg, shape) in configs().items():
         torch.manual_seed(921)
         brain = generate_brain(config=rr.to_dictconfig(cfg), obs_shape=shape, act_size=4)
+        masked = kind in ("relative_conv_mlp", "merged_conv_mlp", "merged_da3")
+        if kind == "merged_da3":
+            with torch.no_grad():
+                brain.network.local_saliency_vector.add_(0.02 * torch.randn_like(brain.network.local_saliency_vector))
+                brain.network.local_pos_embed.add_(0.02 * torch.randn_like(brain.network.local_pos_embed))
         if kind == "da3":  # zero-initialised embeddings (da3.py:41-44): perturb so the fixture exercises them
             with torch.no_grad():
                 brain.network.saliency_vector.add_(0.02 * torch.randn_like(brain.network.saliency_vector))
@@ -61,9 +89,20 @@ def main():
                 p_.add_(0.01 * torch.randn_like(p_))
         init = {k: v.detach().clone() for k, v in brain.network.state_dict().items()}
         tgt = {k: v.detach().clone() for k, v in brain.target_network.state_dict().items()}
-        batch = synthetic_batch(shape, 7)
+        batch = synthetic_batch(shape, 7, VIEW if masked else None)
+        if masked:
+            gp = torch.Generator().manual_seed(11)
+            for key in ("pos", "next_pos"):
+                batch[key] = torch.stack([torch.randint(0, SIZE[0], (B,), generator=gp),
+                                          torch.randint(0, SIZE[1], (B,), generator=gp)], dim=1)
+            batch["pos"][0], batch["pos"][1] = torch.tensor([0, 0]), torch.tensor([SIZE[0] - 1, SIZE[1] - 1])
+        state = (lambda: ref_state(batch["obs"], batch["pos"])) if masked else (lambda: {"local": batch["obs"].clone()})
+        next_state = (lambda: ref_state(batch["next_obs"], batch["next_pos"])) if masked else \
+            (lambda: {"local": batch["next_obs"].clone()})
         with torch.no_grad():
-            if kind == "c51":
+            if masked:
+                q0 = brain.network(state())
+            elif kind == "c51":
                 from core.agents.models.customs.categorical_dqn import ApplySoftmax
                 q0 = torch.sum(brain.network({"local": batch["obs"].clone()}, ApplySoftmax.NORMAL) * brain.support, dim=2)
             elif kind == "qr":
@@ -85,8 +124,8 @@ def main():
             return t
         for _ in range(2):
             torch.rand = recording_rand if kind == "iqn" else real_rand
-            out = brain.learn({"local": batch["obs"].clone()}, batch["actions"].clone(), batch["rewards"].clone(),
-                              batch["dones"].clone(), {"local": batch["next_obs"].clone()})
+            out = brain.learn(state(), batch["actions"].clone(), batch["rewards"].clone(),
+                              batch["dones"].clone(), next_state())
             torch.rand = real_rand
             losses.append(float(out["total_loss"] if isinstance(out, dict) else out))
         final = {k: v.detach().clone() for k, v in brain.network.state_dict().items()}
@@ -102,7 +141,7 @@ def main():
             arrays["tau0"] = tau0.numpy()
         path = os.path.join(GOLDEN, f"learner_{kind}.npz")
         np.savez_compressed(path, losses=np.array(losses, np.float64), q0=q0.numpy(), shape=np.array(shape),
-                            gamma=float(cfg.gamma), **arrays)
+                            gamma=float(cfg.gamma), area_mask=cfg.observation_area_mask, **arrays)
         print(kind, losses, os.path.getsize(path), "bytes")
 
 
