@@ -30,9 +30,9 @@ ENVS_PER_GPU = 65536
 RING_SLOTS = 8
 B_ALG = 744.0  # algorithmic bytes per agent-step for cfg5 (588 obs + 144 grid r/w + 12)
 METRIC, UNIT = "agent_steps_per_sec", "agent-steps/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of env_step_kernel<7,16,0> at this
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of env_step_kernel<7,16,0,8> at this
 # workload, from profiles/ (ncu --set full)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 282.1e6  # 8.87 MB read + 273.25 MB written (profiles/r1_env_step_kernel_ncu_full.csv)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 284.9e6  # 8.86 MB read + 276.01 MB written (profiles/r1_env_step_kernel_ncu_full.csv)
 
 
 def workload_config():
@@ -227,21 +227,30 @@ def run_ours(args, rank, local_rank, world):
     after = env.stats()
     env_steps = after["env_steps"] - before["env_steps"]  # resets (1 in L+1 calls per env) are not counted
 
-    # ---- end to end through the host-buffer C-ABI entry point: pinned actions in, rewards/dones out
-    actions = torch.randint(0, 4, (E, N), dtype=torch.int8).pin_memory()
-    rewards = torch.empty((E, N), dtype=torch.float32).pin_memory()
-    dones = torch.empty((E, N), dtype=torch.uint8).pin_memory()
-    was_reset = torch.empty((E,), dtype=torch.uint8).pin_memory()
-    for _ in range(3):
-        env.step_host(actions, ring.obs[tick % RING_SLOTS], rewards, dones, was_reset, tick=tick)
+    # ---- end to end through the host-buffer C-ABI entry point: every step copies its pinned actions in and its
+    #      rewards / dones / was_reset out; copies and kernels of consecutive steps overlap (3 steps in flight)
+    depth = 4
+    hb = [{"actions": torch.randint(0, 4, (E, N), dtype=torch.int8).pin_memory(),
+           "rewards": torch.empty((E, N), dtype=torch.float32).pin_memory(),
+           "dones": torch.empty((E, N), dtype=torch.uint8).pin_memory(),
+           "was_reset": torch.empty((E,), dtype=torch.uint8).pin_memory()} for _ in range(depth)]
+
+    def host_step(i, tick):
+        b = hb[i % depth]
+        return env.step_host_async(b["actions"], ring.obs[tick % RING_SLOTS], b["rewards"], b["dones"], b["was_reset"],
+                                   tick=tick)
+    for i in range(3):
+        host_step(i, tick)
         tick += 1
+    env.host_wait()
     k2 = max(1, min(K, 200))
     b2 = env.stats()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(k2):
-        env.step_host(actions, ring.obs[tick % RING_SLOTS], rewards, dones, was_reset, tick=tick)
+    for i in range(k2):
+        host_step(i, tick)
         tick += 1
+    env.host_wait()  # every step's results are in host memory
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_steps = env.stats()["env_steps"] - b2["env_steps"]
@@ -307,8 +316,9 @@ def run_ours(args, rank, local_rank, world):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": config_block(E),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * N, "d2h_bytes_per_step": E * N * 5 + E,
-                    "steps": k2, "note": "maexp_env_step_host: pinned actions H2D, rewards+dones+was_reset D2H every "
-                                         "step, stream sync per step; observations stay in the device replay ring"},
+                    "steps": k2, "note": "maexp_env_step_host_async: pinned actions H2D, rewards+dones+was_reset D2H every "
+                                         "step on copy streams, 3 steps in flight, wall clock until the last step's "
+                                         "results are in host memory; observations stay in the device replay ring"},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,

@@ -118,6 +118,17 @@ int maexp_env_step(maexp_env *env, uint32_t tick, const int8_t *actions, const u
 int maexp_env_step_host(maexp_env *env, uint32_t tick, const int8_t *actions_host, float *obs_ring_slot,
                         float *rewards_host, uint8_t *dones_host, uint8_t *was_reset_host, void *stream);
 
+/* Pipelined form of the same call for host-driven rollouts (the loop of abstract_trainer.py:63-89 with a
+ * scripted or random host policy): returns once the step is enqueued.  The action copy, the step kernel and
+ * the result copies of consecutive steps overlap on separate streams; up to 3 steps are in flight and a call
+ * blocks only until the step issued 3 calls earlier has delivered its results.  Every step still copies its
+ * actions in and its rewards / dones / was_reset out; the host buffers of a step (use pinned memory and a
+ * distinct set per in-flight step) are valid after maexp_env_host_wait(env, ticket); ticket 0 waits for all. */
+int maexp_env_step_host_async(maexp_env *env, uint32_t tick, const int8_t *actions_host, float *obs_ring_slot,
+                              float *rewards_host, uint8_t *dones_host, uint8_t *was_reset_host, void *stream,
+                              uint64_t *ticket);
+int maexp_env_host_wait(maexp_env *env, uint64_t ticket);
+
 /* State taps: map.agents_matrix / objects_matrix / destination_area_matrix and the env counters
  * (default_environment.py:65-69) in the reference's dtypes.  Device pointers, may be NULL. */
 int maexp_env_get_state(maexp_env *env, int8_t *pos /*[E,N,2]*/, int8_t *objects /*[E,T,X,Y]*/,

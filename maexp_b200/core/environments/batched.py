@@ -218,6 +218,20 @@ class BatchedEnvironment:
                                                 C.c_void_p(obs_slot.data_ptr()), hp(rewards_host), hp(dones_host),
                                                 hp(was_reset_host), self._stream()))
 
+    def step_host_async(self, actions_host, obs_slot, rewards_host, dones_host, was_reset_host, tick=None):
+        """Pipelined step_host: returns a ticket at once; the step's host buffers are valid after host_wait(ticket).
+        Use pinned tensors and a distinct set per in-flight step (3 deep)."""
+        def hp(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        ticket = C.c_uint64()
+        _lib.check(self.lib.maexp_env_step_host_async(self.h, self._next_tick(tick), hp(actions_host),
+                                                      C.c_void_p(obs_slot.data_ptr()), hp(rewards_host), hp(dones_host),
+                                                      hp(was_reset_host), self._stream(), C.byref(ticket)))
+        return ticket.value
+
+    def host_wait(self, ticket=0):
+        _lib.check(self.lib.maexp_env_host_wait(self.h, int(ticket)))
+
     def state(self):
         d = self.device
         pos = torch.zeros((self.E, self.N, 2), dtype=torch.int8, device=d)

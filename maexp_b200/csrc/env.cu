@@ -116,6 +116,17 @@ struct maexp_env {
     int8_t *d_actions = nullptr;
     float *d_rewards = nullptr;
     uint8_t *d_dones = nullptr, *d_was_reset = nullptr;
+    // pipelined host entry point: kHostDepth steps in flight, copies on their own streams
+    struct HostSlot {
+        int8_t *actions = nullptr;
+        float *rewards = nullptr;
+        uint8_t *dones = nullptr, *was_reset = nullptr;
+        cudaEvent_t in = nullptr, stepped = nullptr, out = nullptr;
+    };
+    static constexpr int kHostDepth = 3;
+    HostSlot slots[kHostDepth];
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    uint64_t issued = 0;
 };
 
 namespace {
@@ -343,6 +354,17 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
 
 void maexp_env_destroy(maexp_env *h) {
     if (!h) return;
+    if (h->h2d) {
+        cudaStreamSynchronize(h->h2d);
+        cudaStreamSynchronize(h->d2h);
+        for (auto &sl : h->slots) {
+            if (sl.in) cudaEventDestroy(sl.in);
+            if (sl.stepped) cudaEventDestroy(sl.stepped);
+            if (sl.out) cudaEventDestroy(sl.out);
+        }
+        cudaStreamDestroy(h->h2d);
+        cudaStreamDestroy(h->d2h);
+    }
     for (void *d : h->allocs) cudaFree(d);
     delete h;
 }
@@ -379,6 +401,64 @@ int maexp_env_step_host(maexp_env *h, uint32_t tick, const int8_t *actions_host,
     if (dones_host) MAEXP_CUDA(cudaMemcpyAsync(dones_host, h->d_dones, EN, cudaMemcpyDeviceToHost, stream));
     if (was_reset_host) MAEXP_CUDA(cudaMemcpyAsync(was_reset_host, h->d_was_reset, h->p.E, cudaMemcpyDeviceToHost, stream));
     MAEXP_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+int maexp_env_step_host_async(maexp_env *h, uint32_t tick, const int8_t *actions_host, float *obs_ring_slot,
+                              float *rewards_host, uint8_t *dones_host, uint8_t *was_reset_host, void *stream_,
+                              uint64_t *ticket) {
+    if (!h) return fail("maexp_env_step_host_async: null handle");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t E = (size_t)h->p.E, EN = E * h->p.N;
+    if (!h->h2d) {
+        MAEXP_CUDA(cudaStreamCreateWithFlags(&h->h2d, cudaStreamNonBlocking));
+        MAEXP_CUDA(cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking));
+        for (auto &sl : h->slots) {
+            int rc = dev_alloc(h, &sl.actions, EN) | dev_alloc(h, &sl.rewards, EN) | dev_alloc(h, &sl.dones, EN) |
+                     dev_alloc(h, &sl.was_reset, E);
+            if (rc) return -1;
+            MAEXP_CUDA(cudaEventCreateWithFlags(&sl.in, cudaEventDisableTiming));
+            MAEXP_CUDA(cudaEventCreateWithFlags(&sl.stepped, cudaEventDisableTiming));
+            MAEXP_CUDA(cudaEventCreateWithFlags(&sl.out, cudaEventDisableTiming));
+        }
+    }
+    maexp_env::HostSlot &sl = h->slots[h->issued % maexp_env::kHostDepth];
+    // the step issued kHostDepth calls ago used this slot: wait until its results reached the host
+    if (h->issued >= (uint64_t)maexp_env::kHostDepth) MAEXP_CUDA(cudaEventSynchronize(sl.out));
+    if (actions_host) {
+        MAEXP_CUDA(cudaMemcpyAsync(sl.actions, actions_host, EN, cudaMemcpyHostToDevice, h->h2d));
+        MAEXP_CUDA(cudaEventRecord(sl.in, h->h2d));
+        MAEXP_CUDA(cudaStreamWaitEvent(stream, sl.in, 0));
+    }
+    maexp_obs_out out;
+    memset(&out, 0, sizeof(out));
+    out.obs = obs_ring_slot;
+    out.rewards = sl.rewards;
+    out.dones = sl.dones;
+    out.was_reset = sl.was_reset;
+    if (launch(h, tick, 0, nullptr, actions_host ? sl.actions : nullptr, nullptr, nullptr, &out, stream)) return -1;
+    MAEXP_CUDA(cudaEventRecord(sl.stepped, stream));
+    MAEXP_CUDA(cudaStreamWaitEvent(h->d2h, sl.stepped, 0));
+    if (rewards_host) MAEXP_CUDA(cudaMemcpyAsync(rewards_host, sl.rewards, EN * sizeof(float), cudaMemcpyDeviceToHost, h->d2h));
+    if (dones_host) MAEXP_CUDA(cudaMemcpyAsync(dones_host, sl.dones, EN, cudaMemcpyDeviceToHost, h->d2h));
+    if (was_reset_host) MAEXP_CUDA(cudaMemcpyAsync(was_reset_host, sl.was_reset, E, cudaMemcpyDeviceToHost, h->d2h));
+    MAEXP_CUDA(cudaEventRecord(sl.out, h->d2h));
+    h->issued += 1;
+    if (ticket) *ticket = h->issued;
+    return 0;
+}
+
+int maexp_env_host_wait(maexp_env *h, uint64_t ticket) {
+    if (!h) return fail("maexp_env_host_wait: null handle");
+    if (!h->h2d || h->issued == 0) return 0;
+    if (ticket > h->issued) return fail("maexp_env_host_wait: unknown ticket");
+    const uint64_t depth = maexp_env::kHostDepth;
+    const uint64_t first = ticket ? ticket : (h->issued > depth ? h->issued - depth + 1 : 1);
+    const uint64_t last = ticket ? ticket : h->issued;
+    for (uint64_t t = first; t <= last; ++t) {
+        if (t + depth <= h->issued) continue;  // its slot was reused, so it was already waited for
+        MAEXP_CUDA(cudaEventSynchronize(h->slots[(t - 1) % depth].out));
+    }
     return 0;
 }
 

@@ -164,6 +164,33 @@ def test_host_buffer_entry_point():
         assert np.array_equal(b.env.view(slot).cpu().numpy(), o["obs"])
 
 
+def test_pipelined_host_entry_point():
+    """maexp_env_step_host_async: 9 steps issued back to back (3 in flight), every step's host results equal the oracle's."""
+    cfg = baseline_config(5).merged_with(max_episode_length=5)
+    E, N, K = 256, 8, 9
+    b = CudaBackend(cfg, E, first_global_env_id=0, auto_reset=True, extras=False)
+    orc = Oracle(cfg, E, auto_reset=True, first_global_env_id=0)
+    b.reset(0), orc.reset(0)
+    rng = np.random.default_rng(5)
+    acts = [torch.from_numpy(rng.integers(0, 4, size=(E, N)).astype(np.int8)).pin_memory() for _ in range(K)]
+    rewards = [torch.empty((E, N), dtype=torch.float32).pin_memory() for _ in range(K)]
+    dones = [torch.empty((E, N), dtype=torch.uint8).pin_memory() for _ in range(K)]
+    was_reset = [torch.empty((E,), dtype=torch.uint8).pin_memory() for _ in range(K)]
+    slots = [b.env.new_slot() for _ in range(K)]
+    tickets = [b.env.step_host_async(acts[k], slots[k], rewards[k], dones[k], was_reset[k], tick=k + 1) for k in range(K)]
+    assert tickets == list(range(1, K + 1))
+    b.env.host_wait(tickets[2])
+    b.env.host_wait()
+    resets = 0
+    for k in range(K):
+        o = orc.step(k + 1, actions=acts[k].numpy())
+        assert np.array_equal(rewards[k].numpy(), o["rewards"]) and np.array_equal(dones[k].numpy(), o["dones"]), k
+        assert np.array_equal(was_reset[k].numpy(), o["was_reset"]), k
+        assert np.array_equal(b.env.view(slots[k]).cpu().numpy(), o["obs"]), k
+        resets += int(was_reset[k].sum())
+    assert resets > 0
+
+
 def test_unsupported_configs_fail_loudly():
     from tests.cuda_backend import make_env
     with pytest.raises(ValueError):

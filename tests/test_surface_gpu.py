@@ -118,3 +118,33 @@ def test_trainer_runs_and_saves_reference_compatible_checkpoints(tmp_path):
     trainer.load_state_dict(str(tmp_path))
     with pytest.raises(ValueError):
         generate_trainer(cfg.merged_with(trainer="nope"), env)
+
+
+def test_trainer_merged_view_da3_end_to_end():
+    """BASELINE cfg4 (MergedDA3 on the merged view): the trainer feeds ring positions to the learner and the actor;
+    the Q-values it acts on equal the torch oracle's on the same observations and positions."""
+    from maexp_b200.core.handlers.trainers import generate_trainer
+    from oracle.torch_learner import TorchLearner
+    from tests.cuda_backend import make_env
+    cfg = baseline_config(4).merged_with(max_episode_length=6, batch_size=16, populate_steps=4 * 32, capacity=32 * 16,
+                                         synchronize_frequency=1)
+    env = make_env(cfg, 32, auto_reset=True)
+    trainer = generate_trainer(cfg, env)
+    assert trainer.env.model_obs_shape == [trainer.env.C, int(cfg.map.SIZE_X), int(cfg.map.SIZE_Y)]
+    before = trainer.learner.params().clone()
+    hist = trainer.run(max_epochs=1)
+    assert np.isfinite(hist[-1]["loss"]) and not torch.equal(trainer.learner.params(), before)
+    ring, e, N = trainer.buffer, trainer.env, trainer.env.N
+    head = ring.head
+    obs_slot, positions = ring.obs[head], ring.positions[head]            # [N,E,slot], [E,N,2]
+    q = trainer.learner.q_values(obs_slot[:, :16].contiguous(), pos=positions[:16].transpose(0, 1).contiguous()).cpu()
+    dense = e.view(obs_slot).cpu()                                        # [E,N,C,V,V]
+    for a in (0, N - 1):
+        o = TorchLearner("da3", trainer.learner.state_dict(a), 4, float(cfg.gamma), 1e-3, 0.99, 1e-8, area_mask="merged",
+                         size=[int(cfg.map.SIZE_X), int(cfg.map.SIZE_Y)], num_heads=int(cfg.model.num_heads))
+        want = o.q_values((dense[:16, a], positions[:16, a].cpu().long()))
+        assert float((q[a] - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-6
+    sd = trainer.learner.state_dict(0)
+    assert tuple(sd["drl_head.weight"].shape)[0] == 4 and "local_blocks.0.attn.qkv.weight" in sd and "relative_conv.conv_post.weight" in sd
+    with pytest.raises(ValueError):  # the noise-free "relative" key is not kept in the ring
+        generate_trainer(cfg.merged_with(observation_noise="flip"), env)
