@@ -21,7 +21,7 @@ extern "C" {
 #endif
 
 #define MAEXP_MAX_AGENTS 16
-#define MAEXP_MAX_TYPES 4
+#define MAEXP_MAX_TYPES 8
 #define MAEXP_MAX_RINGS 4
 
 /* agent_view_method (core/handlers/observations/agents/__init__.py:22-46) */
@@ -34,11 +34,16 @@ enum { MAEXP_MASK_LOCAL = 0, MAEXP_MASK_RELATIVE = 1, MAEXP_MASK_MERGED = 2 };
 enum { MAEXP_NOISE_NONE = 0, MAEXP_NOISE_FLIP = 1, MAEXP_NOISE_DIST = 2, MAEXP_NOISE_THRESHOLD_DIST = 3, MAEXP_NOISE_FLAT = 4 };
 /* environment (core/environments/__init__.py:37-71; shared_reward_environment.py:15-28) */
 enum { MAEXP_REWARD_DEFAULT = 0, MAEXP_REWARD_SHARED_MEAN = 1, MAEXP_REWARD_SHARED_MAX = 2 };
+/* which reward_ind / generate_objects override runs: DefaultEnvironment (default_environment.py:123-132,196-231),
+ * SequentialEnvironment (sequential_environment.py:20-64: picking type t puts type t+1 on the same cell, the last
+ * type respawns one type-0 object; only type 0 is generated at reset), JunctionalEnvironment
+ * (junctional_environment.py:20-71: type 1 -> 3 for agents 2,3 / -> 2 for agents 4,5, type 2 -> 4) */
+enum { MAEXP_ENV_DEFAULT = 0, MAEXP_ENV_SEQUENTIAL = 1, MAEXP_ENV_JUNCTIONAL = 2 };
 
 typedef struct {
     int32_t num_envs;            /* E environments resident on this GPU */
     int32_t num_agents;          /* config.num_agents, N <= 16 */
-    int32_t type_objects;        /* config.type_objects, T <= 4 */
+    int32_t type_objects;        /* config.type_objects, T <= 8 */
     int32_t size_x, size_y;      /* map.SIZE_X / SIZE_Y (Y + V/2 <= 32: grid rows are 32-bit) */
     int32_t visible_range;       /* 5, 7 or 9 */
     int32_t past_step;           /* transition views only */
@@ -59,6 +64,7 @@ typedef struct {
     float flip_noise_range[MAEXP_MAX_RINGS]; /* fp32 0.5/(p-1), flip_observation_noise.py:28 */
     float std_distribution[MAEXP_MAX_RINGS];
     float noise_threshold[MAEXP_MAX_RINGS];  /* fp32(std*ratio), dist_observation_noise.py:60,66 */
+    int32_t env_kind;            /* MAEXP_ENV_* */
 } maexp_env_cfg;
 
 /* Static per-map tables in the REFERENCE's layout, HOST pointers; packed to bit rows and

@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmaexp_b200.so")
 
-MAX_AGENTS, MAX_TYPES, MAX_RINGS = 16, 4, 4
+MAX_AGENTS, MAX_TYPES, MAX_RINGS = 16, 8, 4
 
 
 class MaexpError(RuntimeError):
@@ -27,7 +27,7 @@ class EnvCfg(C.Structure):
         ("init_xys", (C.c_int32 * 2) * MAX_AGENTS), ("task_mask", C.c_int32 * MAX_AGENTS),
         ("task_order", (C.c_int32 * MAX_TYPES) * MAX_AGENTS),
         ("flip_noise_range", C.c_float * MAX_RINGS), ("std_distribution", C.c_float * MAX_RINGS),
-        ("noise_threshold", C.c_float * MAX_RINGS),
+        ("noise_threshold", C.c_float * MAX_RINGS), ("env_kind", C.c_int32),
     ]
 
 

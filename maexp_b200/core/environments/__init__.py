@@ -16,7 +16,7 @@ from .batched import BatchedEnvironment
 logger = initialize_logging(__name__)
 
 __all__ = ["BatchedEnvironment", "DefaultEnvironment", "SharedMeanRewardEnvironment", "SharedMaxRewardEnvironment",
-           "generate_environment"]
+           "SequentialEnvironment", "JunctionalEnvironment", "generate_environment"]
 
 
 class DefaultEnvironment:
@@ -87,6 +87,16 @@ class SharedMaxRewardEnvironment(DefaultEnvironment):
     reward_environment = "shared_max_reward"
 
 
+class SequentialEnvironment(DefaultEnvironment):
+    """sequential_environment.py:20-64: object types are picked up as a chain t -> t+1 on the same cell."""
+    reward_environment = "sequential"
+
+
+class JunctionalEnvironment(DefaultEnvironment):
+    """junctional_environment.py:20-71: the chain forks after type 1 depending on the agent."""
+    reward_environment = "junctional"
+
+
 def generate_environment(config, world):
     if config.environment == "default":
         return DefaultEnvironment(config=config, world=world)
@@ -94,5 +104,9 @@ def generate_environment(config, world):
         return SharedMeanRewardEnvironment(config=config, world=world)
     if config.environment == "shared_max_reward":
         return SharedMaxRewardEnvironment(config=config, world=world)
+    if config.environment == "sequential":
+        return SequentialEnvironment(config=config, world=world)
+    if config.environment == "junctional":
+        return JunctionalEnvironment(config=config, world=world)
     logger.warning(f"Unexpected environment is given. config.environment: {config.environment}")
     raise ValueError()

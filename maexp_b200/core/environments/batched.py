@@ -16,7 +16,8 @@ AGENT_VIEWS = {"default": 0, "simple": 1, "individual": 2, "transition": 3, "ind
 OBJECT_VIEWS = {"default": 0, "simple": 1, "object_types": 2}
 AREA_MASKS = {"local": 0, "relative": 1, "merged": 2}
 NOISES = {False: 0, None: 0, "flip": 1, "sensing_dist": 2, "threshold_sensing_dist": 3, "flat": 4}
-REWARD_MODES = {"default": 0, "shared_mean_reward": 1, "shared_max_reward": 2}
+REWARD_MODES = {"default": 0, "shared_mean_reward": 1, "shared_max_reward": 2, "sequential": 0, "junctional": 0}
+ENV_KINDS = {"sequential": 1, "junctional": 2}  # sequential_environment.py:20, junctional_environment.py:20
 
 
 def noise_constants(config):
@@ -48,6 +49,12 @@ def validate(config, world_map):
         raise ValueError("observation noise with observation_area_mask=relative fails in the reference (appendix C)")
     if len(config.init_xys) < N or len(config.agent_tasks) < N:
         raise ValueError("init_xys / agent_tasks shorter than num_agents")
+    if config.shuffle_init_xys and len(config.init_xys) != N:
+        # default_environment.py:33,97-98 shuffles ALL len(init_xys) entries and uses the first num_agents
+        raise ValueError("shuffle_init_xys with more init_xys than agents is not supported")
+    env_name = config.environment
+    if env_name == "junctional" and T < 5:
+        raise ValueError("environment=junctional places object types 2, 3 and 4 (junctional_environment.py:44-51): type_objects >= 5")
     cells = set()
     for xy in list(config.init_xys)[:N]:
         ix, iy = world_map.coord2ind(xy)
@@ -57,7 +64,7 @@ def validate(config, world_map):
     if len(cells) < N:
         raise ValueError("init_xys must be distinct")
     free = (world_map.wall_matrix == 0)
-    for t in range(T):
+    for t in range(T if env_name not in ("sequential", "junctional") else 1):  # those two only ever sample type 0
         if (world_map.objects_area_matrix[t] * free).sum() < int(config.num_objects) + N:
             # the reference's rejection sampler would never terminate (§E-8)
             raise ValueError(f"objects_area of type {t} cannot hold num_objects={config.num_objects}")
@@ -89,6 +96,7 @@ class BatchedEnvironment:
         cfg.area_mask = AREA_MASKS[config.observation_area_mask]
         cfg.noise = NOISES[config.observation_noise]
         cfg.reward_mode = REWARD_MODES[config.environment]
+        cfg.env_kind = ENV_KINDS.get(config.environment, 0)
         cfg.max_episode_length = int(config.max_episode_length)
         cfg.num_objects = int(config.num_objects)
         cfg.keep_objects_num = int(bool(config.keep_objects_num))

@@ -151,12 +151,123 @@ class FourRectangleMap(AbstractMap):
             w[lo:hi, 13] = 0
 
 
+def _room(w, x0, x1, y0, y1):
+    """Square room outline x0..x1 / y0..y1 (inclusive) with a 3-cell door in the middle of every side."""
+    w[x0:x1 + 1, [y0, y1]] = 1
+    w[[x0, x1], y0:y1 + 1] = 1
+    mx, my = (x0 + x1) // 2, (y0 + y1) // 2
+    w[mx - 1:mx + 2, [y0, y1]] = 0
+    w[[x0, x1], my - 1:my + 2] = 0
+
+
+def _half_planes(X, Y, inside):
+    """[x < X//2, x >= X//2, y < Y//2, y >= Y//2] as masks holding `inside` there and 1 - inside elsewhere."""
+    m = np.full((4, X, Y), 1 - inside, np.int8)
+    m[0, :X // 2, :] = inside
+    m[1, X // 2:, :] = inside
+    m[2, :, :Y // 2] = inside
+    m[3, :, Y // 2:] = inside
+    return m
+
+
+class CentralRoomMap(AbstractMap):
+    """core/maps/central_room_map.py:10-52: one 9x9 room in the middle; only type 0 has an objects area."""
+
+    def locate_walls(self):
+        self._border()
+        _room(self.wall_matrix, 8, 16, 8, 16)
+
+    def set_objects_area(self):
+        if 1 <= self.type_objects <= 5:
+            self.objects_area_matrix[0, 1:24, 1:24] = 1
+            self.objects_area_matrix[0, 8:17, 8:17] = 0
+
+
+class CentralRoomDestinationMap(CentralRoomMap):
+    """core/maps/central_room_destination_map.py:12-22: four half-planes blanked out plus the full map."""
+    RANDOM_DESTINATIONS = True
+
+    def destination_masks(self):
+        return np.concatenate([_half_planes(self.SIZE_X, self.SIZE_Y, 0), np.ones((1, self.SIZE_X, self.SIZE_Y), np.int8)])
+
+
+class CentralRoomLargeMap(AbstractMap):
+    """core/maps/central_room_large_map.py:10-23"""
+
+    def locate_walls(self):
+        self._border()
+        _room(self.wall_matrix, 20, 28, 8, 16)
+
+    def set_objects_area(self):
+        self.objects_area_matrix[0, 1:48, 1:24] = 1
+        self.objects_area_matrix[0, 20:29, 8:17] = 0
+
+
+class CentralRoomLargeDestinationMap(CentralRoomLargeMap):
+    """core/maps/central_room_large_destination_map.py:12-22: the four half-planes themselves."""
+    RANDOM_DESTINATIONS = True
+
+    def destination_masks(self):
+        return _half_planes(self.SIZE_X, self.SIZE_Y, 1)
+
+
+class TwoCentralRoomsMap(AbstractMap):
+    """core/maps/two_central_rooms_map.py:10-69: two rooms, fixed destination areas per agent pair."""
+
+    def locate_walls(self):
+        self._border()
+        _room(self.wall_matrix, 8, 16, 8, 16)
+        _room(self.wall_matrix, 33, 41, 8, 16)
+
+    def set_objects_area(self):
+        a = self.objects_area_matrix
+        if self.type_objects == 1:
+            a[0, 1:24, 1:24] = 1
+            a[0, 8:17, 8:17] = 0
+        elif self.type_objects == 2:
+            a[0, 1:26, 1:13] = 1
+            a[0, 8:17, 8:13] = 0
+            a[0, 24:49, 12:24] = 1
+            a[0, 33:42, 12:17] = 0
+            a[1, 1:26, 12:24] = 1
+            a[1, 8:17, 12:17] = 0
+            a[1, 24:49, 1:13] = 1
+            a[1, 33:42, 8:13] = 0
+
+    def destination_masks(self):
+        """One mask per agent (the step kernel maps agent k to mask min(k, M-1)); agents past the twelfth get zeros."""
+        X, Y = self.SIZE_X, self.SIZE_Y
+        pairs = np.zeros((6, X, Y), np.int8)
+        pairs[0, 1:26, 1:13] = 1
+        pairs[0, 24:49, 12:24] = 1
+        pairs[1, 1:26, 12:24] = 1
+        pairs[1, 24:49, 1:13] = 1
+        pairs[2, 1:49, 1:13] = 1
+        pairs[3, 1:49, 12:24] = 1
+        pairs[4, 1:26, 1:24] = 1
+        pairs[5, 24:49, 1:24] = 1
+        n = min(self.num_agents, 12)
+        masks = [pairs[k // 2] for k in range(n)]
+        if self.num_agents > 12:
+            masks.append(np.zeros((X, Y), np.int8))
+        return np.stack(masks)
+
+    def reset_destination_area(self):
+        m = self.destination_masks()
+        self.destination_area_matrix = np.stack([m[min(k, len(m) - 1)] for k in range(self.num_agents)])
+
+
 _REGISTRY = {
     # name -> (class, fixed size or None for config.map.SIZE_X/SIZE_Y)  core/maps/__init__.py:26-39
     "simple": (SimpleMap, None),
     "four_rooms": (FourRoomsMap, (24, 24)),
     "three_rooms": (ThreeRoomsMap, (25, 25)),
     "four_rectangle": (FourRectangleMap, (40, 24)),
+    "central_room": (CentralRoomMap, (25, 25)),
+    "two_central_rooms": (TwoCentralRoomsMap, (50, 25)),
+    "central_room_destination": (CentralRoomDestinationMap, (25, 25)),
+    "central_room_large": (CentralRoomLargeMap, (49, 25)),
+    "central_room_large_destination": (CentralRoomLargeDestinationMap, (49, 25)),
 }
 
 

@@ -198,7 +198,10 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     const int V = cfg->visible_range, P = cfg->past_step, M = cfg->num_destinations;
     if (E < 1) return fail("maexp_env_create: num_envs < 1");
     if (N < 1 || N > MAEXP_MAX_AGENTS) return fail("maexp_env_create: num_agents must be in 1..16");
-    if (T < 1 || T > MAEXP_MAX_TYPES) return fail("maexp_env_create: type_objects must be in 1..4");
+    if (T < 1 || T > MAEXP_MAX_TYPES) return fail("maexp_env_create: type_objects must be in 1..8");
+    if (cfg->env_kind < MAEXP_ENV_DEFAULT || cfg->env_kind > MAEXP_ENV_JUNCTIONAL) return fail("maexp_env_create: unknown env_kind");
+    if (cfg->env_kind == MAEXP_ENV_JUNCTIONAL && T < 5)
+        return fail("maexp_env_create: the junctional environment places object types 2, 3 and 4 (needs type_objects >= 5)");
     if (X < 3 || X > 255 || Y < 3 || Y + cfg->visible_range / 2 > 32)
         return fail("maexp_env_create: map must satisfy 3<=X<=255, 3<=Y and Y + visible_range/2 <= 32 (32-bit grid rows)");
     if (V != 5 && V != 7 && V != 9) return fail("maexp_env_create: visible_range must be 5, 7 or 9");
@@ -257,6 +260,7 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     p.L = cfg->max_episode_length; p.num_objects = cfg->num_objects; p.keep = cfg->keep_objects_num;
     p.shuffle_init = cfg->shuffle_init_xys; p.auto_reset = cfg->auto_reset; p.random_dest = cfg->random_destinations;
     p.seed = cfg->seed; p.gid0 = cfg->first_global_env_id;
+    p.env_kind = cfg->env_kind;
     for (int i = 0; i < N; ++i) {
         p.init_xy[i] = (uint16_t)(cfg->init_xys[i][0] | (cfg->init_xys[i][1] << 8));
         p.no_task[i] = cfg->task_mask[i] < 0;

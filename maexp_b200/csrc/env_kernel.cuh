@@ -20,7 +20,7 @@ struct EnvParams {
     uint32_t qps_magic;
     int agent_view, object_view, merged, noise, reward_mode, shared_max_is_mean;
     int fast3;  // 3 channels (total agents, all objects, area) and V <= 7: compile-time bit assembly
-    int L, num_objects, keep, shuffle_init, auto_reset, random_dest;
+    int L, num_objects, keep, shuffle_init, auto_reset, random_dest, env_kind;
     uint32_t seed, gid0, tick;
     int force_reset;
     const uint8_t *env_mask;
@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
 #pragma unroll 4
         for (int i = lane; i < nenv * TX; i += 32) {
             const int e = (int)__umulhi((uint32_t)i, p.tx_magic), r = i - e * TX;
-            const int t = (r >= X) + (r >= 2 * X) + (r >= 3 * X);
+            int t = (r >= X) + (r >= 2 * X) + (r >= 3 * X);
+            if (!NSPEC && T > 4) t += (r >= 4 * X) + (r >= 5 * X) + (r >= 6 * X) + (r >= 7 * X);
             s_grid[e * p.gs + R + r + t * 2 * R] = src[i] << R;
         }
     }
@@ -278,7 +279,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             for (int k = 0; k < N; ++k) agrid[mypos[k * EPW] & 0xFF] |= 1u << ((mypos[k * EPW] >> 8) + R);
             attempt = 0;
             nobj = 0;
-            for (int t = 0; t < T; ++t)
+            // sequential_environment.py:21-23 / junctional_environment.py:21-23 only generate type 0
+            const int t_gen = (NSPEC || p.env_kind == MAEXP_ENV_DEFAULT) ? T : 1;
+            for (int t = 0; t < t_gen; ++t)
                 for (int n = 0; n < p.num_objects; ++n) spawn(t, kStreamObjects);
             for (int q = 0; q < P; ++q)  // transition_agent_observation.py:76-79
                 for (int k = 0; k < N; ++k) s_past[(q * N + k) * EPW + lane] = mypos[k * EPW];
@@ -354,7 +357,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                             grid[t * XP + px] &= ~bit;
                             --nobj;
                             ++c_done;
-                            if (p.keep) spawn(t, kStreamRespawn);
+                            if (NSPEC || p.env_kind == MAEXP_ENV_DEFAULT) {
+                                if (p.keep) spawn(t, kStreamRespawn);
+                            } else {
+                                // sequential_environment.py:44-48, junctional_environment.py:44-56: the next object of
+                                // the chain appears on this cell (generate_object_at), the last type respawns a type 0
+                                int next = -1;
+                                bool respawn = false;
+                                if (p.env_kind == MAEXP_ENV_JUNCTIONAL && t == 1) {
+                                    if (i == 2 || i == 3) next = 3;
+                                    if (i == 4 || i == 5) next = 2;
+                                } else if (p.env_kind == MAEXP_ENV_JUNCTIONAL && t == 2) next = 4;
+                                else if (t < T - 1) next = t + 1;
+                                else respawn = p.keep != 0;
+                                if (next >= 0) {
+                                    if (!(grid[next * XP + px] & bit)) ++nobj;
+                                    grid[next * XP + px] |= bit;
+                                    ++c_gen;
+                                }
+                                if (respawn) spawn(0, kStreamRespawn);
+                            }
                         }
                     }
                     if (ca & (1u << i)) { rew_neg |= 1u << i; ++c_ca; }
@@ -632,7 +654,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
 #pragma unroll 4
         for (int i = lane; i < nenv * TX; i += 32) {
             const int e = (int)__umulhi((uint32_t)i, p.tx_magic), r = i - e * TX;
-            const int t = (r >= X) + (r >= 2 * X) + (r >= 3 * X);
+            int t = (r >= X) + (r >= 2 * X) + (r >= 3 * X);
+            if (!NSPEC && T > 4) t += (r >= 4 * X) + (r >= 5 * X) + (r >= 6 * X) + (r >= 7 * X);
             if (s_active[e] & 1) dst[i] = s_grid[e * p.gs + R + r + t * 2 * R] >> R;
         }
     }

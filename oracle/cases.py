@@ -38,4 +38,33 @@ def cases():
     c["shared_max_reference_compat"] = (make_config(environment="shared_max_reward", num_agents=5,
                                                     shuffle_init_xys=False), 60, None,
                                         {"shared_max_is_mean": True})
+    # ---- sequential / junctional environments and the central-room maps
+    xy8 = [[-2, 2], [2, 2], [-2, -2], [2, -2], [0, 2], [0, -2], [2, 0], [-2, 0]]  # configs/experiments/IJCNN2025/exp2
+    c["sequential_central_room_t3"] = (make_config(
+        environment="sequential", map=dict(name="central_room", SIZE_X=25, SIZE_Y=25), type_objects=3, num_objects=60,
+        agent_tasks=["0", "0", "1", "1", "2", "2", "012", "01"], init_xys=xy8, agent_view_method="individual",
+        object_view_method="object_types"), 160, None, {})
+    c["junctional_central_room_t5_merged"] = (make_config(
+        environment="junctional", map=dict(name="central_room", SIZE_X=25, SIZE_Y=25), type_objects=5, num_objects=60,
+        agent_tasks=["0", "0", "12", "12", "13", "13", "4", "4"], init_xys=xy8, agent_view_method="individual",
+        object_view_method="object_types", observation_area_mask="merged"), 160, None, {})
+    c["junctional_chain_tasks"] = (make_config(
+        environment="junctional", map=dict(name="central_room", SIZE_X=25, SIZE_Y=25), type_objects=5, num_objects=80,
+        agent_tasks=["01", "01234", "0123", "012", "0124", "01", "43210", "0"], init_xys=xy8, max_episode_length=90), 200, None, {})
+    c["sequential_no_keep"] = (make_config(
+        environment="sequential", map=dict(name="central_room", SIZE_X=25, SIZE_Y=25), type_objects=2, num_objects=12,
+        keep_objects_num=False, agent_tasks=["01"] * 8, init_xys=xy8, max_episode_length=400), 300, None, {})
+    c["central_room_destination"] = (make_config(
+        map=dict(name="central_room_destination", SIZE_X=25, SIZE_Y=25), num_agents=6, init_xys=xy8[:6], num_objects=60,
+        max_episode_length=30), 100, None, {})
+    c["central_room_large_destination_v9"] = (make_config(
+        map=dict(name="central_room_large_destination", SIZE_X=49, SIZE_Y=25), num_agents=6, init_xys=xy8[:6], num_objects=90,
+        visible_range=9, flip_noise_probabilities=[0.2, 0.1, 0.05, 0.02], max_episode_length=30), 70, None, {})
+    c["central_room_large_sequential"] = (make_config(
+        environment="sequential", map=dict(name="central_room_large", SIZE_X=49, SIZE_Y=25), type_objects=2, num_objects=90,
+        agent_tasks=["0", "1", "01", "10", "0", "1", "01", "10"], init_xys=xy8), 80, None, {})
+    c["two_central_rooms_t2_n12"] = (make_config(
+        map=dict(name="two_central_rooms", SIZE_X=50, SIZE_Y=25), type_objects=2, num_agents=12, num_objects=60,
+        agent_tasks=["0", "0", "1", "1", "01", "01", "10", "10", "0", "1", "01", "-1"],
+        init_xys=xy8 + [[-3, 3], [3, 3], [-3, -3], [3, -3]], object_view_method="object_types"), 80, None, {})
     return c

@@ -135,6 +135,58 @@ static void build_map(orc_env *o) {
         }
         break;
     }
+    /* central_room_map.py:10-52 (every type_objects branch only fills type 0) and central_room_destination_map.py */
+    case ORC_MAP_CENTRAL_ROOM:
+    case ORC_MAP_CENTRAL_ROOM_DESTINATION: {
+        for (int v = 8; v < 17; ++v) { o->wall[v][8] = o->wall[v][16] = 1; o->wall[8][v] = o->wall[16][v] = 1; }
+        for (int v = 11; v < 14; ++v) { o->wall[v][8] = o->wall[v][16] = 0; o->wall[8][v] = o->wall[16][v] = 0; }
+        if (T >= 1 && T <= 5) {
+            area_box(o, 0, 1, 24, 1, 24);
+            for (int x = 8; x < 17; ++x)
+                for (int y = 8; y < 17; ++y) OA(o, 0, x, y) = 0;
+        }
+        break;
+    }
+    /* central_room_large_map.py:10-23 */
+    case ORC_MAP_CENTRAL_ROOM_LARGE:
+    case ORC_MAP_CENTRAL_ROOM_LARGE_DESTINATION: {
+        for (int x = 20; x < 29; ++x) o->wall[x][8] = o->wall[x][16] = 1;
+        for (int y = 8; y < 17; ++y) o->wall[20][y] = o->wall[28][y] = 1;
+        for (int x = 23; x < 26; ++x) o->wall[x][8] = o->wall[x][16] = 0;
+        for (int y = 11; y < 14; ++y) o->wall[20][y] = o->wall[28][y] = 0;
+        area_box(o, 0, 1, 48, 1, 24);
+        for (int x = 20; x < 29; ++x)
+            for (int y = 8; y < 17; ++y) OA(o, 0, x, y) = 0;
+        break;
+    }
+    /* two_central_rooms_map.py:10-46 */
+    case ORC_MAP_TWO_CENTRAL_ROOMS: {
+        for (int v = 8; v < 17; ++v) { o->wall[v][8] = o->wall[v][16] = 1; o->wall[8][v] = o->wall[16][v] = 1; }
+        for (int v = 11; v < 14; ++v) { o->wall[v][8] = o->wall[v][16] = 0; o->wall[8][v] = o->wall[16][v] = 0; }
+        for (int x = 33; x < 42; ++x) o->wall[x][8] = o->wall[x][16] = 1;
+        for (int y = 8; y < 17; ++y) o->wall[33][y] = o->wall[41][y] = 1;
+        for (int x = 36; x < 39; ++x) o->wall[x][8] = o->wall[x][16] = 0;
+        for (int y = 11; y < 14; ++y) o->wall[33][y] = o->wall[41][y] = 0;
+        if (T == 1) {
+            area_box(o, 0, 1, 24, 1, 24);
+            for (int x = 8; x < 17; ++x)
+                for (int y = 8; y < 17; ++y) OA(o, 0, x, y) = 0;
+        } else if (T == 2) {
+            area_box(o, 0, 1, 26, 1, 13);
+            for (int x = 8; x < 17; ++x)
+                for (int y = 8; y < 13; ++y) OA(o, 0, x, y) = 0;
+            area_box(o, 0, 24, 49, 12, 24);
+            for (int x = 33; x < 42; ++x)
+                for (int y = 12; y < 17; ++y) OA(o, 0, x, y) = 0;
+            area_box(o, 1, 1, 26, 12, 24);
+            for (int x = 8; x < 17; ++x)
+                for (int y = 12; y < 17; ++y) OA(o, 1, x, y) = 0;
+            area_box(o, 1, 24, 49, 1, 13);
+            for (int x = 33; x < 42; ++x)
+                for (int y = 8; y < 13; ++y) OA(o, 1, x, y) = 0;
+        }
+        break;
+    }
     default: abort();
     }
 }
@@ -298,6 +350,9 @@ orc_env *orc_create(const orc_cfg *cfg) {
     case ORC_MAP_FOUR_ROOMS: o->X = 24; o->Y = 24; break;
     case ORC_MAP_THREE_ROOMS: o->X = 25; o->Y = 25; break;
     case ORC_MAP_FOUR_RECTANGLE: o->X = 40; o->Y = 24; break;
+    case ORC_MAP_CENTRAL_ROOM: case ORC_MAP_CENTRAL_ROOM_DESTINATION: o->X = 25; o->Y = 25; break;
+    case ORC_MAP_CENTRAL_ROOM_LARGE: case ORC_MAP_CENTRAL_ROOM_LARGE_DESTINATION: o->X = 49; o->Y = 25; break;
+    case ORC_MAP_TWO_CENTRAL_ROOMS: o->X = 50; o->Y = 25; break;
     default: free(o); return NULL;
     }
     o->V = cfg->visible_range;
@@ -396,29 +451,74 @@ static void generate_one_object(orc_env *o, int e, uint32_t tick, uint32_t strea
     }
 }
 
-/* three_rooms_map.py:42-55 (other maps: abstract_map.py:80-81, all ones) */
+/* Candidate list entry m of the maps that redraw destinations at reset, value at (x, y):
+ * three_rooms_map.py:43-51, central_room_destination_map.py:14-18, central_room_large_destination_map.py:14-18 */
+static int dest_candidate(const orc_env *o, int m, int x, int y) {
+    const int X = o->X, Y = o->Y;
+    switch (o->cfg.map_id) {
+    case ORC_MAP_THREE_ROOMS: { /* note: both axes are split at SIZE_X // 2 */
+        const int h = X / 2;
+        if ((m == 0 || m == 1) && x < h) return 0;
+        if ((m == 2 || m == 3) && x >= h) return 0;
+        if ((m == 4 || m == 5) && y < h) return 0;
+        if ((m == 6 || m == 7) && y >= h) return 0;
+        return 1;
+    }
+    case ORC_MAP_CENTRAL_ROOM_DESTINATION:
+        if (m == 0 && x < X / 2) return 0;
+        if (m == 1 && x >= X / 2) return 0;
+        if (m == 2 && y < Y / 2) return 0;
+        if (m == 3 && y >= Y / 2) return 0;
+        return 1;
+    case ORC_MAP_CENTRAL_ROOM_LARGE_DESTINATION:
+        if (m == 0) return x < X / 2;
+        if (m == 1) return x >= X / 2;
+        if (m == 2) return y < Y / 2;
+        return y >= Y / 2;
+    }
+    return 1;
+}
+
+/* two_central_rooms_map.py:48-69: fixed areas for agent pairs; agents past the twelfth keep zeros */
+static int two_central_rooms_destination(int k, int x, int y) {
+    const int in_a = (x >= 1 && x < 26 && y >= 1 && y < 13) || (x >= 24 && x < 49 && y >= 12 && y < 24);
+    const int in_b = (x >= 1 && x < 26 && y >= 12 && y < 24) || (x >= 24 && x < 49 && y >= 1 && y < 13);
+    switch (k / 2) {
+    case 0: return in_a;
+    case 1: return in_b;
+    case 2: return x >= 1 && x < 49 && y >= 1 && y < 13;
+    case 3: return x >= 1 && x < 49 && y >= 12 && y < 24;
+    case 4: return x >= 1 && x < 26 && y >= 1 && y < 24;
+    case 5: return x >= 24 && x < 49 && y >= 1 && y < 24;
+    }
+    return 0;
+}
+
+/* abstract_map.py:80-81 (all ones) and the per-map overrides */
 static void reset_destination_area(orc_env *o, int e, uint32_t tick) {
     env_t *en = &o->envs[e];
     const int N = o->cfg.num_agents, X = o->X, Y = o->Y;
     memset(en->destination, 1, (size_t)N * X * Y);
-    if (o->cfg.map_id != ORC_MAP_THREE_ROOMS) return;
+    if (o->cfg.map_id == ORC_MAP_TWO_CENTRAL_ROOMS) {
+        for (int k = 0; k < N; ++k)
+            for (int x = 0; x < X; ++x)
+                for (int y = 0; y < Y; ++y) DM(o, en, k, x, y) = (int8_t)two_central_rooms_destination(k, x, y);
+        return;
+    }
+    int M = 0;
+    if (o->cfg.map_id == ORC_MAP_THREE_ROOMS) M = 9;
+    else if (o->cfg.map_id == ORC_MAP_CENTRAL_ROOM_DESTINATION) M = 5;
+    else if (o->cfg.map_id == ORC_MAP_CENTRAL_ROOM_LARGE_DESTINATION) M = 4;
+    if (!M) return;
     int32_t perm[9];
-    for (int i = 0; i < 9; ++i) perm[i] = i;
+    for (int i = 0; i < M; ++i) perm[i] = i;
     uint32_t d = 0;
-    tape_shuffle(o, e, tick, MAEXP_STREAM_DEST, &d, perm, 9);
-    const int h = X / 2;
-    for (int k = 0; k < N; ++k) {
-        const uint32_t pick = maexp_scale(maexp_draw(o->cfg.seed, genv(o, e), tick, MAEXP_STREAM_DEST, d++, 0), 9u);
+    tape_shuffle(o, e, tick, MAEXP_STREAM_DEST, &d, perm, M); /* random.shuffle(destination_area) */
+    for (int k = 0; k < N; ++k) {                             /* random.choice(destination_area) per agent */
+        const uint32_t pick = maexp_scale(maexp_draw(o->cfg.seed, genv(o, e), tick, MAEXP_STREAM_DEST, d++, 0), (uint32_t)M);
         const int m = perm[pick];
         for (int x = 0; x < X; ++x)
-            for (int y = 0; y < Y; ++y) {
-                int v = 1;
-                if ((m == 0 || m == 1) && x < h) v = 0;
-                if ((m == 2 || m == 3) && x >= h) v = 0;
-                if ((m == 4 || m == 5) && y < h) v = 0;
-                if ((m == 6 || m == 7) && y >= h) v = 0;
-                DM(o, en, k, x, y) = (int8_t)v;
-            }
+            for (int y = 0; y < Y; ++y) DM(o, en, k, x, y) = (int8_t)dest_candidate(o, m, x, y);
     }
 }
 
@@ -631,8 +731,8 @@ static void reset_one(orc_env *o, int e, uint32_t tick, const orc_out *out) {
         coord2ind(o, en->xy[i], &ix, &iy);
         AM(o, en, i, ix, iy) = 1;
     }
-    uint32_t attempt = 0; /* :112, :123-132 */
-    for (int t = 0; t < T; ++t)
+    uint32_t attempt = 0; /* :112, :123-132; sequential_environment.py:21-23 / junctional_environment.py:21-23: type 0 only */
+    for (int t = 0; t < (o->cfg.env_kind == ORC_ENV_DEFAULT ? T : 1); ++t)
         for (int n = 0; n < o->cfg.num_objects; ++n)
             generate_one_object(o, e, tick, MAEXP_STREAM_OBJECTS, &attempt, t);
     /* observation_handler.py:136-144 */
@@ -718,7 +818,25 @@ static void step_one(orc_env *o, int e, uint32_t tick, const int8_t *actions, co
                     reward = 1.0f;
                     OM(o, en, t, ax, ay) = 0;
                     en->counters[1] += 1;
-                    if (o->cfg.keep_objects_num) generate_one_object(o, e, tick, MAEXP_STREAM_RESPAWN, &attempt, t);
+                    if (o->cfg.env_kind == ORC_ENV_DEFAULT) {
+                        if (o->cfg.keep_objects_num) generate_one_object(o, e, tick, MAEXP_STREAM_RESPAWN, &attempt, t);
+                    } else {
+                        /* sequential_environment.py:44-48, junctional_environment.py:44-56: the next object of the
+                         * chain appears on the same cell (default_environment.py:118-121), the last one respawns type 0 */
+                        int next = -1, respawn = 0;
+                        if (o->cfg.env_kind == ORC_ENV_JUNCTIONAL && t == 1) {
+                            if (i == 2 || i == 3) next = 3;
+                            if (i == 4 || i == 5) next = 2;
+                        } else if (o->cfg.env_kind == ORC_ENV_JUNCTIONAL && t == 2) next = 4;
+                        else if (t < T - 1) next = t + 1;
+                        else if (t == T - 1) respawn = o->cfg.keep_objects_num;
+                        if (next >= 0) {
+                            if (next >= T) abort(); /* IndexError in the reference */
+                            OM(o, en, next, ax, ay) = 1;
+                            en->counters[0] += 1;
+                        }
+                        if (respawn) generate_one_object(o, e, tick, MAEXP_STREAM_RESPAWN, &attempt, 0);
+                    }
                 }
             }
             if (en->collide_agents[i]) { reward = -1.0f; en->collide_agents[i] = 0; en->counters[2] += 1; }

@@ -17,7 +17,11 @@
 extern "C" {
 #endif
 
-enum { ORC_MAP_SIMPLE = 0, ORC_MAP_FOUR_ROOMS = 1, ORC_MAP_THREE_ROOMS = 2, ORC_MAP_FOUR_RECTANGLE = 3 };
+enum { ORC_MAP_SIMPLE = 0, ORC_MAP_FOUR_ROOMS = 1, ORC_MAP_THREE_ROOMS = 2, ORC_MAP_FOUR_RECTANGLE = 3,
+       ORC_MAP_CENTRAL_ROOM = 4, ORC_MAP_CENTRAL_ROOM_DESTINATION = 5, ORC_MAP_CENTRAL_ROOM_LARGE = 6,
+       ORC_MAP_CENTRAL_ROOM_LARGE_DESTINATION = 7, ORC_MAP_TWO_CENTRAL_ROOMS = 8 };
+/* core/environments/__init__.py:40-71: which reward_ind / generate_objects override runs */
+enum { ORC_ENV_DEFAULT = 0, ORC_ENV_SEQUENTIAL = 1, ORC_ENV_JUNCTIONAL = 2 };
 enum { ORC_AV_DEFAULT = 0, ORC_AV_SIMPLE = 1, ORC_AV_INDIVIDUAL = 2, ORC_AV_TRANSITION = 3, ORC_AV_INDIVIDUAL_TRANSITION = 4 };
 enum { ORC_OV_DEFAULT = 0, ORC_OV_SIMPLE = 1, ORC_OV_TYPES = 2 };
 enum { ORC_MASK_LOCAL = 0, ORC_MASK_RELATIVE = 1, ORC_MASK_MERGED = 2 };
@@ -25,7 +29,7 @@ enum { ORC_NOISE_NONE = 0, ORC_NOISE_FLIP = 1, ORC_NOISE_DIST = 2, ORC_NOISE_THR
 enum { ORC_REWARD_DEFAULT = 0, ORC_REWARD_SHARED_MEAN = 1, ORC_REWARD_SHARED_MAX = 2 };
 
 #define ORC_MAX_AGENTS 16
-#define ORC_MAX_TYPES 4
+#define ORC_MAX_TYPES 8
 #define ORC_MAX_RINGS 4
 
 typedef struct {
@@ -52,6 +56,7 @@ typedef struct {
     float flip_noise_range[ORC_MAX_RINGS]; /* fp32 0.5/(p-1), flip_observation_noise.py:28 */
     float std_distribution[ORC_MAX_RINGS];
     float noise_threshold[ORC_MAX_RINGS];  /* fp32(std*ratio), dist_observation_noise.py:60-66 */
+    int32_t env_kind;              /* ORC_ENV_* */
 } orc_cfg;
 
 typedef struct orc_env orc_env;

@@ -16,13 +16,15 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-MAX_AGENTS, MAX_TYPES, MAX_RINGS = 16, 4, 4
-MAPS = {"simple": 0, "four_rooms": 1, "three_rooms": 2, "four_rectangle": 3}
+MAX_AGENTS, MAX_TYPES, MAX_RINGS = 16, 8, 4
+MAPS = {"simple": 0, "four_rooms": 1, "three_rooms": 2, "four_rectangle": 3, "central_room": 4,
+        "central_room_destination": 5, "central_room_large": 6, "central_room_large_destination": 7, "two_central_rooms": 8}
 AGENT_VIEWS = {"default": 0, "simple": 1, "individual": 2, "transition": 3, "individual_transition": 4}
 OBJECT_VIEWS = {"default": 0, "simple": 1, "object_types": 2}
 MASKS = {"local": 0, "relative": 1, "merged": 2}
 NOISES = {False: 0, None: 0, "flip": 1, "sensing_dist": 2, "threshold_sensing_dist": 3, "flat": 4}
-REWARDS = {"default": 0, "shared_mean_reward": 1, "shared_max_reward": 2}
+REWARDS = {"default": 0, "shared_mean_reward": 1, "shared_max_reward": 2, "sequential": 0, "junctional": 0}
+ENV_KINDS = {"sequential": 1, "junctional": 2}
 COORD_KEYS = ("obs_x_min", "obs_x_max", "obs_y_min", "obs_y_max", "area_x_min", "area_x_max", "area_y_min",
               "area_y_max", "map_x_min", "map_x_max", "map_y_min", "map_y_max")
 
@@ -38,7 +40,7 @@ class OrcCfg(C.Structure):
         ("first_global_env_id", C.c_uint32), ("init_xys", (C.c_int32 * 2) * MAX_AGENTS),
         ("task_mask", C.c_int32 * MAX_AGENTS), ("task_order", (C.c_int32 * MAX_TYPES) * MAX_AGENTS),
         ("flip_noise_range", C.c_float * MAX_RINGS), ("std_distribution", C.c_float * MAX_RINGS),
-        ("noise_threshold", C.c_float * MAX_RINGS),
+        ("noise_threshold", C.c_float * MAX_RINGS), ("env_kind", C.c_int32),
     ]
 
 
@@ -124,6 +126,7 @@ def make_cfg(cfg, num_envs=1, auto_reset=False, first_global_env_id=0, shared_ma
     c.area_mask = MASKS[_get(cfg, "observation_area_mask")]
     c.noise = NOISES[_get(cfg, "observation_noise")]
     c.reward_mode = REWARDS[_get(cfg, "environment")]
+    c.env_kind = ENV_KINDS.get(_get(cfg, "environment"), 0)
     c.transparent_observation = int(bool(_get(cfg, "transparent_observation")))
     c.max_episode_length = int(_get(cfg, "max_episode_length"))
     c.num_objects = int(_get(cfg, "num_objects"))

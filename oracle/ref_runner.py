@@ -171,6 +171,8 @@ class RefEnv:
         _import_reference()
         with contextlib.redirect_stderr(io.StringIO()):  # tqdm bar of the mask generator
             import core.environments.default_environment as de
+            import core.maps.central_room_destination_map as crd
+            import core.maps.central_room_large_destination_map as crld
             import core.maps.three_rooms_map as trm
             from core.environments import generate_environment
             from core.environments.default_environment import DefaultEnvironment
@@ -183,7 +185,7 @@ class RefEnv:
             self.seed = int(self.cfg.seed) & 0xFFFFFFFF
             self.env_id = env_id
             self.env_tape, self.map_tape = EnvTape(self.seed, env_id), MapTape(self.seed, env_id)
-            self._mods = (de, trm)
+            self._mods = (de, trm, crd, crld)
             self._noise_mods = (flip_observation_noise, dist_observation_noise, flat_observation_noise)
             self._proxy = TorchProxy(self)
             self._field = None
@@ -212,15 +214,19 @@ class RefEnv:
 
     @contextlib.contextmanager
     def _patched(self):
-        de, trm = self._mods
-        saved = (de.random, trm.random, [m.torch for m in self._noise_mods])
-        de.random, trm.random = self.env_tape, self.map_tape
+        de, map_mods = self._mods[0], self._mods[1:]
+        saved = (de.random, [m.random for m in map_mods], [m.torch for m in self._noise_mods])
+        de.random = self.env_tape
+        for m in map_mods:  # three_rooms_map.py:52-55 and the central_room*_destination maps draw from `random`
+            m.random = self.map_tape
         for m in self._noise_mods:
             m.torch = self._proxy
         try:
             yield
         finally:
-            de.random, trm.random = saved[0], saved[1]
+            de.random = saved[0]
+            for m, r in zip(map_mods, saved[1]):
+                m.random = r
             for m, t in zip(self._noise_mods, saved[2]):
                 m.torch = t
 

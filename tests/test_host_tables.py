@@ -72,3 +72,21 @@ def test_product_path_has_no_oracle_import():
             if f.endswith(".py"):
                 src = open(os.path.join(base, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(base, f)
+
+
+@pytest.mark.parametrize("name,X,Y", [("central_room", 25, 25), ("central_room_destination", 25, 25),
+                                      ("central_room_large", 49, 25), ("central_room_large_destination", 49, 25),
+                                      ("two_central_rooms", 50, 25)])
+@pytest.mark.parametrize("V", [5, 7, 9])
+def test_central_room_maps_match_oracle(name, X, Y, V):
+    """SURVEY.md 8(f)-1 maps: walls, object areas and line-of-sight tables equal the C oracle's (which the
+    fixtures pin against the live reference)."""
+    for T in (1, 2, 5):
+        cfg = make_config(map=dict(name=name, SIZE_X=X, SIZE_Y=Y), visible_range=V, type_objects=T,
+                          flip_noise_probabilities=[0.2, 0.1, 0.05, 0.02])
+        world = generate_world(cfg, generate_map(cfg))
+        assert (world.map.SIZE_X, world.map.SIZE_Y) == (X, Y)
+        wall, area, los = Oracle(cfg, 1).tables()
+        assert np.array_equal(world.map.wall_matrix, wall)
+        assert np.array_equal(world.map.objects_area_matrix, area)
+        assert np.array_equal(generate_observation_area_mask(cfg, world), los)
