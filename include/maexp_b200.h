@@ -192,7 +192,10 @@ enum {
     MAEXP_LEARNER_QR = 2,           /* qr_dqn_brain.py:81-119, customs/qr_dqn.py:20-65 */
     MAEXP_LEARNER_DQN_MLP = 3,      /* model mlp on the flattened observation (mlp.py:14-34) */
     MAEXP_LEARNER_IQN = 4,          /* iqn_brain.py:60-115, customs/iqn.py:21-162 (num_atoms = model.num_quantiles) */
-    MAEXP_LEARNER_DA3 = 5           /* brain da3 + model da3, local view: da3_brain.py:58-89, customs/da3.py:22-96, vit.py */
+    MAEXP_LEARNER_DA3 = 5,          /* brain da3 + model da3, local view: da3_brain.py:58-89, customs/da3.py:22-96, vit.py */
+    MAEXP_LEARNER_DA6 = 6           /* brain da6 + model da6 (merged view): da6_brain.py:44-75, customs/da6.py:22-126 — a relative
+                                       transformer on the area canvas (patch_size = model.relative_patch_size) feeds token 0 of the
+                                       local transformer (local_patch_size) */
 };
 enum { MAEXP_BUF_ONLINE = 0, MAEXP_BUF_TARGET = 1, MAEXP_BUF_GRADS = 2, MAEXP_BUF_SQUARE_AVG = 3, MAEXP_BUF_SUPPORT = 4 };
 
@@ -215,7 +218,9 @@ typedef struct {
     int32_t area_mask;        /* MAEXP_MASK_*: relative (conv_mlp on the decoded [C,X,Y] canvas, conv_mlp.py:56-66) and merged
                                  (MergedConvMLP conv_mlp.py:69-108, MergedDA3 da3.py:99-225) need the observing agents' positions */
     int32_t size_x, size_y;   /* map size for the relative canvas */
-    int32_t patch_size;       /* DA3 model.patch_size (only sizes the parent's unused parameters of MergedDA3) */
+    int32_t patch_size;       /* DA3 model.patch_size (only sizes the parent's unused parameters of MergedDA3);
+                                 DA6: model.relative_patch_size */
+    int32_t local_patch_size; /* DA6: model.local_patch_size (0 = 1) */
 } maexp_learner_cfg;
 
 typedef struct maexp_learner maexp_learner;

@@ -55,10 +55,10 @@ class LearnerCfg(C.Structure):
                [(n, C.c_float) for n in ("gamma", "v_min", "v_max", "delta_z", "learning_rate", "alpha",
                                           "one_minus_alpha", "eps", "max_norm")] + \
                [(n, C.c_int32) for n in ("num_quantiles_dash", "num_cosines", "embed_dim", "num_heads", "mlp_hidden",
-                                          "block_loop", "area_mask", "size_x", "size_y", "patch_size")]
+                                          "block_loop", "area_mask", "size_x", "size_y", "patch_size", "local_patch_size")]
 
 
-LEARNER_KINDS = {"dqn_conv_mlp": 0, "c51": 1, "qr": 2, "dqn_mlp": 3, "iqn": 4, "da3": 5}
+LEARNER_KINDS = {"dqn_conv_mlp": 0, "c51": 1, "qr": 2, "dqn_mlp": 3, "iqn": 4, "da3": 5, "da6": 6}
 BUF_ONLINE, BUF_TARGET, BUF_GRADS, BUF_SQUARE_AVG, BUF_SUPPORT = range(5)
 
 # every symbol include/maexp_b200.h declares: name -> (restype, argtypes)

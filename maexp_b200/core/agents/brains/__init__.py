@@ -16,7 +16,7 @@ logger = initialize_logging(__name__)
 
 # brain name -> (learner kind for conv models, clip max_norm)      brains/*.py
 _BRAINS = {"dqn": ("dqn_conv_mlp", 0.1), "da3_baseline": ("dqn_conv_mlp", 0.1), "categorical_dqn": ("c51", 10.0),
-           "qr_dqn": ("qr", 0.1), "iqn": ("iqn", 0.1), "da3": ("da3", 0.1)}
+           "qr_dqn": ("qr", 0.1), "iqn": ("iqn", 0.1), "da3": ("da3", 0.1), "da6": ("da6", 0.1)}
 
 
 def learner_kind(config):
@@ -28,6 +28,12 @@ def learner_kind(config):
         if kind != "dqn_conv_mlp":
             raise ValueError("model=mlp is only defined for the dqn brain")
         kind = "dqn_mlp"
+    elif config.model.name == "da6" or kind == "da6":
+        if kind != "da6" or config.model.name != "da6":
+            raise ValueError("brain=da6 and model=da6 go together (da6_brain.py, customs/da6.py)")
+        if config.observation_area_mask != "merged" or config.model.get("attention") == "hard" or \
+                config.get("objects_channel") or config.get("agents_channel"):
+            raise ValueError("DA6 is implemented for the merged view, soft attention, without objects / agents channels")
     elif config.model.name == "da3" or kind == "da3":
         if kind != "da3" or config.model.name != "da3":
             raise ValueError("brain=da3 and model=da3 go together (da3_brain.py, customs/da3.py)")
@@ -37,8 +43,8 @@ def learner_kind(config):
     elif config.model.name not in ("conv_mlp", "da3_baseline", "categorical_dqn", "qr_dqn", "iqn"):
         logger.warning(f"Unexpected network is given. config.model.name: {config.model.name}")
         raise ValueError()
-    if config.observation_area_mask != "local" and kind not in ("dqn_conv_mlp", "da3"):
-        raise ValueError("relative / merged views are implemented for the conv_mlp DQN and the merged DA3")
+    if config.observation_area_mask != "local" and kind not in ("dqn_conv_mlp", "da3", "da6"):
+        raise ValueError("relative / merged views are implemented for the conv_mlp DQN, the merged DA3 and DA6")
     if config.observation_area_mask == "merged" and config.observation_noise:
         # the merged models read the area channel of the NOISE-FREE "relative" key (merged_observtion_handler.py:26-29);
         # the replay ring keeps only the noisy crop, so this combination is refused rather than approximated
@@ -71,8 +77,11 @@ class LearnerGroup:
         cfg.area_mask = AREA_MASKS[self.area_mask]
         cfg.size_x, cfg.size_y = int(config.map.SIZE_X), int(config.map.SIZE_Y)
         cfg.patch_size = int(m.get("patch_size") or 1)
-        cfg.hidden = int(m.hidden_layer_sizes[0]) if (self.kind != "da3" or self.area_mask == "merged") else 0
-        if self.kind == "da3":
+        cfg.hidden = 0 if self.kind == "da6" or (self.kind == "da3" and self.area_mask != "merged") else \
+            int(m.hidden_layer_sizes[0])
+        if self.kind == "da6":
+            cfg.patch_size, cfg.local_patch_size = int(m.relative_patch_size), int(m.local_patch_size)
+        if self.kind in ("da3", "da6"):
             cfg.embed_dim, cfg.num_heads, cfg.block_loop = int(m.embed_dim), int(m.num_heads), int(m.block_loop)
             cfg.mlp_hidden = int(int(m.embed_dim) * float(m.mlp_ratio))
         cfg.conv1_channels = int(m.get("hidden_channels", [32])[0])

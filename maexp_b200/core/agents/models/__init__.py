@@ -144,6 +144,25 @@ class _MergedDA3(_DA3):
         self.drl_head = nn.Linear(int(m.embed_dim) + d, act_size)
 
 
+class _DA6(nn.Module):
+    """Parameter layout and construction order of customs/da6.py:22-96 (objects_channel / agents_channel off)."""
+
+    def __init__(self, config, obs_shape, act_size):
+        super().__init__()
+        m, v, e = config.model, int(config.visible_range), int(config.model.embed_dim)
+        rp, lp = int(m.relative_patch_size), int(m.local_patch_size)
+        self.relative_patch_embed = _PatchEmbed(rp, 1, e)
+        self.local_patch_embed = _PatchEmbed(lp, int(obs_shape[0]), e)
+        self.saliency_vector = nn.Parameter(torch.zeros(1, 1, e))
+        self.relative_pos_embed = nn.Parameter(torch.zeros(1, (int(obs_shape[1]) // rp) * (int(obs_shape[2]) // rp) + 1, e))
+        self.local_pos_embed = nn.Parameter(torch.zeros(1, (v // lp) * (v // lp) + 1, e))
+        self.relative_blocks = nn.ModuleList([_Block(e, float(m.mlp_ratio)) for _ in range(int(m.block_loop))])
+        self.local_blocks = nn.ModuleList([_Block(e, float(m.mlp_ratio)) for _ in range(int(m.block_loop))])
+        self.norm = nn.LayerNorm(e)
+        self.fc1 = nn.Linear(e, e)
+        self.drl_head = nn.Linear(e, act_size)
+
+
 def build_reference_modules(config, obs_shape, act_size):
     name = config.model.name
     if name == "mlp":  # SURVEY.md appendix E-2: the flattened observation feeds the MLP
@@ -160,6 +179,8 @@ def build_reference_modules(config, obs_shape, act_size):
         return _ConvHeads(config, obs_shape, [("fc_V", z), ("fc_A", act_size * z)])
     if name == "iqn":
         return _IQN(config, obs_shape, act_size)
+    if name == "da6":
+        return _DA6(config, obs_shape, act_size)
     if name == "da3":
         if config.observation_area_mask == "merged":
             return _MergedDA3(config, obs_shape, act_size)

@@ -642,29 +642,36 @@ __global__ void iqn_q_kernel(const float *v, const float *adv, int B, int A, int
 
 
 // ------------------------------------------------------------------------------ DA3 (ViT) pieces
-// patches[g][(b,pos)][c] = obs[g][b][c*VV + pos]   (PatchEmbed with patch_size 1 is a per-pixel linear map, vit.py:34-47)
-__global__ void da3_patch_gather_kernel(const float *obs, float *patches, int B, int C, int VV, long long stride,
-                                        long long gObs, long long gP) {
+// PatchEmbed (vit.py:34-47) is a stride-ps convolution: gather its im2col rows
+// patches[g][(b,tx,ty)][(c,i,j)] = src[g][b*sb + c*sc + (tx*ps+i)*Win + (ty*ps+j)], tokens ordered tx*Wt + ty (flatten(2))
+__global__ void vit_patch_gather_kernel(const float *src, float *patches, int B, int Cin, int Ht, int Wt, int Win, int ps,
+                                        long long sb, long long sc, long long gSrc, long long gP) {
     const int g = blockIdx.y;
-    const long long total = (long long)B * VV * C;
+    const int K = Cin * ps * ps, nt = Ht * Wt;
+    const long long total = (long long)B * nt * K;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const int pos = (int)((i / C) % VV);
-        const long long b = i / ((long long)C * VV);
-        patches[(size_t)g * gP + i] = obs[(size_t)g * gObs + b * stride + (long long)c * VV + pos];
+        const int k = (int)(i % K);
+        const int t = (int)((i / K) % nt);
+        const long long b = i / ((long long)K * nt);
+        const int c = k / (ps * ps), ij = k - c * ps * ps, pi = ij / ps, pj = ij - pi * ps;
+        const int tx = t / Wt, ty = t - tx * Wt;
+        patches[(size_t)g * gP + i] = src[(size_t)g * gSrc + b * sb + (long long)c * sc + (long long)(tx * ps + pi) * Win + (ty * ps + pj)];
     }
 }
 
-// x0[b][t] = (t == 0 ? saliency_vector : tok[b][t-1]) + pos_embed[t]     (da3.py:77-83)
-__global__ void da3_tokens_kernel(const float *tok, const float *sal, const float *pos, float *x0, int B, int Tn, int E,
-                                  long long gTok, long long gX, long long P) {
+// x0[b][t] = (t == 0 ? token0 : tok[b][t-1]) + pos_embed[t]     (da3.py:77-83); token0 is the saliency_vector parameter,
+// or, for DA6's local stage, a per-sample vector tok0_ext [B][E] (da6.py:113-116)
+__global__ void da3_tokens_kernel(const float *tok, const float *sal, const float *tok0_ext, const float *pos, float *x0, int B,
+                                  int Tn, int E, long long gTok, long long gX, long long gT0, long long P) {
     const int g = blockIdx.y;
     const long long total = (long long)B * Tn * E;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int d = (int)(i % E);
         const int t = (int)((i / E) % Tn);
         const long long b = i / ((long long)E * Tn);
-        const float base = t == 0 ? sal[(size_t)g * P + d] : tok[(size_t)g * gTok + (b * (Tn - 1) + (t - 1)) * E + d];
+        float base;
+        if (t == 0) base = tok0_ext ? tok0_ext[(size_t)g * gT0 + b * E + d] : sal[(size_t)g * P + d];
+        else base = tok[(size_t)g * gTok + (b * (Tn - 1) + (t - 1)) * E + d];
         x0[(size_t)g * gX + i] = __fadd_rn(base, pos[(size_t)g * P + (size_t)t * E + d]);
     }
 }
@@ -927,11 +934,10 @@ struct maexp_learner {
     maexp_learner_cfg cfg;
     int G, B, C, V, A, H, F1, F2, Z, D;  // D = flattened conv output (or C*V*V for the plain MLP)
     int H1, Hp, H2;                      // conv1 out side, pooled side, conv2 out side
-    bool has_conv, dist, iqn, da3;
-    int E_, heads_, Fm, L_, Tn;   // DA3: embed_dim, num_heads, mlp hidden, block_loop, tokens
-    long long o_sal, o_pos, o_pew, o_peb, o_nfw, o_nfb, o_hw, o_hb;
+    bool has_conv, dist, iqn, da3, da6 = false;
+    int E_, heads_, Fm, L_, Tn;   // DA3 / DA6: embed_dim, num_heads, mlp hidden, block_loop, max tokens of any stack
+    long long o_nfw, o_nfb, o_hw, o_hb, o_f1w = 0, o_f1b = 0;  // shared final norm, drl_head, DA6 fc1
     struct BlockLayout { long long n1w, n1b, qkvw, projw, projb, n2w, n2b, f1w, f1b, f2w, f2b; };
-    std::vector<BlockLayout> blocks;
     int Nq, Nd, ncos, rows_max;  // IQN: quantiles, target quantiles, cosines, B * max(Nq, Nd)
     HeadLayout se;               // IQN state_embedder (customs/iqn.py:51-53)
     long long o_cw, o_cb;        // IQN cosine_net.net.0
@@ -952,7 +958,15 @@ struct maexp_learner {
     } iq[3];
     float *d_e = nullptr, *d_phi = nullptr, *d_psi = nullptr, *d_hrow = nullptr;
     struct Da3Block { float *n1, *m1, *r1, *qkv, *probs, *ao, *x1, *n2, *m2, *r2, *f1, *g1, *x2; };
-    struct Da3Acts { float *patches, *tok, *x0, *nf, *mf, *rf, *q; std::vector<Da3Block> blk; } da[3];
+    struct Da3Acts { float *patches, *tok, *x0, *nf, *mf, *rf, *q; std::vector<Da3Block> blk; };
+    // one transformer stack: patch embedding of a [Cin, Hin, Win] image, token 0, pre-LN blocks (vit.py)
+    struct VitStack {
+        int Cin = 0, Hin = 0, Win = 0, ps = 1, Ht = 0, Wt = 0, Tn = 0, K = 0;  // Tn = Ht*Wt + 1 tokens, K = Cin*ps*ps
+        long long o_sal = -1, o_pos = 0, o_pew = 0, o_peb = 0;
+        std::vector<BlockLayout> blocks;
+        Da3Acts a[3];
+    } vloc, vrel;  // local crop (DA3, MergedDA3, DA6) and relative canvas (DA6)
+    float *sal2[3] = {nullptr, nullptr, nullptr}, *d_sal2 = nullptr;  // DA6: fc1(LN(relative token 0)) and its gradient
     // generalized conv trunks (rectangular input, any source): relative / merged models
     struct GTrunk {
         int Cin, Hin, Win, H1, W1, Hp, Wp, H2, W2, D;
@@ -1025,8 +1039,8 @@ void gemm(cudaStream_t st, int G, const float *A, const float *Bm, float *C, con
 
 // bias gradient: column sums as ones[1,M] x dY[M,N] through the split-K GEMM (fixed order)
 void colsum(cudaStream_t st, int G, const float *ones, const float *X, float *out, int M, int N, long long gX,
-            long long gOut) {
-    gemm(st, G, ones, X, out, nullptr, 1, N, M, 0, 0, N, 1, N, 1, 0, gX, gOut, 0);
+            long long gOut, int accumulate = 0) {
+    gemm(st, G, ones, X, out, nullptr, 1, N, M, 0, 0, N, 1, N, 1, 0, gX, gOut, 0, 0, accumulate);
 }
 
 // ---- conv trunk: obs [G][B][obs_stride] -> a.flat [G][Bmax][D]
@@ -1174,21 +1188,22 @@ inline void ln_fwd(maexp_learner *h, cudaStream_t st, const float *params, const
                                                                               h->E_, gX, rows_max * h->E_, rows_max, h->P);
 }
 
-void da3_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, int pass,
-                 bool with_head = true) {
-    maexp_learner::Da3Acts &a = h->da[pass];
-    const int G = h->G, C = h->C, VV = h->V * h->V, E = h->E_, Tn = h->Tn, Fm = h->Fm;
-    const long long P = h->P, Bmax = h->B, Rm = Bmax * Tn, R49 = Bmax * (Tn - 1);
-    const int rows = B * Tn, rows49 = B * (Tn - 1);
-    da3_patch_gather_kernel<<<grid1d((long long)rows49 * C, G), 256, 0, st>>>(obs, a.patches, B, C, VV, h->cfg.obs_stride,
-                                                                              (long long)B * h->cfg.obs_stride, R49 * C);
-    gemm(st, G, a.patches, params + h->o_pew, a.tok, params + h->o_peb, rows49, E, C, C, 1, 1, C, E, 1, R49 * C, P, R49 * E, P);
-    da3_tokens_kernel<<<grid1d((long long)rows * E, G), 256, 0, st>>>(a.tok, params + h->o_sal, params + h->o_pos, a.x0, B, Tn, E,
-                                                                      R49 * E, Rm * E, P);
+// one stack: src image [g][b*sb + c*sc + x*Win + y] -> s.a[pass].nf = LN(last block output)[:, 0]
+void vit_forward(maexp_learner *h, cudaStream_t st, const float *params, maexp_learner::VitStack &s, const float *src,
+                 long long sb, long long sc, long long gSrc, int B, int pass, const float *tok0_ext) {
+    maexp_learner::Da3Acts &a = s.a[pass];
+    const int G = h->G, E = h->E_, Tn = s.Tn, Fm = h->Fm, K = s.K;
+    const long long P = h->P, Bmax = h->B, Rm = Bmax * Tn, Rt = Bmax * (Tn - 1);
+    const int rows = B * Tn, rowst = B * (Tn - 1);
+    vit_patch_gather_kernel<<<grid1d((long long)rowst * K, G), 256, 0, st>>>(src, a.patches, B, s.Cin, s.Ht, s.Wt, s.Win, s.ps, sb,
+                                                                             sc, gSrc, Rt * K);
+    gemm(st, G, a.patches, params + s.o_pew, a.tok, params + s.o_peb, rowst, E, K, K, 1, 1, K, E, 1, Rt * K, P, Rt * E, P);
+    da3_tokens_kernel<<<grid1d((long long)rows * E, G), 256, 0, st>>>(a.tok, tok0_ext ? nullptr : params + s.o_sal, tok0_ext,
+                                                                      params + s.o_pos, a.x0, B, Tn, E, Rt * E, Rm * E, Bmax * E, P);
     const float *x = a.x0;
     const float scale = 1.0f / sqrtf((float)(E / h->heads_));
     for (int l = 0; l < h->L_; ++l) {
-        const maexp_learner::BlockLayout &w = h->blocks[l];
+        const maexp_learner::BlockLayout &w = s.blocks[l];
         maexp_learner::Da3Block &k = a.blk[l];
         ln_fwd(h, st, params, x, E, Rm * E, w.n1w, w.n1b, k.n1, k.m1, k.r1, rows, Rm);
         gemm(st, G, k.n1, params + w.qkvw, k.qkv, nullptr, rows, 3 * E, E, E, 1, 1, E, 3 * E, 1, Rm * E, P, Rm * 3 * E, 0);
@@ -1204,19 +1219,18 @@ void da3_forward(maexp_learner *h, cudaStream_t st, const float *params, const f
         gemm(st, G, k.g1, params + w.f2w, k.x2, params + w.f2b, rows, E, Fm, Fm, 1, 1, Fm, E, 1, Rm * Fm, P, Rm * E, P, 0, 1);
         x = k.x2;
     }
-    // final LayerNorm on the saliency token only, then the head (da3.py:59-60,90-96)
+    // final LayerNorm on the saliency token only (da3.py:59-60,90-91)
     layernorm_fwd_kernel<<<dim3((B * 32 + 255) / 256, G), 256, 0, st>>>(x, (long long)Tn * E, params + h->o_nfw, params + h->o_nfb,
                                                                         a.nf, a.mf, a.rf, B, E, Rm * E, Bmax * E, Bmax, P);
-    if (with_head)
-        gemm(st, G, a.nf, params + h->o_hw, a.q, params + h->o_hb, B, h->A, E, E, 1, 1, E, h->A, 1, Bmax * E, P, Bmax * h->A, P);
 }
 
-void da3_backward(maexp_learner *h, cudaStream_t st, bool with_head = true) {
-    maexp_learner::Da3Acts &a = h->da[0];
-    const int G = h->G, B = h->B, C = h->C, E = h->E_, Tn = h->Tn, Fm = h->Fm, A = h->A;
-    const long long P = h->P, Rm = (long long)B * Tn, R49 = (long long)B * (Tn - 1);
-    const int rows = B * Tn, rows49 = B * (Tn - 1);
-    const float *dq = h->d_out[0];
+// gradients of one stack from h->da_dnf = d LN(token 0); norm_acc: the shared final norm was already written by
+// another stack (DA6), so add.  d_tok0_ext != nullptr: token 0 was a per-sample input, return its gradient [G][B][E].
+void vit_backward(maexp_learner *h, cudaStream_t st, maexp_learner::VitStack &s, float *d_tok0_ext, int norm_acc) {
+    maexp_learner::Da3Acts &a = s.a[0];
+    const int G = h->G, B = h->B, E = h->E_, Tn = s.Tn, Fm = h->Fm, K = s.K;
+    const long long P = h->P, Rm = (long long)B * Tn, Rt = (long long)B * (Tn - 1);
+    const int rows = B * Tn, rowst = B * (Tn - 1);
     float *grads = h->grads;
     const float *W = h->online;
     const float scale = 1.0f / sqrtf((float)(E / h->heads_));
@@ -1226,19 +1240,14 @@ void da3_backward(maexp_learner *h, cudaStream_t st, bool with_head = true) {
                                                                                 h->da_gx, nrows, E, nrows_max * E, gX, gDx,
                                                                                 nrows_max, P);
     };
-    if (with_head) {  // drl_head; the merged model fills da_dnf from its own concatenated head
-        gemm(st, G, dq, a.nf, grads + h->o_hw, nullptr, A, E, B, 1, A, E, 1, E, 1, (long long)B * A, (long long)B * E, P, 0);
-        colsum(st, G, h->ones, dq, grads + h->o_hb, B, A, (long long)B * A, P);
-        gemm(st, G, dq, W + h->o_hw, h->da_dnf, nullptr, B, E, A, A, 1, E, 1, E, 1, (long long)B * A, P, (long long)B * E, 0);
-    }
     const float *x_last = h->L_ ? a.blk[h->L_ - 1].x2 : a.x0;
     ln_bwd(h->da_dnf, x_last, (long long)Tn * E, Rm * E, h->o_nfw, a.mf, a.rf, h->da_dtok0, E, (long long)B * E, 0, B, B);
-    colsum(st, G, h->ones, h->da_gx, grads + h->o_nfw, B, E, (long long)B * E, P);
-    colsum(st, G, h->ones, h->da_dnf, grads + h->o_nfb, B, E, (long long)B * E, P);
+    colsum(st, G, h->ones, h->da_gx, grads + h->o_nfw, B, E, (long long)B * E, P, norm_acc);
+    colsum(st, G, h->ones, h->da_dnf, grads + h->o_nfb, B, E, (long long)B * E, P, norm_acc);
     da3_scatter_token0_kernel<<<grid1d((long long)rows * E, G), 256, 0, st>>>(h->da_dtok0, h->da_dx, B, Tn, E, (long long)B * E,
                                                                               Rm * E);
     for (int l = h->L_ - 1; l >= 0; --l) {
-        const maexp_learner::BlockLayout &w = h->blocks[l];
+        const maexp_learner::BlockLayout &w = s.blocks[l];
         maexp_learner::Da3Block &k = a.blk[l];
         const float *x_in = l ? a.blk[l - 1].x2 : a.x0;
         // mlp branch: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
@@ -1265,12 +1274,72 @@ void da3_backward(maexp_learner *h, cudaStream_t st, bool with_head = true) {
         colsum(st, G, h->ones, h->da_gx, grads + w.n1w, rows, E, Rm * E, P);
         colsum(st, G, h->ones, h->da_dn, grads + w.n1b, rows, E, Rm * E, P);
     }
-    // embeddings: pos_embed, saliency_vector, patch projection (da_dx = d x0)
-    colsum(st, G, h->ones, h->da_dx, grads + h->o_pos, B, Tn * E, Rm * E, P);
-    gemm(st, G, h->ones, h->da_dx, grads + h->o_sal, nullptr, 1, E, B, 0, 0, (long long)Tn * E, 1, E, 1, 0, Rm * E, P, 0);
-    da3_token_rows_kernel<<<grid1d((long long)rows49 * E, G), 256, 0, st>>>(h->da_dx, h->da_dtok, B, Tn, E, Rm * E, R49 * E);
-    gemm(st, G, h->da_dtok, a.patches, grads + h->o_pew, nullptr, E, C, rows49, 1, E, C, 1, C, 1, R49 * E, R49 * C, P, 0);
-    colsum(st, G, h->ones, h->da_dtok, grads + h->o_peb, rows49, E, R49 * E, P);
+    // embeddings: pos_embed, token 0 (parameter or per-sample input), patch projection (da_dx = d x0)
+    colsum(st, G, h->ones, h->da_dx, grads + s.o_pos, B, Tn * E, Rm * E, P);
+    if (d_tok0_ext)  // rows (g, b, token 0) of da_dx; B == batch_size in the backward pass, so (g*B + b) * Tn * E is uniform
+        cudaMemcpy2DAsync(d_tok0_ext, sizeof(float) * E, h->da_dx, sizeof(float) * (size_t)Tn * E, sizeof(float) * E,
+                          (size_t)G * B, cudaMemcpyDeviceToDevice, st);
+    else
+        gemm(st, G, h->ones, h->da_dx, grads + s.o_sal, nullptr, 1, E, B, 0, 0, (long long)Tn * E, 1, E, 1, 0, Rm * E, P, 0);
+    da3_token_rows_kernel<<<grid1d((long long)rowst * E, G), 256, 0, st>>>(h->da_dx, h->da_dtok, B, Tn, E, Rm * E, Rt * E);
+    gemm(st, G, h->da_dtok, a.patches, grads + s.o_pew, nullptr, E, K, rowst, 1, E, K, 1, K, 1, Rt * E, Rt * K, P, 0);
+    colsum(st, G, h->ones, h->da_dtok, grads + s.o_peb, rowst, E, Rt * E, P);
+}
+
+// DA3 / MergedDA3's local stack on the batch's V x V crops, optionally followed by the drl_head (da3.py:64-96)
+void da3_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, int pass,
+                 bool with_head = true) {
+    const long long P = h->P, Bmax = h->B;
+    const int E = h->E_;
+    vit_forward(h, st, params, h->vloc, obs, h->cfg.obs_stride, (long long)h->V * h->V, (long long)B * h->cfg.obs_stride, B, pass,
+                nullptr);
+    if (with_head)
+        gemm(st, h->G, h->vloc.a[pass].nf, params + h->o_hw, h->vloc.a[pass].q, params + h->o_hb, B, h->A, E, E, 1, 1, E, h->A, 1,
+             Bmax * E, P, Bmax * h->A, P);
+}
+
+// drl_head gradients and d LN(token 0) into h->da_dnf
+void head_backward(maexp_learner *h, cudaStream_t st, const float *nf) {
+    const int G = h->G, B = h->B, E = h->E_, A = h->A;
+    const long long P = h->P;
+    const float *dq = h->d_out[0];
+    gemm(st, G, dq, nf, h->grads + h->o_hw, nullptr, A, E, B, 1, A, E, 1, E, 1, (long long)B * A, (long long)B * E, P, 0);
+    colsum(st, G, h->ones, dq, h->grads + h->o_hb, B, A, (long long)B * A, P);
+    gemm(st, G, dq, h->online + h->o_hw, h->da_dnf, nullptr, B, E, A, A, 1, E, 1, E, 1, (long long)B * A, P, (long long)B * E, 0);
+}
+
+void da3_backward(maexp_learner *h, cudaStream_t st, bool with_head = true) {
+    if (with_head) head_backward(h, st, h->vloc.a[0].nf);  // the merged model fills da_dnf from its own concatenated head
+    vit_backward(h, st, h->vloc, nullptr, 0);
+}
+
+int decode_canvas(maexp_learner *h, cudaStream_t st, const float *obs, const int8_t *pos, int B, int pass, int only_area);
+
+// DA6 (customs/da6.py:98-126): relative stack on the area canvas -> LN -> fc1 -> token 0 of the local stack -> LN -> drl_head
+int da6_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, const int8_t *pos, int B, int pass) {
+    const long long P = h->P, Bmax = h->B, XY = (long long)h->X * h->Y;
+    const int E = h->E_, G = h->G;
+    if (decode_canvas(h, st, obs, pos, B, pass, 1)) return -1;
+    vit_forward(h, st, params, h->vrel, h->canvas[pass], XY, XY, (long long)B * XY, B, pass, nullptr);
+    gemm(st, G, h->vrel.a[pass].nf, params + h->o_f1w, h->sal2[pass], params + h->o_f1b, B, E, E, E, 1, 1, E, E, 1, Bmax * E, P,
+         Bmax * E, P);
+    vit_forward(h, st, params, h->vloc, obs, h->cfg.obs_stride, (long long)h->V * h->V, (long long)B * h->cfg.obs_stride, B, pass,
+                h->sal2[pass]);
+    gemm(st, G, h->vloc.a[pass].nf, params + h->o_hw, h->vloc.a[pass].q, params + h->o_hb, B, h->A, E, E, 1, 1, E, h->A, 1,
+         Bmax * E, P, Bmax * h->A, P);
+    return 0;
+}
+
+void da6_backward(maexp_learner *h, cudaStream_t st) {
+    const int G = h->G, B = h->B, E = h->E_;
+    const long long P = h->P, BE = (long long)B * E;
+    head_backward(h, st, h->vloc.a[0].nf);
+    vit_backward(h, st, h->vloc, h->d_sal2, 0);
+    // fc1: sal2 = nf_rel W^T + b
+    gemm(st, G, h->d_sal2, h->vrel.a[0].nf, h->grads + h->o_f1w, nullptr, E, E, B, 1, E, E, 1, E, 1, BE, BE, P, 0);
+    colsum(st, G, h->ones, h->d_sal2, h->grads + h->o_f1b, B, E, BE, P);
+    gemm(st, G, h->d_sal2, h->online + h->o_f1w, h->da_dnf, nullptr, B, E, E, E, 1, E, 1, E, 1, BE, P, BE, 0);
+    vit_backward(h, st, h->vrel, nullptr, /*norm_acc=*/1);  // the final norm is shared by both stages (da6.py:94,110,121)
 }
 
 // ---- generalized conv trunk: src[g][b*sb + c*sc + y*sy + x*sx] -> flat slice [b*flat_row + flat_off + ...]
@@ -1360,12 +1429,12 @@ int merged_forward(maexp_learner *h, cudaStream_t st, const float *params, const
     for (int g = 0; g < h->G; ++g) {  // concatenate per group (2-D copies are graph-capturable)
         cudaMemcpy2DAsync(h->feat[pass] + (size_t)g * Bmax * Dt, sizeof(float) * Dt, h->rse_out[pass] + (size_t)g * Bmax * Dr,
                           sizeof(float) * Dr, sizeof(float) * Dr, B, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpy2DAsync(h->feat[pass] + (size_t)g * Bmax * Dt + Dr, sizeof(float) * Dt, h->da[pass].nf + (size_t)g * Bmax * E,
+        cudaMemcpy2DAsync(h->feat[pass] + (size_t)g * Bmax * Dt + Dr, sizeof(float) * Dt, h->vloc.a[pass].nf + (size_t)g * Bmax * E,
                           sizeof(float) * E, sizeof(float) * E, B, cudaMemcpyDeviceToDevice, st);
     }
-    gemm(st, h->G, h->feat[pass], params + h->o_hw, h->da[pass].q, params + h->o_hb, B, h->A, Dt, Dt, 1, 1, Dt, h->A, 1, Bmax * Dt, P,
+    gemm(st, h->G, h->feat[pass], params + h->o_hw, h->vloc.a[pass].q, params + h->o_hb, B, h->A, Dt, Dt, 1, 1, Dt, h->A, 1, Bmax * Dt, P,
          Bmax * h->A, P);
-    *q_out = h->da[pass].q;
+    *q_out = h->vloc.a[pass].q;
     return 0;
 }
 
@@ -1407,7 +1476,7 @@ extern "C" {
 
 int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (!cfg || !out) return fail("maexp_learner_create: null argument");
-    if (cfg->kind < MAEXP_LEARNER_DQN_CONV_MLP || cfg->kind > MAEXP_LEARNER_DA3)
+    if (cfg->kind < MAEXP_LEARNER_DQN_CONV_MLP || cfg->kind > MAEXP_LEARNER_DA6)
         return fail("maexp_learner_create: unknown kind");
     if (cfg->num_agents < 1 || cfg->batch_size < 1) return fail("maexp_learner_create: bad num_agents / batch_size");
     if (cfg->num_actions < 1 || cfg->num_actions > kMaxActions) return fail("maexp_learner_create: num_actions must be in 1..8");
@@ -1415,13 +1484,15 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     h->cfg = *cfg;
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
     h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;
-    h->da3 = cfg->kind == MAEXP_LEARNER_DA3;
+    h->da6 = cfg->kind == MAEXP_LEARNER_DA6;
+    h->da3 = cfg->kind == MAEXP_LEARNER_DA3 || h->da6;  // da3: "has transformer stacks"
     h->area_mask = cfg->area_mask; h->X = cfg->size_x; h->Y = cfg->size_y;
     h->relative_conv = cfg->kind == MAEXP_LEARNER_DQN_CONV_MLP && cfg->area_mask == MAEXP_MASK_RELATIVE;
     h->merged_conv = cfg->kind == MAEXP_LEARNER_DQN_CONV_MLP && cfg->area_mask == MAEXP_MASK_MERGED;
-    h->merged_da3 = h->da3 && cfg->area_mask == MAEXP_MASK_MERGED;
+    h->merged_da3 = h->da3 && !h->da6 && cfg->area_mask == MAEXP_MASK_MERGED;
     const bool gmodel = h->relative_conv || h->merged_conv || h->merged_da3;
-    if (cfg->area_mask != MAEXP_MASK_LOCAL && !gmodel) { delete h; return fail("maexp_learner_create: relative / merged views are implemented for conv_mlp (dqn) and da3 (merged)"); }
+    if (h->da6 && (cfg->area_mask != MAEXP_MASK_MERGED || h->X < 4 || h->Y < 4)) { delete h; return fail("maexp_learner_create: DA6 reads the merged view (area_mask merged, size_x / size_y set)"); }
+    if (cfg->area_mask != MAEXP_MASK_LOCAL && !gmodel && !h->da6) { delete h; return fail("maexp_learner_create: relative / merged views are implemented for conv_mlp (dqn) and da3 (merged)"); }
     if (gmodel && (h->X < 4 || h->Y < 4)) { delete h; return fail("maexp_learner_create: size_x / size_y missing for a relative / merged model"); }
     h->has_conv = cfg->kind != MAEXP_LEARNER_DQN_MLP && !h->da3 && !gmodel;
     h->dist = cfg->kind == MAEXP_LEARNER_C51 || cfg->kind == MAEXP_LEARNER_QR;
@@ -1464,15 +1535,46 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     }
     if (h->da3) {
         h->E_ = cfg->embed_dim; h->heads_ = cfg->num_heads; h->Fm = cfg->mlp_hidden; h->L_ = cfg->block_loop;
-        h->Tn = h->V * h->V + 1;
         h->H1 = h->Hp = h->H2 = 0;
         h->D = h->E_;
+        auto set_stack = [&](maexp_learner::VitStack &s, int cin, int hin, int win, int ps) {
+            s.Cin = cin; s.Hin = hin; s.Win = win; s.ps = ps > 0 ? ps : 1;
+            s.Ht = hin / s.ps; s.Wt = win / s.ps; s.Tn = s.Ht * s.Wt + 1; s.K = cin * s.ps * s.ps;
+        };
+        set_stack(h->vloc, h->C, h->V, h->V, h->da6 ? cfg->local_patch_size : 1);
+        if (h->da6) set_stack(h->vrel, 1, h->X, h->Y, cfg->patch_size);
+        h->Tn = h->da6 && h->vrel.Tn > h->vloc.Tn ? h->vrel.Tn : h->vloc.Tn;
         if (h->E_ < 1 || h->heads_ < 1 || h->E_ % h->heads_ || h->E_ / h->heads_ > kMaxHeadDim || h->Tn > kMaxTokens || h->Fm < 1 ||
+            h->vloc.Tn < 2 || (h->da6 && h->vrel.Tn < 2) ||
             h->L_ < 0 || (4 * h->Tn * (h->E_ / h->heads_) + h->Tn * h->Tn) * 4 > 48 * 1024) {
             delete h;
-            return fail("maexp_learner_create: unsupported DA3 shape (tokens <= 96, head_dim <= 32, attention tile <= 48 KB)");
+            return fail("maexp_learner_create: unsupported DA3 / DA6 shape (2 <= tokens <= 96, head_dim <= 32, attention tile <= 48 KB)");
         }
-        // own parameters first, then submodules in registration order (customs/da3.py:33-60)
+        auto add_blocks = [&](maexp_learner::VitStack &s, const std::string &prefix) {
+            for (int l = 0; l < h->L_; ++l) {
+                const std::string b = prefix + "blocks." + std::to_string(l) + ".";
+                maexp_learner::BlockLayout w;
+                w.n1w = add(b + "norm1.weight", h->E_); w.n1b = add(b + "norm1.bias", h->E_);
+                w.qkvw = add(b + "attn.qkv.weight", 3ll * h->E_ * h->E_);
+                w.projw = add(b + "attn.proj.weight", (long long)h->E_ * h->E_); w.projb = add(b + "attn.proj.bias", h->E_);
+                w.n2w = add(b + "norm2.weight", h->E_); w.n2b = add(b + "norm2.bias", h->E_);
+                w.f1w = add(b + "mlp.fc1.weight", (long long)h->Fm * h->E_); w.f1b = add(b + "mlp.fc1.bias", h->Fm);
+                w.f2w = add(b + "mlp.fc2.weight", (long long)h->E_ * h->Fm); w.f2b = add(b + "mlp.fc2.bias", h->E_);
+                s.blocks.push_back(w);
+            }
+        };
+        // own parameters first, then submodules in registration order (customs/da3.py:33-60, customs/da6.py:40-96)
+        if (h->da6) {
+            h->vrel.o_sal = add("saliency_vector", h->E_);
+            h->vrel.o_pos = add("relative_pos_embed", (long long)h->vrel.Tn * h->E_);
+            h->vloc.o_pos = add("local_pos_embed", (long long)h->vloc.Tn * h->E_);
+            h->vrel.o_pew = add("relative_patch_embed.proj.weight", (long long)h->E_ * h->vrel.K);
+            h->vrel.o_peb = add("relative_patch_embed.proj.bias", h->E_);
+            h->vloc.o_pew = add("local_patch_embed.proj.weight", (long long)h->E_ * h->vloc.K);
+            h->vloc.o_peb = add("local_patch_embed.proj.bias", h->E_);
+            add_blocks(h->vrel, "relative_");
+            add_blocks(h->vloc, "local_");
+        } else {
         const std::string lp = h->merged_da3 ? "local_" : "";
         if (h->merged_da3) {  // parameters the parent DA3.__init__ creates and MergedDA3 never uses (da3.py:99-103)
             const int ps = cfg->patch_size > 0 ? cfg->patch_size : 1;
@@ -1480,32 +1582,17 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             add("pos_embed", (long long)((h->X / ps) * (h->Y / ps) + 1) * h->E_);
             add("patch_embed.proj.weight", (long long)h->E_ * h->C * ps * ps);
             add("patch_embed.proj.bias", h->E_);
-            for (int l = 0; l < h->L_; ++l) {
-                const std::string b = "blocks." + std::to_string(l) + ".";
-                add(b + "norm1.weight", h->E_); add(b + "norm1.bias", h->E_);
-                add(b + "attn.qkv.weight", 3ll * h->E_ * h->E_);
-                add(b + "attn.proj.weight", (long long)h->E_ * h->E_); add(b + "attn.proj.bias", h->E_);
-                add(b + "norm2.weight", h->E_); add(b + "norm2.bias", h->E_);
-                add(b + "mlp.fc1.weight", (long long)h->Fm * h->E_); add(b + "mlp.fc1.bias", h->Fm);
-                add(b + "mlp.fc2.weight", (long long)h->E_ * h->Fm); add(b + "mlp.fc2.bias", h->E_);
-            }
+            maexp_learner::VitStack unused;
+            add_blocks(unused, "");
         }
-        h->o_sal = add(lp + "saliency_vector", h->E_);
-        h->o_pos = add(lp + "pos_embed", (long long)h->Tn * h->E_);
-        h->o_pew = add(lp + "patch_embed.proj.weight", (long long)h->E_ * h->C);
-        h->o_peb = add(lp + "patch_embed.proj.bias", h->E_);
-        for (int l = 0; l < h->L_; ++l) {
-            const std::string b = lp + "blocks." + std::to_string(l) + ".";
-            maexp_learner::BlockLayout w;
-            w.n1w = add(b + "norm1.weight", h->E_); w.n1b = add(b + "norm1.bias", h->E_);
-            w.qkvw = add(b + "attn.qkv.weight", 3ll * h->E_ * h->E_);
-            w.projw = add(b + "attn.proj.weight", (long long)h->E_ * h->E_); w.projb = add(b + "attn.proj.bias", h->E_);
-            w.n2w = add(b + "norm2.weight", h->E_); w.n2b = add(b + "norm2.bias", h->E_);
-            w.f1w = add(b + "mlp.fc1.weight", (long long)h->Fm * h->E_); w.f1b = add(b + "mlp.fc1.bias", h->Fm);
-            w.f2w = add(b + "mlp.fc2.weight", (long long)h->E_ * h->Fm); w.f2b = add(b + "mlp.fc2.bias", h->E_);
-            h->blocks.push_back(w);
+        h->vloc.o_sal = add(lp + "saliency_vector", h->E_);
+        h->vloc.o_pos = add(lp + "pos_embed", (long long)h->vloc.Tn * h->E_);
+        h->vloc.o_pew = add(lp + "patch_embed.proj.weight", (long long)h->E_ * h->C);
+        h->vloc.o_peb = add(lp + "patch_embed.proj.bias", h->E_);
+        add_blocks(h->vloc, lp);
         }
         h->o_nfw = add("norm.weight", h->E_); h->o_nfb = add("norm.bias", h->E_);
+        if (h->da6) { h->o_f1w = add("fc1.weight", (long long)h->E_ * h->E_); h->o_f1b = add("fc1.bias", h->E_); }
         if (h->merged_da3) {
             set_trunk(h->gt_rel, "relative_conv", 1, h->X, h->Y);
             h->Drel = h->gt_rel.D; h->Dloc = 0;
@@ -1593,26 +1680,38 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     const long long R = h->iqn ? h->rows_max : B;
     if (h->da3) {
         const long long Rm = B * h->Tn, R49 = B * (h->Tn - 1), E = h->E_;
-        for (int k = 0; k < 3; ++k) {
-            maexp_learner::Da3Acts &a = h->da[k];
-            rc |= lalloc(h, &a.patches, G * R49 * h->C);
-            rc |= lalloc(h, &a.tok, G * R49 * E);
-            rc |= lalloc(h, &a.x0, G * Rm * E);
-            rc |= lalloc(h, &a.nf, G * B * E);
-            rc |= lalloc(h, &a.mf, G * B);
-            rc |= lalloc(h, &a.rf, G * B);
-            rc |= lalloc(h, &a.q, G * B * h->A);
-            a.blk.resize(h->L_);
-            for (int l = 0; l < h->L_; ++l) {
-                maexp_learner::Da3Block &q = a.blk[l];
-                rc |= lalloc(h, &q.n1, G * Rm * E); rc |= lalloc(h, &q.m1, G * Rm); rc |= lalloc(h, &q.r1, G * Rm);
-                rc |= lalloc(h, &q.qkv, G * Rm * 3 * E);
-                rc |= lalloc(h, &q.probs, G * B * h->heads_ * h->Tn * h->Tn);
-                rc |= lalloc(h, &q.ao, G * Rm * E); rc |= lalloc(h, &q.x1, G * Rm * E);
-                rc |= lalloc(h, &q.n2, G * Rm * E); rc |= lalloc(h, &q.m2, G * Rm); rc |= lalloc(h, &q.r2, G * Rm);
-                rc |= lalloc(h, &q.f1, G * Rm * h->Fm); rc |= lalloc(h, &q.g1, G * Rm * h->Fm);
-                rc |= lalloc(h, &q.x2, G * Rm * E);
+        auto alloc_stack = [&](maexp_learner::VitStack &s) {
+            const long long Rs = B * s.Tn, Rt = B * (s.Tn - 1);
+            for (int k = 0; k < 3; ++k) {
+                maexp_learner::Da3Acts &a = s.a[k];
+                rc |= lalloc(h, &a.patches, G * Rt * s.K);
+                rc |= lalloc(h, &a.tok, G * Rt * E);
+                rc |= lalloc(h, &a.x0, G * Rs * E);
+                rc |= lalloc(h, &a.nf, G * B * E);
+                rc |= lalloc(h, &a.mf, G * B);
+                rc |= lalloc(h, &a.rf, G * B);
+                rc |= lalloc(h, &a.q, G * B * h->A);
+                a.blk.resize(h->L_);
+                for (int l = 0; l < h->L_; ++l) {
+                    maexp_learner::Da3Block &q = a.blk[l];
+                    rc |= lalloc(h, &q.n1, G * Rs * E); rc |= lalloc(h, &q.m1, G * Rs); rc |= lalloc(h, &q.r1, G * Rs);
+                    rc |= lalloc(h, &q.qkv, G * Rs * 3 * E);
+                    rc |= lalloc(h, &q.probs, G * B * h->heads_ * s.Tn * s.Tn);
+                    rc |= lalloc(h, &q.ao, G * Rs * E); rc |= lalloc(h, &q.x1, G * Rs * E);
+                    rc |= lalloc(h, &q.n2, G * Rs * E); rc |= lalloc(h, &q.m2, G * Rs); rc |= lalloc(h, &q.r2, G * Rs);
+                    rc |= lalloc(h, &q.f1, G * Rs * h->Fm); rc |= lalloc(h, &q.g1, G * Rs * h->Fm);
+                    rc |= lalloc(h, &q.x2, G * Rs * E);
+                }
             }
+        };
+        alloc_stack(h->vloc);
+        if (h->da6) {
+            alloc_stack(h->vrel);
+            for (int k = 0; k < 3; ++k) {
+                rc |= lalloc(h, &h->sal2[k], G * B * E);
+                rc |= lalloc(h, &h->canvas[k], G * B * h->X * h->Y);
+            }
+            rc |= lalloc(h, &h->d_sal2, G * B * E);
         }
         rc |= lalloc(h, &h->d_out[0], G * B * h->A);
         rc |= lalloc(h, &h->da_dx, G * Rm * E); rc |= lalloc(h, &h->da_dn, G * Rm * E); rc |= lalloc(h, &h->da_gx, G * Rm * E);
@@ -1755,8 +1854,12 @@ int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int us
         return 0;
     }
     if (h->da3) {
-        da3_forward(h, st, use_target ? h->target : h->online, obs, batch, 1);
-        MAEXP_CUDA_L(cudaMemcpy2DAsync(q_out, sizeof(float) * batch * h->A, h->da[1].q, sizeof(float) * h->B * h->A,
+        if (h->da6) {
+            if (da6_forward(h, st, use_target ? h->target : h->online, obs, h->pos, batch, 1)) return -1;
+        } else {
+            da3_forward(h, st, use_target ? h->target : h->online, obs, batch, 1);
+        }
+        MAEXP_CUDA_L(cudaMemcpy2DAsync(q_out, sizeof(float) * batch * h->A, h->vloc.a[1].q, sizeof(float) * h->B * h->A,
                                        sizeof(float) * batch * h->A, h->G, cudaMemcpyDeviceToDevice, st));
         MAEXP_CUDA_L(cudaGetLastError());
         return 0;
@@ -1793,12 +1896,18 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         return 0;
     }
     if (h->da3) {  // DA3Brain.learn: TD target + MSE on the attention network (da3_brain.py:58-89)
-        da3_forward(h, st, h->online, obs, B, 0);
-        da3_forward(h, st, h->target, next_obs, B, 2);
-        dqn_loss_kernel<<<dim3((B + 127) / 128, G), 128, 0, st>>>(h->da[0].q, h->da[2].q, actions, rewards, dones, h->cfg.gamma, B,
-                                                                  A, h->d_out[0], h->per_sample);
+        if (h->da6) {  // DA6Brain.learn (da6_brain.py:44-75): the same TD target + MSE
+            if (da6_forward(h, st, h->online, obs, h->pos, B, 0)) return -1;
+            if (da6_forward(h, st, h->target, next_obs, h->next_pos, B, 2)) return -1;
+        } else {
+            da3_forward(h, st, h->online, obs, B, 0);
+            da3_forward(h, st, h->target, next_obs, B, 2);
+        }
+        dqn_loss_kernel<<<dim3((B + 127) / 128, G), 128, 0, st>>>(h->vloc.a[0].q, h->vloc.a[2].q, actions, rewards, dones,
+                                                                  h->cfg.gamma, B, A, h->d_out[0], h->per_sample);
         mean_kernel<<<G, 256, 0, st>>>(h->per_sample, loss_out ? loss_out : h->q_tmp, B);
-        da3_backward(h, st);
+        if (h->da6) da6_backward(h, st);
+        else da3_backward(h, st);
         MAEXP_CUDA_L(cudaGetLastError());
         return 0;
     }

@@ -42,7 +42,11 @@ def configs():
     mconv = view("merged", "da3_baseline", "da3_baseline")
     mda3 = view("merged", "da3", "da3", embed_dim=32, block_loop=1, mlp_ratio=4.0, attention="soft", af_lambd=0.5)
     mda3["agent_type"] = "attention"
-    return {"relative_conv_mlp": (rel, [4, *SIZE]), "merged_conv_mlp": (mconv, [4, *SIZE]), "merged_da3": (mda3, [4, *SIZE]),
+    da6 = view("merged", "da6", "da6", embed_dim=32, block_loop=1, mlp_ratio=4.0, attention="soft", af_lambd=0.5,
+               relative_patch_size=3, local_patch_size=1)
+    da6["agent_type"] = "attention"
+    da6["objects_channel"], da6["agents_channel"] = False, False
+    return {"da6": (da6, [4, *SIZE]),"relative_conv_mlp": (rel, [4, *SIZE]), "merged_conv_mlp": (mconv, [4, *SIZE]), "merged_da3": (mda3, [4, *SIZE]),
             "da3": (da3, [3, 7, 7]), "dqn_conv_mlp": (dqn, [7, 7, 7]), "c51": (c5.merged_with(batch_size=B), [3, 7, 7]),
             "qr": (c3.merged_with(batch_size=B), [3, 7, 7]), "iqn": (iqn, [3, 7, 7])}
 
@@ -74,7 +78,12 @@ def main():
     for kind, (cfg, shape) in configs().items():
         torch.manual_seed(921)
         brain = generate_brain(config=rr.to_dictconfig(cfg), obs_shape=shape, act_size=4)
-        masked = kind in ("relative_conv_mlp", "merged_conv_mlp", "merged_da3")
+        masked = kind in ("relative_conv_mlp", "merged_conv_mlp", "merged_da3", "da6")
+        if kind == "da6":  # zero-initialised embeddings (da6.py:52-66)
+            with torch.no_grad():
+                for name in ("saliency_vector", "relative_pos_embed", "local_pos_embed"):
+                    p_ = getattr(brain.network, name)
+                    p_.add_(0.02 * torch.randn_like(p_))
         if kind == "merged_da3":
             with torch.no_grad():
                 brain.network.local_saliency_vector.add_(0.02 * torch.randn_like(brain.network.local_saliency_vector))

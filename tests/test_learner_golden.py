@@ -10,9 +10,10 @@ from oracle.torch_learner import TorchLearner
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KINDS = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLDEN, "learner_*.npz")))
-ATOMS = {"dqn_conv_mlp": 1, "c51": 51, "qr": 100, "iqn": 4, "da3": 1}
+ATOMS = {"dqn_conv_mlp": 1, "c51": 51, "qr": 100, "iqn": 4, "da3": 1, "da6": 1}
 # fixtures of the relative / merged views -> (network kind, attention heads)
-MASKED = {"relative_conv_mlp": ("dqn_conv_mlp", 4), "merged_conv_mlp": ("dqn_conv_mlp", 4), "merged_da3": ("da3", 2)}
+MASKED = {"relative_conv_mlp": ("dqn_conv_mlp", 4), "merged_conv_mlp": ("dqn_conv_mlp", 4), "merged_da3": ("da3", 2),
+          "da6": ("da6", 2)}
 
 
 def load(kind):
