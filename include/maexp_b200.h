@@ -218,10 +218,19 @@ typedef struct {
     int32_t area_mask;        /* MAEXP_MASK_*: relative (conv_mlp on the decoded [C,X,Y] canvas, conv_mlp.py:56-66) and merged
                                  (MergedConvMLP conv_mlp.py:69-108, MergedDA3 da3.py:99-225) need the observing agents' positions */
     int32_t size_x, size_y;   /* map size for the relative canvas */
-    int32_t patch_size;       /* DA3 model.patch_size (only sizes the parent's unused parameters of MergedDA3);
-                                 DA6: model.relative_patch_size */
-    int32_t local_patch_size; /* DA6: model.local_patch_size (0 = 1) */
+    int32_t patch_size;       /* model.patch_size: only sizes the parent's unused parameters of MergedDA3 / MergedDA3_IQN / DA6_IQN */
+    int32_t local_patch_size; /* DA6: model.local_patch_size; DA6_IQN: 1 (da6_iqn.py:55-58) */
+    int32_t relative_patch_size; /* DA6: model.relative_patch_size; DA6_IQN: 5 (da6_iqn.py:50-53) */
+    int32_t iqn_trunk;        /* MAEXP_LEARNER_IQN only: which network produces the state embedding, MAEXP_IQN_TRUNK_* */
 } maexp_learner_cfg;
+
+/* state-embedding producer under the IQN head (brain iqn / da3_iqn, iqn_brain.py:60-115, da3_iqn_brain.py:14-54) */
+enum {
+    MAEXP_IQN_TRUNK_CONV = 0,        /* model iqn: conv + state_embedder (customs/iqn.py:36-94) */
+    MAEXP_IQN_TRUNK_DA3 = 1,         /* model da3_iqn, local view (customs/da3_iqn.py:87-190) */
+    MAEXP_IQN_TRUNK_MERGED_DA3 = 2,  /* model da3_iqn, merged view (customs/da3_iqn.py:213-330) */
+    MAEXP_IQN_TRUNK_DA6 = 3          /* model da6_iqn (customs/da6_iqn.py:24-176) */
+};
 
 typedef struct maexp_learner maexp_learner;
 

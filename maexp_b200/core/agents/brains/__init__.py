@@ -16,7 +16,18 @@ logger = initialize_logging(__name__)
 
 # brain name -> (learner kind for conv models, clip max_norm)      brains/*.py
 _BRAINS = {"dqn": ("dqn_conv_mlp", 0.1), "da3_baseline": ("dqn_conv_mlp", 0.1), "categorical_dqn": ("c51", 10.0),
-           "qr_dqn": ("qr", 0.1), "iqn": ("iqn", 0.1), "da3": ("da3", 0.1), "da6": ("da6", 0.1)}
+           "qr_dqn": ("qr", 0.1), "iqn": ("iqn", 0.1), "da3": ("da3", 0.1), "da6": ("da6", 0.1),
+           "da3_iqn": ("iqn", 0.1)}  # DA3_IQNBrain(IQNBrain) keeps IQNBrain.learn (da3_iqn_brain.py:14)
+
+IQN_TRUNKS = {"iqn": 0, "da3_iqn": 1, "merged_da3_iqn": 2, "da6_iqn": 3}
+
+
+def iqn_trunk(config):
+    """Which network produces the state embedding under the IQN head (models/__init__.py:51-72)."""
+    name, mask = config.model.name, config.observation_area_mask
+    if name == "da3_iqn" and mask == "merged":
+        return "merged_da3_iqn"
+    return name
 
 
 def learner_kind(config):
@@ -28,6 +39,17 @@ def learner_kind(config):
         if kind != "dqn_conv_mlp":
             raise ValueError("model=mlp is only defined for the dqn brain")
         kind = "dqn_mlp"
+    elif config.model.name in ("da3_iqn", "da6_iqn"):
+        if config.brain not in ("da3_iqn", "iqn"):
+            raise ValueError("model da3_iqn / da6_iqn needs an IQN brain (brain=da3_iqn)")
+        mask = config.observation_area_mask
+        if config.model.get("attention") in ("hard", "aoa") or config.get("objects_channel") or \
+                config.get("agents_channel") or config.get("destination_channel"):
+            raise ValueError("attention IQN models are implemented with soft attention and without extra canvas channels")
+        if config.model.name == "da6_iqn" and mask != "merged":
+            raise ValueError("da6_iqn reads the merged view (customs/da6_iqn.py:160-176)")
+        if config.model.name == "da3_iqn" and (mask == "relative" or (mask == "local" and int(config.model.patch_size) != 1)):
+            raise ValueError("da3_iqn is implemented for the local view (patch_size=1) and the merged view")
     elif config.model.name == "da6" or kind == "da6":
         if kind != "da6" or config.model.name != "da6":
             raise ValueError("brain=da6 and model=da6 go together (da6_brain.py, customs/da6.py)")
@@ -43,8 +65,9 @@ def learner_kind(config):
     elif config.model.name not in ("conv_mlp", "da3_baseline", "categorical_dqn", "qr_dqn", "iqn"):
         logger.warning(f"Unexpected network is given. config.model.name: {config.model.name}")
         raise ValueError()
-    if config.observation_area_mask != "local" and kind not in ("dqn_conv_mlp", "da3", "da6"):
-        raise ValueError("relative / merged views are implemented for the conv_mlp DQN, the merged DA3 and DA6")
+    if config.observation_area_mask != "local" and kind not in ("dqn_conv_mlp", "da3", "da6") and \
+            config.model.name not in ("da3_iqn", "da6_iqn"):
+        raise ValueError("relative / merged views are implemented for the conv_mlp DQN, DA3 / DA6 and their IQN variants")
     if config.observation_area_mask == "merged" and config.observation_noise:
         # the merged models read the area channel of the NOISE-FREE "relative" key (merged_observtion_handler.py:26-29);
         # the replay ring keeps only the noisy crop, so this combination is refused rather than approximated
@@ -79,9 +102,14 @@ class LearnerGroup:
         cfg.patch_size = int(m.get("patch_size") or 1)
         cfg.hidden = 0 if self.kind == "da6" or (self.kind == "da3" and self.area_mask != "merged") else \
             int(m.hidden_layer_sizes[0])
+        self.trunk = iqn_trunk(config) if self.kind == "iqn" else None
         if self.kind == "da6":
-            cfg.patch_size, cfg.local_patch_size = int(m.relative_patch_size), int(m.local_patch_size)
-        if self.kind in ("da3", "da6"):
+            cfg.relative_patch_size, cfg.local_patch_size = int(m.relative_patch_size), int(m.local_patch_size)
+        if self.kind == "iqn":
+            cfg.iqn_trunk = IQN_TRUNKS[self.trunk]
+            if self.trunk == "da6_iqn":  # hard-coded in da6_iqn.py:50-58
+                cfg.relative_patch_size, cfg.local_patch_size = 5, 1
+        if self.kind in ("da3", "da6") or self.trunk in ("da3_iqn", "merged_da3_iqn", "da6_iqn"):
             cfg.embed_dim, cfg.num_heads, cfg.block_loop = int(m.embed_dim), int(m.num_heads), int(m.block_loop)
             cfg.mlp_hidden = int(int(m.embed_dim) * float(m.mlp_ratio))
         cfg.conv1_channels = int(m.get("hidden_channels", [32])[0])

@@ -144,6 +144,52 @@ class _MergedDA3(_DA3):
         self.drl_head = nn.Linear(int(m.embed_dim) + d, act_size)
 
 
+class _IQNHead(nn.Module):
+    """customs/da3_iqn.py:26-40"""
+
+    def __init__(self, config, d, act_size):
+        super().__init__()
+        self.cosine_net = nn.Module()
+        self.cosine_net.net = nn.Sequential(nn.Linear(int(config.model.num_cosines), d), nn.ReLU(inplace=False))
+        self.fc_V = _MLP(config, d, 1)
+        self.fc_A = _MLP(config, d, act_size)
+
+
+class _DA3IQN(_DA3):
+    """customs/da3_iqn.py:87-145: DA3's transformer with the IQN head."""
+
+    def __init__(self, config, obs_shape, act_size):
+        super().__init__(config, obs_shape, act_size)
+        self.drl_head = _IQNHead(config, int(config.model.embed_dim), act_size)
+
+
+class _MergedDA3IQN(_MergedDA3):
+    """customs/da3_iqn.py:213-265"""
+
+    def __init__(self, config, obs_shape, act_size):
+        super().__init__(config, obs_shape, act_size)
+        d = conv_output_size(config, [1, *obs_shape[1:]])
+        self.drl_head = _IQNHead(config, int(config.model.embed_dim) + d, act_size)
+
+
+class _DA6IQN(_DA3):
+    """customs/da6_iqn.py:24-96: DA3_IQN's (unused) parameters plus the two DA6 stages; patch sizes 5 and 1 are hard-coded."""
+
+    def __init__(self, config, obs_shape, act_size):
+        super().__init__(config, obs_shape, act_size)
+        m, v, e = config.model, int(config.visible_range), int(config.model.embed_dim)
+        self.relative_patch_embed = _PatchEmbed(5, 1, e)
+        self.local_patch_embed = _PatchEmbed(1, int(obs_shape[0]), e)
+        self.saliency_vector = nn.Parameter(torch.zeros(1, 1, e))
+        self.relative_pos_embed = nn.Parameter(torch.zeros(1, (int(obs_shape[1]) // 5) * (int(obs_shape[2]) // 5) + 1, e))
+        self.local_pos_embed = nn.Parameter(torch.zeros(1, v * v + 1, e))
+        self.relative_blocks = nn.ModuleList([_Block(e, float(m.mlp_ratio)) for _ in range(int(m.block_loop))])
+        self.local_blocks = nn.ModuleList([_Block(e, float(m.mlp_ratio)) for _ in range(int(m.block_loop))])
+        self.norm = nn.LayerNorm(e)
+        self.fc1 = nn.Linear(e, e)
+        self.drl_head = _IQNHead(config, e, act_size)
+
+
 class _DA6(nn.Module):
     """Parameter layout and construction order of customs/da6.py:22-96 (objects_channel / agents_channel off)."""
 
@@ -181,6 +227,12 @@ def build_reference_modules(config, obs_shape, act_size):
         return _IQN(config, obs_shape, act_size)
     if name == "da6":
         return _DA6(config, obs_shape, act_size)
+    if name == "da6_iqn":
+        return _DA6IQN(config, obs_shape, act_size)
+    if name == "da3_iqn":
+        if config.observation_area_mask == "merged":
+            return _MergedDA3IQN(config, obs_shape, act_size)
+        return _DA3IQN(config, obs_shape, act_size)
     if name == "da3":
         if config.observation_area_mask == "merged":
             return _MergedDA3(config, obs_shape, act_size)

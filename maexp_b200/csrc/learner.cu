@@ -1142,45 +1142,6 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
 }
 
 // ---- IQN (customs/iqn.py:88-139): quantiles of `nq` taus per sample; taus per sample [G][B][nq] or shared [G][nq]
-void iqn_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, const float *taus, int nq,
-                 int per_sample, int pass) {
-    maexp_learner::Acts &a = h->acts[pass];
-    maexp_learner::IqnActs &q = h->iq[pass];
-    const int G = h->G, D = h->D;
-    const long long P = h->P, Bmax = h->B, R = h->rows_max;
-    trunk_forward(h, st, params, obs, B, a);
-    const MlpIn se_in = {a.flat, D, Bmax * D, B, Bmax, D};
-    mlp_forward(h, st, params, h->se, se_in, q.se_h, q.psi);  // state_embedder
-    const int rows = B * nq;
-    iqn_cos_kernel<<<grid1d((long long)rows * h->ncos, G), 256, 0, st>>>(taus, q.cosf, B, nq, h->ncos, per_sample,
-                                                                         per_sample ? (long long)B * nq : (long long)nq,
-                                                                         R * h->ncos);
-    // phi = relu(cos W^T + b)   (cosine_net.net.0 + ReLU, customs/iqn.py:24)
-    gemm(st, G, q.cosf, params + h->o_cw, q.phi, params + h->o_cb, rows, D, h->ncos, h->ncos, 1, 1, h->ncos, D, 1,
-         R * h->ncos, P, R * D, P, /*relu=*/1);
-    iqn_hadamard_fwd_kernel<<<grid1d((long long)rows * D, G), 256, 0, st>>>(q.psi, q.phi, q.e, B, nq, D, Bmax * D, R * D);
-    const MlpIn e_in = {q.e, D, R * D, rows, R, D};
-    for (int k = 0; k < 2; ++k) mlp_forward(h, st, params, h->heads[k], e_in, q.hrow[k], q.out[k]);
-}
-
-void iqn_backward(maexp_learner *h, cudaStream_t st, int nq) {
-    maexp_learner::Acts &a = h->acts[0];
-    maexp_learner::IqnActs &q = h->iq[0];
-    const int G = h->G, B = h->B, D = h->D, rows = B * nq;
-    const long long P = h->P, R = h->rows_max;
-    const MlpIn e_in = {q.e, D, R * D, rows, R, D};
-    for (int k = 0; k < 2; ++k) mlp_backward(h, st, h->heads[k], e_in, h->d_out[k], q.hrow[k], h->d_hrow, h->d_e, k > 0);
-    iqn_hadamard_bwd_kernel<<<grid1d((long long)B * D, G), 256, 0, st>>>(h->d_e, q.psi, q.phi, h->d_phi, h->d_psi, B, nq, D,
-                                                                         (long long)B * D, R * D);
-    // cosine net: dW[D,ncos] = dphi^T cos ; db = colsum(dphi)
-    gemm(st, G, h->d_phi, q.cosf, h->grads + h->o_cw, nullptr, D, h->ncos, rows, 1, D, h->ncos, 1, h->ncos, 1, R * D,
-         R * h->ncos, P, 0);
-    colsum(st, G, h->ones, h->d_phi, h->grads + h->o_cb, rows, D, R * D, P);
-    const MlpIn se_in = {a.flat, D, (long long)B * D, B, B, D};
-    mlp_backward(h, st, h->se, se_in, h->d_psi, q.se_h, h->d_h, h->d_flat, 0);
-    trunk_backward(h, st);
-}
-
 // ---- DA3 (customs/da3.py:22-96, vit.py): patch embedding, saliency token, pre-LN blocks, final LN, head
 inline void ln_fwd(maexp_learner *h, cudaStream_t st, const float *params, const float *x, long long x_row, long long gX,
                    long long wo, long long bo, float *y, float *m, float *r, int rows, long long rows_max) {
@@ -1316,7 +1277,8 @@ void da3_backward(maexp_learner *h, cudaStream_t st, bool with_head = true) {
 int decode_canvas(maexp_learner *h, cudaStream_t st, const float *obs, const int8_t *pos, int B, int pass, int only_area);
 
 // DA6 (customs/da6.py:98-126): relative stack on the area canvas -> LN -> fc1 -> token 0 of the local stack -> LN -> drl_head
-int da6_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, const int8_t *pos, int B, int pass) {
+int da6_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, const int8_t *pos, int B, int pass,
+                bool with_head = true) {
     const long long P = h->P, Bmax = h->B, XY = (long long)h->X * h->Y;
     const int E = h->E_, G = h->G;
     if (decode_canvas(h, st, obs, pos, B, pass, 1)) return -1;
@@ -1325,15 +1287,16 @@ int da6_forward(maexp_learner *h, cudaStream_t st, const float *params, const fl
          Bmax * E, P);
     vit_forward(h, st, params, h->vloc, obs, h->cfg.obs_stride, (long long)h->V * h->V, (long long)B * h->cfg.obs_stride, B, pass,
                 h->sal2[pass]);
-    gemm(st, G, h->vloc.a[pass].nf, params + h->o_hw, h->vloc.a[pass].q, params + h->o_hb, B, h->A, E, E, 1, 1, E, h->A, 1,
-         Bmax * E, P, Bmax * h->A, P);
+    if (with_head)
+        gemm(st, G, h->vloc.a[pass].nf, params + h->o_hw, h->vloc.a[pass].q, params + h->o_hb, B, h->A, E, E, 1, 1, E, h->A, 1,
+             Bmax * E, P, Bmax * h->A, P);
     return 0;
 }
 
-void da6_backward(maexp_learner *h, cudaStream_t st) {
+void da6_backward(maexp_learner *h, cudaStream_t st, bool with_head = true) {
     const int G = h->G, B = h->B, E = h->E_;
     const long long P = h->P, BE = (long long)B * E;
-    head_backward(h, st, h->vloc.a[0].nf);
+    if (with_head) head_backward(h, st, h->vloc.a[0].nf);  // else da_dnf already holds d LN(token 0) (IQN head)
     vit_backward(h, st, h->vloc, h->d_sal2, 0);
     // fc1: sal2 = nf_rel W^T + b
     gemm(st, G, h->d_sal2, h->vrel.a[0].nf, h->grads + h->o_f1w, nullptr, E, E, B, 1, E, E, 1, E, 1, BE, BE, P, 0);
@@ -1411,7 +1374,7 @@ int rel_forward(maexp_learner *h, cudaStream_t st, const float *params, const fl
 }
 
 int merged_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, const int8_t *pos, int B, int pass,
-                   float **q_out) {
+                   float **q_out, bool with_head = true) {
     const long long Bmax = h->B, P = h->P;
     if (rel_forward(h, st, params, obs, pos, B, pass)) return -1;
     if (!h->merged_da3) {
@@ -1432,13 +1395,14 @@ int merged_forward(maexp_learner *h, cudaStream_t st, const float *params, const
         cudaMemcpy2DAsync(h->feat[pass] + (size_t)g * Bmax * Dt + Dr, sizeof(float) * Dt, h->vloc.a[pass].nf + (size_t)g * Bmax * E,
                           sizeof(float) * E, sizeof(float) * E, B, cudaMemcpyDeviceToDevice, st);
     }
+    if (!with_head) return 0;  // MergedDA3_IQN: h->feat[pass] is the state embedding of the IQN head
     gemm(st, h->G, h->feat[pass], params + h->o_hw, h->vloc.a[pass].q, params + h->o_hb, B, h->A, Dt, Dt, 1, 1, Dt, h->A, 1, Bmax * Dt, P,
          Bmax * h->A, P);
     *q_out = h->vloc.a[pass].q;
     return 0;
 }
 
-void merged_backward(maexp_learner *h, cudaStream_t st) {
+void merged_backward(maexp_learner *h, cudaStream_t st, bool with_head = true) {
     const int G = h->G, B = h->B, A = h->A;
     const long long P = h->P;
     if (!h->merged_da3) {
@@ -1454,10 +1418,12 @@ void merged_backward(maexp_learner *h, cudaStream_t st) {
         return;
     }
     const int E = h->E_, Dr = h->Drel, Dt = Dr + E;
-    const float *dq = h->d_out[0];
-    gemm(st, G, dq, h->feat[0], h->grads + h->o_hw, nullptr, A, Dt, B, 1, A, Dt, 1, Dt, 1, (long long)B * A, (long long)B * Dt, P, 0);
-    colsum(st, G, h->ones, dq, h->grads + h->o_hb, B, A, (long long)B * A, P);
-    gemm(st, G, dq, h->online + h->o_hw, h->d_feat, nullptr, B, Dt, A, A, 1, Dt, 1, Dt, 1, (long long)B * A, P, (long long)B * Dt, 0);
+    if (with_head) {  // else d_feat already holds the gradient of the concatenated embedding (IQN head)
+        const float *dq = h->d_out[0];
+        gemm(st, G, dq, h->feat[0], h->grads + h->o_hw, nullptr, A, Dt, B, 1, A, Dt, 1, Dt, 1, (long long)B * A, (long long)B * Dt, P, 0);
+        colsum(st, G, h->ones, dq, h->grads + h->o_hb, B, A, (long long)B * A, P);
+        gemm(st, G, dq, h->online + h->o_hw, h->d_feat, nullptr, B, Dt, A, A, 1, Dt, 1, Dt, 1, (long long)B * A, P, (long long)B * Dt, 0);
+    }
     for (int g = 0; g < G; ++g) {  // split the concatenated gradient
         cudaMemcpy2DAsync(h->d_relsal + (size_t)g * B * Dr, sizeof(float) * Dr, h->d_feat + (size_t)g * B * Dt, sizeof(float) * Dt,
                           sizeof(float) * Dr, B, cudaMemcpyDeviceToDevice, st);
@@ -1468,6 +1434,72 @@ void merged_backward(maexp_learner *h, cudaStream_t st) {
     mlp_backward(h, st, h->rse, rin, h->d_relsal, h->rse_h[0], h->d_h, h->d_relflat, 0);
     gtrunk_backward(h, st, h->gt_rel, h->d_relflat, Dr, 0, (long long)B * Dr);
     da3_backward(h, st, /*with_head=*/false);
+}
+
+// ---- IQN head on a state embedding psi [G][B][D] (customs/iqn.py:96-136, customs/da3_iqn.py:26-84).  The embedding comes
+//      from conv + state_embedder (IQN), the local transformer (DA3_IQN), relative embedder ++ local transformer
+//      (MergedDA3_IQN) or the two-stage transformer (DA6_IQN)
+int iqn_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, const int8_t *pos, int B,
+                const float *taus, int nq, int per_sample, int pass) {
+    maexp_learner::Acts &a = h->acts[pass];
+    maexp_learner::IqnActs &q = h->iq[pass];
+    const int G = h->G, D = h->D;
+    const long long P = h->P, Bmax = h->B, R = h->rows_max;
+    const float *psi = q.psi;
+    if (h->da6) {
+        if (da6_forward(h, st, params, obs, pos, B, pass, /*with_head=*/false)) return -1;
+        psi = h->vloc.a[pass].nf;
+    } else if (h->merged_da3) {
+        float *unused = nullptr;
+        if (merged_forward(h, st, params, obs, pos, B, pass, &unused, /*with_head=*/false)) return -1;
+        psi = h->feat[pass];
+    } else if (h->da3) {
+        da3_forward(h, st, params, obs, B, pass, /*with_head=*/false);
+        psi = h->vloc.a[pass].nf;
+    } else {
+        trunk_forward(h, st, params, obs, B, a);
+        const MlpIn se_in = {a.flat, D, Bmax * D, B, Bmax, D};
+        mlp_forward(h, st, params, h->se, se_in, q.se_h, q.psi);  // state_embedder
+    }
+    const int rows = B * nq;
+    iqn_cos_kernel<<<grid1d((long long)rows * h->ncos, G), 256, 0, st>>>(taus, q.cosf, B, nq, h->ncos, per_sample,
+                                                                         per_sample ? (long long)B * nq : (long long)nq,
+                                                                         R * h->ncos);
+    // phi = relu(cos W^T + b)   (cosine_net.net.0 + ReLU, customs/iqn.py:24)
+    gemm(st, G, q.cosf, params + h->o_cw, q.phi, params + h->o_cb, rows, D, h->ncos, h->ncos, 1, 1, h->ncos, D, 1,
+         R * h->ncos, P, R * D, P, /*relu=*/1);
+    iqn_hadamard_fwd_kernel<<<grid1d((long long)rows * D, G), 256, 0, st>>>(psi, q.phi, q.e, B, nq, D, Bmax * D, R * D);
+    const MlpIn e_in = {q.e, D, R * D, rows, R, D};
+    for (int k = 0; k < 2; ++k) mlp_forward(h, st, params, h->heads[k], e_in, q.hrow[k], q.out[k]);
+    return 0;
+}
+
+void iqn_backward(maexp_learner *h, cudaStream_t st, int nq) {
+    maexp_learner::Acts &a = h->acts[0];
+    maexp_learner::IqnActs &q = h->iq[0];
+    const int G = h->G, B = h->B, D = h->D, rows = B * nq;
+    const long long P = h->P, R = h->rows_max;
+    const float *psi = h->merged_da3 ? h->feat[0] : h->da3 ? h->vloc.a[0].nf : q.psi;
+    const MlpIn e_in = {q.e, D, R * D, rows, R, D};
+    for (int k = 0; k < 2; ++k) mlp_backward(h, st, h->heads[k], e_in, h->d_out[k], q.hrow[k], h->d_hrow, h->d_e, k > 0);
+    // h->d_psi aliases the buffer the embedding's producer reads its output gradient from (set in create)
+    iqn_hadamard_bwd_kernel<<<grid1d((long long)B * D, G), 256, 0, st>>>(h->d_e, psi, q.phi, h->d_phi, h->d_psi, B, nq, D,
+                                                                         (long long)B * D, R * D);
+    // cosine net: dW[D,ncos] = dphi^T cos ; db = colsum(dphi)
+    gemm(st, G, h->d_phi, q.cosf, h->grads + h->o_cw, nullptr, D, h->ncos, rows, 1, D, h->ncos, 1, h->ncos, 1, R * D,
+         R * h->ncos, P, 0);
+    colsum(st, G, h->ones, h->d_phi, h->grads + h->o_cb, rows, D, R * D, P);
+    if (h->da6) {
+        da6_backward(h, st, /*with_head=*/false);
+    } else if (h->merged_da3) {
+        merged_backward(h, st, /*with_head=*/false);
+    } else if (h->da3) {
+        da3_backward(h, st, /*with_head=*/false);
+    } else {
+        const MlpIn se_in = {a.flat, D, (long long)B * D, B, B, D};
+        mlp_backward(h, st, h->se, se_in, h->d_psi, q.se_h, h->d_h, h->d_flat, 0);
+        trunk_backward(h, st);
+    }
 }
 
 }  // namespace
@@ -1484,12 +1516,16 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     h->cfg = *cfg;
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
     h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;
-    h->da6 = cfg->kind == MAEXP_LEARNER_DA6;
-    h->da3 = cfg->kind == MAEXP_LEARNER_DA3 || h->da6;  // da3: "has transformer stacks"
+    const int trunk = cfg->kind == MAEXP_LEARNER_IQN ? cfg->iqn_trunk : 0;  // MAEXP_IQN_TRUNK_*
+    if (trunk < 0 || trunk > MAEXP_IQN_TRUNK_DA6) { delete h; return fail("maexp_learner_create: unknown iqn_trunk"); }
+    h->da6 = cfg->kind == MAEXP_LEARNER_DA6 || trunk == MAEXP_IQN_TRUNK_DA6;
+    h->da3 = cfg->kind == MAEXP_LEARNER_DA3 || h->da6 || trunk != 0;  // da3: "has transformer stacks"
     h->area_mask = cfg->area_mask; h->X = cfg->size_x; h->Y = cfg->size_y;
     h->relative_conv = cfg->kind == MAEXP_LEARNER_DQN_CONV_MLP && cfg->area_mask == MAEXP_MASK_RELATIVE;
     h->merged_conv = cfg->kind == MAEXP_LEARNER_DQN_CONV_MLP && cfg->area_mask == MAEXP_MASK_MERGED;
-    h->merged_da3 = h->da3 && !h->da6 && cfg->area_mask == MAEXP_MASK_MERGED;
+    h->merged_da3 = (cfg->kind == MAEXP_LEARNER_DA3 && cfg->area_mask == MAEXP_MASK_MERGED) || trunk == MAEXP_IQN_TRUNK_MERGED_DA3;
+    if (trunk == MAEXP_IQN_TRUNK_DA3 && cfg->area_mask != MAEXP_MASK_LOCAL) { delete h; return fail("maexp_learner_create: the DA3 IQN trunk reads the local view"); }
+    if (trunk == MAEXP_IQN_TRUNK_MERGED_DA3 && cfg->area_mask != MAEXP_MASK_MERGED) { delete h; return fail("maexp_learner_create: the MergedDA3 IQN trunk reads the merged view"); }
     const bool gmodel = h->relative_conv || h->merged_conv || h->merged_da3;
     if (h->da6 && (cfg->area_mask != MAEXP_MASK_MERGED || h->X < 4 || h->Y < 4)) { delete h; return fail("maexp_learner_create: DA6 reads the merged view (area_mask merged, size_x / size_y set)"); }
     if (cfg->area_mask != MAEXP_MASK_LOCAL && !gmodel && !h->da6) { delete h; return fail("maexp_learner_create: relative / merged views are implemented for conv_mlp (dqn) and da3 (merged)"); }
@@ -1542,7 +1578,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             s.Ht = hin / s.ps; s.Wt = win / s.ps; s.Tn = s.Ht * s.Wt + 1; s.K = cin * s.ps * s.ps;
         };
         set_stack(h->vloc, h->C, h->V, h->V, h->da6 ? cfg->local_patch_size : 1);
-        if (h->da6) set_stack(h->vrel, 1, h->X, h->Y, cfg->patch_size);
+        if (h->da6) set_stack(h->vrel, 1, h->X, h->Y, cfg->relative_patch_size);
         h->Tn = h->da6 && h->vrel.Tn > h->vloc.Tn ? h->vrel.Tn : h->vloc.Tn;
         if (h->E_ < 1 || h->heads_ < 1 || h->E_ % h->heads_ || h->E_ / h->heads_ > kMaxHeadDim || h->Tn > kMaxTokens || h->Fm < 1 ||
             h->vloc.Tn < 2 || (h->da6 && h->vrel.Tn < 2) ||
@@ -1564,7 +1600,17 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             }
         };
         // own parameters first, then submodules in registration order (customs/da3.py:33-60, customs/da6.py:40-96)
+        auto add_unused_parent = [&](bool with_saliency) {  // what DA3.__init__ / DA3_IQN.__init__ creates and a subclass never uses
+            const int ps = cfg->patch_size > 0 ? cfg->patch_size : 1;
+            if (with_saliency) add("saliency_vector", h->E_);
+            add("pos_embed", (long long)((h->X / ps) * (h->Y / ps) + 1) * h->E_);
+            add("patch_embed.proj.weight", (long long)h->E_ * h->C * ps * ps);
+            add("patch_embed.proj.bias", h->E_);
+            maexp_learner::VitStack unused;
+            add_blocks(unused, "");
+        };
         if (h->da6) {
+            if (h->iqn) add_unused_parent(false);  // DA6_IQN(DA3_IQN) re-assigns saliency_vector (da6_iqn.py:25-28,66)
             h->vrel.o_sal = add("saliency_vector", h->E_);
             h->vrel.o_pos = add("relative_pos_embed", (long long)h->vrel.Tn * h->E_);
             h->vloc.o_pos = add("local_pos_embed", (long long)h->vloc.Tn * h->E_);
@@ -1576,15 +1622,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             add_blocks(h->vloc, "local_");
         } else {
         const std::string lp = h->merged_da3 ? "local_" : "";
-        if (h->merged_da3) {  // parameters the parent DA3.__init__ creates and MergedDA3 never uses (da3.py:99-103)
-            const int ps = cfg->patch_size > 0 ? cfg->patch_size : 1;
-            add("saliency_vector", h->E_);
-            add("pos_embed", (long long)((h->X / ps) * (h->Y / ps) + 1) * h->E_);
-            add("patch_embed.proj.weight", (long long)h->E_ * h->C * ps * ps);
-            add("patch_embed.proj.bias", h->E_);
-            maexp_learner::VitStack unused;
-            add_blocks(unused, "");
-        }
+        if (h->merged_da3) add_unused_parent(true);  // da3.py:99-103, da3_iqn.py:214-218
         h->vloc.o_sal = add(lp + "saliency_vector", h->E_);
         h->vloc.o_pos = add(lp + "pos_embed", (long long)h->vloc.Tn * h->E_);
         h->vloc.o_pew = add(lp + "patch_embed.proj.weight", (long long)h->E_ * h->C);
@@ -1597,7 +1635,8 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             set_trunk(h->gt_rel, "relative_conv", 1, h->X, h->Y);
             h->Drel = h->gt_rel.D; h->Dloc = 0;
         }
-        h->o_hw = add("drl_head.weight", (long long)h->A * (h->E_ + h->Drel)); h->o_hb = add("drl_head.bias", h->A);
+        if (h->iqn) h->D = h->E_ + h->Drel;  // embedding_dim of IQN_Head (da3_iqn.py:142-144,263-265)
+        else { h->o_hw = add("drl_head.weight", (long long)h->A * (h->E_ + h->Drel)); h->o_hb = add("drl_head.bias", h->A); }
     } else if (gmodel) {
         // layout set above
     } else if (h->has_conv) {
@@ -1629,6 +1668,12 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         h->rse = h->heads.back();
         h->heads.pop_back();
         h->D = keepD;
+    }
+    if (h->da3 && h->iqn) {  // IQN_Head (da3_iqn.py:26-40)
+        h->o_cw = add("drl_head.cosine_net.net.0.weight", (long long)h->D * h->ncos);
+        h->o_cb = add("drl_head.cosine_net.net.0.bias", h->D);
+        add_head("drl_head.fc_V", 1);
+        add_head("drl_head.fc_A", h->A);
     } else if (h->da3) {
         // no MLP heads: the drl_head is part of the layout above
     } else if (h->relative_conv || h->merged_conv) {
@@ -1736,6 +1781,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         rc |= lalloc(h, &h->d_e, G * R * h->D);
         rc |= lalloc(h, &h->d_phi, G * R * h->D);
         rc |= lalloc(h, &h->d_psi, G * B * h->D);
+
         rc |= lalloc(h, &h->d_hrow, G * R * h->H);
     }
     rc |= lalloc(h, &h->d_h, G * B * h->H);
@@ -1780,6 +1826,8 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             rc |= lalloc(h, &h->d_relflat, G * B * h->Drel);
         }
     }
+    if (h->iqn && h->da3)  // the embedding's producer reads its output gradient from its own buffer
+        h->d_psi = h->merged_da3 ? h->d_feat : h->da_dnf;
     rc |= lalloc(h, &h->per_sample, G * B);
     rc |= lalloc(h, &h->m_scratch, G * B * 128);
     rc |= lalloc(h, &h->q_tmp, G * B * h->A);
@@ -1943,7 +1991,7 @@ int maexp_learner_q_values_iqn(maexp_learner *h, const float *obs, int batch, in
     if (batch < 1 || batch > h->B) return fail("maexp_learner_q_values_iqn: batch must be in 1..batch_size");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     g_splitk_ws = h->splitk_ws;
-    iqn_forward(h, st, use_target ? h->target : h->online, obs, batch, tau_sel, h->Nq, /*per_sample=*/0, 1);
+    if (iqn_forward(h, st, use_target ? h->target : h->online, obs, h->pos, batch, tau_sel, h->Nq, /*per_sample=*/0, 1)) return -1;
     iqn_q_kernel<<<dim3((batch + 127) / 128, h->G), 128, 0, st>>>(h->iq[1].out[0], h->iq[1].out[1], batch, h->A, h->Nq,
                                                                   h->rows_max, h->rows_max * h->A, q_out);
     MAEXP_CUDA_L(cudaGetLastError());
@@ -1960,9 +2008,9 @@ int maexp_learner_grads_iqn(maexp_learner *h, const float *obs, const float *nex
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int G = h->G, B = h->B;
     g_splitk_ws = h->splitk_ws;
-    iqn_forward(h, st, h->online, obs, B, taus, h->Nq, 1, 0);
-    iqn_forward(h, st, h->online, next_obs, B, tau_sel, h->Nq, 0, 1);
-    iqn_forward(h, st, h->target, next_obs, B, tau_dashes, h->Nd, 1, 2);
+    if (iqn_forward(h, st, h->online, obs, h->pos, B, taus, h->Nq, 1, 0)) return -1;
+    if (iqn_forward(h, st, h->online, next_obs, h->next_pos, B, tau_sel, h->Nq, 0, 1)) return -1;
+    if (iqn_forward(h, st, h->target, next_obs, h->next_pos, B, tau_dashes, h->Nd, 1, 2)) return -1;
     IqnArgs p;
     p.v0 = h->iq[0].out[0]; p.a0 = h->iq[0].out[1];
     p.v1 = h->iq[1].out[0]; p.a1 = h->iq[1].out[1];

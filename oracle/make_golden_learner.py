@@ -46,7 +46,16 @@ def configs():
                relative_patch_size=3, local_patch_size=1)
     da6["agent_type"] = "attention"
     da6["objects_channel"], da6["agents_channel"] = False, False
-    return {"da6": (da6, [4, *SIZE]),"relative_conv_mlp": (rel, [4, *SIZE]), "merged_conv_mlp": (mconv, [4, *SIZE]), "merged_da3": (mda3, [4, *SIZE]),
+    iq = dict(embed_dim=32, block_loop=1, mlp_ratio=4.0, attention="soft", af_lambd=0.5, num_quantiles=4, num_quantiles_dash=4,
+              num_cosines=4, relative_patch_size=5, local_patch_size=1)
+    def attn_iqn(mask, name):
+        c = view(mask, name, "da3_iqn", **iq)
+        c["agent_type"] = "attention"
+        c["objects_channel"], c["agents_channel"], c["destination_channel"] = False, False, False
+        return c
+    return {"da3_iqn": (attn_iqn("local", "da3_iqn"), [4, VIEW, VIEW]), "merged_da3_iqn": (attn_iqn("merged", "da3_iqn"), [4, *SIZE]),
+            "da6_iqn": (attn_iqn("merged", "da6_iqn"), [4, *SIZE]),
+            "da6": (da6, [4, *SIZE]),"relative_conv_mlp": (rel, [4, *SIZE]), "merged_conv_mlp": (mconv, [4, *SIZE]), "merged_da3": (mda3, [4, *SIZE]),
             "da3": (da3, [3, 7, 7]), "dqn_conv_mlp": (dqn, [7, 7, 7]), "c51": (c5.merged_with(batch_size=B), [3, 7, 7]),
             "qr": (c3.merged_with(batch_size=B), [3, 7, 7]), "iqn": (iqn, [3, 7, 7])}
 
@@ -78,7 +87,13 @@ def main():
     for kind, (cfg, shape) in configs().items():
         torch.manual_seed(921)
         brain = generate_brain(config=rr.to_dictconfig(cfg), obs_shape=shape, act_size=4)
-        masked = kind in ("relative_conv_mlp", "merged_conv_mlp", "merged_da3", "da6")
+        masked = kind in ("relative_conv_mlp", "merged_conv_mlp", "merged_da3", "da6", "merged_da3_iqn", "da6_iqn")
+        is_iqn = kind in ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn")
+        with torch.no_grad():  # zero-initialised embeddings: perturb so the fixtures exercise them
+            for name in {"da3_iqn": ("saliency_vector", "pos_embed"), "merged_da3_iqn": ("local_saliency_vector", "local_pos_embed"),
+                         "da6_iqn": ("saliency_vector", "relative_pos_embed", "local_pos_embed")}.get(kind, ()):
+                p_ = getattr(brain.network, name)
+                p_.add_(0.02 * torch.randn_like(p_))
         if kind == "da6":  # zero-initialised embeddings (da6.py:52-66)
             with torch.no_grad():
                 for name in ("saliency_vector", "relative_pos_embed", "local_pos_embed"):
@@ -109,7 +124,10 @@ def main():
         next_state = (lambda: ref_state(batch["next_obs"], batch["next_pos"])) if masked else \
             (lambda: {"local": batch["next_obs"].clone()})
         with torch.no_grad():
-            if masked:
+            if is_iqn and kind != "iqn":
+                tau0 = torch.rand(1, 4)
+                q0 = brain.network(state(), external_taus=tau0)
+            elif masked:
                 q0 = brain.network(state())
             elif kind == "c51":
                 from core.agents.models.customs.categorical_dqn import ApplySoftmax
@@ -132,7 +150,7 @@ def main():
             drawn.append(t.clone())
             return t
         for _ in range(2):
-            torch.rand = recording_rand if kind == "iqn" else real_rand
+            torch.rand = recording_rand if is_iqn else real_rand
             out = brain.learn(state(), batch["actions"].clone(), batch["rewards"].clone(),
                               batch["dones"].clone(), next_state())
             torch.rand = real_rand
@@ -142,7 +160,7 @@ def main():
         arrays.update({"target/" + k: v.numpy() for k, v in tgt.items()})
         arrays.update({"final/" + k: v.numpy() for k, v in final.items()})
         arrays.update({"batch/" + k: v.numpy() for k, v in batch.items()})
-        if kind == "iqn":  # per learn call: taus [B,N], tau_sel [1,N], tau_dashes [B,N']
+        if is_iqn:  # per learn call: taus [B,N], tau_sel [1,N], tau_dashes [B,N']
             assert len(drawn) == 6
             for u in range(2):
                 arrays[f"taus/{u}/taus"], arrays[f"taus/{u}/sel"], arrays[f"taus/{u}/dash"] = (

@@ -11,9 +11,10 @@ from oracle.torch_learner import TorchLearner
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KINDS = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLDEN, "learner_*.npz")))
 ATOMS = {"dqn_conv_mlp": 1, "c51": 51, "qr": 100, "iqn": 4, "da3": 1, "da6": 1}
+IQN_KINDS = ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn")  # fixture name == state-embedding trunk of the IQN head
 # fixtures of the relative / merged views -> (network kind, attention heads)
 MASKED = {"relative_conv_mlp": ("dqn_conv_mlp", 4), "merged_conv_mlp": ("dqn_conv_mlp", 4), "merged_da3": ("da3", 2),
-          "da6": ("da6", 2)}
+          "da6": ("da6", 2), "merged_da3_iqn": ("iqn", 2), "da6_iqn": ("iqn", 2)}
 
 
 def load(kind):
@@ -22,7 +23,7 @@ def load(kind):
     fix = {"init": part("init/"), "target": part("target/"), "final": part("final/"), "batch": part("batch/"),
            "losses": z["losses"], "q0": torch.from_numpy(z["q0"]), "gamma": float(z["gamma"]),
            "shape": [int(v) for v in z["shape"]], "area_mask": str(z["area_mask"])}
-    if kind == "iqn":  # the fractions the reference drew: per update (taus, tau_dashes, tau_sel), and q0's tau
+    if kind in IQN_KINDS:  # the fractions the reference drew: per update (taus, tau_dashes, tau_sel), and q0's tau
         fix["taus"] = [(torch.from_numpy(z[f"taus/{u}/taus"]), torch.from_numpy(z[f"taus/{u}/dash"]),
                         torch.from_numpy(z[f"taus/{u}/sel"])) for u in range(2)]
         fix["tau0"] = torch.from_numpy(z["tau0"])
@@ -30,9 +31,10 @@ def load(kind):
 
 
 def make_oracle(kind, fix, sd=None, target=None):
-    net, heads = MASKED.get(kind, (kind, 4))
+    net, heads = MASKED.get(kind, ("iqn", 2) if kind == "da3_iqn" else (kind, 4))
     o = TorchLearner(net, sd or fix["init"], 4, fix["gamma"], 1e-3, 0.99, 1e-8, num_atoms=ATOMS[net],
-                     area_mask=fix["area_mask"], size=fix["shape"][1:], num_heads=heads)
+                     area_mask=fix["area_mask"], size=fix["shape"][1:], num_heads=heads,
+                     trunk=kind if kind in IQN_KINDS else "iqn")
     o.target = {k: v.clone() for k, v in (target or fix["target"]).items()}
     return o
 
@@ -49,11 +51,11 @@ def test_torch_oracle_matches_reference_brain(kind):
     fix = load(kind)
     o, b = make_oracle(kind, fix), fix["batch"]
     obs, next_obs = oracle_inputs(fix, b)
-    q0 = o.q_values_iqn(obs, fix["tau0"]) if kind == "iqn" else o.q_values(obs)
+    q0 = o.q_values_iqn(obs, fix["tau0"]) if kind in IQN_KINDS else o.q_values(obs)
     assert torch.allclose(q0, fix["q0"], rtol=1e-6, atol=1e-6)
     for u, want in enumerate(fix["losses"]):
         loss, _ = o.learn(obs, next_obs, b["actions"], b["rewards"], b["dones"],
-                          taus=fix["taus"][u] if kind == "iqn" else None)
+                          taus=fix["taus"][u] if kind in IQN_KINDS else None)
         assert abs(float(loss) - want) <= 1e-6 * max(1.0, abs(want)), (float(loss), want)
     for k, v in fix["final"].items():
         assert torch.allclose(o.sd[k].detach(), v, rtol=1e-5, atol=1e-6), k

@@ -11,7 +11,7 @@ import torch
 from maexp_b200.config import Config, baseline_config
 from oracle.make_golden_learner import configs as golden_configs
 from oracle.torch_learner import TorchLearner
-from tests.test_learner_golden import ATOMS, KINDS, MASKED, load, make_oracle, oracle_inputs
+from tests.test_learner_golden import ATOMS, IQN_KINDS, KINDS, MASKED, load, make_oracle, oracle_inputs
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
@@ -49,10 +49,10 @@ def test_cuda_learner_matches_reference_fixture(kind):
     if kind in MASKED:
         batch["pos"] = b["pos"].to(torch.int8)[None].contiguous().cuda()
         batch["next_pos"] = b["next_pos"].to(torch.int8)[None].contiguous().cuda()
-    q = g.q_values(batch["obs"], tau_sel=fix["tau0"].cuda() if kind == "iqn" else None, pos=batch.get("pos")).cpu()[0]
+    q = g.q_values(batch["obs"], tau_sel=fix["tau0"].cuda() if kind in IQN_KINDS else None, pos=batch.get("pos")).cpu()[0]
     assert rel_err(q, fix["q0"]) < RTOL
     for u, want in enumerate(fix["losses"]):
-        if kind == "iqn":
+        if kind in IQN_KINDS:
             t, d, sel = fix["taus"][u]
             batch.update(taus=t[None].contiguous().cuda(), tau_dashes=d[None].contiguous().cuda(), tau_sel=sel.contiguous().cuda())
         loss = float(g.learn(batch).cpu()[0])
@@ -68,7 +68,8 @@ def test_cuda_learner_matches_reference_fixture(kind):
 
 
 @pytest.mark.parametrize("kind,B", [("dqn_conv_mlp", 32), ("c51", 256), ("qr", 256), ("iqn", 256), ("da3", 32),
-                                    ("relative_conv_mlp", 32), ("merged_conv_mlp", 32), ("merged_da3", 32), ("da6", 32)])
+                                    ("relative_conv_mlp", 32), ("merged_conv_mlp", 32), ("merged_da3", 32), ("da6", 32),
+                                    ("da3_iqn", 32), ("merged_da3_iqn", 32), ("da6_iqn", 32)])
 def test_cuda_learner_group_matches_torch_oracle(kind, B):
     """G independent networks with different weights and batches, BASELINE batch sizes."""
     G = 3
@@ -103,19 +104,19 @@ def test_cuda_learner_group_matches_torch_oracle(kind, B):
         batch["pos"] = torch.stack([b["pos"] for b in batches]).to(torch.int8).cuda()
         batch["next_pos"] = torch.stack([b["next_pos"] for b in batches]).to(torch.int8).cuda()
     taus = None
-    if kind == "iqn":
+    if kind in IQN_KINDS:
         taus = [(torch.rand((B, 4), generator=gen), torch.rand((B, 4), generator=gen), torch.rand((1, 4), generator=gen))
                 for _ in range(G)]
         batch.update(taus=torch.stack([t[0] for t in taus]).cuda(), tau_dashes=torch.stack([t[1] for t in taus]).cuda(),
                      tau_sel=torch.cat([t[2] for t in taus]).cuda())
         for a in range(G):
             oracles[a].taus = taus[a]
-        q = g.q_values(batch["obs"], tau_sel=batch["tau_sel"]).cpu()
+        q = g.q_values(batch["obs"], tau_sel=batch["tau_sel"], pos=batch.get("pos")).cpu()
     else:
         q = g.q_values(batch["obs"], pos=batch.get("pos")).cpu()
     ins = [oracle_inputs(fix, b) for b in batches]
     for a in range(G):
-        want_q = oracles[a].q_values_iqn(ins[a][0], taus[a][2]) if kind == "iqn" else oracles[a].q_values(ins[a][0])
+        want_q = oracles[a].q_values_iqn(ins[a][0], taus[a][2]) if kind in IQN_KINDS else oracles[a].q_values(ins[a][0])
         assert rel_err(q[a], want_q) < RTOL
     # gradients of the first update, then two full updates
     loss = g.grads(batch).cpu()
