@@ -169,6 +169,8 @@ KernelFn pick_kernel(int V, int epw, int noise, int nspec) {
     return nullptr;
 }
 
+inline bool misaligned_obs(const void *ptr) { return ptr && (reinterpret_cast<uintptr_t>(ptr) & 15); }
+
 int launch(maexp_env *h, uint32_t tick, int force_reset, const uint8_t *env_mask, const int8_t *actions,
            const uint8_t *order, const float *noise_tape, const maexp_obs_out *out, cudaStream_t stream) {
     EnvParams p = h->p;
@@ -180,6 +182,13 @@ int launch(maexp_env *h, uint32_t tick, int force_reset, const uint8_t *env_mask
     p.noise_tape = noise_tape;
     if (out) p.out = *out;
     else memset(&p.out, 0, sizeof(p.out));
+    if ((p.N & 7) == 0) {  // the kernel writes eight agents per vector store
+        auto misaligned = [](const void *ptr, size_t a) { return ptr && (reinterpret_cast<uintptr_t>(ptr) & (a - 1)); };
+        if (misaligned(p.out.rewards, 16) || misaligned(p.out.dones, 8) || misaligned(p.out.positions, 16) ||
+            misaligned(p.out.actions_taken, 8))
+            return fail("maexp_env_step: rewards / positions must be 16-byte aligned, dones / actions_taken 8-byte aligned");
+    }
+    if (misaligned_obs(p.out.obs) || misaligned_obs(p.out.obs_rel)) return fail("maexp_env_step: obs slots must be 16-byte aligned");
     h->fn<<<h->grid_ctas, kWarpsPerCta * 32, h->smem_bytes, stream>>>(p);
     MAEXP_CUDA(cudaGetLastError());
     return 0;

@@ -618,10 +618,52 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             if (mean) shared = (float)((double)sum / (double)N);
             else shared = (rew_pos & ~rew_neg) ? 1.0f : ((rew_neg == ((1u << N) - 1u)) ? -1.0f : 0.0f);
         }
-        for (int k = 0; k < N; ++k) {
+        auto reward_of = [&](int k) -> float {
             float r = (rew_neg >> k) & 1u ? -1.0f : ((rew_pos >> k) & 1u ? 1.0f : 0.0f);
             if (p.reward_mode != MAEXP_REWARD_DEFAULT) r = shared;
-            if (is_reset) r = 0.0f;
+            return is_reset ? 0.0f : r;
+        };
+        if ((N & 7) == 0) {
+            // eight agents at a time: every per-agent output row of this env is an aligned 8 / 16 / 32-byte run
+            for (int k0 = 0; k0 < N; k0 += 8) {
+                const size_t o = (size_t)env * N + k0;
+                uint32_t pw[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    pw[j] = (uint32_t)mypos[(k0 + 2 * j) * EPW] | ((uint32_t)mypos[(k0 + 2 * j + 1) * EPW] << 16);
+                *reinterpret_cast<uint4 *>(p.pos + o) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                if (p.out.rewards) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.out.rewards + o);
+                    dst[0] = make_float4(reward_of(k0), reward_of(k0 + 1), reward_of(k0 + 2), reward_of(k0 + 3));
+                    dst[1] = make_float4(reward_of(k0 + 4), reward_of(k0 + 5), reward_of(k0 + 6), reward_of(k0 + 7));
+                }
+                if (p.out.dones) {
+                    const uint32_t d = done_bits >> k0;  // bit k -> byte k
+                    const uint32_t lo = (d & 1u) | ((d & 2u) << 7) | ((d & 4u) << 14) | ((d & 8u) << 21);
+                    const uint32_t hi = ((d >> 4) & 1u) | (((d >> 4) & 2u) << 7) | (((d >> 4) & 4u) << 14) | (((d >> 4) & 8u) << 21);
+                    *reinterpret_cast<uint2 *>(p.out.dones + o) = make_uint2(lo, hi);
+                }
+                if (p.out.positions) {  // int8 (x, y) pairs: the u16 cells already are x | y << 8
+                    *reinterpret_cast<uint4 *>(p.out.positions + o * 2) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                }
+                if (p.out.actions_taken) {
+                    uint32_t a[2] = {0u, 0u};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t v = is_reset ? 0xFFu : (uint32_t)((acts_taken >> (3 * (k0 + j))) & 7);
+                        a[j >> 2] |= v << (8 * (j & 3));
+                    }
+                    *reinterpret_cast<uint2 *>(p.out.actions_taken + o) = make_uint2(a[0], a[1]);
+                }
+                if (p.out.destination)
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = k0 + j;
+                        p.out.destination[o + j] = (uint8_t)(p.random_dest ? nib(dsel, k) : (k < p.M ? k : p.M - 1));
+                    }
+            }
+        } else {
+        for (int k = 0; k < N; ++k) {
+            const float r = reward_of(k);
             if (p.out.rewards) p.out.rewards[(size_t)env * N + k] = r;
             if (p.out.dones) p.out.dones[(size_t)env * N + k] = (uint8_t)((done_bits >> k) & 1u);
             if (p.out.positions) {
@@ -634,6 +676,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                 p.out.destination[(size_t)env * N + k] =
                     (uint8_t)(p.random_dest ? nib(dsel, k) : (k < p.M ? k : p.M - 1));
             p.pos[(size_t)env * N + k] = mypos[k * EPW];
+        }
         }
         if (p.out.was_reset) p.out.was_reset[env] = is_reset ? 1 : 0;
         p.step[env] = stepc;
