@@ -489,8 +489,33 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             float *const dst_rel = (p.merged && p.out.obs_rel) ? p.out.obs_rel + base : nullptr;
             const bool check = (NOISE != MAEXP_NOISE_NONE) || !all_on;
 
+            // per-element noise constants of quad q (the same for every env a lane visits): scale of the draw, threshold,
+            // and the +1 / -1 the flip noise wraps around channel 2 (flip_observation_noise.py:31,44)
+            struct QuadNoise { float scale[4], thr[4], pre[4]; };
+            auto quad_noise = [&](int q) {
+                QuadNoise n;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = q * 4 + j;
+                    const int c = k / VV, rem = k - c * VV, a = rem / V, b = rem - a * V;
+                    const int ring = min(min(min(a, b), min(V - 1 - a, V - 1 - b)), V / 2 - 1);
+                    const bool in = k < p.K;
+                    n.pre[j] = 0.0f;
+                    n.thr[j] = 0.0f;
+                    if constexpr (NOISE == MAEXP_NOISE_FLIP) {
+                        n.scale[j] = in ? p.flip_range[ring] : 0.0f;
+                        n.pre[j] = (in && c == 2) ? 1.0f : 0.0f;
+                    } else if constexpr (NOISE == MAEXP_NOISE_FLAT) {
+                        n.scale[j] = (in && c < 3) ? 0.03f : 0.0f;  // flat_observation_noise.py:28-34 (3 hard-coded channels)
+                    } else {
+                        n.scale[j] = in ? p.std_dist[ring] : 0.0f;
+                        n.thr[j] = p.noise_thr[ring];
+                    }
+                }
+                return n;
+            };
             // one quad (4 consecutive fp32 of the slot) of env e: table lookup, optional noise, 128-bit stores
-            auto emit = [&](int e, int q, uint32_t word, int sh, int lut_off) {
+            auto emit = [&](int e, int q, uint32_t word, int sh, int lut_off, const QuadNoise &qn) {
                 const float4 o = s_lut[lut_off + ((word >> sh) & 0xFu)];
                 const int off = e * env_stride + q * 4;
                 if constexpr (NOISE == MAEXP_NOISE_NONE) {
@@ -523,26 +548,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int k = k0 + j;
-                            if (k >= p.K) continue;
-                            const int c = k / VV, rem = k - c * VV, a = rem / V, b = rem - a * V;
-                            const int ring = min(min(min(a, b), min(V - 1 - a, V - 1 - b)), V / 2 - 1);
                             float x = v[j];
                             if constexpr (NOISE == MAEXP_NOISE_FLIP) {  // flip_observation_noise.py:28-46
-                                if (c == 2) x = __fadd_rn(x, 1.0f);
-                                x = __fadd_rn(x, __fmul_rn(dr[j], p.flip_range[ring]));
+                                x = __fadd_rn(x, qn.pre[j]);
+                                x = __fadd_rn(x, __fmul_rn(dr[j], qn.scale[j]));
                                 x = fabsf(rintf(x));
-                                if (c == 2) x = __fadd_rn(x, -1.0f);
-                            } else if constexpr (NOISE == MAEXP_NOISE_DIST) {  // dist_observation_noise.py:29-41
-                                x = __fadd_rn(x, __fmul_rn(dr[j], p.std_dist[ring]));
-                            } else if constexpr (NOISE == MAEXP_NOISE_THRESHOLD_DIST) {  // :53-75
-                                const float g = __fmul_rn(dr[j], p.std_dist[ring]), th = p.noise_thr[ring];
+                                x = __fadd_rn(x, -qn.pre[j]);
+                            } else if constexpr (NOISE == MAEXP_NOISE_THRESHOLD_DIST) {  // dist_observation_noise.py:53-75
+                                const float g = __fmul_rn(dr[j], qn.scale[j]), th = qn.thr[j];
                                 float n = 0.0f;
                                 if (g < -th) n = g;
                                 if (th < g) n = g;
                                 x = __fadd_rn(x, n);
-                            } else {  // flat_observation_noise.py:28-34 (3 hard-coded channels)
-                                if (c < 3) x = __fadd_rn(x, __fmul_rn(dr[j], 0.03f));
+                            } else {  // dist_observation_noise.py:29-41, flat_observation_noise.py:28-34
+                                x = __fadd_rn(x, __fmul_rn(dr[j], qn.scale[j]));
                             }
                             v[j] = x;
                         }
@@ -559,6 +578,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                 const int q = c * 32 + lane;
                 const int sh = (q & 7) * 4, lut_off = quad_class(q);
                 const uint32_t *wq = s_w + (q >> 3);
+                const QuadNoise qn = quad_noise(q);
                 if (NOISE == MAEXP_NOISE_NONE && !check && !dst_rel) {
                     // hot path: running pointers, ~12 instructions per 16 bytes stored
                     const float4 *lut = s_lut + lut_off;
@@ -568,10 +588,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                         store_quad(reinterpret_cast<float4 *>(dp), lut[(*wq >> sh) & 0xFu]);
                 } else if (!check) {
 #pragma unroll 4
-                    for (int e = 0; e < nenv; ++e) emit(e, q, wq[e * ws], sh, lut_off);
+                    for (int e = 0; e < nenv; ++e) emit(e, q, wq[e * ws], sh, lut_off, qn);
                 } else {
                     for (int e = 0; e < nenv; ++e)
-                        if (s_active[e] & 1) emit(e, q, wq[e * ws], sh, lut_off);
+                        if (s_active[e] & 1) emit(e, q, wq[e * ws], sh, lut_off, qn);
                 }
             }
             // (2) the qps % 32 trailing quads: lanes split as (env sub-index, quad) with a power-of-two quad
@@ -585,6 +605,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                     const int q = nfull * 32 + r;
                     const int sh = (q & 7) * 4, lut_off = quad_class(q);
                     const uint32_t *wq = s_w + esub * ws + (q >> 3);
+                    const QuadNoise qn = quad_noise(q);
                     if (NOISE == MAEXP_NOISE_NONE && !check && !dst_rel) {
                         const float4 *lut = s_lut + lut_off;
                         float *dp = dst + esub * env_stride + q * 4;
@@ -593,7 +614,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                             store_quad(reinterpret_cast<float4 *>(dp), lut[(*wq >> sh) & 0xFu]);
                     } else {
                         for (int e = esub; e < nenv; e += estep, wq += estep * ws)
-                            if (!check || (s_active[e] & 1)) emit(e, q, *wq, sh, lut_off);
+                            if (!check || (s_active[e] & 1)) emit(e, q, *wq, sh, lut_off, qn);
                     }
                 }
             }
