@@ -948,6 +948,11 @@ struct maexp_learner {
     std::vector<void *> allocs;
     float *online = nullptr, *target = nullptr, *grads = nullptr, *sq = nullptr;
     float *support = nullptr, *ones = nullptr, *splitk_ws = nullptr;
+    // the three forward passes of an update are independent: passes 1 and 2 run on side streams (fork / join with
+    // events, which also works under stream capture) with their own split-K workspaces
+    float *splitk_side[2] = {nullptr, nullptr};
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     // activations of the three passes (0: online(s) kept for backward, 1: online(s'), 2: target(s'))
     struct Acts {
         float *col1, *y1, *p, *col2, *y2, *flat, *h[2], *out[2];
@@ -1436,6 +1441,19 @@ void merged_backward(maexp_learner *h, cudaStream_t st, bool with_head = true) {
     da3_backward(h, st, /*with_head=*/false);
 }
 
+// fork: side stream k continues from `st`; returns the stream pass k+1 is issued on and selects its split-K workspace
+cudaStream_t fork_pass(maexp_learner *h, cudaStream_t st, int k, bool first) {
+    if (first) cudaEventRecord(h->ev_fork, st);
+    cudaStreamWaitEvent(h->side[k], h->ev_fork, 0);
+    g_splitk_ws = h->splitk_side[k];
+    return h->side[k];
+}
+void join_pass(maexp_learner *h, cudaStream_t st, int k) {
+    cudaEventRecord(h->ev_join[k], h->side[k]);
+    cudaStreamWaitEvent(st, h->ev_join[k], 0);
+    g_splitk_ws = h->splitk_ws;
+}
+
 // ---- IQN head on a state embedding psi [G][B][D] (customs/iqn.py:96-136, customs/da3_iqn.py:26-84).  The embedding comes
 //      from conv + state_embedder (IQN), the local transformer (DA3_IQN), relative embedder ++ local transformer
 //      (MergedDA3_IQN) or the two-stage transformer (DA6_IQN)
@@ -1705,6 +1723,12 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     rc |= lalloc(h, &h->support, 128);
     rc |= lalloc(h, &h->ones, 4);
     rc |= lalloc(h, &h->splitk_ws, (size_t)kSplitWorkspaceFloats);
+    for (int k = 0; k < 2; ++k) {
+        rc |= lalloc(h, &h->splitk_side[k], (size_t)kSplitWorkspaceFloats);
+        rc |= cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking) != cudaSuccess;
+        rc |= cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming) != cudaSuccess;
+    }
+    rc |= cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess;
     for (int k = 0; k < 3; ++k) {
         maexp_learner::Acts &a = h->acts[k];
         memset(&a, 0, sizeof(a));
@@ -1842,6 +1866,11 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
 
 void maexp_learner_destroy(maexp_learner *h) {
     if (!h) return;
+    for (int k = 0; k < 2; ++k) {
+        if (h->side[k]) { cudaStreamSynchronize(h->side[k]); cudaStreamDestroy(h->side[k]); }
+        if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (void *d : h->allocs) cudaFree(d);
     delete h;
 }
@@ -1934,8 +1963,11 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
     g_splitk_ws = h->splitk_ws;
     if (h->relative_conv || h->merged_conv || h->merged_da3) {  // TD target + MSE on the relative / merged models
         float *q0 = nullptr, *q2 = nullptr;
+        cudaStream_t s2 = fork_pass(h, st, 0, true);
+        if (merged_forward(h, s2, h->target, next_obs, h->next_pos, B, 2, &q2)) return -1;
+        g_splitk_ws = h->splitk_ws;
         if (merged_forward(h, st, h->online, obs, h->pos, B, 0, &q0)) return -1;
-        if (merged_forward(h, st, h->target, next_obs, h->next_pos, B, 2, &q2)) return -1;
+        join_pass(h, st, 0);
         dqn_loss_kernel<<<dim3((B + 127) / 128, G), 128, 0, st>>>(q0, q2, actions, rewards, dones, h->cfg.gamma, B, A, h->d_out[0],
                                                                   h->per_sample);
         mean_kernel<<<G, 256, 0, st>>>(h->per_sample, loss_out ? loss_out : h->q_tmp, B);
@@ -1944,13 +1976,17 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         return 0;
     }
     if (h->da3) {  // DA3Brain.learn: TD target + MSE on the attention network (da3_brain.py:58-89)
+        cudaStream_t s2 = fork_pass(h, st, 0, true);
         if (h->da6) {  // DA6Brain.learn (da6_brain.py:44-75): the same TD target + MSE
+            if (da6_forward(h, s2, h->target, next_obs, h->next_pos, B, 2)) return -1;
+            g_splitk_ws = h->splitk_ws;
             if (da6_forward(h, st, h->online, obs, h->pos, B, 0)) return -1;
-            if (da6_forward(h, st, h->target, next_obs, h->next_pos, B, 2)) return -1;
         } else {
+            da3_forward(h, s2, h->target, next_obs, B, 2);
+            g_splitk_ws = h->splitk_ws;
             da3_forward(h, st, h->online, obs, B, 0);
-            da3_forward(h, st, h->target, next_obs, B, 2);
         }
+        join_pass(h, st, 0);
         dqn_loss_kernel<<<dim3((B + 127) / 128, G), 128, 0, st>>>(h->vloc.a[0].q, h->vloc.a[2].q, actions, rewards, dones,
                                                                   h->cfg.gamma, B, A, h->d_out[0], h->per_sample);
         mean_kernel<<<G, 256, 0, st>>>(h->per_sample, loss_out ? loss_out : h->q_tmp, B);
@@ -1959,13 +1995,22 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         MAEXP_CUDA_L(cudaGetLastError());
         return 0;
     }
-    forward(h, st, h->online, obs, B, h->acts[0]);
-    forward(h, st, h->target, next_obs, B, h->acts[2]);
+    {
+        cudaStream_t s2 = fork_pass(h, st, 0, true);
+        forward(h, s2, h->target, next_obs, B, h->acts[2]);
+        if (h->dist) {  // double-DQN action selection by the online net
+            cudaStream_t s1 = fork_pass(h, st, 1, false);
+            forward(h, s1, h->online, next_obs, B, h->acts[1]);
+        }
+        g_splitk_ws = h->splitk_ws;
+        forward(h, st, h->online, obs, B, h->acts[0]);
+        join_pass(h, st, 0);
+        if (h->dist) join_pass(h, st, 1);
+    }
     if (!h->dist) {
         dqn_loss_kernel<<<dim3((B + 127) / 128, G), 128, 0, st>>>(h->acts[0].out[0], h->acts[2].out[0], actions, rewards,
                                                                   dones, h->cfg.gamma, B, A, h->d_out[0], h->per_sample);
     } else {
-        forward(h, st, h->online, next_obs, B, h->acts[1]);  // double-DQN action selection by the online net
         DistArgs p;
         p.v_s = h->acts[0].out[0]; p.a_s = h->acts[0].out[1];
         p.v_n = h->acts[1].out[0]; p.a_n = h->acts[1].out[1];
@@ -2008,9 +2053,14 @@ int maexp_learner_grads_iqn(maexp_learner *h, const float *obs, const float *nex
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int G = h->G, B = h->B;
     g_splitk_ws = h->splitk_ws;
+    cudaStream_t s1 = fork_pass(h, st, 0, true);
+    if (iqn_forward(h, s1, h->online, next_obs, h->next_pos, B, tau_sel, h->Nq, 0, 1)) return -1;
+    cudaStream_t s2 = fork_pass(h, st, 1, false);
+    if (iqn_forward(h, s2, h->target, next_obs, h->next_pos, B, tau_dashes, h->Nd, 1, 2)) return -1;
+    g_splitk_ws = h->splitk_ws;
     if (iqn_forward(h, st, h->online, obs, h->pos, B, taus, h->Nq, 1, 0)) return -1;
-    if (iqn_forward(h, st, h->online, next_obs, h->next_pos, B, tau_sel, h->Nq, 0, 1)) return -1;
-    if (iqn_forward(h, st, h->target, next_obs, h->next_pos, B, tau_dashes, h->Nd, 1, 2)) return -1;
+    join_pass(h, st, 0);
+    join_pass(h, st, 1);
     IqnArgs p;
     p.v0 = h->iq[0].out[0]; p.a0 = h->iq[0].out[1];
     p.v1 = h->iq[1].out[0]; p.a1 = h->iq[1].out[1];
