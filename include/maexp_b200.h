@@ -244,6 +244,13 @@ int maexp_learner_tensor(const maexp_learner *learner, int index, char *name, in
                          int64_t *count);
 /* device buffers [G, num_params] (MAEXP_BUF_SUPPORT: [128] atoms z_j or tau_hat_j, written by the host) */
 float *maexp_learner_buffer(maexp_learner *learner, int which);
+/* Attention weights computed by the LAST maexp_learner_q_values / maexp_learner_q_values_iqn call — what forward_attn of the
+ * attention models returns next to the Q-values (da3.py:64-88, da6.py:128-165, vit.py Block.forward_attn) and
+ * AttentionAgent.get_action_attns stacks (attention_agent.py:14-22).  stack 0 = local transformer, 1 = relative
+ * transformer (DA6 / DA6_IQN only); out fp32 [G, batch, heads, T, T], T = maexp_learner_attention_tokens(stack). */
+int maexp_learner_attention_tokens(const maexp_learner *learner, int stack);
+int maexp_learner_attention(maexp_learner *learner, int stack, int layer, int batch, float *out, void *stream);
+
 /* relative / merged models: index-space positions of the observing agent, int8 [G,B,2] for the state batch and for
  * the next-state batch (maexp_batch.pos / next_pos); used by the following grads / q_values calls */
 int maexp_learner_bind_positions(maexp_learner *learner, const int8_t *pos, const int8_t *next_pos);

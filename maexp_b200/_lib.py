@@ -89,6 +89,8 @@ SYMBOLS = {
     "maexp_learner_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64)]),
     "maexp_learner_buffer": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "maexp_learner_attention_tokens": (C.c_int, [C.c_void_p, C.c_int]),
+    "maexp_learner_attention": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "maexp_learner_bind_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "maexp_learner_sync_target": (C.c_int, [C.c_void_p, C.c_void_p]),
     "maexp_learner_q_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

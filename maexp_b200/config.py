@@ -54,6 +54,7 @@ _DEFAULTS = dict(
     buffer="default", synchronize_frequency=5, gamma=0.9,
     epsilon_initial=1.0, epsilon_end=0.05, epsilon_decay=0.999,
     agent_type="default", brain="da3_baseline", trainer="default", evaluator="default",
+    validate_epochs=1000, pretrained_weight_path=False,
     model=dict(name="conv_mlp", hidden_channels=[32], output_channel=64, hidden_kernels=[2, 2],
                hidden_strides=[1, 1], conv_afs=["max_pool2d", "max_pool2d"], af_kernels=[2, 2],
                af_strides=[2, 2], hidden_layer_sizes=[128], fc_afs=["relu"]),

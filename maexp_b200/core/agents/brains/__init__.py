@@ -219,6 +219,16 @@ class LearnerGroup:
                                                    C.c_void_p(q.data_ptr()), self._stream()))
         return q
 
+    def attention(self, batch, stack=0, layer=0):
+        """Attention weights [G, batch, heads, T, T] of the last q_values call (forward_attn of the attention models)."""
+        T = self.lib.maexp_learner_attention_tokens(self.h, stack)
+        if T < 0:
+            raise ValueError("no such transformer stack in this model")
+        heads = int(self.config.model.num_heads)
+        out = torch.empty((self.G, batch, heads, T, T), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.maexp_learner_attention(self.h, stack, layer, batch, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     def grads(self, batch):
         """Forward, TD target, loss [G] and gradients (kept in the library's grad buffer)."""
         p = lambda t: C.c_void_p(t.data_ptr())

@@ -100,7 +100,7 @@ class DefaultTrainer:
 
 
 def generate_trainer(config, environment, **kw):
-    if config.trainer == "default":
+    if config.trainer in ("default", "attention"):  # attention_trainer.py only adds attention-map logging
         return DefaultTrainer(config=config, environment=environment, **kw)
     logger.warning(f"Unexpected trainer is given. config.trainer: {config.trainer}")
     raise ValueError()

@@ -1954,6 +1954,24 @@ int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int us
     return 0;
 }
 
+int maexp_learner_attention_tokens(const maexp_learner *h, int stack) {
+    if (!h || !h->da3 || stack < 0 || stack > 1 || (stack == 1 && !h->da6)) return -1;
+    return stack ? h->vrel.Tn : h->vloc.Tn;
+}
+
+int maexp_learner_attention(maexp_learner *h, int stack, int layer, int batch, float *out, void *stream) {
+    if (!h || !out) return fail("maexp_learner_attention: null argument");
+    if (!h->da3) return fail("maexp_learner_attention: not an attention model");
+    if (stack < 0 || stack > 1 || (stack == 1 && !h->da6)) return fail("maexp_learner_attention: no such transformer stack");
+    if (layer < 0 || layer >= h->L_) return fail("maexp_learner_attention: no such block");
+    if (batch < 1 || batch > h->B) return fail("maexp_learner_attention: batch must be in 1..batch_size");
+    maexp_learner::VitStack &s = stack ? h->vrel : h->vloc;
+    const size_t per = (size_t)h->heads_ * s.Tn * s.Tn * sizeof(float);  // one sample
+    MAEXP_CUDA_L(cudaMemcpy2DAsync(out, per * batch, s.a[1].blk[layer].probs, per * h->B, per * batch, h->G,
+                                   cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_obs, const int32_t *actions,
                         const float *rewards, const uint8_t *dones, float *loss_out, void *stream) {
     if (!h || !obs || !next_obs || !actions || !rewards || !dones) return fail("maexp_learner_grads: null argument");

@@ -229,3 +229,28 @@ def test_reference_style_brain_interface():
     assert abs(float(out["total_loss"]) - fix["losses"][0]) <= RTOL * fix["losses"][0]
     with pytest.raises(ValueError):
         generate_brain(cfg.merged_with(brain="nope"), shape, 4)
+
+
+def test_attention_maps_match_torch_oracle():
+    """forward_attn of DA6 (da6.py:128-165): local and relative attention weights of the acting forward pass."""
+    from oracle.torch_learner import da6_forward
+    kind = "da6"
+    fix = load(kind)
+    b = fix["batch"]
+    B = b["obs"].shape[0]
+    g = make_group(kind, fix["shape"], 1, B)
+    g.load_state_dict(0, fix["init"])
+    pos = b["pos"].to(torch.int8)[None].contiguous().cuda()
+    q = g.q_values(pack(g, b["obs"][None]), pos=pos).cpu()[0]
+    attns = [[], []]
+    want_q = da6_forward(fix["init"], (b["obs"], b["pos"]), fix["shape"][1:], 2, attns=attns)
+    assert rel_err(q, want_q) < RTOL
+    for stack in (0, 1):
+        got = g.attention(B, stack=stack, layer=0).cpu()[0]
+        assert got.shape == attns[stack][0].shape
+        assert float((got - attns[stack][0]).abs().max()) < 1e-6
+    with pytest.raises(Exception):
+        g.attention(B, stack=0, layer=3)
+    dqn = make_group("dqn_conv_mlp", load("dqn_conv_mlp")["shape"], 1, 4)
+    with pytest.raises(ValueError):
+        dqn.attention(4)

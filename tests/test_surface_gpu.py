@@ -148,3 +148,27 @@ def test_trainer_merged_view_da3_end_to_end():
     assert tuple(sd["drl_head.weight"].shape)[0] == 4 and "local_blocks.0.attn.qkv.weight" in sd and "relative_conv.conv_post.weight" in sd
     with pytest.raises(ValueError):  # the noise-free "relative" key is not kept in the ring
         generate_trainer(cfg.merged_with(observation_noise="flip"), env)
+
+
+def test_evaluator_greedy_rollouts_with_saved_weights(tmp_path):
+    """generate_evaluator: epsilon = 0 episodes with weights written by the trainer; greedy actions of identical
+    networks on identical envs are reproducible, and the counters the reference logs are returned."""
+    from maexp_b200.core.handlers.evaluators import generate_evaluator
+    from maexp_b200.core.handlers.trainers import generate_trainer
+    from tests.cuda_backend import make_env
+    cfg = baseline_config(2).merged_with(max_episode_length=12, batch_size=16, populate_steps=4 * 32, capacity=32 * 16,
+                                         observation_noise=False, validate_epochs=2)
+    trainer = generate_trainer(cfg, make_env(cfg, 32, auto_reset=True))
+    trainer.run(max_epochs=1)
+    trainer.save_state_dict(str(tmp_path))
+    runs = []
+    for _ in range(2):
+        ev = generate_evaluator(cfg.merged_with(pretrained_weight_path=str(tmp_path)), make_env(cfg, 32, auto_reset=False))
+        ev.load_state_dict()
+        assert torch.equal(ev.learner.params(), trainer.learner.params())
+        runs.append(ev.run())
+    assert len(runs[0]) == 2 and runs[0] == runs[1]
+    assert set(runs[0][0]) >= {"episode/total_reward", "episode/objects_completed", "episode/agents_collided"}
+    assert runs[0][0]["episode/objects_generated"] >= cfg.num_objects
+    with pytest.raises(ValueError):
+        generate_evaluator(cfg.merged_with(evaluator="nope"), trainer.env)
