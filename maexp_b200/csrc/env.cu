@@ -332,7 +332,9 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // envs per warp (one lane per env in the sequential phase).  Measured on B200 at E = 65536:
     // 8 -> 119 us, 16 -> 89 us, 32 -> 93 us per step; small batches prefer more, shorter groups.
-    h->epw = (E >= 16 * sms * 8) ? 16 : 8;
+    // With observation noise the expansion phase dominates (one Philox call per quad), and it runs at full lane
+    // efficiency only when a warp's group has 32 envs: flip-noise cfg2 256 -> 223 us per step.
+    h->epw = (E >= 16 * sms * 8) ? (p.noise != MAEXP_NOISE_NONE && E >= 32 * sms * 4 ? 32 : 16) : 8;
     if (const char *force = getenv("MAEXP_EPW")) {
         const int v = atoi(force);
         if (v == 8 || v == 16 || v == 32) h->epw = v;
