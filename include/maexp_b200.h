@@ -93,6 +93,10 @@ typedef struct {
     int8_t *objects;       /* [E,N,T,X,Y] objects_matrix snapshot at agent i's observation time */
     uint8_t *destination;  /* [E,N] selected destination mask per agent ("destination" key = table row) */
     int8_t *actions_taken; /* [E,N] the actions executed by this call (given or Philox-drawn); -1 on reset */
+    int32_t *heatmaps;     /* optional visit statistics of default_environment.py:37-61,118-148,196-231,172, summed over ALL
+                              environments with atomics (the caller zeroes them, as reset() does in the reference):
+                              [agents N·X·Y | complete N·X·Y | objects T·X·Y | objects_left T·X·Y | wall_collision X·Y |
+                              agents_collision X·Y], maexp_env_heatmap_ints() values in total */
 } maexp_obs_out;
 
 typedef struct maexp_env maexp_env;
@@ -118,6 +122,9 @@ int maexp_env_reset(maexp_env *env, uint32_t tick, const uint8_t *env_mask, cons
  * order uint8 [E,N] permutation (NULL: Philox Fisher-Yates, abstract_trainer.py:66). */
 int maexp_env_step(maexp_env *env, uint32_t tick, const int8_t *actions, const uint8_t *order,
                    const float *noise_tape, const maexp_obs_out *out, void *stream);
+
+/* number of int32 values behind maexp_obs_out.heatmaps: (2N + 2T + 2)·X·Y */
+int64_t maexp_env_heatmap_ints(const maexp_env *env);
 
 /* Same call with HOST buffers (pinned or pageable): copies actions in, steps, copies rewards /
  * dones / was_reset out and synchronises.  Observations stay in the device ring slot `obs`. */

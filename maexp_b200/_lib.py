@@ -37,7 +37,7 @@ class Tables(C.Structure):
 
 class ObsOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates",
-                                           "positions", "objects", "destination", "actions_taken")]
+                                           "positions", "objects", "destination", "actions_taken", "heatmaps")]
 
 
 class ReplayView(C.Structure):
@@ -73,6 +73,7 @@ SYMBOLS = {
                                  C.c_void_p]),
     "maexp_env_step_host": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "maexp_env_heatmap_ints": (C.c_int64, [C.c_void_p]),
     "maexp_env_step_host_async": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "maexp_env_host_wait": (C.c_int, [C.c_void_p, C.c_uint64]),

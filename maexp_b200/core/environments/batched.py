@@ -155,6 +155,25 @@ class BatchedEnvironment:
             return [self.C, self.V, self.V]
         return [self.C, int(self.map.SIZE_X), int(self.map.SIZE_Y)]
 
+    def new_heatmaps(self):
+        """Zeroed int32 buffer for out["heatmaps"] and a function splitting it into the reference's named arrays
+        (default_environment.py:70-96)."""
+        n = int(self.lib.maexp_env_heatmap_ints(self.h))
+        buf = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        N, T, X, Y = self.N, self.T, self.X, self.Y
+
+        def split(b=buf):
+            sizes = [("heatmap_agents", (N, X, Y)), ("heatmap_complete", (N, X, Y)), ("heatmap_objects", (T, X, Y)),
+                     ("heatmap_objects_left", (T, X, Y)), ("heatmap_wall_collision", (X, Y)),
+                     ("heatmap_agents_collision", (X, Y))]
+            out, off = {}, 0
+            for name, shape in sizes:
+                cnt = int(np.prod(shape))
+                out[name] = b[off:off + cnt].view(*shape)
+                off += cnt
+            return out
+        return buf, split
+
     def new_slot(self):
         """One replay-ring slot, agent-major: fp32 [N, E, slot_floats] (slot_floats = C*V*V padded to 32 bytes)."""
         return torch.empty((self.N, self.E, self.slot_floats), dtype=torch.float32, device=self.device)
@@ -186,7 +205,7 @@ class BatchedEnvironment:
     def _out_struct(self, out):
         s = _lib.ObsOut()
         for name in ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates", "positions", "objects",
-                     "destination", "actions_taken"):
+                     "destination", "actions_taken", "heatmaps"):
             t = out.get(name)
             if t is not None:
                 assert t.is_cuda and t.is_contiguous()

@@ -419,6 +419,11 @@ int maexp_env_step_host(maexp_env *h, uint32_t tick, const int8_t *actions_host,
     return 0;
 }
 
+int64_t maexp_env_heatmap_ints(const maexp_env *h) {
+    if (!h) return -1;
+    return (int64_t)(2 * h->p.N + 2 * h->p.T + 2) * h->p.X * h->p.Y;
+}
+
 int maexp_env_step_host_async(maexp_env *h, uint32_t tick, const int8_t *actions_host, float *obs_ring_slot,
                               float *rewards_host, uint8_t *dones_host, uint8_t *was_reset_host, void *stream_,
                               uint64_t *ticket) {

@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
 
     auto agent_at = [&](int x, int y) { return (agrid[x] >> (y + R)) & 1u; };
     // default_environment.py:134-148, one accepted object; two uniforms per attempt
+    int32_t *const hm = p.out.heatmaps;  // optional visit statistics, see maexp_obs_out
     auto spawn = [&](int t, uint32_t stream) {
         for (;;) {
             if (attempt >= (uint32_t)kRespawnCap) {
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                 grid[t * XP + x] |= bit;
                 ++c_gen;
                 ++nobj;
+                if (hm) atomicAdd(hm + ((2 * N + t) * X + x) * Y + y, 1);  // heatmap_objects (default_environment.py:145)
                 return;
             }
         }
@@ -347,6 +349,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             const int px = me & 0xFF, py = me >> 8;
             if (!is_reset) {
                 // ---------------------------------------- default_environment.py:196-231
+                if (hm) atomicAdd(hm + (i * X + px) * Y + py, 1);  // heatmap_agents
                 if (!p.no_task[i]) {
                     const int sel = p.random_dest ? (int)nib(dsel, i) : (i < p.M ? i : p.M - 1);
                     const uint32_t bit = 1u << (py + R);
@@ -357,6 +360,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                             grid[t * XP + px] &= ~bit;
                             --nobj;
                             ++c_done;
+                            if (hm) atomicAdd(hm + ((N + i) * X + px) * Y + py, 1);  // heatmap_complete
                             if (NSPEC || p.env_kind == MAEXP_ENV_DEFAULT) {
                                 if (p.keep) spawn(t, kStreamRespawn);
                             } else {
@@ -374,13 +378,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                                     if (!(grid[next * XP + px] & bit)) ++nobj;
                                     grid[next * XP + px] |= bit;
                                     ++c_gen;
+                                    if (hm) atomicAdd(hm + ((2 * N + next) * X + px) * Y + py, 1);
                                 }
                                 if (respawn) spawn(0, kStreamRespawn);
                             }
                         }
                     }
-                    if (ca & (1u << i)) { rew_neg |= 1u << i; ++c_ca; }
-                    if (cw & (1u << i)) { rew_neg |= 1u << i; ++c_cw; }
+                    if (ca & (1u << i)) {
+                        rew_neg |= 1u << i; ++c_ca;
+                        if (hm) atomicAdd(hm + ((2 * N + 2 * T + 1) * X + px) * Y + py, 1);  // heatmap_agents_collision
+                    }
+                    if (cw & (1u << i)) {
+                        rew_neg |= 1u << i; ++c_cw;
+                        if (hm) atomicAdd(hm + ((2 * N + 2 * T) * X + px) * Y + py, 1);  // heatmap_wall_collision
+                    }
                 }
                 // ---------------------------------------- default_environment.py:233-237
                 if (nobj == 0 || stepc == p.L - 1) done_bits |= 1u << i;
@@ -631,6 +642,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             if (P > 0)
                 for (int k = 0; k < N; ++k) s_past[k * EPW + lane] = mypos[k * EPW];
             ++stepc;  // default_environment.py:172
+            if (hm)  // :173 heatmap_objects_left += objects_matrix
+                for (int t = 0; t < T; ++t)
+                    for (int x = 0; x < X; ++x)
+                        for (uint32_t row = grid[t * XP + x] >> R; row; row &= row - 1)
+                            atomicAdd(hm + ((2 * N + T + t) * X + x) * Y + (__ffs(row) - 1), 1);
         }
         float shared = 0.0f;
         if (p.reward_mode != MAEXP_REWARD_DEFAULT) {  // shared_reward_environment.py:15-28

@@ -43,7 +43,16 @@ struct orc_env {
     int8_t noise_area[MAXX][MAXY];
     int8_t *los;          /* [X,Y,V,V] 1 visible / 0 hidden  (local_area_mask.py:97) */
     env_t *envs;
+    int32_t *hm;          /* orc_out.heatmaps of the running call (NULL: off) */
 };
+
+/* offsets into orc_out.heatmaps */
+#define HM_AGENTS(o, k, x, y) ((o)->hm[(((k)) * (o)->X + (x)) * (o)->Y + (y)])
+#define HM_COMPLETE(o, k, x, y) ((o)->hm[(((o)->cfg.num_agents + (k)) * (o)->X + (x)) * (o)->Y + (y)])
+#define HM_OBJECTS(o, t, x, y) ((o)->hm[((2 * (o)->cfg.num_agents + (t)) * (o)->X + (x)) * (o)->Y + (y)])
+#define HM_LEFT(o, t, x, y) ((o)->hm[((2 * (o)->cfg.num_agents + (o)->cfg.type_objects + (t)) * (o)->X + (x)) * (o)->Y + (y)])
+#define HM_WALL(o, x, y) ((o)->hm[((2 * (o)->cfg.num_agents + 2 * (o)->cfg.type_objects) * (o)->X + (x)) * (o)->Y + (y)])
+#define HM_COLLIDE(o, x, y) ((o)->hm[((2 * (o)->cfg.num_agents + 2 * (o)->cfg.type_objects + 1) * (o)->X + (x)) * (o)->Y + (y)])
 
 #define AM(o, e, k, x, y) ((e)->agents_matrix[((k) * (o)->X + (x)) * (o)->Y + (y)])
 #define OM(o, e, t, x, y) ((e)->objects_matrix[((t) * (o)->X + (x)) * (o)->Y + (y)])
@@ -445,6 +454,7 @@ static void generate_one_object(orc_env *o, int e, uint32_t tick, uint32_t strea
         for (int t = 0; t < T; ++t) objects += OM(o, en, t, x, y);
         if (o->wall[x][y] == 0 && agents == 0 && objects == 0 && OA(o, object_type, x, y) == 1) {
             OM(o, en, object_type, x, y) = 1;
+            if (o->hm) HM_OBJECTS(o, object_type, x, y) += 1; /* :145 */
             en->counters[0] += 1;
             return;
         }
@@ -747,6 +757,7 @@ static void reset_one(orc_env *o, int e, uint32_t tick, const orc_out *out) {
 }
 
 void orc_reset(orc_env *o, uint32_t tick, const uint8_t *env_mask, const orc_out *out) {
+    o->hm = out ? out->heatmaps : NULL;
     for (int e = 0; e < o->cfg.num_envs; ++e)
         if (!env_mask || env_mask[e]) reset_one(o, e, tick, out);
 }
@@ -811,6 +822,7 @@ static void step_one(orc_env *o, int e, uint32_t tick, const int8_t *actions, co
         int ax, ay;
         coord2ind(o, en->xy[i], &ax, &ay);
         float reward = 0.0f; /* :196-231 */
+        if (o->hm) HM_AGENTS(o, i, ax, ay) += 1; /* :198 */
         if (o->cfg.task_mask[i] >= 0) { /* :201-202: task "-1" returns before the collision handling */
             for (int q = 0; q < ORC_MAX_TYPES && o->cfg.task_order[i][q] >= 0; ++q) {
                 const int t = o->cfg.task_order[i][q];
@@ -818,6 +830,7 @@ static void step_one(orc_env *o, int e, uint32_t tick, const int8_t *actions, co
                     reward = 1.0f;
                     OM(o, en, t, ax, ay) = 0;
                     en->counters[1] += 1;
+                    if (o->hm) HM_COMPLETE(o, i, ax, ay) += 1; /* :213 */
                     if (o->cfg.env_kind == ORC_ENV_DEFAULT) {
                         if (o->cfg.keep_objects_num) generate_one_object(o, e, tick, MAEXP_STREAM_RESPAWN, &attempt, t);
                     } else {
@@ -833,14 +846,21 @@ static void step_one(orc_env *o, int e, uint32_t tick, const int8_t *actions, co
                         if (next >= 0) {
                             if (next >= T) abort(); /* IndexError in the reference */
                             OM(o, en, next, ax, ay) = 1;
+                            if (o->hm) HM_OBJECTS(o, next, ax, ay) += 1; /* default_environment.py:118-121 */
                             en->counters[0] += 1;
                         }
                         if (respawn) generate_one_object(o, e, tick, MAEXP_STREAM_RESPAWN, &attempt, 0);
                     }
                 }
             }
-            if (en->collide_agents[i]) { reward = -1.0f; en->collide_agents[i] = 0; en->counters[2] += 1; }
-            if (en->collide_walls[i]) { reward = -1.0f; en->collide_walls[i] = 0; en->counters[3] += 1; }
+            if (en->collide_agents[i]) {
+                reward = -1.0f; en->collide_agents[i] = 0; en->counters[2] += 1;
+                if (o->hm) HM_COLLIDE(o, ax, ay) += 1; /* :221 */
+            }
+            if (en->collide_walls[i]) {
+                reward = -1.0f; en->collide_walls[i] = 0; en->counters[3] += 1;
+                if (o->hm) HM_WALL(o, ax, ay) += 1; /* :228 */
+            }
         }
         reward_n[i] = reward;
         /* :233-237 */
@@ -858,6 +878,10 @@ static void step_one(orc_env *o, int e, uint32_t tick, const int8_t *actions, co
         get_past_global_agents(o, en, 0);
     }
     en->current_step += 1; /* :172 */
+    if (o->hm) /* :173 */
+        for (int t = 0; t < T; ++t)
+            for (int x = 0; x < o->X; ++x)
+                for (int y = 0; y < o->Y; ++y) HM_LEFT(o, t, x, y) += OM(o, en, t, x, y);
 
     /* shared_reward_environment.py:15-28 */
     if (o->cfg.reward_mode != ORC_REWARD_DEFAULT) {
@@ -887,6 +911,8 @@ static void *step_worker(void *p) {
 void orc_step(orc_env *o, uint32_t tick, const int8_t *actions, const uint8_t *order, const orc_out *out,
               int num_threads) {
     const int E = o->cfg.num_envs;
+    o->hm = out ? out->heatmaps : NULL;
+    if (o->hm) num_threads = 1; /* the shared statistics are plain (non-atomic) sums */
     if (num_threads > 64) num_threads = 64;
     if (num_threads > E) num_threads = E;
     if (num_threads <= 1) {

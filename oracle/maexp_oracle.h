@@ -86,6 +86,9 @@ typedef struct {
     int8_t *objects;       /* [E,N,T,X,Y] snapshot at agent i's observation time */
     int8_t *destination;   /* [E,N,X,Y] */
     const float *noise_tape;
+    int32_t *heatmaps;     /* optional, summed over all envs, never zeroed here (default_environment.py:70-96 zeroes per reset):
+                              [heatmap_agents N,X,Y | heatmap_complete N,X,Y | heatmap_objects T,X,Y |
+                               heatmap_objects_left T,X,Y | heatmap_wall_collision X,Y | heatmap_agents_collision X,Y] */
 } orc_out;
 
 /* reset every env with env_mask[e]!=0 (NULL: all). tick keys the RNG draws. */

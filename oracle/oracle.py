@@ -46,7 +46,7 @@ class OrcCfg(C.Structure):
 
 class OrcOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates",
-                                           "agents", "objects", "destination", "noise_tape")]
+                                           "agents", "objects", "destination", "noise_tape", "heatmaps")]
 
 
 def build(force=False):
@@ -176,6 +176,7 @@ class Oracle:
         self.X, self.Y = self.L.orc_size_x(self.h), self.L.orc_size_y(self.h)
         self.merged = self.c.area_mask == MASKS["merged"]
         self.extras = extras
+        self.heatmaps = None
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -211,7 +212,22 @@ class Oracle:
             assert noise_tape.shape == (E, N, Cn, V, V)
             s.noise_tape = noise_tape.ctypes.data
         o["_keep"] = noise_tape
+        if self.heatmaps is not None:
+            s.heatmaps = self.heatmaps.ctypes.data
         return o, s
+
+    def enable_heatmaps(self):
+        """Allocates the visit statistics (summed over envs) and returns the named views of default_environment.py:70-96."""
+        N, T, X, Y = self.N, self.T, self.X, self.Y
+        self.heatmaps = np.zeros(((2 * N + 2 * T + 2) * X * Y,), np.int32)
+        out, off = {}, 0
+        for name, shape in (("heatmap_agents", (N, X, Y)), ("heatmap_complete", (N, X, Y)), ("heatmap_objects", (T, X, Y)),
+                            ("heatmap_objects_left", (T, X, Y)), ("heatmap_wall_collision", (X, Y)),
+                            ("heatmap_agents_collision", (X, Y))):
+            cnt = int(np.prod(shape))
+            out[name] = self.heatmaps[off:off + cnt].reshape(shape)
+            off += cnt
+        return out
 
     def reset(self, tick, env_mask=None, noise_tape=None):
         o, s = self._out(noise_tape)

@@ -200,3 +200,23 @@ def test_unsupported_configs_fail_loudly():
     with pytest.raises(ValueError):
         make_env(make_config(map=dict(name="four_rooms", SIZE_X=24, SIZE_Y=24), type_objects=3,
                              agent_tasks=["0"] * 8), 1)  # empty objects_area: reference spins forever (§E-8)
+
+
+@pytest.mark.parametrize("name", ["cfg5_four_rooms_n8", "junctional_chain_tasks", "cfg4_four_rectangle_merged_types"])
+def test_heatmaps_match_oracle(name):
+    """Optional visit statistics (maexp_obs_out.heatmaps) summed over 64 environments, with auto-resets."""
+    from oracle.cases import cases
+    cfg = cases()[name][0].merged_with(max_episode_length=12)
+    E = 64
+    b = CudaBackend(cfg, E, first_global_env_id=11, auto_reset=True, extras=False)
+    orc = Oracle(cfg, E, auto_reset=True, first_global_env_id=11)
+    want = orc.enable_heatmaps()
+    buf, split = b.env.new_heatmaps()
+    b.out["heatmaps"] = buf
+    b.reset(0), orc.reset(0)
+    for tick in range(1, 40):
+        got, ref = b.step(tick), orc.step(tick)
+        assert np.array_equal(got["rewards"], ref["rewards"])
+    for key, t in split().items():
+        assert np.array_equal(t.cpu().numpy(), want[key]), key
+    assert want["heatmap_agents"].sum() > 0 and want["heatmap_wall_collision"].sum() > 0

@@ -58,3 +58,21 @@ def test_fixed_scenario_pickup_and_collision():
     assert np.array_equal(a["rewards"].astype(np.float32), b["rewards"][0])
     assert np.array_equal(a["obs"], b["obs"][0]) and np.array_equal(a["objects"], b["objects"][0])
     assert a["objects"][0].sum() == 1 and a["objects"][0][0, 6, 5] == 0  # consumed, respawned elsewhere
+
+
+@pytest.mark.parametrize("name", ["cfg5_four_rooms_n8", "sequential_central_room_t3", "junctional_chain_tasks"])
+def test_heatmaps_match_reference(name):
+    """Visit statistics of default_environment.py:70-96: the six integer heat-maps after 80 steps."""
+    cfg = cases()[name][0]
+    ref = rr.RefEnv(cfg, env_id=5)
+    orc = Oracle(cfg, num_envs=1, first_global_env_id=5)
+    hm = orc.enable_heatmaps()
+    ref.reset(0), orc.reset(0)
+    for tick in range(1, 81):
+        a, b = ref.step(tick), orc.step(tick)
+        assert np.array_equal(a["obs"], b["obs"][0])
+    env = ref.env
+    for key in ("heatmap_agents", "heatmap_complete", "heatmap_objects", "heatmap_objects_left", "heatmap_wall_collision",
+                "heatmap_agents_collision"):
+        assert np.array_equal(np.asarray(getattr(env, key)), hm[key]), key
+    assert hm["heatmap_complete"].sum() > 0 and hm["heatmap_objects_left"].sum() > 0
