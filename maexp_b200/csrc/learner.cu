@@ -53,8 +53,8 @@ constexpr int kTile = 64, kBK = 16;
 // part[slice][g][M][N]; splitk_reduce_kernel then adds the slices in a fixed order and applies the
 // epilogue.  With ksplit == 1 the epilogue runs here and C is written directly.
 __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a, int ksplit, int kslice, float *part) {
-    __shared__ float As[kBK][kTile + 4];
-    __shared__ float Bs[kBK][kTile + 4];
+    __shared__ __align__(16) float As[kBK][kTile + 4];
+    __shared__ __align__(16) float Bs[kBK][kTile + 4];
     const int g = blockIdx.z / ksplit, slice = blockIdx.z - g * ksplit;
     const float *A = a.A + (size_t)g * a.gA, *B = a.B + (size_t)g * a.gB;
     const int m0 = blockIdx.y * kTile, n0 = blockIdx.x * kTile;
@@ -95,15 +95,15 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a, int ksplit,
         if (k0 + kBK < kend) fetch(k0 + kBK);  // next tile's loads overlap this tile's math
 #pragma unroll
         for (int kk = 0; kk < kBK; ++kk) {
-            float av[4], bv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+            // 128-bit shared loads and fused multiply-adds (the 1e-5 learner bar does not need separately rounded products;
+            // the env kernel's bit-exact noise arithmetic is what --fmad=false is for)
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(av[i], bv[j]));
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
