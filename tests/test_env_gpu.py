@@ -36,7 +36,8 @@ def _compare(a, b, keys, what):
 
 BATCH_CASES = ["cfg1_simple_mlp", "cfg2_four_rooms_transition_flip_sharedmean", "cfg3_three_rooms",
                "cfg4_four_rectangle_merged_types", "cfg5_four_rooms_n8", "indtrans_t2_v9_tasks",
-               "no_keep_small", "relative_transparent", "simple_views_v5"]
+               "no_keep_small", "relative_transparent", "simple_views_v5", "sequential_central_room_t3",
+               "junctional_central_room_t5_merged", "two_central_rooms_t2_n12", "central_room_large_destination_v9"]
 
 
 @pytest.mark.parametrize("name", BATCH_CASES)
@@ -58,6 +59,36 @@ def test_cuda_batch_matches_oracle(name, num_envs):
         _compare(sa, sb, ("pos", "objects", "counters", "steps", "destination"), f"{name} state tick {tick}")
     st = cuda.env.stats()
     assert st["error_flag"] == 0 and st["resets"] >= num_envs * 2  # initial reset + one auto-reset each
+
+
+@pytest.mark.parametrize("epw", [8, 16, 32])
+@pytest.mark.parametrize("name", ["cfg2_four_rooms_transition_flip_sharedmean", "cfg5_four_rooms_n8", "merged_flip_three_rooms"])
+def test_every_envs_per_warp_instantiation(name, epw, monkeypatch):
+    """The library picks 8 / 16 / 32 envs per warp from the batch size; force each instantiation on a ragged batch."""
+    monkeypatch.setenv("MAEXP_EPW", str(epw))
+    cfg, _, _, okw = cases()[name]
+    cfg = cfg.merged_with(max_episode_length=9)
+    cuda = CudaBackend(cfg, 133, first_global_env_id=77, auto_reset=True, extras=True, **okw)
+    orc = Oracle(cfg, 133, auto_reset=True, first_global_env_id=77, extras=True, **okw)
+    keys = ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates", "objects", "destination")
+    _compare(cuda.reset(0), orc.reset(0), keys, f"{name} reset")
+    for tick in range(1, 22):
+        _compare(cuda.step(tick), orc.step(tick, threads=4), keys, f"{name} epw {epw} tick {tick}")
+
+
+@pytest.mark.parametrize("num_agents", [1, 3, 12, 16])
+def test_agent_counts(num_agents):
+    """1..16 agents (16 is the packing limit of the order / selection nibbles), including the eight-wide vector stores."""
+    xy = [[4, 4], [-4, 4], [4, -4], [-4, -4], [6, 6], [-6, 6], [6, -6], [-6, -6], [4, 6], [-4, 6], [4, -6], [-4, -6],
+          [6, 4], [-6, 4], [6, -4], [-6, -4]]
+    cfg = make_config(num_agents=num_agents, init_xys=xy[:num_agents], agent_view_method="individual", max_episode_length=10)
+    cuda = CudaBackend(cfg, 70, first_global_env_id=5, auto_reset=True, extras=True)
+    orc = Oracle(cfg, 70, auto_reset=True, first_global_env_id=5, extras=True)
+    keys = ("obs", "rewards", "dones", "was_reset", "coordinates", "objects", "destination")
+    _compare(cuda.reset(0), orc.reset(0), keys, "reset")
+    for tick in range(1, 25):
+        _compare(cuda.step(tick), orc.step(tick, threads=4), keys, f"N={num_agents} tick {tick}")
+        _compare(cuda.state(), orc.state(), ("pos", "objects", "counters", "steps"), f"N={num_agents} state {tick}")
 
 
 def test_masked_reset_and_injected_actions():
