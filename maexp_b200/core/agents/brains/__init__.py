@@ -48,8 +48,8 @@ def learner_kind(config):
             raise ValueError("attention IQN models are implemented with soft attention and without extra canvas channels")
         if config.model.name == "da6_iqn" and mask != "merged":
             raise ValueError("da6_iqn reads the merged view (customs/da6_iqn.py:160-176)")
-        if config.model.name == "da3_iqn" and (mask == "relative" or (mask == "local" and int(config.model.patch_size) != 1)):
-            raise ValueError("da3_iqn is implemented for the local view (patch_size=1) and the merged view")
+        if config.model.name == "da3_iqn" and mask == "local" and int(config.model.patch_size) != 1:
+            raise ValueError("da3_iqn on the local view is implemented for patch_size=1")
     elif config.model.name == "da6" or kind == "da6":
         if kind != "da6" or config.model.name != "da6":
             raise ValueError("brain=da6 and model=da6 go together (da6_brain.py, customs/da6.py)")
@@ -59,9 +59,9 @@ def learner_kind(config):
     elif config.model.name == "da3" or kind == "da3":
         if kind != "da3" or config.model.name != "da3":
             raise ValueError("brain=da3 and model=da3 go together (da3_brain.py, customs/da3.py)")
-        if config.observation_area_mask == "relative" or config.model.get("attention") == "hard" or \
-                config.get("objects_channel") or (config.observation_area_mask == "local" and int(config.model.patch_size) != 1):
-            raise ValueError("DA3 is implemented for the local view (patch_size=1) and the merged view, soft attention")
+        if config.model.get("attention") == "hard" or config.get("objects_channel") or \
+                (config.observation_area_mask == "local" and int(config.model.patch_size) != 1):
+            raise ValueError("DA3 is implemented with soft attention, without the objects channel; local view: patch_size=1")
     elif config.model.name not in ("conv_mlp", "da3_baseline", "categorical_dqn", "qr_dqn", "iqn"):
         logger.warning(f"Unexpected network is given. config.model.name: {config.model.name}")
         raise ValueError()

@@ -980,7 +980,7 @@ struct maexp_learner {
         float *d_y2, *d_col2, *d_p, *d_y1;
     } gt_rel, gt_loc;
     int area_mask = 0, X = 0, Y = 0, Drel = 0, Dloc = 0;
-    bool merged_conv = false, relative_conv = false, merged_da3 = false;
+    bool merged_conv = false, relative_conv = false, merged_da3 = false, relative_vit = false;
     HeadLayout rse;                 // MergedDA3 relative_state_embedder
     const int8_t *pos = nullptr, *next_pos = nullptr;  // bound by maexp_learner_bind_positions
     float *canvas[3] = {nullptr, nullptr, nullptr}, *feat[3] = {nullptr, nullptr, nullptr}, *d_feat = nullptr;
@@ -1253,15 +1253,24 @@ void vit_backward(maexp_learner *h, cudaStream_t st, maexp_learner::VitStack &s,
 }
 
 // DA3 / MergedDA3's local stack on the batch's V x V crops, optionally followed by the drl_head (da3.py:64-96)
-void da3_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, int pass,
-                 bool with_head = true) {
+int decode_canvas(maexp_learner *h, cudaStream_t st, const float *obs, const int8_t *pos, int B, int pass, int only_area);
+
+int da3_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, int pass,
+                bool with_head = true, const int8_t *pos = nullptr) {
     const long long P = h->P, Bmax = h->B;
     const int E = h->E_;
-    vit_forward(h, st, params, h->vloc, obs, h->cfg.obs_stride, (long long)h->V * h->V, (long long)B * h->cfg.obs_stride, B, pass,
-                nullptr);
+    if (h->relative_vit) {  // relative view: the transformer reads the decoded [C, X, Y] canvas (da3.py:98-109, da3_iqn.py:194-210)
+        const long long XY = (long long)h->X * h->Y;
+        if (decode_canvas(h, st, obs, pos, B, pass, 0)) return -1;
+        vit_forward(h, st, params, h->vloc, h->canvas[pass], h->C * XY, XY, (long long)B * h->C * XY, B, pass, nullptr);
+    } else {
+        vit_forward(h, st, params, h->vloc, obs, h->cfg.obs_stride, (long long)h->V * h->V, (long long)B * h->cfg.obs_stride, B,
+                    pass, nullptr);
+    }
     if (with_head)
         gemm(st, h->G, h->vloc.a[pass].nf, params + h->o_hw, h->vloc.a[pass].q, params + h->o_hb, B, h->A, E, E, 1, 1, E, h->A, 1,
              Bmax * E, P, Bmax * h->A, P);
+    return 0;
 }
 
 // drl_head gradients and d LN(token 0) into h->da_dnf
@@ -1472,7 +1481,7 @@ int iqn_forward(maexp_learner *h, cudaStream_t st, const float *params, const fl
         if (merged_forward(h, st, params, obs, pos, B, pass, &unused, /*with_head=*/false)) return -1;
         psi = h->feat[pass];
     } else if (h->da3) {
-        da3_forward(h, st, params, obs, B, pass, /*with_head=*/false);
+        if (da3_forward(h, st, params, obs, B, pass, /*with_head=*/false, pos)) return -1;
         psi = h->vloc.a[pass].nf;
     } else {
         trunk_forward(h, st, params, obs, B, a);
@@ -1542,11 +1551,13 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     h->relative_conv = cfg->kind == MAEXP_LEARNER_DQN_CONV_MLP && cfg->area_mask == MAEXP_MASK_RELATIVE;
     h->merged_conv = cfg->kind == MAEXP_LEARNER_DQN_CONV_MLP && cfg->area_mask == MAEXP_MASK_MERGED;
     h->merged_da3 = (cfg->kind == MAEXP_LEARNER_DA3 && cfg->area_mask == MAEXP_MASK_MERGED) || trunk == MAEXP_IQN_TRUNK_MERGED_DA3;
-    if (trunk == MAEXP_IQN_TRUNK_DA3 && cfg->area_mask != MAEXP_MASK_LOCAL) { delete h; return fail("maexp_learner_create: the DA3 IQN trunk reads the local view"); }
+    if (trunk == MAEXP_IQN_TRUNK_DA3 && cfg->area_mask == MAEXP_MASK_MERGED) { delete h; return fail("maexp_learner_create: the DA3 IQN trunk reads the local or relative view"); }
+    h->relative_vit = h->da3 && !h->da6 && !h->merged_da3 && cfg->area_mask == MAEXP_MASK_RELATIVE;
+    if (h->relative_vit && (h->X < 4 || h->Y < 4 || cfg->patch_size < 1)) { delete h; return fail("maexp_learner_create: relative DA3 needs size_x / size_y / patch_size"); }
     if (trunk == MAEXP_IQN_TRUNK_MERGED_DA3 && cfg->area_mask != MAEXP_MASK_MERGED) { delete h; return fail("maexp_learner_create: the MergedDA3 IQN trunk reads the merged view"); }
     const bool gmodel = h->relative_conv || h->merged_conv || h->merged_da3;
     if (h->da6 && (cfg->area_mask != MAEXP_MASK_MERGED || h->X < 4 || h->Y < 4)) { delete h; return fail("maexp_learner_create: DA6 reads the merged view (area_mask merged, size_x / size_y set)"); }
-    if (cfg->area_mask != MAEXP_MASK_LOCAL && !gmodel && !h->da6) { delete h; return fail("maexp_learner_create: relative / merged views are implemented for conv_mlp (dqn) and da3 (merged)"); }
+    if (cfg->area_mask != MAEXP_MASK_LOCAL && !gmodel && !h->da6 && !h->relative_vit) { delete h; return fail("maexp_learner_create: relative / merged views are implemented for conv_mlp (dqn) and da3 (merged)"); }
     if (gmodel && (h->X < 4 || h->Y < 4)) { delete h; return fail("maexp_learner_create: size_x / size_y missing for a relative / merged model"); }
     h->has_conv = cfg->kind != MAEXP_LEARNER_DQN_MLP && !h->da3 && !gmodel;
     h->dist = cfg->kind == MAEXP_LEARNER_C51 || cfg->kind == MAEXP_LEARNER_QR;
@@ -1595,7 +1606,8 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             s.Cin = cin; s.Hin = hin; s.Win = win; s.ps = ps > 0 ? ps : 1;
             s.Ht = hin / s.ps; s.Wt = win / s.ps; s.Tn = s.Ht * s.Wt + 1; s.K = cin * s.ps * s.ps;
         };
-        set_stack(h->vloc, h->C, h->V, h->V, h->da6 ? cfg->local_patch_size : 1);
+        if (h->relative_vit) set_stack(h->vloc, h->C, h->X, h->Y, cfg->patch_size);
+        else set_stack(h->vloc, h->C, h->V, h->V, h->da6 ? cfg->local_patch_size : 1);
         if (h->da6) set_stack(h->vrel, 1, h->X, h->Y, cfg->relative_patch_size);
         h->Tn = h->da6 && h->vrel.Tn > h->vloc.Tn ? h->vrel.Tn : h->vloc.Tn;
         if (h->E_ < 1 || h->heads_ < 1 || h->E_ % h->heads_ || h->E_ / h->heads_ > kMaxHeadDim || h->Tn > kMaxTokens || h->Fm < 1 ||
@@ -1643,7 +1655,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         if (h->merged_da3) add_unused_parent(true);  // da3.py:99-103, da3_iqn.py:214-218
         h->vloc.o_sal = add(lp + "saliency_vector", h->E_);
         h->vloc.o_pos = add(lp + "pos_embed", (long long)h->vloc.Tn * h->E_);
-        h->vloc.o_pew = add(lp + "patch_embed.proj.weight", (long long)h->E_ * h->C);
+        h->vloc.o_pew = add(lp + "patch_embed.proj.weight", (long long)h->E_ * h->vloc.K);
         h->vloc.o_peb = add(lp + "patch_embed.proj.bias", h->E_);
         add_blocks(h->vloc, lp);
         }
@@ -1782,6 +1794,8 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             }
             rc |= lalloc(h, &h->d_sal2, G * B * E);
         }
+        if (h->relative_vit)
+            for (int k = 0; k < 3; ++k) rc |= lalloc(h, &h->canvas[k], G * B * h->C * h->X * h->Y);
         rc |= lalloc(h, &h->d_out[0], G * B * h->A);
         rc |= lalloc(h, &h->da_dx, G * Rm * E); rc |= lalloc(h, &h->da_dn, G * Rm * E); rc |= lalloc(h, &h->da_gx, G * Rm * E);
         rc |= lalloc(h, &h->da_dqkv, G * Rm * 3 * E); rc |= lalloc(h, &h->da_dao, G * Rm * E);
@@ -1934,7 +1948,7 @@ int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int us
         if (h->da6) {
             if (da6_forward(h, st, use_target ? h->target : h->online, obs, h->pos, batch, 1)) return -1;
         } else {
-            da3_forward(h, st, use_target ? h->target : h->online, obs, batch, 1);
+            if (da3_forward(h, st, use_target ? h->target : h->online, obs, batch, 1, true, h->pos)) return -1;
         }
         MAEXP_CUDA_L(cudaMemcpy2DAsync(q_out, sizeof(float) * batch * h->A, h->vloc.a[1].q, sizeof(float) * h->B * h->A,
                                        sizeof(float) * batch * h->A, h->G, cudaMemcpyDeviceToDevice, st));
@@ -2000,9 +2014,9 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
             g_splitk_ws = h->splitk_ws;
             if (da6_forward(h, st, h->online, obs, h->pos, B, 0)) return -1;
         } else {
-            da3_forward(h, s2, h->target, next_obs, B, 2);
+            if (da3_forward(h, s2, h->target, next_obs, B, 2, true, h->next_pos)) return -1;
             g_splitk_ws = h->splitk_ws;
-            da3_forward(h, st, h->online, obs, B, 0);
+            if (da3_forward(h, st, h->online, obs, B, 0, true, h->pos)) return -1;
         }
         join_pass(h, st, 0);
         dqn_loss_kernel<<<dim3((B + 127) / 128, G), 128, 0, st>>>(h->vloc.a[0].q, h->vloc.a[2].q, actions, rewards, dones,

@@ -53,7 +53,13 @@ def configs():
         c["agent_type"] = "attention"
         c["objects_channel"], c["agents_channel"], c["destination_channel"] = False, False, False
         return c
-    return {"da3_iqn": (attn_iqn("local", "da3_iqn"), [4, VIEW, VIEW]), "merged_da3_iqn": (attn_iqn("merged", "da3_iqn"), [4, *SIZE]),
+    rda3 = view("relative", "da3", "da3", embed_dim=32, block_loop=1, mlp_ratio=4.0, attention="soft", af_lambd=0.5)
+    rda3["model"]["patch_size"] = 3
+    rda3["agent_type"] = "attention"
+    rda3_iqn = attn_iqn("relative", "da3_iqn")
+    rda3_iqn["model"]["patch_size"] = 3
+    return {"relative_da3": (rda3, [4, *SIZE]), "relative_da3_iqn": (rda3_iqn, [4, *SIZE]),
+            "da3_iqn": (attn_iqn("local", "da3_iqn"), [4, VIEW, VIEW]), "merged_da3_iqn": (attn_iqn("merged", "da3_iqn"), [4, *SIZE]),
             "da6_iqn": (attn_iqn("merged", "da6_iqn"), [4, *SIZE]),
             "da6": (da6, [4, *SIZE]),"relative_conv_mlp": (rel, [4, *SIZE]), "merged_conv_mlp": (mconv, [4, *SIZE]), "merged_da3": (mda3, [4, *SIZE]),
             "da3": (da3, [3, 7, 7]), "dqn_conv_mlp": (dqn, [7, 7, 7]), "c51": (c5.merged_with(batch_size=B), [3, 7, 7]),
@@ -87,10 +93,12 @@ def main():
     for kind, (cfg, shape) in configs().items():
         torch.manual_seed(921)
         brain = generate_brain(config=rr.to_dictconfig(cfg), obs_shape=shape, act_size=4)
-        masked = kind in ("relative_conv_mlp", "merged_conv_mlp", "merged_da3", "da6", "merged_da3_iqn", "da6_iqn")
-        is_iqn = kind in ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn")
+        masked = kind in ("relative_conv_mlp", "merged_conv_mlp", "merged_da3", "da6", "merged_da3_iqn", "da6_iqn",
+                          "relative_da3", "relative_da3_iqn")
+        is_iqn = kind in ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn", "relative_da3_iqn")
         with torch.no_grad():  # zero-initialised embeddings: perturb so the fixtures exercise them
-            for name in {"da3_iqn": ("saliency_vector", "pos_embed"), "merged_da3_iqn": ("local_saliency_vector", "local_pos_embed"),
+            for name in {"da3_iqn": ("saliency_vector", "pos_embed"), "relative_da3": ("saliency_vector", "pos_embed"),
+                         "relative_da3_iqn": ("saliency_vector", "pos_embed"), "merged_da3_iqn": ("local_saliency_vector", "local_pos_embed"),
                          "da6_iqn": ("saliency_vector", "relative_pos_embed", "local_pos_embed")}.get(kind, ()):
                 p_ = getattr(brain.network, name)
                 p_.add_(0.02 * torch.randn_like(p_))

@@ -11,10 +11,12 @@ from oracle.torch_learner import TorchLearner
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KINDS = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLDEN, "learner_*.npz")))
 ATOMS = {"dqn_conv_mlp": 1, "c51": 51, "qr": 100, "iqn": 4, "da3": 1, "da6": 1}
-IQN_KINDS = ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn")  # fixture name == state-embedding trunk of the IQN head
+IQN_KINDS = ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn", "relative_da3_iqn")
+TRUNKS = {"relative_da3_iqn": "da3_iqn"}  # fixture name -> state-embedding trunk of the IQN head (default: the name)
 # fixtures of the relative / merged views -> (network kind, attention heads)
 MASKED = {"relative_conv_mlp": ("dqn_conv_mlp", 4), "merged_conv_mlp": ("dqn_conv_mlp", 4), "merged_da3": ("da3", 2),
-          "da6": ("da6", 2), "merged_da3_iqn": ("iqn", 2), "da6_iqn": ("iqn", 2)}
+          "da6": ("da6", 2), "merged_da3_iqn": ("iqn", 2), "da6_iqn": ("iqn", 2), "relative_da3": ("da3", 2),
+          "relative_da3_iqn": ("iqn", 2)}
 
 
 def load(kind):
@@ -34,7 +36,7 @@ def make_oracle(kind, fix, sd=None, target=None):
     net, heads = MASKED.get(kind, ("iqn", 2) if kind == "da3_iqn" else (kind, 4))
     o = TorchLearner(net, sd or fix["init"], 4, fix["gamma"], 1e-3, 0.99, 1e-8, num_atoms=ATOMS[net],
                      area_mask=fix["area_mask"], size=fix["shape"][1:], num_heads=heads,
-                     trunk=kind if kind in IQN_KINDS else "iqn")
+                     trunk=TRUNKS.get(kind, kind) if kind in IQN_KINDS else "iqn")
     o.target = {k: v.clone() for k, v in (target or fix["target"]).items()}
     return o
 
