@@ -65,9 +65,10 @@ def learner_kind(config):
     elif config.model.name not in ("conv_mlp", "da3_baseline", "categorical_dqn", "qr_dqn", "iqn"):
         logger.warning(f"Unexpected network is given. config.model.name: {config.model.name}")
         raise ValueError()
-    if config.observation_area_mask != "local" and kind not in ("dqn_conv_mlp", "da3", "da6") and \
-            config.model.name not in ("da3_iqn", "da6_iqn"):
-        raise ValueError("relative / merged views are implemented for the conv_mlp DQN, DA3 / DA6 and their IQN variants")
+    if config.observation_area_mask != "local" and kind not in ("dqn_conv_mlp", "da3", "da6", "iqn"):
+        raise ValueError("relative / merged views are implemented for the conv_mlp DQN, IQN, DA3 / DA6 and their IQN variants")
+    if config.observation_area_mask != "local" and (config.get("objects_channel") or config.get("agents_channel")):
+        raise ValueError("objects_channel / agents_channel canvas inputs are not implemented")
     if config.observation_area_mask == "merged" and config.observation_noise:
         # the merged models read the area channel of the NOISE-FREE "relative" key (merged_observtion_handler.py:26-29);
         # the replay ring keeps only the noisy crop, so this combination is refused rather than approximated

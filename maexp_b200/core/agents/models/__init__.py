@@ -63,6 +63,26 @@ class _IQN(nn.Module):
         self.fc_A = _MLP(config, d, act_size)
 
 
+class _MergedIQN(_IQN):
+    """customs/iqn.py:165-201: IQN's conv / state_embedder stay as unused parameters; the heads are rebuilt on the
+    concatenated local + relative embedding."""
+
+    def __init__(self, config, obs_shape, act_size):
+        super().__init__(config, obs_shape, act_size)
+        v = int(config.visible_range)
+        self.local_conv = _Conv(config, obs_shape[0], config.model.output_channel)
+        self.relative_conv = _Conv(config, 1, config.model.output_channel)
+        torch.randn(1, obs_shape[0], v, v)
+        torch.randn(1, 1, *obs_shape[1:])
+        dl, dr = conv_output_size(config, [obs_shape[0], v, v]), conv_output_size(config, [1, *obs_shape[1:]])
+        self.local_state_embedder = _MLP(config, dl, dl)
+        self.relative_state_embedder = _MLP(config, dr, dr)
+        self.cosine_net = nn.Module()
+        self.cosine_net.net = nn.Sequential(nn.Linear(int(config.model.num_cosines), dl + dr), nn.ReLU(inplace=False))
+        self.fc_V = _MLP(config, dl + dr, 1)
+        self.fc_A = _MLP(config, dl + dr, act_size)
+
+
 class _MergedConvMLP(nn.Module):
     """customs/conv_mlp.py:69-98: the parent's `conv` stays as unused parameters; `mlp` is replaced."""
 
@@ -224,6 +244,8 @@ def build_reference_modules(config, obs_shape, act_size):
         z = int(config.model.num_quantiles)
         return _ConvHeads(config, obs_shape, [("fc_V", z), ("fc_A", act_size * z)])
     if name == "iqn":
+        if config.observation_area_mask == "merged":
+            return _MergedIQN(config, obs_shape, act_size)
         return _IQN(config, obs_shape, act_size)
     if name == "da6":
         return _DA6(config, obs_shape, act_size)

@@ -981,7 +981,8 @@ struct maexp_learner {
     } gt_rel, gt_loc;
     int area_mask = 0, X = 0, Y = 0, Drel = 0, Dloc = 0;
     bool merged_conv = false, relative_conv = false, merged_da3 = false, relative_vit = false;
-    HeadLayout rse;                 // MergedDA3 relative_state_embedder
+    HeadLayout rse, lse;            // relative_state_embedder (MergedDA3, MergedIQN), local_state_embedder (MergedIQN)
+    float *lse_h[3] = {nullptr, nullptr, nullptr}, *lse_out[3] = {nullptr, nullptr, nullptr}, *d_locsal = nullptr, *d_locflat = nullptr;
     const int8_t *pos = nullptr, *next_pos = nullptr;  // bound by maexp_learner_bind_positions
     float *canvas[3] = {nullptr, nullptr, nullptr}, *feat[3] = {nullptr, nullptr, nullptr}, *d_feat = nullptr;
     float *rel_flat[3] = {nullptr, nullptr, nullptr}, *rse_h[3] = {nullptr, nullptr, nullptr}, *rse_out[3] = {nullptr, nullptr, nullptr};
@@ -1483,6 +1484,22 @@ int iqn_forward(maexp_learner *h, cudaStream_t st, const float *params, const fl
     } else if (h->da3) {
         if (da3_forward(h, st, params, obs, B, pass, /*with_head=*/false, pos)) return -1;
         psi = h->vloc.a[pass].nf;
+    } else if (h->relative_conv) {  // IQN on the relative view: conv(decoded canvas) -> state_embedder (customs/iqn.py:88-94,141-160)
+        if (rel_forward(h, st, params, obs, pos, B, pass)) return -1;
+        const MlpIn se_in = {h->feat[pass], D, Bmax * D, B, Bmax, D};
+        mlp_forward(h, st, params, h->se, se_in, q.se_h, q.psi);
+    } else if (h->merged_conv) {  // MergedIQN (customs/iqn.py:203-216): [rel embedder(conv(area)), local embedder(conv(crop))]
+        if (rel_forward(h, st, params, obs, pos, B, pass)) return -1;
+        const int Dr = h->Drel, Dl = h->Dloc;
+        const MlpIn rin = {h->feat[pass], D, Bmax * D, B, Bmax, Dr};
+        const MlpIn lin = {h->feat[pass] + Dr, D, Bmax * D, B, Bmax, Dl};
+        mlp_forward(h, st, params, h->rse, rin, h->rse_h[pass], h->rse_out[pass]);
+        mlp_forward(h, st, params, h->lse, lin, h->lse_h[pass], h->lse_out[pass]);
+        // one 2-D copy per branch: rows (g, b) are uniform because the strides are per maximum batch
+        cudaMemcpy2DAsync(q.psi, sizeof(float) * D, h->rse_out[pass], sizeof(float) * Dr, sizeof(float) * Dr, (size_t)G * Bmax,
+                          cudaMemcpyDeviceToDevice, st);
+        cudaMemcpy2DAsync(q.psi + Dr, sizeof(float) * D, h->lse_out[pass], sizeof(float) * Dl, sizeof(float) * Dl, (size_t)G * Bmax,
+                          cudaMemcpyDeviceToDevice, st);
     } else {
         trunk_forward(h, st, params, obs, B, a);
         const MlpIn se_in = {a.flat, D, Bmax * D, B, Bmax, D};
@@ -1522,6 +1539,22 @@ void iqn_backward(maexp_learner *h, cudaStream_t st, int nq) {
         merged_backward(h, st, /*with_head=*/false);
     } else if (h->da3) {
         da3_backward(h, st, /*with_head=*/false);
+    } else if (h->relative_conv) {
+        const MlpIn se_in = {h->feat[0], D, (long long)B * D, B, B, D};
+        mlp_backward(h, st, h->se, se_in, h->d_psi, q.se_h, h->d_h, h->d_feat, 0);
+        gtrunk_backward(h, st, h->gt_rel, h->d_feat, D, 0, (long long)B * D);
+    } else if (h->merged_conv) {
+        const int Dr = h->Drel, Dl = h->Dloc;
+        cudaMemcpy2DAsync(h->d_relsal, sizeof(float) * Dr, h->d_psi, sizeof(float) * D, sizeof(float) * Dr, (size_t)G * B,
+                          cudaMemcpyDeviceToDevice, st);
+        cudaMemcpy2DAsync(h->d_locsal, sizeof(float) * Dl, h->d_psi + Dr, sizeof(float) * D, sizeof(float) * Dl, (size_t)G * B,
+                          cudaMemcpyDeviceToDevice, st);
+        const MlpIn rin = {h->feat[0], D, (long long)B * D, B, B, Dr};
+        const MlpIn lin = {h->feat[0] + Dr, D, (long long)B * D, B, B, Dl};
+        mlp_backward(h, st, h->rse, rin, h->d_relsal, h->rse_h[0], h->d_h, h->d_relflat, 0);
+        gtrunk_backward(h, st, h->gt_rel, h->d_relflat, Dr, 0, (long long)B * Dr);
+        mlp_backward(h, st, h->lse, lin, h->d_locsal, h->lse_h[0], h->d_h, h->d_locflat, 0);
+        gtrunk_backward(h, st, h->gt_loc, h->d_locflat, Dl, 0, (long long)B * Dl);
     } else {
         const MlpIn se_in = {a.flat, D, (long long)B * D, B, B, D};
         mlp_backward(h, st, h->se, se_in, h->d_psi, q.se_h, h->d_h, h->d_flat, 0);
@@ -1548,8 +1581,10 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     h->da6 = cfg->kind == MAEXP_LEARNER_DA6 || trunk == MAEXP_IQN_TRUNK_DA6;
     h->da3 = cfg->kind == MAEXP_LEARNER_DA3 || h->da6 || trunk != 0;  // da3: "has transformer stacks"
     h->area_mask = cfg->area_mask; h->X = cfg->size_x; h->Y = cfg->size_y;
-    h->relative_conv = cfg->kind == MAEXP_LEARNER_DQN_CONV_MLP && cfg->area_mask == MAEXP_MASK_RELATIVE;
-    h->merged_conv = cfg->kind == MAEXP_LEARNER_DQN_CONV_MLP && cfg->area_mask == MAEXP_MASK_MERGED;
+    // conv trunks on the decoded canvas: ConvMLP / IQN on the relative view, MergedConvMLP / MergedIQN on the merged view
+    const bool conv_kind = cfg->kind == MAEXP_LEARNER_DQN_CONV_MLP || (cfg->kind == MAEXP_LEARNER_IQN && trunk == MAEXP_IQN_TRUNK_CONV);
+    h->relative_conv = conv_kind && cfg->area_mask == MAEXP_MASK_RELATIVE;
+    h->merged_conv = conv_kind && cfg->area_mask == MAEXP_MASK_MERGED;
     h->merged_da3 = (cfg->kind == MAEXP_LEARNER_DA3 && cfg->area_mask == MAEXP_MASK_MERGED) || trunk == MAEXP_IQN_TRUNK_MERGED_DA3;
     if (trunk == MAEXP_IQN_TRUNK_DA3 && cfg->area_mask == MAEXP_MASK_MERGED) { delete h; return fail("maexp_learner_create: the DA3 IQN trunk reads the local or relative view"); }
     h->relative_vit = h->da3 && !h->da6 && !h->merged_da3 && cfg->area_mask == MAEXP_MASK_RELATIVE;
@@ -1557,7 +1592,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (trunk == MAEXP_IQN_TRUNK_MERGED_DA3 && cfg->area_mask != MAEXP_MASK_MERGED) { delete h; return fail("maexp_learner_create: the MergedDA3 IQN trunk reads the merged view"); }
     const bool gmodel = h->relative_conv || h->merged_conv || h->merged_da3;
     if (h->da6 && (cfg->area_mask != MAEXP_MASK_MERGED || h->X < 4 || h->Y < 4)) { delete h; return fail("maexp_learner_create: DA6 reads the merged view (area_mask merged, size_x / size_y set)"); }
-    if (cfg->area_mask != MAEXP_MASK_LOCAL && !gmodel && !h->da6 && !h->relative_vit) { delete h; return fail("maexp_learner_create: relative / merged views are implemented for conv_mlp (dqn) and da3 (merged)"); }
+    if (cfg->area_mask != MAEXP_MASK_LOCAL && !gmodel && !h->da6 && !h->relative_vit) { delete h; return fail("maexp_learner_create: relative / merged views are implemented for conv_mlp (dqn), iqn, da3 and da6"); }
     if (gmodel && (h->X < 4 || h->Y < 4)) { delete h; return fail("maexp_learner_create: size_x / size_y missing for a relative / merged model"); }
     h->has_conv = cfg->kind != MAEXP_LEARNER_DQN_MLP && !h->da3 && !gmodel;
     h->dist = cfg->kind == MAEXP_LEARNER_C51 || cfg->kind == MAEXP_LEARNER_QR;
@@ -1593,6 +1628,10 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     } else if (h->merged_conv) {  // MergedConvMLP (conv_mlp.py:69-108); the parent's `conv` keeps unused parameters
         maexp_learner::GTrunk unused;
         set_trunk(unused, "conv", h->C, h->X, h->Y);
+        if (cfg->kind == MAEXP_LEARNER_IQN) {  // IQN.__init__'s state_embedder on the unused trunk (customs/iqn.py:51-53,167)
+            add("state_embedder.fc_list.0.weight", (long long)h->H * unused.D); add("state_embedder.fc_list.0.bias", h->H);
+            add("state_embedder.fc_post.weight", (long long)unused.D * h->H); add("state_embedder.fc_post.bias", unused.D);
+        }
         set_trunk(h->gt_loc, "local_conv", h->C, h->V, h->V);
         set_trunk(h->gt_rel, "relative_conv", 1, h->X, h->Y);
         h->Drel = h->gt_rel.D; h->Dloc = h->gt_loc.D; h->D = h->Drel + h->Dloc;
@@ -1706,12 +1745,19 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         add_head("drl_head.fc_A", h->A);
     } else if (h->da3) {
         // no MLP heads: the drl_head is part of the layout above
-    } else if (h->relative_conv || h->merged_conv) {
+    } else if ((h->relative_conv || h->merged_conv) && !h->iqn) {
         add_head("mlp", h->A);
     } else if (h->iqn) {  // state_dict order of customs/iqn.py:43-67
-        add_head("state_embedder", h->D);
-        h->se = h->heads.back();
-        h->heads.pop_back();
+        if (h->merged_conv) {  // MergedIQN: one embedder per branch (customs/iqn.py:183-188)
+            const int keepD = h->D;
+            h->D = h->Dloc; add_head("local_state_embedder", h->Dloc); h->lse = h->heads.back(); h->heads.pop_back();
+            h->D = h->Drel; add_head("relative_state_embedder", h->Drel); h->rse = h->heads.back(); h->heads.pop_back();
+            h->D = keepD;
+        } else {
+            add_head("state_embedder", h->D);
+            h->se = h->heads.back();
+            h->heads.pop_back();
+        }
         h->o_cw = add("cosine_net.net.0.weight", (long long)h->D * h->ncos);
         h->o_cb = add("cosine_net.net.0.bias", h->D);
         add_head("fc_V", 1);
@@ -1852,16 +1898,24 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         for (int k = 0; k < 3; ++k) {
             rc |= lalloc(h, &h->canvas[k], G * B * (h->relative_conv ? h->C : 1) * h->X * h->Y);
             rc |= lalloc(h, &h->feat[k], G * B * Dt);
-            if (h->merged_da3) {
+            if (h->merged_da3 || (h->iqn && h->merged_conv)) {
                 rc |= lalloc(h, &h->rel_flat[k], G * B * h->Drel);
                 rc |= lalloc(h, &h->rse_h[k], G * B * h->H);
                 rc |= lalloc(h, &h->rse_out[k], G * B * h->Drel);
             }
+            if (h->iqn && h->merged_conv) {
+                rc |= lalloc(h, &h->lse_h[k], G * B * h->H);
+                rc |= lalloc(h, &h->lse_out[k], G * B * h->Dloc);
+            }
         }
         rc |= lalloc(h, &h->d_feat, G * B * Dt);
-        if (h->merged_da3) {
+        if (h->merged_da3 || (h->iqn && h->merged_conv)) {
             rc |= lalloc(h, &h->d_relsal, G * B * h->Drel);
             rc |= lalloc(h, &h->d_relflat, G * B * h->Drel);
+        }
+        if (h->iqn && h->merged_conv) {
+            rc |= lalloc(h, &h->d_locsal, G * B * h->Dloc);
+            rc |= lalloc(h, &h->d_locflat, G * B * h->Dloc);
         }
     }
     if (h->iqn && h->da3)  // the embedding's producer reads its output gradient from its own buffer

@@ -58,7 +58,12 @@ def configs():
     rda3["agent_type"] = "attention"
     rda3_iqn = attn_iqn("relative", "da3_iqn")
     rda3_iqn["model"]["patch_size"] = 3
-    return {"relative_da3": (rda3, [4, *SIZE]), "relative_da3_iqn": (rda3_iqn, [4, *SIZE]),
+    def conv_iqn(mask):
+        c = view(mask, "iqn", "iqn", num_quantiles=4, num_quantiles_dash=4, num_cosines=4)
+        c["objects_channel"], c["agents_channel"] = False, False
+        return c
+    return {"relative_iqn": (conv_iqn("relative"), [4, *SIZE]), "merged_iqn": (conv_iqn("merged"), [4, *SIZE]),
+            "relative_da3": (rda3, [4, *SIZE]), "relative_da3_iqn": (rda3_iqn, [4, *SIZE]),
             "da3_iqn": (attn_iqn("local", "da3_iqn"), [4, VIEW, VIEW]), "merged_da3_iqn": (attn_iqn("merged", "da3_iqn"), [4, *SIZE]),
             "da6_iqn": (attn_iqn("merged", "da6_iqn"), [4, *SIZE]),
             "da6": (da6, [4, *SIZE]),"relative_conv_mlp": (rel, [4, *SIZE]), "merged_conv_mlp": (mconv, [4, *SIZE]), "merged_da3": (mda3, [4, *SIZE]),
@@ -94,8 +99,8 @@ def main():
         torch.manual_seed(921)
         brain = generate_brain(config=rr.to_dictconfig(cfg), obs_shape=shape, act_size=4)
         masked = kind in ("relative_conv_mlp", "merged_conv_mlp", "merged_da3", "da6", "merged_da3_iqn", "da6_iqn",
-                          "relative_da3", "relative_da3_iqn")
-        is_iqn = kind in ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn", "relative_da3_iqn")
+                          "relative_da3", "relative_da3_iqn", "relative_iqn", "merged_iqn")
+        is_iqn = kind in ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn", "relative_da3_iqn", "relative_iqn", "merged_iqn")
         with torch.no_grad():  # zero-initialised embeddings: perturb so the fixtures exercise them
             for name in {"da3_iqn": ("saliency_vector", "pos_embed"), "relative_da3": ("saliency_vector", "pos_embed"),
                          "relative_da3_iqn": ("saliency_vector", "pos_embed"), "merged_da3_iqn": ("local_saliency_vector", "local_pos_embed"),

@@ -11,12 +11,12 @@ from oracle.torch_learner import TorchLearner
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KINDS = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLDEN, "learner_*.npz")))
 ATOMS = {"dqn_conv_mlp": 1, "c51": 51, "qr": 100, "iqn": 4, "da3": 1, "da6": 1}
-IQN_KINDS = ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn", "relative_da3_iqn")
-TRUNKS = {"relative_da3_iqn": "da3_iqn"}  # fixture name -> state-embedding trunk of the IQN head (default: the name)
+IQN_KINDS = ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn", "relative_da3_iqn", "relative_iqn", "merged_iqn")
+TRUNKS = {"relative_da3_iqn": "da3_iqn", "relative_iqn": "iqn"}  # fixture name -> state-embedding trunk of the IQN head (default: the name)
 # fixtures of the relative / merged views -> (network kind, attention heads)
 MASKED = {"relative_conv_mlp": ("dqn_conv_mlp", 4), "merged_conv_mlp": ("dqn_conv_mlp", 4), "merged_da3": ("da3", 2),
           "da6": ("da6", 2), "merged_da3_iqn": ("iqn", 2), "da6_iqn": ("iqn", 2), "relative_da3": ("da3", 2),
-          "relative_da3_iqn": ("iqn", 2)}
+          "relative_da3_iqn": ("iqn", 2), "relative_iqn": ("iqn", 2), "merged_iqn": ("iqn", 2)}
 
 
 def load(kind):

@@ -70,7 +70,7 @@ def test_cuda_learner_matches_reference_fixture(kind):
 @pytest.mark.parametrize("kind,B", [("dqn_conv_mlp", 32), ("c51", 256), ("qr", 256), ("iqn", 256), ("da3", 32),
                                     ("relative_conv_mlp", 32), ("merged_conv_mlp", 32), ("merged_da3", 32), ("da6", 32),
                                     ("da3_iqn", 32), ("merged_da3_iqn", 32), ("da6_iqn", 32), ("relative_da3", 32),
-                                    ("relative_da3_iqn", 32)])
+                                    ("relative_da3_iqn", 32), ("relative_iqn", 32), ("merged_iqn", 32)])
 def test_cuda_learner_group_matches_torch_oracle(kind, B):
     """G independent networks with different weights and batches, BASELINE batch sizes."""
     G = 3
