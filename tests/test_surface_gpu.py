@@ -172,3 +172,33 @@ def test_evaluator_greedy_rollouts_with_saved_weights(tmp_path):
     assert runs[0][0]["episode/objects_generated"] >= cfg.num_objects
     with pytest.raises(ValueError):
         generate_evaluator(cfg.merged_with(evaluator="nope"), trainer.env)
+
+
+@pytest.mark.parametrize("environment,brain,model,mask,types,tasks", [
+    ("sequential", "da3_iqn", "da3_iqn", "merged", 3, ["0", "0", "1", "1", "2", "2", "012", "01"]),
+    ("junctional", "da3_iqn", "da6_iqn", "merged", 5, ["0", "0", "12", "12", "13", "13", "4", "4"]),
+    ("sequential", "da6", "da6", "merged", 3, ["0", "0", "1", "1", "2", "2", "012", "01"]),
+    ("default", "iqn", "iqn", "relative", 1, ["0"] * 8),
+    ("sequential", "da3", "da3", "relative", 2, ["0", "1"] * 4),
+])
+def test_trainer_on_shipped_experiment_shapes(environment, brain, model, mask, types, tasks):
+    """The combinations of configs/experiments/IJCNN2025 (central_room, 8 agents, individual / object_types views):
+    environment, brain, model and view wired through generate_trainer for a short run."""
+    from maexp_b200.core.handlers.trainers import generate_trainer
+    from tests.cuda_backend import make_env
+    xy8 = [[-2, 2], [2, 2], [-2, -2], [2, -2], [0, 2], [0, -2], [2, 0], [-2, 0]]
+    m = dict(name=model, embed_dim=32, patch_size=5, relative_patch_size=5, local_patch_size=1, block_loop=1, num_heads=2,
+             mlp_ratio=2.0, attention="normal", af_lambd=0.5, hidden_channels=[8], output_channel=16, hidden_kernels=[2, 2],
+             hidden_strides=[1, 1], conv_afs=["max_pool2d", "max_pool2d"], af_kernels=[2, 2], af_strides=[2, 2],
+             hidden_layer_sizes=[32], fc_afs=["relu"], num_quantiles=8, num_quantiles_dash=8, num_cosines=8)
+    from maexp_b200.config import make_config
+    cfg = make_config(environment=environment, map=dict(name="central_room", SIZE_X=25, SIZE_Y=25), type_objects=types,
+                      num_objects=40, agent_tasks=tasks, init_xys=xy8, agent_view_method="individual",
+                      object_view_method="object_types", observation_area_mask=mask, agent_type="attention", trainer="attention",
+                      brain=brain, model=m, max_episode_length=6, batch_size=8, populate_steps=4 * 16, capacity=16 * 16,
+                      synchronize_frequency=1)
+    trainer = generate_trainer(cfg, make_env(cfg, 16, auto_reset=True))
+    before = trainer.learner.params().clone()
+    hist = trainer.run(max_epochs=1)
+    assert np.isfinite(hist[-1]["loss"]) and not torch.equal(trainer.learner.params(), before)
+    assert trainer.env.stats()["error_flag"] == 0
