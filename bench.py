@@ -185,6 +185,8 @@ def run_ours(args, rank, local_rank, world):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -228,17 +230,18 @@ def run_ours(args, rank, local_rank, world):
     env_steps = after["env_steps"] - before["env_steps"]  # resets (1 in L+1 calls per env) are not counted
 
     # ---- end to end through the host-buffer C-ABI entry point: every step copies its pinned actions in and its
-    #      rewards / dones / was_reset out; copies and kernels of consecutive steps overlap (3 steps in flight)
+    #      rewards / done flags / was_reset out (compact encoding: int8 rewards in {-1,0,1}, one done flag per env —
+    #      lossless for the default reward mode); copies and kernels of consecutive steps overlap (3 steps in flight)
     depth = 4
     hb = [{"actions": torch.randint(0, 4, (E, N), dtype=torch.int8).pin_memory(),
-           "rewards": torch.empty((E, N), dtype=torch.float32).pin_memory(),
-           "dones": torch.empty((E, N), dtype=torch.uint8).pin_memory(),
+           "rewards": torch.empty((E, N), dtype=torch.int8).pin_memory(),
+           "done": torch.empty((E,), dtype=torch.uint8).pin_memory(),
            "was_reset": torch.empty((E,), dtype=torch.uint8).pin_memory()} for _ in range(depth)]
 
     def host_step(i, tick):
         b = hb[i % depth]
-        return env.step_host_async(b["actions"], ring.obs[tick % RING_SLOTS], b["rewards"], b["dones"], b["was_reset"],
-                                   tick=tick)
+        return env.step_host_compact_async(b["actions"], ring.obs[tick % RING_SLOTS], b["rewards"], b["done"], b["was_reset"],
+                                           tick=tick)
     for i in range(3):
         host_step(i, tick)
         tick += 1
@@ -315,10 +318,10 @@ def run_ours(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": config_block(E),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * N, "d2h_bytes_per_step": E * N * 5 + E,
-                    "steps": k2, "note": "maexp_env_step_host_async: pinned actions H2D, rewards+dones+was_reset D2H every "
-                                         "step on copy streams, 3 steps in flight, wall clock until the last step's "
-                                         "results are in host memory; observations stay in the device replay ring"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * N, "d2h_bytes_per_step": E * N + 2 * E,
+                    "steps": k2, "note": "maexp_env_step_host_compact_async: pinned actions H2D, int8 rewards + per-env done + "
+                                         "was_reset D2H every step on copy streams, 3 steps in flight, wall clock until the "
+                                         "last step's results are in host memory; observations stay in the device replay ring"},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,

@@ -93,6 +93,9 @@ typedef struct {
     int8_t *objects;       /* [E,N,T,X,Y] objects_matrix snapshot at agent i's observation time */
     uint8_t *destination;  /* [E,N] selected destination mask per agent ("destination" key = table row) */
     int8_t *actions_taken; /* [E,N] the actions executed by this call (given or Philox-drawn); -1 on reset */
+    int8_t *rewards_i8;    /* [E,N] compact rewards for host-driven rollouts: exactly -1 / 0 / +1, so only written for the
+                              default reward mode (shared rewards are fractions) */
+    uint8_t *done_env;     /* [E] done_n[0] (done_ind is the same for every agent, default_environment.py:233-237) */
     int32_t *heatmaps;     /* optional visit statistics of default_environment.py:37-61,118-148,196-231,172, summed over ALL
                               environments with atomics (the caller zeroes them, as reset() does in the reference):
                               [agents N·X·Y | complete N·X·Y | objects T·X·Y | objects_left T·X·Y | wall_collision X·Y |
@@ -141,6 +144,13 @@ int maexp_env_step_host_async(maexp_env *env, uint32_t tick, const int8_t *actio
                               float *rewards_host, uint8_t *dones_host, uint8_t *was_reset_host, void *stream,
                               uint64_t *ticket);
 int maexp_env_host_wait(maexp_env *env, uint64_t ticket);
+
+/* The same pipelined call with the compact result encoding (6.5 bytes per env instead of 41 for N = 8, which keeps
+ * eight ranks inside the host's PCIe bandwidth): rewards int8 [E,N] in {-1,0,+1}, one done flag per env.
+ * Only for the default reward mode (returns an error for shared rewards, whose values are fractions). */
+int maexp_env_step_host_compact_async(maexp_env *env, uint32_t tick, const int8_t *actions_host, float *obs_ring_slot,
+                                      int8_t *rewards_i8_host, uint8_t *done_env_host, uint8_t *was_reset_host,
+                                      void *stream, uint64_t *ticket);
 
 /* State taps: map.agents_matrix / objects_matrix / destination_area_matrix and the env counters
  * (default_environment.py:65-69) in the reference's dtypes.  Device pointers, may be NULL. */

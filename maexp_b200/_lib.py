@@ -37,7 +37,8 @@ class Tables(C.Structure):
 
 class ObsOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates",
-                                           "positions", "objects", "destination", "actions_taken", "heatmaps")]
+                                           "positions", "objects", "destination", "actions_taken", "rewards_i8", "done_env",
+                                           "heatmaps")]
 
 
 class ReplayView(C.Structure):
@@ -77,6 +78,8 @@ SYMBOLS = {
     "maexp_env_step_host_async": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "maexp_env_host_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "maexp_env_step_host_compact_async": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "maexp_env_get_state": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
     "maexp_env_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "maexp_env_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32),

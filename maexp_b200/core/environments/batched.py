@@ -205,7 +205,7 @@ class BatchedEnvironment:
     def _out_struct(self, out):
         s = _lib.ObsOut()
         for name in ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates", "positions", "objects",
-                     "destination", "actions_taken", "heatmaps"):
+                     "destination", "actions_taken", "rewards_i8", "done_env", "heatmaps"):
             t = out.get(name)
             if t is not None:
                 assert t.is_cuda and t.is_contiguous()
@@ -254,6 +254,17 @@ class BatchedEnvironment:
         _lib.check(self.lib.maexp_env_step_host_async(self.h, self._next_tick(tick), hp(actions_host),
                                                       C.c_void_p(obs_slot.data_ptr()), hp(rewards_host), hp(dones_host),
                                                       hp(was_reset_host), self._stream(), C.byref(ticket)))
+        return ticket.value
+
+    def step_host_compact_async(self, actions_host, obs_slot, rewards_i8_host, done_env_host, was_reset_host, tick=None):
+        """step_host_async with int8 rewards [E,N] and one done flag per env (default reward mode only)."""
+        def hp(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        ticket = C.c_uint64()
+        _lib.check(self.lib.maexp_env_step_host_compact_async(self.h, self._next_tick(tick), hp(actions_host),
+                                                              C.c_void_p(obs_slot.data_ptr()), hp(rewards_i8_host),
+                                                              hp(done_env_host), hp(was_reset_host), self._stream(),
+                                                              C.byref(ticket)))
         return ticket.value
 
     def host_wait(self, ticket=0):

@@ -118,9 +118,9 @@ struct maexp_env {
     uint8_t *d_dones = nullptr, *d_was_reset = nullptr;
     // pipelined host entry point: kHostDepth steps in flight, copies on their own streams
     struct HostSlot {
-        int8_t *actions = nullptr;
+        int8_t *actions = nullptr, *rewards_i8 = nullptr;
         float *rewards = nullptr;
-        uint8_t *dones = nullptr, *was_reset = nullptr;
+        uint8_t *dones = nullptr, *was_reset = nullptr, *done_env = nullptr;
         cudaEvent_t in = nullptr, stepped = nullptr, out = nullptr;
     };
     static constexpr int kHostDepth = 3;
@@ -185,7 +185,7 @@ int launch(maexp_env *h, uint32_t tick, int force_reset, const uint8_t *env_mask
     if ((p.N & 7) == 0) {  // the kernel writes eight agents per vector store
         auto misaligned = [](const void *ptr, size_t a) { return ptr && (reinterpret_cast<uintptr_t>(ptr) & (a - 1)); };
         if (misaligned(p.out.rewards, 16) || misaligned(p.out.dones, 8) || misaligned(p.out.positions, 16) ||
-            misaligned(p.out.actions_taken, 8))
+            misaligned(p.out.actions_taken, 8) || misaligned(p.out.rewards_i8, 8))
             return fail("maexp_env_step: rewards / positions must be 16-byte aligned, dones / actions_taken 8-byte aligned");
     }
     if (misaligned_obs(p.out.obs) || misaligned_obs(p.out.obs_rel)) return fail("maexp_env_step: obs slots must be 16-byte aligned");
@@ -424,10 +424,15 @@ int64_t maexp_env_heatmap_ints(const maexp_env *h) {
     return (int64_t)(2 * h->p.N + 2 * h->p.T + 2) * h->p.X * h->p.Y;
 }
 
-int maexp_env_step_host_async(maexp_env *h, uint32_t tick, const int8_t *actions_host, float *obs_ring_slot,
-                              float *rewards_host, uint8_t *dones_host, uint8_t *was_reset_host, void *stream_,
-                              uint64_t *ticket) {
+}  // extern "C"
+
+namespace {
+// compact: rewards_host is int8 [E,N], dones_host is uint8 [E]
+int step_host_pipelined(maexp_env *h, uint32_t tick, const int8_t *actions_host, float *obs_ring_slot, void *rewards_host,
+                        uint8_t *dones_host, uint8_t *was_reset_host, void *stream_, uint64_t *ticket, bool compact) {
     if (!h) return fail("maexp_env_step_host_async: null handle");
+    if (compact && h->p.reward_mode != MAEXP_REWARD_DEFAULT)
+        return fail("maexp_env_step_host_compact_async: shared rewards are fractions, use maexp_env_step_host_async");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t E = (size_t)h->p.E, EN = E * h->p.N;
     if (!h->h2d) {
@@ -435,7 +440,7 @@ int maexp_env_step_host_async(maexp_env *h, uint32_t tick, const int8_t *actions
         MAEXP_CUDA(cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking));
         for (auto &sl : h->slots) {
             int rc = dev_alloc(h, &sl.actions, EN) | dev_alloc(h, &sl.rewards, EN) | dev_alloc(h, &sl.dones, EN) |
-                     dev_alloc(h, &sl.was_reset, E);
+                     dev_alloc(h, &sl.was_reset, E) | dev_alloc(h, &sl.rewards_i8, EN) | dev_alloc(h, &sl.done_env, E);
             if (rc) return -1;
             MAEXP_CUDA(cudaEventCreateWithFlags(&sl.in, cudaEventDisableTiming));
             MAEXP_CUDA(cudaEventCreateWithFlags(&sl.stepped, cudaEventDisableTiming));
@@ -453,19 +458,41 @@ int maexp_env_step_host_async(maexp_env *h, uint32_t tick, const int8_t *actions
     maexp_obs_out out;
     memset(&out, 0, sizeof(out));
     out.obs = obs_ring_slot;
-    out.rewards = sl.rewards;
-    out.dones = sl.dones;
+    if (compact) { out.rewards_i8 = sl.rewards_i8; out.done_env = sl.done_env; }
+    else { out.rewards = sl.rewards; out.dones = sl.dones; }
     out.was_reset = sl.was_reset;
     if (launch(h, tick, 0, nullptr, actions_host ? sl.actions : nullptr, nullptr, nullptr, &out, stream)) return -1;
     MAEXP_CUDA(cudaEventRecord(sl.stepped, stream));
     MAEXP_CUDA(cudaStreamWaitEvent(h->d2h, sl.stepped, 0));
-    if (rewards_host) MAEXP_CUDA(cudaMemcpyAsync(rewards_host, sl.rewards, EN * sizeof(float), cudaMemcpyDeviceToHost, h->d2h));
-    if (dones_host) MAEXP_CUDA(cudaMemcpyAsync(dones_host, sl.dones, EN, cudaMemcpyDeviceToHost, h->d2h));
+    if (compact) {
+        if (rewards_host) MAEXP_CUDA(cudaMemcpyAsync(rewards_host, sl.rewards_i8, EN, cudaMemcpyDeviceToHost, h->d2h));
+        if (dones_host) MAEXP_CUDA(cudaMemcpyAsync(dones_host, sl.done_env, E, cudaMemcpyDeviceToHost, h->d2h));
+    } else {
+        if (rewards_host) MAEXP_CUDA(cudaMemcpyAsync(rewards_host, sl.rewards, EN * sizeof(float), cudaMemcpyDeviceToHost, h->d2h));
+        if (dones_host) MAEXP_CUDA(cudaMemcpyAsync(dones_host, sl.dones, EN, cudaMemcpyDeviceToHost, h->d2h));
+    }
     if (was_reset_host) MAEXP_CUDA(cudaMemcpyAsync(was_reset_host, sl.was_reset, E, cudaMemcpyDeviceToHost, h->d2h));
     MAEXP_CUDA(cudaEventRecord(sl.out, h->d2h));
     h->issued += 1;
     if (ticket) *ticket = h->issued;
     return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int maexp_env_step_host_async(maexp_env *h, uint32_t tick, const int8_t *actions_host, float *obs_ring_slot,
+                              float *rewards_host, uint8_t *dones_host, uint8_t *was_reset_host, void *stream,
+                              uint64_t *ticket) {
+    return step_host_pipelined(h, tick, actions_host, obs_ring_slot, rewards_host, dones_host, was_reset_host, stream, ticket,
+                               false);
+}
+
+int maexp_env_step_host_compact_async(maexp_env *h, uint32_t tick, const int8_t *actions_host, float *obs_ring_slot,
+                                      int8_t *rewards_i8_host, uint8_t *done_env_host, uint8_t *was_reset_host, void *stream,
+                                      uint64_t *ticket) {
+    return step_host_pipelined(h, tick, actions_host, obs_ring_slot, rewards_i8_host, done_env_host, was_reset_host, stream,
+                               ticket, true);
 }
 
 int maexp_env_host_wait(maexp_env *h, uint64_t ticket) {

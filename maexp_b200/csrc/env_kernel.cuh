@@ -674,6 +674,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                     dst[0] = make_float4(reward_of(k0), reward_of(k0 + 1), reward_of(k0 + 2), reward_of(k0 + 3));
                     dst[1] = make_float4(reward_of(k0 + 4), reward_of(k0 + 5), reward_of(k0 + 6), reward_of(k0 + 7));
                 }
+                if (p.out.rewards_i8) {  // -1 / 0 / +1 as bytes (default reward mode)
+                    uint32_t r8[2] = {0u, 0u};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = k0 + j;
+                        const uint32_t v = is_reset ? 0u : ((rew_neg >> k) & 1u ? 0xFFu : ((rew_pos >> k) & 1u));
+                        r8[j >> 2] |= v << (8 * (j & 3));
+                    }
+                    *reinterpret_cast<uint2 *>(p.out.rewards_i8 + o) = make_uint2(r8[0], r8[1]);
+                }
                 if (p.out.dones) {
                     const uint32_t d = done_bits >> k0;  // bit k -> byte k
                     const uint32_t lo = (d & 1u) | ((d & 2u) << 7) | ((d & 4u) << 14) | ((d & 8u) << 21);
@@ -702,6 +712,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
         for (int k = 0; k < N; ++k) {
             const float r = reward_of(k);
             if (p.out.rewards) p.out.rewards[(size_t)env * N + k] = r;
+            if (p.out.rewards_i8) p.out.rewards_i8[(size_t)env * N + k] = (int8_t)r;
             if (p.out.dones) p.out.dones[(size_t)env * N + k] = (uint8_t)((done_bits >> k) & 1u);
             if (p.out.positions) {
                 p.out.positions[((size_t)env * N + k) * 2 + 0] = (int8_t)(mypos[k * EPW] & 0xFF);
@@ -716,6 +727,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
         }
         }
         if (p.out.was_reset) p.out.was_reset[env] = is_reset ? 1 : 0;
+        if (p.out.done_env) p.out.done_env[env] = (uint8_t)(done_bits & 1u);
         p.step[env] = stepc;
         p.pending[env] = (p.auto_reset && !is_reset && (done_bits & 1u)) ? 1 : 0;  // default_trainer.py:85
         *reinterpret_cast<int4 *>(p.counters + (size_t)env * 4) = make_int4(c_gen, c_done, c_ca, c_cw);

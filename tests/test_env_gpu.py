@@ -222,6 +222,31 @@ def test_pipelined_host_entry_point():
     assert resets > 0
 
 
+def test_compact_host_entry_point():
+    """maexp_env_step_host_compact_async: int8 rewards and one done flag per env carry the same information."""
+    cfg = baseline_config(5).merged_with(max_episode_length=5)
+    E, N, K = 200, 8, 8
+    b = CudaBackend(cfg, E, first_global_env_id=0, auto_reset=True, extras=False)
+    orc = Oracle(cfg, E, auto_reset=True, first_global_env_id=0)
+    b.reset(0), orc.reset(0)
+    rng = np.random.default_rng(6)
+    acts = [torch.from_numpy(rng.integers(0, 4, size=(E, N)).astype(np.int8)).pin_memory() for _ in range(K)]
+    rewards = [torch.empty((E, N), dtype=torch.int8).pin_memory() for _ in range(K)]
+    done = [torch.empty((E,), dtype=torch.uint8).pin_memory() for _ in range(K)]
+    was_reset = [torch.empty((E,), dtype=torch.uint8).pin_memory() for _ in range(K)]
+    slot = b.env.new_slot()
+    for k in range(K):
+        b.env.step_host_compact_async(acts[k], slot, rewards[k], done[k], was_reset[k], tick=k + 1)
+    b.env.host_wait()
+    for k in range(K):
+        o = orc.step(k + 1, actions=acts[k].numpy())
+        assert np.array_equal(rewards[k].numpy().astype(np.float32), o["rewards"]), k
+        assert np.array_equal(done[k].numpy(), o["dones"][:, 0]) and np.array_equal(was_reset[k].numpy(), o["was_reset"]), k
+    shared = CudaBackend(baseline_config(2), 32, auto_reset=True, extras=False)
+    with pytest.raises(Exception):
+        shared.env.step_host_compact_async(None, shared.env.new_slot(), rewards[0], done[0], was_reset[0], tick=1)
+
+
 def test_unsupported_configs_fail_loudly():
     from tests.cuda_backend import make_env
     with pytest.raises(ValueError):
