@@ -952,7 +952,9 @@ struct maexp_learner {
     // events, which also works under stream capture) with their own split-K workspaces
     float *splitk_side[2] = {nullptr, nullptr};
     cudaStream_t side[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_w[2] = {nullptr, nullptr};
+    float *d_h2 = nullptr, *d_hrow2 = nullptr;  // second hidden-gradient buffers: weight-gradient GEMMs of head k read
+                                                // theirs on a side stream while head k+1's data gradients are computed
     // activations of the three passes (0: online(s) kept for backward, 1: online(s'), 2: target(s'))
     struct Acts {
         float *col1, *y1, *p, *col2, *y2, *flat, *h[2], *out[2];
@@ -1049,6 +1051,42 @@ void colsum(cudaStream_t st, int G, const float *ones, const float *X, float *ou
     gemm(st, G, ones, X, out, nullptr, 1, N, M, 0, 0, N, 1, N, 1, 0, gX, gOut, 0, 0, accumulate);
 }
 
+// Weight / bias gradients never feed the data-gradient chain, so inside a backward pass that opts in (g_wg.h set) they
+// are issued on the two side streams, alternating, each behind an event recorded on the main stream at that point.
+struct WGradCtx {
+    maexp_learner *h = nullptr;
+    cudaStream_t main_stream = nullptr;
+    int next = 0;
+    bool used[2] = {false, false};
+} g_wg;
+
+cudaStream_t wgrad_begin(cudaStream_t st) {
+    if (!g_wg.h) return st;
+    maexp_learner *h = g_wg.h;
+    const int k = g_wg.next;
+    g_wg.next ^= 1;
+    cudaEventRecord(h->ev_w[k], st);
+    cudaStreamWaitEvent(h->side[k], h->ev_w[k], 0);
+    g_splitk_ws = h->splitk_side[k];
+    g_wg.used[k] = true;
+    return h->side[k];
+}
+void wgrad_end() {
+    if (g_wg.h) g_splitk_ws = g_wg.h->splitk_ws;
+}
+void wgrad_open(maexp_learner *h, cudaStream_t st) { g_wg = WGradCtx(); g_wg.h = h; g_wg.main_stream = st; }
+void wgrad_close() {  // join the side streams back into the main stream
+    maexp_learner *h = g_wg.h;
+    if (!h) return;
+    for (int k = 0; k < 2; ++k)
+        if (g_wg.used[k]) {
+            cudaEventRecord(h->ev_join[k], h->side[k]);
+            cudaStreamWaitEvent(g_wg.main_stream, h->ev_join[k], 0);
+        }
+    g_splitk_ws = h->splitk_ws;
+    g_wg = WGradCtx();
+}
+
 // ---- conv trunk: obs [G][B][obs_stride] -> a.flat [G][Bmax][D]
 void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, maexp_learner::Acts &a) {
     const int G = h->G, C = h->C, V = h->V, F1 = h->F1, F2 = h->F2;
@@ -1078,15 +1116,25 @@ void trunk_backward(maexp_learner *h, cudaStream_t st) {
     const long long gcol2 = (long long)B * H2 * H2 * F1 * 4, gy2 = (long long)B * H2 * H2 * F2;
     nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, st>>>(h->d_flat, h->d_y2, B, H2 * H2, F2, gy2, 1);
     const int M2 = B * H2 * H2;
-    gemm(st, G, h->d_y2, a.col2, h->grads + h->o_c2w, nullptr, F2, F1 * 4, M2, 1, F2, F1 * 4, 1, F1 * 4, 1, gy2, gcol2, P, 0);
-    colsum(st, G, h->ones, h->d_y2, h->grads + h->o_c2b, M2, F2, gy2, P);
+    {
+        cudaStream_t ws = wgrad_begin(st);
+        gemm(ws, G, h->d_y2, a.col2, h->grads + h->o_c2w, nullptr, F2, F1 * 4, M2, 1, F2, F1 * 4, 1, F1 * 4, 1, gy2, gcol2, P, 0);
+        colsum(ws, G, h->ones, h->d_y2, h->grads + h->o_c2b, M2, F2, gy2, P);
+        wgrad_end();
+    }
     gemm(st, G, h->d_y2, h->online + h->o_c2w, h->d_col2, nullptr, M2, F1 * 4, F2, F2, 1, F1 * 4, 1, F1 * 4, 1, gy2, P,
          gcol2, 0);
     col2im_kernel<<<grid1d((long long)B * Hp * Hp * F1, G), 256, 0, st>>>(h->d_col2, h->d_p, B, Hp, Hp, F1, gcol2, gp);
     pool_bwd_kernel<<<grid1d((long long)B * H1 * H1 * F1, G), 256, 0, st>>>(h->d_p, a.arg, h->d_y1, B, H1, H1, F1, gy1, gp);
     const int M1 = B * H1 * H1;
-    gemm(st, G, h->d_y1, a.col1, h->grads + h->o_c1w, nullptr, F1, C * 4, M1, 1, F1, C * 4, 1, C * 4, 1, gy1, gcol1, P, 0);
-    colsum(st, G, h->ones, h->d_y1, h->grads + h->o_c1b, M1, F1, gy1, P);
+    {   // the two conv1 reductions over B*H1*H1 rows run side by side
+        cudaStream_t ws = wgrad_begin(st);
+        gemm(ws, G, h->d_y1, a.col1, h->grads + h->o_c1w, nullptr, F1, C * 4, M1, 1, F1, C * 4, 1, C * 4, 1, gy1, gcol1, P, 0);
+        wgrad_end();
+        ws = wgrad_begin(st);
+        colsum(ws, G, h->ones, h->d_y1, h->grads + h->o_c1b, M1, F1, gy1, P);
+        wgrad_end();
+    }
 }
 
 // ---- MLP with one hidden ReLU layer on `rows` rows per group (mlp.py:28-34); buffers strided by rows_max
@@ -1113,11 +1161,19 @@ void mlp_backward(maexp_learner *h, cudaStream_t st, const HeadLayout &hd, const
                   const float *hbuf, float *dhbuf, float *dx, int accumulate_dx) {
     const int G = h->G, H = h->H, O = hd.out, rows = in.rows;
     const long long P = h->P, gO = in.rows_max * O, gH = in.rows_max * H;
-    gemm(st, G, dout, hbuf, h->grads + hd.w2, nullptr, O, H, rows, 1, O, H, 1, H, 1, gO, gH, P, 0);
-    colsum(st, G, h->ones, dout, h->grads + hd.b2, rows, O, gO, P);
+    {
+        cudaStream_t ws = wgrad_begin(st);
+        gemm(ws, G, dout, hbuf, h->grads + hd.w2, nullptr, O, H, rows, 1, O, H, 1, H, 1, gO, gH, P, 0);
+        colsum(ws, G, h->ones, dout, h->grads + hd.b2, rows, O, gO, P);
+        wgrad_end();
+    }
     gemm(st, G, dout, h->online + hd.w2, dhbuf, nullptr, rows, H, O, O, 1, H, 1, H, 1, gO, P, gH, 0, 0, 0, hbuf, gH);
-    gemm(st, G, dhbuf, in.x, h->grads + hd.w1, nullptr, H, in.din, rows, 1, H, in.x_row, 1, in.din, 1, gH, in.x_g, P, 0);
-    colsum(st, G, h->ones, dhbuf, h->grads + hd.b1, rows, H, gH, P);
+    {
+        cudaStream_t ws = wgrad_begin(st);
+        gemm(ws, G, dhbuf, in.x, h->grads + hd.w1, nullptr, H, in.din, rows, 1, H, in.x_row, 1, in.din, 1, gH, in.x_g, P, 0);
+        colsum(ws, G, h->ones, dhbuf, h->grads + hd.b1, rows, H, gH, P);
+        wgrad_end();
+    }
     if (dx)
         gemm(st, G, dhbuf, h->online + hd.w1, dx, nullptr, rows, in.din, H, H, 1, in.din, 1, in.din, 1, gH, P,
              in.rows_max * in.din, 0, 0, accumulate_dx);
@@ -1142,9 +1198,12 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
     MlpIn in;
     if (h->has_conv) in = {a.flat, h->D, (long long)B * h->D, B, B, h->D};
     else in = {obs, h->cfg.obs_stride, (long long)B * h->cfg.obs_stride, B, B, h->D};
+    wgrad_open(h, st);
     for (size_t k = 0; k < h->heads.size(); ++k)
-        mlp_backward(h, st, h->heads[k], in, h->d_out[k], a.h[k], h->d_h, h->has_conv ? h->d_flat : nullptr, k > 0);
+        mlp_backward(h, st, h->heads[k], in, h->d_out[k], a.h[k], k & 1 ? h->d_h2 : h->d_h, h->has_conv ? h->d_flat : nullptr,
+                     k > 0);
     if (h->has_conv) trunk_backward(h, st);
+    wgrad_close();
 }
 
 // ---- IQN (customs/iqn.py:88-139): quantiles of `nq` taus per sample; taus per sample [G][B][nq] or shared [G][nq]
@@ -1525,7 +1584,10 @@ void iqn_backward(maexp_learner *h, cudaStream_t st, int nq) {
     const long long P = h->P, R = h->rows_max;
     const float *psi = h->merged_da3 ? h->feat[0] : h->da3 ? h->vloc.a[0].nf : q.psi;
     const MlpIn e_in = {q.e, D, R * D, rows, R, D};
-    for (int k = 0; k < 2; ++k) mlp_backward(h, st, h->heads[k], e_in, h->d_out[k], q.hrow[k], h->d_hrow, h->d_e, k > 0);
+    const bool side_wgrads = !h->da3 && !h->relative_conv && !h->merged_conv;  // plain IQN: buffers audited for the overlap
+    if (side_wgrads) wgrad_open(h, st);
+    for (int k = 0; k < 2; ++k)
+        mlp_backward(h, st, h->heads[k], e_in, h->d_out[k], q.hrow[k], k & 1 ? h->d_hrow2 : h->d_hrow, h->d_e, k > 0);
     // h->d_psi aliases the buffer the embedding's producer reads its output gradient from (set in create)
     iqn_hadamard_bwd_kernel<<<grid1d((long long)B * D, G), 256, 0, st>>>(h->d_e, psi, q.phi, h->d_phi, h->d_psi, B, nq, D,
                                                                          (long long)B * D, R * D);
@@ -1560,6 +1622,7 @@ void iqn_backward(maexp_learner *h, cudaStream_t st, int nq) {
         mlp_backward(h, st, h->se, se_in, h->d_psi, q.se_h, h->d_h, h->d_flat, 0);
         trunk_backward(h, st);
     }
+    if (side_wgrads) wgrad_close();
 }
 
 }  // namespace
@@ -1785,6 +1848,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         rc |= lalloc(h, &h->splitk_side[k], (size_t)kSplitWorkspaceFloats);
         rc |= cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking) != cudaSuccess;
         rc |= cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming) != cudaSuccess;
+        rc |= cudaEventCreateWithFlags(&h->ev_w[k], cudaEventDisableTiming) != cudaSuccess;
     }
     rc |= cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess;
     for (int k = 0; k < 3; ++k) {
@@ -1867,8 +1931,10 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         rc |= lalloc(h, &h->d_psi, G * B * h->D);
 
         rc |= lalloc(h, &h->d_hrow, G * R * h->H);
+        rc |= lalloc(h, &h->d_hrow2, G * R * h->H);
     }
     rc |= lalloc(h, &h->d_h, G * B * h->H);
+    rc |= lalloc(h, &h->d_h2, G * B * h->H);
     if (h->has_conv) {
         rc |= lalloc(h, &h->d_flat, G * B * h->D);
         rc |= lalloc(h, &h->d_y2, G * B * h->D);
@@ -1937,6 +2003,7 @@ void maexp_learner_destroy(maexp_learner *h) {
     for (int k = 0; k < 2; ++k) {
         if (h->side[k]) { cudaStreamSynchronize(h->side[k]); cudaStreamDestroy(h->side[k]); }
         if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
+        if (h->ev_w[k]) cudaEventDestroy(h->ev_w[k]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (void *d : h->allocs) cudaFree(d);

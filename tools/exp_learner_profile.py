@@ -40,3 +40,12 @@ tot = sum(v[1] for v in agg.values())
 print(f"span per update {(t1 - t0) / R:.1f} us, sum of kernel times per update {tot / R:.1f} us")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
     print(f"{k:62s} n/update {n / R:6.1f}  us/update {t / R:8.1f}  avg {t / n:6.2f}")
+
+# kernel sequence of ONE replay in start order (side-stream passes interleave)
+with profile(activities=[ProfilerActivity.CUDA]) as prof1:
+    gr.replay()
+    torch.cuda.synchronize()
+ev = sorted([e for e in prof1.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
+t0 = ev[0].time_range.start
+for e in ev:
+    print(f"{e.time_range.start - t0:8.1f} +{e.time_range.end - e.time_range.start:6.1f}  {e.name[:70]}")
