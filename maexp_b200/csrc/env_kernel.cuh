@@ -122,6 +122,9 @@ struct BitStream {
     }
 };
 
+#ifndef MAEXP_NOISE_UNROLL
+#define MAEXP_NOISE_UNROLL 2
+#endif
 template <int V, int EPW, int NOISE, int NSPEC>
 #ifndef MAEXP_MINB
 #define MAEXP_MINB 7
@@ -498,7 +501,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             const size_t base = ((size_t)i * p.E + env0) * p.slot_floats;
             float *const dst = p.out.obs + base;
             float *const dst_rel = (p.merged && p.out.obs_rel) ? p.out.obs_rel + base : nullptr;
-            const bool check = (NOISE != MAEXP_NOISE_NONE) || !all_on;
+            const bool check = !all_on;  // some env of the group is masked out of this call
+            // envs interleaved per lane in the expansion loops: independent Philox chains of the noise variants overlap
+            constexpr int kUnrollEnvs = NOISE != MAEXP_NOISE_NONE ? MAEXP_NOISE_UNROLL : 4;
 
             // per-element noise constants of quad q (the same for every env a lane visits): scale of the draw, threshold,
             // and the +1 / -1 the flip noise wraps around channel 2 (flip_observation_noise.py:31,44)
@@ -598,7 +603,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                     for (int e = 0; e < nenv; ++e, wq += ws, dp += env_stride)
                         store_quad(reinterpret_cast<float4 *>(dp), lut[(*wq >> sh) & 0xFu]);
                 } else if (!check) {
-#pragma unroll 4
+#pragma unroll kUnrollEnvs
                     for (int e = 0; e < nenv; ++e) emit(e, q, wq[e * ws], sh, lut_off, qn);
                 } else {
                     for (int e = 0; e < nenv; ++e)
@@ -623,9 +628,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
 #pragma unroll 2
                         for (int e = esub; e < nenv; e += estep, wq += estep * ws, dp += estep * env_stride)
                             store_quad(reinterpret_cast<float4 *>(dp), lut[(*wq >> sh) & 0xFu]);
+                    } else if (!check) {
+#pragma unroll kUnrollEnvs
+                        for (int e = esub; e < nenv; e += estep) emit(e, q, wq[(e - esub) * ws], sh, lut_off, qn);
                     } else {
                         for (int e = esub; e < nenv; e += estep, wq += estep * ws)
-                            if (!check || (s_active[e] & 1)) emit(e, q, *wq, sh, lut_off, qn);
+                            if (s_active[e] & 1) emit(e, q, *wq, sh, lut_off, qn);
                     }
                 }
             }

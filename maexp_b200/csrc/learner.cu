@@ -138,7 +138,15 @@ __global__ void splitk_reduce_kernel(const GemmArgs a, int ksplit, int G, const 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int m = (int)(i / a.N), n = (int)(i - (long long)m * a.N);
         float v = 0.0f;
-        for (int s = 0; s < ksplit; ++s) v = __fadd_rn(v, part[((size_t)s * G + g) * total + i]);
+        int s = 0;
+        for (; s + 8 <= ksplit; s += 8) {  // eight independent loads in flight, summed in slice order
+            float t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = part[((size_t)(s + j) * G + g) * total + i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v = __fadd_rn(v, t[j]);
+        }
+        for (; s < ksplit; ++s) v = __fadd_rn(v, part[((size_t)s * G + g) * total + i]);
         if (a.bias) v = __fadd_rn(v, a.bias[(size_t)g * a.gBias + n]);
         if (a.relu) v = fmaxf(v, 0.0f);
         const size_t ci = (size_t)m * a.scm + (size_t)n * a.scn;
