@@ -239,6 +239,8 @@ typedef struct {
     int32_t local_patch_size; /* DA6: model.local_patch_size; DA6_IQN: 1 (da6_iqn.py:55-58) */
     int32_t relative_patch_size; /* DA6: model.relative_patch_size; DA6_IQN: 5 (da6_iqn.py:50-53) */
     int32_t iqn_trunk;        /* MAEXP_LEARNER_IQN only: which network produces the state embedding, MAEXP_IQN_TRUNK_* */
+    int32_t optimizer;        /* generate_optimizer (optimizers/__init__.py:17-42): 0 = optim.RMSprop, 1 = optim.Adam */
+    float beta1, beta2;       /* Adam betas (configs/opt/adam.yaml); learning_rate and eps are shared */
 } maexp_learner_cfg;
 
 /* state-embedding producer under the IQN head (brain iqn / da3_iqn, iqn_brain.py:60-115, da3_iqn_brain.py:14-54) */

@@ -91,8 +91,9 @@ class LearnerGroup:
         self.K = C_ * V * V
         self.obs_stride = int(obs_stride or (self.K + 7) // 8 * 8)
         m, opt = config.model, config.opt
-        if opt.name != "rmsprop":
-            raise ValueError("only opt=rmsprop is implemented (all shipped configs use it)")
+        if opt.name not in ("rmsprop", "adam"):  # optimizers/__init__.py:17-42
+            logger.warning(f"Unexpected optimizer name is given. config.opt.name: {opt.name}")
+            raise ValueError()
         cfg = _lib.LearnerCfg()
         cfg.kind = _lib.LEARNER_KINDS[self.kind]
         cfg.num_agents, cfg.batch_size, cfg.channels, cfg.visible_range = self.G, self.B, C_, V
@@ -124,8 +125,11 @@ class LearnerGroup:
         if self.kind == "c51":
             cfg.v_min, cfg.v_max = float(m.V_min), float(m.V_max)
             cfg.delta_z = (float(m.V_max) - float(m.V_min)) / (self.Z - 1)  # python double -> fp32, as torch does
-        cfg.learning_rate, cfg.alpha, cfg.eps = float(opt.learning_rate), float(opt.alpha), float(opt.eps)
-        cfg.one_minus_alpha = 1.0 - float(opt.alpha)
+        cfg.learning_rate, cfg.eps = float(opt.learning_rate), float(opt.eps)
+        if opt.name == "adam":
+            cfg.optimizer, cfg.beta1, cfg.beta2 = 1, float(opt.betas[0]), float(opt.betas[1])
+        else:
+            cfg.alpha, cfg.one_minus_alpha = float(opt.alpha), 1.0 - float(opt.alpha)
         cfg.max_norm = max_norm
         handle = C.c_void_p()
         with torch.cuda.device(self.device):

@@ -903,6 +903,41 @@ __global__ void sqnorm_partial_kernel(const float *grads, float *partial, long l
 }
 
 // nn.utils.clip_grad_norm_(max_norm) + optim.RMSprop(lr, alpha, eps).step()  (optimizers/__init__.py:28-33)
+// optim.Adam single-tensor update (torch/optim/adam.py _single_tensor_adam, no amsgrad / weight decay) after the same clip:
+// exp_avg.lerp_(g, 1-b1); exp_avg_sq = b2*exp_avg_sq + (1-b2)*g*g; p -= (lr / (1-b1^t)) * exp_avg / (sqrt(exp_avg_sq)/sqrt(1-b2^t) + eps)
+// with the scalar factors evaluated in double, as Python does.  steps[g] was incremented by adam_step_kernel.
+__global__ void clip_adam_kernel(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, const float *partial,
+                                 int nparts, long long P, float scale, float max_norm, float lr, float beta1, float beta2,
+                                 float eps, const uint8_t *active, const int *steps, float *norm_out) {
+    const int g = blockIdx.y;
+    if (active && !active[g]) return;
+    float total = 0.0f;
+    for (int i = 0; i < nparts; ++i) total = __fadd_rn(total, partial[(size_t)g * nparts + i]);
+    const float norm = sqrtf(total);
+    const float coef = fminf(__fdiv_rn(max_norm, __fadd_rn(norm, 1e-6f)), 1.0f);
+    if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) norm_out[g] = norm;
+    const double t = (double)steps[g];
+    const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+    const float step_size = (float)((double)lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+    const float w1 = (float)(1.0 - (double)beta1), w2 = (float)(1.0 - (double)beta2);
+    float *p = params + (size_t)g * P, *m = exp_avg + (size_t)g * P, *v = exp_avg_sq + (size_t)g * P;
+    const float *gr = grads + (size_t)g * P;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = __fmul_rn(__fmul_rn(gr[i], scale), coef);
+        const float mi = __fadd_rn(m[i], __fmul_rn(w1, __fadd_rn(gi, -m[i])));
+        const float vi = __fadd_rn(__fmul_rn(v[i], beta2), __fmul_rn(__fmul_rn(w2, gi), gi));
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+        p[i] = __fadd_rn(p[i], -__fmul_rn(step_size, __fdiv_rn(mi, denom)));
+    }
+}
+
+__global__ void adam_step_kernel(int *steps, const uint8_t *active, int G) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < G && (!active || active[g])) steps[g] += 1;
+}
+
 __global__ void clip_rmsprop_kernel(float *params, const float *grads, float *sq, const float *partial, int nparts,
                                     long long P, float scale, float max_norm, float lr, float alpha, float one_minus_alpha, float eps,
                                     const uint8_t *active, float *norm_out) {
@@ -954,7 +989,8 @@ struct maexp_learner {
     std::vector<HeadLayout> heads;
     std::vector<ParamEntry> table;
     std::vector<void *> allocs;
-    float *online = nullptr, *target = nullptr, *grads = nullptr, *sq = nullptr;
+    float *online = nullptr, *target = nullptr, *grads = nullptr, *sq = nullptr, *exp_avg = nullptr;
+    int *adam_steps = nullptr;
     float *support = nullptr, *ones = nullptr, *splitk_ws = nullptr;
     // the three forward passes of an update are independent: passes 1 and 2 run on side streams (fork / join with
     // events, which also works under stream capture) with their own split-K workspaces
@@ -1642,6 +1678,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (cfg->kind < MAEXP_LEARNER_DQN_CONV_MLP || cfg->kind > MAEXP_LEARNER_DA6)
         return fail("maexp_learner_create: unknown kind");
     if (cfg->num_agents < 1 || cfg->batch_size < 1) return fail("maexp_learner_create: bad num_agents / batch_size");
+    if (cfg->optimizer < 0 || cfg->optimizer > 1) return fail("maexp_learner_create: optimizer must be 0 (rmsprop) or 1 (adam)");
     if (cfg->num_actions < 1 || cfg->num_actions > kMaxActions) return fail("maexp_learner_create: num_actions must be in 1..8");
     maexp_learner *h = new maexp_learner();
     h->cfg = *cfg;
@@ -1849,6 +1886,10 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     rc |= lalloc(h, &h->target, G * P);
     rc |= lalloc(h, &h->grads, G * P);
     rc |= lalloc(h, &h->sq, G * P);
+    if (cfg->optimizer == 1) {
+        rc |= lalloc(h, &h->exp_avg, G * P);
+        rc |= lalloc(h, &h->adam_steps, G);
+    }
     rc |= lalloc(h, &h->support, 128);
     rc |= lalloc(h, &h->ones, 4);
     rc |= lalloc(h, &h->splitk_ws, (size_t)kSplitWorkspaceFloats);
@@ -2243,9 +2284,16 @@ int maexp_learner_apply(maexp_learner *h, float grad_scale, const uint8_t *activ
     if (!h) return fail("maexp_learner_apply: null handle");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     sqnorm_partial_kernel<<<dim3(h->nparts, h->G), 256, 0, st>>>(h->grads, h->partial, h->P, grad_scale);
-    clip_rmsprop_kernel<<<dim3(64, h->G), 256, 0, st>>>(h->online, h->grads, h->sq, h->partial, h->nparts, h->P, grad_scale,
-                                                        h->cfg.max_norm, h->cfg.learning_rate, h->cfg.alpha, h->cfg.one_minus_alpha, h->cfg.eps,
-                                                        active, grad_norm_out);
+    if (h->cfg.optimizer == 1) {
+        adam_step_kernel<<<(h->G + 63) / 64, 64, 0, st>>>(h->adam_steps, active, h->G);
+        clip_adam_kernel<<<dim3(64, h->G), 256, 0, st>>>(h->online, h->grads, h->exp_avg, h->sq, h->partial, h->nparts, h->P,
+                                                         grad_scale, h->cfg.max_norm, h->cfg.learning_rate, h->cfg.beta1,
+                                                         h->cfg.beta2, h->cfg.eps, active, h->adam_steps, grad_norm_out);
+    } else {
+        clip_rmsprop_kernel<<<dim3(64, h->G), 256, 0, st>>>(h->online, h->grads, h->sq, h->partial, h->nparts, h->P, grad_scale,
+                                                            h->cfg.max_norm, h->cfg.learning_rate, h->cfg.alpha,
+                                                            h->cfg.one_minus_alpha, h->cfg.eps, active, grad_norm_out);
+    }
     MAEXP_CUDA_L(cudaGetLastError());
     return 0;
 }

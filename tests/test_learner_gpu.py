@@ -255,3 +255,35 @@ def test_attention_maps_match_torch_oracle():
     dqn = make_group("dqn_conv_mlp", load("dqn_conv_mlp")["shape"], 1, 4)
     with pytest.raises(ValueError):
         dqn.attention(4)
+
+
+def test_adam_optimizer_matches_torch():
+    """configs/opt/adam.yaml through generate_optimizer (optimizers/__init__.py:18-24): five updates against torch.optim.Adam,
+    with one agent masked out (its step counter and moments must not advance)."""
+    from maexp_b200.core.agents.brains import LearnerGroup
+    kind, B, G = "dqn_conv_mlp", 32, 2
+    fix = load(kind)
+    b = fix["batch"]
+    cfg, _ = golden_configs()[kind]
+    cfg = cfg.merged_with(batch_size=B, opt=Config(dict(name="adam", learning_rate=1e-3, betas=[0.9, 0.999], eps=1e-8)))
+    g = LearnerGroup(cfg, fix["shape"], 4, G, B)
+    for a in range(G):
+        g.load_state_dict(a, fix["init"])
+    g.synchronize()
+    o = TorchLearner(kind, fix["init"], 4, fix["gamma"], 1e-3, 0.99, 1e-8, adam_betas=(0.9, 0.999))
+    batch = {"obs": pack(g, torch.stack([b["obs"]] * G)), "next_obs": pack(g, torch.stack([b["next_obs"]] * G)),
+             "actions": torch.stack([b["actions"]] * G).to(torch.int32).cuda(),
+             "rewards": torch.stack([b["rewards"]] * G).float().cuda(),
+             "dones": torch.stack([b["dones"]] * G).to(torch.uint8).cuda()}
+    before = g.params().clone()
+    active = torch.tensor([1, 0], dtype=torch.uint8, device="cuda")
+    for step in range(5):
+        loss = g.learn(batch, active=active).cpu()
+        want, _ = o.learn(b["obs"], b["next_obs"], b["actions"], b["rewards"], b["dones"])
+        assert abs(float(loss[0]) - float(want)) <= 5e-5 * abs(float(want)), (step, float(loss[0]), float(want))
+    got = g.state_dict(0)
+    for k, v in o.sd.items():
+        assert float((got[k] - v.detach()).abs().max()) <= 2e-5 + 1e-4 * float(v.detach().abs().max()), k
+    assert torch.equal(g.params()[1], before[1])  # the masked agent did not move
+    with pytest.raises(ValueError):
+        LearnerGroup(cfg.merged_with(opt=Config(dict(name="sgd", learning_rate=1e-3))), fix["shape"], 4, 1, B)
