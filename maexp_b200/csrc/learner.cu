@@ -131,6 +131,83 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a, int ksplit,
     }
 }
 
+// Large-M variant for the acting / evaluation batches (thousands of rows per agent): 128 x 64 x 16 tiles, 8 x 4 outputs per
+// thread, 128-bit global loads along K for both operands (activations [M,K] and PyTorch-layout weights [N,K] are K-major),
+// register prefetch of the next tile.  Same epilogue as gemm_kernel; no split-K (the grid is large already).
+constexpr int kBigM = 128, kBigN = 64, kBigK = 16;
+__global__ void __launch_bounds__(256) gemm_big_kernel(const GemmArgs a) {
+    __shared__ __align__(16) float As[kBigK][kBigM + 4];
+    __shared__ __align__(16) float Bs[kBigK][kBigN + 4];
+    const int g = blockIdx.z;
+    const float *A = a.A + (size_t)g * a.gA, *B = a.B + (size_t)g * a.gB;
+    const int m0 = blockIdx.y * kBigM, n0 = blockIdx.x * kBigN;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // thread tile: rows ty*8.., cols tx*4..
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    // staging: A tile 128 x 16 = 512 float4 (two per thread), B tile 64 x 16 = 256 float4 (one per thread)
+    const int am[2] = {tid >> 2, (tid + 256) >> 2}, ak = (tid & 3) * 4;
+    const int bn = tid >> 2, bk = (tid & 3) * 4;
+    float4 ra[2], rb;
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int m = m0 + am[r];
+            ra[r] = (m < a.M && k0 + ak < a.K) ? *reinterpret_cast<const float4 *>(A + (size_t)m * a.sam + k0 + ak)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const int n = n0 + bn;  // weights sit at arbitrary offsets of the flat parameter vector: scalar loads
+        if (n < a.N && k0 + bk < a.K) {
+            const float *w = B + (size_t)n * a.sbn + k0 + bk;
+            rb = make_float4(w[0], w[1], w[2], w[3]);
+        } else {
+            rb = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < a.K; k0 += kBigK) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            As[ak + 0][am[r]] = ra[r].x; As[ak + 1][am[r]] = ra[r].y; As[ak + 2][am[r]] = ra[r].z; As[ak + 3][am[r]] = ra[r].w;
+        }
+        Bs[bk + 0][bn] = rb.x; Bs[bk + 1][bn] = rb.y; Bs[bk + 2][bn] = rb.z; Bs[bk + 3][bn] = rb.w;
+        __syncthreads();
+        if (k0 + kBigK < a.K) fetch(k0 + kBigK);
+#pragma unroll
+        for (int kk = 0; kk < kBigK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8 + 4]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *C = a.C + (size_t)g * a.gC;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
+        if (m >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= a.N) continue;
+            float v = acc[i][j];
+            if (a.bias) v = __fadd_rn(v, a.bias[(size_t)g * a.gBias + n]);
+            if (a.relu) v = fmaxf(v, 0.0f);
+            const size_t ci = (size_t)m * a.scm + (size_t)n * a.scn;
+            if (a.mask_aux) v = (a.aux[(size_t)g * a.gAux + ci] > 0.0f) ? v : 0.0f;
+            if (a.accumulate) v = __fadd_rn(C[ci], v);
+            C[ci] = v;
+        }
+    }
+}
+
 __global__ void splitk_reduce_kernel(const GemmArgs a, int ksplit, int G, const float *part) {
     const int g = blockIdx.y;
     const long long total = (long long)a.M * a.N;
@@ -1073,6 +1150,13 @@ void gemm(cudaStream_t st, int G, const float *A, const float *Bm, float *C, con
     a.sam = sam; a.sak = sak; a.sbk = sbk; a.sbn = sbn; a.scm = scm; a.scn = scn;
     a.gA = gA; a.gB = gB; a.gC = gC; a.gBias = gBias; a.gAux = gAux;
     a.relu = relu; a.accumulate = accumulate; a.mask_aux = aux != nullptr;
+    // thousands of rows, both operands K-major and 16-byte aligned along K: the large-tile kernel
+    auto aligned16 = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+    if (M >= 2048 && sak == 1 && sbk == 1 && (K & 3) == 0 && (sam & 3) == 0 && (gA & 3) == 0 && aligned16(A)) {
+        dim3 grid((N + kBigN - 1) / kBigN, (M + kBigM - 1) / kBigM, G);
+        gemm_big_kernel<<<grid, 256, 0, st>>>(a);
+        return;
+    }
     const int tm = (M + kTile - 1) / kTile, tn = (N + kTile - 1) / kTile;
     // split K (powers of two, slices >= 64) until the grid covers two waves of 148 SMs; shapes only → deterministic
     int ksplit = 1;
