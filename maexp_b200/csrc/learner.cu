@@ -1215,11 +1215,121 @@ void wgrad_close() {  // join the side streams back into the main stream
     g_wg = WGradCtx();
 }
 
+// Inference-only conv trunk (acting / evaluation batches): conv 2x2 -> max_pool2d(2,2) -> conv 2x2 -> flatten in ONE
+// kernel, one warp per sample, so no intermediate ever reaches HBM (the layer-by-layer path moves ~12 KB per sample).
+// Lanes are output channels: conv1 + pooling with lane = conv1 channel (F1 <= 32), conv2 with lane = output channel
+// (and lane + 32 when F2 > 32).  The agent's conv weights sit in shared memory: conv1 k-major, conv2 as eight
+// consecutive floats per (input channel, lane) so that one input channel costs two 128-bit loads; the pooled map is
+// stored channel-major so that a channel's cells are three 128-bit broadcast loads.  V is a template parameter: every
+// cell / tap index is a compile-time constant.  flat[b][oc*H2*W2 + pos] is PyTorch's flatten order (convolution.py:44-55).
+template <int V>
+__global__ void __launch_bounds__(128) trunk_fused_fwd_kernel(const float *obs, const float *params, float *flat, int B, int C,
+                                                              int F1, int F2, long long stride, long long gObs, long long P,
+                                                              long long o_c1w, long long o_c1b, long long o_c2w,
+                                                              long long o_c2b, long long gFlat) {
+    constexpr int H1 = V - 1, Hp = H1 / 2, H2 = Hp - 1, Q = H2 * H2, NC = Hp * Hp, PC = (NC + 3) / 4 * 4;
+    extern __shared__ __align__(16) float sm[];
+    const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int K1 = C * 4, CVV = C * V * V, D = F2 * Q;
+    float *w2t = sm;                      // [F1][32][8]: (tap, half) of output channels lane / lane + 32
+    float *w1t = w2t + F1 * 256;          // [K1][32]    conv1 weight, k-major
+    float *b1 = w1t + K1 * 32;            // [32]
+    float *b2 = b1 + 32;                  // [64]
+    float *s_p = b2 + 64 + warp * (32 * PC + (CVV + 3) / 4 * 4);  // per warp: pooled [ic][PC] (16-byte aligned), then the observation
+    float *s_obs = s_p + 32 * PC;
+    const float *W = params + (size_t)g * P;
+    for (int i = threadIdx.x; i < F1 * 256; i += blockDim.x) {
+        const int ic = i >> 8, l = (i >> 3) & 31, tap = (i >> 1) & 3, oc = l + 32 * (i & 1);
+        w2t[i] = oc < F2 ? W[o_c2w + ((size_t)oc * F1 + ic) * 4 + tap] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < K1 * 32; i += blockDim.x) {
+        const int k = i >> 5, f = i & 31;
+        w1t[i] = f < F1 ? W[o_c1w + (size_t)f * K1 + k] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) b1[i] = i < F1 ? W[o_c1b + i] : 0.0f;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) b2[i] = i < F2 ? W[o_c2b + i] : 0.0f;
+    for (int i = lane; i < 32 * PC; i += 32) s_p[i] = 0.0f;
+    __syncthreads();
+    const float *src = obs + (size_t)g * gObs;
+    float *dst = flat + (size_t)g * gFlat;
+    for (int b = blockIdx.x * nwarps + warp; b < B; b += gridDim.x * nwarps) {
+        for (int i = lane; i < CVV; i += 32) s_obs[i] = src[(size_t)b * stride + i];
+        __syncwarp();
+        // conv1 + max-pool, lane = conv1 output channel: the 3x3 input patch of a pooled cell is read once per input
+        // channel and feeds the four conv positions under the pooling window
+#pragma unroll
+        for (int cell = 0; cell < NC; ++cell) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int py = cell / Hp, px = cell % Hp;
+            float a00 = 0.0f, a01 = 0.0f, a10 = 0.0f, a11 = 0.0f;
+            for (int c = 0; c < C; ++c) {
+                const float *o = s_obs + c * V * V + (py * 2) * V + px * 2;
+                const float *w = w1t + (c * 4) * 32 + lane;
+                const float w0 = w[0], w1 = w[32], w2 = w[64], w3 = w[96];
+                const float o00 = o[0], o01 = o[1], o02 = o[2], o10 = o[V], o11 = o[V + 1], o12 = o[V + 2],
+                            o20 = o[2 * V], o21 = o[2 * V + 1], o22 = o[2 * V + 2];
+                a00 = fmaf(o00, w0, a00); a00 = fmaf(o01, w1, a00); a00 = fmaf(o10, w2, a00); a00 = fmaf(o11, w3, a00);
+                a01 = fmaf(o01, w0, a01); a01 = fmaf(o02, w1, a01); a01 = fmaf(o11, w2, a01); a01 = fmaf(o12, w3, a01);
+                a10 = fmaf(o10, w0, a10); a10 = fmaf(o11, w1, a10); a10 = fmaf(o20, w2, a10); a10 = fmaf(o21, w3, a10);
+                a11 = fmaf(o11, w0, a11); a11 = fmaf(o12, w1, a11); a11 = fmaf(o21, w2, a11); a11 = fmaf(o22, w3, a11);
+            }
+            s_p[lane * PC + cell] = fmaxf(fmaxf(a00, a01), fmaxf(a10, a11)) + b1[lane];  // max(x_i) + b == max(x_i + b)
+        }
+        __syncwarp();
+        // conv2, lane = output channel (two per lane when F2 > 32)
+        float acc0[Q], acc1[Q];
+#pragma unroll
+        for (int pos = 0; pos < Q; ++pos) acc0[pos] = acc1[pos] = 0.0f;
+        for (int ic = 0; ic < F1; ++ic) {
+            float pv[PC];
+#pragma unroll
+            for (int v4 = 0; v4 < PC / 4; ++v4) {
+                const float4 t = *reinterpret_cast<const float4 *>(s_p + ic * PC + v4 * 4);
+                pv[v4 * 4] = t.x; pv[v4 * 4 + 1] = t.y; pv[v4 * 4 + 2] = t.z; pv[v4 * 4 + 3] = t.w;
+            }
+            const float4 wa = *reinterpret_cast<const float4 *>(w2t + (ic * 32 + lane) * 8);
+            const float4 wb = *reinterpret_cast<const float4 *>(w2t + (ic * 32 + lane) * 8 + 4);
+            const float w0[4] = {wa.x, wa.z, wb.x, wb.z}, w1[4] = {wa.y, wa.w, wb.y, wb.w};  // [tap] for oc = lane, lane + 32
+#pragma unroll
+            for (int pos = 0; pos < Q; ++pos) {
+#pragma unroll
+                for (int tap = 0; tap < 4; ++tap) {
+                    const float p = pv[(pos / H2 + (tap >> 1)) * Hp + pos % H2 + (tap & 1)];
+                    acc0[pos] = fmaf(p, w0[tap], acc0[pos]);
+                    acc1[pos] = fmaf(p, w1[tap], acc1[pos]);
+                }
+            }
+        }
+#pragma unroll
+        for (int pos = 0; pos < Q; ++pos) {
+            if (lane < F2) dst[(size_t)b * D + (size_t)lane * Q + pos] = acc0[pos] + b2[lane];
+            if (lane + 32 < F2) dst[(size_t)b * D + (size_t)(lane + 32) * Q + pos] = acc1[pos] + b2[lane + 32];
+        }
+        __syncwarp();
+    }
+}
+
 // ---- conv trunk: obs [G][B][obs_stride] -> a.flat [G][Bmax][D]
-void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, maexp_learner::Acts &a) {
+void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, maexp_learner::Acts &a,
+                   bool inference = false) {
     const int G = h->G, C = h->C, V = h->V, F1 = h->F1, F2 = h->F2;
     const long long P = h->P, Bmax = h->B, stride = h->cfg.obs_stride;
     const int H1 = h->H1, Hp = h->Hp, H2 = h->H2;
+    if (inference && B >= 512 && F1 <= 32 && F2 <= 64 && (V == 5 || V == 7 || V == 9)) {  // nothing is kept for a backward pass
+        const int warps = 4, pc = (Hp * Hp + 3) / 4 * 4;
+        const size_t smem = sizeof(float) * ((size_t)F1 * 256 + (size_t)C * 4 * 32 + 96 +
+                                             (size_t)warps * (32 * pc + (C * V * V + 3) / 4 * 4));
+        if (smem <= 200 * 1024) {
+            auto fn = V == 5 ? trunk_fused_fwd_kernel<5> : V == 7 ? trunk_fused_fwd_kernel<7> : trunk_fused_fwd_kernel<9>;
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            int blocks = (B + warps - 1) / warps;
+            if (blocks > 148 * 4) blocks = 148 * 4;
+            fn<<<dim3(blocks, G), warps * 32, smem, st>>>(obs, params, a.flat, B, C, F1, F2, stride, (long long)B * stride, P,
+                                                         h->o_c1w, h->o_c1b, h->o_c2w, h->o_c2b, Bmax * h->D);
+            return;
+        }
+    }
     const long long gcol1 = Bmax * H1 * H1 * C * 4, gy1 = Bmax * H1 * H1 * F1, gp = Bmax * Hp * Hp * F1;
     const long long gcol2 = Bmax * H2 * H2 * F1 * 4, gy2 = Bmax * H2 * H2 * F2;
     im2col_kernel<<<grid1d((long long)B * H1 * H1 * C * 4, G), 256, 0, st>>>(
@@ -1308,10 +1418,11 @@ void mlp_backward(maexp_learner *h, cudaStream_t st, const HeadLayout &hd, const
 }
 
 // forward of one (non-IQN) network for all groups
-void forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, maexp_learner::Acts &a) {
+void forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, maexp_learner::Acts &a,
+             bool inference = false) {
     MlpIn in;
     if (h->has_conv) {
-        trunk_forward(h, st, params, obs, B, a);
+        trunk_forward(h, st, params, obs, B, a, inference);
         in = {a.flat, h->D, (long long)h->B * h->D, B, h->B, h->D};
     } else {
         in = {obs, h->cfg.obs_stride, (long long)B * h->cfg.obs_stride, B, h->B, h->D};
@@ -1688,7 +1799,7 @@ int iqn_forward(maexp_learner *h, cudaStream_t st, const float *params, const fl
         cudaMemcpy2DAsync(q.psi + Dr, sizeof(float) * D, h->lse_out[pass], sizeof(float) * Dl, sizeof(float) * Dl, (size_t)G * Bmax,
                           cudaMemcpyDeviceToDevice, st);
     } else {
-        trunk_forward(h, st, params, obs, B, a);
+        trunk_forward(h, st, params, obs, B, a, /*inference=*/pass == 1);  // pass 1 never feeds a backward pass
         const MlpIn se_in = {a.flat, D, Bmax * D, B, Bmax, D};
         mlp_forward(h, st, params, h->se, se_in, q.se_h, q.psi);  // state_embedder
     }
@@ -2209,7 +2320,7 @@ int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int us
         MAEXP_CUDA_L(cudaGetLastError());
         return 0;
     }
-    forward(h, st, use_target ? h->target : h->online, obs, batch, a);
+    forward(h, st, use_target ? h->target : h->online, obs, batch, a, /*inference=*/true);
     if (!h->dist) {
         // heads are strided by the maximum batch: compact to [G][batch][A]
         MAEXP_CUDA_L(cudaMemcpy2DAsync(q_out, sizeof(float) * batch * h->A, a.out[0], sizeof(float) * h->B * h->A,
