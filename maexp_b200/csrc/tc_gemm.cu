@@ -1,0 +1,253 @@
+// tcgen05 (5th-generation tensor core) GEMM for the large acting / evaluation batches:
+//     C[M,N] = epi( A[M,K] * W[N,K]^T + bias ),   fp32 in, fp32 out, accumulators in tensor memory (TMEM).
+// The operands are fp32; the tensor cores take them as TF32.  With split = 3 every product is evaluated as
+// a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (a_hi = rna-tf32(a), a_lo = a - a_hi), which keeps the result within ~2^-21 of the
+// fp32 product sum, so the actor's Q-values stay inside the 1e-5 bar of the fp32 learner.  split = 1 is plain TF32.
+//
+// One CTA (4 warps) owns a 128-row tile and all N <= 256 columns:
+//   * all threads stage a 128 x 32 slab of A and an Npad x 32 slab of W into shared memory in the K-major
+//     SWIZZLE_128B canonical layout (rows of 128 bytes, 16-byte chunk c of row r stored at chunk c ^ (r & 7)),
+//     double-buffered; fence.proxy.async makes the generic-proxy stores visible to the tensor core
+//   * one thread issues tcgen05.mma.cta_group::1.kind::tf32 (UMMA 128 x Npad x 8, four per slab and term) and
+//     tcgen05.commit, whose mbarrier arrival releases the slab for the next load
+//   * epilogue: each warp reads its 32 TMEM lanes (= rows) with tcgen05.ld.32x32b, adds bias / ReLU, stores rows.
+// No TMA descriptors: the weights sit at arbitrary float offsets of the flat per-agent parameter vector.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "maexp_b200.h"
+
+namespace maexp {
+int fail(const std::string &msg);  // env.cu
+}
+
+namespace {
+
+constexpr int kBM = 128, kBK = 32;  // rows per CTA, K floats per slab (= one 128-byte swizzle row)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity));
+        if (spin > (1u << 26)) __trap();  // a lost arrival must not hang the GPU
+    }
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp): start address >> 4 in bits
+// [0,14), leading byte offset [16,30) (unused for swizzled K-major), stride byte offset [32,46) = 1024 B between
+// 8-row groups, version 1 in [46,48), layout type 2 (SWIZZLE_128B) in [61,64)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TcArgs {
+    const float *A, *W, *bias;
+    float *C;
+    int M, N, K, npad;
+    long long lda, ldw, ldc, gA, gW, gBias, gC;
+    int relu, split;
+};
+
+// dynamic shared memory: [stage][A_hi | A_lo | W_hi | W_lo], each tile 1024-byte aligned
+template <int SPLIT>
+__global__ void __launch_bounds__(128) tc_gemm_kernel(const TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = blockIdx.y;
+    const int m0 = blockIdx.x * kBM, npad = a.npad;
+    const float *A = a.A + (size_t)g * a.gA, *W = a.W + (size_t)g * a.gW;
+    const uint32_t a_bytes = kBM * 128, w_bytes = (uint32_t)npad * 128;
+    const uint32_t stage_bytes = (SPLIT == 3 ? 2 : 1) * (a_bytes + w_bytes);
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)npad) ncols <<= 1;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+    // instruction descriptor: D = F32 (bits 4-5 = 1), A and B = TF32 (bits 7-9 and 10-12 = 2), both K-major,
+    // N >> 3 in bits 17-22, M >> 4 in bits 24-28
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+    const int num_kb = (a.K + kBK - 1) / kBK;
+    const bool a_vec = (a.lda & 3) == 0 && (a.gA & 3) == 0 && ((uintptr_t)a.A & 15) == 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+        const int buf = kb & 1, k0 = kb * kBK;
+        if (kb >= 2) mbar_wait(&bars[buf], ((kb >> 1) - 1) & 1);  // the MMAs that read this buffer have completed
+        uint8_t *sA = smem + (size_t)buf * stage_bytes, *sAlo = sA + a_bytes;
+        uint8_t *sW = sA + (SPLIT == 3 ? 2 : 1) * a_bytes, *sWlo = sW + w_bytes;
+        // ---- stage A: thread = row (128 bytes of one row: eight 16-byte chunks, swizzled)
+        {
+            const int r = tid, m = m0 + r;
+            const float *src = A + (size_t)m * a.lda + k0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < a.M) {
+                    if (a_vec && k0 + c * 4 + 3 < a.K) {
+                        v = *reinterpret_cast<const float4 *>(src + c * 4);
+                    } else {
+                        if (k0 + c * 4 + 0 < a.K) v.x = src[c * 4 + 0];
+                        if (k0 + c * 4 + 1 < a.K) v.y = src[c * 4 + 1];
+                        if (k0 + c * 4 + 2 < a.K) v.z = src[c * 4 + 2];
+                        if (k0 + c * 4 + 3 < a.K) v.w = src[c * 4 + 3];
+                    }
+                }
+                const uint32_t off = (uint32_t)r * 128 + (uint32_t)((c ^ (r & 7)) * 16);
+                if (SPLIT == 3) {
+                    const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                    *reinterpret_cast<float4 *>(sA + off) = hi;
+                    *reinterpret_cast<float4 *>(sAlo + off) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                } else {
+                    *reinterpret_cast<float4 *>(sA + off) = v;
+                }
+            }
+        }
+        // ---- stage W: rows n = tid, tid + 128 (weights at arbitrary float offsets: scalar loads)
+        for (int r = tid; r < npad; r += 128) {
+            const float *src = W + (size_t)r * a.ldw + k0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < a.N) {
+                    if (k0 + c * 4 + 0 < a.K) v.x = src[c * 4 + 0];
+                    if (k0 + c * 4 + 1 < a.K) v.y = src[c * 4 + 1];
+                    if (k0 + c * 4 + 2 < a.K) v.z = src[c * 4 + 2];
+                    if (k0 + c * 4 + 3 < a.K) v.w = src[c * 4 + 3];
+                }
+                const uint32_t off = (uint32_t)r * 128 + (uint32_t)((c ^ (r & 7)) * 16);
+                if (SPLIT == 3) {
+                    const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                    *reinterpret_cast<float4 *>(sW + off) = hi;
+                    *reinterpret_cast<float4 *>(sWlo + off) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                } else {
+                    *reinterpret_cast<float4 *>(sW + off) = v;
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t aA = smem_u32(sA), aAlo = smem_u32(sAlo), aW = smem_u32(sW), aWlo = smem_u32(sWlo);
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {  // UMMA_K = 8 TF32 = 32 bytes: advance the start address inside the swizzle row
+                const uint32_t ko = (uint32_t)k * 32;
+                umma_tf32(tmem_d, smem_desc(aA + ko), smem_desc(aW + ko), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                if (SPLIT == 3) {
+                    umma_tf32(tmem_d, smem_desc(aAlo + ko), smem_desc(aW + ko), idesc, 1u);
+                    umma_tf32(tmem_d, smem_desc(aA + ko), smem_desc(aWlo + ko), idesc, 1u);
+                }
+            }
+            umma_commit(&bars[buf]);  // arrives when the MMAs above have finished reading this buffer
+        }
+    }
+    // the last commit on each buffer: use count u = number of slabs that went through it
+    for (int buf = 0; buf < 2; ++buf) {
+        const int uses = (num_kb - buf + 1) / 2;
+        if (uses > 0) mbar_wait(&bars[buf], (uses - 1) & 1);
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: warp w owns TMEM lanes 32w .. 32w+31 (= rows), 8 columns per tcgen05.ld
+    const int m = m0 + warp * 32 + lane;
+    float *crow = a.C + (size_t)g * a.gC + (size_t)m * a.ldc;
+    const float *bias = a.bias ? a.bias + (size_t)g * a.gBias : nullptr;
+    for (int n0 = 0; n0 < npad; n0 += 8) {
+        uint32_t r[8];
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (m < a.M) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = n0 + j;
+                if (n < a.N) {
+                    float v = __uint_as_float(r[j]);
+                    if (bias) v += bias[n];
+                    if (a.relu) v = fmaxf(v, 0.0f);
+                    crow[n] = v;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(ncols) : "memory");
+}
+
+}  // namespace
+
+namespace maexp {
+
+// grouped launch used by the learner's inference path; returns false when the shape is outside what the kernel handles
+bool tc_gemm_launch(cudaStream_t st, int G, const float *A, const float *W, const float *bias, float *C, int M, int N, int K,
+                    long long lda, long long ldw, long long ldc, long long gA, long long gW, long long gBias, long long gC, int relu,
+                    int split) {
+    if (N < 1 || N > 256 || M < 1 || K < 1) return false;
+    TcArgs a;
+    a.A = A; a.W = W; a.bias = bias; a.C = C;
+    a.M = M; a.N = N; a.K = K; a.npad = (N + 15) / 16 * 16;
+    a.lda = lda; a.ldw = ldw; a.ldc = ldc; a.gA = gA; a.gW = gW; a.gBias = gBias; a.gC = gC;
+    a.relu = relu; a.split = split;
+    const size_t stage = (size_t)(split == 3 ? 2 : 1) * ((size_t)kBM * 128 + (size_t)a.npad * 128);
+    const size_t smem = 2 * stage + 1024;
+    if (smem > 200 * 1024) return false;
+    auto fn = split == 3 ? tc_gemm_kernel<3> : tc_gemm_kernel<1>;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    fn<<<dim3((M + kBM - 1) / kBM, G), 128, smem, st>>>(a);
+    return true;
+}
+
+}  // namespace maexp
+
+extern "C" int maexp_tc_gemm(const float *A, const float *W, const float *bias, float *C, int32_t M, int32_t N, int32_t K,
+                             int64_t lda, int64_t ldw, int64_t ldc, int32_t relu, int32_t split, void *stream) {
+    if (!A || !W || !C) return maexp::fail("maexp_tc_gemm: null argument");
+    if (split != 1 && split != 3) return maexp::fail("maexp_tc_gemm: split must be 1 (TF32) or 3 (3xTF32)");
+    if (!maexp::tc_gemm_launch(static_cast<cudaStream_t>(stream), 1, A, W, bias, C, M, N, K, lda, ldw, ldc, 0, 0, 0, 0, relu, split))
+        return maexp::fail("maexp_tc_gemm: unsupported shape (N <= 256)");
+    if (cudaGetLastError() != cudaSuccess) return maexp::fail("maexp_tc_gemm: launch failed");
+    return 0;
+}
