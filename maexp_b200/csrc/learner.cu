@@ -27,6 +27,10 @@
 
 namespace maexp {
 int fail(const std::string &msg);  // env.cu
+// tc_gemm.cu: tcgen05 tensor-core GEMM (3xTF32) for the large inference batches
+bool tc_gemm_launch(cudaStream_t st, int G, const float *A, const float *W, const float *bias, float *C, int M, int N, int K,
+                    long long lda, long long ldw, long long ldc, long long gA, long long gW, long long gBias, long long gC, int relu,
+                    int split);
 #define MAEXP_CUDA_L(call)                                                                        \
     do {                                                                                          \
         cudaError_t err__ = (call);                                                               \
@@ -1055,6 +1059,7 @@ struct maexp_learner {
     int G, B, C, V, A, H, F1, F2, Z, D;  // D = flattened conv output (or C*V*V for the plain MLP)
     int H1, Hp, H2;                      // conv1 out side, pooled side, conv2 out side
     bool has_conv, dist, iqn, da3, da6 = false;
+    bool use_tc = true;  // tensor-core GEMMs for large inference batches (MAEXP_TC=0 turns them off)
     int E_, heads_, Fm, L_, Tn;   // DA3 / DA6: embed_dim, num_heads, mlp hidden, block_loop, max tokens of any stack
     long long o_nfw, o_nfb, o_hw, o_hb, o_f1w = 0, o_f1b = 0;  // shared final norm, drl_head, DA6 fc1
     struct BlockLayout { long long n1w, n1b, qkvw, projw, projb, n2w, n2b, f1w, f1b, f2w, f2b; };
@@ -1139,6 +1144,7 @@ inline dim3 grid1d(long long total, int g, int threads = 256, int cap = 1024) {
 
 constexpr long long kSplitWorkspaceFloats = 8ll << 20;  // 32 MB of partial tiles
 float *g_splitk_ws = nullptr;                            // set per call from the handle (single host thread)
+bool g_inference_tc = false;                             // set by the q_values entry points around their forward pass
 
 void gemm(cudaStream_t st, int G, const float *A, const float *Bm, float *C, const float *bias, int M, int N, int K,
           long long sam, long long sak, long long sbk, long long sbn, long long scm, long long scn, long long gA,
@@ -1150,8 +1156,12 @@ void gemm(cudaStream_t st, int G, const float *A, const float *Bm, float *C, con
     a.sam = sam; a.sak = sak; a.sbk = sbk; a.sbn = sbn; a.scm = scm; a.scn = scn;
     a.gA = gA; a.gB = gB; a.gC = gC; a.gBias = gBias; a.gAux = gAux;
     a.relu = relu; a.accumulate = accumulate; a.mask_aux = aux != nullptr;
-    // thousands of rows, both operands K-major and 16-byte aligned along K: the large-tile kernel
+    // thousands of rows, both operands K-major and 16-byte aligned along K: the large-tile kernels
     auto aligned16 = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+    // acting / evaluation forward passes (g_inference_tc): tensor cores, three TF32 terms per product (fp32-level accuracy)
+    if (g_inference_tc && M >= 2048 && N <= 256 && K >= 32 && sak == 1 && sbk == 1 && scn == 1 && !accumulate && !aux &&
+        tc_gemm_launch(st, G, A, Bm, bias, C, M, N, K, sam, sbn, scm, gA, gB, gBias, gC, relu, 3))
+        return;
     if (M >= 2048 && sak == 1 && sbk == 1 && (K & 3) == 0 && (sam & 3) == 0 && (gA & 3) == 0 && aligned16(A)) {
         dim3 grid((N + kBigN - 1) / kBigN, (M + kBigM - 1) / kBigM, G);
         gemm_big_kernel<<<grid, 256, 0, st>>>(a);
@@ -1877,6 +1887,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (cfg->num_actions < 1 || cfg->num_actions > kMaxActions) return fail("maexp_learner_create: num_actions must be in 1..8");
     maexp_learner *h = new maexp_learner();
     h->cfg = *cfg;
+    if (const char *tc = getenv("MAEXP_TC")) h->use_tc = atoi(tc) != 0;
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
     h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;
     const int trunk = cfg->kind == MAEXP_LEARNER_IQN ? cfg->iqn_trunk : 0;  // MAEXP_IQN_TRUNK_*
@@ -1910,6 +1921,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (cfg->obs_stride < h->C * h->V * h->V) { delete h; return fail("maexp_learner_create: obs_stride < C*V*V"); }
     long long off = 0;
     auto add = [&](const std::string &name, long long count) {
+        off = (off + 3) & ~3ll;  // every tensor starts on a 16-byte boundary of the flat vector (vector loads of weights)
         h->table.push_back({name, off, count});
         const long long o = off;
         off += count;
@@ -2074,7 +2086,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         add_head("", h->A);               // mlp.py:19-26 (flattened observation)
         for (auto &e : h->table) e.name = e.name.substr(1);
     }
-    h->P = off;
+    h->P = (off + 3) & ~3ll;  // padding elements stay zero: zero gradient, zero optimizer update
     const long long G = h->G, B = h->B, P = h->P;
     int rc = 0;
     rc |= lalloc(h, &h->online, G * P);
@@ -2320,7 +2332,9 @@ int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int us
         MAEXP_CUDA_L(cudaGetLastError());
         return 0;
     }
+    g_inference_tc = h->use_tc;
     forward(h, st, use_target ? h->target : h->online, obs, batch, a, /*inference=*/true);
+    g_inference_tc = false;
     if (!h->dist) {
         // heads are strided by the maximum batch: compact to [G][batch][A]
         MAEXP_CUDA_L(cudaMemcpy2DAsync(q_out, sizeof(float) * batch * h->A, a.out[0], sizeof(float) * h->B * h->A,
@@ -2433,7 +2447,10 @@ int maexp_learner_q_values_iqn(maexp_learner *h, const float *obs, int batch, in
     if (batch < 1 || batch > h->B) return fail("maexp_learner_q_values_iqn: batch must be in 1..batch_size");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     g_splitk_ws = h->splitk_ws;
-    if (iqn_forward(h, st, use_target ? h->target : h->online, obs, h->pos, batch, tau_sel, h->Nq, /*per_sample=*/0, 1)) return -1;
+    g_inference_tc = h->use_tc;
+    const int rc_fwd = iqn_forward(h, st, use_target ? h->target : h->online, obs, h->pos, batch, tau_sel, h->Nq, /*per_sample=*/0, 1);
+    g_inference_tc = false;
+    if (rc_fwd) return -1;
     iqn_q_kernel<<<dim3((batch + 127) / 128, h->G), 128, 0, st>>>(h->iq[1].out[0], h->iq[1].out[1], batch, h->A, h->Nq,
                                                                   h->rows_max, h->rows_max * h->A, q_out);
     MAEXP_CUDA_L(cudaGetLastError());

@@ -4,10 +4,11 @@
 // a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (a_hi = rna-tf32(a), a_lo = a - a_hi), which keeps the result within ~2^-21 of the
 // fp32 product sum, so the actor's Q-values stay inside the 1e-5 bar of the fp32 learner.  split = 1 is plain TF32.
 //
-// One CTA (4 warps) owns a 128-row tile and all N <= 256 columns:
+// One CTA (8 warps) owns a 128-row tile and all N <= 256 columns:
 //   * all threads stage a 128 x 32 slab of A and an Npad x 32 slab of W into shared memory in the K-major
-//     SWIZZLE_128B canonical layout (rows of 128 bytes, 16-byte chunk c of row r stored at chunk c ^ (r & 7)),
-//     double-buffered; fence.proxy.async makes the generic-proxy stores visible to the tensor core
+//     SWIZZLE_128B canonical layout (rows of 128 bytes, 16-byte chunk c of row r stored at chunk c ^ (r & 7));
+//     fence.proxy.async makes the generic-proxy stores visible to the tensor core.  One slab per CTA (16-64 KB), so
+//     several CTAs are resident per SM and one CTA's loads overlap another's MMAs
 //   * one thread issues tcgen05.mma.cta_group::1.kind::tf32 (UMMA 128 x Npad x 8, four per slab and term) and
 //     tcgen05.commit, whose mbarrier arrival releases the slab for the next load
 //   * epilogue: each warp reads its 32 TMEM lanes (= rows) with tcgen05.ld.32x32b, adds bias / ReLU, stores rows.
@@ -75,24 +76,48 @@ struct TcArgs {
     int relu, split;
 };
 
-// dynamic shared memory: [stage][A_hi | A_lo | W_hi | W_lo], each tile 1024-byte aligned
+// dynamic shared memory: [A_hi | A_lo | W_hi | W_lo], each tile 1024-byte aligned
+constexpr int kThreads = 256;
+
+// one 16-byte chunk (4 consecutive K values of one row) -> swizzled shared memory, optionally split into hi / lo
 template <int SPLIT>
-__global__ void __launch_bounds__(128) tc_gemm_kernel(const TcArgs a) {
+__device__ __forceinline__ void stage_chunk(uint8_t *hi_tile, uint8_t *lo_tile, int r, int c, float4 v) {
+    const uint32_t off = (uint32_t)r * 128 + (uint32_t)((c ^ (r & 7)) * 16);
+    if (SPLIT == 3) {
+        const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+        *reinterpret_cast<float4 *>(hi_tile + off) = hi;
+        *reinterpret_cast<float4 *>(lo_tile + off) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+    } else {
+        *reinterpret_cast<float4 *>(hi_tile + off) = v;
+    }
+}
+__device__ __forceinline__ float4 load_chunk(const float *src, int k, int K, bool vec) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec && k + 3 < K) return *reinterpret_cast<const float4 *>(src);
+    if (k + 0 < K) v.x = src[0];
+    if (k + 1 < K) v.y = src[1];
+    if (k + 2 < K) v.z = src[2];
+    if (k + 3 < K) v.w = src[3];
+    return v;
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t bars[2];
+    __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_smem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = blockIdx.y;
     const int m0 = blockIdx.x * kBM, npad = a.npad;
     const float *A = a.A + (size_t)g * a.gA, *W = a.W + (size_t)g * a.gW;
     const uint32_t a_bytes = kBM * 128, w_bytes = (uint32_t)npad * 128;
-    const uint32_t stage_bytes = (SPLIT == 3 ? 2 : 1) * (a_bytes + w_bytes);
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem, *sAlo = sA + a_bytes;
+    uint8_t *sW = sA + (SPLIT == 3 ? 2 : 1) * a_bytes, *sWlo = sW + w_bytes;
     uint32_t ncols = 32;
     while (ncols < (uint32_t)npad) ncols <<= 1;
 
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -110,59 +135,22 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const TcArgs a) {
 
     const int num_kb = (a.K + kBK - 1) / kBK;
     const bool a_vec = (a.lda & 3) == 0 && (a.gA & 3) == 0 && ((uintptr_t)a.A & 15) == 0;
+    const bool w_vec = (a.ldw & 3) == 0 && (a.gW & 3) == 0 && ((uintptr_t)a.W & 15) == 0;
     for (int kb = 0; kb < num_kb; ++kb) {
-        const int buf = kb & 1, k0 = kb * kBK;
-        if (kb >= 2) mbar_wait(&bars[buf], ((kb >> 1) - 1) & 1);  // the MMAs that read this buffer have completed
-        uint8_t *sA = smem + (size_t)buf * stage_bytes, *sAlo = sA + a_bytes;
-        uint8_t *sW = sA + (SPLIT == 3 ? 2 : 1) * a_bytes, *sWlo = sW + w_bytes;
-        // ---- stage A: thread = row (128 bytes of one row: eight 16-byte chunks, swizzled)
-        {
-            const int r = tid, m = m0 + r;
-            const float *src = A + (size_t)m * a.lda + k0;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m < a.M) {
-                    if (a_vec && k0 + c * 4 + 3 < a.K) {
-                        v = *reinterpret_cast<const float4 *>(src + c * 4);
-                    } else {
-                        if (k0 + c * 4 + 0 < a.K) v.x = src[c * 4 + 0];
-                        if (k0 + c * 4 + 1 < a.K) v.y = src[c * 4 + 1];
-                        if (k0 + c * 4 + 2 < a.K) v.z = src[c * 4 + 2];
-                        if (k0 + c * 4 + 3 < a.K) v.w = src[c * 4 + 3];
-                    }
-                }
-                const uint32_t off = (uint32_t)r * 128 + (uint32_t)((c ^ (r & 7)) * 16);
-                if (SPLIT == 3) {
-                    const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-                    *reinterpret_cast<float4 *>(sA + off) = hi;
-                    *reinterpret_cast<float4 *>(sAlo + off) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-                } else {
-                    *reinterpret_cast<float4 *>(sA + off) = v;
-                }
-            }
+        const int k0 = kb * kBK;
+        if (kb >= 1) mbar_wait(&bar, (kb - 1) & 1);  // the MMAs of the previous slab have finished reading shared memory
+        // ---- stage A (128 rows x 8 chunks) and W (npad rows x 8 chunks): consecutive threads take consecutive chunks
+        for (int i = tid; i < kBM * 8; i += kThreads) {
+            const int r = i >> 3, c = i & 7, m = m0 + r;
+            const float4 v = m < a.M ? load_chunk(A + (size_t)m * a.lda + k0 + c * 4, k0 + c * 4, a.K, a_vec)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            stage_chunk<SPLIT>(sA, sAlo, r, c, v);
         }
-        // ---- stage W: rows n = tid, tid + 128 (weights at arbitrary float offsets: scalar loads)
-        for (int r = tid; r < npad; r += 128) {
-            const float *src = W + (size_t)r * a.ldw + k0;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < a.N) {
-                    if (k0 + c * 4 + 0 < a.K) v.x = src[c * 4 + 0];
-                    if (k0 + c * 4 + 1 < a.K) v.y = src[c * 4 + 1];
-                    if (k0 + c * 4 + 2 < a.K) v.z = src[c * 4 + 2];
-                    if (k0 + c * 4 + 3 < a.K) v.w = src[c * 4 + 3];
-                }
-                const uint32_t off = (uint32_t)r * 128 + (uint32_t)((c ^ (r & 7)) * 16);
-                if (SPLIT == 3) {
-                    const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-                    *reinterpret_cast<float4 *>(sW + off) = hi;
-                    *reinterpret_cast<float4 *>(sWlo + off) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-                } else {
-                    *reinterpret_cast<float4 *>(sW + off) = v;
-                }
-            }
+        for (int i = tid; i < npad * 8; i += kThreads) {
+            const int r = i >> 3, c = i & 7;
+            const float4 v = r < a.N ? load_chunk(W + (size_t)r * a.ldw + k0 + c * 4, k0 + c * 4, a.K, w_vec)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            stage_chunk<SPLIT>(sW, sWlo, r, c, v);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
         __syncthreads();
@@ -178,23 +166,20 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const TcArgs a) {
                     umma_tf32(tmem_d, smem_desc(aA + ko), smem_desc(aWlo + ko), idesc, 1u);
                 }
             }
-            umma_commit(&bars[buf]);  // arrives when the MMAs above have finished reading this buffer
+            umma_commit(&bar);  // arrives when the MMAs above have finished
         }
     }
-    // the last commit on each buffer: use count u = number of slabs that went through it
-    for (int buf = 0; buf < 2; ++buf) {
-        const int uses = (num_kb - buf + 1) / 2;
-        if (uses > 0) mbar_wait(&bars[buf], (uses - 1) & 1);
-    }
+    mbar_wait(&bar, (num_kb - 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- epilogue: warp w owns TMEM lanes 32w .. 32w+31 (= rows), 8 columns per tcgen05.ld
-    const int m = m0 + warp * 32 + lane;
+    // ---- (a warp may only read the TMEM lane quadrant warp % 4: warps 0-3 take the even column groups, 4-7 the odd ones)
+    const int quad = warp & 3, m = m0 + quad * 32 + lane;
     float *crow = a.C + (size_t)g * a.gC + (size_t)m * a.ldc;
     const float *bias = a.bias ? a.bias + (size_t)g * a.gBias : nullptr;
-    for (int n0 = 0; n0 < npad; n0 += 8) {
+    for (int n0 = (warp >> 2) * 8; n0 < npad; n0 += 16) {
         uint32_t r[8];
-        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0;
+        const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)n0;
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                      : "r"(taddr));
@@ -231,12 +216,11 @@ bool tc_gemm_launch(cudaStream_t st, int G, const float *A, const float *W, cons
     a.M = M; a.N = N; a.K = K; a.npad = (N + 15) / 16 * 16;
     a.lda = lda; a.ldw = ldw; a.ldc = ldc; a.gA = gA; a.gW = gW; a.gBias = gBias; a.gC = gC;
     a.relu = relu; a.split = split;
-    const size_t stage = (size_t)(split == 3 ? 2 : 1) * ((size_t)kBM * 128 + (size_t)a.npad * 128);
-    const size_t smem = 2 * stage + 1024;
+    const size_t smem = (size_t)(split == 3 ? 2 : 1) * ((size_t)kBM * 128 + (size_t)a.npad * 128) + 1024;
     if (smem > 200 * 1024) return false;
     auto fn = split == 3 ? tc_gemm_kernel<3> : tc_gemm_kernel<1>;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-    fn<<<dim3((M + kBM - 1) / kBM, G), 128, smem, st>>>(a);
+    fn<<<dim3((M + kBM - 1) / kBM, G), kThreads, smem, st>>>(a);
     return true;
 }
 

@@ -289,12 +289,14 @@ def test_adam_optimizer_matches_torch():
         LearnerGroup(cfg.merged_with(opt=Config(dict(name="sgd", learning_rate=1e-3))), fix["shape"], 4, 1, B)
 
 
-@pytest.mark.parametrize("kind,V,C", [("dqn_conv_mlp", 7, 7), ("c51", 7, 3), ("iqn", 7, 3), ("c51", 5, 3), ("qr", 9, 4)])
-def test_large_batch_inference_path_matches_oracle(kind, V, C):
-    """Acting / evaluation batches (>= 512 rows) take the fused conv trunk and the large-tile GEMM: same Q-values."""
+@pytest.mark.parametrize("kind,V,C,B", [("dqn_conv_mlp", 7, 7, 640), ("c51", 7, 3, 640), ("iqn", 7, 3, 640), ("c51", 5, 3, 640),
+                                        ("qr", 9, 4, 640), ("c51", 7, 3, 2304), ("dqn_conv_mlp", 7, 7, 2100), ("da3", 7, 3, 2100)])
+def test_large_batch_inference_path_matches_oracle(kind, V, C, B):
+    """Acting / evaluation batches take the fused conv trunk (>= 512 rows) and, from 2048 rows, the tcgen05 tensor-core
+    GEMM with three TF32 terms per product: the Q-values stay within 1e-5 of the fp32 oracle."""
     from maexp_b200.core.agents.brains import LearnerGroup
     cfg, _ = golden_configs()[kind]
-    B, G = 640, 2
+    G = 2
     cfg = cfg.merged_with(batch_size=B, visible_range=V)
     g = LearnerGroup(cfg, [C, V, V], 4, G, B)
     gen = torch.Generator().manual_seed(3)
@@ -306,7 +308,7 @@ def test_large_batch_inference_path_matches_oracle(kind, V, C):
     for a in range(G):
         o = TorchLearner(kind, g.state_dict(a), 4, float(cfg.gamma), 1e-3, 0.99, 1e-8, num_atoms=ATOMS[kind])
         want = o.q_values_iqn(obs[a], tau[a:a + 1]) if kind == "iqn" else o.q_values(obs[a])
-        assert rel_err(q[a], want) < RTOL, (kind, a)
+        assert rel_err(q[a], want) < RTOL, (kind, a, rel_err(q[a], want))
     # a smaller batch through the same handle takes the layer-by-layer path and must agree
     q_small = g.q_values(packed[:, :100].contiguous(), tau_sel=tau.cuda() if kind == "iqn" else None).cpu()
     assert float((q_small - q[:, :100]).abs().max()) <= 1e-5 * float(q.abs().max())
