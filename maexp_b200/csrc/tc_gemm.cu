@@ -136,21 +136,34 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const TcArgs a) {
     const int num_kb = (a.K + kBK - 1) / kBK;
     const bool a_vec = (a.lda & 3) == 0 && (a.gA & 3) == 0 && ((uintptr_t)a.A & 15) == 0;
     const bool w_vec = (a.ldw & 3) == 0 && (a.gW & 3) == 0 && ((uintptr_t)a.W & 15) == 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-        const int k0 = kb * kBK;
-        if (kb >= 1) mbar_wait(&bar, (kb - 1) & 1);  // the MMAs of the previous slab have finished reading shared memory
-        // ---- stage A (128 rows x 8 chunks) and W (npad rows x 8 chunks): consecutive threads take consecutive chunks
-        for (int i = tid; i < kBM * 8; i += kThreads) {
-            const int r = i >> 3, c = i & 7, m = m0 + r;
-            const float4 v = m < a.M ? load_chunk(A + (size_t)m * a.lda + k0 + c * 4, k0 + c * 4, a.K, a_vec)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-            stage_chunk<SPLIT>(sA, sAlo, r, c, v);
+    // register prefetch: the global loads of slab kb + 1 are issued right after slab kb's MMAs and stay in flight
+    // while those run and while this CTA waits for them (4 A chunks and up to 8 W chunks of 16 bytes per thread)
+    float4 ra[kBM * 8 / kThreads], rw[256 * 8 / kThreads];
+    auto prefetch = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < kBM * 8 / kThreads; ++j) {
+            const int i = tid + j * kThreads, r = i >> 3, c = i & 7, m = m0 + r;
+            ra[j] = m < a.M ? load_chunk(A + (size_t)m * a.lda + k0 + c * 4, k0 + c * 4, a.K, a_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (int i = tid; i < npad * 8; i += kThreads) {
-            const int r = i >> 3, c = i & 7;
-            const float4 v = r < a.N ? load_chunk(W + (size_t)r * a.ldw + k0 + c * 4, k0 + c * 4, a.K, w_vec)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-            stage_chunk<SPLIT>(sW, sWlo, r, c, v);
+#pragma unroll
+        for (int j = 0; j < 256 * 8 / kThreads; ++j) {
+            const int i = tid + j * kThreads, r = i >> 3, c = i & 7;
+            if (i < npad * 8)
+                rw[j] = r < a.N ? load_chunk(W + (size_t)r * a.ldw + k0 + c * 4, k0 + c * 4, a.K, w_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    prefetch(0);
+    for (int kb = 0; kb < num_kb; ++kb) {
+        if (kb >= 1) mbar_wait(&bar, (kb - 1) & 1);  // the MMAs of the previous slab have finished reading shared memory
+#pragma unroll
+        for (int j = 0; j < kBM * 8 / kThreads; ++j) {
+            const int i = tid + j * kThreads;
+            stage_chunk<SPLIT>(sA, sAlo, i >> 3, i & 7, ra[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 256 * 8 / kThreads; ++j) {
+            const int i = tid + j * kThreads;
+            if (i < npad * 8) stage_chunk<SPLIT>(sW, sWlo, i >> 3, i & 7, rw[j]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
         __syncthreads();
@@ -168,31 +181,46 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const TcArgs a) {
             }
             umma_commit(&bar);  // arrives when the MMAs above have finished
         }
+        if (kb + 1 < num_kb) prefetch((kb + 1) * kBK);
     }
     mbar_wait(&bar, (num_kb - 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- epilogue: warp w owns TMEM lanes 32w .. 32w+31 (= rows), 8 columns per tcgen05.ld
-    // ---- (a warp may only read the TMEM lane quadrant warp % 4: warps 0-3 take the even column groups, 4-7 the odd ones)
+    // ---- (a warp may only read the TMEM lane quadrant warp % 4: warps 0-3 take the even 16-column groups, 4-7 the odd
+    //      ones).  Sixteen consecutive columns per load = 64 contiguous bytes of the thread's output row.
     const int quad = warp & 3, m = m0 + quad * 32 + lane;
     float *crow = a.C + (size_t)g * a.gC + (size_t)m * a.ldc;
     const float *bias = a.bias ? a.bias + (size_t)g * a.gBias : nullptr;
-    for (int n0 = (warp >> 2) * 8; n0 < npad; n0 += 16) {
-        uint32_t r[8];
+    const bool c_vec = (a.ldc & 3) == 0 && (a.gC & 3) == 0 && ((uintptr_t)a.C & 15) == 0;
+    for (int n0 = (warp >> 2) * 16; n0 < npad; n0 += 32) {
+        uint32_t r[16];
         const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)n0;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                     : "r"(taddr));
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (m < a.M) {
+            float v[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const int n = n0 + j;
-                if (n < a.N) {
-                    float v = __uint_as_float(r[j]);
-                    if (bias) v += bias[n];
-                    if (a.relu) v = fmaxf(v, 0.0f);
-                    crow[n] = v;
+                float x = __uint_as_float(r[j]);
+                if (bias && n < a.N) x += bias[n];
+                if (a.relu) x = fmaxf(x, 0.0f);
+                v[j] = x;
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const int n = n0 + j4 * 4;
+                if (c_vec && n + 3 < a.N) {
+                    *reinterpret_cast<float4 *>(crow + n) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < a.N) crow[n + j] = v[j4 * 4 + j];
                 }
             }
         }

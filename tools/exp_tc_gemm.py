@@ -33,3 +33,14 @@ for split in (1, 3):
     b.record(); torch.cuda.synchronize()
     us = a.elapsed_time(b) / 20 * 1e3
     print(f"split={split}: {us:.1f} us, {2 * M * N * K / us / 1e6:.1f} TFLOP/s (fp32-equivalent)")
+
+print("fixed vs per-slab cost (M=32768, N=128, split=3):")
+for K in (32, 64, 128, 256, 512):
+    A = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda")
+    for _ in range(3):
+        lib.maexp_tc_gemm(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), None, C.c_void_p(Cout.data_ptr()), M, N, K, K, K, N, 0, 3, None)
+    a.record()
+    for _ in range(20):
+        lib.maexp_tc_gemm(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), None, C.c_void_p(Cout.data_ptr()), M, N, K, K, K, N, 0, 3, None)
+    b.record(); torch.cuda.synchronize()
+    print(f"  K={K}: {a.elapsed_time(b) / 20 * 1e3:.1f} us")
