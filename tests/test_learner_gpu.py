@@ -312,3 +312,29 @@ def test_large_batch_inference_path_matches_oracle(kind, V, C, B):
     # a smaller batch through the same handle takes the layer-by-layer path and must agree
     q_small = g.q_values(packed[:, :100].contiguous(), tau_sel=tau.cuda() if kind == "iqn" else None).cpu()
     assert float((q_small - q[:, :100]).abs().max()) <= 1e-5 * float(q.abs().max())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (300, 64, 72), (4096, 128, 256), (4096, 51, 128), (2500, 204, 128), (1000, 32, 96),
+                                   (513, 256, 40)])
+def test_tcgen05_gemm_against_fp64(M, N, K):
+    """maexp_tc_gemm (tcgen05.mma kind::tf32): three TF32 terms per product stay within 1e-5 of the exact product sum,
+    single-pass TF32 within 2e-3; ragged M / N / K, misaligned weight rows, bias and ReLU."""
+    import ctypes as C
+    from maexp_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((M, K), generator=gen).cuda()
+    flat = torch.randn((N * K + 3,), generator=gen).cuda() * 0.1
+    W = flat[1:1 + N * K].view(N, K) if K % 4 else flat[:N * K].view(N, K)   # odd offsets exercise the scalar weight loads
+    bias = torch.randn((N,), generator=gen).cuda()
+    want = torch.relu(A.double() @ W.double().T + bias.double())
+    for split, tol in ((3, 1e-5), (1, 2e-3)):
+        out = torch.full((M, N), float("nan"), device="cuda")
+        _lib.check(lib.maexp_tc_gemm(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(bias.data_ptr()),
+                                     C.c_void_p(out.data_ptr()), M, N, K, K, K, N, 1, split, None))
+        torch.cuda.synchronize()
+        assert not torch.isnan(out).any()
+        assert float((out.double() - want).abs().max() / want.abs().max()) < tol, (split,)
+    with pytest.raises(Exception):
+        _lib.check(lib.maexp_tc_gemm(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), None, C.c_void_p(out.data_ptr()),
+                                     M, 300, K, K, K, 300, 0, 3, None))
