@@ -47,7 +47,7 @@ def generate_agents(config, observation_space, action_space):
 class BatchedActor:
     """Epsilon-greedy actions for all environments of a BatchedEnvironment from a LearnerGroup's online nets."""
 
-    def __init__(self, config, env, learner, chunk=4096):
+    def __init__(self, config, env, learner, chunk=8192):
         self.lib = _lib.load()
         self.env, self.learner = env, learner
         self.chunk = min(int(chunk), env.E)

@@ -9,6 +9,9 @@ from tests.cuda_backend import make_env
 E = int(os.environ.get("E", "65536"))
 cfg = baseline_config(int(os.environ.get("CFG", "5"))).merged_with(populate_steps=4 * E, capacity=8 * E, max_episode_length=200)
 t = generate_trainer(cfg, make_env(cfg, E, auto_reset=True))
+if os.environ.get("CHUNK"):
+    from maexp_b200.core.agents import BatchedActor
+    t.actor = BatchedActor(cfg, t.env, t.learner, chunk=int(os.environ["CHUNK"]))
 t.populate(4)
 torch.cuda.synchronize()
 
