@@ -581,22 +581,47 @@ __global__ void dist_q_kernel(const float *v, const float *adv, const float *sup
     const int g = blockIdx.y, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     const size_t i = (size_t)g * Bmax + warp;  // head outputs are strided by the maximum batch
-    for (int a = 0; a < A; ++a) {
+    const float *vrow = v + i * Z, *arow = adv + i * A * Z;
+    // each lane keeps its atoms of every action: v + (adv - mean over actions), computed once (same operation order as dueling())
+    float d[kMaxActions][kMaxAtomsPerLane];
+#pragma unroll
+    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+        const int j = lane + 32 * t;
+        if (j >= Z) continue;
+        float ad[kMaxActions], s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kMaxActions; ++k)
+            if (k < A) { ad[k] = arow[k * Z + j]; s = __fadd_rn(s, ad[k]); }
+        const float mean = __fdiv_rn(s, (float)A), vj = vrow[j];
+#pragma unroll
+        for (int k = 0; k < kMaxActions; ++k)
+            if (k < A) d[k][t] = __fadd_rn(vj, __fadd_rn(ad[k], -mean));
+    }
+#pragma unroll
+    for (int a = 0; a < kMaxActions; ++a) {
+        if (a >= A) break;
         float out;
         if (categorical) {
             float mx = -INFINITY;
-            for (int j = lane; j < Z; j += 32) mx = fmaxf(mx, dueling(v + i * Z, adv + i * A * Z, A, Z, a, j));
+#pragma unroll
+            for (int t = 0; t < kMaxAtomsPerLane; ++t)
+                if (lane + 32 * t < Z) mx = fmaxf(mx, d[a][t]);
             mx = warp_max(mx);
             float se = 0.0f, sq = 0.0f;
-            for (int j = lane; j < Z; j += 32) {
-                const float e = expf(__fadd_rn(dueling(v + i * Z, adv + i * A * Z, A, Z, a, j), -mx));
+#pragma unroll
+            for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+                const int j = lane + 32 * t;
+                if (j >= Z) continue;
+                const float e = expf(__fadd_rn(d[a][t], -mx));
                 se = __fadd_rn(se, e);
                 sq = __fadd_rn(sq, __fmul_rn(e, support[j]));
             }
             out = __fdiv_rn(warp_sum(sq), warp_sum(se));
         } else {
             float s = 0.0f;
-            for (int j = lane; j < Z; j += 32) s = __fadd_rn(s, dueling(v + i * Z, adv + i * A * Z, A, Z, a, j));
+#pragma unroll
+            for (int t = 0; t < kMaxAtomsPerLane; ++t)
+                if (lane + 32 * t < Z) s = __fadd_rn(s, d[a][t]);
             out = __fdiv_rn(warp_sum(s), (float)Z);
         }
         if (lane == 0) q[((size_t)g * B + warp) * A + a] = out;
