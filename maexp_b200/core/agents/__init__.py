@@ -37,9 +37,25 @@ class DefaultAgent:
         self.brain.synchronize_network()
 
 
+class AttentionAgent(DefaultAgent):
+    """attention_agent.py:13-27: the brain returns (action, attns); the maps of each group are stacked over the blocks."""
+
+    def get_action_attns(self, state, epsilon):
+        action, attns = self.brain.get_action(state)
+        attns = [torch.stack(attn) for attn in attns]
+        if random.random() < epsilon:
+            action = self.get_random_action()
+        return action, attns
+
+    def get_action(self, state, epsilon):
+        return self.get_action_attns(state, epsilon)[0]
+
+
 def generate_agents(config, observation_space, action_space):
     if config.agent_type == "default":
         return [DefaultAgent(config, obs, act) for obs, act in zip(observation_space, action_space)]
+    if config.agent_type == "attention":
+        return [AttentionAgent(config, obs, act) for obs, act in zip(observation_space, action_space)]
     logger.warning(f"Unexpected agent type is given. config.agent_type: {config.agent_type}")
     raise ValueError()
 

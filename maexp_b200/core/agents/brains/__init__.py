@@ -296,9 +296,27 @@ class Brain:
 
     @torch.no_grad()
     def get_action(self, state):
+        """int for the plain brains (abstract_brain.py:52-64); (action, attns) for the attention brains:
+        da3 / da3_iqn return forward_attn's per-block attention weights [1, heads, T, T] — [attns] on the local view,
+        [local_attns, relative_attns] for the merged models and DA6 (da3_brain.py:47-56, customs/da3.py:167-176,
+        customs/da6.py:128-165) — and da3_baseline a zero placeholder (da3_brain.py:93-123)."""
         pos = self._positions(state, False) if self.group.area_mask != "local" else None
         q = self.group.q_values(self._pack(state[self.view].unsqueeze(0)), pos=pos)
-        return int(q[0, 0].argmax().item())
+        action = int(q[0, 0].argmax().item())
+        brain = self.config.brain
+        if brain == "da3_baseline":
+            t = int(self.config.visible_range) ** 2 + 1
+            heads = int(self.config.model.get("num_heads") or 1)
+            return action, [[torch.zeros((int(self.config.batch_size), heads, t, t), device=self.device)]]
+        if brain in ("da3", "da6", "da3_iqn"):
+            g, blocks = self.group, int(self.config.model.block_loop)
+            local = [g.attention(1, stack=0, layer=l)[0] for l in range(blocks)]
+            if g.lib.maexp_learner_attention_tokens(g.h, 1) > 0:  # DA6 / DA6_IQN: the relative transformer
+                return action, [local, [g.attention(1, stack=1, layer=l)[0] for l in range(blocks)]]
+            if g.area_mask == "merged":  # MergedDA3 returns the local maps twice (customs/da3.py:199-201)
+                return action, [local, local]
+            return action, [local]
+        return action
 
     def learn(self, states_ind, actions_ind, rewards_ind, dones_ind, next_states_ind):
         batch = {"obs": self._pack(states_ind[self.view]), "next_obs": self._pack(next_states_ind[self.view]),

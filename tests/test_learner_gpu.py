@@ -338,3 +338,31 @@ def test_tcgen05_gemm_against_fp64(M, N, K):
     with pytest.raises(Exception):
         _lib.check(lib.maexp_tc_gemm(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), None, C.c_void_p(out.data_ptr()),
                                      M, 300, K, K, K, 300, 0, 3, None))
+
+
+def test_attention_agent_returns_reference_structures():
+    """generate_agents(agent_type=attention): get_action_attns -> (action, [stacked maps per group]) as attention_agent.py:14-22;
+    DA6 gives [local, relative], the da3_baseline brain the zero placeholder of da3_brain.py:107-123."""
+    from maexp_b200.core.agents import generate_agents
+    from oracle.make_golden_learner import ref_state
+    fix = load("da6")
+    cfg, shape = golden_configs()["da6"]
+    agents = generate_agents(cfg.merged_with(agent_type="attention"), [shape], [4])
+    assert len(agents) == 1
+    agent = agents[0]
+    agent.brain.network.load_state_dict(fix["init"])
+    b = fix["batch"]
+    st = ref_state(b["obs"][:1], b["pos"][:1])
+    state = {"local": st["local"][0], "relative": st["relative"][0], "coordinates": {k: int(v[0]) for k, v in st["coordinates"].items()}}
+    action, attns = agent.get_action_attns(state, 0.0)
+    assert action == int(fix["q0"][0].argmax())
+    heads, blocks = int(cfg["model"]["num_heads"]), int(cfg["model"]["block_loop"])
+    assert len(attns) == 2 and attns[0].shape == (blocks, 1, heads, 26, 26) and attns[1].shape == (blocks, 1, heads, 13, 13)
+    assert float((attns[0].sum(-1) - 1).abs().max()) < 1e-5  # softmax rows
+    assert isinstance(agent.get_action(state, 0.0), int)
+    base_cfg, base_shape = golden_configs()["dqn_conv_mlp"]
+    base = generate_agents(base_cfg.merged_with(agent_type="attention"), [base_shape], [4])[0]
+    a, placeholder = base.get_action_attns({"local": load("dqn_conv_mlp")["batch"]["obs"][0].clone()}, 0.0)
+    assert isinstance(a, int) and float(placeholder[0].abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        generate_agents(cfg.merged_with(agent_type="nope"), [shape], [4])
