@@ -1170,6 +1170,10 @@ inline dim3 grid1d(long long total, int g, int threads = 256, int cap = 1024) {
 constexpr long long kSplitWorkspaceFloats = 8ll << 20;  // 32 MB of partial tiles
 float *g_splitk_ws = nullptr;                            // set per call from the handle (single host thread)
 bool g_inference_tc = false;                             // set by the q_values entry points around their forward pass
+struct InferenceScope {                                  // (every model family: conv heads, transformer projections)
+    explicit InferenceScope(bool on) { g_inference_tc = on; }
+    ~InferenceScope() { g_inference_tc = false; }
+};
 
 void gemm(cudaStream_t st, int G, const float *A, const float *Bm, float *C, const float *bias, int M, int N, int K,
           long long sam, long long sak, long long sbk, long long sbn, long long scm, long long scn, long long gA,
@@ -2338,6 +2342,7 @@ int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int us
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     maexp_learner::Acts &a = h->acts[1];
     g_splitk_ws = h->splitk_ws;
+    const InferenceScope tensor_cores(h->use_tc);
     if (h->relative_conv || h->merged_conv || h->merged_da3) {
         float *q = nullptr;
         if (merged_forward(h, st, use_target ? h->target : h->online, obs, h->pos, batch, 1, &q)) return -1;
@@ -2357,9 +2362,7 @@ int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int us
         MAEXP_CUDA_L(cudaGetLastError());
         return 0;
     }
-    g_inference_tc = h->use_tc;
     forward(h, st, use_target ? h->target : h->online, obs, batch, a, /*inference=*/true);
-    g_inference_tc = false;
     if (!h->dist) {
         // heads are strided by the maximum batch: compact to [G][batch][A]
         MAEXP_CUDA_L(cudaMemcpy2DAsync(q_out, sizeof(float) * batch * h->A, a.out[0], sizeof(float) * h->B * h->A,
@@ -2472,10 +2475,8 @@ int maexp_learner_q_values_iqn(maexp_learner *h, const float *obs, int batch, in
     if (batch < 1 || batch > h->B) return fail("maexp_learner_q_values_iqn: batch must be in 1..batch_size");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     g_splitk_ws = h->splitk_ws;
-    g_inference_tc = h->use_tc;
-    const int rc_fwd = iqn_forward(h, st, use_target ? h->target : h->online, obs, h->pos, batch, tau_sel, h->Nq, /*per_sample=*/0, 1);
-    g_inference_tc = false;
-    if (rc_fwd) return -1;
+    const InferenceScope tensor_cores(h->use_tc);
+    if (iqn_forward(h, st, use_target ? h->target : h->online, obs, h->pos, batch, tau_sel, h->Nq, /*per_sample=*/0, 1)) return -1;
     iqn_q_kernel<<<dim3((batch + 127) / 128, h->G), 128, 0, st>>>(h->iq[1].out[0], h->iq[1].out[1], batch, h->A, h->Nq,
                                                                   h->rows_max, h->rows_max * h->A, q_out);
     MAEXP_CUDA_L(cudaGetLastError());
