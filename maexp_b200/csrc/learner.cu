@@ -1262,7 +1262,7 @@ void wgrad_close() {  // join the side streams back into the main stream
 // stored channel-major so that a channel's cells are three 128-bit broadcast loads.  V is a template parameter: every
 // cell / tap index is a compile-time constant.  flat[b][oc*H2*W2 + pos] is PyTorch's flatten order (convolution.py:44-55).
 template <int V>
-__global__ void __launch_bounds__(128) trunk_fused_fwd_kernel(const float *obs, const float *params, float *flat, int B, int C,
+__global__ void __launch_bounds__(256) trunk_fused_fwd_kernel(const float *obs, const float *params, float *flat, int B, int C,
                                                               int F1, int F2, long long stride, long long gObs, long long P,
                                                               long long o_c1w, long long o_c1b, long long o_c2w,
                                                               long long o_c2b, long long gFlat) {
@@ -1356,7 +1356,7 @@ void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const
     const long long P = h->P, Bmax = h->B, stride = h->cfg.obs_stride;
     const int H1 = h->H1, Hp = h->Hp, H2 = h->H2;
     if (inference && B >= 512 && F1 <= 32 && F2 <= 64 && (V == 5 || V == 7 || V == 9)) {  // nothing is kept for a backward pass
-        const int warps = 4, pc = (Hp * Hp + 3) / 4 * 4;
+        const int warps = 8, pc = (Hp * Hp + 3) / 4 * 4;
         const size_t smem = sizeof(float) * ((size_t)F1 * 256 + (size_t)C * 4 * 32 + 96 +
                                              (size_t)warps * (32 * pc + (C * V * V + 3) / 4 * 4));
         if (smem <= 200 * 1024) {
