@@ -271,7 +271,7 @@ int maexp_learner_attention_tokens(const maexp_learner *learner, int stack);
 int maexp_learner_attention(maexp_learner *learner, int stack, int layer, int batch, float *out, void *stream);
 
 /* Tensor-core GEMM of the large acting / evaluation batches (csrc/tc_gemm.cu: tcgen05.mma kind::tf32, accumulators in
- * tensor memory): C[M,N] = epi(A[M,K] * W[N,K]^T + bias) with fp32 device buffers, N <= 256; the layer products of
+ * tensor memory): C[M,N] = epi(A[M,K] * W[N,K]^T + bias) with fp32 device buffers (column tiles of 256); the layer products of
  * models/mlp.py:28-34 at inference batch sizes.  split = 3 evaluates every product as three TF32 terms (fp32-level
  * accuracy), split = 1 is plain TF32. */
 int maexp_tc_gemm(const float *A, const float *W, const float *bias, float *C, int32_t M, int32_t N, int32_t K, int64_t lda,

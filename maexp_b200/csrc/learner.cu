@@ -1188,7 +1188,7 @@ void gemm(cudaStream_t st, int G, const float *A, const float *Bm, float *C, con
     // thousands of rows, both operands K-major and 16-byte aligned along K: the large-tile kernels
     auto aligned16 = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
     // acting / evaluation forward passes (g_inference_tc): tensor cores, three TF32 terms per product (fp32-level accuracy)
-    if (g_inference_tc && M >= 2048 && N <= 256 && K >= 32 && sak == 1 && sbk == 1 && scn == 1 && !accumulate && !aux &&
+    if (g_inference_tc && M >= 512 && K >= 32 && sak == 1 && sbk == 1 && scn == 1 && !accumulate && !aux &&
         tc_gemm_launch(st, G, A, Bm, bias, C, M, N, K, sam, sbn, scm, gA, gB, gBias, gC, relu, 3))
         return;
     if (M >= 2048 && sak == 1 && sbk == 1 && (K & 3) == 0 && (sam & 3) == 0 && (gA & 3) == 0 && aligned16(A)) {

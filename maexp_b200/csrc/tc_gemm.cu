@@ -107,8 +107,10 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const TcArgs a) {
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_smem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = blockIdx.y;
-    const int m0 = blockIdx.x * kBM, npad = a.npad;
-    const float *A = a.A + (size_t)g * a.gA, *W = a.W + (size_t)g * a.gW;
+    // wide layers: blockIdx.z walks column tiles of 256; a.N / a.npad below are this tile's
+    const int nt0 = blockIdx.z * 256, tileN = min(256, a.N - nt0), npad = (tileN + 15) / 16 * 16;
+    const int m0 = blockIdx.x * kBM;
+    const float *A = a.A + (size_t)g * a.gA, *W = a.W + (size_t)g * a.gW + (size_t)nt0 * a.ldw;
     const uint32_t a_bytes = kBM * 128, w_bytes = (uint32_t)npad * 128;
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem, *sAlo = sA + a_bytes;
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const TcArgs a) {
         for (int j = 0; j < 256 * 8 / kThreads; ++j) {
             const int i = tid + j * kThreads, r = i >> 3, c = i & 7;
             if (i < npad * 8)
-                rw[j] = r < a.N ? load_chunk(W + (size_t)r * a.ldw + k0 + c * 4, k0 + c * 4, a.K, w_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                rw[j] = r < tileN ? load_chunk(W + (size_t)r * a.ldw + k0 + c * 4, k0 + c * 4, a.K, w_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     prefetch(0);
@@ -190,8 +192,8 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const TcArgs a) {
     // ---- (a warp may only read the TMEM lane quadrant warp % 4: warps 0-3 take the even 16-column groups, 4-7 the odd
     //      ones).  Sixteen consecutive columns per load = 64 contiguous bytes of the thread's output row.
     const int quad = warp & 3, m = m0 + quad * 32 + lane;
-    float *crow = a.C + (size_t)g * a.gC + (size_t)m * a.ldc;
-    const float *bias = a.bias ? a.bias + (size_t)g * a.gBias : nullptr;
+    float *crow = a.C + (size_t)g * a.gC + (size_t)m * a.ldc + nt0;
+    const float *bias = a.bias ? a.bias + (size_t)g * a.gBias + nt0 : nullptr;
     const bool c_vec = (a.ldc & 3) == 0 && (a.gC & 3) == 0 && ((uintptr_t)a.C & 15) == 0;
     for (int n0 = (warp >> 2) * 16; n0 < npad; n0 += 32) {
         uint32_t r[16];
@@ -208,19 +210,19 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const TcArgs a) {
             for (int j = 0; j < 16; ++j) {
                 const int n = n0 + j;
                 float x = __uint_as_float(r[j]);
-                if (bias && n < a.N) x += bias[n];
+                if (bias && n < tileN) x += bias[n];
                 if (a.relu) x = fmaxf(x, 0.0f);
                 v[j] = x;
             }
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
                 const int n = n0 + j4 * 4;
-                if (c_vec && n + 3 < a.N) {
+                if (c_vec && n + 3 < tileN) {
                     *reinterpret_cast<float4 *>(crow + n) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (n + j < a.N) crow[n + j] = v[j4 * 4 + j];
+                        if (n + j < tileN) crow[n + j] = v[j4 * 4 + j];
                 }
             }
         }
@@ -238,17 +240,17 @@ namespace maexp {
 bool tc_gemm_launch(cudaStream_t st, int G, const float *A, const float *W, const float *bias, float *C, int M, int N, int K,
                     long long lda, long long ldw, long long ldc, long long gA, long long gW, long long gBias, long long gC, int relu,
                     int split) {
-    if (N < 1 || N > 256 || M < 1 || K < 1) return false;
+    if (N < 1 || M < 1 || K < 1) return false;
     TcArgs a;
     a.A = A; a.W = W; a.bias = bias; a.C = C;
-    a.M = M; a.N = N; a.K = K; a.npad = (N + 15) / 16 * 16;
+    a.M = M; a.N = N; a.K = K; a.npad = ((N < 256 ? N : 256) + 15) / 16 * 16;  // widest column tile (sizes shared memory)
     a.lda = lda; a.ldw = ldw; a.ldc = ldc; a.gA = gA; a.gW = gW; a.gBias = gBias; a.gC = gC;
     a.relu = relu; a.split = split;
     const size_t smem = (size_t)(split == 3 ? 2 : 1) * ((size_t)kBM * 128 + (size_t)a.npad * 128) + 1024;
     if (smem > 200 * 1024) return false;
     auto fn = split == 3 ? tc_gemm_kernel<3> : tc_gemm_kernel<1>;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-    fn<<<dim3((M + kBM - 1) / kBM, G), kThreads, smem, st>>>(a);
+    fn<<<dim3((M + kBM - 1) / kBM, G, (N + 255) / 256), kThreads, smem, st>>>(a);
     return true;
 }
 
@@ -259,7 +261,7 @@ extern "C" int maexp_tc_gemm(const float *A, const float *W, const float *bias, 
     if (!A || !W || !C) return maexp::fail("maexp_tc_gemm: null argument");
     if (split != 1 && split != 3) return maexp::fail("maexp_tc_gemm: split must be 1 (TF32) or 3 (3xTF32)");
     if (!maexp::tc_gemm_launch(static_cast<cudaStream_t>(stream), 1, A, W, bias, C, M, N, K, lda, ldw, ldc, 0, 0, 0, 0, relu, split))
-        return maexp::fail("maexp_tc_gemm: unsupported shape (N <= 256)");
+        return maexp::fail("maexp_tc_gemm: unsupported shape");
     if (cudaGetLastError() != cudaSuccess) return maexp::fail("maexp_tc_gemm: launch failed");
     return 0;
 }

@@ -315,7 +315,7 @@ def test_large_batch_inference_path_matches_oracle(kind, V, C, B):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (300, 64, 72), (4096, 128, 256), (4096, 51, 128), (2500, 204, 128), (1000, 32, 96),
-                                   (513, 256, 40)])
+                                   (513, 256, 40), (640, 700, 64), (300, 257, 32)])
 def test_tcgen05_gemm_against_fp64(M, N, K):
     """maexp_tc_gemm (tcgen05.mma kind::tf32): three TF32 terms per product stay within 1e-5 of the exact product sum,
     single-pass TF32 within 2e-3; ragged M / N / K, misaligned weight rows, bias and ReLU."""
@@ -337,7 +337,7 @@ def test_tcgen05_gemm_against_fp64(M, N, K):
         assert float((out.double() - want).abs().max() / want.abs().max()) < tol, (split,)
     with pytest.raises(Exception):
         _lib.check(lib.maexp_tc_gemm(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), None, C.c_void_p(out.data_ptr()),
-                                     M, 300, K, K, K, 300, 0, 3, None))
+                                     M, N, K, K, K, N, 0, 2, None))  # split must be 1 or 3
 
 
 def test_attention_agent_returns_reference_structures():
