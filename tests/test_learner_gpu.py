@@ -290,7 +290,7 @@ def test_adam_optimizer_matches_torch():
 
 
 @pytest.mark.parametrize("kind,V,C,B", [("dqn_conv_mlp", 7, 7, 640), ("c51", 7, 3, 640), ("iqn", 7, 3, 640), ("c51", 5, 3, 640),
-                                        ("qr", 9, 4, 640), ("c51", 7, 3, 2304), ("dqn_conv_mlp", 7, 7, 2100), ("da3", 7, 3, 2100), ("da3", 7, 3, 48)])
+                                        ("qr", 9, 4, 640), ("c51", 7, 3, 2304), ("dqn_conv_mlp", 7, 7, 2100), ("da3", 7, 3, 2100), ("da3", 7, 3, 48), ("da3", 9, 3, 300)])
 def test_large_batch_inference_path_matches_oracle(kind, V, C, B):
     """Acting / evaluation batches take the fused conv trunk (>= 512 rows) and, from 2048 rows, the tcgen05 tensor-core
     GEMM with three TF32 terms per product: the Q-values stay within 1e-5 of the fp32 oracle."""
