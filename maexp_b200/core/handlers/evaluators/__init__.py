@@ -60,7 +60,8 @@ class DefaultEvaluator:
             reward_sum = torch.zeros((env.N,), device=env.device)
             for _ in range(int(self.config.max_episode_length)):
                 head = ring.head
-                actions = self.actor.act(ring.obs[head], 0.0, self.tick, positions=ring.positions[head])  # greedy
+                positions = None if ring.positions is None else ring.positions[head]
+                actions = self.actor.act(ring.obs[head], 0.0, self.tick, positions=positions)  # greedy
                 out = ring.next_outputs()
                 env.step(out, actions=actions, tick=self._tick())
                 ring.commit()

@@ -58,7 +58,8 @@ class DefaultTrainer:
         loss = self.learner.learn(self.batch, active=self.active, all_reduce=self.all_reduce)
         self.actor.refresh()
         head = self.buffer.head
-        actions = self.actor.act(self.buffer.obs[head], self.epsilon, self.tick, positions=self.buffer.positions[head])
+        positions = None if self.buffer.positions is None else self.buffer.positions[head]
+        actions = self.actor.act(self.buffer.obs[head], self.epsilon, self.tick, positions=positions)
         out = self.buffer.next_outputs()
         self.env.step(out, actions=actions, tick=self._tick())
         self.buffer.commit()

@@ -15,7 +15,7 @@ logger = initialize_logging(__name__)
 
 
 class DeviceReplayRing:
-    def __init__(self, env, num_slots):
+    def __init__(self, env, num_slots, keep_positions=False):
         self.lib = _lib.load()
         self.env, self.S = env, int(num_slots)
         E, N, d = env.E, env.N, env.device
@@ -24,7 +24,10 @@ class DeviceReplayRing:
         self.rewards = torch.zeros((self.S, E, N), dtype=torch.float32, device=d)
         self.dones = torch.zeros((self.S, E, N), dtype=torch.uint8, device=d)
         self.was_reset = torch.ones((self.S, E), dtype=torch.uint8, device=d)
-        self.positions = torch.zeros((self.S, E, N, 2), dtype=torch.int8, device=d)
+        # the agents' cells stand in for the `coordinates` dict, which only the relative / merged models read
+        # (observation_handler.py:150-216); local-view rings do not spend a store per agent on them
+        self.positions = None if env.config.observation_area_mask == "local" and not keep_positions else \
+            torch.zeros((self.S, E, N, 2), dtype=torch.int8, device=d)
         self.head, self.count = -1, 0
 
     def __len__(self):
@@ -34,8 +37,11 @@ class DeviceReplayRing:
     def next_outputs(self):
         """Output dict for env.step / env.reset that targets the next ring slot; call commit() after."""
         s = (self.head + 1) % self.S
-        return {"obs": self.obs[s], "rewards": self.rewards[s], "dones": self.dones[s],
-                "was_reset": self.was_reset[s], "actions_taken": self.actions[s], "positions": self.positions[s]}
+        out = {"obs": self.obs[s], "rewards": self.rewards[s], "dones": self.dones[s],
+               "was_reset": self.was_reset[s], "actions_taken": self.actions[s]}
+        if self.positions is not None:
+            out["positions"] = self.positions[s]
+        return out
 
     def commit(self):
         self.head = (self.head + 1) % self.S
@@ -56,7 +62,8 @@ class DeviceReplayRing:
         """Fills `batch` (from new_batch) with uniformly sampled transitions; indices: int32 [B,2]."""
         B = batch["actions"].shape[1]
         view = _lib.ReplayView(self.obs.data_ptr(), self.actions.data_ptr(), self.rewards.data_ptr(),
-                               self.dones.data_ptr(), self.was_reset.data_ptr(), self.positions.data_ptr(), self.S, self.env.E, self.env.N,
+                               self.dones.data_ptr(), self.was_reset.data_ptr(),
+                               None if self.positions is None else self.positions.data_ptr(), self.S, self.env.E, self.env.N,
                                self.env.slot_floats, self.head, self.count)
         out = _lib.Batch(*[batch[k].data_ptr() for k in ("obs", "next_obs", "actions", "rewards", "dones", "picked", "pos",
                                                          "next_pos")])

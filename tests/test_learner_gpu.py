@@ -179,7 +179,8 @@ def test_replay_ring_sampling():
     cfg = baseline_config(5).merged_with(max_episode_length=7)
     E, N, S, B = 48, 8, 16, 64
     env = make_env(cfg, E, auto_reset=True)
-    ring = DeviceReplayRing(env, S)
+    assert DeviceReplayRing(env, 2).positions is None  # local view: the models never read the coordinates
+    ring = DeviceReplayRing(env, S, keep_positions=True)
     env.reset(ring.next_outputs(), tick=0)
     ring.commit()
     for t in range(1, 23):  # wraps the ring, crosses two auto-resets

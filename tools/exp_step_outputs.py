@@ -14,7 +14,7 @@ from tests.cuda_backend import make_env
 
 E = 65536
 env = make_env(baseline_config(5), E, auto_reset=True)
-ring = DeviceReplayRing(env, 8)
+ring = DeviceReplayRing(env, 8, keep_positions=True)
 env.reset(ring.next_outputs(), tick=0)
 ring.commit()
 tick = [0]

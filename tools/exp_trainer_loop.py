@@ -30,14 +30,14 @@ print("loop_step ms      ", timed(t.loop_step))
 print("  sample+learn ms ", timed(lambda: (t.buffer.sample(t.batch, seed=1, tick=t.tick), t.learner.learn(t.batch, active=t.active))))
 print("  refresh ms      ", timed(t.actor.refresh))
 h = t.buffer.head
-print("  act ms          ", timed(lambda: t.actor.act(t.buffer.obs[h], 0.1, 5, positions=t.buffer.positions[h])))
+print("  act ms          ", timed(lambda: t.actor.act(t.buffer.obs[h], 0.1, 5, positions=None if t.buffer.positions is None else t.buffer.positions[h])))
 print("  env.step ms     ", timed(lambda: t.env.step(t.buffer.next_outputs(), tick=t._tick())))
 print("agent-steps/s in the loop:", E * t.env.N / (timed(t.loop_step) * 1e-3))
 
 import collections
 from torch.profiler import ProfilerActivity, profile
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    t.actor.act(t.buffer.obs[h], 0.1, 5, positions=t.buffer.positions[h])
+    t.actor.act(t.buffer.obs[h], 0.1, 5, positions=None if t.buffer.positions is None else t.buffer.positions[h])
     torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0, 0.0])
 for e in prof.events():
