@@ -276,3 +276,78 @@ def test_heatmaps_match_oracle(name):
     for key, t in split().items():
         assert np.array_equal(t.cpu().numpy(), want[key]), key
     assert want["heatmap_agents"].sum() > 0 and want["heatmap_wall_collision"].sum() > 0
+
+
+def _random_config(rng):
+    """A random valid configuration over the whole supported surface (maps, views, masks, noises, environments)."""
+    maps = {
+        "simple": (dict(name="simple", SIZE_X=int(rng.integers(12, 27)), SIZE_Y=int(rng.integers(12, 25))), (1, 2)),
+        "four_rooms": (dict(name="four_rooms", SIZE_X=24, SIZE_Y=24), (1, 2)),
+        "three_rooms": (dict(name="three_rooms", SIZE_X=25, SIZE_Y=25), (1, 2)),
+        "four_rectangle": (dict(name="four_rectangle", SIZE_X=40, SIZE_Y=24), (1, 2)),
+        "central_room": (dict(name="central_room", SIZE_X=25, SIZE_Y=25), (1,)),
+        "central_room_destination": (dict(name="central_room_destination", SIZE_X=25, SIZE_Y=25), (1,)),
+        "central_room_large": (dict(name="central_room_large", SIZE_X=49, SIZE_Y=25), (1,)),
+        "central_room_large_destination": (dict(name="central_room_large_destination", SIZE_X=49, SIZE_Y=25), (1,)),
+        "two_central_rooms": (dict(name="two_central_rooms", SIZE_X=50, SIZE_Y=25), (1, 2)),
+    }
+    name = str(rng.choice(list(maps)))
+    m, types = maps[name]
+    environment = str(rng.choice(["default", "default", "shared_mean_reward", "shared_max_reward", "sequential", "junctional"]))
+    T = int(rng.choice(types))
+    if environment == "sequential":
+        T = int(rng.integers(1, 5)) if name.startswith("central_room") else T
+    if environment == "junctional":
+        if not name.startswith("central_room"):
+            environment = "default"
+        else:
+            T = 5
+    N = int(rng.integers(1, 11))
+    xy = [[2, 2], [-2, 2], [2, -2], [-2, -2], [0, 2], [0, -2], [2, 0], [-2, 0], [3, 3], [-3, -3]]
+    if name == "four_rooms" or name == "three_rooms" or name == "four_rectangle":
+        xy = [[4, 4], [-4, 4], [4, -4], [-4, -4], [6, 6], [-6, 6], [6, -6], [-6, -6], [4, 6], [-4, 6]]
+    tasks = []
+    for _ in range(N):
+        k = int(rng.integers(0, T + 1))
+        tasks.append("-1" if rng.random() < 0.1 else "".join(str(d) for d in rng.permutation(T)[:max(1, k)]))
+    mask = str(rng.choice(["local", "local", "relative", "merged"]))
+    noise = rng.choice([False, False, "flip", "sensing_dist", "threshold_sensing_dist"])
+    noise = False if (mask == "relative" or noise == "False") else (noise if noise is False else str(noise))
+    V = int(rng.choice([5, 7, 9]))
+    cfg = make_config(map=m, environment=environment, type_objects=T, num_agents=N, init_xys=xy[:N], agent_tasks=tasks,
+                      agent_view_method=str(rng.choice(["default", "simple", "individual", "transition", "individual_transition"])),
+                      object_view_method=str(rng.choice(["default", "simple", "object_types"])), past_step=int(rng.integers(1, 5)),
+                      observation_area_mask=mask, observation_noise=noise, visible_range=V,
+                      flip_noise_probabilities=[0.2, 0.1, 0.05, 0.02], std_distribution=[0.3, 0.2, 0.1, 0.05],
+                      noise_threshold_ratio=0.7, transparent_observation=bool(rng.random() < 0.2),
+                      keep_objects_num=bool(rng.random() < 0.7), num_objects=int(rng.integers(3, 40)),
+                      shuffle_init_xys=bool(rng.random() < 0.7), max_episode_length=int(rng.integers(6, 30)))
+    return cfg
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_configurations_match_oracle(seed):
+    """Randomised sweep over maps x environments x views x masks x noises x sizes: every output and the state stay
+    bit-identical to the C oracle across resets (gaussian noises are compared with taped draws)."""
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(50):
+        cfg = _random_config(rng)
+        E, first = int(rng.choice([1, 17, 70])), int(rng.integers(0, 1000))
+        try:
+            cuda = CudaBackend(cfg, E, first_global_env_id=first, auto_reset=True, extras=True)
+        except ValueError:
+            continue  # e.g. the object area cannot hold num_objects (the reference would spin forever)
+        break
+    else:
+        pytest.skip("no valid configuration drawn")
+    orc = Oracle(cfg, E, auto_reset=True, first_global_env_id=first, extras=True)
+    gaussian = cfg.observation_noise in ("sensing_dist", "threshold_sensing_dist")
+    shape = (E, cuda.env.N, cuda.env.C, cuda.env.V, cuda.env.V)
+    keys = ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates", "objects", "destination")
+    tape = rng.standard_normal(shape).astype(np.float32) if gaussian else None
+    _compare(cuda.reset(0, noise_tape=tape), orc.reset(0, noise_tape=tape), keys, f"seed {seed} reset {dict(cfg)}")
+    for tick in range(1, 26):
+        tape = rng.standard_normal(shape).astype(np.float32) if gaussian else None
+        _compare(cuda.step(tick, noise_tape=tape), orc.step(tick, noise_tape=tape, threads=4), keys, f"seed {seed} tick {tick}")
+        _compare(cuda.state(), orc.state(), ("pos", "objects", "counters", "steps", "destination"), f"seed {seed} state {tick}")
+    assert cuda.env.stats()["error_flag"] == 0
