@@ -1127,6 +1127,9 @@ struct maexp_learner {
     int H1, Hp, H2;                      // conv1 out side, pooled side, conv2 out side
     bool has_conv, dist, iqn, da3, da6 = false;
     bool use_tc = true;  // tensor-core GEMMs for large inference batches (MAEXP_TC=0 turns them off)
+    bool fused_trunk = true;       // one-kernel conv trunk for every local-view pass (MAEXP_FUSED_TRUNK=0: layer by layer)
+    const float *bwd_obs = nullptr;  // observations of the last training pass (conv1's im2col in trunk_backward)
+    bool fused_trunk_acts = false; // the last training pass kept p / arg only: trunk_backward builds col1 / col2 itself
     int last_q_batch = 0;
     int E_, heads_, Fm, L_, Tn;   // DA3 / DA6: embed_dim, num_heads, mlp hidden, block_loop, max tokens of any stack
     long long o_nfw, o_nfb, o_hw, o_hb, o_f1w = 0, o_f1b = 0;  // shared final norm, drl_head, DA6 fc1
@@ -1305,11 +1308,14 @@ void wgrad_close() {  // join the side streams back into the main stream
 // consecutive floats per (input channel, lane) so that one input channel costs two 128-bit loads; the pooled map is
 // stored channel-major so that a channel's cells are three 128-bit broadcast loads.  V is a template parameter: every
 // cell / tap index is a compile-time constant.  flat[b][oc*H2*W2 + pos] is PyTorch's flatten order (convolution.py:44-55).
-template <int V>
+// TRAIN (the learner's online(s) pass) also keeps what the backward pass reads: the pooled map p[b][cell][F1] (NHWC) and
+// the pooling argmax (bias added before the comparison, first maximum wins: F.max_pool2d on the biased conv output).
+template <int V, bool TRAIN>
 __global__ void __launch_bounds__(256) trunk_fused_fwd_kernel(const float *obs, const float *params, float *flat, int B, int C,
                                                               int F1, int F2, long long stride, long long gObs, long long P,
                                                               long long o_c1w, long long o_c1b, long long o_c2w,
-                                                              long long o_c2b, long long gFlat) {
+                                                              long long o_c2b, long long gFlat, float *p_out, uint8_t *arg_out,
+                                                              long long gP) {
     constexpr int H1 = V - 1, Hp = H1 / 2, H2 = Hp - 1, Q = H2 * H2, NC = Hp * Hp, PC = (NC + 3) / 4 * 4;
     extern __shared__ __align__(16) float sm[];
     const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1357,7 +1363,22 @@ __global__ void __launch_bounds__(256) trunk_fused_fwd_kernel(const float *obs, 
                 a10 = fmaf(o10, w0, a10); a10 = fmaf(o11, w1, a10); a10 = fmaf(o20, w2, a10); a10 = fmaf(o21, w3, a10);
                 a11 = fmaf(o11, w0, a11); a11 = fmaf(o12, w1, a11); a11 = fmaf(o21, w2, a11); a11 = fmaf(o22, w3, a11);
             }
-            s_p[lane * PC + cell] = fmaxf(fmaxf(a00, a01), fmaxf(a10, a11)) + b1[lane];  // max(x_i) + b == max(x_i + b)
+            if constexpr (TRAIN) {
+                const float bb = b1[lane];
+                float best = a00 + bb;
+                int bi = 0;
+                if (a01 + bb > best) { best = a01 + bb; bi = 1; }
+                if (a10 + bb > best) { best = a10 + bb; bi = 2; }
+                if (a11 + bb > best) { best = a11 + bb; bi = 3; }
+                s_p[lane * PC + cell] = best;
+                if (lane < F1) {
+                    const size_t pi = (size_t)g * gP + ((size_t)b * NC + cell) * F1 + lane;
+                    p_out[pi] = best;
+                    arg_out[pi] = (uint8_t)bi;
+                }
+            } else {
+                s_p[lane * PC + cell] = fmaxf(fmaxf(a00, a01), fmaxf(a10, a11)) + b1[lane];  // max(x_i) + b == max(x_i + b)
+            }
         }
         __syncwarp();
         // conv2, lane = output channel (two per lane when F2 > 32)
@@ -1399,17 +1420,25 @@ void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const
     const int G = h->G, C = h->C, V = h->V, F1 = h->F1, F2 = h->F2;
     const long long P = h->P, Bmax = h->B, stride = h->cfg.obs_stride;
     const int H1 = h->H1, Hp = h->Hp, H2 = h->H2;
-    if (inference && B >= 512 && F1 <= 32 && F2 <= 64 && (V == 5 || V == 7 || V == 9)) {  // nothing is kept for a backward pass
-        const int warps = 8, pc = (Hp * Hp + 3) / 4 * 4;
+    // one fused kernel for the whole trunk; the training pass (inference == false) also keeps p / arg, and trunk_backward
+    // builds the two im2col matrices its weight-gradient GEMMs read on their side streams (h->fused_trunk_acts)
+    h->fused_trunk_acts = false;
+    if (h->fused_trunk && F1 <= 32 && F2 <= 64 && (V == 5 || V == 7 || V == 9)) {
+        const int warps = B >= 512 ? 8 : 4, pc = (Hp * Hp + 3) / 4 * 4;
         const size_t smem = sizeof(float) * ((size_t)F1 * 256 + (size_t)C * 4 * 32 + 96 +
                                              (size_t)warps * (32 * pc + (C * V * V + 3) / 4 * 4));
         if (smem <= 200 * 1024) {
-            auto fn = V == 5 ? trunk_fused_fwd_kernel<5> : V == 7 ? trunk_fused_fwd_kernel<7> : trunk_fused_fwd_kernel<9>;
+            auto fn = inference ? (V == 5 ? trunk_fused_fwd_kernel<5, false> : V == 7 ? trunk_fused_fwd_kernel<7, false>
+                                                                                       : trunk_fused_fwd_kernel<9, false>)
+                                : (V == 5 ? trunk_fused_fwd_kernel<5, true> : V == 7 ? trunk_fused_fwd_kernel<7, true>
+                                                                                      : trunk_fused_fwd_kernel<9, true>);
             cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             int blocks = (B + warps - 1) / warps;
             if (blocks > 148 * 4) blocks = 148 * 4;
             fn<<<dim3(blocks, G), warps * 32, smem, st>>>(obs, params, a.flat, B, C, F1, F2, stride, (long long)B * stride, P,
-                                                         h->o_c1w, h->o_c1b, h->o_c2w, h->o_c2b, Bmax * h->D);
+                                                         h->o_c1w, h->o_c1b, h->o_c2w, h->o_c2b, Bmax * h->D, a.p, a.arg,
+                                                         Bmax * Hp * Hp * F1);
+            if (!inference) { h->fused_trunk_acts = true; h->bwd_obs = obs; }
             return;
         }
     }
@@ -1439,6 +1468,9 @@ void trunk_backward(maexp_learner *h, cudaStream_t st) {
     const int M2 = B * H2 * H2;
     {
         cudaStream_t ws = wgrad_begin(st);
+        if (h->fused_trunk_acts)  // the fused forward kept the pooled map only
+            im2col_kernel<<<grid1d((long long)B * H2 * H2 * F1 * 4, G), 256, 0, ws>>>(
+                a.p, a.col2, B, F1, H2, H2, (long long)Hp * Hp * F1, 1, (long long)Hp * F1, F1, gp, gcol2);
         gemm(ws, G, h->d_y2, a.col2, h->grads + h->o_c2w, nullptr, F2, F1 * 4, M2, 1, F2, F1 * 4, 1, F1 * 4, 1, gy2, gcol2, P, 0);
         colsum(ws, G, h->ones, h->d_y2, h->grads + h->o_c2b, M2, F2, gy2, P);
         wgrad_end();
@@ -1450,6 +1482,10 @@ void trunk_backward(maexp_learner *h, cudaStream_t st) {
     const int M1 = B * H1 * H1;
     {   // the two conv1 reductions over B*H1*H1 rows run side by side
         cudaStream_t ws = wgrad_begin(st);
+        if (h->fused_trunk_acts)
+            im2col_kernel<<<grid1d((long long)B * H1 * H1 * C * 4, G), 256, 0, ws>>>(
+                h->bwd_obs, a.col1, B, C, H1, H1, h->cfg.obs_stride, (long long)h->V * h->V, h->V, 1,
+                (long long)B * h->cfg.obs_stride, gcol1);
         gemm(ws, G, h->d_y1, a.col1, h->grads + h->o_c1w, nullptr, F1, C * 4, M1, 1, F1, C * 4, 1, C * 4, 1, gy1, gcol1, P, 0);
         wgrad_end();
         ws = wgrad_begin(st);
@@ -1888,7 +1924,7 @@ int iqn_forward(maexp_learner *h, cudaStream_t st, const float *params, const fl
         cudaMemcpy2DAsync(q.psi + Dr, sizeof(float) * D, h->lse_out[pass], sizeof(float) * Dl, sizeof(float) * Dl, (size_t)G * Bmax,
                           cudaMemcpyDeviceToDevice, st);
     } else {
-        trunk_forward(h, st, params, obs, B, a, /*inference=*/pass == 1);  // pass 1 never feeds a backward pass
+        trunk_forward(h, st, params, obs, B, a, /*inference=*/pass != 0);  // only pass 0 feeds a backward pass
         const MlpIn se_in = {a.flat, D, Bmax * D, B, Bmax, D};
         mlp_forward(h, st, params, h->se, se_in, q.se_h, q.psi);  // state_embedder
     }
@@ -1967,6 +2003,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     maexp_learner *h = new maexp_learner();
     h->cfg = *cfg;
     if (const char *tc = getenv("MAEXP_TC")) h->use_tc = atoi(tc) != 0;
+    if (const char *ft = getenv("MAEXP_FUSED_TRUNK")) h->fused_trunk = atoi(ft) != 0;
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
     h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;
     const int trunk = cfg->kind == MAEXP_LEARNER_IQN ? cfg->iqn_trunk : 0;  // MAEXP_IQN_TRUNK_*
@@ -2489,10 +2526,10 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
     }
     {
         cudaStream_t s2 = fork_pass(h, st, 0, true);
-        forward(h, s2, h->target, next_obs, B, h->acts[2]);
+        forward(h, s2, h->target, next_obs, B, h->acts[2], /*inference=*/true);  // passes 1 and 2 never feed a backward pass
         if (h->dist) {  // double-DQN action selection by the online net
             cudaStream_t s1 = fork_pass(h, st, 1, false);
-            forward(h, s1, h->online, next_obs, B, h->acts[1]);
+            forward(h, s1, h->online, next_obs, B, h->acts[1], /*inference=*/true);
         }
         g_splitk_ws = h->splitk_ws;
         forward(h, st, h->online, obs, B, h->acts[0]);
