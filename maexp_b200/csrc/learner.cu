@@ -52,6 +52,7 @@ struct GemmArgs {
 };
 
 constexpr int kTile = 64, kBK = 16;
+constexpr int kTrunkBwdBlocks = 64;  // most blocks per agent of trunk_fused_bwd_kernel (= partial sums per gradient element)
 
 // Deterministic split-K: slice z of the K range accumulates into a dense partial tile
 // part[slice][g][M][N]; splitk_reduce_kernel then adds the slices in a fixed order and applies the
@@ -1127,8 +1128,10 @@ struct maexp_learner {
     int H1, Hp, H2;                      // conv1 out side, pooled side, conv2 out side
     bool has_conv, dist, iqn, da3, da6 = false;
     bool use_tc = true;  // tensor-core GEMMs for large inference batches (MAEXP_TC=0 turns them off)
+    bool fused_mlp = true;         // one-kernel MLP heads for the update batches (MAEXP_FUSED_MLP=0: GEMM by GEMM)
     bool fused_trunk = true;       // one-kernel conv trunk for every local-view pass (MAEXP_FUSED_TRUNK=0: layer by layer)
     const float *bwd_obs = nullptr;  // observations of the last training pass (conv1's im2col in trunk_backward)
+    float *trunk_part = nullptr;      // block partials of trunk_fused_bwd_kernel
     bool fused_trunk_acts = false; // the last training pass kept p / arg only: trunk_backward builds col1 / col2 itself
     int last_q_batch = 0;
     int E_, heads_, Fm, L_, Tn;   // DA3 / DA6: embed_dim, num_heads, mlp hidden, block_loop, max tokens of any stack
@@ -1414,6 +1417,253 @@ __global__ void __launch_bounds__(256) trunk_fused_fwd_kernel(const float *obs, 
     }
 }
 
+// Backward of the conv trunk below conv2's output, for the activations the fused forward kept.  One warp per sample,
+// lane = conv1 channel (= conv2 input channel): d_p = conv2^T(d_flat) with the agent's conv2 weights in shared memory,
+// routed through the pooling argmax straight into conv1's weight / bias gradient (the pooled gradient is one non-zero per
+// 2x2 window, so conv1's [B*H1*H1, F1] gradient matrix and the 9 216-row reduction over it never exist), plus conv2's bias
+// gradient.  Sums run in a fixed order: samples per warp, warps per block in shared memory, blocks in
+// trunk_bwd_reduce_kernel — deterministic.  part[g][block][K1*32 + 32 + 64].
+template <int V>
+__global__ void __launch_bounds__(256) trunk_fused_bwd_kernel(const float *d_flat, const float *obs, const float *params,
+                                                              const uint8_t *arg, float *part, int B, int C, int F1, int F2,
+                                                              long long stride, long long gObs, long long P, long long o_c2w,
+                                                              long long gFlat, long long gP) {
+    constexpr int H1 = V - 1, Hp = H1 / 2, H2 = Hp - 1, Q = H2 * H2, NC = Hp * Hp;
+    extern __shared__ __align__(16) float sm[];
+    const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int K1 = C * 4, CVV = C * V * V, D = F2 * Q, Dp = (D + 3) / 4 * 4, CVVp = (CVV + 3) / 4 * 4;
+    const int per_warp = Dp + CVVp + K1 * 32 + 96;
+    float *w2s = sm;                                // [F2][32][4]: taps of (oc, ic = lane)
+    float *s_d = w2s + F2 * 128 + warp * per_warp;  // this sample's d_flat row
+    float *s_obs = s_d + Dp;
+    float *gw = s_obs + CVVp;                       // [K1][32] conv1 weight gradient of this warp's samples, then [32] + [64] biases
+    const float *W = params + (size_t)g * P;
+    for (int i = threadIdx.x; i < F2 * 128; i += blockDim.x) {
+        const int oc = i >> 7, ic = (i >> 2) & 31, tap = i & 3;
+        w2s[i] = ic < F1 ? W[o_c2w + ((size_t)oc * F1 + ic) * 4 + tap] : 0.0f;
+    }
+    for (int i = lane; i < K1 * 32 + 96; i += 32) gw[i] = 0.0f;
+    __syncthreads();
+    float gb1 = 0.0f, gb2a = 0.0f, gb2b = 0.0f;
+    for (int b = blockIdx.x * nwarps + warp; b < B; b += gridDim.x * nwarps) {
+        const float *dsrc = d_flat + (size_t)g * gFlat + (size_t)b * D;
+        const float *osrc = obs + (size_t)g * gObs + (size_t)b * stride;
+        for (int i = lane; i < D; i += 32) s_d[i] = dsrc[i];
+        for (int i = lane; i < CVV; i += 32) s_obs[i] = osrc[i];
+        __syncwarp();
+        float acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = 0.0f;
+        for (int oc = 0; oc < F2; ++oc) {
+            const float4 w4 = *reinterpret_cast<const float4 *>(w2s + (oc * 32 + lane) * 4);
+            const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int pos = 0; pos < Q; ++pos) {
+                const float dv = s_d[oc * Q + pos];
+#pragma unroll
+                for (int tap = 0; tap < 4; ++tap) {
+                    const int cell = (pos / H2 + (tap >> 1)) * Hp + pos % H2 + (tap & 1);
+                    acc[cell] = fmaf(dv, w[tap], acc[cell]);
+                }
+            }
+        }
+        // conv2 bias gradient: lanes are output channels here
+        if (lane < F2)
+            for (int pos = 0; pos < Q; ++pos) gb2a += s_d[lane * Q + pos];
+        if (lane + 32 < F2)
+            for (int pos = 0; pos < Q; ++pos) gb2b += s_d[(lane + 32) * Q + pos];
+        // pooling argmax -> the conv1 output position that received each pooled gradient
+        int off[NC];
+#pragma unroll
+        for (int cell = 0; cell < NC; ++cell) {
+            const int a = lane < F1 ? arg[(size_t)g * gP + ((size_t)b * NC + cell) * F1 + lane] : 0;
+            off[cell] = (2 * (cell / Hp) + (a >> 1)) * V + 2 * (cell % Hp) + (a & 1);
+            gb1 += acc[cell];
+        }
+        for (int k = 0; k < K1; ++k) {
+            const float *o = s_obs + (k >> 2) * V * V + ((k >> 1) & 1) * V + (k & 1);
+            float sum = 0.0f;
+#pragma unroll
+            for (int cell = 0; cell < NC; ++cell) sum = fmaf(acc[cell], o[off[cell]], sum);
+            gw[k * 32 + lane] += sum;
+        }
+        __syncwarp();
+    }
+    gw[K1 * 32 + lane] = gb1;
+    gw[K1 * 32 + 32 + lane] = gb2a;
+    gw[K1 * 32 + 64 + lane] = gb2b;
+    __syncthreads();
+    const int n = K1 * 32 + 96;
+    float *dst = part + ((size_t)g * gridDim.x + blockIdx.x) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float sum = 0.0f;
+        for (int w = 0; w < nwarps; ++w) sum += sm[F2 * 128 + w * per_warp + Dp + CVVp + i];
+        dst[i] = sum;
+    }
+}
+
+// block partials -> conv1 weight / bias and conv2 bias gradients (fixed order)
+__global__ void trunk_bwd_reduce_kernel(const float *part, float *grads, int nblk, int K1, int F1, int F2, long long P,
+                                        long long o_c1w, long long o_c1b, long long o_c2b) {
+    const int g = blockIdx.y, n = K1 * 32 + 96;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float sum = 0.0f;
+    for (int blk = 0; blk < nblk; ++blk) sum += part[((size_t)g * nblk + blk) * n + i];
+    float *G = grads + (size_t)g * P;
+    if (i < K1 * 32) {
+        const int k = i >> 5, f = i & 31;
+        if (f < F1) G[o_c1w + (size_t)f * K1 + k] = sum;
+    } else {
+        const int j = i - K1 * 32;
+        if (j < 32) { if (j < F1) G[o_c1b + j] = sum; }
+        else if (j - 32 < F2) G[o_c2b + j - 32] = sum;
+    }
+}
+
+// One-hidden-layer MLP head (mlp.py:28-34) in ONE kernel for up to two heads of every agent: a CTA owns 32 rows of one
+// (agent, head), computes hidden = relu(x W1^T + b1) (hidden <= 128 units) with the tile kept in shared memory as the A
+// operand of the second layer, and streams W1 / W2 (PyTorch [out][in] layout, K-major) through shared memory in 32-wide
+// K chunks with a register prefetch of the next chunk.  Replaces gemm + split-K reduce + gemm + split-K reduce per head
+// (four launches of ~10 us each at the update batch sizes); the sums run k = 0..K-1 in order (deterministic).
+struct MlpHeads {
+    long long w1[2], b1[2], w2[2], b2[2];
+    int out[2];
+    float *hbuf[2], *outp[2];
+    int vec_w1[2], vec_w2[2];  // 128-bit loads along K are legal for this head's weights
+};
+constexpr int kMlpTM = 32, kMlpTN = 128, kMlpBK = 32;
+
+__global__ void __launch_bounds__(256) mlp_fused_fwd_kernel(const float *x, long long x_row, long long x_g, int vec_x,
+                                                            const float *params, long long P, const MlpHeads hd, int rows,
+                                                            long long rows_max, int din, int H) {
+    constexpr int TM = kMlpTM, TN = kMlpTN, BK = kMlpBK;
+    __shared__ __align__(16) float As[BK][TM + 4];
+    __shared__ __align__(16) float Bs[BK][TN + 4];
+    __shared__ __align__(16) float Hs[TN][TM + 4];
+    const int g = blockIdx.z, head = blockIdx.y, m0 = blockIdx.x * TM;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const float *X = x + (size_t)g * x_g;
+    const float *Wg = params + (size_t)g * P;
+    const int am = tid >> 3, ak = (tid & 7) * 4;  // this thread's A element group: row am, k offset ak..ak+3
+    float4 ra, rb[4];
+    auto fetch_a = [&](int k0) {
+        const int m = m0 + am, k = k0 + ak;
+        ra = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (m < rows) {
+            const float *src = X + (size_t)m * x_row + k;
+            if (vec_x && k + 3 < din) ra = *reinterpret_cast<const float4 *>(src);
+            else {
+                if (k < din) ra.x = src[0];
+                if (k + 1 < din) ra.y = src[1];
+                if (k + 2 < din) ra.z = src[2];
+                if (k + 3 < din) ra.w = src[3];
+            }
+        }
+    };
+    auto fetch_b = [&](const float *W, int N, int K, int n0, int k0, int vec) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int idx = tid + r * 256, n = n0 + (idx >> 3), k = k0 + (idx & 7) * 4;
+            rb[r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (n < N) {
+                const float *src = W + (size_t)n * K + k;
+                if (vec && k + 3 < K) rb[r] = *reinterpret_cast<const float4 *>(src);
+                else {
+                    if (k < K) rb[r].x = src[0];
+                    if (k + 1 < K) rb[r].y = src[1];
+                    if (k + 2 < K) rb[r].z = src[2];
+                    if (k + 3 < K) rb[r].w = src[3];
+                }
+            }
+        }
+    };
+    auto store_a = [&]() { As[ak][am] = ra.x; As[ak + 1][am] = ra.y; As[ak + 2][am] = ra.z; As[ak + 3][am] = ra.w; };
+    auto store_b = [&]() {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int idx = tid + r * 256, n = idx >> 3, k = (idx & 7) * 4;
+            Bs[k][n] = rb[r].x; Bs[k + 1][n] = rb[r].y; Bs[k + 2][n] = rb[r].z; Bs[k + 3][n] = rb[r].w;
+        }
+    };
+    float acc[4][4];
+    auto clear = [&]() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    };
+    auto mma = [&](const float (*A)[TM + 4]) {
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&A[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+    };
+    // ---- layer 1: hidden[32][H] = relu(X W1^T + b1)
+    {
+        const float *W1 = Wg + hd.w1[head];
+        const int vec = hd.vec_w1[head];
+        clear();
+        fetch_a(0);
+        fetch_b(W1, H, din, 0, 0, vec);
+        for (int k0 = 0; k0 < din; k0 += BK) {
+            store_a();
+            store_b();
+            __syncthreads();
+            if (k0 + BK < din) { fetch_a(k0 + BK); fetch_b(W1, H, din, 0, k0 + BK, vec); }
+            mma(As);
+            __syncthreads();
+        }
+        const float *b1 = Wg + hd.b1[head];
+        float *hb = hd.hbuf[head] + (size_t)g * rows_max * H;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = tx * 4 + j;
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = n < H ? fmaxf(__fadd_rn(acc[i][j], b1[n]), 0.0f) : 0.0f;
+            *reinterpret_cast<float4 *>(&Hs[n][ty * 4]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        __syncthreads();
+        // hidden activations to HBM (the backward pass and its ReLU mask read them), coalesced along the hidden index
+        for (int i = tid; i < TM * TN; i += 256) {
+            const int m = i >> 7, n = i & (TN - 1);
+            if (m0 + m < rows && n < H) hb[(size_t)(m0 + m) * H + n] = Hs[n][m];
+        }
+    }
+    // ---- layer 2: out[32][O] = hidden W2^T + b2, 128 output columns at a time
+    const float *W2 = Wg + hd.w2[head], *b2 = Wg + hd.b2[head];
+    const int O = hd.out[head], vec2 = hd.vec_w2[head];
+    float *outp = hd.outp[head] + (size_t)g * rows_max * O;
+    for (int n0 = 0; n0 < O; n0 += TN) {
+        clear();
+        fetch_b(W2, O, H, n0, 0, vec2);
+        for (int k0 = 0; k0 < H; k0 += BK) {
+            store_b();
+            __syncthreads();
+            if (k0 + BK < H) fetch_b(W2, O, H, n0, k0 + BK, vec2);
+            mma(Hs + k0);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + ty * 4 + i;
+            if (m >= rows) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + tx * 4 + j;
+                if (n < O) outp[(size_t)m * O + n] = __fadd_rn(acc[i][j], b2[n]);
+            }
+        }
+    }
+}
+
 // ---- conv trunk: obs [G][B][obs_stride] -> a.flat [G][Bmax][D]
 void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, maexp_learner::Acts &a,
                    bool inference = false) {
@@ -1422,7 +1672,7 @@ void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const
     const int H1 = h->H1, Hp = h->Hp, H2 = h->H2;
     // one fused kernel for the whole trunk; the training pass (inference == false) also keeps p / arg, and trunk_backward
     // builds the two im2col matrices its weight-gradient GEMMs read on their side streams (h->fused_trunk_acts)
-    h->fused_trunk_acts = false;
+    if (!inference) h->fused_trunk_acts = false;
     if (h->fused_trunk && F1 <= 32 && F2 <= 64 && (V == 5 || V == 7 || V == 9)) {
         const int warps = B >= 512 ? 8 : 4, pc = (Hp * Hp + 3) / 4 * 4;
         const size_t smem = sizeof(float) * ((size_t)F1 * 256 + (size_t)C * 4 * 32 + 96 +
@@ -1464,8 +1714,32 @@ void trunk_backward(maexp_learner *h, cudaStream_t st) {
     const int H1 = h->H1, Hp = h->Hp, H2 = h->H2;
     const long long gcol1 = (long long)B * H1 * H1 * C * 4, gy1 = (long long)B * H1 * H1 * F1, gp = (long long)B * Hp * Hp * F1;
     const long long gcol2 = (long long)B * H2 * H2 * F1 * 4, gy2 = (long long)B * H2 * H2 * F2;
-    nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, st>>>(h->d_flat, h->d_y2, B, H2 * H2, F2, gy2, 1);
     const int M2 = B * H2 * H2;
+    if (h->fused_trunk_acts && h->trunk_part) {
+        const int V = h->V, warps = 8, K1 = C * 4, D = F2 * H2 * H2;
+        const size_t smem = sizeof(float) * ((size_t)F2 * 128 + (size_t)warps * ((D + 3) / 4 * 4 + (C * V * V + 3) / 4 * 4 + K1 * 32 + 96));
+        int nblk = (B + warps * 2 - 1) / (warps * 2);  // two samples per warp
+        if (nblk > kTrunkBwdBlocks) nblk = kTrunkBwdBlocks;
+        if (smem <= 200 * 1024) {
+            {   // conv2's weight gradient stays a GEMM, off the critical path
+                cudaStream_t ws = wgrad_begin(st);
+                nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, ws>>>(h->d_flat, h->d_y2, B, H2 * H2, F2, gy2, 1);
+                im2col_kernel<<<grid1d((long long)B * H2 * H2 * F1 * 4, G), 256, 0, ws>>>(
+                        a.p, a.col2, B, F1, H2, H2, (long long)Hp * Hp * F1, 1, (long long)Hp * F1, F1, gp, gcol2);
+                gemm(ws, G, h->d_y2, a.col2, h->grads + h->o_c2w, nullptr, F2, F1 * 4, M2, 1, F2, F1 * 4, 1, F1 * 4, 1, gy2, gcol2, P, 0);
+                wgrad_end();
+            }
+            auto fn = V == 5 ? trunk_fused_bwd_kernel<5> : V == 7 ? trunk_fused_bwd_kernel<7> : trunk_fused_bwd_kernel<9>;
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            fn<<<dim3(nblk, G), warps * 32, smem, st>>>(h->d_flat, h->bwd_obs, h->online, a.arg, h->trunk_part, B, C, F1, F2,
+                                                       h->cfg.obs_stride, (long long)B * h->cfg.obs_stride, P, h->o_c2w,
+                                                       (long long)B * D, gp);
+            trunk_bwd_reduce_kernel<<<dim3((K1 * 32 + 96 + 127) / 128, G), 128, 0, st>>>(h->trunk_part, h->grads, nblk, K1, F1, F2, P,
+                                                                                       h->o_c1w, h->o_c1b, h->o_c2b);
+            return;
+        }
+    }
+    nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, st>>>(h->d_flat, h->d_y2, B, H2 * H2, F2, gy2, 1);
     {
         cudaStream_t ws = wgrad_begin(st);
         if (h->fused_trunk_acts)  // the fused forward kept the pooled map only
@@ -1503,10 +1777,32 @@ struct MlpIn {
     int din;
 };
 
+// all heads of a network that share the input (fc_V / fc_A of the distributional nets) in one fused launch
+bool mlp_fused_forward(maexp_learner *h, cudaStream_t st, const float *params, const HeadLayout *hds, int nheads, const MlpIn &in,
+                       float *const *hbufs, float *const *outs) {
+    const int H = h->H;
+    // large acting batches keep the tensor-core path; the fused kernel serves the update batches and small inference calls
+    if (!h->fused_mlp || nheads < 1 || nheads > 2 || H > kMlpTN || (g_inference_tc && in.rows >= 512)) return false;
+    auto aligned16 = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+    const long long P = h->P;
+    MlpHeads a;
+    for (int k = 0; k < nheads; ++k) {
+        a.w1[k] = hds[k].w1; a.b1[k] = hds[k].b1; a.w2[k] = hds[k].w2; a.b2[k] = hds[k].b2;
+        a.out[k] = hds[k].out; a.hbuf[k] = hbufs[k]; a.outp[k] = outs[k];
+        a.vec_w1[k] = (in.din & 3) == 0 && (P & 3) == 0 && aligned16(params + hds[k].w1);
+        a.vec_w2[k] = (H & 3) == 0 && (P & 3) == 0 && aligned16(params + hds[k].w2);
+    }
+    const int vec_x = (in.x_row & 3) == 0 && (in.x_g & 3) == 0 && aligned16(in.x);
+    dim3 grid((in.rows + kMlpTM - 1) / kMlpTM, nheads, h->G);
+    mlp_fused_fwd_kernel<<<grid, 256, 0, st>>>(in.x, in.x_row, in.x_g, vec_x, params, P, a, in.rows, in.rows_max, in.din, H);
+    return true;
+}
+
 void mlp_forward(maexp_learner *h, cudaStream_t st, const float *params, const HeadLayout &hd, const MlpIn &in, float *hbuf,
                  float *out) {
     const int G = h->G, H = h->H;
     const long long P = h->P;
+    if (mlp_fused_forward(h, st, params, &hd, 1, in, &hbuf, &out)) return;
     gemm(st, G, in.x, params + hd.w1, hbuf, params + hd.b1, in.rows, H, in.din, in.x_row, 1, 1, in.din, H, 1, in.x_g, P,
          in.rows_max * H, P, /*relu=*/1);
     gemm(st, G, hbuf, params + hd.w2, out, params + hd.b2, in.rows, hd.out, H, H, 1, 1, H, hd.out, 1, in.rows_max * H, P,
@@ -1546,6 +1842,7 @@ void forward(maexp_learner *h, cudaStream_t st, const float *params, const float
     } else {
         in = {obs, h->cfg.obs_stride, (long long)B * h->cfg.obs_stride, B, h->B, h->D};
     }
+    if (h->heads.size() == 2 && mlp_fused_forward(h, st, params, h->heads.data(), 2, in, a.h, a.out)) return;
     for (size_t k = 0; k < h->heads.size(); ++k) mlp_forward(h, st, params, h->heads[k], in, a.h[k], a.out[k]);
 }
 
@@ -2004,6 +2301,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     h->cfg = *cfg;
     if (const char *tc = getenv("MAEXP_TC")) h->use_tc = atoi(tc) != 0;
     if (const char *ft = getenv("MAEXP_FUSED_TRUNK")) h->fused_trunk = atoi(ft) != 0;
+    if (const char *fm = getenv("MAEXP_FUSED_MLP")) h->fused_mlp = atoi(fm) != 0;
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
     h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;
     const int trunk = cfg->kind == MAEXP_LEARNER_IQN ? cfg->iqn_trunk : 0;  // MAEXP_IQN_TRUNK_*
@@ -2311,6 +2609,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         rc |= lalloc(h, &h->d_flat, G * B * h->D);
         rc |= lalloc(h, &h->d_y2, G * B * h->D);
         rc |= lalloc(h, &h->d_col2, G * B * h->H2 * h->H2 * h->F1 * 4);
+        rc |= lalloc(h, &h->trunk_part, (size_t)G * kTrunkBwdBlocks * (h->C * 4 * 32 + 96));
         rc |= lalloc(h, &h->d_p, G * B * h->Hp * h->Hp * h->F1);
         rc |= lalloc(h, &h->d_y1, G * B * h->H1 * h->H1 * h->F1);
     }
@@ -2525,14 +2824,16 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         return 0;
     }
     {
-        cudaStream_t s2 = fork_pass(h, st, 0, true);
+        // the training pass is the longest chain: it is issued first (its nodes come first in a captured graph), the side
+        // passes fork from the point before it
+        cudaEventRecord(h->ev_fork, st);
+        forward(h, st, h->online, obs, B, h->acts[0]);
+        cudaStream_t s2 = fork_pass(h, st, 0, false);
         forward(h, s2, h->target, next_obs, B, h->acts[2], /*inference=*/true);  // passes 1 and 2 never feed a backward pass
         if (h->dist) {  // double-DQN action selection by the online net
             cudaStream_t s1 = fork_pass(h, st, 1, false);
             forward(h, s1, h->online, next_obs, B, h->acts[1], /*inference=*/true);
         }
-        g_splitk_ws = h->splitk_ws;
-        forward(h, st, h->online, obs, B, h->acts[0]);
         join_pass(h, st, 0);
         if (h->dist) join_pass(h, st, 1);
     }
@@ -2584,12 +2885,12 @@ int maexp_learner_grads_iqn(maexp_learner *h, const float *obs, const float *nex
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int G = h->G, B = h->B;
     g_splitk_ws = h->splitk_ws;
-    cudaStream_t s1 = fork_pass(h, st, 0, true);
+    cudaEventRecord(h->ev_fork, st);  // training pass first (see maexp_learner_grads)
+    if (iqn_forward(h, st, h->online, obs, h->pos, B, taus, h->Nq, 1, 0)) return -1;
+    cudaStream_t s1 = fork_pass(h, st, 0, false);
     if (iqn_forward(h, s1, h->online, next_obs, h->next_pos, B, tau_sel, h->Nq, 0, 1)) return -1;
     cudaStream_t s2 = fork_pass(h, st, 1, false);
     if (iqn_forward(h, s2, h->target, next_obs, h->next_pos, B, tau_dashes, h->Nd, 1, 2)) return -1;
-    g_splitk_ws = h->splitk_ws;
-    if (iqn_forward(h, st, h->online, obs, h->pos, B, taus, h->Nq, 1, 0)) return -1;
     join_pass(h, st, 0);
     join_pass(h, st, 1);
     IqnArgs p;

@@ -367,3 +367,55 @@ def test_attention_agent_returns_reference_structures():
     assert isinstance(a, int) and float(placeholder[0].abs().sum()) == 0.0
     with pytest.raises(ValueError):
         generate_agents(cfg.merged_with(agent_type="nope"), [shape], [4])
+
+
+@pytest.mark.parametrize("kind,V,C,B", [("c51", 7, 3, 256), ("c51", 5, 3, 37), ("qr", 9, 4, 64), ("dqn_conv_mlp", 7, 11, 32),
+                                        ("iqn", 7, 3, 50), ("dqn_conv_mlp", 9, 7, 300), ("c51", 7, 3, 1100)])
+def test_fused_trunk_matches_layer_by_layer_and_torch(kind, V, C, B, monkeypatch):
+    """The fused kernels of the update (conv trunk forward keeping pooled map + argmax, its backward through conv2 / pooling
+    into conv1's gradients, one-kernel MLP heads) and the layer-by-layer path (MAEXP_FUSED_TRUNK=0, MAEXP_FUSED_MLP=0), both
+    against torch autograd: loss and every gradient."""
+    from maexp_b200.core.agents.brains import LearnerGroup
+    cfg, _ = golden_configs()[kind]
+    G = 2
+    cfg = cfg.merged_with(batch_size=B, visible_range=V)
+    torch.manual_seed(1000 + B)  # the networks' default initialisation: fixed, so that a run is reproducible (a sample whose
+    gen = torch.Generator().manual_seed(5)  # TD error or greedy action sits within rounding of a kink would differ from CPU torch)
+    obs = (torch.rand((G, B, C, V, V), generator=gen) < 0.25).float()
+    nxt = (torch.rand((G, B, C, V, V), generator=gen) < 0.25).float()
+    obs[:, :, -1] -= 1
+    nxt[:, :, -1] -= 1
+    groups = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("MAEXP_FUSED_TRUNK", fused)
+        monkeypatch.setenv("MAEXP_FUSED_MLP", fused)
+        groups.append(LearnerGroup(cfg, [C, V, V], 4, G, B))
+    g, ref = groups
+    for a in range(G):
+        ref.load_state_dict(a, g.state_dict(a))
+        ref.load_state_dict(a, g.state_dict(a, which=1), which=1)
+    batch = {"obs": pack(g, obs), "next_obs": pack(g, nxt),
+             "actions": torch.randint(0, 4, (G, B), generator=gen).to(torch.int32).cuda(),
+             "rewards": torch.randint(-1, 2, (G, B), generator=gen).float().cuda(),
+             "dones": (torch.rand((G, B), generator=gen) < 0.1).to(torch.uint8).cuda()}
+    taus = None
+    if kind == "iqn":
+        taus = (torch.rand((G, B, 4), generator=gen), torch.rand((G, B, 4), generator=gen), torch.rand((G, 4), generator=gen))
+        batch.update(taus=taus[0].cuda(), tau_dashes=taus[1].cuda(), tau_sel=taus[2].cuda())
+    loss, loss_ref = g.grads(batch).cpu(), ref.grads(batch).cpu()
+    grads, grads_ref = g.params(2).cpu(), ref.params(2).cpu()
+    assert float((loss - loss_ref).abs().max()) <= 1e-5 * float(loss_ref.abs().max())
+    for a in range(G):
+        o = TorchLearner(kind, g.state_dict(a), 4, float(cfg.gamma), 1e-3, 0.99, 1e-8, num_atoms=ATOMS[kind])
+        o.target = {k: v.clone() for k, v in g.state_dict(a, which=1).items()}
+        if kind == "iqn":
+            o.taus = (taus[0][a], taus[1][a], taus[2][a:a + 1])
+        o.opt.zero_grad()
+        want = o.loss(obs[a], nxt[a], batch["actions"][a].cpu().long(), batch["rewards"][a].cpu().double(), batch["dones"][a].cpu().bool())
+        want.backward()
+        assert abs(float(loss[a]) - float(want.detach())) <= 2e-5 * abs(float(want.detach()))
+        for name, off, cnt in g.table:
+            refg = o.sd[name].grad.reshape(-1)
+            e_fused = float((grads[a, off:off + cnt] - refg).norm()) / (float(refg.norm()) + 1e-12)
+            e_layer = float((grads_ref[a, off:off + cnt] - refg).norm()) / (float(refg.norm()) + 1e-12)
+            assert e_fused <= 1e-4 and e_layer <= 1e-4, (a, name, e_fused, e_layer)
