@@ -1664,6 +1664,149 @@ __global__ void __launch_bounds__(256) mlp_fused_fwd_kernel(const float *x, long
     }
 }
 
+// Data-gradient chain of the MLP heads in ONE kernel: for every head, dh = (dout W2) * [h > 0] (kept in shared memory as the
+// A operand of the next product and written out for the weight-gradient GEMMs), then dx (+)= dh W1, summed over the heads
+// in registers.  A CTA owns 32 rows and one 128-column tile of dx (blockIdx.y); both weight matrices are read in their
+// PyTorch layout, which is already [k][n] for these two products.  Replaces 2 GEMMs + 2 split-K reductions per head on the
+// critical path of the backward pass.  dx == nullptr: only dh (plain MLP on the observation).
+struct MlpBwdHeads {
+    long long w1[2], w2[2];
+    int out[2];
+    const float *dout[2], *hbuf[2];
+    float *dh[2];
+};
+
+__global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params, long long P, const MlpBwdHeads hd, int nheads,
+                                                            int rows, long long rows_max, int din, int H, float *dx,
+                                                            int vec_w1) {
+    constexpr int TM = kMlpTM, TN = kMlpTN, BK = kMlpBK;
+    __shared__ __align__(16) float As[BK][TM + 4];
+    __shared__ __align__(16) float Bs[BK][TN + 4];
+    __shared__ __align__(16) float Hs[TN][TM + 4];
+    const int g = blockIdx.z, m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const float *Wg = params + (size_t)g * P;
+    const int am = tid >> 3, ak = (tid & 7) * 4;
+    float4 ra, rb[4];
+    auto fetch_a = [&](const float *A, int K, int k0) {  // A[m][k], K-major rows (dout), scalar loads: K = 51 / 204 / 4 ...
+        const int m = m0 + am, k = k0 + ak;
+        ra = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (m < rows) {
+            const float *src = A + (size_t)m * K + k;
+            if (k < K) ra.x = src[0];
+            if (k + 1 < K) ra.y = src[1];
+            if (k + 2 < K) ra.z = src[2];
+            if (k + 3 < K) ra.w = src[3];
+        }
+    };
+    auto fetch_b = [&](const float *W, int K, int N, int k0, int nbase, int vec) {  // W[k][n] row-major
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int idx = tid + r * 256, k = k0 + (idx >> 5), n = nbase + (idx & 31) * 4;
+            rb[r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (k < K) {
+                const float *src = W + (size_t)k * N + n;
+                if (vec && n + 3 < N) rb[r] = *reinterpret_cast<const float4 *>(src);
+                else {
+                    if (n < N) rb[r].x = src[0];
+                    if (n + 1 < N) rb[r].y = src[1];
+                    if (n + 2 < N) rb[r].z = src[2];
+                    if (n + 3 < N) rb[r].w = src[3];
+                }
+            }
+        }
+    };
+    auto store_a = [&]() { As[ak][am] = ra.x; As[ak + 1][am] = ra.y; As[ak + 2][am] = ra.z; As[ak + 3][am] = ra.w; };
+    auto store_b = [&]() {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int idx = tid + r * 256;
+            *reinterpret_cast<float4 *>(&Bs[idx >> 5][(idx & 31) * 4]) = rb[r];
+        }
+    };
+    float acc[4][4], accx[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) accx[i][j] = 0.0f;
+    auto mma = [&](const float (*A)[TM + 4], float (&c)[4][4]) {
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&A[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[i][j] = fmaf(av[i], bv[j], c[i][j]);
+        }
+    };
+    const int vec_h = (H & 3) == 0;  // W2 rows are H floats: 16-byte aligned when the tensor is (checked by the host for W1 only)
+    for (int head = 0; head < nheads; ++head) {
+        const int O = head == 0 ? hd.out[0] : hd.out[1];
+        const float *dout = (head == 0 ? hd.dout[0] : hd.dout[1]) + (size_t)g * rows_max * O;
+        const float *hb = (head == 0 ? hd.hbuf[0] : hd.hbuf[1]) + (size_t)g * rows_max * H;
+        float *dh = (head == 0 ? hd.dh[0] : hd.dh[1]) + (size_t)g * rows_max * H;
+        const float *W2 = Wg + (head == 0 ? hd.w2[0] : hd.w2[1]);
+        const float *W1 = Wg + (head == 0 ? hd.w1[0] : hd.w1[1]);
+        const int vec2 = vec_h && ((reinterpret_cast<uintptr_t>(W2) & 15) == 0);
+        // ---- dh[32][H] = dout[32][O] W2[O][H], masked by the forward ReLU
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+        fetch_a(dout, O, 0);
+        fetch_b(W2, O, H, 0, 0, vec2);
+        for (int k0 = 0; k0 < O; k0 += BK) {
+            store_a();
+            store_b();
+            __syncthreads();
+            if (k0 + BK < O) { fetch_a(dout, O, k0 + BK); fetch_b(W2, O, H, k0 + BK, 0, vec2); }
+            mma(As, acc);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = tx * 4 + j;
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = m0 + ty * 4 + i;
+                v[i] = (n < H && m < rows && hb[(size_t)m * H + n] > 0.0f) ? acc[i][j] : 0.0f;
+            }
+            *reinterpret_cast<float4 *>(&Hs[n][ty * 4]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        __syncthreads();
+        if (blockIdx.y == 0)
+            for (int i = tid; i < TM * TN; i += 256) {
+                const int m = i >> 7, n = i & (TN - 1);
+                if (m0 + m < rows && n < H) dh[(size_t)(m0 + m) * H + n] = Hs[n][m];
+            }
+        if (!dx) { __syncthreads(); continue; }
+        // ---- dx tile += dh[32][H] W1[H][din]
+        fetch_b(W1, H, din, 0, n0, vec_w1);
+        for (int k0 = 0; k0 < H; k0 += BK) {
+            store_b();
+            __syncthreads();
+            if (k0 + BK < H) fetch_b(W1, H, din, k0 + BK, n0, vec_w1);
+            mma(Hs + k0, accx);
+            __syncthreads();
+        }
+    }
+    if (!dx) return;
+    float *dst = dx + (size_t)g * rows_max * din;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= rows) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < din) dst[(size_t)m * din + n] = accx[i][j];
+        }
+    }
+}
+
 // ---- conv trunk: obs [G][B][obs_stride] -> a.flat [G][Bmax][D]
 void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, maexp_learner::Acts &a,
                    bool inference = false) {
@@ -1674,7 +1817,7 @@ void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const
     // builds the two im2col matrices its weight-gradient GEMMs read on their side streams (h->fused_trunk_acts)
     if (!inference) h->fused_trunk_acts = false;
     if (h->fused_trunk && F1 <= 32 && F2 <= 64 && (V == 5 || V == 7 || V == 9)) {
-        const int warps = B >= 512 ? 8 : 4, pc = (Hp * Hp + 3) / 4 * 4;
+        const int warps = B >= 64 ? 8 : 4, pc = (Hp * Hp + 3) / 4 * 4;  // the 32 KB of conv2 weights are staged once per CTA
         const size_t smem = sizeof(float) * ((size_t)F1 * 256 + (size_t)C * 4 * 32 + 96 +
                                              (size_t)warps * (32 * pc + (C * V * V + 3) / 4 * 4));
         if (smem <= 200 * 1024) {
@@ -1854,9 +1997,40 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
     if (h->has_conv) in = {a.flat, h->D, (long long)B * h->D, B, B, h->D};
     else in = {obs, h->cfg.obs_stride, (long long)B * h->cfg.obs_stride, B, B, h->D};
     wgrad_open(h, st);
-    for (size_t k = 0; k < h->heads.size(); ++k)
-        mlp_backward(h, st, h->heads[k], in, h->d_out[k], a.h[k], k & 1 ? h->d_h2 : h->d_h, h->has_conv ? h->d_flat : nullptr,
-                     k > 0);
+    const int nheads = (int)h->heads.size(), H = h->H, G = h->G;
+    if (h->fused_mlp && nheads <= 2 && H <= kMlpTN) {
+        // weight gradients on the side streams around ONE kernel for the data-gradient chain of all heads
+        const long long P = h->P, gH = (long long)B * H;
+        MlpBwdHeads bh;
+        float *dhs[2] = {h->d_h, h->d_h2};
+        for (int k = 0; k < nheads; ++k) {
+            const HeadLayout &hd = h->heads[k];
+            const int O = hd.out;
+            bh.w1[k] = hd.w1; bh.w2[k] = hd.w2; bh.out[k] = O;
+            bh.dout[k] = h->d_out[k]; bh.hbuf[k] = h->acts[0].h[k]; bh.dh[k] = dhs[k];
+            cudaStream_t ws = wgrad_begin(st);
+            gemm(ws, G, h->d_out[k], bh.hbuf[k], h->grads + hd.w2, nullptr, O, H, B, 1, O, H, 1, H, 1, (long long)B * O, gH, P, 0);
+            colsum(ws, G, h->ones, h->d_out[k], h->grads + hd.b2, B, O, (long long)B * O, P);
+            wgrad_end();
+        }
+        auto aligned16 = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+        const int vec_w1 = (in.din & 3) == 0 && (P & 3) == 0 && aligned16(h->online + h->heads[0].w1) &&
+                           (nheads < 2 || aligned16(h->online + h->heads[1].w1));
+        float *dx = h->has_conv ? h->d_flat : nullptr;
+        dim3 grid((B + kMlpTM - 1) / kMlpTM, dx ? (in.din + kMlpTN - 1) / kMlpTN : 1, G);
+        mlp_fused_bwd_kernel<<<grid, 256, 0, st>>>(h->online, P, bh, nheads, B, B, in.din, H, dx, vec_w1);
+        for (int k = 0; k < nheads; ++k) {
+            const HeadLayout &hd = h->heads[k];
+            cudaStream_t ws = wgrad_begin(st);
+            gemm(ws, G, dhs[k], in.x, h->grads + hd.w1, nullptr, H, in.din, B, 1, H, in.x_row, 1, in.din, 1, gH, in.x_g, P, 0);
+            colsum(ws, G, h->ones, dhs[k], h->grads + hd.b1, B, H, gH, P);
+            wgrad_end();
+        }
+    } else {
+        for (size_t k = 0; k < h->heads.size(); ++k)
+            mlp_backward(h, st, h->heads[k], in, h->d_out[k], a.h[k], k & 1 ? h->d_h2 : h->d_h, h->has_conv ? h->d_flat : nullptr,
+                         k > 0);
+    }
     if (h->has_conv) trunk_backward(h, st);
     wgrad_close();
 }
