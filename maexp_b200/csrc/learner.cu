@@ -52,6 +52,7 @@ struct GemmArgs {
 };
 
 constexpr int kTile = 64, kBK = 16;
+constexpr int kSides = 4;  // side streams: forward passes 1 and 2 use the first two, weight gradients rotate over all
 constexpr int kTrunkBwdBlocks = 64;  // most blocks per agent of trunk_fused_bwd_kernel (= partial sums per gradient element)
 
 // Deterministic split-K: slice z of the K range accumulates into a dense partial tile
@@ -1132,6 +1133,8 @@ struct maexp_learner {
     bool fused_trunk = true;       // one-kernel conv trunk for every local-view pass (MAEXP_FUSED_TRUNK=0: layer by layer)
     const float *bwd_obs = nullptr;  // observations of the last training pass (conv1's im2col in trunk_backward)
     float *trunk_part = nullptr;      // block partials of trunk_fused_bwd_kernel
+    bool col2_ready = false, dy2_ready = false;  // backward(): conv2's im2col is in flight on a side stream (ev_col2) / the
+    cudaEvent_t ev_col2 = nullptr;               // fused MLP backward wrote d_y2 itself
     bool fused_trunk_acts = false; // the last training pass kept p / arg only: trunk_backward builds col1 / col2 itself
     int last_q_batch = 0;
     int E_, heads_, Fm, L_, Tn;   // DA3 / DA6: embed_dim, num_heads, mlp hidden, block_loop, max tokens of any stack
@@ -1150,9 +1153,9 @@ struct maexp_learner {
     float *support = nullptr, *ones = nullptr, *splitk_ws = nullptr;
     // the three forward passes of an update are independent: passes 1 and 2 run on side streams (fork / join with
     // events, which also works under stream capture) with their own split-K workspaces
-    float *splitk_side[2] = {nullptr, nullptr};
-    cudaStream_t side[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_w[2] = {nullptr, nullptr};
+    float *splitk_side[kSides] = {};
+    cudaStream_t side[kSides] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kSides] = {}, ev_w[kSides] = {};
     float *d_h2 = nullptr, *d_hrow2 = nullptr;  // second hidden-gradient buffers: weight-gradient GEMMs of head k read
                                                 // theirs on a side stream while head k+1's data gradients are computed
     // activations of the three passes (0: online(s) kept for backward, 1: online(s'), 2: target(s'))
@@ -1269,19 +1272,19 @@ void colsum(cudaStream_t st, int G, const float *ones, const float *X, float *ou
 }
 
 // Weight / bias gradients never feed the data-gradient chain, so inside a backward pass that opts in (g_wg.h set) they
-// are issued on the two side streams, alternating, each behind an event recorded on the main stream at that point.
+// are issued on the side streams, in rotation, each behind an event recorded on the main stream at that point.
 struct WGradCtx {
     maexp_learner *h = nullptr;
     cudaStream_t main_stream = nullptr;
     int next = 0;
-    bool used[2] = {false, false};
+    bool used[kSides] = {};
 } g_wg;
 
 cudaStream_t wgrad_begin(cudaStream_t st) {
     if (!g_wg.h) return st;
     maexp_learner *h = g_wg.h;
     const int k = g_wg.next;
-    g_wg.next ^= 1;
+    g_wg.next = (k + 1) % kSides;
     cudaEventRecord(h->ev_w[k], st);
     cudaStreamWaitEvent(h->side[k], h->ev_w[k], 0);
     g_splitk_ws = h->splitk_side[k];
@@ -1295,7 +1298,7 @@ void wgrad_open(maexp_learner *h, cudaStream_t st) { g_wg = WGradCtx(); g_wg.h =
 void wgrad_close() {  // join the side streams back into the main stream
     maexp_learner *h = g_wg.h;
     if (!h) return;
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < kSides; ++k)
         if (g_wg.used[k]) {
             cudaEventRecord(h->ev_join[k], h->side[k]);
             cudaStreamWaitEvent(g_wg.main_stream, h->ev_join[k], 0);
@@ -1678,7 +1681,7 @@ struct MlpBwdHeads {
 
 __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params, long long P, const MlpBwdHeads hd, int nheads,
                                                             int rows, long long rows_max, int din, int H, float *dx,
-                                                            int vec_w1) {
+                                                            int vec_w1, float *dx_nhwc, int Q) {
     constexpr int TM = kMlpTM, TN = kMlpTN, BK = kMlpBK;
     __shared__ __align__(16) float As[BK][TM + 4];
     __shared__ __align__(16) float Bs[BK][TN + 4];
@@ -1802,7 +1805,12 @@ __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params,
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            if (n < din) dst[(size_t)m * din + n] = accx[i][j];
+            if (n < din) {
+                dst[(size_t)m * din + n] = accx[i][j];
+                // the same gradient as conv2's NHWC output gradient [m][pos][oc] (flatten order is oc*Q + pos): what the
+                // conv2 weight-gradient GEMM reads
+                if (dx_nhwc) dx_nhwc[(size_t)g * rows_max * din + ((size_t)m * Q + n % Q) * (din / Q) + n / Q] = accx[i][j];
+            }
         }
     }
 }
@@ -1866,9 +1874,13 @@ void trunk_backward(maexp_learner *h, cudaStream_t st) {
         if (smem <= 200 * 1024) {
             {   // conv2's weight gradient stays a GEMM, off the critical path
                 cudaStream_t ws = wgrad_begin(st);
-                nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, ws>>>(h->d_flat, h->d_y2, B, H2 * H2, F2, gy2, 1);
-                im2col_kernel<<<grid1d((long long)B * H2 * H2 * F1 * 4, G), 256, 0, ws>>>(
+                if (!h->dy2_ready)  // else the fused MLP backward wrote d_y2 next to d_flat
+                    nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, ws>>>(h->d_flat, h->d_y2, B, H2 * H2, F2, gy2, 1);
+                if (h->col2_ready) cudaStreamWaitEvent(ws, h->ev_col2, 0);
+                else
+                    im2col_kernel<<<grid1d((long long)B * H2 * H2 * F1 * 4, G), 256, 0, ws>>>(
                         a.p, a.col2, B, F1, H2, H2, (long long)Hp * Hp * F1, 1, (long long)Hp * F1, F1, gp, gcol2);
+                h->col2_ready = h->dy2_ready = false;
                 gemm(ws, G, h->d_y2, a.col2, h->grads + h->o_c2w, nullptr, F2, F1 * 4, M2, 1, F2, F1 * 4, 1, F1 * 4, 1, gy2, gcol2, P, 0);
                 wgrad_end();
             }
@@ -1885,9 +1897,11 @@ void trunk_backward(maexp_learner *h, cudaStream_t st) {
     nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, st>>>(h->d_flat, h->d_y2, B, H2 * H2, F2, gy2, 1);
     {
         cudaStream_t ws = wgrad_begin(st);
-        if (h->fused_trunk_acts)  // the fused forward kept the pooled map only
+        if (h->col2_ready) cudaStreamWaitEvent(ws, h->ev_col2, 0);
+        else if (h->fused_trunk_acts)  // the fused forward kept the pooled map only
             im2col_kernel<<<grid1d((long long)B * H2 * H2 * F1 * 4, G), 256, 0, ws>>>(
                 a.p, a.col2, B, F1, H2, H2, (long long)Hp * Hp * F1, 1, (long long)Hp * F1, F1, gp, gcol2);
+        h->col2_ready = h->dy2_ready = false;
         gemm(ws, G, h->d_y2, a.col2, h->grads + h->o_c2w, nullptr, F2, F1 * 4, M2, 1, F2, F1 * 4, 1, F1 * 4, 1, gy2, gcol2, P, 0);
         colsum(ws, G, h->ones, h->d_y2, h->grads + h->o_c2b, M2, F2, gy2, P);
         wgrad_end();
@@ -2018,7 +2032,20 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
                            (nheads < 2 || aligned16(h->online + h->heads[1].w1));
         float *dx = h->has_conv ? h->d_flat : nullptr;
         dim3 grid((B + kMlpTM - 1) / kMlpTM, dx ? (in.din + kMlpTN - 1) / kMlpTN : 1, G);
-        mlp_fused_bwd_kernel<<<grid, 256, 0, st>>>(h->online, P, bh, nheads, B, B, in.din, H, dx, vec_w1);
+        const bool to_trunk = h->has_conv && h->fused_trunk_acts && h->trunk_part;
+        if (to_trunk) {  // conv2's im2col only needs the forward pass: issue it now, on a side stream
+            maexp_learner::Acts &a0 = h->acts[0];
+            const int Hp = h->Hp, H2 = h->H2, F1 = h->F1;
+            cudaStream_t ws = wgrad_begin(st);
+            im2col_kernel<<<grid1d((long long)B * H2 * H2 * F1 * 4, G), 256, 0, ws>>>(
+                a0.p, a0.col2, B, F1, H2, H2, (long long)Hp * Hp * F1, 1, (long long)Hp * F1, F1, (long long)B * Hp * Hp * F1,
+                (long long)B * H2 * H2 * F1 * 4);
+            cudaEventRecord(h->ev_col2, ws);
+            wgrad_end();
+            h->col2_ready = h->dy2_ready = true;
+        }
+        mlp_fused_bwd_kernel<<<grid, 256, 0, st>>>(h->online, P, bh, nheads, B, B, in.din, H, dx, vec_w1,
+                                                   to_trunk ? h->d_y2 : nullptr, h->H2 * h->H2);
         for (int k = 0; k < nheads; ++k) {
             const HeadLayout &hd = h->heads[k];
             cudaStream_t ws = wgrad_begin(st);
@@ -2688,13 +2715,14 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     rc |= lalloc(h, &h->support, 128);
     rc |= lalloc(h, &h->ones, 4);
     rc |= lalloc(h, &h->splitk_ws, (size_t)kSplitWorkspaceFloats);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kSides; ++k) {
         rc |= lalloc(h, &h->splitk_side[k], (size_t)kSplitWorkspaceFloats);
         rc |= cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking) != cudaSuccess;
         rc |= cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming) != cudaSuccess;
         rc |= cudaEventCreateWithFlags(&h->ev_w[k], cudaEventDisableTiming) != cudaSuccess;
     }
     rc |= cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess;
+    rc |= cudaEventCreateWithFlags(&h->ev_col2, cudaEventDisableTiming) != cudaSuccess;
     for (int k = 0; k < 3; ++k) {
         maexp_learner::Acts &a = h->acts[k];
         memset(&a, 0, sizeof(a));
@@ -2845,12 +2873,13 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
 
 void maexp_learner_destroy(maexp_learner *h) {
     if (!h) return;
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kSides; ++k) {
         if (h->side[k]) { cudaStreamSynchronize(h->side[k]); cudaStreamDestroy(h->side[k]); }
         if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
         if (h->ev_w[k]) cudaEventDestroy(h->ev_w[k]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_col2) cudaEventDestroy(h->ev_col2);
     for (void *d : h->allocs) cudaFree(d);
     delete h;
 }
