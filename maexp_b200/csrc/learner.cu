@@ -1129,6 +1129,7 @@ struct maexp_learner {
     int H1, Hp, H2;                      // conv1 out side, pooled side, conv2 out side
     bool has_conv, dist, iqn, da3, da6 = false;
     bool use_tc = true;  // tensor-core GEMMs for large inference batches (MAEXP_TC=0 turns them off)
+    bool batched_fwd = false;      // all forward passes of an update as slices of one launch (MAEXP_BATCHED_FWD=1; measured slower than one stream each: 263 vs 234 us)
     bool fused_mlp = true;         // one-kernel MLP heads for the update batches (MAEXP_FUSED_MLP=0: GEMM by GEMM)
     bool fused_trunk = true;       // one-kernel conv trunk for every local-view pass (MAEXP_FUSED_TRUNK=0: layer by layer)
     const float *bwd_obs = nullptr;  // observations of the last training pass (conv1's im2col in trunk_backward)
@@ -1316,14 +1317,24 @@ void wgrad_close() {  // join the side streams back into the main stream
 // cell / tap index is a compile-time constant.  flat[b][oc*H2*W2 + pos] is PyTorch's flatten order (convolution.py:44-55).
 // TRAIN (the learner's online(s) pass) also keeps what the backward pass reads: the pooled map p[b][cell][F1] (NHWC) and
 // the pooling argmax (bias added before the comparison, first maximum wins: F.max_pool2d on the biased conv output).
+// blockIdx.z selects one of up to three passes of an update (online(s), online(s'), target(s')), so that all of them are one
+// launch and share the SMs instead of queueing behind each other's shared-memory footprint.
+struct TrunkPasses {
+    const float *obs[3], *params[3];
+    float *flat[3];
+    int train[3];
+};
 template <int V, bool TRAIN>
-__global__ void __launch_bounds__(256) trunk_fused_fwd_kernel(const float *obs, const float *params, float *flat, int B, int C,
+__global__ void __launch_bounds__(256) trunk_fused_fwd_kernel(const __grid_constant__ TrunkPasses tp, int B, int C,
                                                               int F1, int F2, long long stride, long long gObs, long long P,
                                                               long long o_c1w, long long o_c1b, long long o_c2w,
                                                               long long o_c2b, long long gFlat, float *p_out, uint8_t *arg_out,
                                                               long long gP) {
     constexpr int H1 = V - 1, Hp = H1 / 2, H2 = Hp - 1, Q = H2 * H2, NC = Hp * Hp, PC = (NC + 3) / 4 * 4;
     extern __shared__ __align__(16) float sm[];
+    const float *obs = tp.obs[blockIdx.z], *params = tp.params[blockIdx.z];
+    float *flat = tp.flat[blockIdx.z];
+    const bool train = TRAIN && tp.train[blockIdx.z];
     const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int K1 = C * 4, CVV = C * V * V, D = F2 * Q;
     float *w2t = sm;                      // [F1][32][8]: (tap, half) of output channels lane / lane + 32
@@ -1369,7 +1380,7 @@ __global__ void __launch_bounds__(256) trunk_fused_fwd_kernel(const float *obs, 
                 a10 = fmaf(o10, w0, a10); a10 = fmaf(o11, w1, a10); a10 = fmaf(o20, w2, a10); a10 = fmaf(o21, w3, a10);
                 a11 = fmaf(o11, w0, a11); a11 = fmaf(o12, w1, a11); a11 = fmaf(o21, w2, a11); a11 = fmaf(o22, w3, a11);
             }
-            if constexpr (TRAIN) {
+            if (train) {
                 const float bb = b1[lane];
                 float best = a00 + bb;
                 int bi = 0;
@@ -1529,25 +1540,30 @@ __global__ void trunk_bwd_reduce_kernel(const float *part, float *grads, int nbl
 // operand of the second layer, and streams W1 / W2 (PyTorch [out][in] layout, K-major) through shared memory in 32-wide
 // K chunks with a register prefetch of the next chunk.  Replaces gemm + split-K reduce + gemm + split-K reduce per head
 // (four launches of ~10 us each at the update batch sizes); the sums run k = 0..K-1 in order (deterministic).
+// blockIdx.y = head + nheads * pass: up to three passes of an update (their own input, parameter set and outputs) share
+// one launch.
 struct MlpHeads {
     long long w1[2], b1[2], w2[2], b2[2];
-    int out[2];
-    float *hbuf[2], *outp[2];
+    int out[2], nheads;
     int vec_w1[2], vec_w2[2];  // 128-bit loads along K are legal for this head's weights
+    const float *x[3], *params[3];
+    float *hbuf[3][2], *outp[3][2];
+    int vec_x[3];
 };
-constexpr int kMlpTM = 32, kMlpTN = 128, kMlpBK = 32;
+constexpr int kMlpTM = 32, kMlpTN = 128, kMlpBK = 32, kMlpMaxIn = 1024;
 
-__global__ void __launch_bounds__(256) mlp_fused_fwd_kernel(const float *x, long long x_row, long long x_g, int vec_x,
-                                                            const float *params, long long P, const MlpHeads hd, int rows,
+__global__ void __launch_bounds__(256) mlp_fused_fwd_kernel(long long x_row, long long x_g, long long P,
+                                                            const __grid_constant__ MlpHeads hd, int rows,
                                                             long long rows_max, int din, int H) {
     constexpr int TM = kMlpTM, TN = kMlpTN, BK = kMlpBK;
     __shared__ __align__(16) float As[BK][TM + 4];
     __shared__ __align__(16) float Bs[BK][TN + 4];
     __shared__ __align__(16) float Hs[TN][TM + 4];
-    const int g = blockIdx.z, head = blockIdx.y, m0 = blockIdx.x * TM;
+    const int g = blockIdx.z, pass = blockIdx.y / hd.nheads, head = blockIdx.y - pass * hd.nheads, m0 = blockIdx.x * TM;
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-    const float *X = x + (size_t)g * x_g;
-    const float *Wg = params + (size_t)g * P;
+    const float *X = hd.x[pass] + (size_t)g * x_g;
+    const float *Wg = hd.params[pass] + (size_t)g * P;
+    const int vec_x = hd.vec_x[pass];
     const int am = tid >> 3, ak = (tid & 7) * 4;  // this thread's A element group: row am, k offset ak..ak+3
     float4 ra, rb[4];
     auto fetch_a = [&](int k0) {
@@ -1624,7 +1640,7 @@ __global__ void __launch_bounds__(256) mlp_fused_fwd_kernel(const float *x, long
             __syncthreads();
         }
         const float *b1 = Wg + hd.b1[head];
-        float *hb = hd.hbuf[head] + (size_t)g * rows_max * H;
+        float *hb = hd.hbuf[pass][head] + (size_t)g * rows_max * H;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = tx * 4 + j;
@@ -1643,7 +1659,7 @@ __global__ void __launch_bounds__(256) mlp_fused_fwd_kernel(const float *x, long
     // ---- layer 2: out[32][O] = hidden W2^T + b2, 128 output columns at a time
     const float *W2 = Wg + hd.w2[head], *b2 = Wg + hd.b2[head];
     const int O = hd.out[head], vec2 = hd.vec_w2[head];
-    float *outp = hd.outp[head] + (size_t)g * rows_max * O;
+    float *outp = hd.outp[pass][head] + (size_t)g * rows_max * O;
     for (int n0 = 0; n0 < O; n0 += TN) {
         clear();
         fetch_b(W2, O, H, n0, 0, vec2);
@@ -1815,6 +1831,36 @@ __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params,
     }
 }
 
+// the fused trunk for n <= 3 passes in one launch; at most one of them (train[k] != 0) keeps p / arg for the backward pass
+bool trunk_forward_multi(maexp_learner *h, cudaStream_t st, int n, const float *const *params, const float *const *obs,
+                         maexp_learner::Acts *const *acts, const int *train, int B) {
+    const int G = h->G, C = h->C, V = h->V, F1 = h->F1, F2 = h->F2, Hp = h->Hp;
+    const long long P = h->P, Bmax = h->B, stride = h->cfg.obs_stride;
+    if (!h->fused_trunk || F1 > 32 || F2 > 64 || !(V == 5 || V == 7 || V == 9) || n < 1 || n > 3) return false;
+    const int warps = B >= 64 ? 8 : 4, pc = (Hp * Hp + 3) / 4 * 4;  // the 32 KB of conv2 weights are staged once per CTA
+    const size_t smem = sizeof(float) * ((size_t)F1 * 256 + (size_t)C * 4 * 32 + 96 +
+                                         (size_t)warps * (32 * pc + (C * V * V + 3) / 4 * 4));
+    if (smem > 200 * 1024) return false;
+    TrunkPasses tp = {};
+    maexp_learner::Acts *kept = nullptr;
+    for (int k = 0; k < n; ++k) {
+        tp.obs[k] = obs[k]; tp.params[k] = params[k]; tp.flat[k] = acts[k]->flat; tp.train[k] = train[k];
+        if (train[k]) { kept = acts[k]; h->bwd_obs = obs[k]; }
+    }
+    auto fn = !kept ? (V == 5 ? trunk_fused_fwd_kernel<5, false> : V == 7 ? trunk_fused_fwd_kernel<7, false>
+                                                                          : trunk_fused_fwd_kernel<9, false>)
+                    : (V == 5 ? trunk_fused_fwd_kernel<5, true> : V == 7 ? trunk_fused_fwd_kernel<7, true>
+                                                                         : trunk_fused_fwd_kernel<9, true>);
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    int blocks = (B + warps - 1) / warps;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    fn<<<dim3(blocks, G, n), warps * 32, smem, st>>>(tp, B, C, F1, F2, stride, (long long)B * stride, P, h->o_c1w, h->o_c1b,
+                                                    h->o_c2w, h->o_c2b, Bmax * h->D, kept ? kept->p : nullptr,
+                                                    kept ? kept->arg : nullptr, Bmax * Hp * Hp * F1);
+    if (kept) h->fused_trunk_acts = true;
+    return true;
+}
+
 // ---- conv trunk: obs [G][B][obs_stride] -> a.flat [G][Bmax][D]
 void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, int B, maexp_learner::Acts &a,
                    bool inference = false) {
@@ -1824,24 +1870,11 @@ void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const
     // one fused kernel for the whole trunk; the training pass (inference == false) also keeps p / arg, and trunk_backward
     // builds the two im2col matrices its weight-gradient GEMMs read on their side streams (h->fused_trunk_acts)
     if (!inference) h->fused_trunk_acts = false;
-    if (h->fused_trunk && F1 <= 32 && F2 <= 64 && (V == 5 || V == 7 || V == 9)) {
-        const int warps = B >= 64 ? 8 : 4, pc = (Hp * Hp + 3) / 4 * 4;  // the 32 KB of conv2 weights are staged once per CTA
-        const size_t smem = sizeof(float) * ((size_t)F1 * 256 + (size_t)C * 4 * 32 + 96 +
-                                             (size_t)warps * (32 * pc + (C * V * V + 3) / 4 * 4));
-        if (smem <= 200 * 1024) {
-            auto fn = inference ? (V == 5 ? trunk_fused_fwd_kernel<5, false> : V == 7 ? trunk_fused_fwd_kernel<7, false>
-                                                                                       : trunk_fused_fwd_kernel<9, false>)
-                                : (V == 5 ? trunk_fused_fwd_kernel<5, true> : V == 7 ? trunk_fused_fwd_kernel<7, true>
-                                                                                      : trunk_fused_fwd_kernel<9, true>);
-            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            int blocks = (B + warps - 1) / warps;
-            if (blocks > 148 * 4) blocks = 148 * 4;
-            fn<<<dim3(blocks, G), warps * 32, smem, st>>>(obs, params, a.flat, B, C, F1, F2, stride, (long long)B * stride, P,
-                                                         h->o_c1w, h->o_c1b, h->o_c2w, h->o_c2b, Bmax * h->D, a.p, a.arg,
-                                                         Bmax * Hp * Hp * F1);
-            if (!inference) { h->fused_trunk_acts = true; h->bwd_obs = obs; }
-            return;
-        }
+    {
+        const float *ps[1] = {params}, *os[1] = {obs};
+        maexp_learner::Acts *as[1] = {&a};
+        const int tr[1] = {inference ? 0 : 1};
+        if (trunk_forward_multi(h, st, 1, ps, os, as, tr, B)) return;
     }
     const long long gcol1 = Bmax * H1 * H1 * C * 4, gy1 = Bmax * H1 * H1 * F1, gp = Bmax * Hp * Hp * F1;
     const long long gcol2 = Bmax * H2 * H2 * F1 * 4, gy2 = Bmax * H2 * H2 * F2;
@@ -1934,25 +1967,47 @@ struct MlpIn {
     int din;
 };
 
-// all heads of a network that share the input (fc_V / fc_A of the distributional nets) in one fused launch
-bool mlp_fused_forward(maexp_learner *h, cudaStream_t st, const float *params, const HeadLayout *hds, int nheads, const MlpIn &in,
-                       float *const *hbufs, float *const *outs) {
+// all heads of a network that share the input (fc_V / fc_A of the distributional nets), for n <= 3 passes with the same
+// shapes (their own input, parameters and outputs), in one fused launch
+bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const float *const *params, const HeadLayout *hds,
+                             int nheads, const MlpIn *ins, float *const (*hbufs)[2], float *const (*outs)[2]) {
     const int H = h->H;
+    const MlpIn &in = ins[0];
     // large acting batches keep the tensor-core path; the fused kernel serves the update batches and small inference calls
-    if (!h->fused_mlp || nheads < 1 || nheads > 2 || H > kMlpTN || (g_inference_tc && in.rows >= 512)) return false;
+    // and a wide input (the relative-canvas embedders: 7 744 .. 11 520 features on a few rows) needs the split-K GEMM's CTAs
+    if (!h->fused_mlp || nheads < 1 || nheads > 2 || n < 1 || n > 3 || H > kMlpTN || (g_inference_tc && in.rows >= 512) ||
+        in.din > kMlpMaxIn)
+        return false;
     auto aligned16 = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
     const long long P = h->P;
-    MlpHeads a;
+    MlpHeads a = {};
+    a.nheads = nheads;
     for (int k = 0; k < nheads; ++k) {
         a.w1[k] = hds[k].w1; a.b1[k] = hds[k].b1; a.w2[k] = hds[k].w2; a.b2[k] = hds[k].b2;
-        a.out[k] = hds[k].out; a.hbuf[k] = hbufs[k]; a.outp[k] = outs[k];
-        a.vec_w1[k] = (in.din & 3) == 0 && (P & 3) == 0 && aligned16(params + hds[k].w1);
-        a.vec_w2[k] = (H & 3) == 0 && (P & 3) == 0 && aligned16(params + hds[k].w2);
+        a.out[k] = hds[k].out;
+        a.vec_w1[k] = (in.din & 3) == 0 && (P & 3) == 0;
+        a.vec_w2[k] = (H & 3) == 0 && (P & 3) == 0;
+        for (int q = 0; q < n; ++q) {
+            a.vec_w1[k] = a.vec_w1[k] && aligned16(params[q] + hds[k].w1);
+            a.vec_w2[k] = a.vec_w2[k] && aligned16(params[q] + hds[k].w2);
+            a.hbuf[q][k] = hbufs[q][k]; a.outp[q][k] = outs[q][k];
+        }
     }
-    const int vec_x = (in.x_row & 3) == 0 && (in.x_g & 3) == 0 && aligned16(in.x);
-    dim3 grid((in.rows + kMlpTM - 1) / kMlpTM, nheads, h->G);
-    mlp_fused_fwd_kernel<<<grid, 256, 0, st>>>(in.x, in.x_row, in.x_g, vec_x, params, P, a, in.rows, in.rows_max, in.din, H);
+    for (int q = 0; q < n; ++q) {
+        a.x[q] = ins[q].x; a.params[q] = params[q];
+        a.vec_x[q] = (in.x_row & 3) == 0 && (in.x_g & 3) == 0 && aligned16(ins[q].x);
+    }
+    dim3 grid((in.rows + kMlpTM - 1) / kMlpTM, nheads * n, h->G);
+    mlp_fused_fwd_kernel<<<grid, 256, 0, st>>>(in.x_row, in.x_g, P, a, in.rows, in.rows_max, in.din, H);
     return true;
+}
+
+bool mlp_fused_forward(maexp_learner *h, cudaStream_t st, const float *params, const HeadLayout *hds, int nheads, const MlpIn &in,
+                       float *const *hbufs, float *const *outs) {
+    if (nheads < 1 || nheads > 2) return false;
+    float *const hb[1][2] = {{hbufs[0], nheads > 1 ? hbufs[1] : nullptr}};
+    float *const ob[1][2] = {{outs[0], nheads > 1 ? outs[1] : nullptr}};
+    return mlp_fused_forward_multi(h, st, 1, &params, hds, nheads, &in, hb, ob);
 }
 
 void mlp_forward(maexp_learner *h, cudaStream_t st, const float *params, const HeadLayout &hd, const MlpIn &in, float *hbuf,
@@ -2003,6 +2058,34 @@ void forward(maexp_learner *h, cudaStream_t st, const float *params, const float
     for (size_t k = 0; k < h->heads.size(); ++k) mlp_forward(h, st, params, h->heads[k], in, a.h[k], a.out[k]);
 }
 
+// All forward passes of an update (online(s) kept for the backward pass, target(s'), and online(s') for the distributional
+// nets' double-DQN action selection) as two launches: every pass is a slice of the grid of the fused trunk kernel and of the
+// fused MLP kernel.  Separate streams gave the same overlap in principle, but each pass's CTAs queued behind the others'
+// shared-memory footprint and ran at 8 warps per SM.
+bool forward_batched(maexp_learner *h, cudaStream_t st, const float *obs, const float *next_obs, int B) {
+    if (!h->batched_fwd || !h->fused_mlp || h->heads.empty() || h->heads.size() > 2) return false;
+    const int n = h->dist ? 3 : 2;
+    const float *params[3] = {h->online, h->target, h->online};
+    const float *inputs[3] = {obs, next_obs, next_obs};
+    maexp_learner::Acts *acts[3] = {&h->acts[0], &h->acts[2], &h->acts[1]};
+    const int train[3] = {1, 0, 0};
+    MlpIn ins[3];
+    if (h->has_conv) {
+        h->fused_trunk_acts = false;
+        if (!trunk_forward_multi(h, st, n, params, inputs, acts, train, B)) return false;
+        for (int q = 0; q < n; ++q) ins[q] = {acts[q]->flat, h->D, (long long)h->B * h->D, B, h->B, h->D};
+    } else {
+        for (int q = 0; q < n; ++q) ins[q] = {inputs[q], h->cfg.obs_stride, (long long)B * h->cfg.obs_stride, B, h->B, h->D};
+    }
+    float *const hb[3][2] = {{acts[0]->h[0], acts[0]->h[1]}, {acts[1]->h[0], acts[1]->h[1]}, {acts[2]->h[0], acts[2]->h[1]}};
+    float *const ob[3][2] = {{acts[0]->out[0], acts[0]->out[1]}, {acts[1]->out[0], acts[1]->out[1]}, {acts[2]->out[0], acts[2]->out[1]}};
+    if (mlp_fused_forward_multi(h, st, n, params, h->heads.data(), (int)h->heads.size(), ins, hb, ob)) return true;
+    // (shapes the fused MLP does not take: the heads pass by pass on this stream)
+    for (int q = 0; q < n; ++q)
+        for (size_t k = 0; k < h->heads.size(); ++k) mlp_forward(h, st, params[q], h->heads[k], ins[q], acts[q]->h[k], acts[q]->out[k]);
+    return true;
+}
+
 // backward of the online net through the activations of pass 0; d_out[k] already filled
 void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
     maexp_learner::Acts &a = h->acts[0];
@@ -2012,7 +2095,7 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
     else in = {obs, h->cfg.obs_stride, (long long)B * h->cfg.obs_stride, B, B, h->D};
     wgrad_open(h, st);
     const int nheads = (int)h->heads.size(), H = h->H, G = h->G;
-    if (h->fused_mlp && nheads <= 2 && H <= kMlpTN) {
+    if (h->fused_mlp && nheads <= 2 && H <= kMlpTN && in.din <= kMlpMaxIn) {
         // weight gradients on the side streams around ONE kernel for the data-gradient chain of all heads
         const long long P = h->P, gH = (long long)B * H;
         MlpBwdHeads bh;
@@ -2503,6 +2586,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (const char *tc = getenv("MAEXP_TC")) h->use_tc = atoi(tc) != 0;
     if (const char *ft = getenv("MAEXP_FUSED_TRUNK")) h->fused_trunk = atoi(ft) != 0;
     if (const char *fm = getenv("MAEXP_FUSED_MLP")) h->fused_mlp = atoi(fm) != 0;
+    if (const char *bf = getenv("MAEXP_BATCHED_FWD")) h->batched_fwd = atoi(bf) != 0;
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
     h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;
     const int trunk = cfg->kind == MAEXP_LEARNER_IQN ? cfg->iqn_trunk : 0;  // MAEXP_IQN_TRUNK_*
@@ -3026,7 +3110,7 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         MAEXP_CUDA_L(cudaGetLastError());
         return 0;
     }
-    {
+    if (!forward_batched(h, st, obs, next_obs, B)) {
         // the training pass is the longest chain: it is issued first (its nodes come first in a captured graph), the side
         // passes fork from the point before it
         cudaEventRecord(h->ev_fork, st);
