@@ -419,3 +419,34 @@ def test_fused_trunk_matches_layer_by_layer_and_torch(kind, V, C, B, monkeypatch
             e_fused = float((grads[a, off:off + cnt] - refg).norm()) / (float(refg.norm()) + 1e-12)
             e_layer = float((grads_ref[a, off:off + cnt] - refg).norm()) / (float(refg.norm()) + 1e-12)
             assert e_fused <= 1e-4 and e_layer <= 1e-4, (a, name, e_fused, e_layer)
+
+
+@pytest.mark.parametrize("kind,V,C,B", [("c51", 7, 3, 256), ("dqn_conv_mlp", 7, 7, 32), ("qr", 5, 3, 70)])
+def test_batched_forward_passes_match_streamed(kind, V, C, B, monkeypatch):
+    """MAEXP_BATCHED_FWD=1 (all forward passes of an update as grid slices of one launch per fused kernel) computes the
+    same loss and gradients as the default one-stream-per-pass issue order (same kernels, same summation order: bit-equal
+    up to the C51 projection's atomics)."""
+    from maexp_b200.core.agents.brains import LearnerGroup
+    cfg, _ = golden_configs()[kind]
+    G = 2
+    cfg = cfg.merged_with(batch_size=B, visible_range=V)
+    torch.manual_seed(77)
+    gen = torch.Generator().manual_seed(6)
+    obs = (torch.rand((G, B, C, V, V), generator=gen) < 0.25).float()
+    nxt = (torch.rand((G, B, C, V, V), generator=gen) < 0.25).float()
+    groups = []
+    for batched in ("1", "0"):
+        monkeypatch.setenv("MAEXP_BATCHED_FWD", batched)
+        groups.append(LearnerGroup(cfg, [C, V, V], 4, G, B))
+    g, ref = groups
+    for a in range(G):
+        ref.load_state_dict(a, g.state_dict(a))
+        ref.load_state_dict(a, g.state_dict(a, which=1), which=1)
+    batch = {"obs": pack(g, obs), "next_obs": pack(g, nxt),
+             "actions": torch.randint(0, 4, (G, B), generator=gen).to(torch.int32).cuda(),
+             "rewards": torch.randint(-1, 2, (G, B), generator=gen).float().cuda(),
+             "dones": (torch.rand((G, B), generator=gen) < 0.1).to(torch.uint8).cuda()}
+    loss, loss_ref = g.grads(batch).cpu(), ref.grads(batch).cpu()
+    grads, grads_ref = g.params(2).cpu(), ref.params(2).cpu()
+    assert float((loss - loss_ref).abs().max()) <= 1e-6 * float(loss_ref.abs().max())
+    assert float((grads - grads_ref).norm()) <= 1e-6 * float(grads_ref.norm())
