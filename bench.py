@@ -172,7 +172,7 @@ def run_ours(args, rank, local_rank, world):
 
     from maexp_b200 import _lib
     from maexp_b200 import distributed as mdist
-    from maexp_b200.core.agents.brains import LearnerGroup
+    from maexp_b200.core.agents.brains import GraphedUpdate, LearnerGroup
     from maexp_b200.core.environments.batched import BatchedEnvironment
     from maexp_b200.core.maps import generate_map
     from maexp_b200.core.utils.buffer import DeviceReplayRing
@@ -276,23 +276,12 @@ def run_ours(args, rank, local_rank, world):
     B = int(cfg.batch_size)
     group = LearnerGroup(cfg, [3, 7, 7], 4, N, B, obs_stride=env.slot_floats, device=dev)
     batch = ring.new_batch(B)
-    reduce_fn = mdist.make_grad_all_reduce(dist) if dist is not None else None
-    grads_view = group.params(_lib.BUF_GRADS)
     ring.sample(batch, seed=921, tick=0)
-    group.learn(batch, all_reduce=reduce_fn)  # eager warm-up
-    torch.cuda.synchronize(dev)
-    g_grads, g_apply = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g_grads):
-        group.grads(batch)
-    with torch.cuda.graph(g_apply):
-        group.apply(1.0 / world)
+    graphed = GraphedUpdate(group, batch, dist=dist)  # first step eager (warm-up), second captures, then replays
 
     def update(t):
         ring.sample(batch, seed=921, tick=t)
-        g_grads.replay()
-        if reduce_fn is not None:
-            reduce_fn(grads_view)
-        g_apply.replay()
+        graphed.step()
 
     for t in range(5):
         update(t)

@@ -269,6 +269,49 @@ class LearnerGroup:
         return loss
 
 
+class GraphedUpdate:
+    """A team update on a fixed batch buffer replayed from CUDA graphs: one graph for forward / backward of every agent's
+    network and one for clip + optimizer step; the data-parallel learner's NCCL all-reduce of the flat gradient buffer runs
+    between them (capturing it into the graph was measured no faster at 2 GPUs, 0.290 vs 0.289 ms per update, and a captured
+    collective has to be destroyed before the process group).  The first step() runs eagerly (it is a real update and
+    initialises lazily created state such as the NCCL communicator), the second captures, later ones replay.
+
+    dist: torch.distributed module (or None for a single GPU); the replay sampler refills `batch` in place before step()."""
+
+    def __init__(self, group, batch, active=None, dist=None, process_group=None):
+        self.group, self.batch, self.active, self.dist, self.pg = group, batch, active, dist, process_group
+        self.world = dist.get_world_size(process_group) if dist is not None else 1
+        self.grads_view = group.params(_lib.BUF_GRADS)
+        self.g_grads = self.g_apply = None
+        self.calls = 0
+        if group.kind == "iqn" and not all(k in batch for k in ("taus", "tau_dashes", "tau_sel")):
+            # the fractions must live in fixed buffers the caller refreshes: a captured torch.rand would replay one draw
+            raise ValueError("GraphedUpdate on an IQN learner needs taus / tau_dashes / tau_sel tensors in the batch")
+
+    def _reduce(self):
+        if self.dist is not None:
+            self.dist.all_reduce(self.grads_view, op=self.dist.ReduceOp.SUM, group=self.pg)
+
+    def step(self):
+        self.calls += 1
+        if self.calls == 1:
+            loss = self.group.grads(self.batch)
+            self._reduce()
+            self.group.apply(1.0 / self.world, self.active)
+            return loss
+        if self.g_grads is None:
+            torch.cuda.synchronize(self.group.device)
+            self.g_grads, self.g_apply = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_grads):
+                self.group.grads(self.batch)
+            with torch.cuda.graph(self.g_apply):
+                self.group.apply(1.0 / self.world, self.active)
+        self.g_grads.replay()
+        self._reduce()
+        self.g_apply.replay()
+        return self.group.loss
+
+
 class Brain:
     """Single-agent brain with the reference's interface (abstract_brain.py:20-67)."""
 

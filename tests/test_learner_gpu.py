@@ -450,3 +450,34 @@ def test_batched_forward_passes_match_streamed(kind, V, C, B, monkeypatch):
     grads, grads_ref = g.params(2).cpu(), ref.params(2).cpu()
     assert float((loss - loss_ref).abs().max()) <= 1e-6 * float(loss_ref.abs().max())
     assert float((grads - grads_ref).norm()) <= 1e-6 * float(grads_ref.norm())
+
+
+def test_graphed_update_equals_eager_updates():
+    """GraphedUpdate (eager first step, then captured CUDA graphs) walks the parameters exactly like
+    LearnerGroup.learn on a twin group (QR-DQN: no atomics anywhere, so bit-equal)."""
+    from maexp_b200.core.agents.brains import GraphedUpdate, LearnerGroup
+    kind, V, C, B, G = "qr", 7, 3, 64, 3
+    cfg, _ = golden_configs()[kind]
+    cfg = cfg.merged_with(batch_size=B, visible_range=V)
+    torch.manual_seed(5)
+    g, ref = LearnerGroup(cfg, [C, V, V], 4, G, B), LearnerGroup(cfg, [C, V, V], 4, G, B)
+    for a in range(G):
+        ref.load_state_dict(a, g.state_dict(a))
+        ref.load_state_dict(a, g.state_dict(a, which=1), which=1)
+    gen = torch.Generator().manual_seed(8)
+    batch = {"obs": torch.zeros((G, B, g.obs_stride), device="cuda"), "next_obs": torch.zeros((G, B, g.obs_stride), device="cuda"),
+             "actions": torch.zeros((G, B), dtype=torch.int32, device="cuda"), "rewards": torch.zeros((G, B), device="cuda"),
+             "dones": torch.zeros((G, B), dtype=torch.uint8, device="cuda")}
+    graphed = GraphedUpdate(g, batch)
+    for step in range(5):
+        obs = (torch.rand((G, B, C, V, V), generator=gen) < 0.25).float()
+        nxt = (torch.rand((G, B, C, V, V), generator=gen) < 0.25).float()
+        batch["obs"].copy_(pack(g, obs))  # the replay sampler refills the same buffers in the product
+        batch["next_obs"].copy_(pack(g, nxt))
+        batch["actions"].copy_(torch.randint(0, 4, (G, B), generator=gen).to(torch.int32))
+        batch["rewards"].copy_(torch.randint(-1, 2, (G, B), generator=gen).float())
+        loss = graphed.step().cpu().clone()
+        want = ref.learn(batch).cpu()
+        assert torch.equal(loss, want), step
+        assert torch.equal(g.params().cpu(), ref.params().cpu()), step
+    assert graphed.g_grads is not None
