@@ -1325,7 +1325,7 @@ struct TrunkPasses {
     int train[3];
 };
 template <int V, bool TRAIN>
-__global__ void __launch_bounds__(256) trunk_fused_fwd_kernel(const __grid_constant__ TrunkPasses tp, int B, int C,
+__global__ void __launch_bounds__(512) trunk_fused_fwd_kernel(const __grid_constant__ TrunkPasses tp, int B, int C,
                                                               int F1, int F2, long long stride, long long gObs, long long P,
                                                               long long o_c1w, long long o_c1b, long long o_c2w,
                                                               long long o_c2b, long long gFlat, float *p_out, uint8_t *arg_out,
@@ -1837,7 +1837,9 @@ bool trunk_forward_multi(maexp_learner *h, cudaStream_t st, int n, const float *
     const int G = h->G, C = h->C, V = h->V, F1 = h->F1, F2 = h->F2, Hp = h->Hp;
     const long long P = h->P, Bmax = h->B, stride = h->cfg.obs_stride;
     if (!h->fused_trunk || F1 > 32 || F2 > 64 || !(V == 5 || V == 7 || V == 9) || n < 1 || n > 3) return false;
-    const int warps = B >= 64 ? 8 : 4, pc = (Hp * Hp + 3) / 4 * 4;  // the 32 KB of conv2 weights are staged once per CTA
+    // the 32 KB of conv2 weights are staged once per CTA: 16 warps per CTA at the update batch sizes, so that the three
+    // forward passes of an update (3 x 128 CTAs of ~69 KB at B = 256, G = 8) are resident together
+    const int warps = (B >= 128 && B < 512) ? 16 : B >= 64 ? 8 : 4, pc = (Hp * Hp + 3) / 4 * 4;
     const size_t smem = sizeof(float) * ((size_t)F1 * 256 + (size_t)C * 4 * 32 + 96 +
                                          (size_t)warps * (32 * pc + (C * V * V + 3) / 4 * 4));
     if (smem > 200 * 1024) return false;
