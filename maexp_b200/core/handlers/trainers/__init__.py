@@ -11,7 +11,7 @@ import os
 import torch
 
 from ...agents import BatchedActor
-from ...agents.brains import LearnerGroup
+from ...agents.brains import GraphedUpdate, LearnerGroup
 from ...environments.batched import BatchedEnvironment
 from ...utils.buffer import generate_buffer
 from ...utils.logging import initialize_logging
@@ -35,6 +35,11 @@ class DefaultTrainer:
         self.active = 1 - self.actor.no_task  # agent_tasks "-1" agents are never trained (abstract_trainer.py:49-51)
         self.epsilon = float(config.epsilon_initial)
         self.all_reduce = all_reduce
+        # single-GPU updates replay from CUDA graphs (about a hundred launches per update otherwise); the IQN learners draw
+        # their quantile fractions with torch.rand per update and the data-parallel path takes the caller's all-reduce: eager
+        self.graphed = None
+        if all_reduce is None and self.learner.kind != "iqn" and config.get("cuda_graph_update", True):
+            self.graphed = GraphedUpdate(self.learner, self.batch, active=self.active)
         self.tick = 0
         self.episode_count = 0
         self.global_step = 0
@@ -55,7 +60,10 @@ class DefaultTrainer:
     # ---- default_trainer.py:18-85
     def loop_step(self):
         self.buffer.sample(self.batch, seed=int(self.config.seed), tick=self.tick)
-        loss = self.learner.learn(self.batch, active=self.active, all_reduce=self.all_reduce)
+        if self.graphed is not None:
+            loss = self.graphed.step()
+        else:
+            loss = self.learner.learn(self.batch, active=self.active, all_reduce=self.all_reduce)
         self.actor.refresh()
         head = self.buffer.head
         positions = None if self.buffer.positions is None else self.buffer.positions[head]
