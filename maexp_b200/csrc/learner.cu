@@ -1697,7 +1697,7 @@ struct MlpBwdHeads {
 
 __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params, long long P, const MlpBwdHeads hd, int nheads,
                                                             int rows, long long rows_max, int din, int H, float *dx,
-                                                            int vec_w1, float *dx_nhwc, int Q) {
+                                                            int vec_w1, float *dx_nhwc, int Q, int accumulate) {
     constexpr int TM = kMlpTM, TN = kMlpTN, BK = kMlpBK;
     __shared__ __align__(16) float As[BK][TM + 4];
     __shared__ __align__(16) float Bs[BK][TN + 4];
@@ -1822,6 +1822,7 @@ __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params,
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
             if (n < din) {
+                if (accumulate) accx[i][j] = __fadd_rn(dst[(size_t)m * din + n], accx[i][j]);  // dx += (the caller's earlier heads)
                 dst[(size_t)m * din + n] = accx[i][j];
                 // the same gradient as conv2's NHWC output gradient [m][pos][oc] (flatten order is oc*Q + pos): what the
                 // conv2 weight-gradient GEMM reads
@@ -2034,6 +2035,19 @@ void mlp_backward(maexp_learner *h, cudaStream_t st, const HeadLayout &hd, const
         colsum(ws, G, h->ones, dout, h->grads + hd.b2, rows, O, gO, P);
         wgrad_end();
     }
+    if (h->fused_mlp && H <= kMlpTN && in.din <= kMlpMaxIn) {  // the data-gradient chain of this head in one kernel
+        MlpBwdHeads bh = {};
+        bh.w1[0] = hd.w1; bh.w2[0] = hd.w2; bh.out[0] = O; bh.dout[0] = dout; bh.hbuf[0] = hbuf; bh.dh[0] = dhbuf;
+        const int vec_w1 = (in.din & 3) == 0 && (P & 3) == 0 && (reinterpret_cast<uintptr_t>(h->online + hd.w1) & 15) == 0;
+        dim3 grid((rows + kMlpTM - 1) / kMlpTM, dx ? (in.din + kMlpTN - 1) / kMlpTN : 1, G);
+        mlp_fused_bwd_kernel<<<grid, 256, 0, st>>>(h->online, P, bh, 1, rows, in.rows_max, in.din, H, dx, vec_w1, nullptr, 1,
+                                                   accumulate_dx);
+        cudaStream_t ws = wgrad_begin(st);
+        gemm(ws, G, dhbuf, in.x, h->grads + hd.w1, nullptr, H, in.din, rows, 1, H, in.x_row, 1, in.din, 1, gH, in.x_g, P, 0);
+        colsum(ws, G, h->ones, dhbuf, h->grads + hd.b1, rows, H, gH, P);
+        wgrad_end();
+        return;
+    }
     gemm(st, G, dout, h->online + hd.w2, dhbuf, nullptr, rows, H, O, O, 1, H, 1, H, 1, gO, P, gH, 0, 0, 0, hbuf, gH);
     {
         cudaStream_t ws = wgrad_begin(st);
@@ -2130,7 +2144,7 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
             h->col2_ready = h->dy2_ready = true;
         }
         mlp_fused_bwd_kernel<<<grid, 256, 0, st>>>(h->online, P, bh, nheads, B, B, in.din, H, dx, vec_w1,
-                                                   to_trunk ? h->d_y2 : nullptr, h->H2 * h->H2);
+                                                   to_trunk ? h->d_y2 : nullptr, h->H2 * h->H2, 0);
         for (int k = 0; k < nheads; ++k) {
             const HeadLayout &hd = h->heads[k];
             cudaStream_t ws = wgrad_begin(st);
@@ -2520,7 +2534,8 @@ int iqn_forward(maexp_learner *h, cudaStream_t st, const float *params, const fl
          R * h->ncos, P, R * D, P, /*relu=*/1);
     iqn_hadamard_fwd_kernel<<<grid1d((long long)rows * D, G), 256, 0, st>>>(psi, q.phi, q.e, B, nq, D, Bmax * D, R * D);
     const MlpIn e_in = {q.e, D, R * D, rows, R, D};
-    for (int k = 0; k < 2; ++k) mlp_forward(h, st, params, h->heads[k], e_in, q.hrow[k], q.out[k]);
+    if (!mlp_fused_forward(h, st, params, h->heads.data(), 2, e_in, q.hrow, q.out))
+        for (int k = 0; k < 2; ++k) mlp_forward(h, st, params, h->heads[k], e_in, q.hrow[k], q.out[k]);
     return 0;
 }
 

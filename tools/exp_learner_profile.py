@@ -7,12 +7,21 @@ from torch.profiler import ProfilerActivity, profile
 from maexp_b200.config import baseline_config
 from maexp_b200.core.agents.brains import LearnerGroup
 
-cfg = baseline_config(int(os.environ.get("CFG", "5")))
-G, B = int(cfg.num_agents), int(cfg.batch_size)
+if os.environ.get("KIND"):  # a learner kind of oracle/make_golden_learner.py (local 3 x 7 x 7 view), e.g. KIND=iqn B=256 G=8
+    from oracle.make_golden_learner import configs as golden_configs
+    cfg = golden_configs()[os.environ["KIND"]][0]
+    G, B = int(os.environ.get("G", "8")), int(os.environ.get("B", "256"))
+    cfg = cfg.merged_with(batch_size=B)
+else:
+    cfg = baseline_config(int(os.environ.get("CFG", "5")))
+    G, B = int(cfg.num_agents), int(cfg.batch_size)
 g = LearnerGroup(cfg, [3, 7, 7], 4, G, B)
 batch = {"obs": torch.rand(G, B, g.obs_stride, device="cuda").round(), "next_obs": torch.rand(G, B, g.obs_stride, device="cuda").round(),
          "actions": torch.randint(0, 4, (G, B), dtype=torch.int32, device="cuda"), "rewards": torch.zeros(G, B, device="cuda"),
          "dones": torch.zeros(G, B, dtype=torch.uint8, device="cuda")}
+if g.kind == "iqn":  # fixed fraction buffers (a captured torch.rand would replay one draw)
+    batch.update(taus=torch.rand(G, B, g.Z, device="cuda"), tau_dashes=torch.rand(G, B, g.Nd, device="cuda"),
+                 tau_sel=torch.rand(G, g.Z, device="cuda"))
 for _ in range(3):
     g.learn(batch)
 torch.cuda.synchronize()
