@@ -65,6 +65,12 @@ typedef struct {
     float std_distribution[MAEXP_MAX_RINGS];
     float noise_threshold[MAEXP_MAX_RINGS];  /* fp32(std*ratio), dist_observation_noise.py:60,66 */
     int32_t env_kind;            /* MAEXP_ENV_* */
+    int32_t dynamic_obstacles;   /* 1: the dynamic_simple map (core/maps/dynamic_simple_map.py:12-63): the wall cells
+                                  * (X/2, 1) and (X/2, Y/2) of maexp_tables.wall are obstacles that world.step moves
+                                  * one cell per step (abstract_world.py:40) -- the first up and down column X/2
+                                  * between y = 1 and Y-2, the second along row Y/2 between x = 1 and X-2 -- and that
+                                  * keep their place across resets; moves and object respawns see the moved cells,
+                                  * the line-of-sight table stays the one of the initial layout, as in the reference */
 } maexp_env_cfg;
 
 /* Static per-map tables in the REFERENCE's layout, HOST pointers; packed to bit rows and

@@ -97,6 +97,7 @@ class BatchedEnvironment:
         cfg.noise = NOISES[config.observation_noise]
         cfg.reward_mode = REWARD_MODES[config.environment]
         cfg.env_kind = ENV_KINDS.get(config.environment, 0)
+        cfg.dynamic_obstacles = int(config.map.name == "dynamic_simple")  # dynamic_simple_map.py:29-63
         cfg.max_episode_length = int(config.max_episode_length)
         cfg.num_objects = int(config.num_objects)
         cfg.keep_objects_num = int(bool(config.keep_objects_num))

@@ -104,6 +104,40 @@ class SimpleMap(AbstractMap):
         return {1: [(0, 1, -1, 1, -1)], 2: [(0, 1, h, 1, -1), (1, h, -1, 1, -1)]}
 
 
+class DynamicSimpleMap(SimpleMap):
+    """core/maps/dynamic_simple_map.py:12-63.  The simple map with two one-cell obstacles that `world.step` moves
+    one cell per step (abstract_world.py:40) and that `reset()` leaves alone.  On the device the two cells are a
+    closed-form function of a per-environment world-step counter (`dynamic_obstacles` of maexp_env_cfg);
+    `wall_matrix` here is the initial layout, from which the line-of-sight table is generated once, as in the
+    reference.  `step()` restates the shuttle rule on the host matrices for interface compatibility."""
+
+    def __init__(self, config, size_x, size_y):
+        self.obstacles_pos = [[int(size_x) // 2, 1], [int(size_x) // 2, int(size_y) // 2]]
+        self.obstacles_homing_flag = [False, False]
+        super().__init__(config, size_x, size_y)
+
+    def locate_walls(self):
+        self._border()
+        for x, y in self.obstacles_pos:
+            self.wall_matrix[x, y] = 1
+
+    def step(self):
+        X, Y = self.SIZE_X, self.SIZE_Y
+        far = ((X // 2, Y - 2), (X - 2, Y // 2))    # turning points: obstacle 0 shuttles along y, obstacle 1 along x
+        home = ((X // 2, 1), (1, Y // 2))
+        for x, y in self.obstacles_pos:
+            self.wall_matrix[x, y] = 0
+        for k, pos in enumerate(self.obstacles_pos):
+            if tuple(pos) == far[k]:
+                self.obstacles_homing_flag[k] = True
+            elif tuple(pos) == home[k]:
+                self.obstacles_homing_flag[k] = False
+        for k, axis in enumerate((1, 0)):
+            self.obstacles_pos[k][axis] += -1 if self.obstacles_homing_flag[k] else 1
+        for x, y in self.obstacles_pos:
+            self.wall_matrix[x, y] = 1
+
+
 _FOUR_ROOMS_RUN = (1, 2, 3, 7, 8, 9, 10, 13, 14, 15, 16, 20, 21, 22)
 
 
@@ -260,6 +294,7 @@ class TwoCentralRoomsMap(AbstractMap):
 _REGISTRY = {
     # name -> (class, fixed size or None for config.map.SIZE_X/SIZE_Y)  core/maps/__init__.py:26-39
     "simple": (SimpleMap, None),
+    "dynamic_simple": (DynamicSimpleMap, None),
     "four_rooms": (FourRoomsMap, (24, 24)),
     "three_rooms": (ThreeRoomsMap, (25, 25)),
     "four_rectangle": (FourRectangleMap, (40, 24)),

@@ -214,6 +214,7 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     if (X < 3 || X > 255 || Y < 3 || Y + cfg->visible_range / 2 > 32)
         return fail("maexp_env_create: map must satisfy 3<=X<=255, 3<=Y and Y + visible_range/2 <= 32 (32-bit grid rows)");
     if (V != 5 && V != 7 && V != 9) return fail("maexp_env_create: visible_range must be 5, 7 or 9");
+    if (cfg->dynamic_obstacles && (X < 5 || Y < 5)) return fail("maexp_env_create: dynamic_obstacles needs a map of at least 5 x 5");
     if (M < 1 || M > 15) return fail("maexp_env_create: num_destinations must be in 1..15");
     if (!tb->wall || !tb->objects_area || !tb->noise_area || !tb->destination || !tb->los)
         return fail("maexp_env_create: missing table");
@@ -304,7 +305,13 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
                         los[((size_t)x * Y + y) * LW + (bit >> 6)] |= 1ull << (bit & 63);
                     }
     int rc = 0;
-    rc |= upload(h, &p.wall, rows(tb->wall, 1));
+    std::vector<uint32_t> wall_rows = rows(tb->wall, 1);
+    if (cfg->dynamic_obstacles) {  // the kernel adds the two moving cells itself; the table keeps the fixed walls
+        wall_rows[X / 2] &= ~(1u << (1 + V / 2));
+        wall_rows[X / 2] &= ~(1u << (Y / 2 + V / 2));
+        rc |= dev_alloc(h, &p.wsteps, (size_t)E);
+    }
+    rc |= upload(h, &p.wall, wall_rows);
     rc |= upload(h, &p.noise_area, rows(tb->noise_area, 1));
     rc |= upload(h, &p.area, rows(tb->objects_area, T));
     rc |= upload(h, &p.dest, rows(tb->destination, M));

@@ -40,6 +40,8 @@ struct EnvParams {
     unsigned long long *stats;  // [0] env-steps, [1] resets
     uint32_t tx_magic;          // ceil(2^32 / (T*X))
     int32_t *error_flag;
+    // dynamic_simple_map.py: world steps taken since creation (the obstacle phase; survives resets), or nullptr
+    uint32_t *wsteps;
     // io
     const int8_t *actions;
     const uint8_t *order;
@@ -208,6 +210,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     uint32_t attempt = 0;
     uint4 rw = make_uint4(0, 0, 0, 0);
 
+    // Moving obstacles of dynamic_simple (dynamic_simple_map.py:29-63), packed x | y << 8; -1 on every other map.
+    // Obstacle 0 shuttles along y in [1, Y-2] on column X/2 starting at y = 1, obstacle 1 along x in [1, X-2] on
+    // row Y/2 starting at x = X/2, one cell per world step, turning at the ends: a triangle wave of the number of
+    // world steps k since creation (map.reset() does not touch them).
+    int ob0 = -1, ob1 = -1;
+    auto place_obstacles = [&](uint32_t k) {
+        const uint32_t L0 = (uint32_t)(Y - 3), L1 = (uint32_t)(X - 3);
+        const uint32_t m0 = k % (2 * L0), m1 = (k + (uint32_t)(X / 2 - 1)) % (2 * L1);
+        ob0 = (X / 2) | ((1 + (int)(m0 <= L0 ? m0 : 2 * L0 - m0)) << 8);
+        ob1 = (1 + (int)(m1 <= L1 ? m1 : 2 * L1 - m1)) | ((Y / 2) << 8);
+    };
+    auto wall_at = [&](int x, int y) {
+        const int cell = x | (y << 8);
+        return (__ldg(&s_wall[x]) & (1u << (y + R))) != 0 || cell == ob0 || cell == ob1;
+    };
     auto agent_at = [&](int x, int y) { return (agrid[x] >> (y + R)) & 1u; };
     // default_environment.py:134-148, one accepted object; two uniforms per attempt
     int32_t *const hm = p.out.heatmaps;  // optional visit statistics, see maexp_obs_out
@@ -222,7 +239,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             ++attempt;
             const int x = 1 + (int)scale(u1, (uint32_t)(X - 1)), y = 1 + (int)scale(u2, (uint32_t)(Y - 1));
             const uint32_t bit = 1u << (y + R);
-            bool ok = !(__ldg(&s_wall[x]) & bit) && (__ldg(&s_area[t * X + x]) & bit);
+            bool ok = !wall_at(x, y) && (__ldg(&s_area[t * X + x]) & bit);
             for (int t2 = 0; t2 < T; ++t2) ok = ok && !(grid[t2 * XP + x] & bit);
             ok = ok && !agent_at(x, y);
             if (ok) {
@@ -251,6 +268,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
         if (p.random_dest)
             for (int k = 0; k < N; ++k) dsel |= (uint64_t)p.dest_sel[(size_t)env * N + k] << (4 * k);
         for (int q = 0; q < P * N; ++q) s_past[q * EPW + lane] = p.past[(size_t)env * P * N + q];
+        if (p.wsteps) {  // abstract_world.py:40: the map steps first; a reset leaves the obstacles where they are
+            uint32_t k = p.wsteps[env];
+            if (!is_reset) p.wsteps[env] = ++k;
+            place_obstacles(k);
+        }
 
         if (is_reset) {
             // ------------------------------------------------ default_environment.py:64-116
@@ -329,7 +351,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                     ca |= 1u << id;
                     move = false;
                 }
-                if (__ldg(&s_wall[nx]) & (1u << (ny + R))) {
+                if (wall_at(nx, ny)) {
                     cw |= 1u << id;
                     move = false;
                 }

@@ -67,4 +67,16 @@ def cases():
         map=dict(name="two_central_rooms", SIZE_X=50, SIZE_Y=25), type_objects=2, num_agents=12, num_objects=60,
         agent_tasks=["0", "0", "1", "1", "01", "01", "10", "10", "0", "1", "01", "-1"],
         init_xys=xy8 + [[-3, 3], [3, 3], [-3, -3], [3, -3]], object_view_method="object_types"), 80, None, {})
+    # dynamic_simple: two one-cell obstacles inside the object area (configs/map/dynamic_simple.yaml, dra3_exp.yaml);
+    # the 10x10 variant crowds six agents and objects around them
+    c["dynamic_simple_20"] = (make_config(map=dict(name="dynamic_simple", SIZE_X=20, SIZE_Y=20), num_agents=4,
+                                          num_objects=40), 80, None, {})
+    c["dynamic_simple_small_t2"] = (make_config(
+        map=dict(name="dynamic_simple", SIZE_X=10, SIZE_Y=10), type_objects=2, num_objects=8, num_agents=6,
+        agent_tasks=["0", "1", "01", "10", "0", "1"], object_view_method="object_types", max_episode_length=50,
+        init_xys=[[1, 1], [-1, 1], [1, -1], [-1, -1], [2, 2], [-2, -2]]), 120, None, {})
+    # default_environment.py:33,97-98 with more init_xys than agents: all 12 entries are shuffled, 5 are used
+    c["shuffle_spare_init_xys"] = (make_config(num_agents=5, init_xys=xy8 + [[-3, 3], [3, 3], [-3, -3], [3, -3]],
+                                               map=dict(name="central_room", SIZE_X=25, SIZE_Y=25), num_objects=40,
+                                               max_episode_length=12), 80, None, {})
     return c

@@ -33,6 +33,10 @@ typedef struct {
     int32_t counters[4];        /* objects_generated, objects_completed, agents_collided, walls_collided */
     int32_t pending_reset;
     uint32_t respawn_draws;     /* draw counter inside the current call */
+    /* dynamic_simple_map.py:13-18: obstacle cells and homing flags; map.reset() leaves them alone, so they
+     * carry over from episode to episode */
+    int16_t obstacle[2][2];
+    uint8_t homing[2];
 } env_t;
 
 struct orc_env {
@@ -92,6 +96,11 @@ static void build_map(orc_env *o) {
         for (int y = 0; y < Y; ++y) o->noise_area[x][y] = 1; /* abstract_map.py:77-78 */
 
     switch (o->cfg.map_id) {
+    case ORC_MAP_DYNAMIC_SIMPLE:
+        /* dynamic_simple_map.py:13-27: obstacles at [X/2, 1] and [X/2, Y/2]; DynamicSimpleMap.step() has no
+         * caller in the reference, so the obstacles never move.  Areas are SimpleMap's (fall through). */
+        o->wall[X / 2][1] = o->wall[X / 2][Y / 2] = 1;
+        /* fall through */
     case ORC_MAP_SIMPLE:
         if (T == 1) area_box(o, 0, 1, X - 1, 1, Y - 1);
         else if (T == 2) { area_box(o, 0, 1, X / 2, 1, Y - 1); area_box(o, 1, X / 2, X - 1, 1, Y - 1); }
@@ -349,12 +358,37 @@ static void build_los(orc_env *o) {
     for (size_t i = 0; i < (size_t)X * Y * V * V; ++i) o->los[i] += 1;
 }
 
+/* wall_matrix as this environment sees it NOW.  o->wall is the matrix at construction time (the line-of-sight
+ * table is generated from it once, local_area_mask.py:18-97); on dynamic_simple the two obstacle cells move
+ * with every world step (dynamic_simple_map.py:29-63) while the border stays. */
+static int env_wall(const orc_env *o, const env_t *en, int x, int y) {
+    if (o->cfg.map_id != ORC_MAP_DYNAMIC_SIMPLE) return o->wall[x][y];
+    if (x == 0 || y == 0 || x == o->X - 1 || y == o->Y - 1) return 1;
+    for (int k = 0; k < 2; ++k)
+        if (en->obstacle[k][0] == x && en->obstacle[k][1] == y) return 1;
+    return 0;
+}
+
+/* dynamic_simple_map.py:29-63, called first thing in world.step (abstract_world.py:40) */
+static void map_step(const orc_env *o, env_t *en) {
+    if (o->cfg.map_id != ORC_MAP_DYNAMIC_SIMPLE) return;
+    const int X = o->X, Y = o->Y;
+    for (int k = 0; k < 2; ++k) {
+        const int x = en->obstacle[k][0], y = en->obstacle[k][1];
+        if ((x == X / 2 && y == Y - 2 && k == 0) || (x == X - 2 && y == Y / 2 && k == 1)) en->homing[k] = 1;
+        else if ((x == X / 2 && y == 1 && k == 0) || (x == 1 && y == Y / 2 && k == 1)) en->homing[k] = 0;
+    }
+    en->obstacle[0][1] = (int16_t)(en->obstacle[0][1] + (en->homing[0] ? -1 : 1));
+    en->obstacle[1][0] = (int16_t)(en->obstacle[1][0] + (en->homing[1] ? -1 : 1));
+}
+
 /* ------------------------------------------------------------ construction */
 
 orc_env *orc_create(const orc_cfg *cfg) {
     orc_env *o = (orc_env *)calloc(1, sizeof(orc_env));
     o->cfg = *cfg;
     switch (cfg->map_id) { /* core/maps/__init__.py:26-39 */
+    case ORC_MAP_DYNAMIC_SIMPLE:
     case ORC_MAP_SIMPLE: o->X = cfg->size_x; o->Y = cfg->size_y; break;
     case ORC_MAP_FOUR_ROOMS: o->X = 24; o->Y = 24; break;
     case ORC_MAP_THREE_ROOMS: o->X = 25; o->Y = 25; break;
@@ -389,7 +423,9 @@ orc_env *orc_create(const orc_cfg *cfg) {
         en->destination = (int8_t *)malloc(N * XY);
         memset(en->destination, 1, N * XY); /* abstract_map.py:24 */
         en->past_global_agents = (int8_t *)calloc((size_t)(P > 0 ? P : 1) * N * XY, 1);
-        for (int i = 0; i < N; ++i) en->init_xys_order[i] = i; /* default_environment.py:33 */
+        for (int i = 0; i < ORC_MAX_AGENTS; ++i) en->init_xys_order[i] = i; /* default_environment.py:33 */
+        en->obstacle[0][0] = (int16_t)(o->X / 2); en->obstacle[0][1] = 1; /* dynamic_simple_map.py:13-17 */
+        en->obstacle[1][0] = (int16_t)(o->X / 2); en->obstacle[1][1] = (int16_t)(o->Y / 2);
     }
     return o;
 }
@@ -452,7 +488,7 @@ static void generate_one_object(orc_env *o, int e, uint32_t tick, uint32_t strea
         int agents = 0, objects = 0;
         for (int k = 0; k < N; ++k) agents += AM(o, en, k, x, y);
         for (int t = 0; t < T; ++t) objects += OM(o, en, t, x, y);
-        if (o->wall[x][y] == 0 && agents == 0 && objects == 0 && OA(o, object_type, x, y) == 1) {
+        if (env_wall(o, en, x, y) == 0 && agents == 0 && objects == 0 && OA(o, object_type, x, y) == 1) {
             OM(o, en, object_type, x, y) = 1;
             if (o->hm) HM_OBJECTS(o, object_type, x, y) += 1; /* :145 */
             en->counters[0] += 1;
@@ -730,7 +766,8 @@ static void reset_one(orc_env *o, int e, uint32_t tick, const orc_out *out) {
     reset_destination_area(o, e, tick);
     if (o->cfg.shuffle_init_xys) { /* :97-98 */
         uint32_t d = 0;
-        tape_shuffle(o, e, tick, MAEXP_STREAM_INIT_PERM, &d, en->init_xys_order, N);
+        const int n_init = o->cfg.num_init_xys > N ? o->cfg.num_init_xys : N; /* :33: one entry per init_xys row */
+        tape_shuffle(o, e, tick, MAEXP_STREAM_INIT_PERM, &d, en->init_xys_order, n_init);
     }
     for (int i = 0; i < N; ++i) { /* :100-109 */
         const int ord = en->init_xys_order[i];
@@ -788,6 +825,7 @@ static void step_one(orc_env *o, int e, uint32_t tick, const int8_t *actions, co
     }
 
     /* abstract_world.py:39-47, :54-72 */
+    map_step(o, en); /* :40 */
     for (int j = 0; j < N; ++j) {
         const int id = order[j];
         int8_t force[2] = {en->action[id][0], en->action[id][1]};
@@ -802,7 +840,7 @@ static void step_one(orc_env *o, int e, uint32_t tick, const int8_t *actions, co
         }
         int nx, ny;
         coord2ind(o, next, &nx, &ny);
-        if (o->wall[nx][ny] == 1) { force[0] = force[1] = 0; en->collide_walls[id] = 1; }
+        if (env_wall(o, en, nx, ny) == 1) { force[0] = force[1] = 0; en->collide_walls[id] = 1; }
         en->xy[id][0] = (int8_t)(en->xy[id][0] + force[0]);
         en->xy[id][1] = (int8_t)(en->xy[id][1] + force[1]);
     }

@@ -19,7 +19,8 @@ extern "C" {
 
 enum { ORC_MAP_SIMPLE = 0, ORC_MAP_FOUR_ROOMS = 1, ORC_MAP_THREE_ROOMS = 2, ORC_MAP_FOUR_RECTANGLE = 3,
        ORC_MAP_CENTRAL_ROOM = 4, ORC_MAP_CENTRAL_ROOM_DESTINATION = 5, ORC_MAP_CENTRAL_ROOM_LARGE = 6,
-       ORC_MAP_CENTRAL_ROOM_LARGE_DESTINATION = 7, ORC_MAP_TWO_CENTRAL_ROOMS = 8 };
+       ORC_MAP_CENTRAL_ROOM_LARGE_DESTINATION = 7, ORC_MAP_TWO_CENTRAL_ROOMS = 8,
+       ORC_MAP_DYNAMIC_SIMPLE = 9 };
 /* core/environments/__init__.py:40-71: which reward_ind / generate_objects override runs */
 enum { ORC_ENV_DEFAULT = 0, ORC_ENV_SEQUENTIAL = 1, ORC_ENV_JUNCTIONAL = 2 };
 enum { ORC_AV_DEFAULT = 0, ORC_AV_SIMPLE = 1, ORC_AV_INDIVIDUAL = 2, ORC_AV_TRANSITION = 3, ORC_AV_INDIVIDUAL_TRANSITION = 4 };
@@ -37,7 +38,7 @@ typedef struct {
     int32_t num_agents;            /* N */
     int32_t type_objects;          /* T */
     int32_t map_id;                /* ORC_MAP_* */
-    int32_t size_x, size_y;        /* only read for ORC_MAP_SIMPLE (core/maps/__init__.py:26-39) */
+    int32_t size_x, size_y;        /* only read for ORC_MAP_SIMPLE / ORC_MAP_DYNAMIC_SIMPLE (core/maps/__init__.py:26-39) */
     int32_t visible_range;         /* V in {5,7,9} */
     int32_t past_step;             /* transition views */
     int32_t agent_view, object_view, area_mask, noise, reward_mode;
@@ -57,6 +58,8 @@ typedef struct {
     float std_distribution[ORC_MAX_RINGS];
     float noise_threshold[ORC_MAX_RINGS];  /* fp32(std*ratio), dist_observation_noise.py:60-66 */
     int32_t env_kind;              /* ORC_ENV_* */
+    int32_t num_init_xys;          /* len(config.init_xys) >= num_agents (0: num_agents): default_environment.py:33,97-98
+                                    * shuffles ALL entries and hands the first num_agents of the order to the agents */
 } orc_cfg;
 
 typedef struct orc_env orc_env;

@@ -27,6 +27,7 @@ def run_case(cfg, steps, noise_kind, env_id=ENV_ID, seed=5):
     shape = (ref.N, ref.C, ref.V, ref.V)
     rec = {k: [] for k in KEYS}
     rec.update(ticks=[], is_reset=[], noise=[], pos=[], state_objects=[], counters=[])
+    tables = ref.tables()  # before the first step: dynamic_simple moves its obstacle cells in wall_matrix afterwards
 
     def tape():
         return rng.standard_normal(shape).astype(np.float32) if noise_kind == "normal" else None
@@ -51,14 +52,15 @@ def run_case(cfg, steps, noise_kind, env_id=ENV_ID, seed=5):
             tick += 1
             t = tape(); push(ref.reset(tick, t), tick, 1, t)
     arrays = {k: np.stack(v) for k, v in rec.items() if len(v)}
-    arrays["tables_wall"], arrays["tables_area"], arrays["tables_los"] = ref.tables()
+    arrays["tables_wall"], arrays["tables_area"], arrays["tables_los"] = tables
     return arrays
 
 
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     only = set(sys.argv[1:])
-    manifest = {}
+    mpath = os.path.join(GOLDEN, "MANIFEST.json")
+    manifest = json.load(open(mpath))["files"] if only and os.path.exists(mpath) else {}
     for name, (cfg, steps, noise_kind, okw) in cases().items():
         if only and name not in only:
             continue
@@ -72,9 +74,8 @@ def main():
                             oracle_kwargs=json.dumps(okw), env_id=ENV_ID, **arrays)
         manifest[name] = hashlib.sha256(open(path, "rb").read()).hexdigest()[:16]
         print(name, os.path.getsize(path), "bytes", arrays["obs"].shape)
-    if not only:
-        with open(os.path.join(GOLDEN, "MANIFEST.json"), "w") as f:
-            json.dump({"generator": "python -m oracle.make_golden", "reference": "Yoshi-0921/MAEXP (live import)",
+    with open(mpath, "w") as f:
+        json.dump({"generator": "python -m oracle.make_golden", "reference": "Yoshi-0921/MAEXP (live import)",
                        "files": manifest}, f, indent=1)
 
 

@@ -18,7 +18,8 @@ _LIB = None
 
 MAX_AGENTS, MAX_TYPES, MAX_RINGS = 16, 8, 4
 MAPS = {"simple": 0, "four_rooms": 1, "three_rooms": 2, "four_rectangle": 3, "central_room": 4,
-        "central_room_destination": 5, "central_room_large": 6, "central_room_large_destination": 7, "two_central_rooms": 8}
+        "central_room_destination": 5, "central_room_large": 6, "central_room_large_destination": 7, "two_central_rooms": 8,
+        "dynamic_simple": 9}
 AGENT_VIEWS = {"default": 0, "simple": 1, "individual": 2, "transition": 3, "individual_transition": 4}
 OBJECT_VIEWS = {"default": 0, "simple": 1, "object_types": 2}
 MASKS = {"local": 0, "relative": 1, "merged": 2}
@@ -41,6 +42,7 @@ class OrcCfg(C.Structure):
         ("task_mask", C.c_int32 * MAX_AGENTS), ("task_order", (C.c_int32 * MAX_TYPES) * MAX_AGENTS),
         ("flip_noise_range", C.c_float * MAX_RINGS), ("std_distribution", C.c_float * MAX_RINGS),
         ("noise_threshold", C.c_float * MAX_RINGS), ("env_kind", C.c_int32),
+        ("num_init_xys", C.c_int32),
     ]
 
 
@@ -136,6 +138,7 @@ def make_cfg(cfg, num_envs=1, auto_reset=False, first_global_env_id=0, shared_ma
     c.auto_reset = int(bool(auto_reset))
     c.seed = int(_get(cfg, "seed")) & 0xFFFFFFFF
     c.first_global_env_id = first_global_env_id
+    c.num_init_xys = len(_get(cfg, "init_xys"))
     for i, xy in enumerate(_get(cfg, "init_xys")):
         c.init_xys[i][0], c.init_xys[i][1] = int(xy[0]), int(xy[1])
     tasks = _get(cfg, "agent_tasks")

@@ -37,7 +37,8 @@ def _compare(a, b, keys, what):
 BATCH_CASES = ["cfg1_simple_mlp", "cfg2_four_rooms_transition_flip_sharedmean", "cfg3_three_rooms",
                "cfg4_four_rectangle_merged_types", "cfg5_four_rooms_n8", "indtrans_t2_v9_tasks",
                "no_keep_small", "relative_transparent", "simple_views_v5", "sequential_central_room_t3",
-               "junctional_central_room_t5_merged", "two_central_rooms_t2_n12", "central_room_large_destination_v9"]
+               "junctional_central_room_t5_merged", "two_central_rooms_t2_n12", "central_room_large_destination_v9",
+               "dynamic_simple_20", "dynamic_simple_small_t2"]
 
 
 @pytest.mark.parametrize("name", BATCH_CASES)
@@ -59,6 +60,29 @@ def test_cuda_batch_matches_oracle(name, num_envs):
         _compare(sa, sb, ("pos", "objects", "counters", "steps", "destination"), f"{name} state tick {tick}")
     st = cuda.env.stats()
     assert st["error_flag"] == 0 and st["resets"] >= num_envs * 2  # initial reset + one auto-reset each
+
+
+def test_dynamic_obstacles_out_of_lockstep():
+    """dynamic_simple with episodes that end by exhaustion at different times: every environment keeps its own
+    world-step count (a reset consumes a tick without moving the obstacles, dynamic_simple_map.py:29-63 /
+    abstract_map.py:32-36), so the obstacle cells differ between environments of one launch."""
+    from maexp_b200.config import make_config
+    cfg = make_config(map=dict(name="dynamic_simple", SIZE_X=10, SIZE_Y=10), keep_objects_num=False, num_objects=2,
+                      num_agents=6, max_episode_length=40,
+                      init_xys=[[1, 1], [-1, 1], [1, -1], [-1, -1], [2, 2], [-2, -2]])
+    E, gid0 = 150, 77
+    cuda = CudaBackend(cfg, E, first_global_env_id=gid0, auto_reset=True, extras=True)
+    orc = Oracle(cfg, E, auto_reset=True, first_global_env_id=gid0, extras=True)
+    keys = ("obs", "rewards", "dones", "was_reset", "coordinates", "objects")
+    _compare(cuda.reset(0), orc.reset(0), keys, "reset")
+    resets_per_tick = set()
+    for tick in range(1, 160):
+        a, b = cuda.step(tick), orc.step(tick, threads=4)
+        _compare(a, b, keys, f"tick {tick}")
+        resets_per_tick.add(int(a["was_reset"].sum()))
+        if tick % 20 == 0:
+            _compare(cuda.state(), orc.state(), ("pos", "objects", "counters", "steps"), f"state tick {tick}")
+    assert len(resets_per_tick) > 3 and cuda.env.stats()["error_flag"] == 0  # the environments did drift apart
 
 
 @pytest.mark.parametrize("epw", [8, 16, 32])

@@ -90,3 +90,39 @@ def test_central_room_maps_match_oracle(name, X, Y, V):
         assert np.array_equal(world.map.wall_matrix, wall)
         assert np.array_equal(world.map.objects_area_matrix, area)
         assert np.array_equal(generate_observation_area_mask(cfg, world), los)
+
+
+def _triangle_cells(k, X, Y):
+    """The step kernel's closed form of the two dynamic_simple obstacle cells after k world steps
+    (env_kernel.cuh `place_obstacles`)."""
+    L0, L1 = Y - 3, X - 3
+    m0, m1 = k % (2 * L0), (k + X // 2 - 1) % (2 * L1)
+    return [[X // 2, 1 + (m0 if m0 <= L0 else 2 * L0 - m0)], [1 + (m1 if m1 <= L1 else 2 * L1 - m1), Y // 2]]
+
+
+@pytest.mark.parametrize("X,Y", [(20, 20), (10, 10), (9, 14), (5, 5)])
+def test_dynamic_simple_obstacles_closed_form(X, Y):
+    """dynamic_simple_map.py:29-63: the host restatement of the shuttle rule, the kernel's closed form and (in the
+    build container) the reference's own map agree for several periods; the fixtures' wall table is the initial one."""
+    cfg = make_config(map=dict(name="dynamic_simple", SIZE_X=X, SIZE_Y=Y), num_agents=1, init_xys=[[1, 1]])
+    m = generate_map(cfg)
+    ref = None
+    from oracle import ref_runner as rr
+    if rr.available():  # build container only: the reference's own class next to ours
+        import importlib
+        rr._import_reference()
+        ref = importlib.import_module("core.maps.dynamic_simple_map").DynamicSimpleMap(cfg, X, Y)
+    if ref is not None:
+        assert np.array_equal(ref.wall_matrix, m.wall_matrix)
+    for k in range(1, 5 * (X + Y)):
+        m.step()
+        assert m.obstacles_pos == _triangle_cells(k, X, Y), k
+        want = np.zeros((X, Y), np.int8)
+        want[[0, X - 1], :] = 1
+        want[:, [0, Y - 1]] = 1
+        for x, y in m.obstacles_pos:
+            want[x, y] = 1
+        assert np.array_equal(m.wall_matrix, want)
+        if ref is not None:
+            ref.step()
+            assert np.array_equal(ref.wall_matrix, m.wall_matrix), k
