@@ -71,6 +71,9 @@ typedef struct {
                                   * between y = 1 and Y-2, the second along row Y/2 between x = 1 and X-2 -- and that
                                   * keep their place across resets; moves and object respawns see the moved cells,
                                   * the line-of-sight table stays the one of the initial layout, as in the reference */
+    int32_t num_init_xys;        /* len(config.init_xys), num_agents..16 (0: num_agents).  default_environment.py:33,97-98
+                                  * shuffles the order of ALL rows at every reset (the order persists from episode to
+                                  * episode) and agent i starts on row order[i]; rows past num_agents are spare cells */
 } maexp_env_cfg;
 
 /* Static per-map tables in the REFERENCE's layout, HOST pointers; packed to bit rows and

@@ -28,7 +28,7 @@ class EnvCfg(C.Structure):
         ("task_order", (C.c_int32 * MAX_TYPES) * MAX_AGENTS),
         ("flip_noise_range", C.c_float * MAX_RINGS), ("std_distribution", C.c_float * MAX_RINGS),
         ("noise_threshold", C.c_float * MAX_RINGS), ("env_kind", C.c_int32),
-        ("dynamic_obstacles", C.c_int32),
+        ("dynamic_obstacles", C.c_int32), ("num_init_xys", C.c_int32),
     ]
 
 

@@ -49,19 +49,20 @@ def validate(config, world_map):
         raise ValueError("observation noise with observation_area_mask=relative fails in the reference (appendix C)")
     if len(config.init_xys) < N or len(config.agent_tasks) < N:
         raise ValueError("init_xys / agent_tasks shorter than num_agents")
-    if config.shuffle_init_xys and len(config.init_xys) != N:
-        # default_environment.py:33,97-98 shuffles ALL len(init_xys) entries and uses the first num_agents
-        raise ValueError("shuffle_init_xys with more init_xys than agents is not supported")
+    if config.shuffle_init_xys and len(config.init_xys) > _lib.MAX_AGENTS:
+        # default_environment.py:33,97-98 shuffles ALL len(init_xys) rows and uses the first num_agents of the order
+        raise ValueError(f"shuffle_init_xys supports at most {_lib.MAX_AGENTS} init_xys rows")
     env_name = config.environment
     if env_name == "junctional" and T < 5:
         raise ValueError("environment=junctional places object types 2, 3 and 4 (junctional_environment.py:44-51): type_objects >= 5")
     cells = set()
-    for xy in list(config.init_xys)[:N]:
+    rows = list(config.init_xys) if config.shuffle_init_xys else list(config.init_xys)[:N]
+    for xy in rows:
         ix, iy = world_map.coord2ind(xy)
         if world_map.wall_matrix[ix, iy]:
             raise ValueError(f"init_xys {list(xy)} is on a wall")
         cells.add((int(ix), int(iy)))
-    if len(cells) < N:
+    if len(cells) < len(rows):
         raise ValueError("init_xys must be distinct")
     free = (world_map.wall_matrix == 0)
     for t in range(T if env_name not in ("sequential", "junctional") else 1):  # those two only ever sample type 0
@@ -109,7 +110,9 @@ class BatchedEnvironment:
         cfg.random_destinations = int(bool(self.map.RANDOM_DESTINATIONS))
         cfg.seed = int(config.seed) & 0xFFFFFFFF
         cfg.first_global_env_id = int(first_global_env_id)
-        for i, xy in enumerate(list(config.init_xys)[:self.N]):
+        rows = list(config.init_xys) if config.shuffle_init_xys else list(config.init_xys)[:self.N]
+        cfg.num_init_xys = len(rows)
+        for i, xy in enumerate(rows):
             ix, iy = self.map.coord2ind(xy)
             cfg.init_xys[i][0], cfg.init_xys[i][1] = int(ix), int(iy)
         for i in range(self.N):

@@ -93,8 +93,8 @@ __global__ void set_state_kernel(const EnvParams p, const int8_t *pos, const int
 __global__ void init_state_kernel(const EnvParams p) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
+    for (int k = 0; k < p.n_init; ++k) p.init_perm[(size_t)env * p.n_init + k] = (uint8_t)k;  // default_environment.py:33
     for (int k = 0; k < p.N; ++k) {
-        p.init_perm[(size_t)env * p.N + k] = (uint8_t)k;  // default_environment.py:33
         p.dest_sel[(size_t)env * p.N + k] = 0;
         p.pos[(size_t)env * p.N + k] = p.init_xy[k];
     }
@@ -214,6 +214,7 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     if (X < 3 || X > 255 || Y < 3 || Y + cfg->visible_range / 2 > 32)
         return fail("maexp_env_create: map must satisfy 3<=X<=255, 3<=Y and Y + visible_range/2 <= 32 (32-bit grid rows)");
     if (V != 5 && V != 7 && V != 9) return fail("maexp_env_create: visible_range must be 5, 7 or 9");
+    if (cfg->num_init_xys > MAEXP_MAX_AGENTS) return fail("maexp_env_create: at most 16 init_xys rows");
     if (cfg->dynamic_obstacles && (X < 5 || Y < 5)) return fail("maexp_env_create: dynamic_obstacles needs a map of at least 5 x 5");
     if (M < 1 || M > 15) return fail("maexp_env_create: num_destinations must be in 1..15");
     if (!tb->wall || !tb->objects_area || !tb->noise_area || !tb->destination || !tb->los)
@@ -271,8 +272,9 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     p.shuffle_init = cfg->shuffle_init_xys; p.auto_reset = cfg->auto_reset; p.random_dest = cfg->random_destinations;
     p.seed = cfg->seed; p.gid0 = cfg->first_global_env_id;
     p.env_kind = cfg->env_kind;
+    p.n_init = cfg->num_init_xys > N ? cfg->num_init_xys : N;
+    for (int i = 0; i < p.n_init; ++i) p.init_xy[i] = (uint16_t)(cfg->init_xys[i][0] | (cfg->init_xys[i][1] << 8));
     for (int i = 0; i < N; ++i) {
-        p.init_xy[i] = (uint16_t)(cfg->init_xys[i][0] | (cfg->init_xys[i][1] << 8));
         p.no_task[i] = cfg->task_mask[i] < 0;
         for (int q = 0; q < MAEXP_MAX_TYPES; ++q) p.task_order[i][q] = (int8_t)cfg->task_order[i][q];
     }
@@ -322,7 +324,7 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     rc |= dev_alloc(h, &p.step, (size_t)E);
     rc |= dev_alloc(h, &p.pending, (size_t)E);
     rc |= dev_alloc(h, &p.counters, (size_t)E * 4);
-    rc |= dev_alloc(h, &p.init_perm, (size_t)E * N);
+    rc |= dev_alloc(h, &p.init_perm, (size_t)E * p.n_init);
     rc |= dev_alloc(h, &p.dest_sel, (size_t)E * N);
     rc |= dev_alloc(h, &p.past, (size_t)E * (p.P ? p.P : 1) * N);
     rc |= dev_alloc(h, &p.stats, 2);

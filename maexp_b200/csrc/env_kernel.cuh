@@ -21,6 +21,7 @@ struct EnvParams {
     int agent_view, object_view, merged, noise, reward_mode, shared_max_is_mean;
     int fast3;  // 3 channels (total agents, all objects, area) and V <= 7: compile-time bit assembly
     int L, num_objects, keep, shuffle_init, auto_reset, random_dest, env_kind;
+    int n_init;  // len(config.init_xys) >= N: the start-cell order has one entry per init_xys row
     uint32_t seed, gid0, tick;
     int force_reset;
     const uint8_t *env_mask;
@@ -295,11 +296,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                 for (int k = 0; k < N; ++k) p.dest_sel[(size_t)env * N + k] = (uint8_t)nib(dsel, k);
             }
             uint64_t perm = 0;  // default_environment.py:33,97-98 (persists across episodes)
-            for (int k = 0; k < N; ++k) perm |= (uint64_t)p.init_perm[(size_t)env * N + k] << (4 * k);
+            const int NI = p.n_init;  // all rows are shuffled, the first N of the order are used
+            for (int k = 0; k < NI; ++k) perm |= (uint64_t)p.init_perm[(size_t)env * NI + k] << (4 * k);
             if (p.shuffle_init) {
                 uint32_t d = 0;
-                perm = fisher_yates(perm, N, p.seed, gid, p.tick, kStreamInitPerm, d);
-                for (int k = 0; k < N; ++k) p.init_perm[(size_t)env * N + k] = (uint8_t)nib(perm, k);
+                perm = fisher_yates(perm, NI, p.seed, gid, p.tick, kStreamInitPerm, d);
+                for (int k = 0; k < NI; ++k) p.init_perm[(size_t)env * NI + k] = (uint8_t)nib(perm, k);
             }
             for (int k = 0; k < N; ++k) mypos[k * EPW] = p.init_xy[nib(perm, k)];
             for (int x = 0; x < X; ++x) agrid[x] = 0;

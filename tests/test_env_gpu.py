@@ -38,7 +38,7 @@ BATCH_CASES = ["cfg1_simple_mlp", "cfg2_four_rooms_transition_flip_sharedmean", 
                "cfg4_four_rectangle_merged_types", "cfg5_four_rooms_n8", "indtrans_t2_v9_tasks",
                "no_keep_small", "relative_transparent", "simple_views_v5", "sequential_central_room_t3",
                "junctional_central_room_t5_merged", "two_central_rooms_t2_n12", "central_room_large_destination_v9",
-               "dynamic_simple_20", "dynamic_simple_small_t2"]
+               "dynamic_simple_20", "dynamic_simple_small_t2", "shuffle_spare_init_xys"]
 
 
 @pytest.mark.parametrize("name", BATCH_CASES)
