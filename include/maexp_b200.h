@@ -250,6 +250,10 @@ typedef struct {
     int32_t iqn_trunk;        /* MAEXP_LEARNER_IQN only: which network produces the state embedding, MAEXP_IQN_TRUNK_* */
     int32_t optimizer;        /* generate_optimizer (optimizers/__init__.py:17-42): 0 = optim.RMSprop, 1 = optim.Adam */
     float beta1, beta2;       /* Adam betas (configs/opt/adam.yaml); learning_rate and eps are shared */
+    int32_t attention_hard;   /* 1: model.attention == "hard" -- the transformer blocks are HardShrinkBlock
+                                 (hard_shrink_attention.py:13-105; DA3_IQN / MergedDA3_IQN da3_iqn.py:118-122,245, DA6 da6.py:67):
+                                 softmax weights <= af_lambd are zeroed before they multiply V and in the exported maps */
+    float af_lambd;           /* model.af_lambd (nn.Hardshrink lambd), read when attention_hard */
 } maexp_learner_cfg;
 
 /* state-embedding producer under the IQN head (brain iqn / da3_iqn, iqn_brain.py:60-115, da3_iqn_brain.py:14-54) */

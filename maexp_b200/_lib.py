@@ -59,7 +59,7 @@ class LearnerCfg(C.Structure):
                [(n, C.c_int32) for n in ("num_quantiles_dash", "num_cosines", "embed_dim", "num_heads", "mlp_hidden",
                                           "block_loop", "area_mask", "size_x", "size_y", "patch_size", "local_patch_size",
                                           "relative_patch_size", "iqn_trunk", "optimizer")] + \
-               [(n, C.c_float) for n in ("beta1", "beta2")]
+               [(n, C.c_float) for n in ("beta1", "beta2")] + [("attention_hard", C.c_int32), ("af_lambd", C.c_float)]
 
 
 LEARNER_KINDS = {"dqn_conv_mlp": 0, "c51": 1, "qr": 2, "dqn_mlp": 3, "iqn": 4, "da3": 5, "da6": 6}

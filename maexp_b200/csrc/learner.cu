@@ -849,8 +849,12 @@ __global__ void layernorm_bwd_kernel(const float *dy, const float *x, long long 
 constexpr int kMaxTokens = 96, kMaxHeadDim = 32;
 
 // Attention.forward (vit.py:116-132) for one (group, sample, head) per block; thread t owns query token t
+// `shrink`: HardShrinkAttention (hard_shrink_attention.py:52-80) zeroes the softmax weights that are not above
+// model.af_lambd before they multiply V; the plain Attention passes -1 (every weight is >= 0 and kept).  `probs`
+// keeps the softmax output itself, which the backward pass needs.
 __global__ void __launch_bounds__(128) da3_attn_fwd_kernel(const float *qkv, float *probs, float *out, int B, int Tn, int E,
-                                                           int heads, float scale, long long gQ, long long gPr, long long gO) {
+                                                           int heads, float scale, long long gQ, long long gPr, long long gO,
+                                                           float shrink) {
     __shared__ float sk[kMaxTokens][kMaxHeadDim + 1], sv[kMaxTokens][kMaxHeadDim + 1];
     const int g = blockIdx.z, b = blockIdx.y, h = blockIdx.x, dh = E / heads, t = threadIdx.x;
     const float *base = qkv + (size_t)g * gQ + (size_t)b * Tn * 3 * E;
@@ -881,8 +885,9 @@ __global__ void __launch_bounds__(128) da3_attn_fwd_kernel(const float *qkv, flo
     float o[kMaxHeadDim];
     for (int d = 0; d < dh; ++d) o[d] = 0.0f;
     for (int u = 0; u < Tn; ++u) {
-        const float pu = __fdiv_rn(pr[u], se);
-        pr[u] = pu;
+        const float pn = __fdiv_rn(pr[u], se);
+        pr[u] = pn;
+        const float pu = pn > shrink ? pn : 0.0f;
         for (int d = 0; d < dh; ++d) o[d] = __fadd_rn(o[d], __fmul_rn(pu, sv[u][d]));
     }
     float *orow = out + (size_t)g * gO + ((size_t)b * Tn + t) * E + h * dh;
@@ -892,7 +897,7 @@ __global__ void __launch_bounds__(128) da3_attn_fwd_kernel(const float *qkv, flo
 // The same attention for the large acting batches: identical arithmetic, but the score rows stay in shared memory instead
 // of using the (then unneeded) probability buffer in HBM as scratch — 0.3 GB less traffic per 8192 observations.
 __global__ void __launch_bounds__(96) da3_attn_infer_kernel(const float *qkv, float *out, int B, int Tn, int E, int heads,
-                                                            float scale, long long gQ, long long gO) {
+                                                            float scale, long long gQ, long long gO, float shrink) {
     __shared__ float sk[kMaxTokens][kMaxHeadDim + 1], sv[kMaxTokens][kMaxHeadDim + 1];
     extern __shared__ float ss[];  // [Tn][Tn + 1] scores / probabilities, one row per thread
     const int g = blockIdx.z, b = blockIdx.y, h = blockIdx.x, dh = E / heads, t = threadIdx.x;
@@ -924,7 +929,8 @@ __global__ void __launch_bounds__(96) da3_attn_infer_kernel(const float *qkv, fl
     float o[kMaxHeadDim];
     for (int d = 0; d < dh; ++d) o[d] = 0.0f;
     for (int u = 0; u < Tn; ++u) {
-        const float pu = __fdiv_rn(pr[u], se);
+        const float pn = __fdiv_rn(pr[u], se);
+        const float pu = pn > shrink ? pn : 0.0f;
         for (int d = 0; d < dh; ++d) o[d] = __fadd_rn(o[d], __fmul_rn(pu, sv[u][d]));
     }
     float *orow = out + (size_t)g * gO + ((size_t)b * Tn + t) * E + h * dh;
@@ -934,7 +940,7 @@ __global__ void __launch_bounds__(96) da3_attn_infer_kernel(const float *qkv, fl
 // backward of the attention core: d(out) -> d(qkv); two phases with a barrier, fixed summation order
 __global__ void __launch_bounds__(128) da3_attn_bwd_kernel(const float *qkv, const float *probs, const float *dout,
                                                            float *dqkv, int B, int Tn, int E, int heads, float scale,
-                                                           long long gQ, long long gPr, long long gO) {
+                                                           long long gQ, long long gPr, long long gO, float shrink) {
     extern __shared__ float smem_attn[];
     const int g = blockIdx.z, b = blockIdx.y, h = blockIdx.x, dh = E / heads, t = threadIdx.x;
     float *sq = smem_attn;                  // [Tn][dh]
@@ -955,11 +961,13 @@ __global__ void __launch_bounds__(128) da3_attn_bwd_kernel(const float *qkv, con
     const float *pr = probs + (size_t)g * gPr + (((size_t)b * heads + h) * Tn) * Tn;
     float *dq_out = dqkv + (size_t)g * gQ + (size_t)b * Tn * 3 * E;
     if (t < Tn) {
-        // dP[t,u] = dO_t . v_u ; dS = P * (dP - sum_u dP*P) ; dq_t = scale * sum_u dS[t,u] k_u
+        // dP[t,u] = dO_t . v_u where P[t,u] > shrink, else 0 (Hardshrink passes the gradient of the kept weights only);
+        // dS = P * (dP - sum_u dP*P) ; dq_t = scale * sum_u dS[t,u] k_u
         float dot = 0.0f;
         for (int u = 0; u < Tn; ++u) {
             float dp = 0.0f;
             for (int d = 0; d < dh; ++d) dp = __fadd_rn(dp, __fmul_rn(sdo[t * dh + d], sv[u * dh + d]));
+            if (!(pr[t * Tn + u] > shrink)) dp = 0.0f;
             sds[t * Tn + u] = dp;
             dot = __fadd_rn(dot, __fmul_rn(dp, pr[t * Tn + u]));
         }
@@ -979,7 +987,7 @@ __global__ void __launch_bounds__(128) da3_attn_bwd_kernel(const float *qkv, con
         float dk[kMaxHeadDim], dv[kMaxHeadDim];
         for (int d = 0; d < dh; ++d) dk[d] = dv[d] = 0.0f;
         for (int tq = 0; tq < Tn; ++tq) {
-            const float ds = sds[tq * Tn + u], pu = pr[tq * Tn + u];
+            const float ds = sds[tq * Tn + u], pn = pr[tq * Tn + u], pu = pn > shrink ? pn : 0.0f;
             for (int d = 0; d < dh; ++d) {
                 dk[d] = __fadd_rn(dk[d], __fmul_rn(ds, sq[tq * dh + d]));
                 dv[d] = __fadd_rn(dv[d], __fmul_rn(pu, sdo[tq * dh + d]));
@@ -990,6 +998,12 @@ __global__ void __launch_bounds__(128) da3_attn_bwd_kernel(const float *qkv, con
             dq_out[(size_t)u * 3 * E + 2 * E + h * dh + d] = dv[d];
         }
     }
+}
+
+// nn.Hardshrink on non-negative softmax weights, in place (attention-map export of the hard-shrink blocks)
+__global__ void hard_shrink_kernel(float *p, long long n, float shrink) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !(p[i] > shrink)) p[i] = 0.0f;
 }
 
 // nn.GELU() (exact erf form) forward / backward
@@ -1139,6 +1153,7 @@ struct maexp_learner {
     bool fused_trunk_acts = false; // the last training pass kept p / arg only: trunk_backward builds col1 / col2 itself
     int last_q_batch = 0;
     int E_, heads_, Fm, L_, Tn;   // DA3 / DA6: embed_dim, num_heads, mlp hidden, block_loop, max tokens of any stack
+    float attn_shrink = -1.0f;    // model.af_lambd of HardShrinkAttention, -1: plain softmax attention
     long long o_nfw, o_nfb, o_hw, o_hb, o_f1w = 0, o_f1b = 0;  // shared final norm, drl_head, DA6 fc1
     struct BlockLayout { long long n1w, n1b, qkvw, projw, projb, n2w, n2b, f1w, f1b, f2w, f2b; };
     int Nq, Nd, ncos, rows_max;  // IQN: quantiles, target quantiles, cosines, B * max(Nq, Nd)
@@ -2191,10 +2206,10 @@ void vit_forward(maexp_learner *h, cudaStream_t st, const float *params, maexp_l
         if (g_inference_tc && B > kAttnMapsBatch) {  // acting batches: no attention maps kept (maexp_learner_attention refuses)
             cudaFuncSetAttribute(da3_attn_infer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024);
             da3_attn_infer_kernel<<<dim3(h->heads_, B, G), (Tn + 31) / 32 * 32, sizeof(float) * Tn * (Tn + 1), st>>>(
-                k.qkv, k.ao, B, Tn, E, h->heads_, scale, Rm * 3 * E, Rm * E);
+                k.qkv, k.ao, B, Tn, E, h->heads_, scale, Rm * 3 * E, Rm * E, h->attn_shrink);
         } else {
             da3_attn_fwd_kernel<<<dim3(h->heads_, B, G), 128, 0, st>>>(k.qkv, k.probs, k.ao, B, Tn, E, h->heads_, scale, Rm * 3 * E,
-                                                                       Bmax * h->heads_ * Tn * Tn, Rm * E);
+                                                                       Bmax * h->heads_ * Tn * Tn, Rm * E, h->attn_shrink);
         }
         cudaMemcpyAsync(k.x1, x, sizeof(float) * (size_t)G * Rm * E, cudaMemcpyDeviceToDevice, st);
         gemm(st, G, k.ao, params + w.projw, k.x1, params + w.projb, rows, E, E, E, 1, 1, E, E, 1, Rm * E, P, Rm * E, P, 0,
@@ -2254,7 +2269,8 @@ void vit_backward(maexp_learner *h, cudaStream_t st, maexp_learner::VitStack &s,
         gemm(st, G, h->da_dx, W + w.projw, h->da_dao, nullptr, rows, E, E, E, 1, E, 1, E, 1, Rm * E, P, Rm * E, 0);
         const size_t smem = sizeof(float) * (size_t)(4 * Tn * (E / h->heads_) + Tn * Tn);
         da3_attn_bwd_kernel<<<dim3(h->heads_, B, G), 128, smem, st>>>(k.qkv, k.probs, h->da_dao, h->da_dqkv, B, Tn, E, h->heads_,
-                                                                      scale, Rm * 3 * E, (long long)B * h->heads_ * Tn * Tn, Rm * E);
+                                                                      scale, Rm * 3 * E, (long long)B * h->heads_ * Tn * Tn, Rm * E,
+                                                                      h->attn_shrink);
         gemm(st, G, h->da_dqkv, k.n1, grads + w.qkvw, nullptr, 3 * E, E, rows, 1, 3 * E, E, 1, E, 1, Rm * 3 * E, Rm * E, P, 0);
         gemm(st, G, h->da_dqkv, W + w.qkvw, h->da_dn, nullptr, rows, E, 3 * E, 3 * E, 1, E, 1, E, 1, Rm * 3 * E, P, Rm * E, 0);
         ln_bwd(h->da_dn, x_in, E, Rm * E, w.n1w, k.m1, k.r1, h->da_dx, E, Rm * E, 1, rows, Rm);
@@ -2670,6 +2686,10 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     }
     if (h->da3) {
         h->E_ = cfg->embed_dim; h->heads_ = cfg->num_heads; h->Fm = cfg->mlp_hidden; h->L_ = cfg->block_loop;
+        if (cfg->attention_hard) {
+            if (!(cfg->af_lambd >= 0.0f)) { delete h; return fail("maexp_learner_create: af_lambd must be >= 0 (nn.Hardshrink)"); }
+            h->attn_shrink = cfg->af_lambd;
+        }
         h->H1 = h->Hp = h->H2 = 0;
         h->D = h->E_;
         auto set_stack = [&](maexp_learner::VitStack &s, int cin, int hin, int win, int ps) {
@@ -3083,6 +3103,11 @@ int maexp_learner_attention(maexp_learner *h, int stack, int layer, int batch, f
     const size_t per = (size_t)h->heads_ * s.Tn * s.Tn * sizeof(float);  // one sample
     MAEXP_CUDA_L(cudaMemcpy2DAsync(out, per * batch, s.a[1].blk[layer].probs, per * h->B, per * batch, h->G,
                                    cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    if (h->attn_shrink >= 0.0f) {  // HardShrinkAttention.forward_attn returns the weights after the shrink
+        const long long n = (long long)h->G * batch * h->heads_ * s.Tn * s.Tn;
+        hard_shrink_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, h->attn_shrink);
+        MAEXP_CUDA_L(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -6,6 +6,7 @@ For each brain: initial state_dict, a synthetic batch, the loss `brain.learn` re
 network's Q-values before the update and the online weights after 2 updates.  TEST INFRASTRUCTURE.
 """
 import os
+import sys
 
 import numpy as np
 import torch
@@ -62,7 +63,17 @@ def configs():
         c = view(mask, "iqn", "iqn", num_quantiles=4, num_quantiles_dash=4, num_cosines=4)
         c["objects_channel"], c["agents_channel"] = False, False
         return c
-    return {"relative_iqn": (conv_iqn("relative"), [4, *SIZE]), "merged_iqn": (conv_iqn("merged"), [4, *SIZE]),
+    # HardShrinkBlock variants (model.attention == "hard", hard_shrink_attention.py): af_lambd near the mean attention
+    # weight of the 26- and 21-token stacks so that a good share of the weights is cut
+    da6_hard = da6.merged_with()
+    da6_hard["model"] = dict(da6.model, attention="hard", af_lambd=0.04)
+    mda3_iqn_hard = attn_iqn("merged", "da3_iqn")
+    mda3_iqn_hard["model"] = dict(mda3_iqn_hard.model, attention="hard", af_lambd=0.04)
+    da3_iqn_hard = attn_iqn("local", "da3_iqn")
+    da3_iqn_hard["model"] = dict(da3_iqn_hard.model, attention="hard", af_lambd=0.04)
+    hard = {"da6_hard": (da6_hard, [4, *SIZE]), "merged_da3_iqn_hard": (mda3_iqn_hard, [4, *SIZE]),
+            "da3_iqn_hard": (da3_iqn_hard, [4, VIEW, VIEW])}
+    return {**hard, "relative_iqn": (conv_iqn("relative"), [4, *SIZE]), "merged_iqn": (conv_iqn("merged"), [4, *SIZE]),
             "relative_da3": (rda3, [4, *SIZE]), "relative_da3_iqn": (rda3_iqn, [4, *SIZE]),
             "da3_iqn": (attn_iqn("local", "da3_iqn"), [4, VIEW, VIEW]), "merged_da3_iqn": (attn_iqn("merged", "da3_iqn"), [4, *SIZE]),
             "da6_iqn": (attn_iqn("merged", "da6_iqn"), [4, *SIZE]),
@@ -95,7 +106,11 @@ def main():
     rr._import_reference()
     from core.agents.brains import generate_brain
     os.makedirs(GOLDEN, exist_ok=True)
-    for kind, (cfg, shape) in configs().items():
+    only = set(sys.argv[1:])
+    for fixture, (cfg, shape) in configs().items():
+        if only and fixture not in only:
+            continue
+        kind = fixture[:-5] if fixture.endswith("_hard") else fixture  # the fixture's network family
         torch.manual_seed(921)
         brain = generate_brain(config=rr.to_dictconfig(cfg), obs_shape=shape, act_size=4)
         masked = kind in ("relative_conv_mlp", "merged_conv_mlp", "merged_da3", "da6", "merged_da3_iqn", "da6_iqn",
@@ -179,10 +194,11 @@ def main():
                 arrays[f"taus/{u}/taus"], arrays[f"taus/{u}/sel"], arrays[f"taus/{u}/dash"] = (
                     drawn[3 * u].numpy(), drawn[3 * u + 1].numpy(), drawn[3 * u + 2].numpy())
             arrays["tau0"] = tau0.numpy()
-        path = os.path.join(GOLDEN, f"learner_{kind}.npz")
+        path = os.path.join(GOLDEN, f"learner_{fixture}.npz")
         np.savez_compressed(path, losses=np.array(losses, np.float64), q0=q0.numpy(), shape=np.array(shape),
-                            gamma=float(cfg.gamma), area_mask=cfg.observation_area_mask, **arrays)
-        print(kind, losses, os.path.getsize(path), "bytes")
+                            gamma=float(cfg.gamma), area_mask=cfg.observation_area_mask,
+                            attn_shrink=float(cfg.model["af_lambd"]) if fixture.endswith("_hard") else -1.0, **arrays)
+        print(fixture, losses, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

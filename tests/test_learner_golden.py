@@ -11,12 +11,14 @@ from oracle.torch_learner import TorchLearner
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KINDS = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLDEN, "learner_*.npz")))
 ATOMS = {"dqn_conv_mlp": 1, "c51": 51, "qr": 100, "iqn": 4, "da3": 1, "da6": 1}
-IQN_KINDS = ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn", "relative_da3_iqn", "relative_iqn", "merged_iqn")
-TRUNKS = {"relative_da3_iqn": "da3_iqn", "relative_iqn": "iqn"}  # fixture name -> state-embedding trunk of the IQN head (default: the name)
+IQN_KINDS = ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn", "relative_da3_iqn", "relative_iqn", "merged_iqn",
+             "da3_iqn_hard", "merged_da3_iqn_hard")  # *_hard: model.attention == "hard" (HardShrinkBlock), af_lambd in the fixture
+TRUNKS = {"relative_da3_iqn": "da3_iqn", "relative_iqn": "iqn", "da3_iqn_hard": "da3_iqn", "merged_da3_iqn_hard": "merged_da3_iqn"}  # fixture name -> state-embedding trunk of the IQN head (default: the name)
 # fixtures of the relative / merged views -> (network kind, attention heads)
 MASKED = {"relative_conv_mlp": ("dqn_conv_mlp", 4), "merged_conv_mlp": ("dqn_conv_mlp", 4), "merged_da3": ("da3", 2),
           "da6": ("da6", 2), "merged_da3_iqn": ("iqn", 2), "da6_iqn": ("iqn", 2), "relative_da3": ("da3", 2),
-          "relative_da3_iqn": ("iqn", 2), "relative_iqn": ("iqn", 2), "merged_iqn": ("iqn", 2)}
+          "relative_da3_iqn": ("iqn", 2), "relative_iqn": ("iqn", 2), "merged_iqn": ("iqn", 2),
+          "da6_hard": ("da6", 2), "merged_da3_iqn_hard": ("iqn", 2)}
 
 
 def load(kind):
@@ -24,7 +26,8 @@ def load(kind):
     part = lambda pre: {k[len(pre):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre)}
     fix = {"init": part("init/"), "target": part("target/"), "final": part("final/"), "batch": part("batch/"),
            "losses": z["losses"], "q0": torch.from_numpy(z["q0"]), "gamma": float(z["gamma"]),
-           "shape": [int(v) for v in z["shape"]], "area_mask": str(z["area_mask"])}
+           "shape": [int(v) for v in z["shape"]], "area_mask": str(z["area_mask"]),
+           "attn_shrink": float(z["attn_shrink"]) if "attn_shrink" in z.files and float(z["attn_shrink"]) >= 0 else None}
     if kind in IQN_KINDS:  # the fractions the reference drew: per update (taus, tau_dashes, tau_sel), and q0's tau
         fix["taus"] = [(torch.from_numpy(z[f"taus/{u}/taus"]), torch.from_numpy(z[f"taus/{u}/dash"]),
                         torch.from_numpy(z[f"taus/{u}/sel"])) for u in range(2)]
@@ -33,10 +36,10 @@ def load(kind):
 
 
 def make_oracle(kind, fix, sd=None, target=None):
-    net, heads = MASKED.get(kind, ("iqn", 2) if kind == "da3_iqn" else (kind, 4))
+    net, heads = MASKED.get(kind, ("iqn", 2) if kind in ("da3_iqn", "da3_iqn_hard") else (kind, 4))
     o = TorchLearner(net, sd or fix["init"], 4, fix["gamma"], 1e-3, 0.99, 1e-8, num_atoms=ATOMS[net],
                      area_mask=fix["area_mask"], size=fix["shape"][1:], num_heads=heads,
-                     trunk=TRUNKS.get(kind, kind) if kind in IQN_KINDS else "iqn")
+                     trunk=TRUNKS.get(kind, kind) if kind in IQN_KINDS else "iqn", attn_shrink=fix["attn_shrink"])
     o.target = {k: v.clone() for k, v in (target or fix["target"]).items()}
     return o
 

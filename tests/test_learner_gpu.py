@@ -258,6 +258,35 @@ def test_attention_maps_match_torch_oracle():
         dqn.attention(4)
 
 
+def test_hard_shrink_attention_maps_match_torch_oracle():
+    """HardShrinkAttention.forward_attn (hard_shrink_attention.py:82-105) returns the weights AFTER nn.Hardshrink:
+    the exported maps of a model.attention == "hard" DA6 hold exact zeros where softmax <= af_lambd."""
+    import oracle.torch_learner as tl
+    kind = "da6_hard"
+    fix = load(kind)
+    b = fix["batch"]
+    B = b["obs"].shape[0]
+    g = make_group(kind, fix["shape"], 1, B)
+    g.load_state_dict(0, fix["init"])
+    pos = b["pos"].to(torch.int8)[None].contiguous().cuda()
+    q = g.q_values(pack(g, b["obs"][None]), pos=pos).cpu()[0]
+    assert rel_err(q, fix["q0"]) < RTOL
+    attns = [[], []]
+    tl._ATTN_SHRINK = fix["attn_shrink"]
+    try:
+        tl.da6_forward(fix["init"], (b["obs"], b["pos"]), fix["shape"][1:], 2, attns=attns)
+    finally:
+        tl._ATTN_SHRINK = None
+    for stack in (0, 1):
+        got, want = g.attention(B, stack=stack, layer=0).cpu()[0], attns[stack][0]
+        cut = want == 0
+        assert 0.005 < float(cut.float().mean()) < 0.95  # the threshold does cut weights (66 % local, 0.8 % relative stack)
+        # a weight within rounding of af_lambd may fall on the other side; everything else agrees
+        near = (want - fix["attn_shrink"]).abs() < 1e-6
+        assert float(((got - want).abs() * (~near)).max()) < 1e-6
+        assert bool(((got == 0) == cut)[~near].all())
+
+
 def test_adam_optimizer_matches_torch():
     """configs/opt/adam.yaml through generate_optimizer (optimizers/__init__.py:18-24): five updates against torch.optim.Adam,
     with one agent masked out (its step counter and moments must not advance)."""
