@@ -324,6 +324,14 @@ int maexp_learner_update(maexp_learner *learner, const float *obs, const float *
 int maexp_decode_relative(const float *obs, const int8_t *positions, float *canvas, int64_t rows, int channels,
                           int visible_range, int size_x, int size_y, int obs_stride, int only_area_plus_one, void *stream);
 
+/* heatmap_observation of DefaultEnvironment (default_environment.py:93,238-247), summed over the environments of one
+ * step: heat[n][k] += sum_e obs[e*env_stride + n*agent_stride + k] for k < elems, skipping environments with skip[e] != 0
+ * (pass maexp_obs_out.was_reset: a reset observation is not counted by the reference).  obs is a slot the step wrote
+ * (local view: elems = C*V*V, env_stride = N*slot_floats, agent_stride = slot_floats) or the canvas maexp_decode_relative
+ * made of it (relative / merged views: elems = C*X*Y).  heat: fp32 [N, elems], accumulated, zeroed by the caller. */
+int maexp_heatmap_observation_add(const float *obs, int64_t num_envs, int num_agents, int elems, int64_t env_stride,
+                                  int64_t agent_stride, const uint8_t *skip, float *heat, void *stream);
+
 /* DefaultAgent.get_action for a chunk of environments (default_agent.py:12-19): with probability epsilon a
  * uniform random action int(random()*A) (abstract_agent.py:31-34), else argmax_a Q.  q_values [G,batch,A];
  * actions int8 [E,G] written at rows env_offset .. env_offset+batch; no_task uint8 [G]: agent_tasks "-1" agents

@@ -107,6 +107,8 @@ SYMBOLS = {
     "maexp_learner_grads_iqn": (C.c_int, [C.c_void_p] + [C.c_void_p] * 9 + [C.c_void_p]),
     "maexp_learner_apply": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "maexp_learner_update": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
+    "maexp_heatmap_observation_add": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
+                                                C.c_void_p, C.c_void_p]),
     "maexp_decode_relative": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_void_p]),
     "maexp_select_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint32,

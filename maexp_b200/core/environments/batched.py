@@ -178,6 +178,37 @@ class BatchedEnvironment:
             return out
         return buf, split
 
+    def new_heatmap_observation(self):
+        """Zeroed fp32 [N, *observation_space] for `accumulate_heatmap_observation` (default_environment.py:93-95)."""
+        return torch.zeros((self.N, *self.model_obs_shape), dtype=torch.float32, device=self.device)
+
+    def accumulate_heatmap_observation(self, out, heat, chunk_envs=8192):
+        """heatmap_observation += the observations `step(out)` just wrote, summed over the environments that were
+        not reset by that call (default_environment.py:238-247: the local observation, or the decoded relative
+        canvas on the relative / merged views — the merged view needs out["positions"])."""
+        assert heat.is_cuda and heat.is_contiguous() and heat.dtype == torch.float32
+        E, N, S = self.E, self.N, self.slot_floats
+        skip = self._p(out["was_reset"])
+        if self.config.observation_area_mask == "local":
+            _lib.check(self.lib.maexp_heatmap_observation_add(self._p(out["obs"]), E, N, self.K, S, E * S, skip,
+                                                              self._p(heat), self._stream()))
+            return heat
+        if out.get("positions") is None:
+            raise ValueError("heatmap_observation on the relative / merged views needs out['positions'] (new_outputs(extras=True))")
+        slot = out["obs_rel"] if self.merged else out["obs"]
+        pos = out["positions"].transpose(0, 1).contiguous()  # [N, E, 2], the slot's row order
+        X, Y = self.X, self.Y
+        canvas = torch.empty((min(E, chunk_envs), self.C, X, Y), dtype=torch.float32, device=self.device)
+        for n in range(N):
+            for e0 in range(0, E, chunk_envs):
+                rows = min(chunk_envs, E - e0)
+                _lib.check(self.lib.maexp_decode_relative(self._p(slot[n, e0:]), self._p(pos[n, e0:]), self._p(canvas), rows,
+                                                          self.C, self.V, X, Y, S, 0, self._stream()))
+                _lib.check(self.lib.maexp_heatmap_observation_add(
+                    self._p(canvas), rows, 1, self.C * X * Y, self.C * X * Y, 0, self._p(out["was_reset"][e0:]),
+                    self._p(heat[n]), self._stream()))
+        return heat
+
     def new_slot(self):
         """One replay-ring slot, agent-major: fp32 [N, E, slot_floats] (slot_floats = C*V*V padded to 32 bytes)."""
         return torch.empty((self.N, self.E, self.slot_floats), dtype=torch.float32, device=self.device)

@@ -17,6 +17,24 @@ namespace maexp {
 int fail(const std::string &msg);
 constexpr uint32_t kStreamEpsilon = 8;
 
+// heatmap_observation (default_environment.py:93,238-247): heat[n][k] += sum over environments of obs[e][n][k], skipping
+// the environments that were reset by this call (the reset observation goes through observation_handler.reset, which does
+// not count).  Thread = one element k of one agent, coalesced along k; blockIdx.z = a slice of the environments; one
+// atomicAdd per thread.  The sums are exact in any order while the observations hold small integers (every view without
+// gaussian noise, below 2^24 counts per element); with sensing noise the order of the slices is not fixed.
+__global__ void __launch_bounds__(128) heatmap_observation_kernel(const float *obs, long long E, int K, long long env_stride,
+                                                                  long long agent_stride, const uint8_t *skip, float *heat) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+    if (k >= K) return;
+    const long long per = (E + gridDim.z - 1) / gridDim.z, e0 = per * blockIdx.z, e1 = min(E, e0 + per);
+    const float *src = obs + n * agent_stride + k;
+    float acc = 0.0f;
+#pragma unroll 4
+    for (long long e = e0; e < e1; ++e)
+        if (!skip || !skip[e]) acc += __ldcs(src + e * env_stride);
+    if (e1 > e0) atomicAdd(heat + (size_t)n * K + k, acc);
+}
+
 // one thread per canvas element, coalesced along y; HBM-bound: writes 4*C*X*Y bytes per observation
 __global__ void decode_relative_kernel(const float *obs, const int8_t *pos, float *canvas, long long rows, int C, int V,
                                        int X, int Y, int obs_stride, int only_area) {
@@ -71,6 +89,23 @@ int maexp_decode_relative(const float *obs, const int8_t *positions, float *canv
         obs, positions, canvas, rows, channels, visible_range, size_x, size_y, obs_stride, only_area_plus_one);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(std::string("maexp_decode_relative: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int maexp_heatmap_observation_add(const float *obs, int64_t num_envs, int num_agents, int elems, int64_t env_stride,
+                                  int64_t agent_stride, const uint8_t *skip, float *heat, void *stream) {
+    if (!obs || !heat) return fail("maexp_heatmap_observation_add: null argument");
+    if (num_envs < 1 || num_agents < 1 || elems < 1) return fail("maexp_heatmap_observation_add: bad shape");
+    // env slices: enough CTAs to fill the 148 SMs a few times over, at least 64 environments per slice
+    const int tiles = (elems + 127) / 128;
+    long long slices = (148LL * 8 + (long long)tiles * num_agents - 1) / ((long long)tiles * num_agents);
+    if (slices > (num_envs + 63) / 64) slices = (num_envs + 63) / 64;
+    if (slices < 1) slices = 1;
+    if (slices > 65535) slices = 65535;
+    heatmap_observation_kernel<<<dim3((unsigned)tiles, (unsigned)num_agents, (unsigned)slices), 128, 0,
+                                 static_cast<cudaStream_t>(stream)>>>(obs, num_envs, elems, env_stride, agent_stride, skip, heat);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("maexp_heatmap_observation_add: ") + cudaGetErrorString(e));
     return 0;
 }
 

@@ -232,6 +232,28 @@ class Oracle:
             off += cnt
         return out
 
+    def heatmap_observation_add(self, heat, out):
+        """default_environment.py:238-247 for the outputs of one step (extras=True): heat[n] += every stepped
+        environment's observation of agent n — the local [C,V,V] crop, or decode_relative_state
+        (observation_handler.py:150-177) of the relative view on the relative / merged masks.  Environments reset by
+        the call are skipped (their observation comes from observation_handler.reset, :114).  Plain numpy loops."""
+        local = self.c.area_mask == MASKS["local"]
+        src = out["obs_rel"] if self.merged else out["obs"]
+        for e in range(self.E):
+            if out["was_reset"][e]:
+                continue
+            for n in range(self.N):
+                if local:
+                    heat[n] += src[e, n]
+                    continue
+                c = dict(zip(COORD_KEYS, (int(v) for v in out["coordinates"][e, n])))
+                canvas = np.zeros((self.Cn, self.X, self.Y), np.float32)
+                canvas[-1] -= 1
+                canvas[:, c["map_x_min"]:c["map_x_max"], c["map_y_min"]:c["map_y_max"]] = \
+                    src[e, n][:, c["obs_x_min"]:c["obs_x_max"], c["obs_y_min"]:c["obs_y_max"]]
+                heat[n] += canvas
+        return heat
+
     def reset(self, tick, env_mask=None, noise_tape=None):
         o, s = self._out(noise_tape)
         if env_mask is not None:

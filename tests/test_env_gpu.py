@@ -302,6 +302,40 @@ def test_heatmaps_match_oracle(name):
     assert want["heatmap_agents"].sum() > 0 and want["heatmap_wall_collision"].sum() > 0
 
 
+@pytest.mark.parametrize("name,E", [("cfg5_four_rooms_n8", 300), ("relative_transparent", 70),
+                                    ("cfg4_four_rectangle_merged_types", 70),
+                                    ("cfg2_four_rooms_transition_flip_sharedmean", 1000), ("sensing_dist", 64)])
+def test_heatmap_observation_matches_oracle(name, E):
+    """heatmap_observation (default_environment.py:93,238-247) summed over a batch of environments with auto-resets:
+    local, relative and merged views; bit-exact for the integer-valued observations (any summation order), 1e-5 with
+    gaussian sensing noise (maexp_heatmap_observation_add + maexp_decode_relative)."""
+    from oracle.cases import cases
+    cfg = cases()[name][0].merged_with(max_episode_length=9)
+    gaussian = cfg.observation_noise in ("sensing_dist", "threshold_sensing_dist")
+    b = CudaBackend(cfg, E, first_global_env_id=11, auto_reset=True, extras=True)
+    orc = Oracle(cfg, E, auto_reset=True, first_global_env_id=11, extras=True)
+    heat = b.env.new_heatmap_observation()
+    want = np.zeros(tuple(heat.shape), np.float32)
+    rng = np.random.default_rng(3)
+    shape = (E, b.env.N, b.env.C, b.env.V, b.env.V)
+    tape = rng.standard_normal(shape).astype(np.float32) if gaussian else None
+    b.reset(0, noise_tape=tape), orc.reset(0, noise_tape=tape)
+    resets = 0
+    for tick in range(1, 25):
+        tape = rng.standard_normal(shape).astype(np.float32) if gaussian else None
+        got, ref = b.step(tick, noise_tape=tape), orc.step(tick, noise_tape=tape, threads=4)
+        assert np.array_equal(got["obs"], ref["obs"])
+        b.env.accumulate_heatmap_observation(b.out, heat, chunk_envs=48)
+        orc.heatmap_observation_add(want, ref)
+        resets += int(ref["was_reset"].sum())
+    got = heat.cpu().numpy()
+    if gaussian:
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-3)
+    else:
+        assert np.array_equal(got, want)
+    assert resets >= E and np.abs(want).sum() > 0
+
+
 def _random_config(rng):
     """A random valid configuration over the whole supported surface (maps, views, masks, noises, environments)."""
     maps = {

@@ -76,3 +76,20 @@ def test_heatmaps_match_reference(name):
                 "heatmap_agents_collision"):
         assert np.array_equal(np.asarray(getattr(env, key)), hm[key]), key
     assert hm["heatmap_complete"].sum() > 0 and hm["heatmap_objects_left"].sum() > 0
+
+
+@pytest.mark.parametrize("name", ["cfg5_four_rooms_n8", "relative_transparent", "cfg4_four_rectangle_merged_types",
+                                  "cfg2_four_rooms_transition_flip_sharedmean"])
+def test_heatmap_observation_matches_reference(name):
+    """heatmap_observation (default_environment.py:93,238-247) on the local, relative and merged views: the sum of the
+    step observations of an episode (decoded to the map canvas on the relative / merged views), zeroed by reset()."""
+    cfg = cases()[name][0]
+    ref = rr.RefEnv(cfg, env_id=5)
+    orc = Oracle(cfg, num_envs=1, first_global_env_id=5, extras=True)
+    ref.reset(0), orc.reset(0)
+    heat = np.zeros(np.asarray(ref.env.heatmap_observation).shape, np.float32)
+    for tick in range(1, 41):
+        ref.step(tick)
+        orc.heatmap_observation_add(heat, orc.step(tick))
+    assert np.array_equal(np.asarray(ref.env.heatmap_observation, np.float32), heat)
+    assert np.abs(heat).sum() > 0
