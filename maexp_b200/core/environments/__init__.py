@@ -16,7 +16,7 @@ from .batched import BatchedEnvironment
 logger = initialize_logging(__name__)
 
 __all__ = ["BatchedEnvironment", "DefaultEnvironment", "SharedMeanRewardEnvironment", "SharedMaxRewardEnvironment",
-           "SequentialEnvironment", "JunctionalEnvironment", "generate_environment"]
+           "SequentialEnvironment", "JunctionalEnvironment", "ObservationStatsEnvironment", "generate_environment"]
 
 
 class DefaultEnvironment:
@@ -36,6 +36,12 @@ class DefaultEnvironment:
         self.out = self.batched.new_outputs(extras=True)
         self.current_step = 0
         self.objects_generated = self.objects_completed = self.agents_collided = self.walls_collided = 0
+        self._heat = self.batched.new_heatmap_observation()  # default_environment.py:93-95
+
+    @property
+    def heatmap_observation(self):
+        """[N, *observation_space] sums of this episode's step observations (default_environment.py:93,238-247)."""
+        return self._heat.cpu().numpy()
 
     # ---- reference structures
     def _obs_n(self):
@@ -63,6 +69,7 @@ class DefaultEnvironment:
 
     def reset(self):
         self.batched.reset(self.out)
+        self._heat.zero_()
         return self._obs_n()
 
     def step(self, action_n, order):
@@ -70,6 +77,7 @@ class DefaultEnvironment:
         actions = torch.as_tensor(np.asarray(action_n, np.int8).reshape(1, -1)).to(dev)
         order = torch.as_tensor(np.asarray(order, np.uint8).reshape(1, -1)).to(dev)
         self.batched.step(self.out, actions=actions, order=order)
+        self.batched.accumulate_heatmap_observation(self.out, self._heat)
         obs_n = self._obs_n()
         rewards = self.out["rewards"][0].cpu().tolist()
         dones = [bool(d) for d in self.out["dones"][0].cpu().tolist()]
@@ -97,6 +105,27 @@ class JunctionalEnvironment(DefaultEnvironment):
     reward_environment = "junctional"
 
 
+class ObservationStatsEnvironment(DefaultEnvironment):
+    """observation_stats_environment.py:16-61: the default step plus `observation_stats`, per-agent sums of every step
+    observation that no reset zeroes (local view: the [C,V,V] crop; relative view: the decoded [C,X,Y] canvas; the
+    reference leaves the merged view out, :46-52)."""
+    reward_environment = "default"
+
+    def __init__(self, config, world, reference_compat=False):
+        super().__init__(config, world, reference_compat)
+        self._stats = self.batched.new_heatmap_observation()
+
+    @property
+    def observation_stats(self):
+        return list(self._stats.cpu().numpy())
+
+    def step(self, action_n, order):
+        result = super().step(action_n, order)
+        if self.view_method in ("relative", "local"):
+            self.batched.accumulate_heatmap_observation(self.out, self._stats)
+        return result
+
+
 def generate_environment(config, world):
     if config.environment == "default":
         return DefaultEnvironment(config=config, world=world)
@@ -108,5 +137,7 @@ def generate_environment(config, world):
         return SequentialEnvironment(config=config, world=world)
     if config.environment == "junctional":
         return JunctionalEnvironment(config=config, world=world)
+    if config.environment == "observation_stats":  # core/environments/__init__.py:52-53
+        return ObservationStatsEnvironment(config=config, world=world)
     logger.warning(f"Unexpected environment is given. config.environment: {config.environment}")
     raise ValueError()

@@ -16,7 +16,8 @@ AGENT_VIEWS = {"default": 0, "simple": 1, "individual": 2, "transition": 3, "ind
 OBJECT_VIEWS = {"default": 0, "simple": 1, "object_types": 2}
 AREA_MASKS = {"local": 0, "relative": 1, "merged": 2}
 NOISES = {False: 0, None: 0, "flip": 1, "sensing_dist": 2, "threshold_sensing_dist": 3, "flat": 4}
-REWARD_MODES = {"default": 0, "shared_mean_reward": 1, "shared_max_reward": 2, "sequential": 0, "junctional": 0}
+REWARD_MODES = {"default": 0, "shared_mean_reward": 1, "shared_max_reward": 2, "sequential": 0, "junctional": 0,
+                "observation_stats": 0}  # observation_stats_environment.py:16-61 steps exactly like the default one
 ENV_KINDS = {"sequential": 1, "junctional": 2}  # sequential_environment.py:20, junctional_environment.py:20
 
 

@@ -24,7 +24,8 @@ AGENT_VIEWS = {"default": 0, "simple": 1, "individual": 2, "transition": 3, "ind
 OBJECT_VIEWS = {"default": 0, "simple": 1, "object_types": 2}
 MASKS = {"local": 0, "relative": 1, "merged": 2}
 NOISES = {False: 0, None: 0, "flip": 1, "sensing_dist": 2, "threshold_sensing_dist": 3, "flat": 4}
-REWARDS = {"default": 0, "shared_mean_reward": 1, "shared_max_reward": 2, "sequential": 0, "junctional": 0}
+REWARDS = {"default": 0, "shared_mean_reward": 1, "shared_max_reward": 2, "sequential": 0, "junctional": 0,
+           "observation_stats": 0}  # observation_stats_environment.py: DefaultEnvironment.step plus a never-zeroed observation sum
 ENV_KINDS = {"sequential": 1, "junctional": 2}
 COORD_KEYS = ("obs_x_min", "obs_x_max", "obs_y_min", "obs_y_max", "area_x_min", "area_x_max", "area_y_min",
               "area_y_max", "map_x_min", "map_x_max", "map_y_min", "map_y_max")

@@ -93,3 +93,28 @@ def test_heatmap_observation_matches_reference(name):
         orc.heatmap_observation_add(heat, orc.step(tick))
     assert np.array_equal(np.asarray(ref.env.heatmap_observation, np.float32), heat)
     assert np.abs(heat).sum() > 0
+
+
+@pytest.mark.parametrize("mask", ["local", "relative"])
+def test_observation_stats_environment_matches_reference(mask):
+    """environment=observation_stats (observation_stats_environment.py:16-61): the default step, heatmap_observation
+    zeroed by every reset() and observation_stats carried across episodes."""
+    cfg = cases()["relative_transparent"][0].merged_with(environment="observation_stats", observation_area_mask=mask)
+    ref = rr.RefEnv(cfg, env_id=2)
+    orc = Oracle(cfg, num_envs=1, first_global_env_id=2, extras=True)
+    stats, tick = None, 0
+    for episode in range(2):
+        a, b = ref.reset(tick), orc.reset(tick)
+        assert np.array_equal(a["obs"], b["obs"][0])
+        shape = np.asarray(ref.env.heatmap_observation).shape  # the attribute is created by reset() (:93)
+        stats = np.zeros(shape, np.float32) if stats is None else stats
+        heat = np.zeros(shape, np.float32)
+        for _ in range(15):
+            tick += 1
+            a, b = ref.step(tick), orc.step(tick)
+            assert np.array_equal(a["obs"], b["obs"][0])
+            orc.heatmap_observation_add(heat, b)
+            orc.heatmap_observation_add(stats, b)
+        tick += 1
+        assert np.array_equal(np.asarray(ref.env.heatmap_observation, np.float32), heat)
+    assert np.array_equal(np.stack(ref.env.observation_stats).astype(np.float32), stats)

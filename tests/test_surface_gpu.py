@@ -48,6 +48,36 @@ def test_generate_environment_returns_reference_structures():
         generate_environment(cfg.merged_with(environment="nope"), _world(cfg))
 
 
+@pytest.mark.parametrize("mask", ["local", "relative"])
+def test_observation_stats_environment(mask):
+    """generate_environment(environment=observation_stats) (observation_stats_environment.py:16-61): observation_stats
+    accumulates across episodes, heatmap_observation (default_environment.py:93,238-247) restarts at reset()."""
+    from maexp_b200.config import make_config
+    from maexp_b200.core.environments import ObservationStatsEnvironment, generate_environment
+    cfg = make_config(environment="observation_stats", observation_area_mask=mask, num_agents=4)
+    env = generate_environment(cfg, _world(cfg))
+    assert isinstance(env, ObservationStatsEnvironment)
+    orc = Oracle(cfg, 1, first_global_env_id=0, extras=True)
+    shape = (4, 3, 7, 7) if mask == "local" else (4, 3, 24, 24)
+    stats = np.zeros(shape, np.float32)
+    rng = np.random.default_rng(1)
+    tick = 0
+    for episode in range(2):
+        env.reset(), orc.reset(tick)
+        heat = np.zeros(shape, np.float32)
+        assert not env.heatmap_observation.any()
+        for _ in range(12):
+            tick += 1
+            actions, order = rng.integers(0, 5, 4), rng.permutation(4)
+            env.step(list(actions), list(order))
+            want = orc.step(tick, actions=actions[None], order=order[None])
+            orc.heatmap_observation_add(heat, want)
+            orc.heatmap_observation_add(stats, want)
+        tick += 1
+        assert np.array_equal(env.heatmap_observation, heat)
+    assert np.array_equal(np.stack(env.observation_stats), stats) and np.abs(stats).sum() > 0
+
+
 def test_decode_relative_state_matches_reference_semantics():
     """observation_handler.py:150-216 restated in numpy on the oracle's coordinates."""
     from maexp_b200.core.handlers.observations import ObservationHandler
