@@ -383,6 +383,45 @@ def _random_config(rng):
     return cfg
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_dynamic_simple_and_spare_init_rows_match_oracle(seed):
+    """The sweep above on the dynamic_simple map (moving obstacles, random sizes) with up to four spare init_xys rows
+    under shuffle_init_xys: outputs and state bit-identical to the C oracle across resets."""
+    rng = np.random.default_rng(5000 + seed)
+    for _ in range(50):
+        cfg = _random_config(rng)
+        if cfg.environment in ("sequential", "junctional"):
+            continue
+        X, Y = int(rng.integers(9, 27)), int(rng.integers(9, 25))
+        spare = [[1, 1], [-1, 1], [1, -1], [-1, -1]][:int(rng.integers(0, 5))]
+        # the spare rows sit next to the centre; the drawn rows are the sweep's (+-2.. cells), all distinct
+        rows = [xy for xy in list(cfg.init_xys) if max(abs(xy[0]), abs(xy[1])) < min(X, Y) // 2 - 1]
+        if not rows:
+            continue
+        N = len(rows)
+        cfg = cfg.merged_with(map=dict(name="dynamic_simple", SIZE_X=X, SIZE_Y=Y), num_agents=N, init_xys=rows + spare,
+                              agent_tasks=list(cfg.agent_tasks)[:N], type_objects=cfg.type_objects)
+        E, first = int(rng.choice([1, 17, 70])), int(rng.integers(0, 1000))
+        try:
+            cuda = CudaBackend(cfg, E, first_global_env_id=first, auto_reset=True, extras=True)
+        except ValueError:
+            continue
+        break
+    else:
+        pytest.skip("no valid configuration drawn")
+    orc = Oracle(cfg, E, auto_reset=True, first_global_env_id=first, extras=True)
+    gaussian = cfg.observation_noise in ("sensing_dist", "threshold_sensing_dist")
+    shape = (E, cuda.env.N, cuda.env.C, cuda.env.V, cuda.env.V)
+    keys = ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates", "objects", "destination")
+    tape = rng.standard_normal(shape).astype(np.float32) if gaussian else None
+    _compare(cuda.reset(0, noise_tape=tape), orc.reset(0, noise_tape=tape), keys, f"seed {seed} reset {dict(cfg)}")
+    for tick in range(1, 40):
+        tape = rng.standard_normal(shape).astype(np.float32) if gaussian else None
+        _compare(cuda.step(tick, noise_tape=tape), orc.step(tick, noise_tape=tape, threads=4), keys, f"seed {seed} tick {tick}")
+        _compare(cuda.state(), orc.state(), ("pos", "objects", "counters", "steps", "destination"), f"seed {seed} state {tick}")
+    assert cuda.env.stats()["error_flag"] == 0
+
+
 @pytest.mark.parametrize("seed", range(24))
 def test_random_configurations_match_oracle(seed):
     """Randomised sweep over maps x environments x views x masks x noises x sizes: every output and the state stay
