@@ -251,7 +251,7 @@ typedef struct {
     int32_t optimizer;        /* generate_optimizer (optimizers/__init__.py:17-42): 0 = optim.RMSprop, 1 = optim.Adam */
     float beta1, beta2;       /* Adam betas (configs/opt/adam.yaml); learning_rate and eps are shared */
     int32_t attention_hard;   /* 1: model.attention == "hard" -- the transformer blocks are HardShrinkBlock
-                                 (hard_shrink_attention.py:13-105; DA3_IQN / MergedDA3_IQN da3_iqn.py:118-122,245, DA6 da6.py:67):
+                                 (hard_shrink_attention.py:13-105; da3.py:46,144, da6.py:67, da3_iqn.py:118-122,245, da6_iqn.py:76-80):
                                  softmax weights <= af_lambd are zeroed before they multiply V and in the exported maps */
     float af_lambd;           /* model.af_lambd (nn.Hardshrink lambd), read when attention_hard */
 } maexp_learner_cfg;

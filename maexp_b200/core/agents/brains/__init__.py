@@ -43,11 +43,10 @@ def learner_kind(config):
         if config.brain not in ("da3_iqn", "iqn"):
             raise ValueError("model da3_iqn / da6_iqn needs an IQN brain (brain=da3_iqn)")
         mask = config.observation_area_mask
-        hard_ok = config.model.name == "da3_iqn"  # da6_iqn.py only ever builds the plain Block
-        if config.model.get("attention") == "aoa" or (config.model.get("attention") == "hard" and not hard_ok) or \
-                config.get("objects_channel") or config.get("agents_channel") or config.get("destination_channel"):
-            raise ValueError("attention IQN models are implemented with soft / hard-shrink attention (da3_iqn) and "
-                             "without extra canvas channels")
+        if config.model.get("attention") == "aoa" or config.get("objects_channel") or config.get("agents_channel") or \
+                config.get("destination_channel"):
+            raise ValueError("attention IQN models are implemented with soft / hard-shrink attention and without extra "
+                             "canvas channels")
         if config.model.name == "da6_iqn" and mask != "merged":
             raise ValueError("da6_iqn reads the merged view (customs/da6_iqn.py:160-176)")
         if config.model.name == "da3_iqn" and mask == "local" and int(config.model.patch_size) != 1:
@@ -60,9 +59,8 @@ def learner_kind(config):
     elif config.model.name == "da3" or kind == "da3":
         if kind != "da3" or config.model.name != "da3":
             raise ValueError("brain=da3 and model=da3 go together (da3_brain.py, customs/da3.py)")
-        if config.model.get("attention") == "hard" or config.get("objects_channel") or \
-                (config.observation_area_mask == "local" and int(config.model.patch_size) != 1):
-            raise ValueError("DA3 is implemented with soft attention, without the objects channel; local view: patch_size=1")
+        if config.get("objects_channel") or (config.observation_area_mask == "local" and int(config.model.patch_size) != 1):
+            raise ValueError("DA3 is implemented without the objects channel; local view: patch_size=1")
     elif config.model.name not in ("conv_mlp", "da3_baseline", "categorical_dqn", "qr_dqn", "iqn"):
         logger.warning(f"Unexpected network is given. config.model.name: {config.model.name}")
         raise ValueError()
@@ -115,8 +113,8 @@ class LearnerGroup:
         if self.kind in ("da3", "da6") or self.trunk in ("da3_iqn", "merged_da3_iqn", "da6_iqn"):
             cfg.embed_dim, cfg.num_heads, cfg.block_loop = int(m.embed_dim), int(m.num_heads), int(m.block_loop)
             cfg.mlp_hidden = int(int(m.embed_dim) * float(m.mlp_ratio))
-            # HardShrinkBlock (hard_shrink_attention.py:13-49) in DA6 (da6.py:67) and DA3_IQN / MergedDA3_IQN (da3_iqn.py:118-122,245)
-            if m.get("attention") == "hard" and (self.kind == "da6" or self.trunk in ("da3_iqn", "merged_da3_iqn")):
+            # HardShrinkBlock (hard_shrink_attention.py:13-49): da3.py:46,144, da6.py:67, da3_iqn.py:118-122,245, da6_iqn.py:76-80
+            if m.get("attention") == "hard":
                 cfg.attention_hard, cfg.af_lambd = 1, float(m.af_lambd)
         cfg.conv1_channels = int(m.get("hidden_channels", [32])[0])
         cfg.conv2_channels = int(m.get("output_channel", 64))

@@ -71,7 +71,11 @@ def configs():
     mda3_iqn_hard["model"] = dict(mda3_iqn_hard.model, attention="hard", af_lambd=0.04)
     da3_iqn_hard = attn_iqn("local", "da3_iqn")
     da3_iqn_hard["model"] = dict(da3_iqn_hard.model, attention="hard", af_lambd=0.04)
-    hard = {"da6_hard": (da6_hard, [4, *SIZE]), "merged_da3_iqn_hard": (mda3_iqn_hard, [4, *SIZE]),
+    da3_hard = da3.merged_with()
+    da3_hard["model"] = dict(da3.model, attention="hard", af_lambd=0.02)  # 50 tokens: mean weight 0.02
+    da6_iqn_hard = attn_iqn("merged", "da6_iqn")
+    da6_iqn_hard["model"] = dict(da6_iqn_hard.model, attention="hard", af_lambd=0.04)
+    hard = {"da3_hard": (da3_hard, [3, 7, 7]), "da6_iqn_hard": (da6_iqn_hard, [4, *SIZE]), "da6_hard": (da6_hard, [4, *SIZE]), "merged_da3_iqn_hard": (mda3_iqn_hard, [4, *SIZE]),
             "da3_iqn_hard": (da3_iqn_hard, [4, VIEW, VIEW])}
     return {**hard, "relative_iqn": (conv_iqn("relative"), [4, *SIZE]), "merged_iqn": (conv_iqn("merged"), [4, *SIZE]),
             "relative_da3": (rda3, [4, *SIZE]), "relative_da3_iqn": (rda3_iqn, [4, *SIZE]),

@@ -12,13 +12,14 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KINDS = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLDEN, "learner_*.npz")))
 ATOMS = {"dqn_conv_mlp": 1, "c51": 51, "qr": 100, "iqn": 4, "da3": 1, "da6": 1}
 IQN_KINDS = ("iqn", "da3_iqn", "merged_da3_iqn", "da6_iqn", "relative_da3_iqn", "relative_iqn", "merged_iqn",
-             "da3_iqn_hard", "merged_da3_iqn_hard")  # *_hard: model.attention == "hard" (HardShrinkBlock), af_lambd in the fixture
-TRUNKS = {"relative_da3_iqn": "da3_iqn", "relative_iqn": "iqn", "da3_iqn_hard": "da3_iqn", "merged_da3_iqn_hard": "merged_da3_iqn"}  # fixture name -> state-embedding trunk of the IQN head (default: the name)
+             "da3_iqn_hard", "merged_da3_iqn_hard", "da6_iqn_hard")  # *_hard: model.attention == "hard" (HardShrinkBlock), af_lambd in the fixture
+TRUNKS = {"relative_da3_iqn": "da3_iqn", "relative_iqn": "iqn", "da3_iqn_hard": "da3_iqn", "merged_da3_iqn_hard": "merged_da3_iqn",
+          "da6_iqn_hard": "da6_iqn"}  # fixture name -> state-embedding trunk of the IQN head (default: the name)
 # fixtures of the relative / merged views -> (network kind, attention heads)
 MASKED = {"relative_conv_mlp": ("dqn_conv_mlp", 4), "merged_conv_mlp": ("dqn_conv_mlp", 4), "merged_da3": ("da3", 2),
           "da6": ("da6", 2), "merged_da3_iqn": ("iqn", 2), "da6_iqn": ("iqn", 2), "relative_da3": ("da3", 2),
           "relative_da3_iqn": ("iqn", 2), "relative_iqn": ("iqn", 2), "merged_iqn": ("iqn", 2),
-          "da6_hard": ("da6", 2), "merged_da3_iqn_hard": ("iqn", 2)}
+          "da6_hard": ("da6", 2), "merged_da3_iqn_hard": ("iqn", 2), "da6_iqn_hard": ("iqn", 2)}
 
 
 def load(kind):
@@ -36,7 +37,8 @@ def load(kind):
 
 
 def make_oracle(kind, fix, sd=None, target=None):
-    net, heads = MASKED.get(kind, ("iqn", 2) if kind in ("da3_iqn", "da3_iqn_hard") else (kind, 4))
+    net, heads = MASKED.get(kind, ("iqn", 2) if kind in ("da3_iqn", "da3_iqn_hard") else
+                            ("da3", 4) if kind == "da3_hard" else (kind, 4))
     o = TorchLearner(net, sd or fix["init"], 4, fix["gamma"], 1e-3, 0.99, 1e-8, num_atoms=ATOMS[net],
                      area_mask=fix["area_mask"], size=fix["shape"][1:], num_heads=heads,
                      trunk=TRUNKS.get(kind, kind) if kind in IQN_KINDS else "iqn", attn_shrink=fix["attn_shrink"])
