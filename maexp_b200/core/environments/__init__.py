@@ -37,11 +37,33 @@ class DefaultEnvironment:
         self.current_step = 0
         self.objects_generated = self.objects_completed = self.agents_collided = self.walls_collided = 0
         self._heat = self.batched.new_heatmap_observation()  # default_environment.py:93-95
+        # the six integer visit statistics of the running episode (default_environment.py:70-92), written by the step
+        # kernel through maexp_obs_out.heatmaps, and their sums over episodes (:36-61, accumulate_heatmap :249-257)
+        self._hm_buf, self._hm_split = self.batched.new_heatmaps()
+        self.out["heatmaps"] = self._hm_buf
+        self._hm_acc = torch.zeros_like(self._hm_buf)
+        self.heatmap_accumulated_observation = np.zeros(tuple(self._heat.shape), np.float32)
 
     @property
     def heatmap_observation(self):
         """[N, *observation_space] sums of this episode's step observations (default_environment.py:93,238-247)."""
         return self._heat.cpu().numpy()
+
+    def __getattr__(self, name):
+        # heatmap_agents, heatmap_complete, heatmap_objects, heatmap_objects_left, heatmap_wall_collision,
+        # heatmap_agents_collision and their heatmap_accumulated_* sums, as numpy int32 arrays
+        if name.startswith("heatmap_") and "_hm_split" in self.__dict__:
+            acc = name.startswith("heatmap_accumulated_")
+            key = "heatmap_" + name[len("heatmap_accumulated_"):] if acc else name
+            views = self._hm_split(self._hm_acc) if acc else self._hm_split()
+            if key in views:
+                return views[key].cpu().numpy()
+        raise AttributeError(name)
+
+    def accumulate_heatmap(self):
+        """default_environment.py:249-257."""
+        self._hm_acc += self._hm_buf
+        self.heatmap_accumulated_observation += self.heatmap_observation
 
     # ---- reference structures
     def _obs_n(self):
@@ -68,6 +90,7 @@ class DefaultEnvironment:
         return obs_n
 
     def reset(self):
+        self._hm_buf.zero_()  # default_environment.py:70-96 re-creates the maps; reset() itself counts the new objects
         self.batched.reset(self.out)
         self._heat.zero_()
         return self._obs_n()

@@ -48,6 +48,40 @@ def test_generate_environment_returns_reference_structures():
         generate_environment(cfg.merged_with(environment="nope"), _world(cfg))
 
 
+def test_single_environment_heatmap_attributes():
+    """heatmap_* / heatmap_accumulated_* attributes and accumulate_heatmap() of DefaultEnvironment
+    (default_environment.py:36-61,70-96,249-257) against the oracle's statistics (which no reset zeroes)."""
+    from maexp_b200.config import make_config
+    from maexp_b200.core.environments import generate_environment
+    cfg = make_config(num_agents=4, type_objects=2, object_view_method="object_types")
+    env = generate_environment(cfg, _world(cfg))
+    keys = ("heatmap_agents", "heatmap_complete", "heatmap_objects", "heatmap_objects_left", "heatmap_wall_collision",
+            "heatmap_agents_collision")
+    orc = Oracle(cfg, 1, first_global_env_id=0)
+    want = orc.enable_heatmaps()
+    rng = np.random.default_rng(4)
+    tick = 0
+    for episode in range(2):
+        env.reset(), orc.reset(tick)
+        for _ in range(20):
+            tick += 1
+            actions, order = rng.integers(0, 5, 4), rng.permutation(4)
+            env.step(list(actions), list(order))
+            orc.step(tick, actions=actions[None], order=order[None])
+        tick += 1
+        for k in keys:  # this episode's maps + the accumulated earlier ones = the oracle's running totals
+            acc = getattr(env, k.replace("heatmap_", "heatmap_accumulated_"))
+            assert np.array_equal(acc + getattr(env, k), want[k]), (episode, k)
+        first_obs = env.heatmap_observation.copy()
+        env.accumulate_heatmap()
+    assert want["heatmap_agents"].sum() > 0 and np.array_equal(env.heatmap_accumulated_agents, want["heatmap_agents"])
+    assert np.abs(env.heatmap_accumulated_observation).sum() > np.abs(first_obs).sum() > 0
+    env.reset()
+    assert not env.heatmap_agents.any() and env.heatmap_objects.sum() == 2 * int(cfg.num_objects)
+    with pytest.raises(AttributeError):
+        env.heatmap_nope
+
+
 @pytest.mark.parametrize("mask", ["local", "relative"])
 def test_observation_stats_environment(mask):
     """generate_environment(environment=observation_stats) (observation_stats_environment.py:16-61): observation_stats
