@@ -304,7 +304,8 @@ def test_heatmaps_match_oracle(name):
 
 @pytest.mark.parametrize("name,E", [("cfg5_four_rooms_n8", 300), ("relative_transparent", 70),
                                     ("cfg4_four_rectangle_merged_types", 70),
-                                    ("cfg2_four_rooms_transition_flip_sharedmean", 1000), ("sensing_dist", 64)])
+                                    ("cfg2_four_rooms_transition_flip_sharedmean", 1000), ("sensing_dist", 64),
+                                    ("merged_flip_three_rooms", 70)])  # 25 x 25 canvas: C*X*Y % 4 != 0, the scalar kernel
 def test_heatmap_observation_matches_oracle(name, E):
     """heatmap_observation (default_environment.py:93,238-247) summed over a batch of environments with auto-resets:
     local, relative and merged views; bit-exact for the integer-valued observations (any summation order), 1e-5 with
