@@ -344,6 +344,37 @@ def test_large_batch_inference_path_matches_oracle(kind, V, C, B):
     assert float((q_small - q[:, :100]).abs().max()) <= 1e-5 * float(q.abs().max())
 
 
+@pytest.mark.parametrize("B", [300, 2100])
+def test_hard_shrink_large_batch_inference_path(B):
+    """The acting-batch attention kernel (scores in shared memory, no probability buffer) with model.attention == "hard":
+    same Q-values as the training-size kernel on the same rows, and the torch oracle's on all but the rare rows where a
+    softmax weight lies within rounding of af_lambd (the shrink is discontinuous there)."""
+    from maexp_b200.core.agents.brains import LearnerGroup
+    cfg, _ = golden_configs()["da3_hard"]
+    G, V, C = 2, 7, 3
+    cfg = cfg.merged_with(batch_size=B)
+    g = LearnerGroup(cfg, [C, V, V], 4, G, B)
+    gen = torch.Generator().manual_seed(5)
+    for a in range(G):  # the embeddings are zero-initialised (da3.py:41-44): perturb them so the weights spread out
+        sd = g.state_dict(a)
+        for k in ("saliency_vector", "pos_embed"):
+            sd[k] = sd[k] + 0.5 * torch.randn(sd[k].shape, generator=gen)
+        g.load_state_dict(a, sd)
+    obs = (torch.rand((G, B, C, V, V), generator=gen) < 0.25).float()
+    obs[:, :, -1] -= 1
+    packed = pack(g, obs)
+    q = g.q_values(packed).cpu()
+    for a in range(G):
+        o = TorchLearner("da3", g.state_dict(a), 4, float(cfg.gamma), 1e-3, 0.99, 1e-8, attn_shrink=float(cfg.model["af_lambd"]))
+        want = o.q_values(obs[a])
+        soft = TorchLearner("da3", g.state_dict(a), 4, float(cfg.gamma), 1e-3, 0.99, 1e-8).q_values(obs[a])
+        err = (q[a] - want).abs().max(dim=1)[0] / want.abs().max()
+        assert float((err < RTOL).float().mean()) > 0.99, float((err < RTOL).float().mean())
+        assert rel_err(soft, want) > 1e-3  # the shrink does change the result
+    q_small = g.q_values(packed[:, :100].contiguous()).cpu()
+    assert float((q_small - q[:, :100]).abs().max()) <= 1e-5 * float(q.abs().max())
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (300, 64, 72), (4096, 128, 256), (4096, 51, 128), (2500, 204, 128), (1000, 32, 96),
                                    (513, 256, 40), (640, 700, 64), (300, 257, 32)])
 def test_tcgen05_gemm_against_fp64(M, N, K):
