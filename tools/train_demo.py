@@ -23,8 +23,16 @@ def main():
     ap.add_argument("--envs", type=int, default=1024)
     ap.add_argument("--epochs", type=int, default=30)
     ap.add_argument("--episode", type=int, default=100)
+    ap.add_argument("--map", default=None, help="e.g. dynamic_simple (20 x 20, moving obstacles) instead of the config's map")
+    ap.add_argument("--attention", default=None, help="hard: HardShrinkBlock with --af-lambd (attention models)")
+    ap.add_argument("--af-lambd", type=float, default=0.02)
     args = ap.parse_args()
-    cfg = baseline_config(args.config).merged_with(max_episode_length=args.episode, populate_steps=4 * args.envs,
+    base = baseline_config(args.config)
+    if args.map:
+        base = base.merged_with(map=dict(name=args.map, SIZE_X=20, SIZE_Y=20))
+    if args.attention:
+        base["model"] = dict(base.model, attention=args.attention, af_lambd=args.af_lambd)
+    cfg = base.merged_with(max_episode_length=args.episode, populate_steps=4 * args.envs,
                                                     capacity=64 * args.envs, synchronize_frequency=1, epsilon_decay=0.9,
                                                     validate_epochs=2, observation_noise=False)
     env = make_env(cfg, args.envs, auto_reset=True)
@@ -43,7 +51,7 @@ def main():
     dt = time.perf_counter() - t0
     after = evaluate()
     steps = args.epochs * args.episode
-    print(json.dumps({"config": args.config, "envs": args.envs, "epochs": args.epochs, "updates": steps,
+    print(json.dumps({"config": args.config, "map": cfg.map["name"], "attention": cfg.model.get("attention"), "envs": args.envs, "epochs": args.epochs, "updates": steps,
                       "train_seconds": dt, "agent_steps_per_sec_in_training": steps * args.envs * env.N / dt,
                       "greedy_reward_before": before[0], "greedy_reward_after": after[0],
                       "objects_completed_before": before[1], "objects_completed_after": after[1],
