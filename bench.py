@@ -126,20 +126,27 @@ def cpu_oracle_rate(n_envs, steps, warmup, threads):
     return n_envs * 8 * steps / dt, dt
 
 
+PY_REFERENCE = {"value": 5733.0, "unit": "agent-steps/s per core", "cores": 1,
+                "source": "BASELINE.md §2: the unmodified Python reference (default_environment.py:153), four_rooms, 8 agents, "
+                          "V=7, C=3, measured in the build container (it cannot travel to the GPU box)"}
+
+
 def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path on the host cores: every step walks ALL envs of the configuration."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_envs = 8192
+    n_envs = args.envs
     steps = max(1, min(args.steps, 400))
     rate, dt = cpu_oracle_rate(n_envs, steps, max(3, min(args.warmup, 10)), threads)
-    sample = "%d of the %d envs, %d steps, %.1f s" % (n_envs, ENVS_PER_GPU, steps, dt)
+    sample = "all %d envs x 8 agents per step, %d steps, %.1f s (C oracle port, %d pthreads)" % (n_envs, steps, dt, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": config_block(ENVS_PER_GPU, {"reference_step": "bounded sample: %d envs per step" % n_envs}),
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": config_block(n_envs),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "python_reference": PY_REFERENCE},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -165,6 +172,59 @@ def learner_cpu_rate(batch_size, steps=8):
     for _ in range(steps):
         o.learn(obs, nxt, act, rew, done)
     return steps / (time.perf_counter() - t0)
+
+
+# fp32 FLOPs of one C51 sample-update (forward of s, two forwards of s', backward), BASELINE.md §3 / SURVEY.md §8d
+C51_FLOP_PER_SAMPLE = 1.45e6
+SIMT_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FMA lanes x 2 FLOP at the 1965 MHz maximum clock
+
+
+def learner_roofline(flop, seconds):
+    """The update's contractions run as three TF32 tensor-core terms per product (fp32-level accuracy): the bound is the
+    measured dense bf16 rate / 2 (TF32 runs at half the bf16 rate) / 3 (terms); the fp32 SIMT peak is printed beside it."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16, src = 1398.0, "fallback (B200_PROFILING.md sustained)"
+    if os.path.exists(path):
+        with open(path) as f:
+            bf16, src = float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2 / 3)"
+    peak = bf16 / 6.0
+    achieved = flop / seconds / 1e12
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": src, "flop_per_team_update": flop, "frac_of_fp32_simt_peak": achieved / SIMT_FP32_TFLOPS,
+            "note": "B = 256 per agent-network: the update is a chain of small dependent layers, latency-bound by design of "
+                    "the workload (2.97 GFLOP per team update)"}
+
+
+def data_parallel_check(torch, dist, group, ring, batch, cfg, env, world, dev):
+    """SURVEY.md §4-iv on hardware: (1) after the timed updates every rank holds the same parameters; (2) the all-reduced,
+    1/world-scaled gradient of one more update equals the gradient a single GPU computes on the concatenated global batch."""
+    from maexp_b200 import _lib
+    from maexp_b200.core.agents.brains import LearnerGroup
+    spread = group.replica_spread(dist)
+    ring.sample(batch, seed=921, tick=9999)
+    group.grads(batch)
+    g_dp = group.params(_lib.BUF_GRADS).clone()
+    dist.all_reduce(g_dp, op=dist.ReduceOp.SUM)
+    g_dp /= world
+    B = batch["actions"].shape[1]
+    big = LearnerGroup(cfg.merged_with(batch_size=B * world), [3, 7, 7], 4, env.N, B * world, obs_stride=env.slot_floats,
+                       device=dev)
+    big.params(_lib.BUF_ONLINE).copy_(group.params(_lib.BUF_ONLINE))
+    big.params(_lib.BUF_TARGET).copy_(group.params(_lib.BUF_TARGET))
+    full = {}
+    for k in ("obs", "next_obs", "actions", "rewards", "dones"):
+        parts = [torch.empty_like(batch[k]) for _ in range(world)]
+        dist.all_gather(parts, batch[k].contiguous())
+        full[k] = torch.cat(parts, dim=1).contiguous()  # [N, world*B, ...]
+    big.grads(full)
+    g_one = big.params(_lib.BUF_GRADS)
+    err = float((g_dp - g_one).norm() / g_one.norm())
+    ok = spread == 0.0 and err <= 1e-6
+    out = {"replicas_in_sync": spread == 0.0, "replica_max_abs_diff": spread,
+           "dp_grad_vs_single_gpu_global_batch_rel_l2": err}
+    if not ok:
+        raise SystemExit("bench.py: data-parallel check failed: %s" % json.dumps(out))
+    return out
 
 
 def run_ours(args, rank, local_rank, world):
@@ -275,6 +335,8 @@ def run_ours(args, rank, local_rank, world):
         tick += 1
     B = int(cfg.batch_size)
     group = LearnerGroup(cfg, [3, 7, 7], 4, N, B, obs_stride=env.slot_floats, device=dev)
+    if dist is not None:
+        group.broadcast(dist)  # data-parallel replicas start from rank 0's weights (each rank initialised its own)
     batch = ring.new_batch(B)
     ring.sample(batch, seed=921, tick=0)
     graphed = GraphedUpdate(group, batch, dist=dist)  # first step eager (warm-up), second captures, then replays
@@ -295,6 +357,10 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     upd_ms = u0.elapsed_time(u1)
     loss = float(group.loss.mean())
+    ring.check(batch)  # the replay sampler's error flag
+    dp_check = None
+    if dist is not None:
+        dp_check = data_parallel_check(torch, dist, group, ring, batch, cfg, env, world, dev)
     sampler.window[1] = time.perf_counter()
     sampler.stop()
 
@@ -313,6 +379,8 @@ def run_ours(args, rank, local_rank, world):
         launch_s = ms * 1e-3 / K
         per_launch_agent_steps = env_steps * N / K / world
         achieved = B_ALG * per_launch_agent_steps / launch_s / 1e9
+        upd_s = upd_ms * 1e-3 / ku
+        learner_flop = C51_FLOP_PER_SAMPLE * B * N
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -325,22 +393,29 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
                          "kernel": "env_step_kernel", "algorithmic_bytes_per_agent_step": B_ALG,
-                         "launch_us": launch_s * 1e6},
+                         "launch_us": launch_s * 1e6,
+                         # the bit-packed state never moves the 144 B / agent-step of int8 grid traffic B_ALG counts:
+                         # the same launch time against the DRAM bytes ncu saw
+                         "real_bytes_frac": NCU_TRAFFIC_BYTES_PER_LAUNCH * (E / ENVS_PER_GPU) / launch_s / 1e9 / peak},
             "clocks": sampler.summary(),
             "learner": {"metric": "learner_updates_per_sec", "unit": "agent-network updates/s",
                         "value": ku * N / (upd_ms * 1e-3), "ms_per_team_update": upd_ms / ku, "brain": "categorical_dqn",
                         "agents": N, "batch_per_gpu": B, "global_batch": B * world, "steps": ku, "loss": loss,
                         "note": "replay sample (1 launch) + forward/backward (CUDA graph) + "
                                 + ("NCCL all-reduce of the flat gradient buffer + " if world > 1 else "")
-                                + "clip+RMSprop (CUDA graph); all 8 agents' networks in grouped launches"},
+                                + "clip+RMSprop (CUDA graph); all 8 agents' networks in grouped launches",
+                        "roofline": learner_roofline(learner_flop, upd_s)},
         }
+        if dp_check is not None:
+            line["learner"].update(dp_check)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            n_cpu, k_cpu = 8192, 150
-            rate, dt = cpu_oracle_rate(n_cpu, k_cpu, 3, threads)
+            k_cpu = 150  # the whole configuration per step, as the --impl reference arm
+            rate, dt = cpu_oracle_rate(E, k_cpu, 5, threads)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "%d of the %d envs, %d steps, %.1f s (C oracle port, pthreads)"
-                                              % (n_cpu, E, k_cpu, dt)}
+                                    "sample": "all %d envs x 8 agents per step, %d steps, %.1f s (C oracle port, %d pthreads)"
+                                              % (E, k_cpu, dt, threads),
+                                    "python_reference": PY_REFERENCE}
             line["learner"]["cpu_baseline"] = {"value": learner_cpu_rate(B), "unit": "agent-network updates/s",
                                                "cores": threads, "kind": "port",
                                                "sample": "torch fp32 restatement of CategoricalDQNBrain.learn, B=%d, "

@@ -200,7 +200,14 @@ typedef struct {
     int32_t *picked;   /* [B,2] (slot of the state, env) — may be NULL */
     int8_t *pos;       /* [N,B,2] observing agent's position in the state (relative / merged models) — may be NULL */
     int8_t *next_pos;  /* [N,B,2] ... in the new state */
+    int32_t *error_flag; /* one int32, OR-ed with MAEXP_REPLAY_ERR_* by the sampler (never cleared by it) — may be NULL */
 } maexp_batch;
+
+/* maexp_batch.error_flag bits.  NO_VALID: 64 redraws and a 4096-pair walk found only transitions into reset slots (a ring of
+ * 2-3 slots whose environments all reset on the same tick), the sampled row is not a transition; INDEX_RANGE: an injected
+ * (slot, env) lay outside the ring and was clamped; INDEX_INVALID: an injected pair names a transition into a reset slot.
+ * A flagged row carries action 0 instead of the reset slot's -1, so the loss kernels never index out of bounds. */
+enum { MAEXP_REPLAY_ERR_NO_VALID = 1, MAEXP_REPLAY_ERR_INDEX_RANGE = 2, MAEXP_REPLAY_ERR_INDEX_INVALID = 4 };
 
 /* Uniform sampling of `batch` whole-team transitions (np.random.choice in buffer.py:61; here with
  * replacement — immaterial for batch << S*E) fused with the gather into per-agent batches.
@@ -223,7 +230,9 @@ enum {
                                        transformer on the area canvas (patch_size = model.relative_patch_size) feeds token 0 of the
                                        local transformer (local_patch_size) */
 };
-enum { MAEXP_BUF_ONLINE = 0, MAEXP_BUF_TARGET = 1, MAEXP_BUF_GRADS = 2, MAEXP_BUF_SQUARE_AVG = 3, MAEXP_BUF_SUPPORT = 4 };
+enum { MAEXP_BUF_ONLINE = 0, MAEXP_BUF_TARGET = 1, MAEXP_BUF_GRADS = 2, MAEXP_BUF_SQUARE_AVG = 3, MAEXP_BUF_SUPPORT = 4,
+       MAEXP_BUF_EXP_AVG = 5,     /* Adam only (NULL for RMSprop); MAEXP_BUF_SQUARE_AVG is Adam's exp_avg_sq */
+       MAEXP_BUF_ADAM_STEPS = 6   /* Adam only: int32 [G] step counters behind the float pointer */ };
 
 typedef struct {
     int32_t kind;
@@ -339,6 +348,11 @@ int maexp_heatmap_observation_add(const float *obs, int64_t num_envs, int num_ag
 int maexp_select_actions(const float *q_values, int8_t *actions, int num_agents, int batch, int num_actions, int env_offset,
                          float epsilon, uint32_t seed, uint32_t first_global_env_id, uint32_t tick, const uint8_t *no_task,
                          void *stream);
+
+/* Quantile fractions of the IQN brains: count floats uniform in [0,1) (24-bit mantissa draws, as torch.rand), Philox keyed
+ * (seed, tick).  Replaces the torch.rand calls of iqn_brain.py:74,87 and customs/iqn.py:105-106 so that a graph-replayed
+ * update reads fresh fractions from fixed buffers. */
+int maexp_fill_uniform(float *out, int64_t count, uint32_t seed, uint32_t tick, void *stream);
 
 const char *maexp_last_error(void);
 int maexp_version(void);

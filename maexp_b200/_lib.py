@@ -48,7 +48,9 @@ class ReplayView(C.Structure):
 
 
 class Batch(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("obs", "next_obs", "actions", "rewards", "dones", "picked", "pos", "next_pos")]
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "next_obs", "actions", "rewards", "dones", "picked", "pos", "next_pos", "error_flag")]
+
+REPLAY_ERR_NO_VALID, REPLAY_ERR_INDEX_RANGE, REPLAY_ERR_INDEX_INVALID = 1, 2, 4
 
 
 class LearnerCfg(C.Structure):
@@ -63,7 +65,7 @@ class LearnerCfg(C.Structure):
 
 
 LEARNER_KINDS = {"dqn_conv_mlp": 0, "c51": 1, "qr": 2, "dqn_mlp": 3, "iqn": 4, "da3": 5, "da6": 6}
-BUF_ONLINE, BUF_TARGET, BUF_GRADS, BUF_SQUARE_AVG, BUF_SUPPORT = range(5)
+BUF_ONLINE, BUF_TARGET, BUF_GRADS, BUF_SQUARE_AVG, BUF_SUPPORT, BUF_EXP_AVG, BUF_ADAM_STEPS = range(7)
 
 # every symbol include/maexp_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -113,6 +115,7 @@ SYMBOLS = {
                                         C.c_int, C.c_int, C.c_void_p]),
     "maexp_select_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint32,
                                        C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "maexp_fill_uniform": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint32, C.c_uint32, C.c_void_p]),
     "maexp_last_error": (C.c_char_p, []),
     "maexp_version": (C.c_int, []),
 }

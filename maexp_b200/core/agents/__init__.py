@@ -91,5 +91,5 @@ class BatchedActor:
             q = self.group.q_values(obs, pos=pos)
             _lib.check(self.lib.maexp_select_actions(C.c_void_p(q.data_ptr()), C.c_void_p(self.actions.data_ptr()),
                                                      env.N, b, 4, e0, float(epsilon), self.seed,
-                                                     0, tick & 0xFFFFFFFF, C.c_void_p(self.no_task.data_ptr()), stream))
+                                                     env.first_global_env_id, tick & 0xFFFFFFFF, C.c_void_p(self.no_task.data_ptr()), stream))
         return self.actions

@@ -177,6 +177,27 @@ class LearnerGroup:
     def params(self, which=_lib.BUF_ONLINE):
         return self._buffer(which, self.G * self.P).view(self.G, self.P)
 
+    def optimizer_state(self):
+        """The optimizer's buffers [G, P] (RMSprop: square_avg; Adam: exp_avg, exp_avg_sq and the int32 step counters)."""
+        bufs = [self.params(_lib.BUF_SQUARE_AVG)]
+        if self.config.opt.name == "adam":
+            bufs.append(self.params(_lib.BUF_EXP_AVG))
+            bufs.append(self._buffer(_lib.BUF_ADAM_STEPS, self.G))  # int32 bits behind a float view: copied verbatim
+        return bufs
+
+    def broadcast(self, dist, process_group=None, src=0):
+        """Data-parallel replicas must start from the same weights and optimizer state: every rank initialises its networks
+        from its own torch RNG (build_reference_modules), so rank `src` sends its online and target parameters and the
+        optimizer buffers to the others.  Call after construction and after load_state_dict."""
+        from .... import distributed as mdist
+        mdist.broadcast_tensors(dist, [self.params(_lib.BUF_ONLINE), self.params(_lib.BUF_TARGET)] + self.optimizer_state(),
+                                process_group, src)
+
+    def replica_spread(self, dist, process_group=None):
+        """max |p_rank - p_rank0| over every parameter and rank (0.0 when the replicas are in sync)."""
+        from .... import distributed as mdist
+        return mdist.replica_spread(dist, self.params(_lib.BUF_ONLINE), process_group)
+
     def _write_support(self, values):
         self._buffer(_lib.BUF_SUPPORT, 128)[: values.numel()].copy_(values.to(self.device))
 
@@ -286,9 +307,20 @@ class GraphedUpdate:
         self.grads_view = group.params(_lib.BUF_GRADS)
         self.g_grads = self.g_apply = None
         self.calls = 0
+        self.draw_taus = False
         if group.kind == "iqn" and not all(k in batch for k in ("taus", "tau_dashes", "tau_sel")):
-            # the fractions must live in fixed buffers the caller refreshes: a captured torch.rand would replay one draw
-            raise ValueError("GraphedUpdate on an IQN learner needs taus / tau_dashes / tau_sel tensors in the batch")
+            # the fractions live in fixed buffers refilled before every replay (a captured torch.rand would replay one
+            # draw): one Philox launch over the three tensors (iqn_brain.py:74,87, customs/iqn.py:105-106)
+            g = group
+            self.tau_flat = torch.empty((g.G * g.B * (g.Z + g.Nd) + g.G * g.Z,), dtype=torch.float32, device=g.device)
+            n1, n2 = g.G * g.B * g.Z, g.G * g.B * g.Nd
+            batch["taus"] = self.tau_flat[:n1].view(g.G, g.B, g.Z)
+            batch["tau_dashes"] = self.tau_flat[n1:n1 + n2].view(g.G, g.B, g.Nd)
+            batch["tau_sel"] = self.tau_flat[n1 + n2:].view(g.G, g.Z)
+            self.draw_taus = True
+            self.tau_seed = int(group.config.seed) & 0xFFFFFFFF
+            if dist is not None:  # every rank samples its own shard of the global batch: its own fractions, too
+                self.tau_seed = (self.tau_seed + 0x9E3779B9 * dist.get_rank(process_group)) & 0xFFFFFFFF
 
     def _reduce(self):
         if self.dist is not None:
@@ -296,6 +328,9 @@ class GraphedUpdate:
 
     def step(self):
         self.calls += 1
+        if self.draw_taus:
+            _lib.check(self.group.lib.maexp_fill_uniform(C.c_void_p(self.tau_flat.data_ptr()), self.tau_flat.numel(),
+                                                         self.tau_seed, self.calls & 0xFFFFFFFF, self.group._stream()))
         if self.calls == 1:
             loss = self.group.grads(self.batch)
             self._reduce()

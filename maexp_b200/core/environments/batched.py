@@ -88,6 +88,7 @@ class BatchedEnvironment:
         self.X, self.Y, self.V = self.map.SIZE_X, self.map.SIZE_Y, int(config.visible_range)
         self.merged = config.observation_area_mask == "merged"
         self.tick = 0
+        self.first_global_env_id = int(first_global_env_id)  # Philox keys are global: shards reproduce a single-GPU run
 
         cfg = _lib.EnvCfg()
         cfg.num_envs, cfg.num_agents, cfg.type_objects = self.E, self.N, self.T

@@ -20,7 +20,13 @@ logger = initialize_logging(__name__)
 
 
 class DefaultTrainer:
-    def __init__(self, config, environment, num_envs=None, all_reduce=None, first_global_env_id=0):
+    """dist: the torch.distributed module of an initialised process group (NCCL on the GPUs, one process per GPU) for the
+    data-parallel learner — every rank steps its own environments (pass first_global_env_id = rank * num_envs) and the
+    per-agent networks are replicas: rank 0's initial weights are broadcast, each update all-reduces the flat gradient
+    buffer between the two CUDA graphs of GraphedUpdate.  all_reduce: legacy callable(grads) -> world size (eager path)."""
+
+    def __init__(self, config, environment, num_envs=None, all_reduce=None, first_global_env_id=0, dist=None,
+                 process_group=None, log_path=None):
         self.config = config
         world = environment.world
         self.env = environment if isinstance(environment, BatchedEnvironment) else BatchedEnvironment(
@@ -30,25 +36,39 @@ class DefaultTrainer:
         self.buffer = generate_buffer(config, env)
         self.learner = LearnerGroup(config, env.model_obs_shape, 4, env.N, int(config.batch_size),
                                     obs_stride=env.slot_floats, device=env.device)
+        self.dist, self.process_group = dist, process_group
+        if dist is not None:
+            self.learner.broadcast(dist, process_group)  # replicas start from rank 0's weights
         self.actor = BatchedActor(config, env, self.learner)
         self.batch = self.buffer.new_batch(int(config.batch_size))
         self.active = 1 - self.actor.no_task  # agent_tasks "-1" agents are never trained (abstract_trainer.py:49-51)
         self.epsilon = float(config.epsilon_initial)
         self.all_reduce = all_reduce
-        # single-GPU updates replay from CUDA graphs (about a hundred launches per update otherwise); the IQN learners draw
-        # their quantile fractions with torch.rand per update and the data-parallel path takes the caller's all-reduce: eager
+        # updates replay from CUDA graphs (about a hundred launches per update otherwise) — single GPU, data parallel
+        # (the NCCL all-reduce runs between the gradient graph and the optimizer graph) and IQN (fractions in fixed
+        # buffers refilled by one Philox launch); only a caller-supplied all_reduce callable takes the eager path
         self.graphed = None
-        if all_reduce is None and self.learner.kind != "iqn" and config.get("cuda_graph_update", True):
-            self.graphed = GraphedUpdate(self.learner, self.batch, active=self.active)
+        if all_reduce is None and config.get("cuda_graph_update", True):
+            self.graphed = GraphedUpdate(self.learner, self.batch, active=self.active, dist=dist, process_group=process_group)
+        elif all_reduce is None and dist is not None:
+            from .... import distributed as mdist
+            self.all_reduce = mdist.make_grad_all_reduce(dist, process_group)
         self.tick = 0
         self.episode_count = 0
         self.global_step = 0
         self.history = []
+        self.log_path = log_path
+        self.episode_return = torch.zeros((env.E,), dtype=torch.float32, device=env.device)
 
-    # ---- abstract_loop_handler.py:51-57
-    def populate(self, steps):
+    # ---- abstract_loop_handler.py:45-57
+    def reset(self):
+        """AbstractLoopHandler.reset: a fresh episode in every environment (one ring slot, marked was_reset)."""
         self.env.reset(self.buffer.next_outputs(), tick=self._tick())
         self.buffer.commit()
+        self.episode_return.zero_()
+
+    def populate(self, steps):
+        self.reset()
         for _ in range(steps):
             self.env.step(self.buffer.next_outputs(), tick=self._tick())  # random policy (epsilon = 1)
             self.buffer.commit()
@@ -79,21 +99,40 @@ class DefaultTrainer:
         self.epsilon = max(float(self.config.epsilon_end), self.epsilon * float(self.config.epsilon_decay))
         if self.episode_count % int(self.config.synchronize_frequency) == 0:
             self.learner.synchronize()
+        self.buffer.check(self.batch)  # the replay sampler's error flag (one host sync per episode)
+        self.log_scalar()
+        self.reset()  # default_trainer.py:99: every epoch is one episode
         self.episode_count += 1
 
+    # ---- abstract_loop_handler.py:407-428 (wandb.log of the episode scalars) as one JSON line per episode
+    def log_scalar(self):
+        if not self.history:
+            return
+        row = self.history[-1]
+        if self.log_path and (self.dist is None or self.dist.get_rank(self.process_group) == 0):
+            import json
+            with open(self.log_path, "a") as f:
+                f.write(json.dumps({"step": self.global_step, **{f"episode/{k}": v for k, v in row.items()}}) + "\n")
+
     def run(self, max_epochs=None):
+        """AbstractLoopHandler.run (abstract_loop_handler.py:79-102).  An epoch is one episode of max_episode_length steps in
+        every environment, closed by reset() as in the reference; an environment whose objects run out before that
+        (keep_objects_num off) restarts on its own inside the epoch, where the reference would end the epoch early."""
         cfg = self.config
         self.populate(max(2, int(cfg.populate_steps) // max(1, self.env.E)))
+        self.reset()
         for _ in range(int(max_epochs if max_epochs is not None else cfg.max_epochs)):
-            reward_sum = torch.zeros((), device=self.env.device)
             loss_sum = torch.zeros((), device=self.env.device)
             for _ in range(int(cfg.max_episode_length)):
                 loss, rewards = self.loop_step()
-                reward_sum += rewards.sum()
+                self.episode_return += rewards.sum(dim=1)
                 loss_sum += loss.sum()
-            self.loop_epoch_end()
+            stats = self.env.stats()
+            if stats["error_flag"]:
+                raise RuntimeError("the respawn sampler hit its attempt cap (objects_area too small, SURVEY.md §E-8)")
             self.history.append({"episode": self.episode_count, "epsilon": self.epsilon,
-                                 "reward_per_env": float(reward_sum) / self.env.E, "loss": float(loss_sum)})
+                                 "reward_per_env": float(self.episode_return.mean()), "loss": float(loss_sum)})
+            self.loop_epoch_end()
         return self.history
 
     # ---- abstract_loop_handler.py:149-166 (local files instead of wandb artifacts)
@@ -106,6 +145,8 @@ class DefaultTrainer:
         for agent_id in range(self.env.N):
             self.learner.load_state_dict(agent_id, torch.load(os.path.join(directory, f"agent{agent_id}.pth")))
         self.learner.synchronize()
+        if self.dist is not None:
+            self.learner.broadcast(self.dist, self.process_group)
 
 
 def generate_trainer(config, environment, **kw):

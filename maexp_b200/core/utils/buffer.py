@@ -56,7 +56,8 @@ class DeviceReplayRing:
                 "dones": torch.empty((N, batch_size), dtype=torch.uint8, device=d),
                 "picked": torch.empty((batch_size, 2), dtype=torch.int32, device=d),
                 "pos": torch.empty((N, batch_size, 2), dtype=torch.int8, device=d),
-                "next_pos": torch.empty((N, batch_size, 2), dtype=torch.int8, device=d)}
+                "next_pos": torch.empty((N, batch_size, 2), dtype=torch.int8, device=d),
+                "error_flag": torch.zeros((1,), dtype=torch.int32, device=d)}
 
     def sample(self, batch, seed=0, tick=0, indices=None):
         """Fills `batch` (from new_batch) with uniformly sampled transitions; indices: int32 [B,2]."""
@@ -65,13 +66,28 @@ class DeviceReplayRing:
                                self.dones.data_ptr(), self.was_reset.data_ptr(),
                                None if self.positions is None else self.positions.data_ptr(), self.S, self.env.E, self.env.N,
                                self.env.slot_floats, self.head, self.count)
-        out = _lib.Batch(*[batch[k].data_ptr() for k in ("obs", "next_obs", "actions", "rewards", "dones", "picked", "pos",
-                                                         "next_pos")])
+        out = _lib.Batch(*[batch[k].data_ptr() if k in batch else None
+                           for k in ("obs", "next_obs", "actions", "rewards", "dones", "picked", "pos", "next_pos",
+                                     "error_flag")])
         idx = None if indices is None else C.c_void_p(indices.data_ptr())
         stream = C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
         _lib.check(self.lib.maexp_replay_sample(C.byref(view), B, seed & 0xFFFFFFFF, tick & 0xFFFFFFFF, idx,
                                                 C.byref(out), stream))
         return batch
+
+    @staticmethod
+    def check(batch):
+        """Raises when a sample() into `batch` could not find a valid transition or was given bad picks (synchronises;
+        the trainers call it once per epoch).  The reference cannot fail this way: its deque only holds transitions."""
+        flag = int(batch["error_flag"].item()) if "error_flag" in batch else 0
+        if flag:
+            batch["error_flag"].zero_()
+            why = [text for bit, text in ((_lib.REPLAY_ERR_NO_VALID, "no valid transition in the ring (every stored step is "
+                                           "followed by a reset: the ring is too short for the episode length)"),
+                                          (_lib.REPLAY_ERR_INDEX_RANGE, "an injected (slot, env) pick lies outside the ring"),
+                                          (_lib.REPLAY_ERR_INDEX_INVALID, "an injected pick names a transition into a reset slot"))
+                   if flag & bit]
+            raise _lib.MaexpError("maexp_replay_sample: " + "; ".join(why))
 
 
 def generate_buffer(config, env=None):

@@ -108,10 +108,30 @@ __global__ void select_actions_kernel(const float *q, int8_t *actions, int G, in
     actions[(size_t)(env0 + e) * G + k] = (int8_t)action;
     (void)num_envs_total;
 }
+// U[0,1) floats with torch.rand's mantissa convention (24 random bits): four per Philox call, keyed (seed, 'TAUS'), counter
+// (tick, stream 8, quad index, 0)
+__global__ void fill_uniform_kernel(float *out, long long n, uint32_t seed, uint32_t tick) {
+    const long long quads = (n + 3) / 4;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+        const uint4 w = philox4x32_10(seed, 0x54415553u /*'TAUS'*/, tick, 8u, (uint32_t)q, (uint32_t)(q >> 32));
+        const float v[4] = {unit_float(w.x), unit_float(w.y), unit_float(w.z), unit_float(w.w)};
+        for (int j = 0; j < 4 && q * 4 + j < n; ++j) out[q * 4 + j] = v[j];
+    }
+}
 }  // namespace maexp
 
 extern "C" {
 using namespace maexp;
+
+int maexp_fill_uniform(float *out, int64_t count, uint32_t seed, uint32_t tick, void *stream) {
+    if (!out || count < 1) return fail("maexp_fill_uniform: null or empty buffer");
+    long long blocks = ((count + 3) / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    fill_uniform_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, count, seed, tick);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("maexp_fill_uniform: ") + cudaGetErrorString(e));
+    return 0;
+}
 
 int maexp_decode_relative(const float *obs, const int8_t *positions, float *canvas, int64_t rows, int channels,
                           int visible_range, int size_x, int size_y, int obs_stride, int only_area_plus_one, void *stream) {

@@ -3027,6 +3027,8 @@ float *maexp_learner_buffer(maexp_learner *h, int which) {
     case MAEXP_BUF_GRADS: return h->grads;
     case MAEXP_BUF_SQUARE_AVG: return h->sq;
     case MAEXP_BUF_SUPPORT: return h->support;
+    case MAEXP_BUF_EXP_AVG: return h->exp_avg;
+    case MAEXP_BUF_ADAM_STEPS: return reinterpret_cast<float *>(h->adam_steps);
     }
     return nullptr;
 }

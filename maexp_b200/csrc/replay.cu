@@ -18,6 +18,15 @@ int fail(const std::string &msg);
 
 constexpr uint32_t kStreamReplay = 7;
 constexpr int kMaxRedraws = 64;
+constexpr int kMaxProbes = 4096;
+
+// state slot of the transition of age `age` (state = head-1-age, next = head-age); false when the next slot is a reset
+__device__ __forceinline__ bool valid_transition(const maexp_replay_view &r, int age, int env, int *slot) {
+    int s = (r.head - 1 - age) % r.num_slots;
+    if (s < 0) s += r.num_slots;
+    *slot = s;
+    return !r.was_reset[(size_t)((s + 1) % r.num_slots) * r.num_envs + env];
+}
 
 __global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint32_t seed, uint32_t tick,
                                      const int32_t *indices, const maexp_batch out) {
@@ -25,23 +34,38 @@ __global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint3
     const int N = r.num_agents;
     if (warp >= batch * N) return;
     const int b = warp / N, agent = warp - b * N;
-    int slot, env;
+    int slot = 0, env = 0, flags = 0;
     if (indices) {
         slot = indices[2 * b];
         env = indices[2 * b + 1];
+        if (slot < 0 || slot >= r.num_slots || env < 0 || env >= r.num_envs) {  // never read outside the ring
+            flags |= MAEXP_REPLAY_ERR_INDEX_RANGE;
+            slot = min(max(slot, 0), r.num_slots - 1);
+            env = min(max(env, 0), r.num_envs - 1);
+        }
+        if (r.was_reset[(size_t)((slot + 1) % r.num_slots) * r.num_envs + env]) flags |= MAEXP_REPLAY_ERR_INDEX_INVALID;
     } else {
         // transition age a in [0, count-2]: state slot = head-1-a, next slot = head-a (mod S)
-        uint32_t d = 0;
-        for (;;) {
+        bool ok = false;
+        int age = 0;
+        for (uint32_t d = 0; d < (uint32_t)kMaxRedraws && !ok; ++d) {
             const uint4 w = philox4x32_10(seed, 0x52504C59u /*'RPLY'*/, tick, kStreamReplay, d, (uint32_t)b);
-            const int age = (int)scale(w.x, (uint32_t)(r.count - 1));
+            age = (int)scale(w.x, (uint32_t)(r.count - 1));
             env = (int)scale(w.y, (uint32_t)r.num_envs);
-            slot = (r.head - 1 - age) % r.num_slots;
-            if (slot < 0) slot += r.num_slots;
-            const int nxt = (slot + 1) % r.num_slots;
-            if (!r.was_reset[(size_t)nxt * r.num_envs + env] || ++d >= (uint32_t)kMaxRedraws) break;
+            ok = valid_transition(r, age, env, &slot);
         }
+        // every redraw hit a transition into a reset slot (tiny rings whose envs reset in lock-step): walk the
+        // (age, env) pairs after the last draw in a fixed order; the N warps of a sample take the same walk
+        for (int probe = 0; probe < kMaxProbes && !ok; ++probe) {
+            if (++age >= r.count - 1) {
+                age = 0;
+                if (++env >= r.num_envs) env = 0;
+            }
+            ok = valid_transition(r, age, env, &slot);
+        }
+        if (!ok) flags |= MAEXP_REPLAY_ERR_NO_VALID;  // the row below is NOT a transition; the caller must not train on it
     }
+    if (flags && lane == 0 && out.error_flag) atomicOr(out.error_flag, flags);
     const int nxt = (slot + 1) % r.num_slots;
     const size_t row = (size_t)r.num_envs * N * r.slot_floats;
     // ring slots are agent-major: [S][N][E][slot_floats]
@@ -55,7 +79,7 @@ __global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint3
     }
     if (lane == 0) {
         const size_t m = ((size_t)nxt * r.num_envs + env) * N + agent, o = (size_t)agent * batch + b;
-        out.actions[o] = r.actions[m];
+        out.actions[o] = max((int)r.actions[m], 0);  // -1 marks a reset slot (flagged above): the loss kernels index with it
         out.rewards[o] = r.rewards[m];
         out.dones[o] = r.dones[m];
         if (out.pos && r.positions) {

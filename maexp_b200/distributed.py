@@ -27,6 +27,22 @@ def make_grad_all_reduce(dist, group=None):
     return all_reduce
 
 
+def broadcast_tensors(dist, tensors, group=None, src=0):
+    """Rank `src` sends every tensor of the list (parameters, target parameters, optimizer state) to the other ranks, in
+    place: data-parallel replicas must start from the same state."""
+    for t in tensors:
+        dist.broadcast(t, src=src, group=group)
+
+
+def replica_spread(dist, params, group=None):
+    """max |params_rank - params_rank0| over all elements and ranks: 0.0 when the replicas are in sync."""
+    ref = params.clone()
+    dist.broadcast(ref, src=0, group=group)
+    spread = (params - ref).abs().max().reshape(1)
+    dist.all_reduce(spread, op=dist.ReduceOp.MAX, group=group)
+    return float(spread)
+
+
 def max_over_ranks(dist, values, device):
     """Element-wise maximum of a list of floats over all ranks (device-side timings)."""
     import torch

@@ -32,7 +32,18 @@ def _worker(rank, world, port, out):
         n = all_reduce(grads)
         mx = mdist.max_over_ranks(dist, [1.0 + rank, 5.0 - rank], "cpu")
         sm = mdist.sum_over_ranks(dist, [float(len(ids))], "cpu")
-        out[rank] = (n, grads.clone(), local, mx, sm, (ids[0], ids[-1]))
+        # replicas: every rank initialises its own weights; rank 0's are broadcast, and K identical "updates" (all-reduced
+        # gradient, scaled by 1/world) keep them bit-equal
+        params, state = torch.randn(8, 1000), torch.rand(8, 1000)
+        spread_before = mdist.replica_spread(dist, params)
+        mdist.broadcast_tensors(dist, [params, state])
+        for k in range(3):
+            g = torch.randn(8, 1000)  # differs per rank (seeded by rank above)
+            w = all_reduce(g)
+            state.mul_(0.99).addcmul_(g / w, g / w, value=0.01)
+            params.sub_(1e-3 * (g / w) / (state.sqrt() + 1e-8))
+        spread_after = mdist.replica_spread(dist, params)
+        out[rank] = (n, grads.clone(), local, mx, sm, (ids[0], ids[-1]), spread_before, spread_after, params.clone())
     finally:
         dist.destroy_process_group()
 
@@ -49,3 +60,6 @@ def test_two_rank_gradient_all_reduce_and_sharding():
     assert res[0][3] == res[1][3] == [2.0, 5.0]                           # max over ranks
     assert res[0][4] == [16384.0]
     assert res[0][5] == (0, 8191) and res[1][5] == (8192, 16383)          # disjoint, contiguous global env ids
+    assert res[0][6] == res[1][6] and res[0][6] > 0.1                      # unsynchronised initialisations differ ...
+    assert res[0][7] == res[1][7] == 0.0                                  # ... broadcast + all-reduced updates do not
+    assert torch.equal(res[0][8], res[1][8])

@@ -147,6 +147,67 @@ def test_cuda_learner_group_matches_torch_oracle(kind, B):
             assert abs(float(g.grad_norm.cpu()[a]) - float(norm)) <= 1e-4 * float(norm)
 
 
+@pytest.mark.parametrize("B,G", [(32, 2), (256, 3), (640, 2), (2304, 2)])
+def test_dqn_mlp_learner_matches_torch_oracle(B, G):
+    """BASELINE configs[0] (map=simple, 2 agents, brain=dqn, model=mlp, visible_range=5): MAEXP_LEARNER_DQN_MLP.
+    The reference's model=mlp path raises a TypeError, so there is no live fixture: the network is
+    core/agents/models/mlp.py:14-34 on the flattened C*V*V observation (hidden 120, configs/model/mlp.yaml) under the
+    DQN update of da3_brain.py:69-87, restated in oracle/torch_learner.py (`dqn_mlp`).  Q-values, loss and every gradient
+    of G independently initialised networks, then two full updates; the larger B take the acting-batch inference path."""
+    from maexp_b200.core.agents.brains import LearnerGroup
+    cfg = baseline_config(1).merged_with(batch_size=B)
+    C, V = 3, int(cfg.visible_range)
+    assert cfg.brain == "dqn" and cfg.model.name == "mlp" and V == 5
+    torch.manual_seed(40 + B)
+    g = LearnerGroup(cfg, [C, V, V], 4, G, B)
+    assert g.kind == "dqn_mlp"
+    gen = torch.Generator().manual_seed(B)
+    oracles = []
+    for a in range(G):
+        tg = {k: v + 0.02 * torch.randn(v.shape, generator=gen) for k, v in g.state_dict(a).items()}
+        g.load_state_dict(a, tg, which=1)
+        o = TorchLearner("dqn_mlp", g.state_dict(a), 4, float(cfg.gamma), 1e-3, 0.99, 1e-8)
+        o.target = {k: v.clone() for k, v in tg.items()}
+        oracles.append(o)
+    obs = (torch.rand((G, B, C, V, V), generator=gen) < 0.25).float()
+    nxt = (torch.rand((G, B, C, V, V), generator=gen) < 0.25).float()
+    obs[:, :, -1] -= 1
+    nxt[:, :, -1] -= 1
+    batch = {"obs": pack(g, obs), "next_obs": pack(g, nxt),
+             "actions": torch.randint(0, 4, (G, B), generator=gen).to(torch.int32).cuda(),
+             "rewards": torch.randint(-1, 2, (G, B), generator=gen).float().cuda(),
+             "dones": (torch.rand((G, B), generator=gen) < 0.1).to(torch.uint8).cuda()}
+    q = g.q_values(batch["obs"]).cpu()
+    for a in range(G):
+        assert rel_err(q[a], oracles[a].q_values(obs[a])) < RTOL
+    args = lambda a: (obs[a], nxt[a], batch["actions"][a].cpu().long(), batch["rewards"][a].cpu().double(),
+                      batch["dones"][a].cpu().bool())
+    loss = g.grads(batch).cpu()
+    grads = g.params(2).cpu()
+    for a in range(G):
+        o = oracles[a]
+        o.opt.zero_grad()
+        want = o.loss(*args(a))
+        want.backward()
+        assert abs(float(loss[a]) - float(want.detach())) <= RTOL * abs(float(want.detach()))
+        for name, off, cnt in g.table:
+            got, ref = grads[a, off:off + cnt], o.sd[name].grad.reshape(-1)
+            assert float((got - ref).norm()) <= 1e-4 * float(ref.norm()) + 1e-9, (a, name)
+    for step in range(2):
+        loss = g.learn(batch).cpu()
+        for a in range(G):
+            want, norm = oracles[a].learn(*args(a))
+            assert abs(float(loss[a]) - float(want)) <= 2e-5 * abs(float(want)), (step, a)
+            assert abs(float(g.grad_norm.cpu()[a]) - float(norm)) <= 1e-4 * float(norm)
+    for a in range(G):  # RMSprop's first steps amplify last-bit differences of near-zero gradients: count outliers
+        got, bad, total = g.state_dict(a), 0, 0
+        for k, v in oracles[a].sd.items():
+            v = v.detach()
+            bad += int(((got[k] - v).abs() > 1e-4 + 1e-4 * v.abs()).sum())
+            total += v.numel()
+        assert bad <= total * 1e-3, (a, bad, total)
+
+
 def test_apply_scale_and_inactive_agents():
     """grad_scale (1/world after an all-reduce) and the agent_tasks "-1" mask of abstract_trainer.py:49-51."""
     kind, B, G = "dqn_conv_mlp", 32, 2
@@ -214,6 +275,57 @@ def test_replay_ring_sampling():
     assert torch.equal(batch["picked"].cpu(), p1)
     ring.sample(batch, seed=921, tick=6)
     assert not torch.equal(batch["picked"].cpu(), p1)
+
+
+def test_replay_sampler_flags_a_ring_without_valid_transitions():
+    """count == 2 with every environment reset by the newest slot: no stored step is a transition.  The sampler must say so
+    (error flag, DeviceReplayRing.check raises) and must not hand the loss kernels the reset slot's action -1."""
+    from maexp_b200 import _lib
+    from maexp_b200.core.utils.buffer import DeviceReplayRing
+    from tests.cuda_backend import make_env
+    cfg = baseline_config(5).merged_with(max_episode_length=3)
+    E, B = 32, 16
+    env = make_env(cfg, E, auto_reset=True)
+    ring = DeviceReplayRing(env, 2)
+    env.reset(ring.next_outputs(), tick=0)
+    ring.commit()
+    for t in range(1, 4):  # steps 0..2: done at step L-1 = 2 ...
+        env.step(ring.next_outputs(), tick=t)
+        ring.commit()
+    env.step(ring.next_outputs(), tick=4)  # ... so this call resets every environment in lock-step
+    ring.commit()
+    assert ring.count == 2 and bool(ring.was_reset[ring.head].all())
+    batch = ring.new_batch(B)
+    ring.sample(batch, seed=921, tick=0)
+    torch.cuda.synchronize()
+    assert int(batch["error_flag"].item()) == _lib.REPLAY_ERR_NO_VALID
+    assert bool((batch["actions"] >= 0).all())
+    with pytest.raises(_lib.MaexpError):
+        ring.check(batch)
+    ring.check(batch)  # the flag was cleared by the raise
+    # one more step: the transition reset-slot -> step is valid again, found by the redraws or by the fixed walk
+    env.step(ring.next_outputs(), tick=5)
+    ring.commit()
+    ring.sample(batch, seed=921, tick=1)
+    ring.check(batch)
+    # injected picks: out of range (clamped, flagged) and a pick into a reset slot (flagged, action clamped to 0)
+    bad = torch.tensor([[7, 0]] + [[(ring.head - 1) % 2, 1]] * (B - 1), dtype=torch.int32).cuda()
+    ring.sample(batch, indices=bad)
+    torch.cuda.synchronize()
+    assert int(batch["error_flag"].item()) == _lib.REPLAY_ERR_INDEX_RANGE
+    with pytest.raises(_lib.MaexpError):
+        ring.check(batch)
+    env2 = make_env(cfg, E, auto_reset=True)
+    ring2 = DeviceReplayRing(env2, 2)
+    env2.reset(ring2.next_outputs(), tick=0)
+    ring2.commit()
+    env2.reset(ring2.next_outputs(), tick=1)
+    ring2.commit()
+    into_reset = torch.tensor([[(ring2.head - 1) % 2, 3]] * B, dtype=torch.int32).cuda()
+    ring2.sample(batch, indices=into_reset)
+    torch.cuda.synchronize()
+    assert int(batch["error_flag"].item()) == _lib.REPLAY_ERR_INDEX_INVALID
+    assert bool((batch["actions"] == 0).all())  # the reset slot's -1 never reaches the loss kernels
 
 
 def test_reference_style_brain_interface():
