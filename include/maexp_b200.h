@@ -109,6 +109,9 @@ typedef struct {
                               environments with atomics (the caller zeroes them, as reset() does in the reference):
                               [agents N·X·Y | complete N·X·Y | objects T·X·Y | objects_left T·X·Y | wall_collision X·Y |
                               agents_collision X·Y], maexp_env_heatmap_ints() values in total */
+    uint32_t *objects_bits;/* [N,T,X,E] the same objects_matrix snapshot as bit rows (bit y of word x), ENV-MINOR so that the
+                              step kernel's stores coalesce: what the replay ring keeps for the `objects_channel` canvas input
+                              of the relative / DA6 models (state["objects"], observation_handler.py:99-101) */
 } maexp_obs_out;
 
 typedef struct maexp_env maexp_env;
@@ -189,6 +192,11 @@ typedef struct {
     int32_t num_envs, num_agents, slot_floats;
     int32_t head;              /* newest written slot */
     int32_t count;             /* number of valid consecutive slots ending at head (>= 2) */
+    /* inputs of the extra canvas channels (objects_channel / agents_channel / destination_channel), any may be NULL */
+    const uint32_t *objects_bits; /* [S,N,T,X,E] maexp_obs_out.objects_bits of every slot */
+    const uint8_t *destination;   /* [S,E,N] maexp_obs_out.destination (index of the agent's destination mask) */
+    const uint32_t *dest_table;   /* [M,X] the destination masks as bit rows (bit y of word x) */
+    int32_t type_objects, size_x; /* T, X of the two arrays above */
 } maexp_replay_view;
 
 typedef struct {
@@ -201,6 +209,11 @@ typedef struct {
     int8_t *pos;       /* [N,B,2] observing agent's position in the state (relative / merged models) — may be NULL */
     int8_t *next_pos;  /* [N,B,2] ... in the new state */
     int32_t *error_flag; /* one int32, OR-ed with MAEXP_REPLAY_ERR_* by the sampler (never cleared by it) — may be NULL */
+    /* extra canvas-channel inputs of the state and the new state (what maexp_learner_bind_canvas_inputs takes), may be NULL:
+     * state["objects"] as bit rows, state["agents"], state["destination"] as bit rows (observation_handler.py:95-105) */
+    uint32_t *obj_rows, *next_obj_rows;   /* [N,B,T,X] */
+    int8_t *agents, *next_agents;         /* [N,B,num_agents,2] index-space cells of ALL agents (needs ring positions) */
+    uint32_t *dest_rows, *next_dest_rows; /* [N,B,X] */
 } maexp_batch;
 
 /* maexp_batch.error_flag bits.  NO_VALID: 64 redraws and a 4096-pair walk found only transitions into reset slots (a ring of
@@ -263,6 +276,13 @@ typedef struct {
                                  (hard_shrink_attention.py:13-105; da3.py:46,144, da6.py:67, da3_iqn.py:118-122,245, da6_iqn.py:76-80):
                                  softmax weights <= af_lambd are zeroed before they multiply V and in the exported maps */
     float af_lambd;           /* model.af_lambd (nn.Hardshrink lambd), read when attention_hard */
+    /* config.objects_channel / agents_channel / destination_channel: extra [T,X,Y] / [num_agents,X,Y] / [1,X,Y] channels
+     * concatenated behind the decoded relative canvas (conv_mlp.py:25-27,61; da3.py:31-33,104; iqn.py:55-60,153-159;
+     * da3_iqn.py:96-104,195-211; da6.py:32-37,170-177; da6_iqn.py:42-47,167-174).  Each family reads the flags its
+     * reference constructor reads; subclasses that never use the parent's first layer still size it with them. */
+    int32_t objects_channel, agents_channel, destination_channel;
+    int32_t type_objects;     /* config.type_objects (T) */
+    int32_t team_agents;      /* config.num_agents (the agents channel has one plane per agent of the team) */
 } maexp_learner_cfg;
 
 /* state-embedding producer under the IQN head (brain iqn / da3_iqn, iqn_brain.py:60-115, da3_iqn_brain.py:14-54) */
@@ -302,6 +322,19 @@ int maexp_tc_gemm(const float *A, const float *W, const float *bias, float *C, i
 /* relative / merged models: index-space positions of the observing agent, int8 [G,B,2] for the state batch and for
  * the next-state batch (maexp_batch.pos / next_pos); used by the following grads / q_values calls */
 int maexp_learner_bind_positions(maexp_learner *learner, const int8_t *pos, const int8_t *next_pos);
+/* Inputs of the extra canvas channels for the following grads / q_values calls (device pointers, NULL where the flag is
+ * off): state["objects"] as bit rows uint32 [G,B,T,X] (bit y of word x; maexp_batch.obj_rows), state["agents"] int8
+ * [G,B,num_agents,2] (every agent's index-space cell) and state["destination"] as bit rows uint32 [G,B,X]
+ * (observation_handler.py:95-105); the first of each pair belongs to the state batch, the second to the new state. */
+int maexp_learner_bind_canvas_inputs(maexp_learner *learner, const uint32_t *obj_rows, const uint32_t *next_obj_rows,
+                                     const int8_t *agents, const int8_t *next_agents, const uint32_t *dest_rows,
+                                     const uint32_t *next_dest_rows);
+/* Merged models with observation noise: the reference feeds them the NOISE-FREE "relative" key
+ * (merged_observtion_handler.py:27,41-47), of which they read only the area channel (conv_mlp.py:100-108, da3.py:217-225,
+ * da6.py:161-179) — a pure function of the observing agent's cell.  los_host: int8 [X,Y,V,V] HOST table (1 visible, 0 hidden;
+ * generate_local_area_mask's return value, the same array maexp_tables.los takes); once set, the area canvas is built from
+ * it instead of from the stored (noisy) crop.  NULL unsets. */
+int maexp_learner_set_los(maexp_learner *learner, const int8_t *los_host);
 /* hard_update (core/utils/updates.py:25-34) */
 int maexp_learner_sync_target(maexp_learner *learner, void *stream);
 /* brain.get_action's values: Q [G,batch,A] (C51: sum_j p_j z_j, QR: mean of quantiles) */

@@ -39,16 +39,19 @@ class Tables(C.Structure):
 class ObsOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates",
                                            "positions", "objects", "destination", "actions_taken", "rewards_i8", "done_env",
-                                           "heatmaps")]
+                                           "heatmaps", "objects_bits")]
 
 
 class ReplayView(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "actions", "rewards", "dones", "was_reset", "positions")] + \
-               [(n, C.c_int32) for n in ("num_slots", "num_envs", "num_agents", "slot_floats", "head", "count")]
+               [(n, C.c_int32) for n in ("num_slots", "num_envs", "num_agents", "slot_floats", "head", "count")] + \
+               [(n, C.c_void_p) for n in ("objects_bits", "destination", "dest_table")] + \
+               [(n, C.c_int32) for n in ("type_objects", "size_x")]
 
 
 class Batch(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("obs", "next_obs", "actions", "rewards", "dones", "picked", "pos", "next_pos", "error_flag")]
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "next_obs", "actions", "rewards", "dones", "picked", "pos", "next_pos", "error_flag",
+                                          "obj_rows", "next_obj_rows", "agents", "next_agents", "dest_rows", "next_dest_rows")]
 
 REPLAY_ERR_NO_VALID, REPLAY_ERR_INDEX_RANGE, REPLAY_ERR_INDEX_INVALID = 1, 2, 4
 
@@ -61,7 +64,9 @@ class LearnerCfg(C.Structure):
                [(n, C.c_int32) for n in ("num_quantiles_dash", "num_cosines", "embed_dim", "num_heads", "mlp_hidden",
                                           "block_loop", "area_mask", "size_x", "size_y", "patch_size", "local_patch_size",
                                           "relative_patch_size", "iqn_trunk", "optimizer")] + \
-               [(n, C.c_float) for n in ("beta1", "beta2")] + [("attention_hard", C.c_int32), ("af_lambd", C.c_float)]
+               [(n, C.c_float) for n in ("beta1", "beta2")] + [("attention_hard", C.c_int32), ("af_lambd", C.c_float)] + \
+               [(n, C.c_int32) for n in ("objects_channel", "agents_channel", "destination_channel", "type_objects",
+                                          "team_agents")]
 
 
 LEARNER_KINDS = {"dqn_conv_mlp": 0, "c51": 1, "qr": 2, "dqn_mlp": 3, "iqn": 4, "da3": 5, "da6": 6}
@@ -102,6 +107,8 @@ SYMBOLS = {
     "maexp_learner_attention_tokens": (C.c_int, [C.c_void_p, C.c_int]),
     "maexp_learner_attention": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "maexp_learner_bind_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "maexp_learner_bind_canvas_inputs": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6),
+    "maexp_learner_set_los": (C.c_int, [C.c_void_p, C.c_void_p]),
     "maexp_learner_sync_target": (C.c_int, [C.c_void_p, C.c_void_p]),
     "maexp_learner_q_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "maexp_learner_grads": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),

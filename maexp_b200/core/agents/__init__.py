@@ -78,9 +78,10 @@ class BatchedActor:
         """Copy the learner's online parameters (the actor is a separate handle sized for acting batches)."""
         self.group.params().copy_(self.learner.params())
 
-    def act(self, obs_slot, epsilon, tick, positions=None):
+    def act(self, obs_slot, epsilon, tick, positions=None, ring=None):
         """obs_slot fp32 [N, E, slot] (an agent-major ring slot) -> int8 actions [E, N] on the device.
-        positions int8 [E, N, 2]: the step's agent cells, needed by the relative / merged models."""
+        positions int8 [E, N, 2]: the step's agent cells, needed by the relative / merged models; ring: the
+        DeviceReplayRing whose newest slot is obs_slot, for the models that read the extra canvas channels."""
         env, stream = self.env, C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
         for e0 in range(0, env.E, self.chunk):
             b = min(self.chunk, env.E - e0)
@@ -88,7 +89,8 @@ class BatchedActor:
             pos = None
             if self.group.area_mask != "local":
                 pos = positions[e0:e0 + b].transpose(0, 1).contiguous()  # [N, b, 2]
-            q = self.group.q_values(obs, pos=pos)
+            canvas = ring.canvas_inputs(e0, b) if ring is not None and any(self.group.canvas_reads) else None
+            q = self.group.q_values(obs, pos=pos, canvas=canvas)
             _lib.check(self.lib.maexp_select_actions(C.c_void_p(q.data_ptr()), C.c_void_p(self.actions.data_ptr()),
                                                      env.N, b, 4, e0, float(epsilon), self.seed,
                                                      env.first_global_env_id, tick & 0xFFFFFFFF, C.c_void_p(self.no_task.data_ptr()), stream))

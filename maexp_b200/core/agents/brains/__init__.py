@@ -43,10 +43,8 @@ def learner_kind(config):
         if config.brain not in ("da3_iqn", "iqn"):
             raise ValueError("model da3_iqn / da6_iqn needs an IQN brain (brain=da3_iqn)")
         mask = config.observation_area_mask
-        if config.model.get("attention") == "aoa" or config.get("objects_channel") or config.get("agents_channel") or \
-                config.get("destination_channel"):
-            raise ValueError("attention IQN models are implemented with soft / hard-shrink attention and without extra "
-                             "canvas channels")
+        if config.model.get("attention") == "aoa":
+            raise ValueError("attention IQN models are implemented with soft / hard-shrink attention")
         if config.model.name == "da6_iqn" and mask != "merged":
             raise ValueError("da6_iqn reads the merged view (customs/da6_iqn.py:160-176)")
         if config.model.name == "da3_iqn" and mask == "local" and int(config.model.patch_size) != 1:
@@ -54,28 +52,56 @@ def learner_kind(config):
     elif config.model.name == "da6" or kind == "da6":
         if kind != "da6" or config.model.name != "da6":
             raise ValueError("brain=da6 and model=da6 go together (da6_brain.py, customs/da6.py)")
-        if config.observation_area_mask != "merged" or config.get("objects_channel") or config.get("agents_channel"):
-            raise ValueError("DA6 is implemented for the merged view, without objects / agents channels")
+        if config.observation_area_mask != "merged":
+            raise ValueError("DA6 reads the merged view (customs/da6.py:161-179)")
     elif config.model.name == "da3" or kind == "da3":
         if kind != "da3" or config.model.name != "da3":
             raise ValueError("brain=da3 and model=da3 go together (da3_brain.py, customs/da3.py)")
-        if config.get("objects_channel") or (config.observation_area_mask == "local" and int(config.model.patch_size) != 1):
-            raise ValueError("DA3 is implemented without the objects channel; local view: patch_size=1")
+        if config.observation_area_mask == "local" and int(config.model.patch_size) != 1:
+            raise ValueError("DA3 on the local view is implemented for patch_size=1")
     elif config.model.name not in ("conv_mlp", "da3_baseline", "categorical_dqn", "qr_dqn", "iqn"):
         logger.warning(f"Unexpected network is given. config.model.name: {config.model.name}")
         raise ValueError()
     if config.observation_area_mask != "local" and kind not in ("dqn_conv_mlp", "da3", "da6", "iqn"):
         raise ValueError("relative / merged views are implemented for the conv_mlp DQN, IQN, DA3 / DA6 and their IQN variants")
-    if config.observation_area_mask != "local" and (config.get("objects_channel") or config.get("agents_channel")):
-        raise ValueError("objects_channel / agents_channel canvas inputs are not implemented")
-    if config.observation_area_mask == "merged" and config.observation_noise:
-        # the merged models read the area channel of the NOISE-FREE "relative" key (merged_observtion_handler.py:26-29);
-        # the replay ring keeps only the noisy crop, so this combination is refused rather than approximated
-        raise ValueError("merged view with observation noise is not implemented in the learner")
+    if config.observation_area_mask == "local" and kind in ("dqn_conv_mlp", "da3", "iqn") and canvas_flags(config, kind)[0]:
+        # the reference sizes the first layer for C + extra channels but feeds it the C-channel crop (conv_mlp.py:25-27,61)
+        raise ValueError("objects_channel / agents_channel / destination_channel need the relative or merged view")
     return kind, max_norm
 
 
 AREA_MASKS = {"local": 0, "relative": 1, "merged": 2}
+
+
+def los_table(config, world=None):
+    """int8 [X,Y,V,V] line-of-sight table of the configuration's map (local_area_mask.py:50-97)."""
+    from ...handlers.observations.masks import generate_observation_area_mask
+    if world is None:
+        from ...maps import generate_map
+        from ...worlds import generate_world
+        world = generate_world(config, generate_map(config))
+    return generate_observation_area_mask(config.merged_with(observation_area_mask="local"), world)
+
+
+def canvas_flags(config, kind):
+    """(extra in_chans the model family's constructor adds, (objects, agents, destination) it reads in state_encoder).
+    conv_mlp.py:25-27,61; da3.py:31-33,104; iqn.py:55-60,153-159; da3_iqn.py:96-104,195-211; da6.py:32-37,170-177;
+    da6_iqn.py:42-47,167-174.  The merged subclasses keep the parent's first layer (sized with the flags) unused."""
+    o, a, d = (bool(config.get(k)) for k in ("objects_channel", "agents_channel", "destination_channel"))
+    name = config.model.name
+    if kind == "dqn_conv_mlp" or (kind == "da3" and name == "da3"):
+        a = d = False
+    elif kind == "da6" or (kind == "iqn" and name == "iqn"):
+        d = False
+    elif kind == "iqn" and name in ("da3_iqn", "da6_iqn"):
+        pass
+    else:
+        o = a = d = False
+    extra = (int(config.type_objects) if o else 0) + (int(config.num_agents) if a else 0) + int(d)
+    reads = config.observation_area_mask == "relative" or name in ("da6", "da6_iqn")
+    if name == "da6_iqn":
+        d = False  # its own relative stack takes objects + agents only; the destination flag sizes the unused parent
+    return extra, (o and reads, a and reads, d and reads)
 
 
 class LearnerGroup:
@@ -133,6 +159,11 @@ class LearnerGroup:
         else:
             cfg.alpha, cfg.one_minus_alpha = float(opt.alpha), 1.0 - float(opt.alpha)
         cfg.max_norm = max_norm
+        for k in ("objects_channel", "agents_channel", "destination_channel"):
+            setattr(cfg, k, int(bool(config.get(k))))
+        cfg.type_objects, cfg.team_agents = int(config.type_objects), int(config.num_agents)
+        self.T, self.N_team, self.X, self.Y = cfg.type_objects, cfg.team_agents, cfg.size_x, cfg.size_y
+        self.canvas_reads = canvas_flags(config, self.kind)[1]  # which of objects / agents / destination the forward pass reads
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.maexp_learner_create(C.byref(cfg), C.byref(handle)))
@@ -229,12 +260,36 @@ class LearnerGroup:
         _lib.check(self.lib.maexp_learner_bind_positions(self.h, C.c_void_p(pos.data_ptr()),
                                                          None if next_pos is None else C.c_void_p(next_pos.data_ptr())))
 
-    def q_values(self, obs, use_target=False, tau_sel=None, pos=None):
+    def bind_canvas_inputs(self, batch, keys=("obj_rows", "next_obj_rows", "agents", "next_agents", "dest_rows", "next_dest_rows")):
+        """state["objects"] (bit rows int32 [G,b,T,X]), state["agents"] (int8 [G,b,num_agents,2]) and state["destination"]
+        (bit rows int32 [G,b,X]) of the state and the new state, for the models that read the extra canvas channels."""
+        o, a, d = self.canvas_reads
+        ptrs = []
+        for key, need in zip(keys, (o, o, a, a, d, d)):
+            t = batch.get(key) if need else None
+            if need and t is None and not key.startswith("next_"):
+                raise ValueError(f"this model reads the {key} canvas input (objects_channel / agents_channel / destination_channel)")
+            ptrs.append(None if t is None else C.c_void_p(t.data_ptr()))
+        self._canvas_keep = [batch.get(k) for k in keys]
+        _lib.check(self.lib.maexp_learner_bind_canvas_inputs(self.h, *ptrs))
+
+    def set_los(self, table):
+        """Merged models under observation noise: the int8 [X,Y,V,V] line-of-sight table (numpy) the noise-free area
+        channel is rebuilt from (merged_observtion_handler.py:27,41-47)."""
+        import numpy as _np
+        t = _np.ascontiguousarray(table, _np.int8)
+        assert t.shape == (self.X, self.Y, self.V, self.V), t.shape
+        _lib.check(self.lib.maexp_learner_set_los(self.h, C.c_void_p(t.ctypes.data)))
+
+    def q_values(self, obs, use_target=False, tau_sel=None, pos=None, canvas=None):
         """obs fp32 [G, b, obs_stride] on the device -> Q [G, b, A].  IQN: tau_sel [G, Nq] (drawn if None,
-        customs/iqn.py:105-106).  Relative / merged models: pos int8 [G, b, 2]."""
+        customs/iqn.py:105-106).  Relative / merged models: pos int8 [G, b, 2]; canvas: dict with obj_rows / agents /
+        dest_rows for the models that read the extra canvas channels."""
         b = obs.shape[1]
         if pos is not None:
             self.bind_positions(pos.contiguous())
+        if any(self.canvas_reads):
+            self.bind_canvas_inputs(canvas or {})
         q = self.q if b == self.B else torch.empty((self.G, b, self.A), dtype=torch.float32, device=self.device)
         if self.kind == "iqn":
             if tau_sel is None:
@@ -262,6 +317,8 @@ class LearnerGroup:
         p = lambda t: C.c_void_p(t.data_ptr())
         if self.area_mask != "local":
             self.bind_positions(batch["pos"], batch["next_pos"])
+        if any(self.canvas_reads):
+            self.bind_canvas_inputs(batch)
         if self.kind == "iqn":  # quantile fractions: injected for parity tests, else drawn like iqn_brain.py:74,87
             d = self.device
             taus = batch["taus"] if "taus" in batch else torch.rand((self.G, self.B, self.Z), device=d)
@@ -357,6 +414,8 @@ class Brain:
         self.device = torch.device("cuda:0")
         self.group = LearnerGroup(config, obs_shape, act_size, 1, int(config.batch_size), device=self.device)
         self.view = "local" if config.observation_area_mask in ("local", "merged") else "relative"
+        if config.observation_area_mask == "merged" and config.observation_noise:
+            self.group.set_los(los_table(config))  # the noise-free "relative" key's area channel
 
     def _pack(self, x):
         g = self.group
@@ -374,6 +433,31 @@ class Brain:
         pos = torch.stack([px.reshape(-1), py.reshape(-1)], dim=1).to(torch.int8)
         return pos.reshape(1, -1, 2).contiguous().to(self.device)
 
+    @staticmethod
+    def _bit_rows(t):
+        """[..., X, Y] 0/1 matrices -> int32 [..., X] bit rows (bit y of word x), the library's layout."""
+        t = (torch.as_tensor(t) != 0).to(torch.int64)
+        weights = (torch.ones((), dtype=torch.int64) << torch.arange(t.shape[-1], dtype=torch.int64))
+        return (t * weights).sum(dim=-1).to(torch.int32)
+
+    def _canvas(self, state, prefix=""):
+        """The reference's "objects" / "agents" / "destination" state keys (observation_handler.py:95-105) in the
+        library's layout, for the models that concatenate them onto the relative canvas."""
+        o, a, d = self.group.canvas_reads
+        out = {}
+        if o:
+            x = torch.as_tensor(state["objects"])
+            x = x.reshape(-1, *x.shape[-3:])
+            out[prefix + "obj_rows"] = self._bit_rows(x).reshape(1, x.shape[0], -1).contiguous().to(self.device)
+        if a:
+            x = torch.as_tensor(state["agents"]).to(torch.int8)
+            out[prefix + "agents"] = x.reshape(1, -1, x.shape[-2], 2).contiguous().to(self.device)
+        if d:
+            x = torch.as_tensor(state["destination"])
+            x = x.reshape(-1, *x.shape[-2:])
+            out[prefix + "dest_rows"] = self._bit_rows(x).reshape(1, x.shape[0], -1).contiguous().to(self.device)
+        return out
+
     @torch.no_grad()
     def get_action(self, state):
         """int for the plain brains (abstract_brain.py:52-64); (action, attns) for the attention brains:
@@ -381,7 +465,7 @@ class Brain:
         [local_attns, relative_attns] for the merged models and DA6 (da3_brain.py:47-56, customs/da3.py:167-176,
         customs/da6.py:128-165) — and da3_baseline a zero placeholder (da3_brain.py:93-123)."""
         pos = self._positions(state, False) if self.group.area_mask != "local" else None
-        q = self.group.q_values(self._pack(state[self.view].unsqueeze(0)), pos=pos)
+        q = self.group.q_values(self._pack(state[self.view].unsqueeze(0)), pos=pos, canvas=self._canvas(state))
         action = int(q[0, 0].argmax().item())
         brain = self.config.brain
         if brain == "da3_baseline":
@@ -405,6 +489,8 @@ class Brain:
                  "dones": dones_ind.to(self.device).to(torch.uint8).reshape(1, -1).contiguous()}
         if self.group.area_mask != "local":
             batch["pos"], batch["next_pos"] = self._positions(states_ind, True), self._positions(next_states_ind, True)
+            batch.update(self._canvas(states_ind))
+            batch.update(self._canvas(next_states_ind, "next_"))
         loss = self.group.learn(batch)
         return {"total_loss": loss[0].detach().cpu()}  # always a dict
 

@@ -32,6 +32,16 @@ class _MLP(nn.Module):
         self.fc_post = nn.Linear(input_size, output_size)
 
 
+def extra_channels(config, family):
+    """in_chans the reference's constructors add for the canvas inputs they concatenate on the relative view: ConvMLP and
+    DA3 read objects_channel (conv_mlp.py:25-27, da3.py:31-33), IQN objects + agents (iqn.py:55-60), DA3_IQN all three
+    (da3_iqn.py:96-104); DA6 / DA6_IQN put objects + agents on their relative stack (da6.py:32-37, da6_iqn.py:42-47)."""
+    t = int(config.type_objects) if config.get("objects_channel") else 0
+    n = int(config.num_agents) if config.get("agents_channel") else 0
+    d = 1 if config.get("destination_channel") else 0
+    return {"conv_mlp": t, "da3": t, "iqn": t + n, "da6": t + n, "da3_iqn": t + n + d}[family]
+
+
 def conv_output_size(config, obs_shape):
     """Flattened size of Conv's output (conv k2 s1 -> max_pool2d(2,2) -> conv k2 s1)."""
     h2, w2 = (int(obs_shape[1]) - 1) // 2 - 1, (int(obs_shape[2]) - 1) // 2 - 1
@@ -39,10 +49,10 @@ def conv_output_size(config, obs_shape):
 
 
 class _ConvHeads(nn.Module):
-    def __init__(self, config, obs_shape, heads):
+    def __init__(self, config, obs_shape, heads, extra=0):
         super().__init__()
-        self.conv = _Conv(config, obs_shape[0], config.model.output_channel)
-        torch.randn(1, *obs_shape)  # the reference probes the conv with a random input here (conv_mlp.py:51)
+        self.conv = _Conv(config, int(obs_shape[0]) + extra, config.model.output_channel)
+        torch.randn(1, int(obs_shape[0]) + extra, *obs_shape[1:])  # the reference probes the conv with a random input here (conv_mlp.py:51)
         d = conv_output_size(config, obs_shape)
         for name, out in heads:
             setattr(self, name, _MLP(config, d, out))
@@ -53,8 +63,9 @@ class _IQN(nn.Module):
 
     def __init__(self, config, obs_shape, act_size):
         super().__init__()
-        self.conv = _Conv(config, obs_shape[0], config.model.output_channel)
-        torch.randn(1, *obs_shape)  # customs/iqn.py:143
+        x = extra_channels(config, "iqn")
+        self.conv = _Conv(config, int(obs_shape[0]) + x, config.model.output_channel)
+        torch.randn(1, int(obs_shape[0]) + x, *obs_shape[1:])  # customs/iqn.py:143
         d = conv_output_size(config, obs_shape)
         self.state_embedder = _MLP(config, d, d)
         self.cosine_net = nn.Module()
@@ -89,8 +100,9 @@ class _MergedConvMLP(nn.Module):
     def __init__(self, config, obs_shape, act_size):
         super().__init__()
         v = int(config.visible_range)
-        self.conv = _Conv(config, obs_shape[0], config.model.output_channel)
-        torch.randn(1, *obs_shape)
+        x = extra_channels(config, "conv_mlp")
+        self.conv = _Conv(config, int(obs_shape[0]) + x, config.model.output_channel)
+        torch.randn(1, int(obs_shape[0]) + x, *obs_shape[1:])
         self.mlp = _MLP(config, conv_output_size(config, obs_shape), act_size)  # replaced below, as in the reference
         self.local_conv = _Conv(config, obs_shape[0], config.model.output_channel)
         self.relative_conv = _Conv(config, 1, config.model.output_channel)
@@ -134,11 +146,13 @@ class _PatchEmbed(nn.Module):
 class _DA3(nn.Module):
     """Parameter layout and construction order of customs/da3.py:22-60."""
 
+    FAMILY = "da3"
+
     def __init__(self, config, obs_shape, act_size):
         super().__init__()
         m = config.model
         tokens = (int(obs_shape[1]) // int(m.patch_size)) * (int(obs_shape[2]) // int(m.patch_size)) + 1
-        self.patch_embed = _PatchEmbed(int(m.patch_size), int(obs_shape[0]), int(m.embed_dim))
+        self.patch_embed = _PatchEmbed(int(m.patch_size), int(obs_shape[0]) + extra_channels(config, self.FAMILY), int(m.embed_dim))
         self.saliency_vector = nn.Parameter(torch.zeros(1, 1, int(m.embed_dim)))
         self.pos_embed = nn.Parameter(torch.zeros(1, tokens, int(m.embed_dim)))
         self.blocks = nn.ModuleList([_Block(int(m.embed_dim), float(m.mlp_ratio)) for _ in range(int(m.block_loop))])
@@ -177,6 +191,7 @@ class _IQNHead(nn.Module):
 
 class _DA3IQN(_DA3):
     """customs/da3_iqn.py:87-145: DA3's transformer with the IQN head."""
+    FAMILY = "da3_iqn"
 
     def __init__(self, config, obs_shape, act_size):
         super().__init__(config, obs_shape, act_size)
@@ -185,6 +200,7 @@ class _DA3IQN(_DA3):
 
 class _MergedDA3IQN(_MergedDA3):
     """customs/da3_iqn.py:213-265"""
+    FAMILY = "da3_iqn"
 
     def __init__(self, config, obs_shape, act_size):
         super().__init__(config, obs_shape, act_size)
@@ -194,11 +210,12 @@ class _MergedDA3IQN(_MergedDA3):
 
 class _DA6IQN(_DA3):
     """customs/da6_iqn.py:24-96: DA3_IQN's (unused) parameters plus the two DA6 stages; patch sizes 5 and 1 are hard-coded."""
+    FAMILY = "da3_iqn"
 
     def __init__(self, config, obs_shape, act_size):
         super().__init__(config, obs_shape, act_size)
         m, v, e = config.model, int(config.visible_range), int(config.model.embed_dim)
-        self.relative_patch_embed = _PatchEmbed(5, 1, e)
+        self.relative_patch_embed = _PatchEmbed(5, 1 + extra_channels(config, "da6"), e)
         self.local_patch_embed = _PatchEmbed(1, int(obs_shape[0]), e)
         self.saliency_vector = nn.Parameter(torch.zeros(1, 1, e))
         self.relative_pos_embed = nn.Parameter(torch.zeros(1, (int(obs_shape[1]) // 5) * (int(obs_shape[2]) // 5) + 1, e))
@@ -211,13 +228,13 @@ class _DA6IQN(_DA3):
 
 
 class _DA6(nn.Module):
-    """Parameter layout and construction order of customs/da6.py:22-96 (objects_channel / agents_channel off)."""
+    """Parameter layout and construction order of customs/da6.py:22-96."""
 
     def __init__(self, config, obs_shape, act_size):
         super().__init__()
         m, v, e = config.model, int(config.visible_range), int(config.model.embed_dim)
         rp, lp = int(m.relative_patch_size), int(m.local_patch_size)
-        self.relative_patch_embed = _PatchEmbed(rp, 1, e)
+        self.relative_patch_embed = _PatchEmbed(rp, 1 + extra_channels(config, "da6"), e)
         self.local_patch_embed = _PatchEmbed(lp, int(obs_shape[0]), e)
         self.saliency_vector = nn.Parameter(torch.zeros(1, 1, e))
         self.relative_pos_embed = nn.Parameter(torch.zeros(1, (int(obs_shape[1]) // rp) * (int(obs_shape[2]) // rp) + 1, e))
@@ -236,7 +253,7 @@ def build_reference_modules(config, obs_shape, act_size):
     if name in ("conv_mlp", "da3_baseline"):
         if config.observation_area_mask == "merged":
             return _MergedConvMLP(config, obs_shape, act_size)
-        return _ConvHeads(config, obs_shape, [("mlp", act_size)])
+        return _ConvHeads(config, obs_shape, [("mlp", act_size)], extra=extra_channels(config, "conv_mlp"))
     if name == "categorical_dqn":
         z = int(config.model.num_atoms)
         return _ConvHeads(config, obs_shape, [("fc_V", z), ("fc_A", act_size * z)])

@@ -242,7 +242,7 @@ class BatchedEnvironment:
     def _out_struct(self, out):
         s = _lib.ObsOut()
         for name in ("obs", "obs_rel", "rewards", "dones", "was_reset", "coordinates", "positions", "objects",
-                     "destination", "actions_taken", "rewards_i8", "done_env", "heatmaps"):
+                     "destination", "actions_taken", "rewards_i8", "done_env", "heatmaps", "objects_bits"):
             t = out.get(name)
             if t is not None:
                 assert t.is_cuda and t.is_contiguous()

@@ -32,6 +32,9 @@ class DefaultEvaluator:
         # weights live in a LearnerGroup sized like the actor's chunks (no optimizer step is ever taken)
         self.learner = LearnerGroup(config, env.model_obs_shape, 4, env.N, 1, obs_stride=env.slot_floats, device=env.device)
         self.actor = BatchedActor(config, env, self.learner)
+        if env.merged and config.observation_noise:  # see DefaultTrainer
+            self.learner.set_los(env.los_table)
+            self.actor.group.set_los(env.los_table)
         self.tick = 0
         self.episode_count = 0
         self.history = []
@@ -61,7 +64,7 @@ class DefaultEvaluator:
             for _ in range(int(self.config.max_episode_length)):
                 head = ring.head
                 positions = None if ring.positions is None else ring.positions[head]
-                actions = self.actor.act(ring.obs[head], 0.0, self.tick, positions=positions)  # greedy
+                actions = self.actor.act(ring.obs[head], 0.0, self.tick, positions=positions, ring=ring)  # greedy
                 out = ring.next_outputs()
                 env.step(out, actions=actions, tick=self._tick())
                 ring.commit()

@@ -40,6 +40,11 @@ class DefaultTrainer:
         if dist is not None:
             self.learner.broadcast(dist, process_group)  # replicas start from rank 0's weights
         self.actor = BatchedActor(config, env, self.learner)
+        if env.merged and config.observation_noise:
+            # the merged models read the area channel of the noise-free "relative" key (merged_observtion_handler.py:27,41-47):
+            # rebuilt from the environment's line-of-sight table, the ring only keeps the noisy crop
+            self.learner.set_los(env.los_table)
+            self.actor.group.set_los(env.los_table)
         self.batch = self.buffer.new_batch(int(config.batch_size))
         self.active = 1 - self.actor.no_task  # agent_tasks "-1" agents are never trained (abstract_trainer.py:49-51)
         self.epsilon = float(config.epsilon_initial)
@@ -87,7 +92,7 @@ class DefaultTrainer:
         self.actor.refresh()
         head = self.buffer.head
         positions = None if self.buffer.positions is None else self.buffer.positions[head]
-        actions = self.actor.act(self.buffer.obs[head], self.epsilon, self.tick, positions=positions)
+        actions = self.actor.act(self.buffer.obs[head], self.epsilon, self.tick, positions=positions, ring=self.buffer)
         out = self.buffer.next_outputs()
         self.env.step(out, actions=actions, tick=self._tick())
         self.buffer.commit()

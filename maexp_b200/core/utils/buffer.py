@@ -28,6 +28,20 @@ class DeviceReplayRing:
         # (observation_handler.py:150-216); local-view rings do not spend a store per agent on them
         self.positions = None if env.config.observation_area_mask == "local" and not keep_positions else \
             torch.zeros((self.S, E, N, 2), dtype=torch.int8, device=d)
+        # inputs of the extra canvas channels the relative / DA6 models concatenate (state["objects"], state["agents"],
+        # state["destination"], observation_handler.py:95-105): the per-agent objects snapshot as bit rows (env-minor, as the
+        # step kernel stores them), every agent's cell (= positions) and the index of the agent's destination mask
+        cfg = env.config
+        canvas = cfg.observation_area_mask != "local"
+        self.objects_bits = self.destination = self.dest_table = None
+        if canvas and cfg.get("objects_channel"):
+            self.objects_bits = torch.zeros((self.S, N, env.T, env.X, E), dtype=torch.int32, device=d)
+        if canvas and cfg.get("destination_channel"):
+            self.destination = torch.zeros((self.S, E, N), dtype=torch.uint8, device=d)
+            masks = torch.from_numpy(env.destination_masks != 0).to(torch.int64)  # [M, X, Y]
+            rows = (masks << torch.arange(env.Y, dtype=torch.int64)).sum(dim=-1)
+            self.dest_table = rows.to(torch.int32).contiguous().to(d)
+        self.keep_agents = bool(canvas and cfg.get("agents_channel"))
         self.head, self.count = -1, 0
 
     def __len__(self):
@@ -41,6 +55,10 @@ class DeviceReplayRing:
                "was_reset": self.was_reset[s], "actions_taken": self.actions[s]}
         if self.positions is not None:
             out["positions"] = self.positions[s]
+        if self.objects_bits is not None:
+            out["objects_bits"] = self.objects_bits[s]
+        if self.destination is not None:
+            out["destination"] = self.destination[s]
         return out
 
     def commit(self):
@@ -49,7 +67,7 @@ class DeviceReplayRing:
 
     def new_batch(self, batch_size):
         N, d, sf = self.env.N, self.env.device, self.env.slot_floats
-        return {"obs": torch.empty((N, batch_size, sf), dtype=torch.float32, device=d),
+        b = {"obs": torch.empty((N, batch_size, sf), dtype=torch.float32, device=d),
                 "next_obs": torch.empty((N, batch_size, sf), dtype=torch.float32, device=d),
                 "actions": torch.empty((N, batch_size), dtype=torch.int32, device=d),
                 "rewards": torch.empty((N, batch_size), dtype=torch.float32, device=d),
@@ -58,6 +76,17 @@ class DeviceReplayRing:
                 "pos": torch.empty((N, batch_size, 2), dtype=torch.int8, device=d),
                 "next_pos": torch.empty((N, batch_size, 2), dtype=torch.int8, device=d),
                 "error_flag": torch.zeros((1,), dtype=torch.int32, device=d)}
+        e = self.env
+        if self.objects_bits is not None:
+            b["obj_rows"] = torch.zeros((N, batch_size, e.T, e.X), dtype=torch.int32, device=d)
+            b["next_obj_rows"] = torch.zeros((N, batch_size, e.T, e.X), dtype=torch.int32, device=d)
+        if self.keep_agents:
+            b["agents"] = torch.zeros((N, batch_size, N, 2), dtype=torch.int8, device=d)
+            b["next_agents"] = torch.zeros((N, batch_size, N, 2), dtype=torch.int8, device=d)
+        if self.destination is not None:
+            b["dest_rows"] = torch.zeros((N, batch_size, e.X), dtype=torch.int32, device=d)
+            b["next_dest_rows"] = torch.zeros((N, batch_size, e.X), dtype=torch.int32, device=d)
+        return b
 
     def sample(self, batch, seed=0, tick=0, indices=None):
         """Fills `batch` (from new_batch) with uniformly sampled transitions; indices: int32 [B,2]."""
@@ -65,15 +94,32 @@ class DeviceReplayRing:
         view = _lib.ReplayView(self.obs.data_ptr(), self.actions.data_ptr(), self.rewards.data_ptr(),
                                self.dones.data_ptr(), self.was_reset.data_ptr(),
                                None if self.positions is None else self.positions.data_ptr(), self.S, self.env.E, self.env.N,
-                               self.env.slot_floats, self.head, self.count)
+                               self.env.slot_floats, self.head, self.count,
+                               None if self.objects_bits is None else self.objects_bits.data_ptr(),
+                               None if self.destination is None else self.destination.data_ptr(),
+                               None if self.dest_table is None else self.dest_table.data_ptr(), self.env.T, self.env.X)
         out = _lib.Batch(*[batch[k].data_ptr() if k in batch else None
                            for k in ("obs", "next_obs", "actions", "rewards", "dones", "picked", "pos", "next_pos",
-                                     "error_flag")])
+                                     "error_flag", "obj_rows", "next_obj_rows", "agents", "next_agents", "dest_rows",
+                                     "next_dest_rows")])
         idx = None if indices is None else C.c_void_p(indices.data_ptr())
         stream = C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
         _lib.check(self.lib.maexp_replay_sample(C.byref(view), B, seed & 0xFFFFFFFF, tick & 0xFFFFFFFF, idx,
                                                 C.byref(out), stream))
         return batch
+
+    def canvas_inputs(self, e0, b):
+        """The extra canvas-channel inputs of the newest slot's states for envs [e0, e0 + b), in the learner's layout
+        (what BatchedActor hands to LearnerGroup.q_values): obj_rows [N,b,T,X], agents [N,b,N,2], dest_rows [N,b,X]."""
+        out, h, N = {}, self.head, self.env.N
+        if self.objects_bits is not None:
+            out["obj_rows"] = self.objects_bits[h, :, :, :, e0:e0 + b].permute(0, 3, 1, 2).contiguous()
+        if self.keep_agents:
+            out["agents"] = self.positions[h, e0:e0 + b].unsqueeze(0).expand(N, b, N, 2).contiguous()
+        if self.destination is not None:
+            idx = self.destination[h, e0:e0 + b].transpose(0, 1).long()  # [N, b]
+            out["dest_rows"] = self.dest_table[idx].contiguous()
+        return out
 
     @staticmethod
     def check(batch):

@@ -70,9 +70,12 @@ __global__ void __launch_bounds__(256) heatmap_observation_vec_kernel(const floa
     }
 }
 
-// one thread per canvas element, coalesced along y; HBM-bound: writes 4*C*X*Y bytes per observation
+// one thread per canvas element, coalesced along y; HBM-bound: writes 4*C*X*Y bytes per observation.  canvas_stride: floats
+// between consecutive rows of the canvas (>= Cout*X*Y: extra channels may follow).  los (only_area only): the [X,Y,V,V]
+// line-of-sight table; the area channel is then table - 1 instead of the crop's last channel, i.e. the NOISE-FREE "relative"
+// key the merged models read (merged_observtion_handler.py:27,41-47) whatever noise the stored crop carries.
 __global__ void decode_relative_kernel(const float *obs, const int8_t *pos, float *canvas, long long rows, int C, int V,
-                                       int X, int Y, int obs_stride, int only_area) {
+                                       int X, int Y, int obs_stride, int only_area, long long canvas_stride, const int8_t *los) {
     const int R = V / 2, Cout = only_area ? 1 : C;
     const long long total = rows * Cout * X * Y;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -83,10 +86,26 @@ __global__ void decode_relative_kernel(const float *obs, const int8_t *pos, floa
         const int px = pos[row * 2], py = pos[row * 2 + 1];
         const int a = x - px + R, b = y - py + R;  // window cell of map cell (x, y); window∩map is what the slices copy
         float v = (c == C - 1) ? -1.0f : 0.0f;
-        if (a >= 0 && a < V && b >= 0 && b < V) v = obs[row * obs_stride + ((long long)c * V + a) * V + b];
+        if (a >= 0 && a < V && b >= 0 && b < V) {
+            if (los) v = (float)los[(((long long)px * Y + py) * V + a) * V + b] - 1.0f;  // observation_handler.py:107-108
+            else v = obs[row * obs_stride + ((long long)c * V + a) * V + b];
+        }
         // merged models use canvas[:, -1:] + 1 (conv_mlp.py:100-108): 1 where visible
-        canvas[i] = only_area ? v + 1.0f : v;
+        canvas[row * canvas_stride + ((long long)co * X + x) * Y + y] = only_area ? v + 1.0f : v;
     }
+}
+
+int decode_relative_launch(const float *obs, const int8_t *positions, float *canvas, long long rows, int channels, int visible_range,
+                           int size_x, int size_y, int obs_stride, int only_area_plus_one, long long canvas_stride,
+                           const int8_t *los, cudaStream_t st) {
+    const long long total = rows * (only_area_plus_one ? 1 : channels) * size_x * size_y;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    decode_relative_kernel<<<(unsigned)blocks, 256, 0, st>>>(obs, positions, canvas, rows, channels, visible_range, size_x, size_y,
+                                                             obs_stride, only_area_plus_one, canvas_stride, los);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("maexp_decode_relative: ") + cudaGetErrorString(e));
+    return 0;
 }
 
 __global__ void select_actions_kernel(const float *q, int8_t *actions, int G, int batch, int A, int env0, int num_envs_total,
@@ -137,14 +156,9 @@ int maexp_decode_relative(const float *obs, const int8_t *positions, float *canv
                           int visible_range, int size_x, int size_y, int obs_stride, int only_area_plus_one, void *stream) {
     if (!obs || !positions || !canvas) return fail("maexp_decode_relative: null argument");
     if (rows < 1 || channels < 1) return fail("maexp_decode_relative: bad shape");
-    const long long total = (long long)rows * (only_area_plus_one ? 1 : channels) * size_x * size_y;
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    decode_relative_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        obs, positions, canvas, rows, channels, visible_range, size_x, size_y, obs_stride, only_area_plus_one);
-    const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(std::string("maexp_decode_relative: ") + cudaGetErrorString(e));
-    return 0;
+    return decode_relative_launch(obs, positions, canvas, rows, channels, visible_range, size_x, size_y, obs_stride,
+                                  only_area_plus_one, (long long)(only_area_plus_one ? 1 : channels) * size_x * size_y, nullptr,
+                                  static_cast<cudaStream_t>(stream));
 }
 
 int maexp_heatmap_observation_add(const float *obs, int64_t num_envs, int num_agents, int elems, int64_t env_stride,

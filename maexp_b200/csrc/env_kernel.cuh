@@ -504,6 +504,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                 c[10] = max(0, py - R);
                 c[11] = min(Y - 1, py + R) + 1;
             }
+            if (p.out.objects_bits) {  // the same snapshot as bit rows, env-minor: a warp's lanes store contiguous words
+                uint32_t *o = p.out.objects_bits + (size_t)i * TX * p.E + env;
+                for (int r = 0; r < TX; ++r) o[(size_t)r * p.E] = grid[(r / X) * XP + (r % X)] >> R;
+            }
             if (p.out.objects) {
                 int8_t *o = p.out.objects + ((size_t)env * N + i) * TX * Y;
                 for (int t = 0; t < T; ++t)

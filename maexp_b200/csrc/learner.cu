@@ -1123,6 +1123,30 @@ __global__ void clip_rmsprop_kernel(float *params, const float *grads, float *sq
     }
 }
 
+// Extra canvas channels behind the `base` decoded ones (customs/da3_iqn.py:195-211, da6.py:166-179, iqn.py:149-160,
+// conv_mlp.py:56-64): objects [T,X,Y] from the snapshot's bit rows, one-hot agent cells [N,X,Y]
+// (ObservationHandler.decode_agents_channel, observation_handler.py:218-250), the agent's destination area [1,X,Y].
+__global__ void canvas_extra_kernel(float *canvas, long long rows, int base, int T, int Na, int Dc, int X, int Y,
+                                    const uint32_t *obj, const int8_t *agents, const uint32_t *dest) {
+    const int Cx = T + Na + Dc, Ct = base + Cx;
+    const long long XY = (long long)X * Y, total = rows * Cx * XY;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i % Y), x = (int)((i / Y) % X), c = (int)((i / XY) % Cx);
+        const long long row = i / (Cx * XY);
+        float v;
+        if (c < T) v = (float)((obj[(row * T + c) * X + x] >> y) & 1u);
+        else if (c < T + Na) {
+            const int8_t *a = agents + (row * Na + (c - T)) * 2;
+            v = (a[0] == x && a[1] == y) ? 1.0f : 0.0f;
+        } else v = (float)((dest[row * X + x] >> y) & 1u);
+        canvas[(row * Ct + base + c) * XY + (long long)x * Y + y] = v;
+    }
+}
+
+int decode_relative_launch(const float *obs, const int8_t *positions, float *canvas, long long rows, int channels, int visible_range,
+                           int size_x, int size_y, int obs_stride, int only_area_plus_one, long long canvas_stride,
+                           const int8_t *los, cudaStream_t st);  // agents.cu
+
 }  // namespace maexp
 
 using namespace maexp;
@@ -1205,6 +1229,12 @@ struct maexp_learner {
     HeadLayout rse, lse;            // relative_state_embedder (MergedDA3, MergedIQN), local_state_embedder (MergedIQN)
     float *lse_h[3] = {nullptr, nullptr, nullptr}, *lse_out[3] = {nullptr, nullptr, nullptr}, *d_locsal = nullptr, *d_locflat = nullptr;
     const int8_t *pos = nullptr, *next_pos = nullptr;  // bound by maexp_learner_bind_positions
+    // extra canvas channels behind the decoded observation (objects_channel / agents_channel / destination_channel):
+    // ex_o = T, ex_a = num_agents, ex_d = 1 where the model reads them (0 otherwise); Cx = their sum; set 0 belongs to the
+    // state batch (h->pos), set 1 to the new-state batch (h->next_pos); bound by maexp_learner_bind_canvas_inputs
+    int ex_o = 0, ex_a = 0, ex_d = 0, Cx = 0, Tn_obj = 0, Nteam = 0;
+    struct CanvasIn { const uint32_t *obj = nullptr; const int8_t *agents = nullptr; const uint32_t *dest = nullptr; } cin[2];
+    int8_t *los = nullptr;  // [X,Y,V,V] line-of-sight table (maexp_learner_set_los): the merged models' noise-free area channel
     float *canvas[3] = {nullptr, nullptr, nullptr}, *feat[3] = {nullptr, nullptr, nullptr}, *d_feat = nullptr;
     float *rel_flat[3] = {nullptr, nullptr, nullptr}, *rse_h[3] = {nullptr, nullptr, nullptr}, *rse_out[3] = {nullptr, nullptr, nullptr};
     float *d_relsal = nullptr, *d_relflat = nullptr;
@@ -2299,7 +2329,8 @@ int da3_forward(maexp_learner *h, cudaStream_t st, const float *params, const fl
     if (h->relative_vit) {  // relative view: the transformer reads the decoded [C, X, Y] canvas (da3.py:98-109, da3_iqn.py:194-210)
         const long long XY = (long long)h->X * h->Y;
         if (decode_canvas(h, st, obs, pos, B, pass, 0)) return -1;
-        vit_forward(h, st, params, h->vloc, h->canvas[pass], h->C * XY, XY, (long long)B * h->C * XY, B, pass, nullptr);
+        const long long Ct = h->C + h->Cx;
+        vit_forward(h, st, params, h->vloc, h->canvas[pass], Ct * XY, XY, (long long)B * Ct * XY, B, pass, nullptr);
     } else {
         vit_forward(h, st, params, h->vloc, obs, h->cfg.obs_stride, (long long)h->V * h->V, (long long)B * h->cfg.obs_stride, B,
                     pass, nullptr);
@@ -2333,7 +2364,8 @@ int da6_forward(maexp_learner *h, cudaStream_t st, const float *params, const fl
     const long long P = h->P, Bmax = h->B, XY = (long long)h->X * h->Y;
     const int E = h->E_, G = h->G;
     if (decode_canvas(h, st, obs, pos, B, pass, 1)) return -1;
-    vit_forward(h, st, params, h->vrel, h->canvas[pass], XY, XY, (long long)B * XY, B, pass, nullptr);
+    const long long Ct = 1 + h->Cx;
+    vit_forward(h, st, params, h->vrel, h->canvas[pass], Ct * XY, XY, (long long)B * Ct * XY, B, pass, nullptr);
     gemm(st, G, h->vrel.a[pass].nf, params + h->o_f1w, h->sal2[pass], params + h->o_f1b, B, E, E, E, 1, 1, E, E, 1, Bmax * E, P,
          Bmax * E, P);
     vit_forward(h, st, params, h->vloc, obs, h->cfg.obs_stride, (long long)h->V * h->V, (long long)B * h->cfg.obs_stride, B, pass,
@@ -2401,7 +2433,20 @@ void gtrunk_backward(maexp_learner *h, cudaStream_t st, maexp_learner::GTrunk &t
 // ---- relative / merged models (conv_mlp.py:56-108, da3.py:99-225): the relative branch reads the decoded canvas
 int decode_canvas(maexp_learner *h, cudaStream_t st, const float *obs, const int8_t *pos, int B, int pass, int only_area) {
     if (!pos) return fail("maexp_learner: relative / merged models need maexp_learner_bind_positions");
-    return maexp_decode_relative(obs, pos, h->canvas[pass], (int64_t)h->G * B, h->C, h->V, h->X, h->Y, h->cfg.obs_stride, only_area, st);
+    const long long rows = (long long)h->G * B, XY = (long long)h->X * h->Y;
+    const int base = only_area ? 1 : h->C, Ct = base + h->Cx;
+    if (decode_relative_launch(obs, pos, h->canvas[pass], rows, h->C, h->V, h->X, h->Y, h->cfg.obs_stride, only_area, Ct * XY,
+                               only_area ? h->los : nullptr, st))
+        return -1;
+    if (h->Cx) {  // state["objects"], decode_agents_channel(state), state["destination"] behind the decoded channels
+        const maexp_learner::CanvasIn &in = h->cin[(pos == h->next_pos && pos != h->pos) ? 1 : 0];
+        if ((h->ex_o && !in.obj) || (h->ex_a && !in.agents) || (h->ex_d && !in.dest))
+            return fail("maexp_learner: objects_channel / agents_channel / destination_channel need maexp_learner_bind_canvas_inputs");
+        const long long total = rows * h->Cx * XY;
+        canvas_extra_kernel<<<grid1d(total, 1, 256, 148 * 16), 256, 0, st>>>(h->canvas[pass], rows, base, h->ex_o, h->ex_a, h->ex_d,
+                                                                             h->X, h->Y, in.obj, in.agents, in.dest);
+    }
+    return 0;
 }
 
 int rel_forward(maexp_learner *h, cudaStream_t st, const float *params, const float *obs, const int8_t *pos, int B, int pass) {
@@ -2409,8 +2454,9 @@ int rel_forward(maexp_learner *h, cudaStream_t st, const float *params, const fl
     const long long Bmax = h->B;
     if (h->relative_conv) {  // ConvMLP on the full canvas [C, X, Y] (conv_mlp.py:56-66)
         if (decode_canvas(h, st, obs, pos, B, pass, 0)) return -1;
-        gtrunk_forward(h, st, params, h->gt_rel, pass, h->canvas[pass], (long long)C * X * Y, (long long)X * Y, Y, 1,
-                       (long long)B * C * X * Y, B, h->feat[pass], h->Drel, 0, Bmax * h->Drel);
+        const long long Ct = C + h->Cx;
+        gtrunk_forward(h, st, params, h->gt_rel, pass, h->canvas[pass], Ct * X * Y, (long long)X * Y, Y, 1,
+                       (long long)B * Ct * X * Y, B, h->feat[pass], h->Drel, 0, Bmax * h->Drel);
     } else {  // merged: conv(area canvas + 1) ++ conv(local)  (conv_mlp.py:87-108)
         if (decode_canvas(h, st, obs, pos, B, pass, 1)) return -1;
         const long long Dt = h->Drel + h->Dloc;
@@ -2637,6 +2683,31 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (h->relative_vit && (h->X < 4 || h->Y < 4 || cfg->patch_size < 1)) { delete h; return fail("maexp_learner_create: relative DA3 needs size_x / size_y / patch_size"); }
     if (trunk == MAEXP_IQN_TRUNK_MERGED_DA3 && cfg->area_mask != MAEXP_MASK_MERGED) { delete h; return fail("maexp_learner_create: the MergedDA3 IQN trunk reads the merged view"); }
     const bool gmodel = h->relative_conv || h->merged_conv || h->merged_da3;
+    // in_chans the reference adds to each model family's (relative) input: ConvMLP and DA3 objects only (conv_mlp.py:25-27,
+    // da3.py:31-33), IQN objects + agents (iqn.py:55-60), DA3_IQN all three (da3_iqn.py:96-104); DA6 / DA6_IQN read
+    // objects + agents on their relative stack (da6.py:32-37, da6_iqn.py:42-47)
+    if ((cfg->objects_channel && (cfg->type_objects < 1 || cfg->type_objects > MAEXP_MAX_TYPES)) ||
+        (cfg->agents_channel && (cfg->team_agents < 1 || cfg->team_agents > MAEXP_MAX_AGENTS))) {
+        delete h;
+        return fail("maexp_learner_create: objects_channel / agents_channel need type_objects / team_agents");
+    }
+    // CategoricalDQN, QRDQN and the plain MLP never read the flags
+    const bool reads_flags = cfg->kind == MAEXP_LEARNER_DQN_CONV_MLP || cfg->kind == MAEXP_LEARNER_IQN ||
+                             cfg->kind == MAEXP_LEARNER_DA3 || cfg->kind == MAEXP_LEARNER_DA6;
+    const int xo = reads_flags && cfg->objects_channel ? cfg->type_objects : 0,
+              xa = reads_flags && cfg->agents_channel ? cfg->team_agents : 0,
+              xd = reads_flags && cfg->destination_channel ? 1 : 0;
+    const bool iqn_kind = cfg->kind == MAEXP_LEARNER_IQN;
+    const bool vit_iqn = iqn_kind && trunk != MAEXP_IQN_TRUNK_CONV;  // DA3_IQN and its subclasses
+    // what the family's constructor sizes its relative-view input with (also where a subclass never uses it)
+    const int parent_extra = xo + ((iqn_kind) ? xa : 0) + (vit_iqn ? xd : 0);
+    if (h->relative_conv || h->relative_vit) { h->ex_o = xo; h->ex_a = iqn_kind ? xa : 0; h->ex_d = vit_iqn ? xd : 0; }
+    if (h->da6) { h->ex_o = xo; h->ex_a = xa; h->ex_d = 0; }
+    h->Cx = h->ex_o + h->ex_a + h->ex_d;
+    if (cfg->area_mask == MAEXP_MASK_LOCAL && parent_extra) {
+        delete h;  // the reference sizes the first layer for C + extras but feeds it the C-channel crop: a shape error
+        return fail("maexp_learner_create: objects_channel / agents_channel / destination_channel need the relative or merged view");
+    }
     if (h->da6 && (cfg->area_mask != MAEXP_MASK_MERGED || h->X < 4 || h->Y < 4)) { delete h; return fail("maexp_learner_create: DA6 reads the merged view (area_mask merged, size_x / size_y set)"); }
     if (cfg->area_mask != MAEXP_MASK_LOCAL && !gmodel && !h->da6 && !h->relative_vit) { delete h; return fail("maexp_learner_create: relative / merged views are implemented for conv_mlp (dqn), iqn, da3 and da6"); }
     if (gmodel && (h->X < 4 || h->Y < 4)) { delete h; return fail("maexp_learner_create: size_x / size_y missing for a relative / merged model"); }
@@ -2669,12 +2740,12 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         t.c2b = add(prefix + ".conv_post.bias", h->F2);
     };
     if (h->relative_conv) {  // ConvMLP on the decoded [C, X, Y] canvas (conv_mlp.py:21-66)
-        set_trunk(h->gt_rel, "conv", h->C, h->X, h->Y);
+        set_trunk(h->gt_rel, "conv", h->C + h->Cx, h->X, h->Y);
         h->Drel = h->gt_rel.D; h->Dloc = 0; h->D = h->Drel;
         h->H1 = h->Hp = h->H2 = 0;
     } else if (h->merged_conv) {  // MergedConvMLP (conv_mlp.py:69-108); the parent's `conv` keeps unused parameters
         maexp_learner::GTrunk unused;
-        set_trunk(unused, "conv", h->C, h->X, h->Y);
+        set_trunk(unused, "conv", h->C + parent_extra, h->X, h->Y);
         if (cfg->kind == MAEXP_LEARNER_IQN) {  // IQN.__init__'s state_embedder on the unused trunk (customs/iqn.py:51-53,167)
             add("state_embedder.fc_list.0.weight", (long long)h->H * unused.D); add("state_embedder.fc_list.0.bias", h->H);
             add("state_embedder.fc_post.weight", (long long)unused.D * h->H); add("state_embedder.fc_post.bias", unused.D);
@@ -2696,9 +2767,9 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             s.Cin = cin; s.Hin = hin; s.Win = win; s.ps = ps > 0 ? ps : 1;
             s.Ht = hin / s.ps; s.Wt = win / s.ps; s.Tn = s.Ht * s.Wt + 1; s.K = cin * s.ps * s.ps;
         };
-        if (h->relative_vit) set_stack(h->vloc, h->C, h->X, h->Y, cfg->patch_size);
+        if (h->relative_vit) set_stack(h->vloc, h->C + h->Cx, h->X, h->Y, cfg->patch_size);
         else set_stack(h->vloc, h->C, h->V, h->V, h->da6 ? cfg->local_patch_size : 1);
-        if (h->da6) set_stack(h->vrel, 1, h->X, h->Y, cfg->relative_patch_size);
+        if (h->da6) set_stack(h->vrel, 1 + h->Cx, h->X, h->Y, cfg->relative_patch_size);
         h->Tn = h->da6 && h->vrel.Tn > h->vloc.Tn ? h->vrel.Tn : h->vloc.Tn;
         if (h->E_ < 1 || h->heads_ < 1 || h->E_ % h->heads_ || h->E_ / h->heads_ > kMaxHeadDim || h->Tn > kMaxTokens || h->Fm < 1 ||
             h->vloc.Tn < 2 || (h->da6 && h->vrel.Tn < 2) ||
@@ -2724,7 +2795,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             const int ps = cfg->patch_size > 0 ? cfg->patch_size : 1;
             if (with_saliency) add("saliency_vector", h->E_);
             add("pos_embed", (long long)((h->X / ps) * (h->Y / ps) + 1) * h->E_);
-            add("patch_embed.proj.weight", (long long)h->E_ * h->C * ps * ps);
+            add("patch_embed.proj.weight", (long long)h->E_ * (h->C + parent_extra) * ps * ps);
             add("patch_embed.proj.bias", h->E_);
             maexp_learner::VitStack unused;
             add_blocks(unused, "");
@@ -2893,12 +2964,12 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
             alloc_stack(h->vrel);
             for (int k = 0; k < 3; ++k) {
                 rc |= lalloc(h, &h->sal2[k], G * B * E);
-                rc |= lalloc(h, &h->canvas[k], G * B * h->X * h->Y);
+                rc |= lalloc(h, &h->canvas[k], G * B * (1 + h->Cx) * h->X * h->Y);
             }
             rc |= lalloc(h, &h->d_sal2, G * B * E);
         }
         if (h->relative_vit)
-            for (int k = 0; k < 3; ++k) rc |= lalloc(h, &h->canvas[k], G * B * h->C * h->X * h->Y);
+            for (int k = 0; k < 3; ++k) rc |= lalloc(h, &h->canvas[k], G * B * (h->C + h->Cx) * h->X * h->Y);
         rc |= lalloc(h, &h->d_out[0], G * B * h->A);
         rc |= lalloc(h, &h->da_dx, G * Rm * E); rc |= lalloc(h, &h->da_dn, G * Rm * E); rc |= lalloc(h, &h->da_gx, G * Rm * E);
         rc |= lalloc(h, &h->da_dqkv, G * Rm * 3 * E); rc |= lalloc(h, &h->da_dao, G * Rm * E);
@@ -2956,7 +3027,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
         if (h->merged_conv) alloc_trunk(h->gt_loc);
         const long long Dt = h->merged_da3 ? h->Drel + h->E_ : h->D;
         for (int k = 0; k < 3; ++k) {
-            rc |= lalloc(h, &h->canvas[k], G * B * (h->relative_conv ? h->C : 1) * h->X * h->Y);
+            rc |= lalloc(h, &h->canvas[k], G * B * (h->relative_conv ? h->C + h->Cx : 1) * h->X * h->Y);
             rc |= lalloc(h, &h->feat[k], G * B * Dt);
             if (h->merged_da3 || (h->iqn && h->merged_conv)) {
                 rc |= lalloc(h, &h->rel_flat[k], G * B * h->Drel);
@@ -3037,6 +3108,25 @@ int maexp_learner_bind_positions(maexp_learner *h, const int8_t *pos, const int8
     if (!h) return fail("maexp_learner_bind_positions: null handle");
     h->pos = pos;
     h->next_pos = next_pos;
+    return 0;
+}
+
+int maexp_learner_bind_canvas_inputs(maexp_learner *h, const uint32_t *obj_rows, const uint32_t *next_obj_rows,
+                                     const int8_t *agents, const int8_t *next_agents, const uint32_t *dest_rows,
+                                     const uint32_t *next_dest_rows) {
+    if (!h) return fail("maexp_learner_bind_canvas_inputs: null handle");
+    h->cin[0].obj = obj_rows; h->cin[0].agents = agents; h->cin[0].dest = dest_rows;
+    h->cin[1].obj = next_obj_rows; h->cin[1].agents = next_agents; h->cin[1].dest = next_dest_rows;
+    return 0;
+}
+
+int maexp_learner_set_los(maexp_learner *h, const int8_t *los_host) {
+    if (!h) return fail("maexp_learner_set_los: null handle");
+    if (!los_host) { h->los = nullptr; return 0; }
+    if (h->area_mask != MAEXP_MASK_MERGED) return fail("maexp_learner_set_los: only the merged models read the noise-free area channel");
+    const size_t n = (size_t)h->X * h->Y * h->V * h->V;
+    if (!h->los && lalloc(h, &h->los, n)) return -1;
+    MAEXP_CUDA_L(cudaMemcpy(h->los, los_host, n, cudaMemcpyHostToDevice));
     return 0;
 }
 

@@ -77,6 +77,26 @@ __global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint3
         d0[q] = __ldg(s0 + q);
         d1[q] = __ldg(s1 + q);
     }
+    if (out.obj_rows && r.objects_bits) {  // agent's objects_matrix snapshot of both slots: T*X strided words each
+        const int TX = r.type_objects * r.size_x;
+        const size_t per_slot = (size_t)N * TX * r.num_envs;
+        const uint32_t *s0b = r.objects_bits + (size_t)slot * per_slot + (size_t)agent * TX * r.num_envs + env;
+        const uint32_t *s1b = r.objects_bits + (size_t)nxt * per_slot + (size_t)agent * TX * r.num_envs + env;
+        const size_t ob = ((size_t)agent * batch + b) * TX;
+        for (int q = lane; q < TX; q += 32) {
+            out.obj_rows[ob + q] = __ldg(s0b + (size_t)q * r.num_envs);
+            out.next_obj_rows[ob + q] = __ldg(s1b + (size_t)q * r.num_envs);
+        }
+    }
+    if (out.dest_rows && r.destination && r.dest_table) {
+        const int d0 = r.destination[((size_t)slot * r.num_envs + env) * N + agent];
+        const int d1 = r.destination[((size_t)nxt * r.num_envs + env) * N + agent];
+        const size_t ob = ((size_t)agent * batch + b) * r.size_x;
+        for (int q = lane; q < r.size_x; q += 32) {
+            out.dest_rows[ob + q] = __ldg(r.dest_table + (size_t)d0 * r.size_x + q);
+            out.next_dest_rows[ob + q] = __ldg(r.dest_table + (size_t)d1 * r.size_x + q);
+        }
+    }
     if (lane == 0) {
         const size_t m = ((size_t)nxt * r.num_envs + env) * N + agent, o = (size_t)agent * batch + b;
         out.actions[o] = max((int)r.actions[m], 0);  // -1 marks a reset slot (flagged above): the loss kernels index with it
@@ -88,6 +108,14 @@ __global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint3
             out.pos[o * 2 + 1] = r.positions[ps + 1];
             out.next_pos[o * 2] = r.positions[pn];
             out.next_pos[o * 2 + 1] = r.positions[pn + 1];
+        }
+        if (out.agents && r.positions) {  // every agent's cell (decode_agents_channel, observation_handler.py:218-250)
+            const int8_t *ps = r.positions + ((size_t)slot * r.num_envs + env) * N * 2;
+            const int8_t *pn = r.positions + ((size_t)nxt * r.num_envs + env) * N * 2;
+            for (int k = 0; k < 2 * N; ++k) {
+                out.agents[o * 2 * N + k] = ps[k];
+                out.next_agents[o * 2 * N + k] = pn[k];
+            }
         }
         if (out.picked && agent == 0) {
             out.picked[2 * b] = slot;

@@ -75,7 +75,22 @@ def configs():
     da3_hard["model"] = dict(da3.model, attention="hard", af_lambd=0.02)  # 50 tokens: mean weight 0.02
     da6_iqn_hard = attn_iqn("merged", "da6_iqn")
     da6_iqn_hard["model"] = dict(da6_iqn_hard.model, attention="hard", af_lambd=0.04)
-    hard = {"da3_hard": (da3_hard, [3, 7, 7]), "da6_iqn_hard": (da6_iqn_hard, [4, *SIZE]), "da6_hard": (da6_hard, [4, *SIZE]), "merged_da3_iqn_hard": (mda3_iqn_hard, [4, *SIZE]),
+    # extra canvas channels (objects_channel / agents_channel / destination_channel; T = 2 object types, 4 agents)
+    def channels(c, o, a, d):
+        c = c.merged_with(objects_channel=o, agents_channel=a, destination_channel=d, type_objects=2, num_agents=4)
+        return c
+    ch = {"relative_conv_mlp_ch": (channels(rel, True, True, True), [4, *SIZE]),     # ConvMLP reads objects only
+          "relative_da3_ch": (channels(rda3, True, False, False), [4, *SIZE]),
+          "relative_iqn_ch": (channels(conv_iqn("relative"), True, True, False), [4, *SIZE]),
+          "relative_da3_iqn_ch": (channels(rda3_iqn, True, True, True), [4, *SIZE]),
+          "da6_ch": (channels(da6, True, True, False), [4, *SIZE]),
+          "da6_iqn_ch": (channels(attn_iqn("merged", "da6_iqn"), True, True, True), [4, *SIZE]),
+          "merged_da3_iqn_ch": (channels(attn_iqn("merged", "da3_iqn"), True, True, True), [4, *SIZE])}  # unused parent only
+    # merged view under observation noise: the models read the noise-free "relative" key (merged_observtion_handler.py:27)
+    noise = {"merged_conv_mlp_noise": (mconv.merged_with(observation_noise="flip"), [4, *SIZE]),
+             "merged_da3_noise": (mda3.merged_with(observation_noise="flip"), [4, *SIZE]),
+             "da6_noise": (da6.merged_with(observation_noise="sensing_dist"), [4, *SIZE])}
+    hard = {**ch, **noise, "da3_hard": (da3_hard, [3, 7, 7]), "da6_iqn_hard": (da6_iqn_hard, [4, *SIZE]), "da6_hard": (da6_hard, [4, *SIZE]), "merged_da3_iqn_hard": (mda3_iqn_hard, [4, *SIZE]),
             "da3_iqn_hard": (da3_iqn_hard, [4, VIEW, VIEW])}
     return {**hard, "relative_iqn": (conv_iqn("relative"), [4, *SIZE]), "merged_iqn": (conv_iqn("merged"), [4, *SIZE]),
             "relative_da3": (rda3, [4, *SIZE]), "relative_da3_iqn": (rda3_iqn, [4, *SIZE]),
@@ -99,11 +114,51 @@ def synthetic_batch(shape, seed, V=None):
             "dones": torch.rand((B,), generator=g) < 0.1}
 
 
-def ref_state(obs, pos):
-    """The dict the reference's relative / merged observation handlers hand to a brain."""
+def ref_state(obs, pos, extras=None):
+    """The dict the reference's relative / merged observation handlers hand to a brain (observation_handler.py:95-105);
+    extras: the state's "objects" / "agents" / "destination" keys and, under observation noise, the noise-free
+    "relative" crop (merged_observtion_handler.py:41-47)."""
     from oracle.torch_learner import coordinates
     c = coordinates(pos, obs.shape[2], *SIZE)
-    return {"local": obs.clone(), "relative": obs.clone(), "coordinates": {k: torch.tensor(v) for k, v in c.items()}}
+    st = {"local": obs.clone(), "relative": obs.clone(), "coordinates": {k: torch.tensor(v) for k, v in c.items()}}
+    for k, v in (extras or {}).items():
+        st[k] = v.clone()
+    return st
+
+
+def synthetic_extras(cfg, fixture, batch, seed):
+    """Synthetic "objects" int8 [B,T,X,Y], "agents" int8 [B,N,2], "destination" int8 [B,X,Y] for the state and the new state,
+    and for the *_noise fixtures a random line-of-sight table with the clean "relative" crops it implies."""
+    g = torch.Generator().manual_seed(seed)
+    X, Y = SIZE
+    T, N = int(cfg.type_objects), int(cfg.num_agents)
+    out = {"": {}, "next_": {}}
+    for pre in out:
+        if fixture.endswith("_ch"):
+            out[pre]["objects"] = (torch.rand((B, T, X, Y), generator=g) < 0.1).to(torch.int8)
+            out[pre]["agents"] = torch.stack([torch.randint(0, X, (B, N), generator=g), torch.randint(0, Y, (B, N), generator=g)],
+                                             dim=2).to(torch.int8)
+            dest = torch.zeros((B, X, Y), dtype=torch.int8)
+            half = torch.randint(0, 4, (B,), generator=g)
+            for b in range(B):  # half-plane destination areas, as the central_room_destination maps use
+                if half[b] == 0: dest[b, : X // 2] = 1
+                elif half[b] == 1: dest[b, X // 2:] = 1
+                elif half[b] == 2: dest[b, :, : Y // 2] = 1
+                else: dest[b] = 1
+            out[pre]["destination"] = dest
+    los = None
+    if fixture.endswith("_noise"):
+        V = VIEW
+        los = (torch.rand((X, Y, V, V), generator=g) < 0.7).to(torch.int8)
+        los[:, :, V // 2, V // 2] = 1
+        for pre, key, pkey in (("", "obs", "pos"), ("next_", "next_obs", "next_pos")):
+            noisy = batch[key]
+            clean = (torch.rand(noisy.shape, generator=g) < 0.15).float()
+            clean[:, -1] = torch.stack([los[int(p[0]), int(p[1])].float() - 1 for p in batch[pkey]])
+            # the local crop is the clean one plus noise on every channel (flip noise leaves integers, sensing noise reals)
+            batch[key] = clean + 0.3 * torch.randn(noisy.shape, generator=g)
+            out[pre]["relative"] = clean
+    return out, los
 
 
 def main():
@@ -114,7 +169,10 @@ def main():
     for fixture, (cfg, shape) in configs().items():
         if only and fixture not in only:
             continue
-        kind = fixture[:-5] if fixture.endswith("_hard") else fixture  # the fixture's network family
+        kind = fixture  # the fixture's network family
+        for suffix in ("_hard", "_ch", "_noise"):
+            if kind.endswith(suffix):
+                kind = kind[:-len(suffix)]
         torch.manual_seed(921)
         brain = generate_brain(config=rr.to_dictconfig(cfg), obs_shape=shape, act_size=4)
         masked = kind in ("relative_conv_mlp", "merged_conv_mlp", "merged_da3", "da6", "merged_da3_iqn", "da6_iqn",
@@ -152,8 +210,11 @@ def main():
                 batch[key] = torch.stack([torch.randint(0, SIZE[0], (B,), generator=gp),
                                           torch.randint(0, SIZE[1], (B,), generator=gp)], dim=1)
             batch["pos"][0], batch["pos"][1] = torch.tensor([0, 0]), torch.tensor([SIZE[0] - 1, SIZE[1] - 1])
-        state = (lambda: ref_state(batch["obs"], batch["pos"])) if masked else (lambda: {"local": batch["obs"].clone()})
-        next_state = (lambda: ref_state(batch["next_obs"], batch["next_pos"])) if masked else \
+        extras, los = ({"": {}, "next_": {}}, None)
+        if masked and (fixture.endswith("_ch") or fixture.endswith("_noise")):
+            extras, los = synthetic_extras(cfg, fixture, batch, 13)
+        state = (lambda: ref_state(batch["obs"], batch["pos"], extras[""])) if masked else (lambda: {"local": batch["obs"].clone()})
+        next_state = (lambda: ref_state(batch["next_obs"], batch["next_pos"], extras["next_"])) if masked else \
             (lambda: {"local": batch["next_obs"].clone()})
         with torch.no_grad():
             if is_iqn and kind != "iqn":
@@ -192,6 +253,10 @@ def main():
         arrays.update({"target/" + k: v.numpy() for k, v in tgt.items()})
         arrays.update({"final/" + k: v.numpy() for k, v in final.items()})
         arrays.update({"batch/" + k: v.numpy() for k, v in batch.items()})
+        for pre, d in extras.items():
+            arrays.update({"extras/" + pre + k: v.numpy() for k, v in d.items()})
+        if los is not None:
+            arrays["los"] = los.numpy()
         if is_iqn:  # per learn call: taus [B,N], tau_sel [1,N], tau_dashes [B,N']
             assert len(drawn) == 6
             for u in range(2):

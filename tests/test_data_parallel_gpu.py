@@ -33,8 +33,8 @@ def _trainer_worker(rank, world, port, brain, out):
         cfg = baseline_config(5 if brain == "c51" else 3).merged_with(max_episode_length=6, batch_size=32, populate_steps=4 * E,
                                                                       capacity=16 * E, max_epochs=2)
         if brain == "iqn":
-            cfg = cfg.merged_with(brain="iqn")
-            cfg["model"] = dict(cfg.model, name="iqn", num_quantiles=8, num_quantiles_dash=8, num_cosines=16)
+            cfg = cfg.merged_with(brain="iqn", model=dict(cfg.model, name="iqn", num_quantiles=8, num_quantiles_dash=8,
+                                                          num_cosines=16))
         torch.manual_seed(100 + rank)  # every rank initialises different weights: the trainer must broadcast rank 0's
 
         class Env:  # the trainer only reads .world of a non-batched environment argument

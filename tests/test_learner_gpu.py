@@ -11,7 +11,7 @@ import torch
 from maexp_b200.config import Config, baseline_config
 from oracle.make_golden_learner import configs as golden_configs
 from oracle.torch_learner import TorchLearner
-from tests.test_learner_golden import ATOMS, IQN_KINDS, KINDS, MASKED, load, make_oracle, oracle_inputs
+from tests.test_learner_golden import ATOMS, IQN_KINDS, KINDS, MASKED, base, load, make_oracle, oracle_inputs
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
@@ -31,6 +31,20 @@ def pack(group, x):
     return out
 
 
+def canvas_batch(extras, next_extras=None):
+    """The reference's "objects" / "agents" / "destination" state keys ([G,B,...] stacks) in the library's layout."""
+    from maexp_b200.core.agents.brains import Brain
+    out = {}
+    for pre, ex in (("", extras), ("next_", next_extras or {})):
+        if "objects" in ex:
+            out[pre + "obj_rows"] = Brain._bit_rows(ex["objects"]).contiguous().cuda()
+        if "agents" in ex:
+            out[pre + "agents"] = ex["agents"].to(torch.int8).contiguous().cuda()
+        if "destination" in ex:
+            out[pre + "dest_rows"] = Brain._bit_rows(ex["destination"]).contiguous().cuda()
+    return out
+
+
 def rel_err(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
@@ -46,13 +60,18 @@ def test_cuda_learner_matches_reference_fixture(kind):
              "actions": b["actions"].to(torch.int32)[None].contiguous().cuda(),
              "rewards": b["rewards"].float()[None].contiguous().cuda(),
              "dones": b["dones"].to(torch.uint8)[None].contiguous().cuda()}
-    if kind in MASKED:
+    if base(kind) in MASKED:
         batch["pos"] = b["pos"].to(torch.int8)[None].contiguous().cuda()
         batch["next_pos"] = b["next_pos"].to(torch.int8)[None].contiguous().cuda()
-    q = g.q_values(batch["obs"], tau_sel=fix["tau0"].cuda() if kind in IQN_KINDS else None, pos=batch.get("pos")).cpu()[0]
+        ex, next_ex = fix["extras"]
+        batch.update(canvas_batch({k: v[None] for k, v in ex.items()}, {k: v[None] for k, v in next_ex.items()}))
+    if fix["los"] is not None:  # *_noise: the stored crop is noisy, the area canvas comes from the line-of-sight table
+        g.set_los(fix["los"])
+    q = g.q_values(batch["obs"], tau_sel=fix["tau0"].cuda() if base(kind) in IQN_KINDS else None, pos=batch.get("pos"),
+                   canvas=batch).cpu()[0]
     assert rel_err(q, fix["q0"]) < RTOL
     for u, want in enumerate(fix["losses"]):
-        if kind in IQN_KINDS:
+        if base(kind) in IQN_KINDS:
             t, d, sel = fix["taus"][u]
             batch.update(taus=t[None].contiguous().cuda(), tau_dashes=d[None].contiguous().cuda(), tau_sel=sel.contiguous().cuda())
         loss = float(g.learn(batch).cpu()[0])
@@ -70,7 +89,10 @@ def test_cuda_learner_matches_reference_fixture(kind):
 @pytest.mark.parametrize("kind,B", [("dqn_conv_mlp", 32), ("c51", 256), ("qr", 256), ("iqn", 256), ("da3", 32),
                                     ("relative_conv_mlp", 32), ("merged_conv_mlp", 32), ("merged_da3", 32), ("da6", 32),
                                     ("da3_iqn", 32), ("merged_da3_iqn", 32), ("da6_iqn", 32), ("relative_da3", 32),
-                                    ("relative_da3_iqn", 32), ("relative_iqn", 32), ("merged_iqn", 32)])
+                                    ("relative_da3_iqn", 32), ("relative_iqn", 32), ("merged_iqn", 32),
+                                    ("relative_conv_mlp_ch", 32), ("relative_da3_ch", 32), ("relative_iqn_ch", 32),
+                                    ("relative_da3_iqn_ch", 32), ("da6_ch", 32), ("da6_iqn_ch", 32), ("merged_da3_iqn_ch", 32),
+                                    ("merged_conv_mlp_noise", 32), ("merged_da3_noise", 32), ("da6_noise", 32)])
 def test_cuda_learner_group_matches_torch_oracle(kind, B):
     """G independent networks with different weights and batches, BASELINE batch sizes."""
     G = 3
@@ -93,31 +115,51 @@ def test_cuda_learner_group_matches_torch_oracle(kind, B):
         batches.append({"obs": obs, "next_obs": nxt, "actions": torch.randint(0, 4, (B,), generator=gen),
                         "rewards": torch.randint(-1, 2, (B,), generator=gen).double(),
                         "dones": torch.rand((B,), generator=gen) < 0.1})
-        if kind in MASKED:
+        if base(kind) in MASKED:
             for key in ("pos", "next_pos"):
                 batches[-1][key] = torch.stack([torch.randint(0, X, (B,), generator=gen), torch.randint(0, Y, (B,), generator=gen)], 1)
+            ex = ({}, {})
+            if kind.endswith("_ch"):  # random objects / agents / destination keys, shaped like the fixture's
+                for d, fx in zip(ex, fix["extras"]):
+                    T, Nteam = fx["objects"].shape[1], fx["agents"].shape[1]
+                    d["objects"] = (torch.rand((B, T, X, Y), generator=gen) < 0.1).to(torch.int8)
+                    d["agents"] = torch.stack([torch.randint(0, X, (B, Nteam), generator=gen),
+                                               torch.randint(0, Y, (B, Nteam), generator=gen)], 2).to(torch.int8)
+                    d["destination"] = (torch.rand((B, X, Y), generator=gen) < 0.5).to(torch.int8)
+            if kind.endswith("_noise"):  # noisy stored crop; the clean "relative" crop's area channel follows the table
+                for d, key, pkey in zip(ex, ("obs", "next_obs"), ("pos", "next_pos")):
+                    clean = batches[-1][key].clone()
+                    clean[:, -1] = torch.stack([torch.from_numpy(fix["los"])[int(p[0]), int(p[1])].float() - 1
+                                                for p in batches[-1][pkey]])
+                    d["relative"] = clean
+                    batches[-1][key] = clean + 0.3 * torch.randn(clean.shape, generator=gen)
+            batches[-1]["extras"] = ex
     batch = {"obs": pack(g, torch.stack([b["obs"] for b in batches])),
              "next_obs": pack(g, torch.stack([b["next_obs"] for b in batches])),
              "actions": torch.stack([b["actions"] for b in batches]).to(torch.int32).cuda(),
              "rewards": torch.stack([b["rewards"] for b in batches]).float().cuda(),
              "dones": torch.stack([b["dones"] for b in batches]).to(torch.uint8).cuda()}
-    if kind in MASKED:
+    if base(kind) in MASKED:
         batch["pos"] = torch.stack([b["pos"] for b in batches]).to(torch.int8).cuda()
         batch["next_pos"] = torch.stack([b["next_pos"] for b in batches]).to(torch.int8).cuda()
+        stack = lambda j: {k: torch.stack([b["extras"][j][k] for b in batches]) for k in batches[0]["extras"][j] if k != "relative"}
+        batch.update(canvas_batch(stack(0), stack(1)))
+    if fix["los"] is not None:
+        g.set_los(fix["los"])
     taus = None
-    if kind in IQN_KINDS:
+    if base(kind) in IQN_KINDS:
         taus = [(torch.rand((B, 4), generator=gen), torch.rand((B, 4), generator=gen), torch.rand((1, 4), generator=gen))
                 for _ in range(G)]
         batch.update(taus=torch.stack([t[0] for t in taus]).cuda(), tau_dashes=torch.stack([t[1] for t in taus]).cuda(),
                      tau_sel=torch.cat([t[2] for t in taus]).cuda())
         for a in range(G):
             oracles[a].taus = taus[a]
-        q = g.q_values(batch["obs"], tau_sel=batch["tau_sel"], pos=batch.get("pos")).cpu()
+        q = g.q_values(batch["obs"], tau_sel=batch["tau_sel"], pos=batch.get("pos"), canvas=batch).cpu()
     else:
-        q = g.q_values(batch["obs"], pos=batch.get("pos")).cpu()
+        q = g.q_values(batch["obs"], pos=batch.get("pos"), canvas=batch).cpu()
     ins = [oracle_inputs(fix, b) for b in batches]
     for a in range(G):
-        want_q = oracles[a].q_values_iqn(ins[a][0], taus[a][2]) if kind in IQN_KINDS else oracles[a].q_values(ins[a][0])
+        want_q = oracles[a].q_values_iqn(ins[a][0], taus[a][2]) if base(kind) in IQN_KINDS else oracles[a].q_values(ins[a][0])
         assert rel_err(q[a], want_q) < RTOL
     # gradients of the first update, then two full updates
     loss = g.grads(batch).cpu()

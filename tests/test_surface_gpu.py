@@ -210,8 +210,38 @@ def test_trainer_merged_view_da3_end_to_end():
         assert float((q[a] - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-6
     sd = trainer.learner.state_dict(0)
     assert tuple(sd["drl_head.weight"].shape)[0] == 4 and "local_blocks.0.attn.qkv.weight" in sd and "relative_conv.conv_post.weight" in sd
-    with pytest.raises(ValueError):  # the noise-free "relative" key is not kept in the ring
-        generate_trainer(cfg.merged_with(observation_noise="flip"), env)
+
+
+def test_trainer_merged_view_under_observation_noise_reads_the_noise_free_area_channel():
+    """BASELINE cfg4 with observation noise: the merged models take the area channel of the NOISE-FREE "relative" key
+    (merged_observtion_handler.py:27,41-47; customs/da3.py:217-225).  The ring keeps only the noisy crop (env slot `obs`)
+    and the trainer binds the environment's line-of-sight table; the Q-values the learner computes from the ring equal
+    the torch oracle's on (noisy local crop, clean relative crop) — the clean crop is what the env writes to `obs_rel`."""
+    from maexp_b200.core.handlers.trainers import generate_trainer
+    from oracle.torch_learner import TorchLearner
+    from tests.cuda_backend import make_env
+    cfg = baseline_config(4).merged_with(max_episode_length=6, batch_size=16, populate_steps=4 * 32, capacity=32 * 16,
+                                         synchronize_frequency=1, observation_noise="sensing_dist")
+    env = make_env(cfg, 32, auto_reset=True)
+    trainer = generate_trainer(cfg, env)
+    before = trainer.learner.params().clone()
+    hist = trainer.run(max_epochs=1)
+    assert np.isfinite(hist[-1]["loss"]) and not torch.equal(trainer.learner.params(), before)
+    e, N = trainer.env, trainer.env.N
+    out = e.new_outputs(extras=True)   # one more step with both keys kept: noisy `obs`, clean `obs_rel`
+    e.step(out, tick=10_000)
+    noisy, clean, positions = e.view(out["obs"]).cpu(), e.view(out["obs_rel"]).cpu(), out["positions"]
+    assert float((noisy - clean).abs().max()) > 1e-3                      # the noise is there ...
+    assert torch.equal(clean[:, :, -1], clean[:, :, -1].round())         # ... and the relative key is free of it
+    q = trainer.learner.q_values(out["obs"][:, :16].contiguous(), pos=positions[:16].transpose(0, 1).contiguous()).cpu()
+    for a in (0, N - 1):
+        o = TorchLearner("da3", trainer.learner.state_dict(a), 4, float(cfg.gamma), 1e-3, 0.99, 1e-8, area_mask="merged",
+                         size=[int(cfg.map.SIZE_X), int(cfg.map.SIZE_Y)], num_heads=int(cfg.model.num_heads))
+        pos = positions[:16, a].cpu().long()
+        want = o.q_values((noisy[:16, a], pos, {"relative": clean[:16, a]}))
+        assert float((q[a] - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-6
+        wrong = o.q_values((noisy[:16, a], pos))                          # area channel taken from the noisy crop
+        assert float((wrong - want).abs().max()) > 1e-4
 
 
 def test_evaluator_greedy_rollouts_with_saved_weights(tmp_path):
@@ -238,14 +268,24 @@ def test_evaluator_greedy_rollouts_with_saved_weights(tmp_path):
         generate_evaluator(cfg.merged_with(evaluator="nope"), trainer.env)
 
 
-@pytest.mark.parametrize("environment,brain,model,mask,types,tasks", [
-    ("sequential", "da3_iqn", "da3_iqn", "merged", 3, ["0", "0", "1", "1", "2", "2", "012", "01"]),
-    ("junctional", "da3_iqn", "da6_iqn", "merged", 5, ["0", "0", "12", "12", "13", "13", "4", "4"]),
-    ("sequential", "da6", "da6", "merged", 3, ["0", "0", "1", "1", "2", "2", "012", "01"]),
-    ("default", "iqn", "iqn", "relative", 1, ["0"] * 8),
-    ("sequential", "da3", "da3", "relative", 2, ["0", "1"] * 4),
+@pytest.mark.parametrize("environment,brain,model,mask,types,tasks,flags", [
+    ("sequential", "da3_iqn", "da3_iqn", "merged", 3, ["0", "0", "1", "1", "2", "2", "012", "01"], ""),
+    ("junctional", "da3_iqn", "da6_iqn", "merged", 5, ["0", "0", "12", "12", "13", "13", "4", "4"], ""),
+    ("sequential", "da6", "da6", "merged", 3, ["0", "0", "1", "1", "2", "2", "012", "01"], ""),
+    ("default", "iqn", "iqn", "relative", 1, ["0"] * 8, ""),
+    ("sequential", "da3", "da3", "relative", 2, ["0", "1"] * 4, ""),
+    # objects_channel / agents_channel / destination_channel on, as configs/experiments/IJCNN2025/exp1/goapos/*.yaml
+    # (Gpos+Opos+Apos: eda3_iqn, eda6_iqn, iqn, dqn, eda6_dqn, eda3_dqn) and KES2023/*.yaml (destination_channel)
+    ("sequential", "da3_iqn", "da3_iqn", "relative", 3, ["0", "0", "1", "1", "2", "2", "012", "01"], "oa"),
+    ("sequential", "da3_iqn", "da6_iqn", "merged", 3, ["0", "0", "1", "1", "2", "2", "012", "01"], "oa"),
+    ("sequential", "iqn", "iqn", "relative", 3, ["0", "0", "1", "1", "2", "2", "012", "01"], "oa"),
+    ("sequential", "da3_baseline", "da3_baseline", "relative", 3, ["0", "0", "1", "1", "2", "2", "012", "01"], "oa"),
+    ("sequential", "da6", "da6", "merged", 2, ["0", "1"] * 4, "oa"),
+    ("sequential", "da3", "da3", "relative", 3, ["0", "0", "1", "1", "2", "2", "012", "01"], "oa"),
+    ("default", "da3_iqn", "da3_iqn", "relative", 1, ["0"] * 8, "d"),
+    ("default", "da6", "da6", "merged", 1, ["0"] * 8, "d"),
 ])
-def test_trainer_on_shipped_experiment_shapes(environment, brain, model, mask, types, tasks):
+def test_trainer_on_shipped_experiment_shapes(environment, brain, model, mask, types, tasks, flags=""):
     """The combinations of configs/experiments/IJCNN2025 (central_room, 8 agents, individual / object_types views):
     environment, brain, model and view wired through generate_trainer for a short run."""
     from maexp_b200.core.handlers.trainers import generate_trainer
@@ -260,9 +300,56 @@ def test_trainer_on_shipped_experiment_shapes(environment, brain, model, mask, t
                       num_objects=40, agent_tasks=tasks, init_xys=xy8, agent_view_method="individual",
                       object_view_method="object_types", observation_area_mask=mask, agent_type="attention", trainer="attention",
                       brain=brain, model=m, max_episode_length=6, batch_size=8, populate_steps=4 * 16, capacity=16 * 16,
-                      synchronize_frequency=1)
+                      synchronize_frequency=1, objects_channel="o" in flags, agents_channel="a" in flags,
+                      destination_channel="d" in flags)
+    if "d" in flags:  # KES2023: one destination half per agent (central_room_destination_map.py)
+        cfg = cfg.merged_with(map=dict(name="central_room_destination", SIZE_X=25, SIZE_Y=25))
     trainer = generate_trainer(cfg, make_env(cfg, 16, auto_reset=True))
     before = trainer.learner.params().clone()
     hist = trainer.run(max_epochs=1)
     assert np.isfinite(hist[-1]["loss"]) and not torch.equal(trainer.learner.params(), before)
     assert trainer.env.stats()["error_flag"] == 0
+    if flags:
+        _check_canvas_inputs_against_env_state(trainer, flags)
+
+
+def _check_canvas_inputs_against_env_state(trainer, flags):
+    """The ring's canvas inputs of the newest slot against the environment's state taps (reference dtypes): the last
+    agent's objects snapshot is the objects_matrix after the step, every agent sees all agents' cells, and the destination
+    rows are the agent's own destination_area_matrix.  Then a sampled batch against the ring, pick by pick."""
+    from maexp_b200.core.agents.brains import Brain
+    ring, env = trainer.buffer, trainer.env
+    E, N, T, X, Y = env.E, env.N, env.T, env.X, env.Y
+    st = env.state()
+    inputs = ring.canvas_inputs(0, E)
+    reads = trainer.learner.canvas_reads
+    assert reads[0] == ("o" in flags) and reads[2] == ("d" in flags and trainer.config.model.name == "da3_iqn")
+    if "o" in flags:
+        rows = Brain._bit_rows(st["objects"].cpu())                       # [E, T, X]
+        assert torch.equal(inputs["obj_rows"][N - 1].cpu(), rows)         # the last agent observes after every pickup
+    if "a" in flags and reads[1]:
+        assert torch.equal(inputs["agents"][0].cpu(), st["pos"].cpu()) and torch.equal(inputs["agents"][N - 1], inputs["agents"][0])
+    if "d" in flags:
+        assert ring.destination is not None
+        if reads[2]:
+            want = Brain._bit_rows(st["destination"].cpu()).transpose(0, 1)   # [N, E, X]
+            assert torch.equal(inputs["dest_rows"].cpu(), want)
+    batch = trainer.batch
+    S = ring.S
+    rng = np.random.default_rng(1)
+    B = batch["actions"].shape[1]
+    picks = np.stack([(ring.head - 1 - rng.integers(0, ring.count - 1, B)) % S, rng.integers(0, E, B)], 1).astype(np.int32)
+    ring.sample(batch, indices=torch.from_numpy(picks).cuda())
+    torch.cuda.synchronize()
+    batch["error_flag"].zero_()  # injected picks may name transitions into reset slots
+    for j, (s0, e) in enumerate(picks):
+        s1 = (s0 + 1) % S
+        if ring.objects_bits is not None:
+            assert torch.equal(batch["obj_rows"][:, j], ring.objects_bits[s0, :, :, :, e])
+            assert torch.equal(batch["next_obj_rows"][:, j], ring.objects_bits[s1, :, :, :, e])
+        if ring.keep_agents:
+            assert torch.equal(batch["agents"][:, j], ring.positions[s0, e].expand(N, N, 2))
+            assert torch.equal(batch["next_agents"][:, j], ring.positions[s1, e].expand(N, N, 2))
+        if ring.destination is not None:
+            assert torch.equal(batch["dest_rows"][:, j], ring.dest_table[ring.destination[s0, e].long()])
+            assert torch.equal(batch["next_dest_rows"][:, j], ring.dest_table[ring.destination[s1, e].long()])
