@@ -285,7 +285,7 @@ def test_evaluator_greedy_rollouts_with_saved_weights(tmp_path):
     ("default", "da3_iqn", "da3_iqn", "relative", 1, ["0"] * 8, "d"),
     ("default", "da6", "da6", "merged", 1, ["0"] * 8, "d"),
 ])
-def test_trainer_on_shipped_experiment_shapes(environment, brain, model, mask, types, tasks, flags=""):
+def test_trainer_on_shipped_experiment_shapes(environment, brain, model, mask, types, tasks, flags):
     """The combinations of configs/experiments/IJCNN2025 (central_room, 8 agents, individual / object_types views):
     environment, brain, model and view wired through generate_trainer for a short run."""
     from maexp_b200.core.handlers.trainers import generate_trainer
