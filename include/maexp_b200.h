@@ -359,6 +359,39 @@ int maexp_learner_apply(maexp_learner *learner, float grad_scale, const uint8_t 
 int maexp_learner_update(maexp_learner *learner, const float *obs, const float *next_obs, const int32_t *actions,
                          const float *rewards, const uint8_t *dones, float *loss_out, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone loss / optimizer kernels on CALLER-OWNED network outputs (fp32 device tensors, e.g. of the reference's own
+ * torch modules): the TD target, loss [G] and the gradient with respect to the online network's output on the state batch,
+ * which the caller back-propagates (out.backward(d_out)).  G independent networks per call (G = 1 for one brain).  They run the
+ * same kernels as maexp_learner_grads / maexp_learner_apply; scratch memory is stream-ordered (cudaMallocAsync).
+ *
+ * maexp_loss_dqn: DA3Brain.learn / DQN TD target + MSE (da3_brain.py:69-87): q = net(s) [G,B,A], q_next_target = target(s'),
+ *   dones uint8 [G,B] mask the bootstrap; dq_out [G,B,A].
+ * maexp_loss_c51: CategoricalDQNBrain.learn (categorical_dqn_brain.py:51-87): RAW logits [G,B,A,Z] (ApplySoftmax.NONE) of
+ *   net(s), net(s') (double-DQN action choice) and target(s'); support [Z] = linspace(V_min, V_max, Z), delta_z the fp32 atom
+ *   spacing; projection with the reference's floor / ceil fix-ups, cross-entropy, no terminal mask (as the reference).
+ * maexp_loss_qr: QRDQNBrain.learn (qr_dqn_brain.py:15-51,91-117): quantiles [G,B,A,Z]; tau_hats [Z] = (2j+1)/(2Z);
+ *   element-wise (j <-> j) quantile Huber, kappa = 1.
+ * maexp_loss_iqn: IQNBrain.learn (iqn_brain.py:15-50,73-113): get_quantiles outputs [G,B,Nq,A] of net(s, taus), net(s', tau_sel)
+ *   (its mean over quantiles picks the action) and [G,B,Nd,A] of target(s', tau_dashes); taus [G,B,Nq]; pairwise quantile Huber.
+ * maexp_clip_rmsprop_step: clip_grad_norm_(max_norm) over each network's flat gradient [G,count] (after grads *= grad_scale),
+ *   then optim.RMSprop (optimizers/__init__.py:28-33; not centered, no momentum) on params / square_avg [G,count];
+ *   active uint8 [G] or NULL; grad_norm_out [G] or NULL (the norm before clipping, clip_grad_norm_'s return value). */
+int maexp_loss_dqn(const float *q, const float *q_next_target, const int32_t *actions, const float *rewards, const uint8_t *dones,
+                   float gamma, int32_t G, int32_t B, int32_t A, float *loss_out, float *dq_out, void *stream);
+int maexp_loss_c51(const float *logits, const float *logits_next_online, const float *logits_next_target, const int32_t *actions,
+                   const float *rewards, const float *support, float gamma, float v_min, float v_max, float delta_z, int32_t G,
+                   int32_t B, int32_t A, int32_t Z, float *loss_out, float *d_logits_out, void *stream);
+int maexp_loss_qr(const float *quantiles, const float *quantiles_next_online, const float *quantiles_next_target,
+                  const int32_t *actions, const float *rewards, const float *tau_hats, float gamma, int32_t G, int32_t B, int32_t A,
+                  int32_t Z, float *loss_out, float *d_quantiles_out, void *stream);
+int maexp_loss_iqn(const float *quantiles, const float *quantiles_next_online, const float *quantiles_next_target,
+                   const float *taus, const int32_t *actions, const float *rewards, float gamma, int32_t G, int32_t B, int32_t A,
+                   int32_t Nq, int32_t Nd, float *loss_out, float *d_quantiles_out, void *stream);
+int maexp_clip_rmsprop_step(float *params, const float *grads, float *square_avg, int64_t count, int32_t G, float grad_scale,
+                            float max_norm, float learning_rate, float alpha, float eps, const uint8_t *active,
+                            float *grad_norm_out, void *stream);
+
 /* ObservationHandler.decode_relative_state (observation_handler.py:150-216): fp32 obs rows
  * [rows, obs_stride] (C*V*V valid) + int8 index-space positions [rows,2] -> canvas [rows,C,X,Y]
  * (0 everywhere, last channel -1, window∩map pasted).  only_area_plus_one = 1 writes

@@ -422,6 +422,7 @@ struct DistArgs {
 };
 
 __device__ __forceinline__ float dueling(const float *v, const float *adv, int A, int Z, int a, int j) {
+    if (!v) return adv[a * Z + j];  // stand-alone loss entry points: adv holds the network's combined output
     float s = 0.0f;
     for (int k = 0; k < A; ++k) s = __fadd_rn(s, adv[k * Z + j]);
     const float mean = __fdiv_rn(s, (float)A);
@@ -434,9 +435,10 @@ __global__ void c51_loss_kernel(const DistArgs p, float *m_scratch) {
     if (warp >= p.B) return;
     const int A = p.A, Z = p.Z;
     const size_t i = (size_t)g * p.B + warp;
-    const float *vs = p.v_s + i * Z, *as = p.a_s + i * A * Z;
-    const float *vn = p.v_n + i * Z, *an = p.a_n + i * A * Z;
-    const float *vt = p.v_t + i * Z, *at = p.a_t + i * A * Z;
+    const bool duel = p.v_s != nullptr;
+    const float *vs = duel ? p.v_s + i * Z : nullptr, *as = p.a_s + i * A * Z;
+    const float *vn = duel ? p.v_n + i * Z : nullptr, *an = p.a_n + i * A * Z;
+    const float *vt = duel ? p.v_t + i * Z : nullptr, *at = p.a_t + i * A * Z;
     const int a_taken = p.act[i];
 
     // best action of the ONLINE net on s': argmax_a sum_j softmax(out[a])_j z_j, first maximum wins
@@ -531,8 +533,8 @@ __global__ void c51_loss_kernel(const DistArgs p, float *m_scratch) {
         if (j >= Z) continue;
         const float sm = expf(__fadd_rn(l[t], -lse));
         const float gl = __fmul_rn(__fadd_rn(__fmul_rn(sm, msum), -m[j]), invB);  // d loss / d out[a_taken][j]
-        p.dv[i * Z + j] = gl;
-        const float shared = __fdiv_rn(gl, (float)A);
+        if (duel) p.dv[i * Z + j] = gl;
+        const float shared = duel ? __fdiv_rn(gl, (float)A) : 0.0f;
         for (int k = 0; k < A; ++k)
             p.da[i * A * Z + k * Z + j] = __fadd_rn(k == a_taken ? gl : 0.0f, -shared);
     }
@@ -544,9 +546,10 @@ __global__ void qr_loss_kernel(const DistArgs p) {
     if (warp >= p.B) return;
     const int A = p.A, Z = p.Z;
     const size_t i = (size_t)g * p.B + warp;
-    const float *vs = p.v_s + i * Z, *as = p.a_s + i * A * Z;
-    const float *vn = p.v_n + i * Z, *an = p.a_n + i * A * Z;
-    const float *vt = p.v_t + i * Z, *at = p.a_t + i * A * Z;
+    const bool duel = p.v_s != nullptr;
+    const float *vs = duel ? p.v_s + i * Z : nullptr, *as = p.a_s + i * A * Z;
+    const float *vn = duel ? p.v_n + i * Z : nullptr, *an = p.a_n + i * A * Z;
+    const float *vt = duel ? p.v_t + i * Z : nullptr, *at = p.a_t + i * A * Z;
     const int a_taken = p.act[i];
     int best = 0;
     float best_q = 0.0f;
@@ -568,8 +571,8 @@ __global__ void qr_loss_kernel(const DistArgs p) {
         loss = __fadd_rn(loss, __fmul_rn(w, huber));
         const float dh = ad <= 1.0f ? delta : (delta > 0.0f ? 1.0f : -1.0f);
         const float gl = __fmul_rn(-__fmul_rn(w, dh), invB);  // d loss / d theta_j
-        p.dv[i * Z + j] = gl;
-        const float shared = __fdiv_rn(gl, (float)A);
+        if (duel) p.dv[i * Z + j] = gl;
+        const float shared = duel ? __fdiv_rn(gl, (float)A) : 0.0f;
         for (int k = 0; k < A; ++k)
             p.da[i * A * Z + k * Z + j] = __fadd_rn(k == a_taken ? gl : 0.0f, -shared);
     }
@@ -694,6 +697,7 @@ struct IqnArgs {
 };
 
 __device__ __forceinline__ float iqn_quantile(const float *v, const float *adv, int A, int r, int a) {
+    if (!v) return adv[(size_t)r * A + a];  // stand-alone entry point: adv holds get_quantiles' output [B, N, A]
     float s = 0.0f;
     for (int k = 0; k < A; ++k) s = __fadd_rn(s, adv[(size_t)r * A + k]);
     return __fadd_rn(v[r], __fadd_rn(adv[(size_t)r * A + a], -__fdiv_rn(s, (float)A)));  // customs/iqn.py:133-134
@@ -704,9 +708,10 @@ __global__ void iqn_loss_kernel(const IqnArgs p) {
     const int g = blockIdx.y, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= p.B) return;
     const int A = p.A, Nq = p.Nq, Nd = p.Nd, b = warp;
-    const float *v0 = p.v0 + (size_t)g * p.gV, *a0 = p.a0 + (size_t)g * p.gA;
-    const float *v1 = p.v1 + (size_t)g * p.gV, *a1 = p.a1 + (size_t)g * p.gA;
-    const float *v2 = p.v2 + (size_t)g * p.gV2, *a2 = p.a2 + (size_t)g * p.gA2;
+    const bool duel = p.v0 != nullptr;
+    const float *v0 = duel ? p.v0 + (size_t)g * p.gV : nullptr, *a0 = p.a0 + (size_t)g * p.gA;
+    const float *v1 = duel ? p.v1 + (size_t)g * p.gV : nullptr, *a1 = p.a1 + (size_t)g * p.gA;
+    const float *v2 = duel ? p.v2 + (size_t)g * p.gV2 : nullptr, *a2 = p.a2 + (size_t)g * p.gA2;
     const size_t sb = (size_t)g * p.B + b;
     const int a_taken = p.act[sb];
     int best = 0;
@@ -736,8 +741,8 @@ __global__ void iqn_loss_kernel(const IqnArgs p) {
         }
         const float gl = __fmul_rn(grad, scale);  // d loss / d theta_i
         const size_t row = (size_t)b * Nq + i;
-        p.dv[(size_t)g * p.gV + row] = gl;
-        const float shared = __fdiv_rn(gl, (float)A);
+        if (duel) p.dv[(size_t)g * p.gV + row] = gl;
+        const float shared = duel ? __fdiv_rn(gl, (float)A) : 0.0f;
         for (int k = 0; k < A; ++k)
             p.da[(size_t)g * p.gA + row * A + k] = __fadd_rn(k == a_taken ? gl : 0.0f, -shared);
     }
@@ -3345,6 +3350,121 @@ int maexp_learner_apply(maexp_learner *h, float grad_scale, const uint8_t *activ
                                                             h->cfg.max_norm, h->cfg.learning_rate, h->cfg.alpha,
                                                             h->cfg.one_minus_alpha, h->cfg.eps, active, grad_norm_out);
     }
+    MAEXP_CUDA_L(cudaGetLastError());
+    return 0;
+}
+
+// ---- stand-alone loss / optimizer entry points on caller-owned network outputs (the same kernels as the learner's)
+namespace {
+struct StreamScratch {  // stream-ordered scratch: safe with concurrent streams and under graph capture
+    cudaStream_t st;
+    std::vector<void *> ptrs;
+    explicit StreamScratch(cudaStream_t s) : st(s) {}
+    float *get(size_t floats) {
+        void *d = nullptr;
+        if (cudaMallocAsync(&d, sizeof(float) * (floats ? floats : 1), st) != cudaSuccess) return nullptr;
+        ptrs.push_back(d);
+        return static_cast<float *>(d);
+    }
+    ~StreamScratch() { for (void *d : ptrs) cudaFreeAsync(d, st); }
+};
+int loss_shape_ok(const char *who, int G, int B, int A, int Z) {
+    if (G < 1 || B < 1 || A < 1 || A > kMaxActions) return fail(std::string(who) + ": bad shape (1 <= num_actions <= 8)");
+    if (Z < 1 || Z > 32 * kMaxAtomsPerLane) return fail(std::string(who) + ": atoms / quantiles must be in 1..128");
+    return 0;
+}
+}  // namespace
+
+int maexp_loss_dqn(const float *q, const float *q_next_target, const int32_t *actions, const float *rewards, const uint8_t *dones,
+                   float gamma, int32_t G, int32_t B, int32_t A, float *loss_out, float *dq_out, void *stream) {
+    if (!q || !q_next_target || !actions || !rewards || !dones || !loss_out || !dq_out) return fail("maexp_loss_dqn: null argument");
+    if (loss_shape_ok("maexp_loss_dqn", G, B, A, 1)) return -1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamScratch ws(st);
+    float *per = ws.get((size_t)G * B);
+    if (!per) return fail("maexp_loss_dqn: scratch allocation failed");
+    dqn_loss_kernel<<<dim3((B + 127) / 128, G), 128, 0, st>>>(q, q_next_target, actions, rewards, dones, gamma, B, A, dq_out, per);
+    mean_kernel<<<G, 256, 0, st>>>(per, loss_out, B);
+    MAEXP_CUDA_L(cudaGetLastError());
+    return 0;
+}
+
+static int dist_loss(const char *who, bool c51, const float *out_s, const float *out_next_online, const float *out_next_target,
+                     const int32_t *actions, const float *rewards, const float *support, float gamma, float v_min, float v_max,
+                     float delta_z, int G, int B, int A, int Z, float *loss_out, float *d_out, void *stream) {
+    if (!out_s || !out_next_online || !out_next_target || !actions || !rewards || !support || !loss_out || !d_out)
+        return fail(std::string(who) + ": null argument");
+    if (loss_shape_ok(who, G, B, A, Z)) return -1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamScratch ws(st);
+    float *per = ws.get((size_t)G * B), *m = c51 ? ws.get((size_t)G * B * Z) : per;
+    if (!per || !m) return fail(std::string(who) + ": scratch allocation failed");
+    DistArgs p;
+    p.v_s = p.v_n = p.v_t = nullptr;  // combined outputs: no dueling inside the kernel
+    p.a_s = out_s; p.a_n = out_next_online; p.a_t = out_next_target;
+    p.act = actions; p.rew = rewards; p.support = support;
+    p.dv = nullptr; p.da = d_out; p.per_sample = per;
+    p.B = B; p.A = A; p.Z = Z;
+    p.gamma = gamma; p.v_min = v_min; p.v_max = v_max; p.delta_z = delta_z;
+    const dim3 grid((B * 32 + 255) / 256, G);
+    if (c51) c51_loss_kernel<<<grid, 256, 0, st>>>(p, m);
+    else qr_loss_kernel<<<grid, 256, 0, st>>>(p);
+    mean_kernel<<<G, 256, 0, st>>>(per, loss_out, B);
+    MAEXP_CUDA_L(cudaGetLastError());
+    return 0;
+}
+
+int maexp_loss_c51(const float *logits, const float *logits_next_online, const float *logits_next_target, const int32_t *actions,
+                   const float *rewards, const float *support, float gamma, float v_min, float v_max, float delta_z, int32_t G,
+                   int32_t B, int32_t A, int32_t Z, float *loss_out, float *d_logits_out, void *stream) {
+    return dist_loss("maexp_loss_c51", true, logits, logits_next_online, logits_next_target, actions, rewards, support, gamma,
+                     v_min, v_max, delta_z, G, B, A, Z, loss_out, d_logits_out, stream);
+}
+
+int maexp_loss_qr(const float *quantiles, const float *quantiles_next_online, const float *quantiles_next_target,
+                  const int32_t *actions, const float *rewards, const float *tau_hats, float gamma, int32_t G, int32_t B, int32_t A,
+                  int32_t Z, float *loss_out, float *d_quantiles_out, void *stream) {
+    return dist_loss("maexp_loss_qr", false, quantiles, quantiles_next_online, quantiles_next_target, actions, rewards, tau_hats,
+                     gamma, 0.0f, 0.0f, 1.0f, G, B, A, Z, loss_out, d_quantiles_out, stream);
+}
+
+int maexp_loss_iqn(const float *quantiles, const float *quantiles_next_online, const float *quantiles_next_target,
+                   const float *taus, const int32_t *actions, const float *rewards, float gamma, int32_t G, int32_t B, int32_t A,
+                   int32_t Nq, int32_t Nd, float *loss_out, float *d_quantiles_out, void *stream) {
+    if (!quantiles || !quantiles_next_online || !quantiles_next_target || !taus || !actions || !rewards || !loss_out || !d_quantiles_out)
+        return fail("maexp_loss_iqn: null argument");
+    if (loss_shape_ok("maexp_loss_iqn", G, B, A, 1) || Nq < 1 || Nd < 1) return fail("maexp_loss_iqn: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamScratch ws(st);
+    float *per = ws.get((size_t)G * B);
+    if (!per) return fail("maexp_loss_iqn: scratch allocation failed");
+    IqnArgs p;
+    p.v0 = p.v1 = p.v2 = nullptr;
+    p.a0 = quantiles; p.a1 = quantiles_next_online; p.a2 = quantiles_next_target;
+    p.taus = taus; p.act = actions; p.rew = rewards;
+    p.dv = nullptr; p.da = d_quantiles_out; p.per_sample = per;
+    p.B = B; p.A = A; p.Nq = Nq; p.Nd = Nd;
+    p.gV = 0; p.gA = (long long)B * Nq * A; p.gV2 = 0; p.gA2 = (long long)B * Nd * A; p.gT = (long long)B * Nq;
+    p.gamma = gamma;
+    iqn_loss_kernel<<<dim3((B * 32 + 255) / 256, G), 256, 0, st>>>(p);
+    mean_kernel<<<G, 256, 0, st>>>(per, loss_out, B);
+    MAEXP_CUDA_L(cudaGetLastError());
+    return 0;
+}
+
+int maexp_clip_rmsprop_step(float *params, const float *grads, float *square_avg, int64_t count, int32_t G, float grad_scale,
+                            float max_norm, float learning_rate, float alpha, float eps, const uint8_t *active,
+                            float *grad_norm_out, void *stream) {
+    if (!params || !grads || !square_avg) return fail("maexp_clip_rmsprop_step: null argument");
+    if (count < 1 || G < 1) return fail("maexp_clip_rmsprop_step: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StreamScratch ws(st);
+    const int nparts = 32;
+    float *partial = ws.get((size_t)G * nparts);
+    if (!partial) return fail("maexp_clip_rmsprop_step: scratch allocation failed");
+    sqnorm_partial_kernel<<<dim3(nparts, G), 256, 0, st>>>(grads, partial, count, grad_scale);
+    clip_rmsprop_kernel<<<dim3(64, G), 256, 0, st>>>(params, grads, square_avg, partial, nparts, count, grad_scale, max_norm,
+                                                     learning_rate, alpha, 1.0f - alpha, eps, active, grad_norm_out);
     MAEXP_CUDA_L(cudaGetLastError());
     return 0;
 }

@@ -302,7 +302,7 @@ def test_replay_ring_sampling():
         n = (s + 1) % S
         assert torch.equal(batch["obs"][:, j].cpu(), obs[s, :, e])
         assert torch.equal(batch["next_obs"][:, j].cpu(), obs[n, :, e])
-        assert torch.equal(batch["actions"][:, j].cpu(), act[n, e].to(torch.int32))
+        assert torch.equal(batch["actions"][:, j].cpu(), act[n, e].to(torch.int32).clamp(min=0))  # -1 (reset slot) is flagged and clamped
         assert torch.equal(batch["rewards"][:, j].cpu(), rew[n, e]) and torch.equal(batch["dones"][:, j].cpu(), done[n, e])
         assert torch.equal(batch["pos"][:, j].cpu(), positions[s, e]) and torch.equal(batch["next_pos"][:, j].cpu(), positions[n, e])
     # (2) Philox picks: in range, never a transition into a reset slot, reproducible, tick-dependent
