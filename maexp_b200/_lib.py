@@ -126,7 +126,7 @@ SYMBOLS = {
     "maexp_loss_c51": (C.c_int, [C.c_void_p] * 6 + [C.c_float] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 3),
     "maexp_loss_qr": (C.c_int, [C.c_void_p] * 6 + [C.c_float] + [C.c_int32] * 4 + [C.c_void_p] * 3),
     "maexp_loss_iqn": (C.c_int, [C.c_void_p] * 6 + [C.c_float] + [C.c_int32] * 5 + [C.c_void_p] * 3),
-    "maexp_clip_rmsprop_step": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32] + [C.c_float] * 6 + [C.c_void_p] * 3),
+    "maexp_clip_rmsprop_step": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32] + [C.c_float] * 5 + [C.c_void_p] * 3),
     "maexp_fill_uniform": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint32, C.c_uint32, C.c_void_p]),
     "maexp_last_error": (C.c_char_p, []),
     "maexp_version": (C.c_int, []),

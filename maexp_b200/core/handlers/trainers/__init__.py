@@ -105,7 +105,6 @@ class DefaultTrainer:
         if self.episode_count % int(self.config.synchronize_frequency) == 0:
             self.learner.synchronize()
         self.buffer.check(self.batch)  # the replay sampler's error flag (one host sync per episode)
-        self.log_scalar()
         self.reset()  # default_trainer.py:99: every epoch is one episode
         self.episode_count += 1
 
@@ -135,9 +134,11 @@ class DefaultTrainer:
             stats = self.env.stats()
             if stats["error_flag"]:
                 raise RuntimeError("the respawn sampler hit its attempt cap (objects_area too small, SURVEY.md §E-8)")
-            self.history.append({"episode": self.episode_count, "epsilon": self.epsilon,
-                                 "reward_per_env": float(self.episode_return.mean()), "loss": float(loss_sum)})
+            reward = float(self.episode_return.mean())  # the episode's return, summed over the team, mean over environments
             self.loop_epoch_end()
+            self.history.append({"episode": self.episode_count, "epsilon": self.epsilon, "reward_per_env": reward,
+                                 "loss": float(loss_sum)})
+            self.log_scalar()
         return self.history
 
     # ---- abstract_loop_handler.py:149-166 (local files instead of wandb artifacts)

@@ -354,7 +354,7 @@ def test_replay_sampler_flags_a_ring_without_valid_transitions():
     bad = torch.tensor([[7, 0]] + [[(ring.head - 1) % 2, 1]] * (B - 1), dtype=torch.int32).cuda()
     ring.sample(batch, indices=bad)
     torch.cuda.synchronize()
-    assert int(batch["error_flag"].item()) == _lib.REPLAY_ERR_INDEX_RANGE
+    assert int(batch["error_flag"].item()) & _lib.REPLAY_ERR_INDEX_RANGE
     with pytest.raises(_lib.MaexpError):
         ring.check(batch)
     env2 = make_env(cfg, E, auto_reset=True)
