@@ -154,8 +154,8 @@ int upload(maexp_env *h, const Tp **ptr, const std::vector<Tp> &host) {
 size_t env_smem_bytes(const EnvParams &p, int V, int epw) {
     (void)V;
     size_t words = 256;  // nibble -> float4 table; static map tables stay in global memory (read-only L1 path)
-    const size_t per_warp = (size_t)epw * p.gs + (size_t)epw * p.as + (size_t)epw * p.ws +
-                            ((size_t)p.N * epw + (size_t)p.P * p.N * epw + 1) / 2 + (epw + 3) / 4;
+    const size_t per_warp = ((size_t)epw * p.gs + (size_t)epw * p.as + (size_t)epw * p.ws +
+                             ((size_t)p.N * epw + (size_t)p.P * p.N * epw + 1) / 2 + (epw + 3) / 4 + 3) & ~(size_t)3;
     words += per_warp * kWarpsPerCta;
     return words * 4;
 }
@@ -254,7 +254,7 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     p.qps = p.slot_floats / 4;
     p.qps_magic = (uint32_t)((0x100000000ull + p.qps - 1) / p.qps);
     p.wpa = (p.K + 31) / 32;
-    p.ws = (p.wpa + 4) | 1;
+    p.ws = p.wpa + 3;  // words per env in the (word-major) observation bit buffer, incl. the zero slack BitStream::finish writes
     p.gs = (T * (X + 2 * (V / 2))) | 1;
     p.tx_magic = (uint32_t)((0x100000000ull + (uint64_t)(T * X) - 1) / (uint64_t)(T * X));
     p.as = (X + 2 * (V / 2)) | 1;

@@ -103,7 +103,9 @@ __device__ __forceinline__ uint64_t fisher_yates(uint64_t v, int n, uint32_t see
 
 // Appends V*V-bit channel masks to a bit stream in output order.  Pending bits live in a
 // register accumulator; completed 32-bit words are written once (no shared-memory RMW chain).
-template <int V>
+// Word k of an env lives at out[k * STRIDE] (STRIDE = envs per warp): the lanes of a warp (one env each) write
+// consecutive banks, and the expansion phase reads four envs' words with one 128-bit load.
+template <int V, int STRIDE>
 struct BitStream {
     unsigned __int128 acc = 0;
     int nbits = 0;
@@ -113,17 +115,87 @@ struct BitStream {
         acc |= (unsigned __int128)m << nbits;  // nbits < 32, V*V <= 81
         nbits += V * V;
         while (nbits >= 32) {
-            *out++ = (uint32_t)acc;
+            *out = (uint32_t)acc;
+            out += STRIDE;
             acc >>= 32;
             nbits -= 32;
         }
     }
     __device__ __forceinline__ void finish() {  // flush the tail and one zero word of slack
-        *out++ = (uint32_t)acc;
-        out[0] = 0u;
-        out[1] = 0u;
+        out[0] = (uint32_t)acc;
+        out[STRIDE] = 0u;
+        out[2 * STRIDE] = 0u;
     }
 };
+
+// Phase B hot path (no noise, every env of the group active, one output slot): expands a full group's bit words of one
+// agent into fp32 and streams them out.  A lane owns quad q (4 consecutive floats) of every env it visits, so the shift,
+// the LUT class and the word row are per-lane constants; the envs' words come four at a time (128-bit shared loads) and
+// with SLOT (floats per agent slot) known at compile time every store address is base + immediate.
+template <int SLOT, int EPW>
+__device__ __forceinline__ void expand_group(const uint32_t *s_w, const float4 *s_lut, float *dst, int lane, int slot_rt,
+                                             int q_str, int q_tail) {
+    const int slot = SLOT ? SLOT : slot_rt, qps = slot >> 2;
+    const int nfull = qps >> 5, rem = qps & 31;
+    // A lookup costs two integer instructions: rotate the word so that the lane's nibble sits at bits 4..7 (= nibble * 16,
+    // the byte offset of the 16-byte LUT entry) and OR it into the class table's shared-memory address (every class table
+    // is 256 bytes and 256-byte aligned: the LUT is the first thing in the 1024-byte aligned dynamic shared memory).
+    auto lut_of = [&](int q) {
+        return (uint32_t)__cvta_generic_to_shared(s_lut + (q > q_tail ? 0 : ((q >= q_str) + (q > q_str) + (q == q_tail)) * 16));
+    };
+    auto look = [](uint32_t lut, uint32_t w, int sh) {
+        const uint32_t r = __funnelshift_r(w, w, (uint32_t)(sh - 4) & 31u);
+        float4 v;
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((r & 0xF0u) | lut));
+        return v;
+    };
+#pragma unroll
+    for (int c = 0; c < nfull; ++c) {
+        const int q = c * 32 + lane, sh = (q & 7) * 4;
+        const uint32_t lut = lut_of(q);
+        const uint32_t *wq = s_w + (q >> 3) * EPW;
+        float *dp = dst + q * 4;
+#pragma unroll
+        for (int e = 0; e < EPW; e += 4) {
+            const uint4 w = *reinterpret_cast<const uint4 *>(wq + e);
+            store_quad(reinterpret_cast<float4 *>(dp + (e + 0) * slot), look(lut, w.x, sh));
+            store_quad(reinterpret_cast<float4 *>(dp + (e + 1) * slot), look(lut, w.y, sh));
+            store_quad(reinterpret_cast<float4 *>(dp + (e + 2) * slot), look(lut, w.z, sh));
+            store_quad(reinterpret_cast<float4 *>(dp + (e + 3) * slot), look(lut, w.w, sh));
+        }
+    }
+    if (rem) {  // trailing quads: lanes split as (env block, quad) with a power-of-two quad pitch
+        int pitch = 1;
+        while (pitch < rem) pitch <<= 1;
+        const int r = lane & (pitch - 1), blocks = 32 / pitch, per = EPW / blocks;  // per: envs a lane visits (contiguous)
+        if (per >= 4) {
+            const int e0 = (lane / pitch) * per;
+            if (r < rem) {
+                const int q = nfull * 32 + r, sh = (q & 7) * 4;
+                const uint32_t lut = lut_of(q);
+                const uint32_t *wq = s_w + (q >> 3) * EPW + e0;
+                float *dp = dst + (size_t)e0 * slot + q * 4;
+#pragma unroll
+                for (int e = 0; e < per; e += 4) {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(wq + e);
+                    store_quad(reinterpret_cast<float4 *>(dp + (e + 0) * slot), look(lut, w.x, sh));
+                    store_quad(reinterpret_cast<float4 *>(dp + (e + 1) * slot), look(lut, w.y, sh));
+                    store_quad(reinterpret_cast<float4 *>(dp + (e + 2) * slot), look(lut, w.z, sh));
+                    store_quad(reinterpret_cast<float4 *>(dp + (e + 3) * slot), look(lut, w.w, sh));
+                }
+            }
+        } else {  // more env blocks than a lane can fill with a vector load: one env at a time
+            const int esub = lane / pitch;
+            if (r < rem) {
+                const int q = nfull * 32 + r, sh = (q & 7) * 4;
+                const uint32_t lut = lut_of(q);
+                const uint32_t *wq = s_w + (q >> 3) * EPW;
+                for (int e = esub; e < EPW; e += blocks)
+                    store_quad(reinterpret_cast<float4 *>(dst + (size_t)e * slot + q * 4), look(lut, wq[e], sh));
+            }
+        }
+    }
+}
 
 #ifndef MAEXP_NOISE_UNROLL
 #define MAEXP_NOISE_UNROLL 2
@@ -136,7 +208,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     constexpr int R = V / 2, VV = V * V;
     constexpr int LW = (V == 9) ? 2 : 1;
     using WinT = typename Win<V>::T;
-    extern __shared__ __align__(16) uint32_t smem[];
+    extern __shared__ __align__(1024) uint32_t smem[];
 
     // NSPEC = 8: agents and object types are compile-time constants (N = 8, T = 1, no transition frames), so the
     // per-agent loops unroll; NSPEC = 0: everything from the parameter block
@@ -150,13 +222,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     const uint32_t *const s_wall = p.wall, *const s_noise = p.noise_area, *const s_area = p.area, *const s_dest = p.dest;
     const uint64_t *const s_los = p.los;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per_warp_words = EPW * p.gs + EPW * p.as + EPW * p.ws + (N * EPW + P * N * EPW + 1) / 2 + (EPW + 3) / 4;
-    uint32_t *s_grid = s_warp0 + (size_t)warp * per_warp_words;
+    const int per_warp_words = (EPW * p.gs + EPW * p.as + EPW * p.ws + (N * EPW + P * N * EPW + 1) / 2 + (EPW + 3) / 4 + 3) & ~3;
+    uint32_t *s_w = s_warp0 + (size_t)warp * per_warp_words;  // observation bit words, word k of env e at s_w[k * EPW + e]
+    uint32_t *s_grid = s_w + EPW * p.ws;
     uint32_t *s_agrid = s_grid + EPW * p.gs;  // agents occupancy, one bit row per map x
-    uint32_t *s_w = s_agrid + EPW * p.as;
-    uint16_t *s_pos = reinterpret_cast<uint16_t *>(s_w + EPW * p.ws);
+    uint16_t *s_pos = reinterpret_cast<uint16_t *>(s_agrid + EPW * p.as);
     uint16_t *s_past = s_pos + N * EPW;
-    uint8_t *s_active = reinterpret_cast<uint8_t *>(s_w + EPW * p.ws + (N * EPW + P * N * EPW + 1) / 2);
+    uint8_t *s_active = reinterpret_cast<uint8_t *>(s_agrid + EPW * p.as + (N * EPW + P * N * EPW + 1) / 2);
 
     if (threadIdx.x < 64) {  // nibble → float4 expansion table, classes: 0 plain, 1 straddle, 2 area, 3 tail
         const int cls = threadIdx.x >> 4, n = threadIdx.x & 15;
@@ -188,7 +260,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
 #pragma unroll 4
         for (int i = lane; i < nenv * TX; i += 32) {
             const int e = (int)__umulhi((uint32_t)i, p.tx_magic), r = i - e * TX;
-            int t = (r >= X) + (r >= 2 * X) + (r >= 3 * X);
+            int t = NSPEC ? 0 : (r >= X) + (r >= 2 * X) + (r >= 3 * X);
             if (!NSPEC && T > 4) t += (r >= 4 * X) + (r >= 5 * X) + (r >= 6 * X) + (r >= 7 * X);
             s_grid[e * p.gs + R + r + t * 2 * R] = src[i] << R;
         }
@@ -201,7 +273,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     const uint32_t gid = p.gid0 + (uint32_t)env;
     uint32_t *grid = s_grid + lane * p.gs + R;    // row (t, x) at grid[t * XP + x], x in [-R, X + R)
     uint32_t *agrid = s_agrid + lane * p.as + R;  // row x at agrid[x]
-    uint32_t *wv = s_w + lane * p.ws;
+    uint32_t *wv = s_w + lane;  // word k at wv[k * EPW]
     uint16_t *mypos = s_pos + lane;  // agent k at mypos[k*EPW]
     int stepc = 0, nobj = 0;
     int c_gen = 0, c_done = 0, c_ca = 0, c_cw = 0;
@@ -447,17 +519,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                     const unsigned __int128 lo = (unsigned __int128)A | ((unsigned __int128)O << VV) |
                                                  ((unsigned __int128)los << (2 * VV));
                     wv[0] = (uint32_t)lo;
-                    wv[1] = (uint32_t)(lo >> 32);
-                    wv[2] = (uint32_t)(lo >> 64);
-                    wv[3] = (uint32_t)(lo >> 96);
+                    wv[EPW] = (uint32_t)(lo >> 32);
+                    wv[2 * EPW] = (uint32_t)(lo >> 64);
+                    wv[3 * EPW] = (uint32_t)(lo >> 96);
                     constexpr int kHi = 128 - 2 * VV;
-                    wv[4] = kHi < 64 ? (uint32_t)(los >> (kHi < 64 ? kHi : 0)) : 0u;
-                    wv[5] = 0u;
+                    wv[4 * EPW] = kHi < 64 ? (uint32_t)(los >> (kHi < 64 ? kHi : 0)) : 0u;
+                    wv[5 * EPW] = 0u;
                     done_fast = true;
                 }
             }
             if (!done_fast) {
-            BitStream<V> bs(wv);
+            BitStream<V, EPW> bs(wv);
             const int av = p.agent_view;
             if (av == MAEXP_AV_INDIVIDUAL || av == MAEXP_AV_INDIVIDUAL_TRANSITION)
                 for (int k = 0; k < N; ++k) bs.put(win_bit(mypos[k * EPW]) & los);
@@ -523,7 +595,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
 
         // ---------------------------------------------------------- phase B: expand + stream out
         if (p.out.obs) {
-            const int qps = p.qps, ws = p.ws;
+            const int qps = p.qps;
             // ring slot layout is agent-major [N][E][slot_floats]: agent i's slots of this group are one contiguous run
             const int env_stride = p.slot_floats;
             const size_t base = ((size_t)i * p.E + env0) * p.slot_floats;
@@ -615,27 +687,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             };
             auto quad_class = [&](int q) { return q > p.q_tail ? 0 : ((q >= p.q_str) + (q > p.q_str) + (q == p.q_tail)) * 16; };
 
+            if (NOISE == MAEXP_NOISE_NONE && !check && !dst_rel && nenv == EPW) {
+                // hot path: the whole group, compile-time slot geometry for the common 3-channel shapes
+                switch (p.slot_floats) {
+                case 152: expand_group<152, EPW>(s_w, s_lut, dst, lane, 152, p.q_str, p.q_tail); break;  // V = 7, C = 3
+                case 80: expand_group<80, EPW>(s_w, s_lut, dst, lane, 80, p.q_str, p.q_tail); break;     // V = 5, C = 3
+                default: expand_group<0, EPW>(s_w, s_lut, dst, lane, p.slot_floats, p.q_str, p.q_tail);
+                }
+            } else {
             // (1) full chunks: lane owns quad q = c*32 + lane of every env → per-lane constants hoisted,
             //     each store instruction covers 512 contiguous bytes of one agent slot
             const int nfull = qps >> 5;
             for (int c = 0; c < nfull; ++c) {
                 const int q = c * 32 + lane;
                 const int sh = (q & 7) * 4, lut_off = quad_class(q);
-                const uint32_t *wq = s_w + (q >> 3);
+                const uint32_t *wq = s_w + (q >> 3) * EPW;
                 const QuadNoise qn = quad_noise(q);
-                if (NOISE == MAEXP_NOISE_NONE && !check && !dst_rel) {
-                    // hot path: running pointers, ~12 instructions per 16 bytes stored
-                    const float4 *lut = s_lut + lut_off;
-                    float *dp = dst + q * 4;
-#pragma unroll 4
-                    for (int e = 0; e < nenv; ++e, wq += ws, dp += env_stride)
-                        store_quad(reinterpret_cast<float4 *>(dp), lut[(*wq >> sh) & 0xFu]);
-                } else if (!check) {
+                if (!check) {
 #pragma unroll kUnrollEnvs
-                    for (int e = 0; e < nenv; ++e) emit(e, q, wq[e * ws], sh, lut_off, qn);
+                    for (int e = 0; e < nenv; ++e) emit(e, q, wq[e], sh, lut_off, qn);
                 } else {
                     for (int e = 0; e < nenv; ++e)
-                        if (s_active[e] & 1) emit(e, q, wq[e * ws], sh, lut_off, qn);
+                        if (s_active[e] & 1) emit(e, q, wq[e], sh, lut_off, qn);
                 }
             }
             // (2) the qps % 32 trailing quads: lanes split as (env sub-index, quad) with a power-of-two quad
@@ -648,22 +721,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                 if (r < rem) {
                     const int q = nfull * 32 + r;
                     const int sh = (q & 7) * 4, lut_off = quad_class(q);
-                    const uint32_t *wq = s_w + esub * ws + (q >> 3);
+                    const uint32_t *wq = s_w + (q >> 3) * EPW;
                     const QuadNoise qn = quad_noise(q);
-                    if (NOISE == MAEXP_NOISE_NONE && !check && !dst_rel) {
-                        const float4 *lut = s_lut + lut_off;
-                        float *dp = dst + esub * env_stride + q * 4;
-#pragma unroll 2
-                        for (int e = esub; e < nenv; e += estep, wq += estep * ws, dp += estep * env_stride)
-                            store_quad(reinterpret_cast<float4 *>(dp), lut[(*wq >> sh) & 0xFu]);
-                    } else if (!check) {
+                    if (!check) {
 #pragma unroll kUnrollEnvs
-                        for (int e = esub; e < nenv; e += estep) emit(e, q, wq[(e - esub) * ws], sh, lut_off, qn);
+                        for (int e = esub; e < nenv; e += estep) emit(e, q, wq[e], sh, lut_off, qn);
                     } else {
-                        for (int e = esub; e < nenv; e += estep, wq += estep * ws)
-                            if (s_active[e] & 1) emit(e, q, *wq, sh, lut_off, qn);
+                        for (int e = esub; e < nenv; e += estep)
+                            if (s_active[e] & 1) emit(e, q, wq[e], sh, lut_off, qn);
                     }
                 }
+            }
             }
         }
         __syncwarp();
@@ -782,7 +850,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
 #pragma unroll 4
         for (int i = lane; i < nenv * TX; i += 32) {
             const int e = (int)__umulhi((uint32_t)i, p.tx_magic), r = i - e * TX;
-            int t = (r >= X) + (r >= 2 * X) + (r >= 3 * X);
+            int t = NSPEC ? 0 : (r >= X) + (r >= 2 * X) + (r >= 3 * X);
             if (!NSPEC && T > 4) t += (r >= 4 * X) + (r >= 5 * X) + (r >= 6 * X) + (r >= 7 * X);
             if (s_active[e] & 1) dst[i] = s_grid[e * p.gs + R + r + t * 2 * R] >> R;
         }
