@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmaexp_b200.so")
+LIB_PATH = os.environ.get("MAEXP_LIB") or os.path.join(HERE, "libmaexp_b200.so")  # MAEXP_LIB: experiment builds (tools/)
 
 MAX_AGENTS, MAX_TYPES, MAX_RINGS = 16, 8, 4
 

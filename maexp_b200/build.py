@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-LIB = os.path.join(HERE, "libmaexp_b200.so")
+LIB = os.environ.get("MAEXP_LIB") or os.path.join(HERE, "libmaexp_b200.so")  # MAEXP_LIB: experiment builds (tools/)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = os.environ.get("MAEXP_EXTRA_NVCC", "").split() + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--fmad=false",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-I", INCLUDE]
@@ -34,7 +34,7 @@ def build(force=False, verbose=False):
     from concurrent.futures import ThreadPoolExecutor
 
     def compile_one(src):
-        obj = os.path.join(CSRC, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(os.environ.get("MAEXP_OBJ_DIR") or CSRC, os.path.basename(src)[:-3] + ".o")
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         subprocess.check_call(cmd)
         return obj

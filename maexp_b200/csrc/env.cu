@@ -343,6 +343,9 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     // 8 -> 119 us, 16 -> 89 us, 32 -> 93 us per step; small batches prefer more, shorter groups.
     // With observation noise the expansion phase dominates (one Philox call per quad), and it runs at full lane
     // efficiency only when a warp's group has 32 envs: flip-noise cfg2 256 -> 223 us per step.
+    p.stagger_ns = 0;
+    p.stagger_div = sms;
+    if (const char *sg = getenv("MAEXP_STAGGER_NS")) p.stagger_ns = atoi(sg);
     h->epw = (E >= 16 * sms * 8) ? (p.noise != MAEXP_NOISE_NONE && E >= 32 * sms * 4 ? 32 : 16) : 8;
     if (const char *force = getenv("MAEXP_EPW")) {
         const int v = atoi(force);

@@ -22,6 +22,7 @@ struct EnvParams {
     int fast3;  // 3 channels (total agents, all objects, area) and V <= 7: compile-time bit assembly
     int L, num_objects, keep, shuffle_init, auto_reset, random_dest, env_kind;
     int n_init;  // len(config.init_xys) >= N: the start-cell order has one entry per init_xys row
+    int stagger_ns, stagger_div;  // experiment knob (MAEXP_STAGGER_NS): CTAs of every other resident slot start late
     uint32_t seed, gid0, tick;
     int force_reset;
     const uint8_t *env_mask;
@@ -63,6 +64,8 @@ __device__ __forceinline__ void store_quad(float4 *ptr, const float4 &v) {
     __stcs(ptr, v);   // st.global.cs: streaming, evict-first
 #elif MAEXP_ST == 1
     *ptr = v;         // default write-back policy
+#elif MAEXP_ST == 3
+    if (__float_as_uint(v.x) == 0x12345678u) __stcs(ptr, v);  // experiment: everything but the store (never taken)
 #else
     __stcg(ptr, v);   // st.global.cg: cache in L2 only
 #endif
@@ -129,39 +132,49 @@ struct BitStream {
 };
 
 // Phase B hot path (no noise, every env of the group active, one output slot): expands a full group's bit words of one
-// agent into fp32 and streams them out.  A lane owns quad q (4 consecutive floats) of every env it visits, so the shift,
-// the LUT class and the word row are per-lane constants; the envs' words come four at a time (128-bit shared loads) and
-// with SLOT (floats per agent slot) known at compile time every store address is base + immediate.
+// agent into fp32 and streams them out.  A lane owns quad q (4 consecutive floats) of every env it visits, so the shift
+// and the quad's class are per-lane constants; the envs' words come four at a time (128-bit shared loads) and with SLOT
+// (floats per agent slot) known at compile time every store address is base + immediate.
+// The expansion is arithmetic (no table lookup: the shared-memory / L1 pipe is this kernel's busiest unit and already
+// carries the stores): element j of the quad is bit_j - sub_j, sub_j = 1 for elements of the area channel
+// (observation_handler.py:107-108), i.e. ((bit_j ^ sub_j) ? (sub_j ? -1.0f : 1.0f) : 0.0f); with t = (x ^ sub) & 2^j in
+// {0, 2^j} the float's bit pattern is t * (pattern >> j) — one LOP3 and one IMAD per element (1.0f and -1.0f have 23 zero
+// low bits, so the shift loses nothing).
 template <int SLOT, int EPW>
-__device__ __forceinline__ void expand_group(const uint32_t *s_w, const float4 *s_lut, float *dst, int lane, int slot_rt,
-                                             int q_str, int q_tail) {
+__device__ __forceinline__ void expand_group(const uint32_t *s_w, float *dst, int lane, int slot_rt, int q_str, int q_tail,
+                                             int sub_str, int sub_tail) {
     const int slot = SLOT ? SLOT : slot_rt, qps = slot >> 2;
     const int nfull = qps >> 5, rem = qps & 31;
-    // A lookup costs two integer instructions: rotate the word so that the lane's nibble sits at bits 4..7 (= nibble * 16,
-    // the byte offset of the 16-byte LUT entry) and OR it into the class table's shared-memory address (every class table
-    // is 256 bytes and 256-byte aligned: the LUT is the first thing in the 1024-byte aligned dynamic shared memory).
-    auto lut_of = [&](int q) {
-        return (uint32_t)__cvta_generic_to_shared(s_lut + (q > q_tail ? 0 : ((q >= q_str) + (q > q_str) + (q == q_tail)) * 16));
+    struct QuadConst { uint32_t sub, h0, h1, h2, h3; int sh; };
+    auto consts = [&](int q) {
+        QuadConst c;
+        const int cls = q > q_tail ? 0 : ((q >= q_str) + (q > q_str) + (q == q_tail));
+        c.sub = cls == 0 ? 0u : (cls == 1 ? (uint32_t)sub_str : (cls == 2 ? 15u : (uint32_t)sub_tail));
+        c.h0 = (0x3f800000u | ((c.sub & 1u) << 31));
+        c.h1 = (0x3f800000u | (((c.sub >> 1) & 1u) << 31)) >> 1;
+        c.h2 = (0x3f800000u | (((c.sub >> 2) & 1u) << 31)) >> 2;
+        c.h3 = (0x3f800000u | (((c.sub >> 3) & 1u) << 31)) >> 3;
+        c.sh = (q & 7) * 4;
+        return c;
     };
-    auto look = [](uint32_t lut, uint32_t w, int sh) {
-        const uint32_t r = __funnelshift_r(w, w, (uint32_t)(sh - 4) & 31u);
-        float4 v;
-        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((r & 0xF0u) | lut));
-        return v;
+    auto expand = [](const QuadConst &c, uint32_t w) {
+        const uint32_t x = w >> c.sh;
+        return make_float4(__uint_as_float(((x ^ c.sub) & 1u) * c.h0), __uint_as_float(((x ^ c.sub) & 2u) * c.h1),
+                           __uint_as_float(((x ^ c.sub) & 4u) * c.h2), __uint_as_float(((x ^ c.sub) & 8u) * c.h3));
     };
 #pragma unroll
     for (int c = 0; c < nfull; ++c) {
-        const int q = c * 32 + lane, sh = (q & 7) * 4;
-        const uint32_t lut = lut_of(q);
+        const int q = c * 32 + lane;
+        const QuadConst k = consts(q);
         const uint32_t *wq = s_w + (q >> 3) * EPW;
         float *dp = dst + q * 4;
 #pragma unroll
         for (int e = 0; e < EPW; e += 4) {
             const uint4 w = *reinterpret_cast<const uint4 *>(wq + e);
-            store_quad(reinterpret_cast<float4 *>(dp + (e + 0) * slot), look(lut, w.x, sh));
-            store_quad(reinterpret_cast<float4 *>(dp + (e + 1) * slot), look(lut, w.y, sh));
-            store_quad(reinterpret_cast<float4 *>(dp + (e + 2) * slot), look(lut, w.z, sh));
-            store_quad(reinterpret_cast<float4 *>(dp + (e + 3) * slot), look(lut, w.w, sh));
+            store_quad(reinterpret_cast<float4 *>(dp + (e + 0) * slot), expand(k, w.x));
+            store_quad(reinterpret_cast<float4 *>(dp + (e + 1) * slot), expand(k, w.y));
+            store_quad(reinterpret_cast<float4 *>(dp + (e + 2) * slot), expand(k, w.z));
+            store_quad(reinterpret_cast<float4 *>(dp + (e + 3) * slot), expand(k, w.w));
         }
     }
     if (rem) {  // trailing quads: lanes split as (env block, quad) with a power-of-two quad pitch
@@ -171,27 +184,27 @@ __device__ __forceinline__ void expand_group(const uint32_t *s_w, const float4 *
         if (per >= 4) {
             const int e0 = (lane / pitch) * per;
             if (r < rem) {
-                const int q = nfull * 32 + r, sh = (q & 7) * 4;
-                const uint32_t lut = lut_of(q);
+                const int q = nfull * 32 + r;
+                const QuadConst k = consts(q);
                 const uint32_t *wq = s_w + (q >> 3) * EPW + e0;
                 float *dp = dst + (size_t)e0 * slot + q * 4;
 #pragma unroll
                 for (int e = 0; e < per; e += 4) {
                     const uint4 w = *reinterpret_cast<const uint4 *>(wq + e);
-                    store_quad(reinterpret_cast<float4 *>(dp + (e + 0) * slot), look(lut, w.x, sh));
-                    store_quad(reinterpret_cast<float4 *>(dp + (e + 1) * slot), look(lut, w.y, sh));
-                    store_quad(reinterpret_cast<float4 *>(dp + (e + 2) * slot), look(lut, w.z, sh));
-                    store_quad(reinterpret_cast<float4 *>(dp + (e + 3) * slot), look(lut, w.w, sh));
+                    store_quad(reinterpret_cast<float4 *>(dp + (e + 0) * slot), expand(k, w.x));
+                    store_quad(reinterpret_cast<float4 *>(dp + (e + 1) * slot), expand(k, w.y));
+                    store_quad(reinterpret_cast<float4 *>(dp + (e + 2) * slot), expand(k, w.z));
+                    store_quad(reinterpret_cast<float4 *>(dp + (e + 3) * slot), expand(k, w.w));
                 }
             }
         } else {  // more env blocks than a lane can fill with a vector load: one env at a time
             const int esub = lane / pitch;
             if (r < rem) {
-                const int q = nfull * 32 + r, sh = (q & 7) * 4;
-                const uint32_t lut = lut_of(q);
+                const int q = nfull * 32 + r;
+                const QuadConst k = consts(q);
                 const uint32_t *wq = s_w + (q >> 3) * EPW;
                 for (int e = esub; e < EPW; e += blocks)
-                    store_quad(reinterpret_cast<float4 *>(dst + (size_t)e * slot + q * 4), look(lut, wq[e], sh));
+                    store_quad(reinterpret_cast<float4 *>(dst + (size_t)e * slot + q * 4), expand(k, wq[e]));
             }
         }
     }
@@ -252,6 +265,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     // One resident wave of CTAs; groups of EPW environments are dealt round-robin (all groups cost about the
     // same, and at the benchmark size every warp owns exactly one group).
     const int num_groups = (p.E + EPW - 1) / EPW;
+    if (p.stagger_ns && ((blockIdx.x / p.stagger_div) & 1)) {
+        // the sequential phase issues no stores and the expansion phase little else: two populations of warps half an
+        // agent-iteration apart keep the memory pipe and the issue slots busy at the same time
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < (unsigned long long)p.stagger_ns);
+    }
     for (int group = blockIdx.x * kWarpsPerCta + warp; group < num_groups; group += gridDim.x * kWarpsPerCta) {
     const int env0 = group * EPW;
     const int nenv = min(EPW, p.E - env0);
@@ -690,9 +713,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
             if (NOISE == MAEXP_NOISE_NONE && !check && !dst_rel && nenv == EPW) {
                 // hot path: the whole group, compile-time slot geometry for the common 3-channel shapes
                 switch (p.slot_floats) {
-                case 152: expand_group<152, EPW>(s_w, s_lut, dst, lane, 152, p.q_str, p.q_tail); break;  // V = 7, C = 3
-                case 80: expand_group<80, EPW>(s_w, s_lut, dst, lane, 80, p.q_str, p.q_tail); break;     // V = 5, C = 3
-                default: expand_group<0, EPW>(s_w, s_lut, dst, lane, p.slot_floats, p.q_str, p.q_tail);
+                case 152: expand_group<152, EPW>(s_w, dst, lane, 152, p.q_str, p.q_tail, p.sub_str, p.sub_tail); break;  // V = 7, C = 3
+                case 80: expand_group<80, EPW>(s_w, dst, lane, 80, p.q_str, p.q_tail, p.sub_str, p.sub_tail); break;     // V = 5, C = 3
+                default: expand_group<0, EPW>(s_w, dst, lane, p.slot_floats, p.q_str, p.q_tail, p.sub_str, p.sub_tail);
                 }
             } else {
             // (1) full chunks: lane owns quad q = c*32 + lane of every env → per-lane constants hoisted,
