@@ -32,7 +32,7 @@ B_ALG = 744.0  # algorithmic bytes per agent-step for cfg5 (588 
 METRIC, UNIT = "agent_steps_per_sec", "agent-steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of env_step_kernel<7,16,0,8> at this
 # workload, from profiles/ (ncu --set full)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 283.8e6  # 8.85 MB read + 274.93 MB written (profiles/r1_env_step_kernel_ncu_full.csv)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 282.45e6  # 8.81 MB read + 273.64 MB written (profiles/r2_env_step_kernel_ncu_full.csv)
 
 
 def workload_config():
