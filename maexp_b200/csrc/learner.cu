@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "../../include/maexp_b200.h"
+#include "tc_mlp.h"
 
 namespace maexp {
 int fail(const std::string &msg);  // env.cu
@@ -1174,6 +1175,8 @@ struct maexp_learner {
     bool use_tc = true;  // tensor-core GEMMs for large inference batches (MAEXP_TC=0 turns them off)
     bool batched_fwd = false;      // all forward passes of an update as slices of one launch (MAEXP_BATCHED_FWD=1; measured slower than one stream each: 263 vs 234 us)
     bool fused_mlp = true;         // one-kernel MLP heads for the update batches (MAEXP_FUSED_MLP=0: GEMM by GEMM)
+    bool tc_mlp = false;           // MAEXP_TC_MLP=1: the MLP heads of >= 128-row batches on tcgen05 (csrc/tc_mlp.cu).  Off by default:
+                                   // measured SLOWER than the SIMT kernel at B = 256 (45 vs 33 us; profiles/r2_tc_mlp_fwd_*.txt)
     bool fused_trunk = true;       // one-kernel conv trunk for every local-view pass (MAEXP_FUSED_TRUNK=0: layer by layer)
     const float *bwd_obs = nullptr;  // observations of the last training pass (conv1's im2col in trunk_backward)
     float *trunk_part = nullptr;      // block partials of trunk_fused_bwd_kernel
@@ -2033,6 +2036,25 @@ bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const flo
         return false;
     auto aligned16 = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
     const long long P = h->P;
+    // update batches of >= 128 rows: both layers on the tensor cores (tcgen05, three TF32 terms per product), the hidden
+    // activation handed from the first accumulator to the second contraction inside the SM (csrc/tc_mlp.cu)
+    if (h->tc_mlp && in.rows >= 128 && H <= 128 && (H & 3) == 0) {
+        bool ok = true;
+        for (int q = 0; q < n && ok; ++q) {
+            TcMlpFwd t = {};
+            t.x = ins[q].x; t.x_row = ins[q].x_row; t.x_g = ins[q].x_g;
+            t.params = params[q]; t.P = P;
+            t.nheads = nheads;
+            for (int k = 0; k < nheads; ++k) {
+                t.w1[k] = hds[k].w1; t.b1[k] = hds[k].b1; t.w2[k] = hds[k].w2; t.b2[k] = hds[k].b2; t.out[k] = hds[k].out;
+                t.hbuf[k] = hbufs[q][k]; t.outp[k] = outs[q][k];
+            }
+            t.rows = ins[q].rows; t.rows_max = ins[q].rows_max; t.din = ins[q].din; t.H = H;
+            if (const char *dbg = getenv("MAEXP_TC_MLP_DBG")) t.dbg = atoi(dbg);
+            ok = tc_mlp_forward(st, h->G, t);
+        }
+        if (ok) return true;
+    }
     MlpHeads a = {};
     a.nheads = nheads;
     for (int k = 0; k < nheads; ++k) {
@@ -2670,6 +2692,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (const char *tc = getenv("MAEXP_TC")) h->use_tc = atoi(tc) != 0;
     if (const char *ft = getenv("MAEXP_FUSED_TRUNK")) h->fused_trunk = atoi(ft) != 0;
     if (const char *fm = getenv("MAEXP_FUSED_MLP")) h->fused_mlp = atoi(fm) != 0;
+    if (const char *tm = getenv("MAEXP_TC_MLP")) h->tc_mlp = atoi(tm) != 0;
     if (const char *bf = getenv("MAEXP_BATCHED_FWD")) h->batched_fwd = atoi(bf) != 0;
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
     h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;
