@@ -355,6 +355,23 @@ int maexp_learner_grads_iqn(maexp_learner *learner, const float *obs, const floa
  * active: optional uint8 [G], 0 skips the agent (agent_tasks "-1", abstract_trainer.py:49-51) */
 int maexp_learner_apply(maexp_learner *learner, float grad_scale, const uint8_t *active, float *grad_norm_out,
                         void *stream);
+/* Data-parallel learner without a separate collective: ONE cooperative kernel does the gradient exchange
+ * over NVLink peer memory and the optimizer step,  sum over ranks -> * 1/world -> clip_grad_norm_ -> RMSprop,  replacing
+ * ncclAllReduce + maexp_learner_apply.  Every rank's gradient buffer must live in peer-mapped ("symmetric") memory:
+ * maexp_learner_bind_grads points the learner's gradient output at such a buffer ([G, num_params] floats, 16-byte aligned,
+ * zero-initialised; NULL re-binds the library's own buffer), maexp_dp_peers lists all ranks' mappings of it, of a
+ * [world, G] float scratch and of a zero-initialised signal pad (>= 8 uint32 per rank).  All ranks must call it once per
+ * update, on devices that can access each other's memory (one process per GPU); the kernel spins on the peers' signals.
+ * Replicas end bit-identical: every reduced value and partial norm is computed by exactly one rank and read by all. */
+typedef struct {
+    int32_t world_size, rank;
+    float *grads[8];
+    float *partials[8];
+    uint32_t *signals[8];
+} maexp_dp_peers;
+int maexp_learner_bind_grads(maexp_learner *learner, float *external_grads);
+int maexp_learner_apply_data_parallel(maexp_learner *learner, const maexp_dp_peers *peers, const uint8_t *active,
+                                      float *grad_norm_out, void *stream);
 /* grads + apply on one GPU */
 int maexp_learner_update(maexp_learner *learner, const float *obs, const float *next_obs, const int32_t *actions,
                          const float *rewards, const uint8_t *dones, float *loss_out, void *stream);

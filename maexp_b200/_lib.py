@@ -69,6 +69,11 @@ class LearnerCfg(C.Structure):
                                           "team_agents")]
 
 
+class DpPeers(C.Structure):
+    _fields_ = [("world_size", C.c_int32), ("rank", C.c_int32), ("grads", C.c_void_p * 8), ("partials", C.c_void_p * 8),
+                ("signals", C.c_void_p * 8)]
+
+
 LEARNER_KINDS = {"dqn_conv_mlp": 0, "c51": 1, "qr": 2, "dqn_mlp": 3, "iqn": 4, "da3": 5, "da6": 6}
 BUF_ONLINE, BUF_TARGET, BUF_GRADS, BUF_SQUARE_AVG, BUF_SUPPORT, BUF_EXP_AVG, BUF_ADAM_STEPS = range(7)
 
@@ -115,6 +120,8 @@ SYMBOLS = {
     "maexp_learner_q_values_iqn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "maexp_learner_grads_iqn": (C.c_int, [C.c_void_p] + [C.c_void_p] * 9 + [C.c_void_p]),
     "maexp_learner_apply": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "maexp_learner_bind_grads": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "maexp_learner_apply_data_parallel": (C.c_int, [C.c_void_p, C.POINTER(DpPeers), C.c_void_p, C.c_void_p, C.c_void_p]),
     "maexp_learner_update": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
     "maexp_heatmap_observation_add": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]),

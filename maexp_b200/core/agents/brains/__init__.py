@@ -358,12 +358,21 @@ class GraphedUpdate:
 
     dist: torch.distributed module (or None for a single GPU); the replay sampler refills `batch` in place before step()."""
 
-    def __init__(self, group, batch, active=None, dist=None, process_group=None):
+    def __init__(self, group, batch, active=None, dist=None, process_group=None, fused_collective=True):
         self.group, self.batch, self.active, self.dist, self.pg = group, batch, active, dist, process_group
         self.world = dist.get_world_size(process_group) if dist is not None else 1
-        self.grads_view = group.params(_lib.BUF_GRADS)
         self.g_grads = self.g_apply = None
         self.calls = 0
+        # data parallel on NVLink peers: the gradient buffer moves into symmetric memory and ONE cooperative kernel does the
+        # exchange and the optimizer step (maexp_learner_apply_data_parallel); otherwise NCCL all-reduce + apply
+        self.peers = None
+        if dist is not None and self.world > 1 and fused_collective and group.config.opt.name == "rmsprop" and \
+                dist.get_backend(process_group) == "nccl":
+            try:
+                self.peers = self._symmetric_gradients()
+            except Exception as exc:  # no peer access / symmetric memory: keep the NCCL path
+                logger.warning(f"fused data-parallel apply unavailable ({exc}); using NCCL all-reduce")
+        self.grads_view = group.params(_lib.BUF_GRADS)
         self.draw_taus = False
         if group.kind == "iqn" and not all(k in batch for k in ("taus", "tau_dashes", "tau_sel")):
             # the fractions live in fixed buffers refilled before every replay (a captured torch.rand would replay one
@@ -379,9 +388,44 @@ class GraphedUpdate:
             if dist is not None:  # every rank samples its own shard of the global batch: its own fractions, too
                 self.tau_seed = (self.tau_seed + 0x9E3779B9 * dist.get_rank(process_group)) & 0xFFFFFFFF
 
+    def _symmetric_gradients(self):
+        import torch.distributed._symmetric_memory as symm
+        g, dist = self.group, self.dist
+        pg = self.pg if self.pg is not None else dist.group.WORLD
+        name = pg.group_name
+        if hasattr(symm, "enable_symm_mem_for_group"):
+            try:
+                symm.enable_symm_mem_for_group(name)
+            except Exception:
+                pass
+        n, W = g.G * g.P, self.world
+        n_part = (W * g.G + 3) // 4 * 4
+        self.symm_buf = symm.empty(n + n_part + 64, dtype=torch.float32, device=g.device)
+        self.symm_buf.zero_()
+        self.symm_hdl = symm.rendezvous(self.symm_buf, name)
+        torch.cuda.synchronize(g.device)
+        dist.barrier(group=self.pg)  # every rank's buffer is zero before the first signal can arrive
+        peers = _lib.DpPeers()
+        peers.world_size, peers.rank = W, dist.get_rank(self.pg)
+        for q, base in enumerate(self.symm_hdl.buffer_ptrs):
+            peers.grads[q], peers.partials[q], peers.signals[q] = base, base + 4 * n, base + 4 * (n + n_part)
+        assert peers.grads[peers.rank] == self.symm_buf.data_ptr()
+        _lib.check(g.lib.maexp_learner_bind_grads(g.h, C.c_void_p(self.symm_buf.data_ptr())))
+        return peers
+
     def _reduce(self):
         if self.dist is not None:
             self.dist.all_reduce(self.grads_view, op=self.dist.ReduceOp.SUM, group=self.pg)
+
+    def _apply(self):
+        """all ranks: exchange + optimizer step"""
+        g = self.group
+        if self.peers is not None:
+            a = None if self.active is None else C.c_void_p(self.active.data_ptr())
+            _lib.check(g.lib.maexp_learner_apply_data_parallel(g.h, C.byref(self.peers), a, C.c_void_p(g.grad_norm.data_ptr()),
+                                                               g._stream()))
+            return True
+        return False
 
     def step(self):
         self.calls += 1
@@ -390,19 +434,23 @@ class GraphedUpdate:
                                                          self.tau_seed, self.calls & 0xFFFFFFFF, self.group._stream()))
         if self.calls == 1:
             loss = self.group.grads(self.batch)
-            self._reduce()
-            self.group.apply(1.0 / self.world, self.active)
+            if not self._apply():
+                self._reduce()
+                self.group.apply(1.0 / self.world, self.active)
             return loss
         if self.g_grads is None:
             torch.cuda.synchronize(self.group.device)
-            self.g_grads, self.g_apply = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            self.g_grads = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_grads):
                 self.group.grads(self.batch)
-            with torch.cuda.graph(self.g_apply):
-                self.group.apply(1.0 / self.world, self.active)
+            if self.peers is None:
+                self.g_apply = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.g_apply):
+                    self.group.apply(1.0 / self.world, self.active)
         self.g_grads.replay()
-        self._reduce()
-        self.g_apply.replay()
+        if not self._apply():  # fused: one cooperative launch (exchange over NVLink + clip + RMSprop)
+            self._reduce()
+            self.g_apply.replay()
         return self.group.loss
 
 

@@ -15,6 +15,7 @@
 // rules out TF32 tensor-core math at these sizes; the networks are 42k-140k parameters and the
 // update is launch-latency bound, so every layer is ONE grouped launch for
 // all agents and the whole update is CUDA-graph capturable (no host sync, no allocation).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -1149,6 +1150,168 @@ __global__ void canvas_extra_kernel(float *canvas, long long rows, int base, int
     }
 }
 
+// ---------------------------------------------------------------------------------- data-parallel learner: fused collective
+// One cooperative kernel per update replaces  NCCL all-reduce(sum) -> grads *= 1/world -> clip_grad_norm_ -> RMSprop  of the
+// data-parallel learner.  Every rank's flat gradient buffer [G*P] lives in peer-mapped (symmetric) memory, so
+// the exchange is plain 128-bit loads / stores over NVLink inside the kernel:
+//   phase 1  reduce-scatter + all-gather: rank r sums slice r of all ranks' buffers in rank order, scales by 1/world and
+//            writes the reduced slice back into EVERY rank's buffer; block partials of the per-agent sum of squares
+//   phase 2  (after a grid sync) block 0 adds the block partials in a fixed order and publishes this rank's per-agent
+//            partial norms to every rank; cross-GPU barrier on the signal pads
+//   phase 3  every rank: norm_g = sqrt(sum of the world partials in rank order), clip coefficient, RMSprop on all G*P
+//            parameters from the reduced gradients now sitting in its own buffer.
+// All ranks apply bit-identical gradients and norms (each value is computed by exactly one rank), so replicas stay equal.
+struct DpPeers {
+    float *grads[8];        // peer-mapped gradient buffers, [G*P] floats each, index = rank
+    float *partials[8];     // peer-mapped [world][G] partial sums of squares, index = rank
+    uint32_t *signals[8];   // peer-mapped signal pads (>= 8 words used), index = rank
+    int world, rank;
+};
+
+__device__ __forceinline__ void dp_barrier(const DpPeers &pe, uint32_t epoch) {
+    // called by block 0 after a grid sync: thread t < world signals rank t and waits for rank t's signal
+    if (threadIdx.x < pe.world) {
+        __threadfence_system();
+        const int t = threadIdx.x;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pe.signals[t] + pe.rank), "r"(epoch) : "memory");
+        uint32_t seen = 0;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(pe.signals[pe.rank] + t) : "memory");
+            if (clock64() - t0 > (1ll << 33)) __trap();  // a rank that never arrives must not wedge the GPU (~4 s)
+        } while ((int32_t)(seen - epoch) < 0);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) dp_reduce_apply_kernel(const DpPeers pe, float *params, float *sq, long long P, int G,
+                                                             uint32_t *epoch_counter, float *block_part, float max_norm, float lr,
+                                                             float alpha, float one_minus_alpha, float eps, const uint8_t *active,
+                                                             float *norm_out) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ float red[256];
+    __shared__ uint32_t s_epoch;
+    const long long N = (long long)G * P, N4 = N >> 2;  // P is a multiple of 4 floats
+    const int W = pe.world, r = pe.rank;
+    const float inv_world = __fdiv_rn(1.0f, (float)W);
+    // every rank's gradients must be complete before anyone reads them (this rank's are, by stream order)
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) s_epoch = *epoch_counter;  // advanced at the end; two barriers per call
+        __syncthreads();
+        dp_barrier(pe, s_epoch + 1);
+    }
+    grid.sync();
+
+    // ---- phase 1: my slice, reduced in rank order and broadcast
+    const long long per = (N4 + W - 1) / W, lo = per * r, hi = min(N4, lo + per);
+    float acc[8];  // sum of squares per agent touched by this thread (a slice spans at most a few agents)
+    const int g_first = (int)((lo * 4) / P);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+    {
+        const long long stride1 = (long long)gridDim.x * blockDim.x;
+        auto reduce_one = [&](long long i, float4 (&u)[8]) {
+            float4 v = u[0];
+            for (int q = 1; q < W; ++q) {
+                v.x = __fadd_rn(v.x, u[q].x); v.y = __fadd_rn(v.y, u[q].y); v.z = __fadd_rn(v.z, u[q].z); v.w = __fadd_rn(v.w, u[q].w);
+            }
+            v.x = __fmul_rn(v.x, inv_world); v.y = __fmul_rn(v.y, inv_world); v.z = __fmul_rn(v.z, inv_world); v.w = __fmul_rn(v.w, inv_world);
+            for (int q = 0; q < W; ++q) *reinterpret_cast<float4 *>(pe.grads[q] + i * 4) = v;
+            const int k = (int)((i * 4) / P) - g_first;  // a float4 never straddles agents (P % 4 == 0)
+            const float ss = __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fadd_rn(__fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w)));
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j == k) acc[j] = __fadd_rn(acc[j], ss);
+        };
+        for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += 2 * stride1) {
+            const long long i2 = i + stride1;
+            float4 ua[8], ub[8];  // all peer loads of two elements in flight before the first add
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < W) ua[q] = *reinterpret_cast<const float4 *>(pe.grads[q] + i * 4);
+            if (i2 < hi) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (q < W) ub[q] = *reinterpret_cast<const float4 *>(pe.grads[q] + i2 * 4);
+            }
+            reduce_one(i, ua);
+            if (i2 < hi) reduce_one(i2, ub);
+        }
+    }
+    // block partials per agent slot (fixed tree order), then block 0 adds the blocks in order: deterministic
+    for (int k = 0; k < 8; ++k) {
+        red[threadIdx.x] = acc[k];
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] = __fadd_rn(red[threadIdx.x], red[threadIdx.x + o]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) block_part[(size_t)blockIdx.x * 8 + k] = red[0];
+        __syncthreads();
+    }
+    __threadfence_system();  // the reduced slice must be visible on every GPU before the barrier below
+    grid.sync();
+    if (blockIdx.x == 0) {
+        // warp k adds agent slot k over the blocks: lane-strided partial sums, then a fixed shuffle tree (deterministic)
+        const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        float part = 0.0f;
+        for (unsigned b = lane; b < gridDim.x; b += 32) part = __fadd_rn(part, block_part[(size_t)b * 8 + k]);
+        for (int o = 16; o > 0; o >>= 1) part = __fadd_rn(part, __shfl_down_sync(0xFFFFFFFFu, part, o));
+        if (lane == 0) red[k] = part;
+        __syncthreads();
+        if (threadIdx.x < G) {
+            const int g = threadIdx.x, slot = g - g_first;
+            const float total = (slot >= 0 && slot < 8) ? red[slot] : 0.0f;  // 0 for agents outside my slice
+            for (int q = 0; q < W; ++q) pe.partials[q][(size_t)r * G + g] = total;
+        }
+        __syncthreads();
+        dp_barrier(pe, s_epoch + 2);
+        if (threadIdx.x == 0) *epoch_counter = s_epoch + 2;
+    }
+    grid.sync();
+
+    // ---- phase 3: clip + RMSprop on every parameter (clip_grad_norm_ after the reduce, as a single GPU on the global batch)
+    __shared__ float s_coef[256];
+    const float *gr = pe.grads[r];
+    const float *part = pe.partials[r];
+    if (threadIdx.x < G) {  // per-agent clip coefficient, once per block: world partials added in rank order
+        const int g = threadIdx.x;
+        float total = 0.0f;
+        for (int q = 0; q < W; ++q) total = __fadd_rn(total, part[(size_t)q * G + g]);
+        const float norm = sqrtf(total);
+        s_coef[g] = (active && !active[g]) ? -1.0f : fminf(__fdiv_rn(max_norm, __fadd_rn(norm, 1e-6f)), 1.0f);
+        if (norm_out && blockIdx.x == 0) norm_out[g] = norm;
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    auto update = [&](long long i, const float4 &g4, const float4 &s4, const float4 &p4) {
+        const float coef = s_coef[(int)((i * 4) / P)];
+        if (coef < 0.0f) return;  // inactive agent (agent_tasks "-1")
+        const float gi[4] = {__fmul_rn(g4.x, coef), __fmul_rn(g4.y, coef), __fmul_rn(g4.z, coef), __fmul_rn(g4.w, coef)};
+        float sv[4] = {s4.x, s4.y, s4.z, s4.w}, pv[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sv[j] = __fadd_rn(__fmul_rn(sv[j], alpha), __fmul_rn(__fmul_rn(one_minus_alpha, gi[j]), gi[j]));
+            pv[j] = __fadd_rn(pv[j], -__fmul_rn(lr, __fdiv_rn(gi[j], __fadd_rn(sqrtf(sv[j]), eps))));
+        }
+        *reinterpret_cast<float4 *>(sq + i * 4) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+        *reinterpret_cast<float4 *>(params + i * 4) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    };
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N4; i += 2 * stride) {  // two float4 in flight
+        const long long i2 = i + stride;
+        const float4 ga = *reinterpret_cast<const float4 *>(gr + i * 4), sa = *reinterpret_cast<const float4 *>(sq + i * 4),
+                     pa = *reinterpret_cast<const float4 *>(params + i * 4);
+        float4 gb = ga, sb = sa, pb = pa;
+        if (i2 < N4) {
+            gb = *reinterpret_cast<const float4 *>(gr + i2 * 4);
+            sb = *reinterpret_cast<const float4 *>(sq + i2 * 4);
+            pb = *reinterpret_cast<const float4 *>(params + i2 * 4);
+        }
+        update(i, ga, sa, pa);
+        if (i2 < N4) update(i2, gb, sb, pb);
+    }
+}
+
 int decode_relative_launch(const float *obs, const int8_t *positions, float *canvas, long long rows, int channels, int visible_range,
                            int size_x, int size_y, int obs_stride, int only_area_plus_one, long long canvas_stride,
                            const int8_t *los, cudaStream_t st);  // agents.cu
@@ -1242,6 +1405,10 @@ struct maexp_learner {
     // state batch (h->pos), set 1 to the new-state batch (h->next_pos); bound by maexp_learner_bind_canvas_inputs
     int ex_o = 0, ex_a = 0, ex_d = 0, Cx = 0, Tn_obj = 0, Nteam = 0;
     struct CanvasIn { const uint32_t *obj = nullptr; const int8_t *agents = nullptr; const uint32_t *dest = nullptr; } cin[2];
+    float *own_grads = nullptr;       // the library's gradient buffer (h->grads may be re-bound to symmetric memory)
+    uint32_t *dp_epoch = nullptr;     // barrier epoch of the fused data-parallel apply
+    float *dp_block_part = nullptr;   // its block partials
+    int dp_blocks = 0;
     int8_t *los = nullptr;  // [X,Y,V,V] line-of-sight table (maexp_learner_set_los): the merged models' noise-free area channel
     float *canvas[3] = {nullptr, nullptr, nullptr}, *feat[3] = {nullptr, nullptr, nullptr}, *d_feat = nullptr;
     float *rel_flat[3] = {nullptr, nullptr, nullptr}, *rse_h[3] = {nullptr, nullptr, nullptr}, *rse_out[3] = {nullptr, nullptr, nullptr};
@@ -3489,6 +3656,50 @@ int maexp_clip_rmsprop_step(float *params, const float *grads, float *square_avg
     clip_rmsprop_kernel<<<dim3(64, G), 256, 0, st>>>(params, grads, square_avg, partial, nparts, count, grad_scale, max_norm,
                                                      learning_rate, alpha, 1.0f - alpha, eps, active, grad_norm_out);
     MAEXP_CUDA_L(cudaGetLastError());
+    return 0;
+}
+
+int maexp_learner_bind_grads(maexp_learner *h, float *external) {
+    if (!h) return fail("maexp_learner_bind_grads: null handle");
+    if (!h->own_grads) h->own_grads = h->grads;
+    if (external && (reinterpret_cast<uintptr_t>(external) & 15)) return fail("maexp_learner_bind_grads: the buffer must be 16-byte aligned");
+    h->grads = external ? external : h->own_grads;
+    return 0;
+}
+
+int maexp_learner_apply_data_parallel(maexp_learner *h, const maexp_dp_peers *peers, const uint8_t *active, float *grad_norm_out,
+                                      void *stream) {
+    if (!h || !peers) return fail("maexp_learner_apply_data_parallel: null argument");
+    if (h->cfg.optimizer != 0) return fail("maexp_learner_apply_data_parallel: implemented for RMSprop (use the NCCL path for Adam)");
+    if (peers->world_size < 1 || peers->world_size > 8 || peers->rank < 0 || peers->rank >= peers->world_size)
+        return fail("maexp_learner_apply_data_parallel: world size must be 1..8");
+    if (h->G > 256) return fail("maexp_learner_apply_data_parallel: at most 256 agents");
+    const long long N4 = (long long)h->G * h->P / 4, per = (N4 + peers->world_size - 1) / peers->world_size;
+    if ((per * 4 + h->P - 1) / h->P + 1 > 8) return fail("maexp_learner_apply_data_parallel: a rank's slice may span at most 8 agents");
+    DpPeers pe = {};
+    pe.world = peers->world_size; pe.rank = peers->rank;
+    for (int q = 0; q < pe.world; ++q) {
+        if (!peers->grads[q] || !peers->partials[q] || !peers->signals[q]) return fail("maexp_learner_apply_data_parallel: null peer pointer");
+        pe.grads[q] = peers->grads[q]; pe.partials[q] = peers->partials[q]; pe.signals[q] = peers->signals[q];
+    }
+    if (pe.grads[pe.rank] != h->grads) return fail("maexp_learner_apply_data_parallel: bind this rank's gradient buffer first (maexp_learner_bind_grads)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!h->dp_epoch) {
+        int dev = 0, sms = 148, per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_reduce_apply_kernel, 256, 0);
+        h->dp_blocks = sms * (per_sm < 2 ? per_sm : 2);  // cooperative: every block resident
+        if (h->dp_blocks < 1) return fail("maexp_learner_apply_data_parallel: no resident block");
+        if (lalloc(h, &h->dp_epoch, 1) || lalloc(h, &h->dp_block_part, (size_t)h->dp_blocks * 8)) return -1;
+    }
+    float *params = h->online, *sq = h->sq, *bp = h->dp_block_part, *norm_out = grad_norm_out;
+    long long P = h->P;
+    int G = h->G;
+    uint32_t *epoch = h->dp_epoch;
+    float max_norm = h->cfg.max_norm, lr = h->cfg.learning_rate, alpha = h->cfg.alpha, oma = h->cfg.one_minus_alpha, eps = h->cfg.eps;
+    void *args[] = {&pe, &params, &sq, &P, &G, &epoch, &bp, &max_norm, &lr, &alpha, &oma, &eps, (void *)&active, &norm_out};
+    MAEXP_CUDA_L(cudaLaunchCooperativeKernel((const void *)dp_reduce_apply_kernel, dim3(h->dp_blocks), dim3(256), args, 0, st));
     return 0;
 }
 

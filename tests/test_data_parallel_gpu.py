@@ -132,3 +132,18 @@ def test_fill_uniform_is_a_unit_uniform_stream():
     hist = torch.histc(a, bins=64, min=0, max=1)
     assert float((hist - n / 64).abs().max()) < 6 * (n / 64) ** 0.5
     assert abs(float(torch.corrcoef(torch.stack([a[:-1], a[1:]]))[0, 1])) < 5e-3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs with peer access")
+def test_fused_nvlink_apply_equals_nccl_path_on_two_gpus():
+    """maexp_learner_apply_data_parallel (one cooperative kernel: reduce-scatter / all-gather over NVLink peer memory + clip +
+    RMSprop) against NCCL all-reduce + maexp_learner_apply on twin learners, one process per GPU: identical parameters on every
+    rank and between the two paths (tools/dp_fused_check.py asserts it and prints the timings)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(_free_port()), os.path.join(root, "tools", "dp_fused_check.py")],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, B="64"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"replica_spread_fused": 0.0' in r.stdout
