@@ -368,6 +368,8 @@ typedef struct {
     float *grads[8];
     float *partials[8];
     uint32_t *signals[8];
+    float *multicast_grads;   /* optional NVLS multicast mapping of the same gradient buffers (NVSwitch): the reduce becomes one
+                                 multimem.ld_reduce and the broadcast one multimem.st per 16 bytes; NULL: peer loads / stores */
 } maexp_dp_peers;
 int maexp_learner_bind_grads(maexp_learner *learner, float *external_grads);
 int maexp_learner_apply_data_parallel(maexp_learner *learner, const maexp_dp_peers *peers, const uint8_t *active,

@@ -71,7 +71,7 @@ class LearnerCfg(C.Structure):
 
 class DpPeers(C.Structure):
     _fields_ = [("world_size", C.c_int32), ("rank", C.c_int32), ("grads", C.c_void_p * 8), ("partials", C.c_void_p * 8),
-                ("signals", C.c_void_p * 8)]
+                ("signals", C.c_void_p * 8), ("multicast_grads", C.c_void_p)]
 
 
 LEARNER_KINDS = {"dqn_conv_mlp": 0, "c51": 1, "qr": 2, "dqn_mlp": 3, "iqn": 4, "da3": 5, "da6": 6}

@@ -1165,8 +1165,21 @@ struct DpPeers {
     float *grads[8];        // peer-mapped gradient buffers, [G*P] floats each, index = rank
     float *partials[8];     // peer-mapped [world][G] partial sums of squares, index = rank
     uint32_t *signals[8];   // peer-mapped signal pads (>= 8 words used), index = rank
+    float *mc_grads;        // NVLS multicast mapping of the gradient buffers (nullptr: peer loads / stores)
     int world, rank;
 };
+
+// in-switch reduction / broadcast over the NVLS multicast mapping (one request instead of `world` peer accesses)
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float *mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st(float *mc, const float4 &v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
 
 __device__ __forceinline__ void dp_barrier(const DpPeers &pe, uint32_t epoch) {
     // called by block 0 after a grid sync: thread t < world signals rank t and waits for rank t's signal
@@ -1223,6 +1236,25 @@ __global__ void __launch_bounds__(256) dp_reduce_apply_kernel(const DpPeers pe, 
             for (int j = 0; j < 8; ++j)
                 if (j == k) acc[j] = __fadd_rn(acc[j], ss);
         };
+        auto finish_one = [&](long long i, float4 v) {  // NVLS: v is already the sum over ranks
+            v.x = __fmul_rn(v.x, inv_world); v.y = __fmul_rn(v.y, inv_world); v.z = __fmul_rn(v.z, inv_world); v.w = __fmul_rn(v.w, inv_world);
+            multimem_st(pe.mc_grads + i * 4, v);
+            const int k = (int)((i * 4) / P) - g_first;
+            const float ss = __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fadd_rn(__fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w)));
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j == k) acc[j] = __fadd_rn(acc[j], ss);
+        };
+        if (pe.mc_grads) {
+            for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += 2 * stride1) {
+                const long long i2 = i + stride1;
+                const float4 va = multimem_ld_reduce_add(pe.mc_grads + i * 4);
+                float4 vb = va;
+                if (i2 < hi) vb = multimem_ld_reduce_add(pe.mc_grads + i2 * 4);
+                finish_one(i, va);
+                if (i2 < hi) finish_one(i2, vb);
+            }
+        } else
         for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += 2 * stride1) {
             const long long i2 = i + stride1;
             float4 ua[8], ub[8];  // all peer loads of two elements in flight before the first add
@@ -3682,6 +3714,7 @@ int maexp_learner_apply_data_parallel(maexp_learner *h, const maexp_dp_peers *pe
         if (!peers->grads[q] || !peers->partials[q] || !peers->signals[q]) return fail("maexp_learner_apply_data_parallel: null peer pointer");
         pe.grads[q] = peers->grads[q]; pe.partials[q] = peers->partials[q]; pe.signals[q] = peers->signals[q];
     }
+    pe.mc_grads = peers->multicast_grads;
     if (pe.grads[pe.rank] != h->grads) return fail("maexp_learner_apply_data_parallel: bind this rank's gradient buffer first (maexp_learner_bind_grads)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!h->dp_epoch) {

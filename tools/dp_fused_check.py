@@ -78,10 +78,12 @@ t_apply_own = timed(Part(ub.g_apply.replay))
 if rank == 0:
     print(json.dumps({"world": world, "batch_per_gpu": B, "fused_vs_nccl_max_abs_param_diff": diff, "params_moved_by": moved,
                       "grad_norm_rel_diff": norm_diff, "replica_spread_fused": spread_a, "replica_spread_nccl": spread_b,
-                      "us_per_update_fused": t_fused, "us_per_update_nccl": t_nccl,
+                      "multimem": bool(ua.peers.multicast_grads), "us_per_update_fused": t_fused, "us_per_update_nccl": t_nccl,
                       "us_grads_graph_symmetric_buffer": t_grads_symm, "us_grads_graph_own_buffer": t_grads_own,
                       "us_fused_exchange_apply_kernel": t_apply_fused, "us_nccl_all_reduce": t_allreduce,
                       "us_clip_rmsprop_graph": t_apply_own}))
-    assert spread_a == 0.0 and diff <= 2e-6 and moved > 1e-3, "fused data-parallel apply disagrees with the NCCL path"
+    # the two paths add the ranks' gradients in different orders; RMSprop's first steps amplify last-bit differences of
+    # near-zero gradients (see tests/test_learner_gpu.py), so the parameters are compared loosely and the norms tightly
+    assert spread_a == 0.0 and norm_diff <= 1e-4 and diff <= 5e-3 and moved > 1e-3, "fused data-parallel apply disagrees with the NCCL path"
 dist.barrier()
 dist.destroy_process_group()
