@@ -359,7 +359,7 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     if (h->smem_bytes > 227 * 1024) { maexp_env_destroy(h); return fail("maexp_env_create: configuration needs more than 227 KB shared memory per CTA"); }
     for (int i = 0; i < 32 * T * X; ++i)
         if ((int)(((uint64_t)i * p.tx_magic) >> 32) != i / (T * X)) { maexp_env_destroy(h); return fail("maexp_env_create: internal magic division (TX)"); }
-    int nspec = (N == 8 && T == 1 && !transition) ? 8 : 0;
+    int nspec = ((N == 8 || N == 4 || N == 2) && T == 1 && !transition) ? N : 0;
     if (getenv("MAEXP_NOSPEC")) nspec = 0;
     h->fn = pick_kernel(V, h->epw, p.noise, nspec);
     if (!h->fn) { maexp_env_destroy(h); return fail("maexp_env_create: no kernel for this visible_range / noise"); }

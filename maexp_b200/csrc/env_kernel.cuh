@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
     using WinT = typename Win<V>::T;
     extern __shared__ __align__(1024) uint32_t smem[];
 
-    // NSPEC = 8: agents and object types are compile-time constants (N = 8, T = 1, no transition frames), so the
-    // per-agent loops unroll; NSPEC = 0: everything from the parameter block
+    // NSPEC = 8 / 4 / 2: agents and object types are compile-time constants (N = NSPEC, T = 1, no transition frames), so
+    // the per-agent loops unroll; NSPEC = 0: everything from the parameter block
     const int N = NSPEC ? NSPEC : p.N, T = NSPEC ? 1 : p.T, X = p.X, Y = p.Y, P = NSPEC ? 0 : p.P, TX = T * X;
     // Shared-memory bit rows are padded: R zero rows on both sides of x and every row shifted left by
     // R bits, so window crops need no bounds checks and no signed shifts.
@@ -890,6 +890,8 @@ KernelFn pick_noise(int noise, int nspec) {
     switch (noise) {
     case MAEXP_NOISE_NONE:
         if (nspec == 8) return env_step_kernel<V, EPW, MAEXP_NOISE_NONE, 8>;
+        if (nspec == 4) return env_step_kernel<V, EPW, MAEXP_NOISE_NONE, 4>;
+        if (nspec == 2) return env_step_kernel<V, EPW, MAEXP_NOISE_NONE, 2>;
         return env_step_kernel<V, EPW, MAEXP_NOISE_NONE, 0>;
     case MAEXP_NOISE_FLIP: return env_step_kernel<V, EPW, MAEXP_NOISE_FLIP, 0>;
     case MAEXP_NOISE_DIST: return env_step_kernel<V, EPW, MAEXP_NOISE_DIST, 0>;

@@ -431,10 +431,14 @@ __device__ __forceinline__ float dueling(const float *v, const float *adv, int A
     return __fadd_rn(v[j], __fadd_rn(adv[a * Z + j], -mean));
 }
 
-// C51 (categorical_dqn_brain.py:51-87)
-__global__ void c51_loss_kernel(const DistArgs p, float *m_scratch) {
-    const int g = blockIdx.y, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// C51 (categorical_dqn_brain.py:51-87).  One warp per (agent, sample); a lane owns atoms lane, lane + 32, ...  The dueling
+// rows of a network are formed once per atom (the same operation order as dueling()), the projection scatters into a
+// per-warp shared-memory row, and every head output is read exactly once.
+__global__ void __launch_bounds__(256) c51_loss_kernel(const DistArgs p, float *m_scratch) {
+    __shared__ float s_m[8][32 * kMaxAtomsPerLane];
+    const int g = blockIdx.y, wid = threadIdx.x >> 5, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= p.B) return;
+    (void)m_scratch;
     const int A = p.A, Z = p.Z;
     const size_t i = (size_t)g * p.B + warp;
     const bool duel = p.v_s != nullptr;
@@ -442,25 +446,52 @@ __global__ void c51_loss_kernel(const DistArgs p, float *m_scratch) {
     const float *vn = duel ? p.v_n + i * Z : nullptr, *an = p.a_n + i * A * Z;
     const float *vt = duel ? p.v_t + i * Z : nullptr, *at = p.a_t + i * A * Z;
     const int a_taken = p.act[i];
+    // all action rows of one network for this lane's atoms: v + (adv[a] - mean_a adv), sum over actions in index order
+    auto rows = [&](const float *v, const float *adv, float (&d)[kMaxActions][kMaxAtomsPerLane]) {
+#pragma unroll
+        for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+            const int jj = lane + 32 * t;
+            if (jj >= Z) continue;
+            float ad[kMaxActions], sum = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kMaxActions; ++k)
+                if (k < A) { ad[k] = adv[k * Z + jj]; sum = __fadd_rn(sum, ad[k]); }
+            if (!v) {
+#pragma unroll
+                for (int k = 0; k < kMaxActions; ++k)
+                    if (k < A) d[k][t] = ad[k];
+            } else {
+                const float mean = __fdiv_rn(sum, (float)A), vj = v[jj];
+#pragma unroll
+                for (int k = 0; k < kMaxActions; ++k)
+                    if (k < A) d[k][t] = __fadd_rn(vj, __fadd_rn(ad[k], -mean));
+            }
+        }
+    };
+    float sup[kMaxAtomsPerLane];
+#pragma unroll
+    for (int t = 0; t < kMaxAtomsPerLane; ++t) sup[t] = (lane + 32 * t < Z) ? p.support[lane + 32 * t] : 0.0f;
 
     // best action of the ONLINE net on s': argmax_a sum_j softmax(out[a])_j z_j, first maximum wins
+    float dn[kMaxActions][kMaxAtomsPerLane];
+    rows(vn, an, dn);
     int best = 0;
     float best_q = 0.0f;
-    for (int a = 0; a < A; ++a) {
-        float l[kMaxAtomsPerLane], mx = -INFINITY;
-        for (int t = 0; t < kMaxAtomsPerLane; ++t) {
-            const int j = lane + 32 * t;
-            l[t] = j < Z ? dueling(vn, an, A, Z, a, j) : -INFINITY;
-            mx = fmaxf(mx, l[t]);
-        }
+#pragma unroll
+    for (int a = 0; a < kMaxActions; ++a) {
+        if (a >= A) break;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < kMaxAtomsPerLane; ++t)
+            if (lane + 32 * t < Z) mx = fmaxf(mx, dn[a][t]);
         mx = warp_max(mx);
         float se = 0.0f, sq = 0.0f;
+#pragma unroll
         for (int t = 0; t < kMaxAtomsPerLane; ++t) {
-            const int j = lane + 32 * t;
-            if (j < Z) {
-                const float e = expf(__fadd_rn(l[t], -mx));
+            if (lane + 32 * t < Z) {
+                const float e = expf(__fadd_rn(dn[a][t], -mx));
                 se = __fadd_rn(se, e);
-                sq = __fadd_rn(sq, __fmul_rn(e, p.support[j]));
+                sq = __fadd_rn(sq, __fmul_rn(e, sup[t]));
             }
         }
         se = warp_sum(se);
@@ -468,31 +499,33 @@ __global__ void c51_loss_kernel(const DistArgs p, float *m_scratch) {
         const float qv = __fdiv_rn(sq, se);
         if (a == 0 || qv > best_q) { best_q = qv; best = a; }
     }
-    // p' = softmax(target(s')[best])
+    // p' = softmax(target(s')[best]): only the best row of the target net is formed
     float pt[kMaxAtomsPerLane], mx = -INFINITY;
+#pragma unroll
     for (int t = 0; t < kMaxAtomsPerLane; ++t) {
-        const int j = lane + 32 * t;
-        pt[t] = j < Z ? dueling(vt, at, A, Z, best, j) : -INFINITY;
+        const int jj = lane + 32 * t;
+        pt[t] = jj < Z ? dueling(vt, at, A, Z, best, jj) : -INFINITY;
         mx = fmaxf(mx, pt[t]);
     }
     mx = warp_max(mx);
     float se = 0.0f;
+#pragma unroll
     for (int t = 0; t < kMaxAtomsPerLane; ++t) {
-        const int j = lane + 32 * t;
-        pt[t] = j < Z ? expf(__fadd_rn(pt[t], -mx)) : 0.0f;
+        pt[t] = (lane + 32 * t < Z) ? expf(__fadd_rn(pt[t], -mx)) : 0.0f;
         se = __fadd_rn(se, pt[t]);
     }
     se = warp_sum(se);
-    // projection onto the support: two scatter-adds per atom (index_add_, :80-81) into per-sample scratch
-    float *m = m_scratch + i * Z;
-    for (int j = lane; j < Z; j += 32) m[j] = 0.0f;
+    // projection onto the support: two scatter-adds per atom (index_add_, :80-81) into this warp's shared-memory row
+    float *m = s_m[wid];
+    for (int jj = lane; jj < Z; jj += 32) m[jj] = 0.0f;
     __syncwarp();
     const float r = p.rew[i];
+#pragma unroll
     for (int t = 0; t < kMaxAtomsPerLane; ++t) {
-        const int j = lane + 32 * t;
-        if (j >= Z) continue;
+        const int jj = lane + 32 * t;
+        if (jj >= Z) continue;
         const float prob = __fdiv_rn(pt[t], se);
-        float tz = __fadd_rn(r, __fmul_rn(p.gamma, p.support[j]));
+        float tz = __fadd_rn(r, __fmul_rn(p.gamma, sup[t]));
         tz = fminf(fmaxf(tz, p.v_min), p.v_max);
         const float bb = __fdiv_rn(__fadd_rn(tz, -p.v_min), p.delta_z);
         int lo = (int)floorf(bb), up = (int)ceilf(bb);
@@ -505,40 +538,42 @@ __global__ void c51_loss_kernel(const DistArgs p, float *m_scratch) {
     // log_softmax(online(s)[a_taken]), loss and its gradient
     float l[kMaxAtomsPerLane];
     mx = -INFINITY;
+#pragma unroll
     for (int t = 0; t < kMaxAtomsPerLane; ++t) {
-        const int j = lane + 32 * t;
-        l[t] = j < Z ? dueling(vs, as, A, Z, a_taken, j) : -INFINITY;
+        const int jj = lane + 32 * t;
+        l[t] = jj < Z ? dueling(vs, as, A, Z, a_taken, jj) : -INFINITY;
         mx = fmaxf(mx, l[t]);
     }
     mx = warp_max(mx);
     float sum_e = 0.0f;
-    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
-        const int j = lane + 32 * t;
-        if (j < Z) sum_e = __fadd_rn(sum_e, expf(__fadd_rn(l[t], -mx)));
-    }
+#pragma unroll
+    for (int t = 0; t < kMaxAtomsPerLane; ++t)
+        if (lane + 32 * t < Z) sum_e = __fadd_rn(sum_e, expf(__fadd_rn(l[t], -mx)));
     sum_e = warp_sum(sum_e);
     const float lse = __fadd_rn(mx, logf(sum_e));
     float loss = 0.0f, msum = 0.0f;
+#pragma unroll
     for (int t = 0; t < kMaxAtomsPerLane; ++t) {
-        const int j = lane + 32 * t;
-        if (j < Z) {
-            loss = __fadd_rn(loss, __fmul_rn(m[j], __fadd_rn(l[t], -lse)));
-            msum = __fadd_rn(msum, m[j]);
+        const int jj = lane + 32 * t;
+        if (jj < Z) {
+            loss = __fadd_rn(loss, __fmul_rn(m[jj], __fadd_rn(l[t], -lse)));
+            msum = __fadd_rn(msum, m[jj]);
         }
     }
     loss = warp_sum(loss);
     msum = warp_sum(msum);
     if (lane == 0) p.per_sample[i] = -loss;
     const float invB = __fdiv_rn(1.0f, (float)p.B);
+#pragma unroll
     for (int t = 0; t < kMaxAtomsPerLane; ++t) {
-        const int j = lane + 32 * t;
-        if (j >= Z) continue;
+        const int jj = lane + 32 * t;
+        if (jj >= Z) continue;
         const float sm = expf(__fadd_rn(l[t], -lse));
-        const float gl = __fmul_rn(__fadd_rn(__fmul_rn(sm, msum), -m[j]), invB);  // d loss / d out[a_taken][j]
-        if (duel) p.dv[i * Z + j] = gl;
+        const float gl = __fmul_rn(__fadd_rn(__fmul_rn(sm, msum), -m[jj]), invB);  // d loss / d out[a_taken][j]
+        if (duel) p.dv[i * Z + jj] = gl;
         const float shared = duel ? __fdiv_rn(gl, (float)A) : 0.0f;
         for (int k = 0; k < A; ++k)
-            p.da[i * A * Z + k * Z + j] = __fadd_rn(k == a_taken ? gl : 0.0f, -shared);
+            p.da[i * A * Z + k * Z + jj] = __fadd_rn(k == a_taken ? gl : 0.0f, -shared);
     }
 }
 

@@ -73,9 +73,23 @@ __global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint3
     const float4 *s1 = reinterpret_cast<const float4 *>(r.obs + (size_t)nxt * row + ((size_t)agent * r.num_envs + env) * r.slot_floats);
     const size_t orow = ((size_t)agent * batch + b) * r.slot_floats;
     float4 *d0 = reinterpret_cast<float4 *>(out.obs + orow), *d1 = reinterpret_cast<float4 *>(out.next_obs + orow);
-    for (int q = lane; q < r.slot_floats / 4; q += 32) {
-        d0[q] = __ldg(s0 + q);
-        d1[q] = __ldg(s1 + q);
+    // all loads of two strides in flight before the first store (the rows are random 600-byte gathers: latency-bound
+    // without memory-level parallelism)
+    const int n4 = r.slot_floats / 4;
+    for (int q = lane; q < n4; q += 64) {
+        const int q2 = q + 32;
+        const float4 a0 = __ldg(s0 + q), b0 = __ldg(s1 + q);
+        float4 a1 = a0, b1 = b0;
+        if (q2 < n4) {
+            a1 = __ldg(s0 + q2);
+            b1 = __ldg(s1 + q2);
+        }
+        d0[q] = a0;
+        d1[q] = b0;
+        if (q2 < n4) {
+            d0[q2] = a1;
+            d1[q2] = b1;
+        }
     }
     if (out.obj_rows && r.objects_bits) {  // agent's objects_matrix snapshot of both slots: T*X strided words each
         const int TX = r.type_objects * r.size_x;

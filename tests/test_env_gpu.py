@@ -449,3 +449,61 @@ def test_random_configurations_match_oracle(seed):
         _compare(cuda.step(tick, noise_tape=tape), orc.step(tick, noise_tape=tape, threads=4), keys, f"seed {seed} tick {tick}")
         _compare(cuda.state(), orc.state(), ("pos", "objects", "counters", "steps", "destination"), f"seed {seed} state {tick}")
     assert cuda.env.stats()["error_flag"] == 0
+
+
+@pytest.mark.parametrize("noise", ["sensing_dist", "threshold_sensing_dist", "flat", "flip"])
+def test_on_chip_noise_stream_has_the_reference_distribution(noise):
+    """The on-chip draws (Philox + Box-Muller with libm logf / cosf / sinf) are bit-exact with the reference only under
+    injected tapes; without a tape the claim is distributional.  Merged view: `obs` carries the noise, `obs_rel` is the same
+    observation without it (merged_observtion_handler.py:27,41-47), so their difference is the noise the kernel drew.
+    sensing_dist: z = (obs - clean) / sigma_ring must be N(0,1) like normal_(0, std) in dist_observation_noise.py:33-35
+    (moments, Kolmogorov-Smirnov distance, tail mass, no correlation between neighbours); threshold_sensing_dist keeps
+    exactly the draws with |noise| > sigma * ratio (:53-75); flat is N(0, 0.03^2) on three channels
+    (flat_observation_noise.py:28-34); flip: |rint(x + u * range)| of u ~ U[0,1) flips a cell with probability p_ring
+    (flip_observation_noise.py:28-46) — checked through the flip rate per ring."""
+    import math
+    from tests.cuda_backend import make_env
+    E = 4096
+    ratio = 1.0
+    cfg = baseline_config(5).merged_with(observation_area_mask="merged", observation_noise=noise, noise_threshold_ratio=ratio,
+                                         std_distribution=[0.3, 0.2, 0.1], flip_noise_probabilities=[0.2, 0.1, 0.05])
+    env = make_env(cfg, E, auto_reset=True)
+    out = env.new_outputs()
+    env.reset(out, tick=0)
+    env.step(out, tick=1)
+    noisy, clean = env.view(out["obs"]).double().cpu(), env.view(out["obs_rel"]).double().cpu()  # [E,N,C,V,V]
+    V, C = env.V, env.C
+    a = torch.arange(V)
+    ring = torch.minimum(torch.minimum(a[:, None], a[None, :]), torch.minimum(V - 1 - a[:, None], V - 1 - a[None, :])).clamp(max=V // 2 - 1)
+    diff = noisy - clean
+    if noise == "flip":
+        # channel 2 is shifted by +1 before and -1 after the rounding (flip_observation_noise.py:33,44): same flip rate
+        flipped = (diff.abs() > 0.5).double()
+        for r, p in enumerate([0.2, 0.1, 0.05]):
+            rate = float(flipped[..., ring == r].mean())
+            n = flipped[..., ring == r].numel()
+            assert abs(rate - p) < 6 * math.sqrt(p * (1 - p) / n), (r, rate, p)
+        return
+    sigma = torch.tensor([0.3, 0.2, 0.1])[ring] if noise != "flat" else torch.full((V, V), 0.03)
+    z = (diff / sigma).reshape(-1, C, V, V)
+    if noise == "threshold_sensing_dist":
+        kept = z != 0
+        # P(|N(0,1)| > ratio) of the draws survive, and every survivor lies outside the threshold
+        p = math.erfc(ratio / math.sqrt(2))
+        assert abs(float(kept.double().mean()) - p) < 6 * math.sqrt(p * (1 - p) / kept.numel())
+        assert float(z[kept].abs().min()) > ratio - 1e-6
+        tail = z[kept]
+        assert abs(float(tail.mean())) < 0.01 and abs(float((tail ** 2).mean()) - (1 + ratio * math.sqrt(2 / math.pi) * math.exp(-ratio ** 2 / 2) / p)) < 0.02
+        return
+    z = z.reshape(-1)
+    n = z.numel()
+    assert abs(float(z.mean())) < 5 / math.sqrt(n) + 2e-4
+    assert abs(float(z.var()) - 1) < 5 * math.sqrt(2 / n) + 2e-3   # fp32 rounding of obs + noise widens the bound a little
+    assert abs(float((z ** 3).mean())) < 0.02 and abs(float((z ** 4).mean()) - 3) < 0.05
+    sample = z[torch.randperm(n, generator=torch.Generator().manual_seed(0))[:200_000]].sort()[0]
+    cdf = 0.5 * (1 + torch.erf(sample / math.sqrt(2)))
+    ks = float((cdf - torch.arange(1, sample.numel() + 1) / sample.numel()).abs().max())
+    assert ks < 1.63 / math.sqrt(sample.numel()) + 1e-3, ks             # 1 % critical value of the KS statistic
+    assert abs(float((z.abs() > 3).double().mean()) - 0.0026998) < 3e-4   # tail mass
+    zz = z.reshape(-1, V * V)
+    assert abs(float(torch.corrcoef(torch.stack([zz[:, 0], zz[:, 1]]))[0, 1])) < 0.01  # neighbouring elements are independent
