@@ -30,9 +30,10 @@ ENVS_PER_GPU = 65536
 RING_SLOTS = 8
 B_ALG = 744.0  # algorithmic bytes per agent-step for cfg5 (588 obs + 144 grid r/w + 12)
 METRIC, UNIT = "agent_steps_per_sec", "agent-steps/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of env_step_kernel<7,16,0,8> at this
-# workload, from profiles/ (ncu --set full)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 282.45e6  # 8.81 MB read + 273.64 MB written (profiles/r2_env_step_kernel_ncu_full.csv)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel at this workload, from profiles/ (ncu --set full):
+# env_step_lanes_kernel<7,8> 8.8 MB read + 274.2 MB written (profiles/r2_env_step_lanes_kernel_ncu_full.csv);
+# env_step_kernel<7,16,0,8> (MAEXP_LANES=0) 8.81 + 273.64 MB (profiles/r2_env_step_kernel_ncu_full.csv)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {True: 282.96e6, False: 282.45e6}
 
 
 def workload_config():
@@ -270,6 +271,7 @@ def run_ours(args, rank, local_rank, world):
     # envs are independent units: contiguous global ids per rank, no data-path collective
     env = BatchedEnvironment(cfg, world_obj, E, device=dev, auto_reset=True,
                              first_global_env_id=mdist.first_global_env_id(rank, E))
+    lanes = env.uses_lanes_kernel()  # one lane per (env, agent): csrc/env_lanes.cu
     ring = DeviceReplayRing(env, RING_SLOTS)  # obs + actions + rewards + dones + was_reset rings in HBM
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -391,12 +393,13 @@ def run_ours(args, rank, local_rank, world):
                                          "last step's results are in host memory; observations stay in the device replay ring"},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
-                         "kernel": "env_step_kernel", "algorithmic_bytes_per_agent_step": B_ALG,
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH[lanes], "peak_source": peak_src,
+                         "kernel": "env_step_lanes_kernel<7,8>" if lanes else "env_step_kernel<7,16,0,8>",
+                         "algorithmic_bytes_per_agent_step": B_ALG,
                          "launch_us": launch_s * 1e6,
                          # the bit-packed state never moves the 144 B / agent-step of int8 grid traffic B_ALG counts:
                          # the same launch time against the DRAM bytes ncu saw
-                         "real_bytes_frac": NCU_TRAFFIC_BYTES_PER_LAUNCH * (E / ENVS_PER_GPU) / launch_s / 1e9 / peak},
+                         "real_bytes_frac": NCU_TRAFFIC_BYTES_PER_LAUNCH[lanes] * (E / ENVS_PER_GPU) / launch_s / 1e9 / peak},
             "clocks": sampler.summary(),
             "learner": {"metric": "learner_updates_per_sec", "unit": "agent-network updates/s",
                         "value": ku * N / (upd_ms * 1e-3), "ms_per_team_update": upd_ms / ku, "brain": "categorical_dqn",

@@ -123,6 +123,12 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tables, maexp
 void maexp_env_destroy(maexp_env *env);
 int maexp_env_channels(const maexp_env *env);     /* ObservationHandler.get_channel, observation_handler.py:55-61 */
 int maexp_env_slot_floats(const maexp_env *env);
+/* 1 when plain calls (no coordinates / objects / objects_bits / heatmaps / obs_rel output) run the agent-parallel step
+ * kernel (csrc/env_lanes.cu: one lane per (environment, agent); N in {2,4,8}, one object type, the three default channels,
+ * visible_range 5 / 7, no observation noise), 0 when every call runs the lane-per-environment kernel.  Both produce the
+ * same bits.  The library takes it by default for N = 8; the environment variable MAEXP_LANES=1 / 0 at creation time forces
+ * it on for every shape it supports / off. */
+int maexp_env_agent_parallel(const maexp_env *env);
 
 /* DefaultEnvironment.reset (default_environment.py:64-116) for every env with env_mask[e] != 0
  * (NULL: all).  noise_tape: optional fp32 [E,N,C*V*V] injected draws (NULL: on-chip Philox). */

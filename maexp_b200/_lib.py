@@ -83,6 +83,7 @@ SYMBOLS = {
     "maexp_env_destroy": (None, [C.c_void_p]),
     "maexp_env_channels": (C.c_int, [C.c_void_p]),
     "maexp_env_slot_floats": (C.c_int, [C.c_void_p]),
+    "maexp_env_agent_parallel": (C.c_int, [C.c_void_p]),
     "maexp_env_reset": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(ObsOut), C.c_void_p]),
     "maexp_env_step": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ObsOut),
                                  C.c_void_p]),

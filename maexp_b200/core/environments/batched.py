@@ -327,6 +327,10 @@ class BatchedEnvironment:
         _lib.check(self.lib.maexp_env_set_state(self.h, self._p(pos), self._p(objects), self._stream()))
         torch.cuda.synchronize(self.device)
 
+    def uses_lanes_kernel(self):
+        """True when plain step / reset calls run the agent-parallel kernel (csrc/env_lanes.cu)."""
+        return bool(self.lib.maexp_env_agent_parallel(self.h))
+
     def stats(self):
         steps, resets, err = C.c_uint64(), C.c_uint64(), C.c_int32()
         _lib.check(self.lib.maexp_env_stats(self.h, C.byref(steps), C.byref(resets), C.byref(err), self._stream()))

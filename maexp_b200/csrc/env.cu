@@ -111,6 +111,11 @@ struct maexp_env {
     size_t smem_bytes;
     int grid_ctas = 0;
     KernelFn fn = nullptr;
+    // agent-parallel kernel (env_lanes.cu) for the shapes it takes; chosen per call when the outputs asked for allow it
+    KernelFn fn_lanes = nullptr;
+    size_t lanes_smem = 0;
+    int lanes_ctas = 0;
+    bool lanes_queue = false;  // MAEXP_LANES_QUEUE=1: work items from an atomic queue instead of the static round-robin
     std::vector<void *> allocs;
     // pinned-free staging for the host-buffer entry point
     int8_t *d_actions = nullptr;
@@ -189,7 +194,11 @@ int launch(maexp_env *h, uint32_t tick, int force_reset, const uint8_t *env_mask
             return fail("maexp_env_step: rewards / positions must be 16-byte aligned, dones / actions_taken 8-byte aligned");
     }
     if (misaligned_obs(p.out.obs) || misaligned_obs(p.out.obs_rel)) return fail("maexp_env_step: obs slots must be 16-byte aligned");
-    h->fn<<<h->grid_ctas, kWarpsPerCta * 32, h->smem_bytes, stream>>>(p);
+    if (!h->lanes_queue) p.queue = nullptr;
+    const bool lanes = h->fn_lanes && !p.out.obs_rel && !p.out.coordinates && !p.out.objects && !p.out.objects_bits &&
+                       !p.out.heatmaps && !(reinterpret_cast<uintptr_t>(p.out.positions) & 1);
+    if (lanes) h->fn_lanes<<<h->lanes_ctas, kWarpsPerCta * 32, h->lanes_smem, stream>>>(p);
+    else h->fn<<<h->grid_ctas, kWarpsPerCta * 32, h->smem_bytes, stream>>>(p);
     MAEXP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -329,6 +338,7 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     rc |= dev_alloc(h, &p.past, (size_t)E * (p.P ? p.P : 1) * N);
     rc |= dev_alloc(h, &p.stats, 2);
     rc |= dev_alloc(h, &p.error_flag, 1);
+    rc |= dev_alloc(h, &p.queue, 2);
     rc |= dev_alloc(h, &h->d_actions, (size_t)E * N);
     rc |= dev_alloc(h, &h->d_rewards, (size_t)E * N);
     rc |= dev_alloc(h, &h->d_dones, (size_t)E * N);
@@ -373,6 +383,32 @@ int maexp_env_create(const maexp_env_cfg *cfg, const maexp_tables *tb, maexp_env
     const int groups = (E + h->epw - 1) / h->epw;
     h->grid_ctas = per_sm * sms;  // persistent: exactly one resident wave
     if (h->grid_ctas > (groups + kWarpsPerCta - 1) / kWarpsPerCta) h->grid_ctas = (groups + kWarpsPerCta - 1) / kWarpsPerCta;
+    // one lane per (env, agent) where the shape allows it (env_lanes.cu); MAEXP_LANES=0 keeps the lane-per-env kernel
+    // Default: N = 8 (62.4 against 67.3 us per step at 65 536 envs; with two agents per environment the lane-per-env kernel
+    // already fills half a warp and measures the same, cfg1 19.7 against 20.4 us).  MAEXP_LANES=1 / 0 forces the choice.
+    const char *lanes_env = getenv("MAEXP_LANES");
+    const bool lanes_wanted = lanes_env ? atoi(lanes_env) != 0 : N == 8;
+    if (nspec && p.fast3 && p.noise == MAEXP_NOISE_NONE && !p.merged && !cfg->dynamic_obstacles &&
+        p.slot_floats == (p.K + 7) / 8 * 8 && lanes_wanted) {
+        h->fn_lanes = pick_lanes(V, N);
+        if (h->fn_lanes) {
+            if (const char *q = getenv("MAEXP_LANES_QUEUE")) h->lanes_queue = atoi(q) != 0;
+            h->lanes_smem = lanes_warp_words(N, V, p.gs, p.as) * 4 * kWarpsPerCta;
+            int lanes_per_sm = 0;
+            if (cudaFuncSetAttribute(h->fn_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->lanes_smem) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lanes_per_sm, h->fn_lanes, kWarpsPerCta * 32, h->lanes_smem) != cudaSuccess ||
+                lanes_per_sm < 1) {
+                cudaGetLastError();
+                h->fn_lanes = nullptr;
+            } else {
+                const int items = (E + 32 / N - 1) / (32 / N);
+                if (N == 8 && lanes_per_sm > 4) lanes_per_sm = 4;  // see MAEXP_LANES_MINB in env_lanes.cu
+                if (const char *c = getenv("MAEXP_LANES_CTAS")) { const int v = atoi(c); if (v >= 1 && v <= 8) lanes_per_sm = v; }
+                h->lanes_ctas = lanes_per_sm * sms;
+                if (h->lanes_ctas > (items + kWarpsPerCta - 1) / kWarpsPerCta) h->lanes_ctas = (items + kWarpsPerCta - 1) / kWarpsPerCta;
+            }
+        }
+    }
     init_state_kernel<<<(E + 127) / 128, 128>>>(p);
     if (cudaDeviceSynchronize() != cudaSuccess) { maexp_env_destroy(h); return fail("maexp_env_create: init kernel failed"); }
     *out = h;
@@ -397,6 +433,7 @@ void maexp_env_destroy(maexp_env *h) {
 }
 
 int maexp_env_channels(const maexp_env *h) { return h ? h->p.C : -1; }
+int maexp_env_agent_parallel(const maexp_env *h) { return (h && h->fn_lanes) ? 1 : 0; }
 int maexp_env_slot_floats(const maexp_env *h) { return h ? h->p.slot_floats : -1; }
 
 int maexp_env_reset(maexp_env *h, uint32_t tick, const uint8_t *env_mask, const float *noise_tape,

@@ -42,6 +42,7 @@ struct EnvParams {
     unsigned long long *stats;  // [0] env-steps, [1] resets
     uint32_t tx_magic;          // ceil(2^32 / (T*X))
     int32_t *error_flag;
+    uint32_t *queue;  // env_step_lanes_kernel: [0] work items handed out past the first static round, [1] warps that left
     // dynamic_simple_map.py: world steps taken since creation (the obstacle phase; survives resets), or nullptr
     uint32_t *wsteps;
     // io
@@ -912,5 +913,8 @@ KernelFn pick_epw(int epw, int noise, int nspec) {
 KernelFn pick_v5(int epw, int noise, int nspec);
 KernelFn pick_v7(int epw, int noise, int nspec);
 KernelFn pick_v9(int epw, int noise, int nspec);
+// env_lanes.cu: one lane per (environment, agent); nullptr for shapes it does not take
+KernelFn pick_lanes(int V, int N);
+size_t lanes_warp_words(int N, int V, int gs, int as);
 
 }  // namespace maexp

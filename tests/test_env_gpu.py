@@ -507,3 +507,110 @@ def test_on_chip_noise_stream_has_the_reference_distribution(noise):
     assert abs(float((z.abs() > 3).double().mean()) - 0.0026998) < 3e-4   # tail mass
     zz = z.reshape(-1, V * V)
     assert abs(float(torch.corrcoef(torch.stack([zz[:, 0], zz[:, 1]]))[0, 1])) < 0.01  # neighbouring elements are independent
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# env_step_lanes_kernel (csrc/env_lanes.cu): one lane per (environment, agent).  The library picks it per call when the
+# shape allows it and no snapshot output is requested, so these tests ask for the plain outputs only.
+def _lanes_outputs(env):
+    d = env.device
+    o = env.new_outputs(extras=False)
+    o["positions"] = torch.zeros((env.E, env.N, 2), dtype=torch.int8, device=d)
+    o["destination"] = torch.zeros((env.E, env.N), dtype=torch.uint8, device=d)
+    o["actions_taken"] = torch.zeros((env.E, env.N), dtype=torch.int8, device=d)
+    o["rewards_i8"] = torch.zeros((env.E, env.N), dtype=torch.int8, device=d)
+    o["done_env"] = torch.zeros((env.E,), dtype=torch.uint8, device=d)
+    return o
+
+
+def _lanes_variants():
+    c = cases()
+    base = c["cfg5_four_rooms_n8"][0]
+    out = {name: (c[name][0], c[name][3]) for name in
+           ("cfg1_simple_mlp", "cfg3_three_rooms", "cfg5_four_rooms_n8", "simple_views_v5", "relative_transparent")}
+    out["n8_no_keep_few_objects"] = (base.merged_with(keep_objects_num=False, num_objects=3), {})
+    out["n8_shared_mean"] = (base.merged_with(environment="shared_mean_reward"), {})
+    out["n8_shared_max"] = (base.merged_with(environment="shared_max_reward"), {"shared_max_is_mean": False})
+    out["n8_tasks"] = (base.merged_with(agent_tasks=["0", "-1", "0", "0", "-1", "0", "0", "0"]), {})
+    out["n8_dense_objects"] = (base.merged_with(num_objects=120), {})
+    out["n4_four_rooms"] = (base.merged_with(num_agents=4, init_xys=[[4, 4], [-4, 4], [4, -4], [-4, -4]], num_objects=60), {})
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(_lanes_variants()))
+@pytest.mark.parametrize("num_envs", [37, 300])
+def test_lanes_kernel_matches_oracle_and_lane_per_env_kernel(name, num_envs, monkeypatch):
+    """Ragged batches through env_step_lanes_kernel against the oracle AND against env_step_kernel (MAEXP_LANES=0) run on
+    the same keys: observations, rewards, dones, positions, actions, compact outputs and the whole state, every tick,
+    across an auto-reset."""
+    cfg, okw = _lanes_variants()[name]
+    cfg = cfg.merged_with(max_episode_length=12)
+    gid0 = 4242
+    monkeypatch.setenv("MAEXP_LANES", "1")  # the default takes it for N = 8 only
+    lanes = CudaBackend(cfg, num_envs, first_global_env_id=gid0, auto_reset=True, extras=False, **okw)
+    assert lanes.env.uses_lanes_kernel(), "this shape should take the agent-parallel kernel"
+    lanes.out = _lanes_outputs(lanes.env)
+    monkeypatch.setenv("MAEXP_LANES", "0")
+    plain = CudaBackend(cfg, num_envs, first_global_env_id=gid0, auto_reset=True, extras=False, **okw)
+    assert not plain.env.uses_lanes_kernel()
+    plain.out = _lanes_outputs(plain.env)
+    orc = Oracle(cfg, num_envs, auto_reset=True, first_global_env_id=gid0, extras=True, **okw)
+    keys = ("obs", "rewards", "dones", "was_reset")
+    raw = ("obs", "rewards", "dones", "was_reset", "positions", "destination", "actions_taken", "rewards_i8", "done_env")
+
+    def check(a, b, ref, what):
+        _compare(a, ref, keys, f"{name} {what} (lanes vs oracle)")
+        for k in raw:
+            assert torch.equal(lanes.out[k], plain.out[k]), f"{name} {what}: {k} differs between the two kernels"
+        _compare(lanes.state(), orc.state(), ("pos", "objects", "counters", "steps", "destination"), f"{name} state {what}")
+
+    check(lanes.reset(0), plain.reset(0), orc.reset(0), "reset")
+    for tick in range(1, 30):
+        check(lanes.step(tick), plain.step(tick), orc.step(tick, threads=4), f"tick {tick}")
+    st = lanes.env.stats()
+    assert st["error_flag"] == 0 and st["resets"] >= num_envs * 2 and st == plain.env.stats()
+
+
+def test_lanes_kernel_injected_actions_orders_and_masked_resets():
+    cfg = baseline_config(5)
+    E = 70
+    cuda = CudaBackend(cfg, E, first_global_env_id=5, extras=False)
+    assert cuda.env.uses_lanes_kernel()
+    orc = Oracle(cfg, E, first_global_env_id=5, extras=True)
+    rng = np.random.default_rng(3)
+    keys = ("obs", "rewards", "dones")
+    _compare(cuda.reset(0), orc.reset(0), keys, "reset")
+    for tick in range(1, 24):
+        actions = rng.integers(0, 5, size=(E, 8)).astype(np.int8)
+        order = np.stack([rng.permutation(8) for _ in range(E)]).astype(np.uint8)
+        _compare(cuda.step(tick, actions, order), orc.step(tick, actions, order), keys, f"tick {tick}")
+        _compare(cuda.state(), orc.state(), ("pos", "objects", "counters", "steps"), f"state {tick}")
+        if tick % 7 == 0:
+            mask = (rng.random(E) < 0.3).astype(np.uint8)
+            a, b = cuda.reset(1000 + tick, env_mask=mask), orc.reset(1000 + tick, env_mask=mask)
+            sel = mask.astype(bool)
+            for k in keys:
+                assert np.array_equal(a[k][sel], b[k][sel]), (tick, k)
+            _compare(cuda.state(), orc.state(), ("pos", "objects", "counters", "steps"), f"masked reset {tick}")
+
+
+def test_lanes_kernel_full_size_equals_lane_per_env_kernel(monkeypatch):
+    """BASELINE configs[4] at full size: both kernels from the same seed, 230 ticks (one auto-reset), every output equal."""
+    cfg = baseline_config(5)
+    E = 65536
+    lanes = CudaBackend(cfg, E, first_global_env_id=0, auto_reset=True, extras=False)
+    assert lanes.env.uses_lanes_kernel()
+    monkeypatch.setenv("MAEXP_LANES", "0")
+    plain = CudaBackend(cfg, E, first_global_env_id=0, auto_reset=True, extras=False)
+    lanes.env.reset(lanes.out, tick=0)
+    plain.env.reset(plain.out, tick=0)
+    for tick in range(1, 231):
+        lanes.env.step(lanes.out, tick=tick)
+        plain.env.step(plain.out, tick=tick)
+        if tick % 10 == 0 or tick > 195:
+            for k in ("obs", "rewards", "dones", "was_reset"):
+                assert torch.equal(lanes.out[k], plain.out[k]), (tick, k)
+    sa, sb = lanes.env.state(), plain.env.state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert lanes.env.stats() == plain.env.stats() and lanes.env.stats()["error_flag"] == 0

@@ -7,6 +7,7 @@
 //   mode 4: chase, then the agent's 9728 bytes leave as four 2432-byte bulk async copies (cp.async.bulk, TMA engine) from a
 //           per-warp shared-memory staging tile written with 128-bit shared stores     mode 5: mode 4 without the chase
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 __global__ void __launch_bounds__(128, 7) overlap(float *dst, int E, int N, int slot, int chase, int mode, int *sink) {
@@ -23,7 +24,7 @@ __global__ void __launch_bounds__(128, 7) overlap(float *dst, int E, int N, int 
         if (k < 16) __stcs(reinterpret_cast<float4 *>(base + k * slot + lane * 4), v);
         else {
             const int r = lane & 7, e = (lane >> 3) * 4 + (k - 16);
-            if (r < 6) __stcs(reinterpret_cast<float4 *>(base + e * slot + (32 + r) * 4), v);
+            if (r < slot / 4 - 32) __stcs(reinterpret_cast<float4 *>(base + e * slot + (32 + r) * 4), v);
         }
     };
     for (int g = blockIdx.x * 4 + warp; g < groups; g += gridDim.x * 4) {
@@ -96,8 +97,9 @@ __global__ void __launch_bounds__(128, 7) overlap(float *dst, int E, int N, int 
     if (idx == 12345) *sink = idx;
 }
 
-int main() {
-    const int E = 65536, N = 8, slot = 152;
+int main(int argc, char **argv) {
+    const int E = 65536, N = 8, slot = argc > 1 ? atoi(argv[1]) : 152;
+    const int ctas_per_sm = argc > 2 ? atoi(argv[2]) : 7;
     float *buf[4];
     int *sink;
     const size_t bytes = (size_t)E * N * slot * 4;
@@ -106,11 +108,11 @@ int main() {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     for (int chase : {260})
-        for (int mode = 0; mode < 10; ++mode) {
-            for (int k = 0; k < 5; ++k) overlap<<<148 * 7, 128>>>(buf[k & 3], E, N, slot, chase, mode, sink);
+        for (int mode : {2, 3, 0}) {
+            for (int k = 0; k < 5; ++k) overlap<<<148 * ctas_per_sm, 128>>>(buf[k & 3], E, N, slot, chase, mode, sink);
             cudaEventRecord(a);
             const int reps = 50;
-            for (int k = 0; k < reps; ++k) overlap<<<148 * 7, 128>>>(buf[k & 3], E, N, slot, chase, mode, sink);
+            for (int k = 0; k < reps; ++k) overlap<<<148 * ctas_per_sm, 128>>>(buf[k & 3], E, N, slot, chase, mode, sink);
             cudaEventRecord(b);
             cudaEventSynchronize(b);
             float ms = 0;
