@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/maexp_b200.h"
+#include "tc_heads.h"
 #include "tc_mlp.h"
 
 namespace maexp {
@@ -1407,6 +1408,9 @@ struct maexp_learner {
     bool fused_mlp = true;         // one-kernel MLP heads for the update batches (MAEXP_FUSED_MLP=0: GEMM by GEMM)
     bool tc_mlp = false;           // MAEXP_TC_MLP=1: the MLP heads of >= 128-row batches on tcgen05 (csrc/tc_mlp.cu).  Off by default:
                                    // measured SLOWER than the SIMT kernel at B = 256 (45 vs 33 us; profiles/r2_tc_mlp_fwd_*.txt)
+    bool tc_heads = true;          // acting batches: both layers of all heads in one TMA-fed tcgen05 kernel (csrc/tc_heads.cu; MAEXP_TC_HEADS=0: GEMM by GEMM)
+    float *tc_heads_ws = nullptr;  // its pre-split weight panels
+    size_t tc_heads_ws_floats = 0;
     bool fused_trunk = true;       // one-kernel conv trunk for every local-view pass (MAEXP_FUSED_TRUNK=0: layer by layer)
     const float *bwd_obs = nullptr;  // observations of the last training pass (conv1's im2col in trunk_backward)
     float *trunk_part = nullptr;      // block partials of trunk_fused_bwd_kernel
@@ -1509,6 +1513,9 @@ inline dim3 grid1d(long long total, int g, int threads = 256, int cap = 1024) {
 
 constexpr long long kSplitWorkspaceFloats = 8ll << 20;  // 32 MB of partial tiles
 float *g_splitk_ws = nullptr;                            // set per call from the handle (single host thread)
+// set by maexp_learner_q_values around the forward pass of the dueling distributional networks: the heads kernel may write the
+// greedy values straight to q_out (and then sets done), which replaces dist_q_kernel and the 255 head outputs per row
+struct FusedQ { float *q_out = nullptr; long long q_g = 0; int categorical = 0; bool done = false; } g_fused_q;
 bool g_inference_tc = false;                             // set by the q_values entry points around their forward pass
 constexpr int kAttnMapsBatch = 256;                      // q_values batches up to this size keep their attention maps
 struct InferenceScope {                                  // (every model family: conv heads, transformer projections)
@@ -2263,6 +2270,35 @@ bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const flo
                              int nheads, const MlpIn *ins, float *const (*hbufs)[2], float *const (*outs)[2]) {
     const int H = h->H;
     const MlpIn &in = ins[0];
+    // acting / evaluation batches: layer 1 of all heads, bias + ReLU and layer 2 in one TMA-fed tcgen05 kernel
+    if (g_inference_tc && h->use_tc && h->tc_heads && in.rows >= 512 && n == 1 && nheads >= 1 && nheads <= 2 && H == 128 &&
+        in.din >= 32 && in.din % 32 == 0) {
+        int outs_n[2] = {hds[0].out, nheads > 1 ? hds[1].out : 0};
+        const size_t need = tc_heads_workspace_floats(h->G, nheads, in.din, outs_n);
+        if (need > h->tc_heads_ws_floats) {  // first call (or a wider layer): the old panel buffer stays in h->allocs until destroy
+            float *ws = nullptr;
+            if (lalloc(h, &ws, need) == 0) { h->tc_heads_ws = ws; h->tc_heads_ws_floats = need; }
+        }
+        if (need <= h->tc_heads_ws_floats) {
+            TcHeadsFwd t = {};
+            t.x = in.x; t.x_row = in.x_row; t.x_g = in.x_g;
+            t.params = params[0]; t.P = h->P;
+            t.nheads = nheads;
+            for (int k = 0; k < nheads; ++k) {
+                t.w1[k] = hds[k].w1; t.b1[k] = hds[k].b1; t.w2[k] = hds[k].w2; t.b2[k] = hds[k].b2; t.out[k] = hds[k].out;
+                t.outp[k] = outs[0][k];
+            }
+            t.rows = in.rows; t.rows_max = in.rows_max; t.din = in.din; t.H = H;
+            t.workspace = h->tc_heads_ws;
+            if (g_fused_q.q_out && h->dist && !h->iqn && nheads == 2) {
+                t.q_out = g_fused_q.q_out; t.q_g = g_fused_q.q_g; t.A = h->A; t.Z = h->Z;
+                t.categorical = g_fused_q.categorical; t.support = h->support;
+                t.fused_q_done = &g_fused_q.done;
+            }
+            if (tc_heads_forward(st, h->G, t)) return true;
+            g_fused_q.done = false;
+        }
+    }
     // large acting batches keep the tensor-core path; the fused kernel serves the update batches and small inference calls
     // and a wide input (the relative-canvas embedders: 7 744 .. 11 520 features on a few rows) needs the split-K GEMM's CTAs
     if (!h->fused_mlp || nheads < 1 || nheads > 2 || n < 1 || n > 3 || H > kMlpTN || (g_inference_tc && in.rows >= 512) ||
@@ -2927,6 +2963,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (const char *ft = getenv("MAEXP_FUSED_TRUNK")) h->fused_trunk = atoi(ft) != 0;
     if (const char *fm = getenv("MAEXP_FUSED_MLP")) h->fused_mlp = atoi(fm) != 0;
     if (const char *tm = getenv("MAEXP_TC_MLP")) h->tc_mlp = atoi(tm) != 0;
+    if (const char *th = getenv("MAEXP_TC_HEADS")) h->tc_heads = atoi(th) != 0;
     if (const char *bf = getenv("MAEXP_BATCHED_FWD")) h->batched_fwd = atoi(bf) != 0;
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
     h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;
@@ -3427,8 +3464,18 @@ int maexp_learner_q_values(maexp_learner *h, const float *obs, int batch, int us
         MAEXP_CUDA_L(cudaGetLastError());
         return 0;
     }
+    g_fused_q = FusedQ();
+    if (h->dist) {
+        g_fused_q.q_out = q_out;
+        g_fused_q.q_g = (long long)batch * h->A;
+        g_fused_q.categorical = h->cfg.kind == MAEXP_LEARNER_C51;
+    }
     forward(h, st, use_target ? h->target : h->online, obs, batch, a, /*inference=*/true);
-    if (!h->dist) {
+    const bool fused_q = g_fused_q.done;
+    g_fused_q = FusedQ();
+    if (fused_q) {
+        // the heads kernel wrote the greedy values
+    } else if (!h->dist) {
         // heads are strided by the maximum batch: compact to [G][batch][A]
         MAEXP_CUDA_L(cudaMemcpy2DAsync(q_out, sizeof(float) * batch * h->A, a.out[0], sizeof(float) * h->B * h->A,
                                        sizeof(float) * batch * h->A, h->G, cudaMemcpyDeviceToDevice, st));

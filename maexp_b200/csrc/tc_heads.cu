@@ -1,0 +1,461 @@
+// TMA-fed, warp-specialised tcgen05 kernel for the acting / evaluation batches (>= 512 rows per agent): the two-layer MLP
+// heads of core/agents/models/mlp.py:28-34 -- fc_V and fc_A of the distributional networks, `mlp` of ConvMLP -- as ONE
+// kernel per forward pass:
+//
+//     hidden_k = relu(x W1_k^T + b1_k)   (all heads share x: one UMMA with N = heads * 128 columns)
+//     out_k    = hidden_k W2_k^T + b2_k  (the hidden activation goes from tensor memory through bias + ReLU back into shared
+//                                         memory as the A operand of the second contraction; it never touches HBM)
+//
+// Every fp32 product is evaluated as three TF32 terms (a_hi b_hi + a_lo b_hi + a_hi b_lo, a_hi = rna-tf32(a)), which keeps
+// the Q-values inside the learner's 1e-5 parity bar (tests/test_learner_gpu.py large-batch tests).
+//
+// Roles (192 threads, one CTA per 128-row tile and agent, one CTA per SM: it owns all 512 TMEM columns):
+//   warp 0      producer: one thread issues the TMA loads (cp.async.bulk.tensor, SWIZZLE_128B boxes of 32 floats x rows) of the
+//               raw fp32 x slab and of the PRE-SPLIT weight slabs (hi / lo panels written once per call by
+//               tc_heads_prepare_kernel, so no thread ever touches a weight) into a two-stage ring, mbarrier expect_tx
+//   warp 1      one thread issues tcgen05.mma.cta_group::1.kind::tf32 (12 per 32-float K slab: 4 K steps x 3 terms) and
+//               tcgen05.commit, whose mbarrier arrival hands the stage back to the producer
+//   warps 2-5   layer 1: split the x slab into hi / lo in place (shared -> registers -> shared, no global latency on this
+//               path); layer 2: read 32 hidden columns of their TMEM lane quadrant (tcgen05.ld), bias + ReLU, split, store
+//               the swizzled A slab; at the end: the output epilogue (bias, row stores)
+// Stage hand-offs: full[s] (TMA bytes landed) -> conv[s] (operands split, fence.proxy.async) -> MMA -> empty[s] (commit).
+// TMEM: columns [0, heads*128) hold the first accumulator; the widest head's output sits at column 256, the other head's
+// output re-uses the first-processed head's hidden columns once they have been consumed.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "tc_common.cuh"
+#include "tc_heads.h"
+
+using namespace maexp_tc;
+
+namespace {
+
+constexpr int kThreads = 192, kStages = 2, kHidden = 128;
+constexpr uint32_t kATile = kBM * 128;          // 16 KB: 128 rows x 32 floats
+constexpr uint32_t kWTile = 256 * 128;          // 32 KB: up to 256 rows x 32 floats
+constexpr uint32_t kStageBytes = 2 * kATile + 2 * kWTile;
+
+struct alignas(64) HeadsArgs {
+    CUtensorMap tm_x, tm_w1hi, tm_w1lo, tm_w2hi[2], tm_w2lo[2];
+    const float *b1cat;   // [G][heads * 128]
+    const float *b2p[2];  // [G][npad_k], zero padded
+    float *out[2];
+    long long out_g[2];
+    int out_n[2], npad[2];
+    int order[2];         // heads in the order their second layer runs
+    uint32_t d2col[2];    // TMEM column of every head's output accumulator
+    int rows, din, nheads;
+    // fused greedy-value epilogue of the dueling distributional heads (head 0 = fc_V [Z], head 1 = fc_A [A][Z]):
+    // epi 1 = categorical expectation (softmax over the atoms, sum p z), epi 2 = mean over the quantiles, 0 = raw head outputs
+    int epi, A, Z, rs;    // rs: odd row pitch (floats) of the shared-memory copy of the two accumulators
+    const float *support; // [Z] atom values (epi 1)
+    float *q_out;         // [G][rows][A]
+    long long q_g;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_3d(uint32_t dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t idesc_tf32(int n) {
+    // D = F32 (bits 4-5 = 1), A and B = TF32 (bits 7-9 and 10-12 = 2), both K-major, N >> 3 in bits 17-22, M >> 4 in bits 24-28
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_constant__ HeadsArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t full[kStages], conv[kStages], empty[kStages], d1_done, all_done;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_b2[512], s_sup[256];  // fused epilogue: both heads' output biases (padded widths back to back), atom values
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.y, m0 = blockIdx.x * kBM;
+    if (a.epi) {
+        for (int i = tid; i < a.npad[0] + a.npad[1]; i += kThreads)
+            s_b2[i] = i < a.npad[0] ? a.b2p[0][(size_t)g * a.npad[0] + i] : a.b2p[1][(size_t)g * a.npad[1] + i - a.npad[0]];
+        for (int i = tid; i < a.Z; i += kThreads) s_sup[i] = a.support ? a.support[i] : 0.0f;
+    }
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    auto a_hi = [&](int s) { return smem + (size_t)s * kStageBytes; };
+    auto a_lo = [&](int s) { return smem + (size_t)s * kStageBytes + kATile; };
+    auto w_hi = [&](int s) { return smem + (size_t)s * kStageBytes + 2 * kATile; };
+    auto w_lo = [&](int s) { return smem + (size_t)s * kStageBytes + 2 * kATile + kWTile; };
+    const int ns1 = a.din / kBK, per_head = kHidden / kBK, T = ns1 + per_head * a.nheads;
+    const int n1 = a.nheads * kHidden;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&conv[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&d1_done, 1);
+        mbar_init(&all_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            for (int t = 0; t < T; ++t) {
+                const int s = t % kStages, n = t / kStages;
+                if (t >= kStages) mbar_wait(&empty[s], (n - 1) & 1);
+                if (t < ns1) {
+                    mbar_expect_tx(&full[s], kATile + 2u * (uint32_t)n1 * 128u);
+                    tma_3d(smem_u32(a_hi(s)), &a.tm_x, &full[s], t * kBK, m0, g);
+                    tma_2d(smem_u32(w_hi(s)), &a.tm_w1hi, &full[s], t * kBK, g * n1);
+                    tma_2d(smem_u32(w_lo(s)), &a.tm_w1lo, &full[s], t * kBK, g * n1);
+                } else {
+                    const int h = a.order[(t - ns1) / per_head], j = (t - ns1) % per_head;
+                    mbar_expect_tx(&full[s], 2u * (uint32_t)a.npad[h] * 128u);
+                    tma_2d(smem_u32(w_hi(s)), &a.tm_w2hi[h], &full[s], j * kBK, g * a.npad[h]);
+                    tma_2d(smem_u32(w_lo(s)), &a.tm_w2lo[h], &full[s], j * kBK, g * a.npad[h]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            for (int t = 0; t < T; ++t) {
+                const int s = t % kStages, n = t / kStages;
+                mbar_wait(&full[s], n & 1);  // the weight slabs (and, in layer 1, the raw x slab) have landed
+                mbar_wait(&conv[s], n & 1);  // the A operand is split and visible to the async proxy
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t d = tmem, idesc = idesc_tf32(n1);
+                bool first = t == 0;
+                if (t >= ns1) {
+                    const int h = a.order[(t - ns1) / per_head], j = (t - ns1) % per_head;
+                    d = tmem + a.d2col[h];
+                    idesc = idesc_tf32(a.npad[h]);
+                    first = j == 0;
+                }
+                const uint32_t aA = smem_u32(a_hi(s)), aAlo = smem_u32(a_lo(s)), aW = smem_u32(w_hi(s)), aWlo = smem_u32(w_lo(s));
+#pragma unroll
+                for (int k = 0; k < kBK / 8; ++k) {  // UMMA_K = 8 TF32 = 32 bytes inside the 128-byte swizzle row
+                    const uint32_t ko = (uint32_t)k * 32;
+                    umma_tf32(d, smem_desc(aA + ko), smem_desc(aW + ko), idesc, (first && k == 0) ? 0u : 1u);
+                    umma_tf32(d, smem_desc(aAlo + ko), smem_desc(aW + ko), idesc, 1u);
+                    umma_tf32(d, smem_desc(aA + ko), smem_desc(aWlo + ko), idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+                if (t == ns1 - 1) umma_commit(&d1_done);
+                if (t == T - 1) umma_commit(&all_done);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ operand conversion + epilogue (128 threads)
+        const int ct = tid - 64, quad = warp & 3, row = quad * 32 + lane;  // a warp reads the TMEM lane quadrant warp % 4
+        for (int t = 0; t < T; ++t) {
+            const int s = t % kStages, n = t / kStages;
+            if (t < ns1) {
+                mbar_wait(&full[s], n & 1);
+                float4 *hi4 = reinterpret_cast<float4 *>(a_hi(s)), *lo4 = reinterpret_cast<float4 *>(a_lo(s));
+#pragma unroll
+                for (int i = 0; i < (int)(kATile / 16 / 128); ++i) {  // element-wise: the swizzled position is kept
+                    const float4 v = hi4[ct + 128 * i];
+                    const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                    hi4[ct + 128 * i] = hi;
+                    lo4[ct + 128 * i] = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                }
+            } else {
+                if (t == ns1) {
+                    mbar_wait(&d1_done, 0);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                if (t >= kStages) mbar_wait(&empty[s], (n - 1) & 1);  // the MMAs that read this stage's A slab have finished
+                const int h = a.order[(t - ns1) / per_head], j = (t - ns1) % per_head;
+                uint32_t r[32];
+                tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * kHidden + j * kBK), r);
+                const float *b1 = a.b1cat + (size_t)g * n1 + h * kHidden + j * kBK;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 b = *reinterpret_cast<const float4 *>(b1 + c * 4);
+                    const float4 v = make_float4(fmaxf(__uint_as_float(r[c * 4]) + b.x, 0.0f), fmaxf(__uint_as_float(r[c * 4 + 1]) + b.y, 0.0f),
+                                                 fmaxf(__uint_as_float(r[c * 4 + 2]) + b.z, 0.0f), fmaxf(__uint_as_float(r[c * 4 + 3]) + b.w, 0.0f));
+                    stage_chunk<3>(a_hi(s), a_lo(s), row, c, v);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(&conv[s]);
+        }
+        // ---- epilogue: bias, row stores (thread = row)
+        mbar_wait(&all_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int m = m0 + row;
+        if (a.epi) {
+            // every thread copies its row of both accumulators into shared memory (odd pitch: conflict-free) and evaluates
+            // the dueling combination and the expectation there -- the 255 head outputs per row never reach HBM
+            float *my = reinterpret_cast<float *>(smem) + (size_t)row * a.rs;
+            for (int h = 0; h < 2; ++h) {
+                const int off = h ? a.npad[0] : 0;
+                for (int c0 = 0; c0 < a.npad[h]; c0 += 16) {
+                    uint32_t r[16];
+                    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + a.d2col[h] + (uint32_t)c0;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) my[off + c0 + j] = __uint_as_float(r[j]);
+                }
+            }
+            const int A = a.A, Z = a.Z;
+            const float *bV = s_b2, *bA = s_b2 + a.npad[0];
+            float *adv = my + a.npad[0];
+            for (int z = 0; z < Z; ++z) {  // v + (adv - mean over actions), kept as c_z = v - mean (dueling of the brains)
+                float sum = 0.0f;
+                for (int k = 0; k < A; ++k) {
+                    const float x = adv[k * Z + z] + bA[k * Z + z];
+                    adv[k * Z + z] = x;
+                    sum += x;
+                }
+                my[z] = (my[z] + bV[z]) - sum / (float)A;
+            }
+            for (int k = 0; k < A; ++k) {
+                float q;
+                if (a.epi == 1) {
+                    float mx = -INFINITY;
+                    for (int z = 0; z < Z; ++z) mx = fmaxf(mx, adv[k * Z + z] + my[z]);
+                    float se = 0.0f, sq = 0.0f;
+                    for (int z = 0; z < Z; ++z) {
+                        const float e = expf((adv[k * Z + z] + my[z]) - mx);
+                        se += e;
+                        sq += e * s_sup[z];
+                    }
+                    q = sq / se;
+                } else {
+                    float sum = 0.0f;
+                    for (int z = 0; z < Z; ++z) sum += adv[k * Z + z] + my[z];
+                    q = sum / (float)Z;
+                }
+                if (m < a.rows) a.q_out[(size_t)g * a.q_g + (size_t)m * A + k] = q;
+            }
+        } else
+        for (int h = 0; h < a.nheads; ++h) {
+            float *orow = a.out[h] + (size_t)g * a.out_g[h] + (size_t)m * a.out_n[h];
+            const float *b2 = a.b2p[h] + (size_t)g * a.npad[h];
+            for (int c0 = 0; c0 < a.npad[h]; c0 += 16) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + a.d2col[h] + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (m < a.rows) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < a.out_n[h]) orow[c0 + j] = __uint_as_float(r[j]) + b2[c0 + j];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// Splits the heads' weights into TF32 hi / lo panels with TMA-friendly strides (rows of din / 128 floats, 16-byte aligned,
+// zero rows up to the padded width) and gathers the biases.  One launch per forward call: ~0.4 MB per agent.
+struct PrepArgs {
+    const float *params;
+    long long P;
+    long long w1[2], b1[2], w2[2], b2[2];
+    int out[2], npad[2], nheads, din;
+    float *w1hi, *w1lo, *w2hi[2], *w2lo[2], *b1cat, *b2p[2];
+};
+__global__ void tc_heads_prepare_kernel(const PrepArgs p) {
+    const int g = blockIdx.y;
+    const float *src = p.params + (size_t)g * p.P;
+    const int n1 = p.nheads * kHidden;
+    const long long w1n = (long long)n1 * p.din;
+    long long total = w1n + n1;
+    for (int h = 0; h < p.nheads; ++h) total += (long long)p.npad[h] * (kHidden + 1);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long j = i;
+        if (j < w1n) {
+            const int r = (int)(j / p.din), k = (int)(j - (long long)r * p.din), h = r / kHidden;
+            const float v = src[p.w1[h] + (long long)(r - h * kHidden) * p.din + k], hi = tf32_rna(v);
+            p.w1hi[(size_t)g * w1n + j] = hi;
+            p.w1lo[(size_t)g * w1n + j] = v - hi;
+            continue;
+        }
+        j -= w1n;
+        if (j < n1) {
+            const int h = (int)j / kHidden;
+            p.b1cat[(size_t)g * n1 + j] = src[p.b1[h] + (j - h * kHidden)];
+            continue;
+        }
+        j -= n1;
+        for (int h = 0; h < p.nheads; ++h) {
+            const long long wn = (long long)p.npad[h] * kHidden;
+            if (j < wn) {
+                const int r = (int)(j / kHidden), k = (int)(j - (long long)r * kHidden);
+                const float v = r < p.out[h] ? src[p.w2[h] + (long long)r * kHidden + k] : 0.0f, hi = tf32_rna(v);
+                p.w2hi[h][(size_t)g * wn + j] = hi;
+                p.w2lo[h][(size_t)g * wn + j] = v - hi;
+                break;
+            }
+            j -= wn;
+            if (j < p.npad[h]) {
+                p.b2p[h][(size_t)g * p.npad[h] + j] = j < p.out[h] ? src[p.b2[h] + j] : 0.0f;
+                break;
+            }
+            j -= p.npad[h];
+        }
+    }
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn encode_fn() {
+    static EncodeFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeFn>(p);
+    }();
+    return fn;
+}
+// fp32 tensor [d2][d1][d0] (d0 contiguous), box = 32 x box_rows x 1, SWIZZLE_128B, zero fill outside
+bool make_map(CUtensorMap *tm, const float *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes,
+              uint32_t box_rows) {
+    EncodeFn fn = encode_fn();
+    if (!fn) return false;
+    const int rank = d2 > 0 ? 3 : 2;
+    cuuint64_t dims[3] = {d0, d1, d2 > 0 ? d2 : 1};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {32, box_rows, 1}, estr[3] = {1, 1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+namespace maexp {
+
+size_t tc_heads_workspace_floats(int G, int nheads, int din, const int *out) {
+    size_t n = 2 * (size_t)G * nheads * kHidden * din + (size_t)G * nheads * kHidden;
+    for (int h = 0; h < nheads; ++h) {
+        const size_t npad = (size_t)(out[h] + 15) / 16 * 16;
+        n += 2 * (size_t)G * npad * kHidden + (size_t)G * npad;
+    }
+    return n + 64;  // 16-byte alignment slack between the panels
+}
+
+bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
+    if (f.nheads < 1 || f.nheads > 2 || f.H != kHidden || f.din < kBK || f.din % kBK || f.rows < 1 || !f.workspace) return false;
+    if ((reinterpret_cast<uintptr_t>(f.x) & 15) || (f.x_row & 3) || (f.x_g & 3)) return false;
+    HeadsArgs a = {};
+    PrepArgs p = {};
+    a.nheads = p.nheads = f.nheads;
+    a.rows = f.rows;
+    a.din = p.din = f.din;
+    for (int h = 0; h < f.nheads; ++h) {
+        a.out_n[h] = p.out[h] = f.out[h];
+        a.npad[h] = p.npad[h] = (f.out[h] + 15) / 16 * 16;
+        if (f.out[h] < 1 || a.npad[h] > 256) return false;
+        a.out[h] = f.outp[h];
+        a.out_g[h] = f.rows_max * f.out[h];
+        p.w1[h] = f.w1[h]; p.b1[h] = f.b1[h]; p.w2[h] = f.w2[h]; p.b2[h] = f.b2[h];
+    }
+    // TMEM plan: first accumulator in columns [0, heads * 128); the widest head's output at column 256, the other one in the
+    // hidden columns of the head processed first (free once its four slabs have been read)
+    if (f.nheads == 2) {
+        const int big = a.npad[1] >= a.npad[0] ? 1 : 0, small = 1 - big;
+        if (a.npad[small] > kHidden) return false;
+        a.order[0] = big; a.order[1] = small;
+        a.d2col[big] = 256;
+        a.d2col[small] = (uint32_t)(big * kHidden);
+    } else {
+        a.order[0] = 0;
+        a.d2col[0] = 256;
+    }
+    // workspace carve-up (16-byte aligned panels)
+    float *w = f.workspace;
+    auto take = [&](size_t n) { float *r = w; w += (n + 3) & ~(size_t)3; return r; };
+    const int n1 = f.nheads * kHidden;
+    p.params = f.params; p.P = f.P;
+    p.w1hi = take((size_t)G * n1 * f.din);
+    p.w1lo = take((size_t)G * n1 * f.din);
+    p.b1cat = take((size_t)G * n1);
+    for (int h = 0; h < f.nheads; ++h) {
+        p.w2hi[h] = take((size_t)G * a.npad[h] * kHidden);
+        p.w2lo[h] = take((size_t)G * a.npad[h] * kHidden);
+        p.b2p[h] = take((size_t)G * a.npad[h]);
+        a.b2p[h] = p.b2p[h];
+    }
+    a.b1cat = p.b1cat;
+    if (reinterpret_cast<uintptr_t>(f.workspace) & 15) return false;
+    bool ok = make_map(&a.tm_x, f.x, (uint64_t)f.din, (uint64_t)f.rows, (uint64_t)G, (uint64_t)f.x_row * 4, (uint64_t)f.x_g * 4, kBM);
+    ok = ok && make_map(&a.tm_w1hi, p.w1hi, (uint64_t)f.din, (uint64_t)G * n1, 0, (uint64_t)f.din * 4, 0, (uint32_t)n1);
+    ok = ok && make_map(&a.tm_w1lo, p.w1lo, (uint64_t)f.din, (uint64_t)G * n1, 0, (uint64_t)f.din * 4, 0, (uint32_t)n1);
+    for (int h = 0; h < f.nheads && ok; ++h) {
+        ok = ok && make_map(&a.tm_w2hi[h], p.w2hi[h], kHidden, (uint64_t)G * a.npad[h], 0, kHidden * 4, 0, (uint32_t)a.npad[h]);
+        ok = ok && make_map(&a.tm_w2lo[h], p.w2lo[h], kHidden, (uint64_t)G * a.npad[h], 0, kHidden * 4, 0, (uint32_t)a.npad[h]);
+    }
+    if (!ok) return false;
+    if (f.q_out && f.nheads == 2 && f.Z >= 1 && f.Z <= 256 && f.out[0] == f.Z && f.out[1] == f.A * f.Z &&
+        a.npad[0] + a.npad[1] <= 512 && (size_t)((a.npad[0] + a.npad[1]) | 1) * kBM * 4 <= (size_t)kStages * kStageBytes) {
+        a.epi = f.categorical ? 1 : 2;
+        a.A = f.A; a.Z = f.Z;
+        a.rs = (a.npad[0] + a.npad[1]) | 1;
+        a.support = f.support;
+        a.q_out = f.q_out;
+        a.q_g = f.q_g;
+    }
+    if (f.fused_q_done) *f.fused_q_done = a.epi != 0;
+    const size_t smem = (size_t)kStages * kStageBytes + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(tc_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+        attr_set = true;
+    }
+    tc_heads_prepare_kernel<<<dim3(64, G), 256, 0, st>>>(p);
+    tc_heads_kernel<<<dim3((f.rows + kBM - 1) / kBM, G), kThreads, smem, st>>>(a);
+    return cudaGetLastError() == cudaSuccess;
+}
+
+}  // namespace maexp

@@ -46,3 +46,15 @@ for e in prof.events():
         agg[e.name[:70]][1] += e.time_range.end - e.time_range.start
 for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
     print(f"{k:72s} n {n:4d}  total {us / 1e3:8.3f} ms  avg {us / n:8.1f} us")
+
+print("---- kernels of one loop_step")
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    t.loop_step()
+    torch.cuda.synchronize()
+agg = collections.defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        agg[e.name[:70]][0] += 1
+        agg[e.name[:70]][1] += e.time_range.end - e.time_range.start
+for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+    print(f"{k:72s} n {n:4d}  total {us / 1e3:8.3f} ms  avg {us / n:8.1f} us")
