@@ -27,6 +27,7 @@
 #include "../../include/maexp_b200.h"
 #include "tc_heads.h"
 #include "tc_mlp.h"
+#include "tc_trunk.h"
 
 namespace maexp {
 int fail(const std::string &msg);  // env.cu
@@ -1409,6 +1410,8 @@ struct maexp_learner {
     bool tc_mlp = false;           // MAEXP_TC_MLP=1: the MLP heads of >= 128-row batches on tcgen05 (csrc/tc_mlp.cu).  Off by default:
                                    // measured SLOWER than the SIMT kernel at B = 256 (45 vs 33 us; profiles/r2_tc_mlp_fwd_*.txt)
     bool tc_heads = true;          // acting batches: both layers of all heads in one TMA-fed tcgen05 kernel (csrc/tc_heads.cu; MAEXP_TC_HEADS=0: GEMM by GEMM)
+    bool tc_trunk = true;          // acting batches: conv2 of the trunk as an implicit GEMM on tcgen05 (csrc/tc_trunk.cu; MAEXP_TC_TRUNK=0: CUDA cores)
+    float *tc_trunk_ws = nullptr;
     float *tc_heads_ws = nullptr;  // its pre-split weight panels
     size_t tc_heads_ws_floats = 0;
     bool fused_trunk = true;       // one-kernel conv trunk for every local-view pass (MAEXP_FUSED_TRUNK=0: layer by layer)
@@ -2132,6 +2135,22 @@ bool trunk_forward_multi(maexp_learner *h, cudaStream_t st, int n, const float *
     const int G = h->G, C = h->C, V = h->V, F1 = h->F1, F2 = h->F2, Hp = h->Hp;
     const long long P = h->P, Bmax = h->B, stride = h->cfg.obs_stride;
     if (!h->fused_trunk || F1 > 32 || F2 > 64 || !(V == 5 || V == 7 || V == 9) || n < 1 || n > 3) return false;
+    // acting / evaluation batches: conv1 + pooling on the CUDA cores, conv2 as an implicit GEMM on the tensor cores
+    if (g_inference_tc && h->use_tc && h->tc_trunk && n == 1 && !train[0] && B >= 2048 && V == 7 && F1 == 32 && F2 == 64) {
+        if (!h->tc_trunk_ws) {
+            float *ws = nullptr;
+            if (lalloc(h, &ws, tc_trunk_workspace_floats(G)) == 0) h->tc_trunk_ws = ws;
+        }
+        if (h->tc_trunk_ws) {
+            TcTrunkFwd t = {};
+            t.obs = obs[0]; t.params = params[0]; t.flat = acts[0]->flat;
+            t.stride = stride; t.g_obs = (long long)B * stride; t.P = P;
+            t.o_c1w = h->o_c1w; t.o_c1b = h->o_c1b; t.o_c2w = h->o_c2w; t.o_c2b = h->o_c2b; t.g_flat = Bmax * h->D;
+            t.B = B; t.C = C; t.V = V; t.F1 = F1; t.F2 = F2;
+            t.workspace = h->tc_trunk_ws;
+            if (tc_trunk_forward(st, G, t)) return true;
+        }
+    }
     // the 32 KB of conv2 weights are staged once per CTA: 16 warps per CTA at the update batch sizes, so that the three
     // forward passes of an update (3 x 128 CTAs of ~69 KB at B = 256, G = 8) are resident together
     const int warps = (B >= 128 && B < 512) ? 16 : B >= 64 ? 8 : 4, pc = (Hp * Hp + 3) / 4 * 4;
@@ -2964,6 +2983,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (const char *fm = getenv("MAEXP_FUSED_MLP")) h->fused_mlp = atoi(fm) != 0;
     if (const char *tm = getenv("MAEXP_TC_MLP")) h->tc_mlp = atoi(tm) != 0;
     if (const char *th = getenv("MAEXP_TC_HEADS")) h->tc_heads = atoi(th) != 0;
+    if (const char *tt = getenv("MAEXP_TC_TRUNK")) h->tc_trunk = atoi(tt) != 0;
     if (const char *bf = getenv("MAEXP_BATCHED_FWD")) h->batched_fwd = atoi(bf) != 0;
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
     h->A = cfg->num_actions; h->H = cfg->hidden; h->F1 = cfg->conv1_channels; h->F2 = cfg->conv2_channels;

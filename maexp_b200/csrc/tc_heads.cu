@@ -30,6 +30,7 @@
 
 #include "tc_common.cuh"
 #include "tc_heads.h"
+#include "tc_tma_host.h"
 
 using namespace maexp_tc;
 
@@ -58,22 +59,6 @@ struct alignas(64) HeadsArgs {
     long long q_g;
 };
 
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_3d(uint32_t dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
@@ -85,18 +70,86 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ uint32_t idesc_tf32(int n) {
-    // D = F32 (bits 4-5 = 1), A and B = TF32 (bits 7-9 and 10-12 = 2), both K-major, N >> 3 in bits 17-22, M >> 4 in bits 24-28
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+// Greedy values of one row from its two accumulators in shared memory (my[0..npadV) = fc_V, adv = fc_A [A][Z], both without
+// bias): dueling combination v + (adv - mean over actions), then the categorical expectation (softmax over the atoms,
+// sum p z) or the mean over the quantiles (get_action of categorical_dqn_brain.py / qr_dqn_brain.py).  TA > 0: the number of
+// actions at compile time -- the per-action chains are independent, which is the only instruction-level parallelism a
+// one-row-per-thread epilogue has.
+template <int TA>
+__device__ __forceinline__ void greedy_values_row(float *my, float *adv, const float *bV, const float *bA, const float *sup, int A_rt,
+                                                  int Z, int categorical, float *q_row, bool store) {
+    const int A = TA ? TA : A_rt;
+    constexpr int NA = TA ? TA : 8;
+    // four interleaved partial sums per action: the expectation sum p z cancels (atoms of both signs), and a single running sum
+    // over the 51 atoms loses ~2.5x more than the tree reduction of dist_q_kernel (measured: 7.6e-6 against 3.0e-6 mean
+    // relative error of the C51 Q-values against the fp32 oracle; tools/exp_tc_accuracy.py)
+    float mx[NA], se[NA][4], sq[NA][4];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        mx[k] = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) se[k][j] = sq[k][j] = 0.0f;
+    }
+    for (int z0 = 0; z0 < Z; z0 += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int z = z0 + j;
+            if (z < Z) {
+                float x[NA], sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < NA; ++k)
+                    if (k < A) { x[k] = adv[k * Z + z] + bA[k * Z + z]; sum += x[k]; }
+                const float c = (my[z] + bV[z]) - sum / (float)A;
+#pragma unroll
+                for (int k = 0; k < NA; ++k)
+                    if (k < A) {
+                        const float d = x[k] + c;
+                        adv[k * Z + z] = d;
+                        mx[k] = fmaxf(mx[k], d);
+                        sq[k][j] += d;  // (mean over the quantiles: the running sums)
+                    }
+            }
+        }
+    }
+    if (categorical) {
+#pragma unroll
+        for (int k = 0; k < NA; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sq[k][j] = 0.0f;
+        for (int z0 = 0; z0 < Z; z0 += 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int z = z0 + j;
+                if (z < Z) {
+                    const float sz = sup[z];
+#pragma unroll
+                    for (int k = 0; k < NA; ++k)
+                        if (k < A) {
+                            const float e = expf(adv[k * Z + z] - mx[k]);
+                            se[k][j] += e;
+                            sq[k][j] += e * sz;
+                        }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+        if (k < A && store) {
+            const float num = (sq[k][0] + sq[k][1]) + (sq[k][2] + sq[k][3]), den = (se[k][0] + se[k][1]) + (se[k][2] + se[k][3]);
+            q_row[k] = categorical ? num / den : num / (float)Z;
+        }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_constant__ HeadsArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full[kStages], conv[kStages], empty[kStages], d1_done, all_done;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_b1[2 * kHidden];
     __shared__ float s_b2[512], s_sup[256];  // fused epilogue: both heads' output biases (padded widths back to back), atom values
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.y, m0 = blockIdx.x * kBM;
+    for (int i = tid; i < a.nheads * kHidden; i += kThreads) s_b1[i] = a.b1cat[(size_t)g * a.nheads * kHidden + i];
     if (a.epi) {
         for (int i = tid; i < a.npad[0] + a.npad[1]; i += kThreads)
             s_b2[i] = i < a.npad[0] ? a.b2p[0][(size_t)g * a.npad[0] + i] : a.b2p[1][(size_t)g * a.npad[1] + i - a.npad[0]];
@@ -156,12 +209,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
                 mbar_wait(&full[s], n & 1);  // the weight slabs (and, in layer 1, the raw x slab) have landed
                 mbar_wait(&conv[s], n & 1);  // the A operand is split and visible to the async proxy
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint32_t d = tmem, idesc = idesc_tf32(n1);
+                uint32_t d = tmem, idesc = idesc_tf32_m128(n1);
                 bool first = t == 0;
                 if (t >= ns1) {
                     const int h = a.order[(t - ns1) / per_head], j = (t - ns1) % per_head;
                     d = tmem + a.d2col[h];
-                    idesc = idesc_tf32(a.npad[h]);
+                    idesc = idesc_tf32_m128(a.npad[h]);
                     first = j == 0;
                 }
                 const uint32_t aA = smem_u32(a_hi(s)), aAlo = smem_u32(a_lo(s)), aW = smem_u32(w_hi(s)), aWlo = smem_u32(w_lo(s));
@@ -201,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
                 const int h = a.order[(t - ns1) / per_head], j = (t - ns1) % per_head;
                 uint32_t r[32];
                 tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * kHidden + j * kBK), r);
-                const float *b1 = a.b1cat + (size_t)g * n1 + h * kHidden + j * kBK;
+                const float *b1 = s_b1 + h * kHidden + j * kBK;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float4 b = *reinterpret_cast<const float4 *>(b1 + c * 4);
@@ -237,37 +290,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
                     for (int j = 0; j < 16; ++j) my[off + c0 + j] = __uint_as_float(r[j]);
                 }
             }
-            const int A = a.A, Z = a.Z;
-            const float *bV = s_b2, *bA = s_b2 + a.npad[0];
-            float *adv = my + a.npad[0];
-            for (int z = 0; z < Z; ++z) {  // v + (adv - mean over actions), kept as c_z = v - mean (dueling of the brains)
-                float sum = 0.0f;
-                for (int k = 0; k < A; ++k) {
-                    const float x = adv[k * Z + z] + bA[k * Z + z];
-                    adv[k * Z + z] = x;
-                    sum += x;
-                }
-                my[z] = (my[z] + bV[z]) - sum / (float)A;
-            }
-            for (int k = 0; k < A; ++k) {
-                float q;
-                if (a.epi == 1) {
-                    float mx = -INFINITY;
-                    for (int z = 0; z < Z; ++z) mx = fmaxf(mx, adv[k * Z + z] + my[z]);
-                    float se = 0.0f, sq = 0.0f;
-                    for (int z = 0; z < Z; ++z) {
-                        const float e = expf((adv[k * Z + z] + my[z]) - mx);
-                        se += e;
-                        sq += e * s_sup[z];
-                    }
-                    q = sq / se;
-                } else {
-                    float sum = 0.0f;
-                    for (int z = 0; z < Z; ++z) sum += adv[k * Z + z] + my[z];
-                    q = sum / (float)Z;
-                }
-                if (m < a.rows) a.q_out[(size_t)g * a.q_g + (size_t)m * A + k] = q;
-            }
+            float *q_row = a.q_out + (size_t)g * a.q_g + (size_t)m * a.A;
+            if (a.A == 4) greedy_values_row<4>(my, my + a.npad[0], s_b2, s_b2 + a.npad[0], s_sup, 4, a.Z, a.epi == 1, q_row, m < a.rows);
+            else if (a.A == 5) greedy_values_row<5>(my, my + a.npad[0], s_b2, s_b2 + a.npad[0], s_sup, 5, a.Z, a.epi == 1, q_row, m < a.rows);
+            else greedy_values_row<0>(my, my + a.npad[0], s_b2, s_b2 + a.npad[0], s_sup, a.A, a.Z, a.epi == 1, q_row, m < a.rows);
         } else
         for (int h = 0; h < a.nheads; ++h) {
             float *orow = a.out[h] + (size_t)g * a.out_g[h] + (size_t)m * a.out_n[h];
@@ -345,33 +371,6 @@ __global__ void tc_heads_prepare_kernel(const PrepArgs p) {
     }
 }
 
-using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeFn encode_fn() {
-    static EncodeFn fn = [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return reinterpret_cast<EncodeFn>(p);
-    }();
-    return fn;
-}
-// fp32 tensor [d2][d1][d0] (d0 contiguous), box = 32 x box_rows x 1, SWIZZLE_128B, zero fill outside
-bool make_map(CUtensorMap *tm, const float *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes,
-              uint32_t box_rows) {
-    EncodeFn fn = encode_fn();
-    if (!fn) return false;
-    const int rank = d2 > 0 ? 3 : 2;
-    cuuint64_t dims[3] = {d0, d1, d2 > 0 ? d2 : 1};
-    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
-    cuuint32_t box[3] = {32, box_rows, 1}, estr[3] = {1, 1, 1};
-    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 }  // namespace
 
 namespace maexp {
@@ -429,15 +428,15 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
     }
     a.b1cat = p.b1cat;
     if (reinterpret_cast<uintptr_t>(f.workspace) & 15) return false;
-    bool ok = make_map(&a.tm_x, f.x, (uint64_t)f.din, (uint64_t)f.rows, (uint64_t)G, (uint64_t)f.x_row * 4, (uint64_t)f.x_g * 4, kBM);
-    ok = ok && make_map(&a.tm_w1hi, p.w1hi, (uint64_t)f.din, (uint64_t)G * n1, 0, (uint64_t)f.din * 4, 0, (uint32_t)n1);
-    ok = ok && make_map(&a.tm_w1lo, p.w1lo, (uint64_t)f.din, (uint64_t)G * n1, 0, (uint64_t)f.din * 4, 0, (uint32_t)n1);
+    bool ok = make_map_f32(&a.tm_x, f.x, (uint64_t)f.din, (uint64_t)f.rows, (uint64_t)G, (uint64_t)f.x_row * 4, (uint64_t)f.x_g * 4, kBM);
+    ok = ok && make_map_f32(&a.tm_w1hi, p.w1hi, (uint64_t)f.din, (uint64_t)G * n1, 0, (uint64_t)f.din * 4, 0, (uint32_t)n1);
+    ok = ok && make_map_f32(&a.tm_w1lo, p.w1lo, (uint64_t)f.din, (uint64_t)G * n1, 0, (uint64_t)f.din * 4, 0, (uint32_t)n1);
     for (int h = 0; h < f.nheads && ok; ++h) {
-        ok = ok && make_map(&a.tm_w2hi[h], p.w2hi[h], kHidden, (uint64_t)G * a.npad[h], 0, kHidden * 4, 0, (uint32_t)a.npad[h]);
-        ok = ok && make_map(&a.tm_w2lo[h], p.w2lo[h], kHidden, (uint64_t)G * a.npad[h], 0, kHidden * 4, 0, (uint32_t)a.npad[h]);
+        ok = ok && make_map_f32(&a.tm_w2hi[h], p.w2hi[h], kHidden, (uint64_t)G * a.npad[h], 0, kHidden * 4, 0, (uint32_t)a.npad[h]);
+        ok = ok && make_map_f32(&a.tm_w2lo[h], p.w2lo[h], kHidden, (uint64_t)G * a.npad[h], 0, kHidden * 4, 0, (uint32_t)a.npad[h]);
     }
     if (!ok) return false;
-    if (f.q_out && f.nheads == 2 && f.Z >= 1 && f.Z <= 256 && f.out[0] == f.Z && f.out[1] == f.A * f.Z &&
+    if (f.q_out && f.nheads == 2 && f.A >= 1 && f.A <= 8 && f.Z >= 1 && f.Z <= 256 && f.out[0] == f.Z && f.out[1] == f.A * f.Z &&
         a.npad[0] + a.npad[1] <= 512 && (size_t)((a.npad[0] + a.npad[1]) | 1) * kBM * 4 <= (size_t)kStages * kStageBytes) {
         a.epi = f.categorical ? 1 : 2;
         a.A = f.A; a.Z = f.Z;
