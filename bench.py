@@ -363,15 +363,42 @@ def run_ours(args, rank, local_rank, world):
     dp_check = None
     if dist is not None:
         dp_check = data_parallel_check(torch, dist, group, ring, batch, cfg, env, world, dev)
+    # ---- training-loop leg: what a real run of DefaultTrainer does per tick (abstract_trainer.py:63-89) -- replay sample + C51
+    #      update, refresh of the acting weights, epsilon-greedy policy inference for ALL environments (conv trunk with conv2 on
+    #      tcgen05 + TMA-fed MLP heads with the fused expectation epilogue), env step with those actions into the next ring slot
+    from maexp_b200.core.agents import BatchedActor
+    actor = BatchedActor(cfg, env, group)
+    loop_tick = [tick]
+
+    def loop_step(t):
+        ring.sample(batch, seed=921, tick=t)
+        graphed.step()
+        actor.refresh()
+        actions = actor.act(ring.obs[ring.head], 0.1, loop_tick[0])
+        env.step(ring.next_outputs(), actions=actions, tick=loop_tick[0])
+        ring.commit()
+        loop_tick[0] += 1
+
+    for t in range(3):
+        loop_step(500 + t)
+    kl = max(5, min(K, 50))
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0.record()
+    for t in range(kl):
+        loop_step(600 + t)
+    l1.record()
+    barrier()
+    loop_ms = l0.elapsed_time(l1)
     sampler.window[1] = time.perf_counter()
     sampler.stop()
 
-    vals = [ms, e2e_s, upd_ms]
+    vals = [ms, e2e_s, upd_ms, loop_ms]
     sums = [float(env_steps), float(e2e_steps)]
     if dist is not None:
         vals = mdist.max_over_ranks(dist, vals, dev)
         sums = mdist.sum_over_ranks(dist, sums, dev)
-    ms, e2e_s, upd_ms = vals
+    ms, e2e_s, upd_ms, loop_ms = vals
     env_steps, e2e_steps = sums
     if rank == 0:
         value = env_steps * N / (ms * 1e-3)
@@ -413,6 +440,11 @@ def run_ours(args, rank, local_rank, world):
                                 + "all 8 agents' networks in grouped launches",
                         "collective": None if world == 1 else ("fused NVLink peer kernel" if graphed.peers is not None else "nccl"),
                         "roofline": learner_roofline(learner_flop, upd_s)},
+            "training_loop": {"metric": "agent_steps_per_sec_in_training_loop", "unit": UNIT,
+                              "value": world * E * N * kl / (loop_ms * 1e-3), "ms_per_loop_step": loop_ms / kl, "steps": kl,
+                              "note": "per tick: replay sample + C51 team update + acting-weight refresh + epsilon-greedy policy "
+                                      "inference for all envs (tc_trunk_kernel + tc_heads_kernel: tcgen05 / TMA, 3 x TF32) + env step "
+                                      "with those actions; CUDA events, max over ranks"},
         }
         if dp_check is not None:
             line["learner"].update(dp_check)

@@ -1407,8 +1407,11 @@ struct maexp_learner {
     bool use_tc = true;  // tensor-core GEMMs for large inference batches (MAEXP_TC=0 turns them off)
     bool batched_fwd = false;      // all forward passes of an update as slices of one launch (MAEXP_BATCHED_FWD=1; measured slower than one stream each: 263 vs 234 us)
     bool fused_mlp = true;         // one-kernel MLP heads for the update batches (MAEXP_FUSED_MLP=0: GEMM by GEMM)
-    bool tc_mlp = false;           // MAEXP_TC_MLP=1: the MLP heads of >= 128-row batches on tcgen05 (csrc/tc_mlp.cu).  Off by default:
-                                   // measured SLOWER than the SIMT kernel at B = 256 (45 vs 33 us; profiles/r2_tc_mlp_fwd_*.txt)
+    bool tc_mlp = true;            // the MLP heads of >= 128-row update batches on tcgen05 (csrc/tc_mlp.cu; MAEXP_TC_MLP=0: the SIMT kernel).
+                                   // First measured slower than the SIMT kernel (45 vs 33 us at B = 256; profiles/r2_tc_mlp_fwd_*.txt): its
+                                   // operand staging went through GENERIC stores (the 1024-byte alignment of the dynamic shared memory was
+                                   // computed through uintptr_t, which loses the address space).  With shared-space stores: C51 team update
+                                   // 239 -> 224 us
     bool tc_heads = true;          // acting batches: both layers of all heads in one TMA-fed tcgen05 kernel (csrc/tc_heads.cu; MAEXP_TC_HEADS=0: GEMM by GEMM)
     bool tc_trunk = true;          // acting batches: conv2 of the trunk as an implicit GEMM on tcgen05 (csrc/tc_trunk.cu; MAEXP_TC_TRUNK=0: CUDA cores)
     float *tc_trunk_ws = nullptr;
@@ -2327,7 +2330,8 @@ bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const flo
     const long long P = h->P;
     // update batches of >= 128 rows: both layers on the tensor cores (tcgen05, three TF32 terms per product), the hidden
     // activation handed from the first accumulator to the second contraction inside the SM (csrc/tc_mlp.cu)
-    if (h->tc_mlp && in.rows >= 128 && H <= 128 && (H & 3) == 0) {
+    // (not IQN: its quantile-Huber gradients amplify the 2e-6 of the three-term TF32 products past the 1e-4 gradient bar)
+    if (h->tc_mlp && !h->iqn && in.rows >= 128 && H <= 128 && (H & 3) == 0) {
         bool ok = true;
         for (int q = 0; q < n && ok; ++q) {
             TcMlpFwd t = {};

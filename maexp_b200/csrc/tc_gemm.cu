@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const TcArgs a) {
     const int m0 = blockIdx.x * kBM;
     const float *A = a.A + (size_t)g * a.gA, *W = a.W + (size_t)g * a.gW + (size_t)nt0 * a.ldw;
     const uint32_t a_bytes = kBM * 128, w_bytes = (uint32_t)npad * 128;
-    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t *sA = smem, *sAlo = sA + a_bytes;
     uint8_t *sW = sA + (SPLIT == 3 ? 2 : 1) * a_bytes, *sWlo = sW + w_bytes;
     uint32_t ncols = 32;

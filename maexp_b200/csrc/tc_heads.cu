@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
             s_b2[i] = i < a.npad[0] ? a.b2p[0][(size_t)g * a.npad[0] + i] : a.b2p[1][(size_t)g * a.npad[1] + i - a.npad[0]];
         for (int i = tid; i < a.Z; i += kThreads) s_sup[i] = a.support ? a.support[i] : 0.0f;
     }
-    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     auto a_hi = [&](int s) { return smem + (size_t)s * kStageBytes; };
     auto a_lo = [&](int s) { return smem + (size_t)s * kStageBytes + kATile; };
     auto w_hi = [&](int s) { return smem + (size_t)s * kStageBytes + 2 * kATile; };

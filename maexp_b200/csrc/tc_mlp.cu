@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const maexp::Tc
                 *B2 = Wg + a.b2[head];
     float *hout = a.hbuf[head] ? a.hbuf[head] + (size_t)g * a.rows_max * H : nullptr;
     float *out = a.outp[head] + (size_t)g * a.rows_max * O;
-    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     constexpr uint32_t kBufBytes = 2 * kBM * 128 + 2 * 256 * 128;  // A hi | A lo | W hi | W lo
     auto bufA = [&](int b) { return smem + (size_t)b * kBufBytes; };
     auto bufAlo = [&](int b) { return bufA(b) + kBM * 128; };

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_trunk_kernel(const __grid_cons
     __shared__ float s_b1[kF1], s_b2[kF2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = blockIdx.y;
     const int C = TC ? TC : a.C, K1 = C * 4;
-    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t *a_hi = smem, *a_lo = smem + kSlabs * kASlab;
     uint8_t *w_hi = smem + 2 * kSlabs * kASlab, *w_lo = w_hi + kSlabs * kWSlab;
     float *w1t = reinterpret_cast<float *>(w_lo + kSlabs * kWSlab);  // [K1][32] conv1 weight, k-major

@@ -58,3 +58,13 @@ for e in prof.events():
         agg[e.name[:70]][1] += e.time_range.end - e.time_range.start
 for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
     print(f"{k:72s} n {n:4d}  total {us / 1e3:8.3f} ms  avg {us / n:8.1f} us")
+
+print("---- host profile of 20 loop steps")
+import cProfile, pstats
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(20):
+    t.loop_step()
+torch.cuda.synchronize()
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
