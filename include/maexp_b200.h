@@ -427,7 +427,8 @@ int maexp_decode_relative(const float *obs, const int8_t *positions, float *canv
 /* heatmap_observation of DefaultEnvironment (default_environment.py:93,238-247), summed over the environments of one
  * step: heat[n][k] += sum_e obs[e*env_stride + n*agent_stride + k] for k < elems, skipping environments with skip[e] != 0
  * (pass maexp_obs_out.was_reset: a reset observation is not counted by the reference).  obs is a slot the step wrote
- * (local view: elems = C*V*V, env_stride = N*slot_floats, agent_stride = slot_floats) or the canvas maexp_decode_relative
+ * (local view: elems = C*V*V; ring slots are AGENT-major [N, E, slot_floats], so env_stride = slot_floats and
+ * agent_stride = E*slot_floats) or the canvas maexp_decode_relative
  * made of it (relative / merged views: elems = C*X*Y).  heat: fp32 [N, elems], accumulated, zeroed by the caller. */
 int maexp_heatmap_observation_add(const float *obs, int64_t num_envs, int num_agents, int elems, int64_t env_stride,
                                   int64_t agent_stride, const uint8_t *skip, float *heat, void *stream);

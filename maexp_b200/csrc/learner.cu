@@ -1417,6 +1417,9 @@ struct maexp_learner {
     float *tc_trunk_ws = nullptr;
     float *tc_heads_ws = nullptr;  // its pre-split weight panels
     size_t tc_heads_ws_floats = 0;
+    // the same kernel for the forward passes of an update (online(s), online(s'), target(s') run concurrently on their own
+    // streams): one panel buffer per pass, keyed by the pass's output buffer
+    struct { const float *key; float *ws; size_t floats; } tc_heads_upd[4] = {};
     bool fused_trunk = true;       // one-kernel conv trunk for every local-view pass (MAEXP_FUSED_TRUNK=0: layer by layer)
     const float *bwd_obs = nullptr;  // observations of the last training pass (conv1's im2col in trunk_backward)
     float *trunk_part = nullptr;      // block partials of trunk_fused_bwd_kernel
@@ -2331,6 +2334,37 @@ bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const flo
     // update batches of >= 128 rows: both layers on the tensor cores (tcgen05, three TF32 terms per product), the hidden
     // activation handed from the first accumulator to the second contraction inside the SM (csrc/tc_mlp.cu)
     // (not IQN: its quantile-Huber gradients amplify the 2e-6 of the three-term TF32 products past the 1e-4 gradient bar)
+    if (h->tc_mlp && h->tc_heads && !h->iqn && !g_inference_tc && in.rows >= 128 && H == 128 && in.din >= 32 && in.din % 32 == 0) {
+        // TMA-fed kernel, all heads of a pass in one CTA per 128-row tile (csrc/tc_heads.cu)
+        bool ok = true;
+        for (int q = 0; q < n && ok; ++q) {
+            int outs_n[2] = {hds[0].out, nheads > 1 ? hds[1].out : 0};
+            const size_t need = tc_heads_workspace_floats(h->G, nheads, in.din, outs_n);
+            int slot = -1;
+            for (int k = 0; k < 4 && slot < 0; ++k)
+                if (h->tc_heads_upd[k].key == outs[q][0] || !h->tc_heads_upd[k].key) slot = k;
+            if (slot < 0) { ok = false; break; }
+            auto &e = h->tc_heads_upd[slot];
+            if (e.floats < need) {
+                float *ws = nullptr;
+                if (lalloc(h, &ws, need)) { ok = false; break; }
+                e.ws = ws; e.floats = need;
+            }
+            e.key = outs[q][0];
+            TcHeadsFwd t = {};
+            t.x = ins[q].x; t.x_row = ins[q].x_row; t.x_g = ins[q].x_g;
+            t.params = params[q]; t.P = P;
+            t.nheads = nheads;
+            for (int k = 0; k < nheads; ++k) {
+                t.w1[k] = hds[k].w1; t.b1[k] = hds[k].b1; t.w2[k] = hds[k].w2; t.b2[k] = hds[k].b2; t.out[k] = hds[k].out;
+                t.outp[k] = outs[q][k]; t.hbuf[k] = hbufs[q][k];
+            }
+            t.rows = ins[q].rows; t.rows_max = ins[q].rows_max; t.din = ins[q].din; t.H = H;
+            t.workspace = e.ws;
+            ok = tc_heads_forward(st, h->G, t);
+        }
+        if (ok) return true;
+    }
     if (h->tc_mlp && !h->iqn && in.rows >= 128 && H <= 128 && (H & 3) == 0) {
         bool ok = true;
         for (int q = 0; q < n && ok; ++q) {

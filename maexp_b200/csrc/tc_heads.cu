@@ -26,6 +26,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "tc_common.cuh"
@@ -36,7 +37,7 @@ using namespace maexp_tc;
 
 namespace {
 
-constexpr int kThreads = 192, kStages = 2, kHidden = 128;
+constexpr int kThreads = 320, kStages = 2, kHidden = 128;  // producer, MMA issuer, 4 operand warps, 4 more epilogue warps
 constexpr uint32_t kATile = kBM * 128;          // 16 KB: 128 rows x 32 floats
 constexpr uint32_t kWTile = 256 * 128;          // 32 KB: up to 256 rows x 32 floats
 constexpr uint32_t kStageBytes = 2 * kATile + 2 * kWTile;
@@ -47,6 +48,8 @@ struct alignas(64) HeadsArgs {
     const float *b2p[2];  // [G][npad_k], zero padded
     float *out[2];
     long long out_g[2];
+    float *hbuf[2];       // training pass: relu(x W1^T + b1) of every head, [G][.][128] (group pitch hbuf_g), or nullptr
+    long long hbuf_g;
     int out_n[2], npad[2];
     int order[2];         // heads in the order their second layer runs
     uint32_t d2col[2];    // TMEM column of every head's output accumulator
@@ -57,6 +60,7 @@ struct alignas(64) HeadsArgs {
     const float *support; // [Z] atom values (epi 1)
     float *q_out;         // [G][rows][A]
     long long q_g;
+    long long *dbg;       // MAEXP_TC_HEADS_DBG: cycle counts of CTA (0, 0) per role and phase
 };
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -70,74 +74,77 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the eight epilogue warps
+__device__ __forceinline__ float fast_exp(float x) {  // x <= 0: one MUFU; the terms that matter (x near 0) are good to ~1e-7
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
 // Greedy values of one row from its two accumulators in shared memory (my[0..npadV) = fc_V, adv = fc_A [A][Z], both without
 // bias): dueling combination v + (adv - mean over actions), then the categorical expectation (softmax over the atoms,
-// sum p z) or the mean over the quantiles (get_action of categorical_dqn_brain.py / qr_dqn_brain.py).  TA > 0: the number of
-// actions at compile time -- the per-action chains are independent, which is the only instruction-level parallelism a
-// one-row-per-thread epilogue has.
+// sum p z) or the mean over the quantiles (get_action of categorical_dqn_brain.py / qr_dqn_brain.py).  TWO threads per row
+// (half = 0 / 1, in different warps): the dueling pass is split over the atoms, the expectation over the actions (half, half
+// + 2, ...), epi_bar() in between.  TA > 0: the number of actions at compile time -- the per-action chains are the only
+// instruction-level parallelism a row has.  Four interleaved partial sums per action: the expectation sum p z cancels (atoms
+// of both signs), and a single running sum over the 51 atoms loses ~2.5x more than the tree reduction of dist_q_kernel
+// (7.6e-6 against 3.0e-6 mean relative error of the C51 Q-values against the fp32 oracle; tools/exp_tc_accuracy.py).
 template <int TA>
 __device__ __forceinline__ void greedy_values_row(float *my, float *adv, const float *bV, const float *bA, const float *sup, int A_rt,
-                                                  int Z, int categorical, float *q_row, bool store) {
+                                                  int Z, int categorical, float *q_row, bool store, int half) {
     const int A = TA ? TA : A_rt;
-    constexpr int NA = TA ? TA : 8;
-    // four interleaved partial sums per action: the expectation sum p z cancels (atoms of both signs), and a single running sum
-    // over the 51 atoms loses ~2.5x more than the tree reduction of dist_q_kernel (measured: 7.6e-6 against 3.0e-6 mean
-    // relative error of the C51 Q-values against the fp32 oracle; tools/exp_tc_accuracy.py)
-    float mx[NA], se[NA][4], sq[NA][4];
+    constexpr int NA = TA ? TA : 8, NH = (NA + 1) / 2;
+    const int zh = (Z + 1) / 2, z_lo = half * zh, z_hi = min(Z, z_lo + zh);
+    for (int z = z_lo; z < z_hi; ++z) {
+        float x[NA], sum = 0.0f;
 #pragma unroll
-    for (int k = 0; k < NA; ++k) {
-        mx[k] = -INFINITY;
+        for (int k = 0; k < NA; ++k)
+            if (k < A) { x[k] = adv[k * Z + z] + bA[k * Z + z]; sum += x[k]; }
+        const float c = (my[z] + bV[z]) - sum / (float)A;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) se[k][j] = sq[k][j] = 0.0f;
+        for (int k = 0; k < NA; ++k)
+            if (k < A) adv[k * Z + z] = x[k] + c;
+    }
+    epi_bar();
+    float mx[NH], se[NH][4], sq[NH][4];
+#pragma unroll
+    for (int i = 0; i < NH; ++i) {
+        mx[i] = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) se[i][j] = sq[i][j] = 0.0f;
+    }
+    if (categorical) {
+        for (int z = 0; z < Z; ++z) {
+#pragma unroll
+            for (int i = 0; i < NH; ++i)
+                if (half + 2 * i < A) mx[i] = fmaxf(mx[i], adv[(half + 2 * i) * Z + z]);
+        }
     }
     for (int z0 = 0; z0 < Z; z0 += 4) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int z = z0 + j;
             if (z < Z) {
-                float x[NA], sum = 0.0f;
+                const float sz = sup[z];
 #pragma unroll
-                for (int k = 0; k < NA; ++k)
-                    if (k < A) { x[k] = adv[k * Z + z] + bA[k * Z + z]; sum += x[k]; }
-                const float c = (my[z] + bV[z]) - sum / (float)A;
-#pragma unroll
-                for (int k = 0; k < NA; ++k)
-                    if (k < A) {
-                        const float d = x[k] + c;
-                        adv[k * Z + z] = d;
-                        mx[k] = fmaxf(mx[k], d);
-                        sq[k][j] += d;  // (mean over the quantiles: the running sums)
+                for (int i = 0; i < NH; ++i)
+                    if (half + 2 * i < A) {
+                        const float d = adv[(half + 2 * i) * Z + z];
+                        if (categorical) {
+                            const float e = fast_exp(d - mx[i]);
+                            se[i][j] += e;
+                            sq[i][j] += e * sz;
+                        } else {
+                            sq[i][j] += d;
+                        }
                     }
             }
         }
     }
-    if (categorical) {
 #pragma unroll
-        for (int k = 0; k < NA; ++k)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sq[k][j] = 0.0f;
-        for (int z0 = 0; z0 < Z; z0 += 4) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int z = z0 + j;
-                if (z < Z) {
-                    const float sz = sup[z];
-#pragma unroll
-                    for (int k = 0; k < NA; ++k)
-                        if (k < A) {
-                            const float e = expf(adv[k * Z + z] - mx[k]);
-                            se[k][j] += e;
-                            sq[k][j] += e * sz;
-                        }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < NA; ++k)
-        if (k < A && store) {
-            const float num = (sq[k][0] + sq[k][1]) + (sq[k][2] + sq[k][3]), den = (se[k][0] + se[k][1]) + (se[k][2] + se[k][3]);
-            q_row[k] = categorical ? num / den : num / (float)Z;
+    for (int i = 0; i < NH; ++i)
+        if (half + 2 * i < A && store) {
+            const float num = (sq[i][0] + sq[i][1]) + (sq[i][2] + sq[i][3]), den = (se[i][0] + se[i][1]) + (se[i][2] + se[i][3]);
+            q_row[half + 2 * i] = categorical ? num / den : num / (float)Z;
         }
 }
 
@@ -150,11 +157,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.y, m0 = blockIdx.x * kBM;
     for (int i = tid; i < a.nheads * kHidden; i += kThreads) s_b1[i] = a.b1cat[(size_t)g * a.nheads * kHidden + i];
-    if (a.epi) {
-        for (int i = tid; i < a.npad[0] + a.npad[1]; i += kThreads)
-            s_b2[i] = i < a.npad[0] ? a.b2p[0][(size_t)g * a.npad[0] + i] : a.b2p[1][(size_t)g * a.npad[1] + i - a.npad[0]];
+    for (int i = tid; i < a.npad[0] + (a.nheads > 1 ? a.npad[1] : 0); i += kThreads)
+        s_b2[i] = i < a.npad[0] ? a.b2p[0][(size_t)g * a.npad[0] + i] : a.b2p[1][(size_t)g * a.npad[1] + i - a.npad[0]];
+    if (a.epi)
         for (int i = tid; i < a.Z; i += kThreads) s_sup[i] = a.support ? a.support[i] : 0.0f;
-    }
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     auto a_hi = [&](int s) { return smem + (size_t)s * kStageBytes; };
     auto a_lo = [&](int s) { return smem + (size_t)s * kStageBytes + kATile; };
@@ -187,7 +193,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
         if (lane == 0) {
             for (int t = 0; t < T; ++t) {
                 const int s = t % kStages, n = t / kStages;
+                const long long c0 = clock64();
                 if (t >= kStages) mbar_wait(&empty[s], (n - 1) & 1);
+                if (a.dbg && blockIdx.x == 0 && g == 0) a.dbg[t] = clock64() - c0;  // producer: wait for the stage
                 if (t < ns1) {
                     mbar_expect_tx(&full[s], kATile + 2u * (uint32_t)n1 * 128u);
                     tma_3d(smem_u32(a_hi(s)), &a.tm_x, &full[s], t * kBK, m0, g);
@@ -206,8 +214,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
         if (lane == 0) {
             for (int t = 0; t < T; ++t) {
                 const int s = t % kStages, n = t / kStages;
+                const long long c0 = clock64();
                 mbar_wait(&full[s], n & 1);  // the weight slabs (and, in layer 1, the raw x slab) have landed
+                const long long c1 = clock64();
                 mbar_wait(&conv[s], n & 1);  // the A operand is split and visible to the async proxy
+                if (a.dbg && blockIdx.x == 0 && g == 0) { a.dbg[32 + t] = c1 - c0; a.dbg[64 + t] = clock64() - c1; a.dbg[96 + t] = c0; }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t d = tmem, idesc = idesc_tf32_m128(n1);
                 bool first = t == 0;
@@ -231,9 +242,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
             }
         }
     } else {
-        // ------------------------------------------------------------------ operand conversion + epilogue (128 threads)
-        const int ct = tid - 64, quad = warp & 3, row = quad * 32 + lane;  // a warp reads the TMEM lane quadrant warp % 4
-        for (int t = 0; t < T; ++t) {
+        // ------------------------------------------------------------------ operand conversion (warps 2-5) + epilogue (warps 2-9)
+        const int ct = (tid - 64) & 127, quad = warp & 3, row = quad * 32 + lane;  // a warp reads the TMEM lane quadrant warp % 4
+        const int half = warp >= 6;  // second thread of the row in the epilogue
+        for (int t = 0; t < (half ? 0 : T); ++t) {
             const int s = t % kStages, n = t / kStages;
             if (t < ns1) {
                 mbar_wait(&full[s], n & 1);
@@ -261,6 +273,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
                     const float4 v = make_float4(fmaxf(__uint_as_float(r[c * 4]) + b.x, 0.0f), fmaxf(__uint_as_float(r[c * 4 + 1]) + b.y, 0.0f),
                                                  fmaxf(__uint_as_float(r[c * 4 + 2]) + b.z, 0.0f), fmaxf(__uint_as_float(r[c * 4 + 3]) + b.w, 0.0f));
                     stage_chunk<3>(a_hi(s), a_lo(s), row, c, v);
+                    if (a.hbuf[h] && m0 + row < a.rows)  // the backward pass and its ReLU mask read the hidden activation
+                        *reinterpret_cast<float4 *>(a.hbuf[h] + (size_t)g * a.hbuf_g + (size_t)(m0 + row) * kHidden + j * kBK + c * 4) = v;
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             }
@@ -268,53 +282,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
             mbar_arrive(&conv[s]);
         }
         // ---- epilogue: bias, row stores (thread = row)
+        const long long e0 = clock64();
         mbar_wait(&all_done, 0);
+        if (a.dbg && blockIdx.x == 0 && g == 0 && tid == 64) { a.dbg[128] = clock64() - e0; a.dbg[129] = clock64(); }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int m = m0 + row;
-        if (a.epi) {
-            // every thread copies its row of both accumulators into shared memory (odd pitch: conflict-free) and evaluates
-            // the dueling combination and the expectation there -- the 255 head outputs per row never reach HBM
-            float *my = reinterpret_cast<float *>(smem) + (size_t)row * a.rs;
-            for (int h = 0; h < 2; ++h) {
-                const int off = h ? a.npad[0] : 0;
-                for (int c0 = 0; c0 < a.npad[h]; c0 += 16) {
-                    uint32_t r[16];
-                    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + a.d2col[h] + (uint32_t)c0;
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) my[off + c0 + j] = __uint_as_float(r[j]);
-                }
-            }
-            float *q_row = a.q_out + (size_t)g * a.q_g + (size_t)m * a.A;
-            if (a.A == 4) greedy_values_row<4>(my, my + a.npad[0], s_b2, s_b2 + a.npad[0], s_sup, 4, a.Z, a.epi == 1, q_row, m < a.rows);
-            else if (a.A == 5) greedy_values_row<5>(my, my + a.npad[0], s_b2, s_b2 + a.npad[0], s_sup, 5, a.Z, a.epi == 1, q_row, m < a.rows);
-            else greedy_values_row<0>(my, my + a.npad[0], s_b2, s_b2 + a.npad[0], s_sup, a.A, a.Z, a.epi == 1, q_row, m < a.rows);
-        } else
+        // every row's accumulators go to shared memory first (odd pitch: conflict-free for row-per-thread access); the two
+        // threads of a row take alternate 16-column groups
+        float *s_acc = reinterpret_cast<float *>(smem);
+        float *my = s_acc + (size_t)row * a.rs;
         for (int h = 0; h < a.nheads; ++h) {
-            float *orow = a.out[h] + (size_t)g * a.out_g[h] + (size_t)m * a.out_n[h];
-            const float *b2 = a.b2p[h] + (size_t)g * a.npad[h];
-            for (int c0 = 0; c0 < a.npad[h]; c0 += 16) {
+            const int off = h ? a.npad[0] : 0;
+            for (int c0 = half * 16; c0 < a.npad[h]; c0 += 32) {
                 uint32_t r[16];
-                const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + a.d2col[h] + (uint32_t)c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (m < a.rows) {
+                tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + a.d2col[h] + (uint32_t)c0, r);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < a.out_n[h]) orow[c0 + j] = __uint_as_float(r[j]) + b2[c0 + j];
-                }
+                for (int j = 0; j < 16; ++j) my[off + c0 + j] = __uint_as_float(r[j]);
+            }
+        }
+        epi_bar();
+        if (a.epi) {
+            // dueling combination + expectation in shared memory: the 255 head outputs per row never reach HBM
+            float *q_row = a.q_out + (size_t)g * a.q_g + (size_t)m * a.A;
+            if (a.A == 4) greedy_values_row<4>(my, my + a.npad[0], s_b2, s_b2 + a.npad[0], s_sup, 4, a.Z, a.epi == 1, q_row, m < a.rows, half);
+            else if (a.A == 5) greedy_values_row<5>(my, my + a.npad[0], s_b2, s_b2 + a.npad[0], s_sup, 5, a.Z, a.epi == 1, q_row, m < a.rows, half);
+            else greedy_values_row<0>(my, my + a.npad[0], s_b2, s_b2 + a.npad[0], s_sup, a.A, a.Z, a.epi == 1, q_row, m < a.rows, half);
+        } else {
+            // raw head outputs: a warp per row, lanes along the columns -> coalesced row stores
+            const int ew = warp - 2;
+            for (int h = 0; h < a.nheads; ++h) {
+                const int off = h ? a.npad[0] : 0, on = a.out_n[h];
+                float *obase = a.out[h] + (size_t)g * a.out_g[h];
+                for (int r = ew; r < kBM && m0 + r < a.rows; r += 8)
+                    for (int c = lane; c < on; c += 32) obase[(size_t)(m0 + r) * on + c] = s_acc[(size_t)r * a.rs + off + c] + s_b2[off + c];
             }
         }
     }
+    if (a.dbg && blockIdx.x == 0 && g == 0 && tid == 64) a.dbg[130] = clock64();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -391,6 +395,7 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
     PrepArgs p = {};
     a.nheads = p.nheads = f.nheads;
     a.rows = f.rows;
+    a.hbuf_g = f.rows_max * kHidden;
     a.din = p.din = f.din;
     for (int h = 0; h < f.nheads; ++h) {
         a.out_n[h] = p.out[h] = f.out[h];
@@ -398,6 +403,8 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
         if (f.out[h] < 1 || a.npad[h] > 256) return false;
         a.out[h] = f.outp[h];
         a.out_g[h] = f.rows_max * f.out[h];
+        a.hbuf[h] = f.hbuf[h];
+        if (f.hbuf[h] && (reinterpret_cast<uintptr_t>(f.hbuf[h]) & 15)) return false;
         p.w1[h] = f.w1[h]; p.b1[h] = f.b1[h]; p.w2[h] = f.w2[h]; p.b2[h] = f.b2[h];
     }
     // TMEM plan: first accumulator in columns [0, heads * 128); the widest head's output at column 256, the other one in the
@@ -436,16 +443,21 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
         ok = ok && make_map_f32(&a.tm_w2lo[h], p.w2lo[h], kHidden, (uint64_t)G * a.npad[h], 0, kHidden * 4, 0, (uint32_t)a.npad[h]);
     }
     if (!ok) return false;
-    if (f.q_out && f.nheads == 2 && f.A >= 1 && f.A <= 8 && f.Z >= 1 && f.Z <= 256 && f.out[0] == f.Z && f.out[1] == f.A * f.Z &&
-        a.npad[0] + a.npad[1] <= 512 && (size_t)((a.npad[0] + a.npad[1]) | 1) * kBM * 4 <= (size_t)kStages * kStageBytes) {
+    a.rs = (a.npad[0] + (f.nheads > 1 ? a.npad[1] : 0)) | 1;  // the epilogue's shared-memory copy of the accumulators
+    if ((size_t)a.rs * kBM * 4 > (size_t)kStages * kStageBytes || a.rs > 512) return false;
+    if (f.q_out && f.nheads == 2 && f.A >= 1 && f.A <= 8 && f.Z >= 1 && f.Z <= 256 && f.out[0] == f.Z && f.out[1] == f.A * f.Z) {
         a.epi = f.categorical ? 1 : 2;
         a.A = f.A; a.Z = f.Z;
-        a.rs = (a.npad[0] + a.npad[1]) | 1;
         a.support = f.support;
         a.q_out = f.q_out;
         a.q_g = f.q_g;
     }
     if (f.fused_q_done) *f.fused_q_done = a.epi != 0;
+    static long long *dbg_buf = nullptr;
+    if (getenv("MAEXP_TC_HEADS_DBG")) {
+        if (!dbg_buf) { cudaMalloc(&dbg_buf, 256 * sizeof(long long)); cudaMemset(dbg_buf, 0, 256 * sizeof(long long)); }
+        a.dbg = dbg_buf;
+    }
     const size_t smem = (size_t)kStages * kStageBytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
@@ -454,6 +466,16 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
     }
     tc_heads_prepare_kernel<<<dim3(64, G), 256, 0, st>>>(p);
     tc_heads_kernel<<<dim3((f.rows + kBM - 1) / kBM, G), kThreads, smem, st>>>(a);
+    if (a.dbg) {
+        long long host[256];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
+        const int T = f.din / kBK + 4 * f.nheads;
+        fprintf(stderr, "tc_heads CTA(0,0) cycles, %d slabs: slab | producer waits empty | MMA waits full | MMA waits conv | MMA start (rel)\n", T);
+        for (int t = 0; t < T && t < 32; ++t)
+            fprintf(stderr, "  %2d %8lld %8lld %8lld %9lld\n", t, host[t], host[32 + t], host[64 + t], host[96 + t] - host[96]);
+        fprintf(stderr, "  epilogue waited %lld, epilogue took %lld, total from first MMA wait %lld\n", host[128], host[130] - host[129], host[130] - host[96]);
+    }
     return cudaGetLastError() == cudaSuccess;
 }
 

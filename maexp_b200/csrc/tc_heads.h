@@ -15,6 +15,7 @@ struct TcHeadsFwd {
     long long w1[2], b1[2], w2[2], b2[2];  // offsets of fc_list.0 / fc_post of every head (mlp.py:19-26)
     int out[2], nheads;
     float *outp[2];          // [G][rows_max][out]
+    float *hbuf[2];          // relu(x W1^T + b1) [G][rows_max][128] of every head (training pass), or nullptr
     int rows;
     long long rows_max;
     int din, H;
