@@ -474,10 +474,14 @@ def test_adam_optimizer_matches_torch():
 
 
 @pytest.mark.parametrize("kind,V,C,B", [("dqn_conv_mlp", 7, 7, 640), ("c51", 7, 3, 640), ("iqn", 7, 3, 640), ("c51", 5, 3, 640),
-                                        ("qr", 9, 4, 640), ("c51", 7, 3, 2304), ("dqn_conv_mlp", 7, 7, 2100), ("da3", 7, 3, 2100), ("da3", 7, 3, 48), ("da3", 9, 3, 300)])
+                                        ("qr", 9, 4, 640), ("c51", 7, 3, 2304), ("dqn_conv_mlp", 7, 7, 2100), ("da3", 7, 3, 2100), ("da3", 7, 3, 48), ("da3", 9, 3, 300),
+                                        # tc_trunk_kernel: a partial last tile of 32 observations, and the generic-channel instantiation
+                                        ("c51", 7, 3, 2100), ("c51", 7, 5, 2304), ("qr", 7, 3, 2304)])
 def test_large_batch_inference_path_matches_oracle(kind, V, C, B):
-    """Acting / evaluation batches take the fused conv trunk (>= 512 rows) and, from 2048 rows, the tcgen05 tensor-core
-    GEMM with three TF32 terms per product: the Q-values stay within 1e-5 of the fp32 oracle."""
+    """Acting / evaluation batches: from 512 rows the MLP heads run on the TMA-fed tcgen05 kernel (csrc/tc_heads.cu, with the
+    fused dueling / expectation epilogue for C51; per-layer tcgen05 GEMMs where it does not apply, e.g. QR-DQN's 400-wide head),
+    from 2048 rows the conv trunk runs conv2 on the tensor cores (csrc/tc_trunk.cu); three TF32 terms per product: the
+    Q-values stay within 1e-5 of the fp32 oracle."""
     from maexp_b200.core.agents.brains import LearnerGroup
     cfg, _ = golden_configs()[kind]
     G = 2
