@@ -324,6 +324,258 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent form for the acting batches of the dueling distributional networks with 4 actions (fused greedy values):
+// a CTA walks the 128-row tiles of one agent, and the epilogue of tile i runs on its own eight warps WHILE the producer / MMA /
+// operand warps are already in tile i + 1.  What makes that possible:
+//   * the advantage head's output columns are atom-major (column z * 4 + k; tc_heads_prepare_kernel permutes W2 / b2), so a
+//     16-column tcgen05.ld holds all four actions of four atoms: the dueling mean needs no shared-memory copy of the accumulator
+//     and the epilogue reads tensor memory directly (the operand ring stays with the main loop)
+//   * the value head's output (64 columns inside the first accumulator's region) is moved to shared memory first thing
+//     (d1_free), after which the next tile's first layer may overwrite it; the advantage head's accumulator (columns 256..)
+//     is only needed by the next tile's SECOND layer (d2_free), eight K slabs later
+// TMEM, roles and the three-term TF32 arithmetic are those of tc_heads_kernel.
+constexpr int kThreadsP = 448;  // producer, MMA issuer, 4 operand warps, 8 epilogue warps
+constexpr int kCPitch = 53;     // floats per row of the c_z = v_z - mean_z exchange buffer (Z <= 52)
+
+__global__ void __launch_bounds__(kThreadsP, 1) tc_heads_acting_kernel(const __grid_constant__ HeadsArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t full[kStages], conv[kStages], empty[kStages], d1_done, d2_full, d1_free, d2_free;
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_b1[2 * kHidden];
+    __shared__ float s_b2[288], s_sup[64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = blockIdx.y;
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    auto a_hi = [&](int s) { return smem + (size_t)s * kStageBytes; };
+    auto a_lo = [&](int s) { return smem + (size_t)s * kStageBytes + kATile; };
+    auto w_hi = [&](int s) { return smem + (size_t)s * kStageBytes + 2 * kATile; };
+    auto w_lo = [&](int s) { return smem + (size_t)s * kStageBytes + 2 * kATile + kWTile; };
+    float *s_c = reinterpret_cast<float *>(smem + (size_t)kStages * kStageBytes);  // [128][kCPitch]
+    const int ns1 = a.din / kBK, per_head = kHidden / kBK, T = ns1 + 2 * per_head, n1 = 2 * kHidden;
+    const int ntiles = (a.rows + kBM - 1) / kBM;
+
+    for (int i = tid; i < n1; i += kThreadsP) s_b1[i] = a.b1cat[(size_t)g * n1 + i];
+    for (int i = tid; i < a.npad[0] + a.npad[1]; i += kThreadsP)
+        s_b2[i] = i < a.npad[0] ? a.b2p[0][(size_t)g * a.npad[0] + i] : a.b2p[1][(size_t)g * a.npad[1] + i - a.npad[0]];
+    for (int i = tid; i < a.Z; i += kThreadsP) s_sup[i] = a.support ? a.support[i] : 0.0f;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&conv[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&d1_done, 1);
+        mbar_init(&d2_full, 1);
+        mbar_init(&d1_free, 256);
+        mbar_init(&d2_free, 256);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            int u = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int t = 0; t < T; ++t, ++u) {
+                    const int s = u % kStages, n = u / kStages;
+                    if (u >= kStages) mbar_wait(&empty[s], (n - 1) & 1);
+                    if (t < ns1) {
+                        mbar_expect_tx(&full[s], kATile + 2u * (uint32_t)n1 * 128u);
+                        tma_3d(smem_u32(a_hi(s)), &a.tm_x, &full[s], t * kBK, tile * kBM, g);
+                        tma_2d(smem_u32(w_hi(s)), &a.tm_w1hi, &full[s], t * kBK, g * n1);
+                        tma_2d(smem_u32(w_lo(s)), &a.tm_w1lo, &full[s], t * kBK, g * n1);
+                    } else {
+                        const int h = a.order[(t - ns1) / per_head], j = (t - ns1) % per_head;
+                        mbar_expect_tx(&full[s], 2u * (uint32_t)a.npad[h] * 128u);
+                        tma_2d(smem_u32(w_hi(s)), &a.tm_w2hi[h], &full[s], j * kBK, g * a.npad[h]);
+                        tma_2d(smem_u32(w_lo(s)), &a.tm_w2lo[h], &full[s], j * kBK, g * a.npad[h]);
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int u = 0, it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it)
+                for (int t = 0; t < T; ++t, ++u) {
+                    const int s = u % kStages, n = u / kStages;
+                    mbar_wait(&full[s], n & 1);
+                    mbar_wait(&conv[s], n & 1);
+                    if (it > 0 && t == 0) mbar_wait(&d1_free, (it - 1) & 1);    // the previous tile's value head has been read
+                    if (it > 0 && t == ns1) mbar_wait(&d2_free, (it - 1) & 1);  // ... and its advantage head
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t d = tmem, idesc = idesc_tf32_m128(n1);
+                    bool first = t == 0;
+                    if (t >= ns1) {
+                        const int h = a.order[(t - ns1) / per_head], j = (t - ns1) % per_head;
+                        d = tmem + a.d2col[h];
+                        idesc = idesc_tf32_m128(a.npad[h]);
+                        first = j == 0;
+                    }
+                    const uint32_t aA = smem_u32(a_hi(s)), aAlo = smem_u32(a_lo(s)), aW = smem_u32(w_hi(s)), aWlo = smem_u32(w_lo(s));
+#pragma unroll
+                    for (int k = 0; k < kBK / 8; ++k) {
+                        const uint32_t ko = (uint32_t)k * 32;
+                        umma_tf32(d, smem_desc(aA + ko), smem_desc(aW + ko), idesc, (first && k == 0) ? 0u : 1u);
+                        umma_tf32(d, smem_desc(aAlo + ko), smem_desc(aW + ko), idesc, 1u);
+                        umma_tf32(d, smem_desc(aA + ko), smem_desc(aWlo + ko), idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                    if (t == ns1 - 1) umma_commit(&d1_done);
+                    if (t == T - 1) umma_commit(&d2_full);
+                }
+        }
+    } else if (warp < 6) {
+        // ------------------------------------------------------------------ operand warps
+        const int ct = tid - 64, quad = warp & 3, row = quad * 32 + lane;
+        int u = 0, it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it)
+            for (int t = 0; t < T; ++t, ++u) {
+                const int s = u % kStages, n = u / kStages;
+                if (t < ns1) {
+                    mbar_wait(&full[s], n & 1);
+                    float4 *hi4 = reinterpret_cast<float4 *>(a_hi(s)), *lo4 = reinterpret_cast<float4 *>(a_lo(s));
+#pragma unroll
+                    for (int i = 0; i < (int)(kATile / 16 / 128); ++i) {
+                        const float4 v = hi4[ct + 128 * i];
+                        const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                        hi4[ct + 128 * i] = hi;
+                        lo4[ct + 128 * i] = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                    }
+                } else {
+                    if (t == ns1) {
+                        mbar_wait(&d1_done, it & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    if (u >= kStages) mbar_wait(&empty[s], (n - 1) & 1);
+                    const int h = a.order[(t - ns1) / per_head], j = (t - ns1) % per_head;
+                    uint32_t r[32];
+                    tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * kHidden + j * kBK), r);
+                    const float *b1 = s_b1 + h * kHidden + j * kBK;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 b = *reinterpret_cast<const float4 *>(b1 + c * 4);
+                        const float4 v = make_float4(fmaxf(__uint_as_float(r[c * 4]) + b.x, 0.0f), fmaxf(__uint_as_float(r[c * 4 + 1]) + b.y, 0.0f),
+                                                     fmaxf(__uint_as_float(r[c * 4 + 2]) + b.z, 0.0f), fmaxf(__uint_as_float(r[c * 4 + 3]) + b.w, 0.0f));
+                        stage_chunk<3>(a_hi(s), a_lo(s), row, c, v);
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&conv[s]);
+            }
+    } else {
+        // ------------------------------------------------------------------ epilogue warps (two threads per row)
+        const int quad = warp & 3, row = quad * 32 + lane, half = warp >= 10;
+        const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+        const int Z = a.Z, npadA = a.npad[1];
+        const float *bV = s_b2, *bA = s_b2 + a.npad[0];
+        float *c_row = s_c + (size_t)row * kCPitch;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            mbar_wait(&d2_full, it & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // value head -> shared memory (two 16-column groups per thread), then the first accumulator's region is free
+            for (int c0 = half * 16; c0 < a.npad[0]; c0 += 32) {
+                uint32_t r[16];
+                tmem_ld16(lane_base + a.d2col[0] + (uint32_t)c0, r);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < Z) c_row[c0 + j] = __uint_as_float(r[j]) + bV[c0 + j];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&d1_free);
+            epi_bar();
+            // dueling pass, split over the atoms: c_z = v_z - mean over the actions (columns z * 4 + k)
+            {
+                const int nchunks = npadA / 16, c_lo = half ? nchunks / 2 : 0, c_hi = half ? nchunks : nchunks / 2;
+                for (int c = c_lo; c < c_hi; ++c) {
+                    uint32_t r[16];
+                    tmem_ld16(lane_base + a.d2col[1] + (uint32_t)(c * 16), r);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int z = c * 4 + q;
+                        if (z < Z) {
+                            const float *b = bA + c * 16 + q * 4;
+                            const float sum = ((__uint_as_float(r[q * 4]) + b[0]) + (__uint_as_float(r[q * 4 + 1]) + b[1])) +
+                                              ((__uint_as_float(r[q * 4 + 2]) + b[2]) + (__uint_as_float(r[q * 4 + 3]) + b[3]));
+                            c_row[z] -= sum * 0.25f;
+                        }
+                    }
+                }
+            }
+            epi_bar();
+            // expectation (C51) / quantile mean (QR-DQN), split over the actions: this thread owns actions half and half + 2
+            float mx[2] = {-INFINITY, -INFINITY}, se[2][4], sq[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) se[i][j] = sq[i][j] = 0.0f;
+            const int nchunks = npadA / 16;
+            if (a.epi == 1) {
+                for (int c = 0; c < nchunks; ++c) {
+                    uint32_t r[16];
+                    tmem_ld16(lane_base + a.d2col[1] + (uint32_t)(c * 16), r);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int z = c * 4 + q;
+                        if (z < Z) {
+                            const float cz = c_row[z];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                mx[i] = fmaxf(mx[i], (__uint_as_float(half ? r[q * 4 + 1 + 2 * i] : r[q * 4 + 2 * i]) + bA[c * 16 + q * 4 + half + 2 * i]) + cz);
+                        }
+                    }
+                }
+            }
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t r[16];
+                tmem_ld16(lane_base + a.d2col[1] + (uint32_t)(c * 16), r);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int z = c * 4 + q;
+                    if (z < Z) {
+                        const float cz = c_row[z], sz = s_sup[z];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const float d = (__uint_as_float(half ? r[q * 4 + 1 + 2 * i] : r[q * 4 + 2 * i]) + bA[c * 16 + q * 4 + half + 2 * i]) + cz;
+                            if (a.epi == 1) {
+                                const float e = fast_exp(d - mx[i]);
+                                se[i][q] += e;
+                                sq[i][q] += e * sz;
+                            } else {
+                                sq[i][q] += d;
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&d2_free);
+            const int m = tile * kBM + row;
+            if (m < a.rows) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float num = (sq[i][0] + sq[i][1]) + (sq[i][2] + sq[i][3]), den = (se[i][0] + se[i][1]) + (se[i][2] + se[i][3]);
+                    a.q_out[(size_t)g * a.q_g + (size_t)m * 4 + half + 2 * i] = a.epi == 1 ? num / den : num / (float)Z;
+                }
+            }
+            epi_bar();  // c_row is rewritten by the next tile
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 // Splits the heads' weights into TF32 hi / lo panels with TMA-friendly strides (rows of din / 128 floats, 16-byte aligned,
 // zero rows up to the padded width) and gathers the biases.  One launch per forward call: ~0.4 MB per agent.
 struct PrepArgs {
@@ -332,6 +584,7 @@ struct PrepArgs {
     long long w1[2], b1[2], w2[2], b2[2];
     int out[2], npad[2], nheads, din;
     float *w1hi, *w1lo, *w2hi[2], *w2lo[2], *b1cat, *b2p[2];
+    int perm_A, perm_Z;  // > 0: head 1's output rows go atom-major (row z * A + k <- k * Z + z), see tc_heads_acting_kernel
 };
 __global__ void tc_heads_prepare_kernel(const PrepArgs p) {
     const int g = blockIdx.y;
@@ -360,14 +613,16 @@ __global__ void tc_heads_prepare_kernel(const PrepArgs p) {
             const long long wn = (long long)p.npad[h] * kHidden;
             if (j < wn) {
                 const int r = (int)(j / kHidden), k = (int)(j - (long long)r * kHidden);
-                const float v = r < p.out[h] ? src[p.w2[h] + (long long)r * kHidden + k] : 0.0f, hi = tf32_rna(v);
+                const int rs = (h == 1 && p.perm_A && r < p.out[h]) ? (r % p.perm_A) * p.perm_Z + r / p.perm_A : r;  // source row
+                const float v = r < p.out[h] ? src[p.w2[h] + (long long)rs * kHidden + k] : 0.0f, hi = tf32_rna(v);
                 p.w2hi[h][(size_t)g * wn + j] = hi;
                 p.w2lo[h][(size_t)g * wn + j] = v - hi;
                 break;
             }
             j -= wn;
             if (j < p.npad[h]) {
-                p.b2p[h][(size_t)g * p.npad[h] + j] = j < p.out[h] ? src[p.b2[h] + j] : 0.0f;
+                const int js = (h == 1 && p.perm_A && j < p.out[h]) ? (int)(j % p.perm_A) * p.perm_Z + (int)(j / p.perm_A) : (int)j;
+                p.b2p[h][(size_t)g * p.npad[h] + j] = j < p.out[h] ? src[p.b2[h] + js] : 0.0f;
                 break;
             }
             j -= p.npad[h];
@@ -452,6 +707,11 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
         a.q_out = f.q_out;
         a.q_g = f.q_g;
     }
+    // acting batches of the 4-action dueling distributional networks: persistent kernel, epilogue overlapped with the next tile
+    static const bool acting_off = getenv("MAEXP_TC_HEADS_PERSISTENT") && atoi(getenv("MAEXP_TC_HEADS_PERSISTENT")) == 0;
+    const bool persistent = a.epi != 0 && f.A == 4 && f.Z <= 52 && a.npad[0] <= 64 && a.npad[0] + a.npad[1] <= 288 && a.order[0] == 1 &&
+                            !f.hbuf[0] && !f.hbuf[1] && !acting_off;
+    if (persistent) { p.perm_A = 4; p.perm_Z = f.Z; }
     if (f.fused_q_done) *f.fused_q_done = a.epi != 0;
     static long long *dbg_buf = nullptr;
     if (getenv("MAEXP_TC_HEADS_DBG")) {
@@ -465,6 +725,22 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
         attr_set = true;
     }
     tc_heads_prepare_kernel<<<dim3(64, G), 256, 0, st>>>(p);
+    if (persistent) {
+        const size_t smem_p = (size_t)kStages * kStageBytes + 1024 + sizeof(float) * kBM * kCPitch;
+        static bool attr_p = false;
+        if (!attr_p) {
+            if (cudaFuncSetAttribute(tc_heads_acting_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p) != cudaSuccess) return false;
+            attr_p = true;
+        }
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int ntiles = (f.rows + kBM - 1) / kBM;
+        int per_group = sms / G < 1 ? 1 : sms / G;
+        if (per_group > ntiles) per_group = ntiles;
+        tc_heads_acting_kernel<<<dim3(per_group, G), kThreadsP, smem_p, st>>>(a);
+        return cudaGetLastError() == cudaSuccess;
+    }
     tc_heads_kernel<<<dim3((f.rows + kBM - 1) / kBM, G), kThreads, smem, st>>>(a);
     if (a.dbg) {
         long long host[256];
