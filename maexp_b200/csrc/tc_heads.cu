@@ -301,7 +301,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
             }
         }
         epi_bar();
-        if (a.epi) {
+        if (a.epi == 3) {
+            // collapsed heads: one value and A advantages per row
+            if (!half && m < a.rows) {
+                const float *adv = my + a.npad[0], *bA = s_b2 + a.npad[0];
+                float sum = 0.0f;
+                for (int k = 0; k < a.A; ++k) sum += adv[k] + bA[k];
+                const float c = (my[0] + s_b2[0]) - sum / (float)a.A;
+                for (int k = 0; k < a.A; ++k) a.q_out[(size_t)g * a.q_g + (size_t)m * a.A + k] = (adv[k] + bA[k]) + c;
+            }
+        } else if (a.epi) {
             // dueling combination + expectation in shared memory: the 255 head outputs per row never reach HBM
             float *q_row = a.q_out + (size_t)g * a.q_g + (size_t)m * a.A;
             if (a.A == 4) greedy_values_row<4>(my, my + a.npad[0], s_b2, s_b2 + a.npad[0], s_sup, 4, a.Z, a.epi == 1, q_row, m < a.rows, half);
@@ -585,6 +594,7 @@ struct PrepArgs {
     int out[2], npad[2], nheads, din;
     float *w1hi, *w1lo, *w2hi[2], *w2lo[2], *b1cat, *b2p[2];
     int perm_A, perm_Z;  // > 0: head 1's output rows go atom-major (row z * A + k <- k * Z + z), see tc_heads_acting_kernel
+    int mean_Z;          // > 0: output row r is the MEAN of the mean_Z source rows r * mean_Z .. (quantile-mean collapse, see below)
 };
 __global__ void tc_heads_prepare_kernel(const PrepArgs p) {
     const int g = blockIdx.y;
@@ -614,7 +624,16 @@ __global__ void tc_heads_prepare_kernel(const PrepArgs p) {
             if (j < wn) {
                 const int r = (int)(j / kHidden), k = (int)(j - (long long)r * kHidden);
                 const int rs = (h == 1 && p.perm_A && r < p.out[h]) ? (r % p.perm_A) * p.perm_Z + r / p.perm_A : r;  // source row
-                const float v = r < p.out[h] ? src[p.w2[h] + (long long)rs * kHidden + k] : 0.0f, hi = tf32_rna(v);
+                float v = 0.0f;
+                if (r < p.out[h]) {
+                    if (p.mean_Z) {
+                        for (int z = 0; z < p.mean_Z; ++z) v += src[p.w2[h] + ((long long)r * p.mean_Z + z) * kHidden + k];
+                        v /= (float)p.mean_Z;
+                    } else {
+                        v = src[p.w2[h] + (long long)rs * kHidden + k];
+                    }
+                }
+                const float hi = tf32_rna(v);
                 p.w2hi[h][(size_t)g * wn + j] = hi;
                 p.w2lo[h][(size_t)g * wn + j] = v - hi;
                 break;
@@ -622,7 +641,16 @@ __global__ void tc_heads_prepare_kernel(const PrepArgs p) {
             j -= wn;
             if (j < p.npad[h]) {
                 const int js = (h == 1 && p.perm_A && j < p.out[h]) ? (int)(j % p.perm_A) * p.perm_Z + (int)(j / p.perm_A) : (int)j;
-                p.b2p[h][(size_t)g * p.npad[h] + j] = j < p.out[h] ? src[p.b2[h] + js] : 0.0f;
+                float b = 0.0f;
+                if (j < p.out[h]) {
+                    if (p.mean_Z) {
+                        for (int z = 0; z < p.mean_Z; ++z) b += src[p.b2[h] + j * p.mean_Z + z];
+                        b /= (float)p.mean_Z;
+                    } else {
+                        b = src[p.b2[h] + js];
+                    }
+                }
+                p.b2p[h][(size_t)g * p.npad[h] + j] = b;
                 break;
             }
             j -= p.npad[h];
@@ -652,9 +680,16 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
     a.rows = f.rows;
     a.hbuf_g = f.rows_max * kHidden;
     a.din = p.din = f.din;
+    // Quantile-mean collapse (QR-DQN acting): the greedy value is the MEAN over the quantiles of v + (adv - mean over actions)
+    // (qr_dqn_brain.py get_action), and the mean commutes with the linear second layer -- so the second layer shrinks from
+    // Z + A Z output rows (100 + 400) to 1 + A rows whose weights are the quantile means of the original rows.
+    const bool collapse = f.q_out && !f.categorical && f.nheads == 2 && f.Z >= 1 && f.A >= 1 && f.A <= 8 && f.out[0] == f.Z &&
+                          f.out[1] == f.A * f.Z && !f.hbuf[0] && !f.hbuf[1];
+    if (collapse) p.mean_Z = f.Z;
     for (int h = 0; h < f.nheads; ++h) {
-        a.out_n[h] = p.out[h] = f.out[h];
-        a.npad[h] = p.npad[h] = (f.out[h] + 15) / 16 * 16;
+        const int eff_out = collapse ? (h ? f.A : 1) : f.out[h];
+        a.out_n[h] = p.out[h] = eff_out;
+        a.npad[h] = p.npad[h] = (eff_out + 15) / 16 * 16;
         if (f.out[h] < 1 || a.npad[h] > 256) return false;
         a.out[h] = f.outp[h];
         a.out_g[h] = f.rows_max * f.out[h];
@@ -700,7 +735,13 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
     if (!ok) return false;
     a.rs = (a.npad[0] + (f.nheads > 1 ? a.npad[1] : 0)) | 1;  // the epilogue's shared-memory copy of the accumulators
     if ((size_t)a.rs * kBM * 4 > (size_t)kStages * kStageBytes || a.rs > 512) return false;
-    if (f.q_out && f.nheads == 2 && f.A >= 1 && f.A <= 8 && f.Z >= 1 && f.Z <= 256 && f.out[0] == f.Z && f.out[1] == f.A * f.Z) {
+    if (collapse) {
+        a.epi = 3;
+        a.A = f.A; a.Z = 1;
+        a.support = nullptr;
+        a.q_out = f.q_out;
+        a.q_g = f.q_g;
+    } else if (f.q_out && f.nheads == 2 && f.A >= 1 && f.A <= 8 && f.Z >= 1 && f.Z <= 256 && f.out[0] == f.Z && f.out[1] == f.A * f.Z) {
         a.epi = f.categorical ? 1 : 2;
         a.A = f.A; a.Z = f.Z;
         a.support = f.support;
@@ -709,7 +750,7 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
     }
     // acting batches of the 4-action dueling distributional networks: persistent kernel, epilogue overlapped with the next tile
     static const bool acting_off = getenv("MAEXP_TC_HEADS_PERSISTENT") && atoi(getenv("MAEXP_TC_HEADS_PERSISTENT")) == 0;
-    const bool persistent = a.epi != 0 && f.A == 4 && f.Z <= 52 && a.npad[0] <= 64 && a.npad[0] + a.npad[1] <= 288 && a.order[0] == 1 &&
+    const bool persistent = (a.epi == 1 || a.epi == 2) && f.A == 4 && f.Z <= 52 && a.npad[0] <= 64 && a.npad[0] + a.npad[1] <= 288 && a.order[0] == 1 &&
                             !f.hbuf[0] && !f.hbuf[1] && !acting_off;
     if (persistent) { p.perm_A = 4; p.perm_Z = f.Z; }
     if (f.fused_q_done) *f.fused_q_done = a.epi != 0;
