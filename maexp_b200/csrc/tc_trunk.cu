@@ -20,6 +20,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 #include "tc_tma_host.h"
@@ -41,6 +43,7 @@ struct alignas(64) TrunkArgs {
     float *flat;
     long long stride, g_obs, P, o_c1w, o_c1b, o_c2b, g_flat;
     int B, C;
+    long long *dbg;  // MAEXP_TC_TRUNK_DBG: cycle stamps of CTA (0, 0)
 };
 
 // TC > 0: the number of observation channels at compile time (the per-channel cell reads become 128-bit loads at static offsets)
@@ -98,7 +101,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_trunk_kernel(const __grid_cons
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         if (warp >= kEpiWarps) {
             // ---------------------------------------------------------- conv1 + max-pool + im2col, one observation per pass
+            const long long c0 = clock64();
             mbar_wait(&obar, it & 1);  // this tile's observations have landed
+            if (a.dbg && blockIdx.x == 0 && g == 0 && tid == kEpiWarps * 32 && it < 16) { a.dbg[it * 8] = c0; a.dbg[it * 8 + 1] = clock64(); }
             for (int o = warp - kEpiWarps; o < kTileObs; o += kConvWarps) {
                 const int b = tile * kTileObs + o;
                 if (b >= a.B) break;  // rows past the batch keep stale operands: their outputs are never stored
@@ -157,6 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_trunk_kernel(const __grid_cons
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+            if (a.dbg && blockIdx.x == 0 && g == 0 && tid == kEpiWarps * 32 && it < 16) a.dbg[it * 8 + 2] = clock64();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // operand tile complete; the previous tile's accumulator has been read
@@ -178,7 +184,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_trunk_kernel(const __grid_cons
             }
             umma_commit(&mbar);
         }
+        if (a.dbg && blockIdx.x == 0 && g == 0 && tid == kEpiWarps * 32 && it < 16) a.dbg[it * 8 + 3] = clock64();
         mbar_wait(&mbar, it & 1);  // the MMAs have finished: the operand tile is free, the accumulator is complete
+        if (a.dbg && blockIdx.x == 0 && g == 0 && tid == kEpiWarps * 32 && it < 16) a.dbg[it * 8 + 4] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (warp < kEpiWarps) {
             // ---------------------------------------------------------- epilogue: row = 4 * observation + position
@@ -242,8 +250,22 @@ bool tc_trunk_forward(cudaStream_t st, int G, const TcTrunkFwd &f) {
     int per_group = sms / G;  // one persistent CTA per SM
     if (per_group < 1) per_group = 1;
     if (per_group > ntiles) per_group = ntiles;
+    static long long *dbg_buf = nullptr;
+    if (getenv("MAEXP_TC_TRUNK_DBG")) {
+        if (!dbg_buf) { cudaMalloc(&dbg_buf, 256 * sizeof(long long)); cudaMemset(dbg_buf, 0, 256 * sizeof(long long)); }
+        a.dbg = dbg_buf;
+    }
     tc_trunk_prepare_kernel<<<dim3(8, G), 256, 0, st>>>(f.params, f.P, f.o_c2w, hi, lo);
     fn<<<dim3(per_group, G), kThreads, smem, st>>>(a);
+    if (a.dbg) {  // measured: wait obs 500 | conv + im2col 7 600 | barrier 300 | wait MMA 3 050 | period 11 700 cycles per 32 observations
+        long long h[256];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "tc_trunk CTA(0,0), a conv warp, cycles per tile: wait obs | conv + im2col | to barrier | wait MMA | tile period\n");
+        for (int it = 1; it < 12; ++it)
+            fprintf(stderr, "  %2d %7lld %7lld %7lld %7lld %8lld\n", it, h[it * 8 + 1] - h[it * 8], h[it * 8 + 2] - h[it * 8 + 1],
+                    h[it * 8 + 3] - h[it * 8 + 2], h[it * 8 + 4] - h[it * 8 + 3], h[it * 8] - h[(it - 1) * 8]);
+    }
     return cudaGetLastError() == cudaSuccess;
 }
 
