@@ -2337,6 +2337,7 @@ bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const flo
     if (h->tc_mlp && h->tc_heads && !h->iqn && !g_inference_tc && in.rows >= 128 && H == 128 && in.din >= 32 && in.din % 32 == 0) {
         // TMA-fed kernel, all heads of a pass in one CTA per 128-row tile (csrc/tc_heads.cu)
         bool ok = true;
+        TcHeadsFwd passes[3] = {};
         for (int q = 0; q < n && ok; ++q) {
             int outs_n[2] = {hds[0].out, nheads > 1 ? hds[1].out : 0};
             const size_t need = tc_heads_workspace_floats(h->G, nheads, in.din, outs_n);
@@ -2351,7 +2352,7 @@ bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const flo
                 e.ws = ws; e.floats = need;
             }
             e.key = outs[q][0];
-            TcHeadsFwd t = {};
+            TcHeadsFwd &t = passes[q];
             t.x = ins[q].x; t.x_row = ins[q].x_row; t.x_g = ins[q].x_g;
             t.params = params[q]; t.P = P;
             t.nheads = nheads;
@@ -2361,9 +2362,8 @@ bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const flo
             }
             t.rows = ins[q].rows; t.rows_max = ins[q].rows_max; t.din = ins[q].din; t.H = H;
             t.workspace = e.ws;
-            ok = tc_heads_forward(st, h->G, t);
         }
-        if (ok) return true;
+        if (ok && tc_heads_forward_multi(st, h->G, passes, n)) return true;  // all passes as grid slices of one launch
     }
     if (h->tc_mlp && !h->iqn && in.rows >= 128 && H <= 128 && (H & 3) == 0) {
         bool ok = true;
@@ -3617,13 +3617,36 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         cudaEventRecord(h->ev_fork, st);
         forward(h, st, h->online, obs, B, h->acts[0]);
         cudaStream_t s2 = fork_pass(h, st, 0, false);
-        forward(h, s2, h->target, next_obs, B, h->acts[2], /*inference=*/true);  // passes 1 and 2 never feed a backward pass
-        if (h->dist) {  // double-DQN action selection by the online net
-            cudaStream_t s1 = fork_pass(h, st, 1, false);
-            forward(h, s1, h->online, next_obs, B, h->acts[1], /*inference=*/true);
+        // The distributional nets run two inference passes, target(s') and online(s') (double-DQN action selection), each on its
+        // own side stream.  MAEXP_MERGE_INFERENCE_PASSES=1 sends both down ONE branch as grid slices of one trunk launch and one
+        // heads launch: under the CUPTI timeline the last of three branches starts ~55 us late and merging looks attractive, but
+        // the unprofiled update gets slower (247 against 220 us per C51 team update), so the three branches stay.
+        bool both = false;
+        if (h->dist && h->has_conv && h->fused_trunk && h->fused_mlp && h->heads.size() == 2 && getenv("MAEXP_MERGE_INFERENCE_PASSES")) {
+            const float *params2[2] = {h->target, h->online}, *inputs2[2] = {next_obs, next_obs};
+            maexp_learner::Acts *acts2[2] = {&h->acts[2], &h->acts[1]};
+            const int train2[2] = {0, 0};
+            if (trunk_forward_multi(h, s2, 2, params2, inputs2, acts2, train2, B)) {
+                MlpIn ins2[2];
+                for (int q = 0; q < 2; ++q) ins2[q] = {acts2[q]->flat, h->D, (long long)h->B * h->D, B, h->B, h->D};
+                float *const hb2[2][2] = {{acts2[0]->h[0], acts2[0]->h[1]}, {acts2[1]->h[0], acts2[1]->h[1]}};
+                float *const ob2[2][2] = {{acts2[0]->out[0], acts2[0]->out[1]}, {acts2[1]->out[0], acts2[1]->out[1]}};
+                if (!mlp_fused_forward_multi(h, s2, 2, params2, h->heads.data(), 2, ins2, hb2, ob2))
+                    for (int q = 0; q < 2; ++q)
+                        for (size_t k = 0; k < h->heads.size(); ++k)
+                            mlp_forward(h, s2, params2[q], h->heads[k], ins2[q], acts2[q]->h[k], acts2[q]->out[k]);
+                both = true;
+            }
+        }
+        if (!both) {
+            forward(h, s2, h->target, next_obs, B, h->acts[2], /*inference=*/true);  // passes 1 and 2 never feed a backward pass
+            if (h->dist) {  // double-DQN action selection by the online net
+                cudaStream_t s1 = fork_pass(h, st, 1, false);
+                forward(h, s1, h->online, next_obs, B, h->acts[1], /*inference=*/true);
+            }
         }
         join_pass(h, st, 0);
-        if (h->dist) join_pass(h, st, 1);
+        if (h->dist && !both) join_pass(h, st, 1);
     }
     if (!h->dist) {
         dqn_loss_kernel<<<dim3((B + 127) / 128, G), 128, 0, st>>>(h->acts[0].out[0], h->acts[2].out[0], actions, rewards,

@@ -148,7 +148,14 @@ __device__ __forceinline__ void greedy_values_row(float *my, float *adv, const f
         }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_constant__ HeadsArgs a) {
+// up to three passes (their own input, parameters and outputs; same shapes) as grid slices of one launch: the forward passes of
+// an update.  The whole block sits in the kernel's parameter space, so the tensor maps of every pass can be addressed there.
+struct alignas(64) HeadsArgsN {
+    HeadsArgs p[3];
+};
+
+__global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_constant__ HeadsArgsN aa) {
+    const HeadsArgs &a = aa.p[blockIdx.z];
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full[kStages], conv[kStages], empty[kStages], d1_done, all_done;
     __shared__ uint32_t tmem_slot;
@@ -671,11 +678,13 @@ size_t tc_heads_workspace_floats(int G, int nheads, int din, const int *out) {
     return n + 64;  // 16-byte alignment slack between the panels
 }
 
-bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
+namespace {
+// arguments of one pass: panel layout, tensor maps, TMEM plan, epilogue mode; false: shape outside what the kernels handle
+bool plan_pass(int G, const TcHeadsFwd &f, HeadsArgs &a, PrepArgs &p, bool &persistent) {
     if (f.nheads < 1 || f.nheads > 2 || f.H != kHidden || f.din < kBK || f.din % kBK || f.rows < 1 || !f.workspace) return false;
     if ((reinterpret_cast<uintptr_t>(f.x) & 15) || (f.x_row & 3) || (f.x_g & 3)) return false;
-    HeadsArgs a = {};
-    PrepArgs p = {};
+    a = HeadsArgs();
+    p = PrepArgs();
     a.nheads = p.nheads = f.nheads;
     a.rows = f.rows;
     a.hbuf_g = f.rows_max * kHidden;
@@ -750,21 +759,55 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
     }
     // acting batches of the 4-action dueling distributional networks: persistent kernel, epilogue overlapped with the next tile
     static const bool acting_off = getenv("MAEXP_TC_HEADS_PERSISTENT") && atoi(getenv("MAEXP_TC_HEADS_PERSISTENT")) == 0;
-    const bool persistent = (a.epi == 1 || a.epi == 2) && f.A == 4 && f.Z <= 52 && a.npad[0] <= 64 && a.npad[0] + a.npad[1] <= 288 && a.order[0] == 1 &&
+    persistent = (a.epi == 1 || a.epi == 2) && f.A == 4 && f.Z <= 52 && a.npad[0] <= 64 && a.npad[0] + a.npad[1] <= 288 && a.order[0] == 1 &&
                             !f.hbuf[0] && !f.hbuf[1] && !acting_off;
     if (persistent) { p.perm_A = 4; p.perm_Z = f.Z; }
     if (f.fused_q_done) *f.fused_q_done = a.epi != 0;
+    return true;
+}
+bool set_smem_attr() {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(tc_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kStages * kStageBytes + 1024)) != cudaSuccess)
+            return false;
+        attr_set = true;
+    }
+    return true;
+}
+}  // namespace
+
+// the forward passes of an update (same shapes, their own inputs / parameters / outputs) as ONE launch: blockIdx.z = pass
+bool tc_heads_forward_multi(cudaStream_t st, int G, const TcHeadsFwd *f, int n) {
+    if (n < 1 || n > 3) return false;
+    HeadsArgsN aa = {};
+    PrepArgs p[3];
+    for (int q = 0; q < n; ++q) {
+        bool persistent = false;
+        if (f[q].rows != f[0].rows || f[q].din != f[0].din || f[q].nheads != f[0].nheads) return false;
+        if (!plan_pass(G, f[q], aa.p[q], p[q], persistent)) return false;
+        if (persistent) {  // (acting batches go through tc_heads_forward)
+            p[q].perm_A = p[q].perm_Z = 0;
+        }
+    }
+    if (!set_smem_attr()) return false;
+    for (int q = 0; q < n; ++q) tc_heads_prepare_kernel<<<dim3(64, G), 256, 0, st>>>(p[q]);
+    tc_heads_kernel<<<dim3((f[0].rows + kBM - 1) / kBM, G, n), kThreads, (size_t)kStages * kStageBytes + 1024, st>>>(aa);
+    return cudaGetLastError() == cudaSuccess;
+}
+
+bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
+    HeadsArgsN aa = {};
+    HeadsArgs &a = aa.p[0];
+    PrepArgs p;
+    bool persistent = false;
+    if (!plan_pass(G, f, a, p, persistent)) return false;
     static long long *dbg_buf = nullptr;
     if (getenv("MAEXP_TC_HEADS_DBG")) {
         if (!dbg_buf) { cudaMalloc(&dbg_buf, 256 * sizeof(long long)); cudaMemset(dbg_buf, 0, 256 * sizeof(long long)); }
         a.dbg = dbg_buf;
     }
     const size_t smem = (size_t)kStages * kStageBytes + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(tc_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-        attr_set = true;
-    }
+    if (!set_smem_attr()) return false;
     tc_heads_prepare_kernel<<<dim3(64, G), 256, 0, st>>>(p);
     if (persistent) {
         const size_t smem_p = (size_t)kStages * kStageBytes + 1024 + sizeof(float) * kBM * kCPitch;
@@ -782,7 +825,7 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
         tc_heads_acting_kernel<<<dim3(per_group, G), kThreadsP, smem_p, st>>>(a);
         return cudaGetLastError() == cudaSuccess;
     }
-    tc_heads_kernel<<<dim3((f.rows + kBM - 1) / kBM, G), kThreads, smem, st>>>(a);
+    tc_heads_kernel<<<dim3((f.rows + kBM - 1) / kBM, G), kThreads, smem, st>>>(aa);
     if (a.dbg) {
         long long host[256];
         cudaStreamSynchronize(st);
