@@ -1447,6 +1447,8 @@ struct maexp_learner {
     float *splitk_side[kSides] = {};
     cudaStream_t side[kSides] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kSides] = {}, ev_w[kSides] = {};
+    cudaEvent_t ev_mark[2] = {};   // backward(): points of the main stream the deferred weight-gradient work waits for
+    bool critical_first = true;    // MAEXP_CRITICAL_FIRST=0: weight-gradient kernels are issued where their inputs become ready
     float *d_h2 = nullptr, *d_hrow2 = nullptr;  // second hidden-gradient buffers: weight-gradient GEMMs of head k read
                                                 // theirs on a side stream while head k+1's data gradients are computed
     // activations of the three passes (0: online(s) kept for backward, 1: online(s'), 2: target(s'))
@@ -1525,6 +1527,20 @@ float *g_splitk_ws = nullptr;                            // set per call from th
 // set by maexp_learner_q_values around the forward pass of the dueling distributional networks: the heads kernel may write the
 // greedy values straight to q_out (and then sets done), which replaces dist_q_kernel and the 255 head outputs per row
 struct FusedQ { float *q_out = nullptr; long long q_g = 0; int categorical = 0; bool done = false; } g_fused_q;
+// MAEXP_LEARNER_STAMPS=1: one-thread kernels that write %globaltimer at the phase boundaries of an update, on the stream
+// that reaches them -- the timeline of the graph-replayed update WITHOUT a profiler attached (CUPTI serialises branches)
+__global__ void stamp_kernel(unsigned long long *slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
+unsigned long long *g_stamps = nullptr;
+void stamp(cudaStream_t st, int slot) {
+    static const bool on = getenv("MAEXP_LEARNER_STAMPS") != nullptr;
+    if (!on) return;
+    if (!g_stamps && cudaMalloc(&g_stamps, 64 * sizeof(unsigned long long)) != cudaSuccess) return;
+    stamp_kernel<<<1, 1, 0, st>>>(g_stamps + slot);
+}
 bool g_inference_tc = false;                             // set by the q_values entry points around their forward pass
 constexpr int kAttnMapsBatch = 256;                      // q_values batches up to this size keep their attention maps
 struct InferenceScope {                                  // (every model family: conv heads, transformer projections)
@@ -1575,6 +1591,31 @@ void colsum(cudaStream_t st, int G, const float *ones, const float *X, float *ou
     gemm(st, G, ones, X, out, nullptr, 1, N, M, 0, 0, N, 1, N, 1, 0, gX, gOut, 0, 0, accumulate);
 }
 
+// All bias gradients of the MLP heads in one launch: column sums of d_out (second layers) and d_h (first layers) over the batch
+// rows, one thread per column, four interleaved partial sums combined in a fixed order (deterministic).  Replaces four
+// ones[1,B] x dY GEMMs and their split-K reductions (8 launches, ~60 us of kernel time per C51 team update).
+struct BiasGradArgs {
+    const float *src[4];
+    long long src_g[4], dst_off[4];
+    int cols[4], n;
+};
+__global__ void bias_grads_kernel(const BiasGradArgs a, float *grads, long long P, int rows) {
+    const int g = blockIdx.z, t = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n || c >= a.cols[t]) return;
+    const int stride = a.cols[t];
+    const float *s = a.src[t] + (size_t)g * a.src_g[t] + c;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int r = 0;
+    for (; r + 3 < rows; r += 4) {
+        s0 += s[(size_t)r * stride];
+        s1 += s[(size_t)(r + 1) * stride];
+        s2 += s[(size_t)(r + 2) * stride];
+        s3 += s[(size_t)(r + 3) * stride];
+    }
+    for (; r < rows; ++r) s0 += s[(size_t)r * stride];
+    grads[(size_t)g * P + a.dst_off[t] + c] = (s0 + s1) + (s2 + s3);
+}
+
 // Weight / bias gradients never feed the data-gradient chain, so inside a backward pass that opts in (g_wg.h set) they
 // are issued on the side streams, in rotation, each behind an event recorded on the main stream at that point.
 struct WGradCtx {
@@ -1591,6 +1632,17 @@ cudaStream_t wgrad_begin(cudaStream_t st) {
     g_wg.next = (k + 1) % kSides;
     cudaEventRecord(h->ev_w[k], st);
     cudaStreamWaitEvent(h->side[k], h->ev_w[k], 0);
+    g_splitk_ws = h->splitk_side[k];
+    g_wg.used[k] = true;
+    return h->side[k];
+}
+// the same, behind an event recorded earlier on the main stream (the work is issued later than its inputs became ready)
+cudaStream_t wgrad_begin_at(cudaStream_t st, cudaEvent_t ev) {
+    if (!g_wg.h) return st;
+    maexp_learner *h = g_wg.h;
+    const int k = g_wg.next;
+    g_wg.next = (k + 1) % kSides;
+    cudaStreamWaitEvent(h->side[k], ev, 0);
     g_splitk_ws = h->splitk_side[k];
     g_wg.used[k] = true;
     return h->side[k];
@@ -2213,7 +2265,7 @@ void trunk_forward(maexp_learner *h, cudaStream_t st, const float *params, const
 }
 
 // ---- conv trunk backward from h->d_flat [G][B][D] (activations of pass 0)
-void trunk_backward(maexp_learner *h, cudaStream_t st) {
+void trunk_backward(maexp_learner *h, cudaStream_t st, bool defer_conv2_wgrad = false, bool only_conv2_wgrad = false, cudaEvent_t after = nullptr) {
     const int G = h->G, B = h->B, C = h->C, F1 = h->F1, F2 = h->F2;
     const long long P = h->P;
     maexp_learner::Acts &a = h->acts[0];
@@ -2227,8 +2279,8 @@ void trunk_backward(maexp_learner *h, cudaStream_t st) {
         int nblk = (B + warps * 2 - 1) / (warps * 2);  // two samples per warp
         if (nblk > kTrunkBwdBlocks) nblk = kTrunkBwdBlocks;
         if (smem <= 200 * 1024) {
-            {   // conv2's weight gradient stays a GEMM, off the critical path
-                cudaStream_t ws = wgrad_begin(st);
+            if (!defer_conv2_wgrad) {   // conv2's weight gradient stays a GEMM, off the critical path
+                cudaStream_t ws = only_conv2_wgrad ? wgrad_begin_at(st, after) : wgrad_begin(st);
                 if (!h->dy2_ready)  // else the fused MLP backward wrote d_y2 next to d_flat
                     nhwc_to_flat_kernel<<<grid1d((long long)B * H2 * H2 * F2, G), 256, 0, ws>>>(h->d_flat, h->d_y2, B, H2 * H2, F2, gy2, 1);
                 if (h->col2_ready) cudaStreamWaitEvent(ws, h->ev_col2, 0);
@@ -2238,12 +2290,14 @@ void trunk_backward(maexp_learner *h, cudaStream_t st) {
                 h->col2_ready = h->dy2_ready = false;
                 gemm(ws, G, h->d_y2, a.col2, h->grads + h->o_c2w, nullptr, F2, F1 * 4, M2, 1, F2, F1 * 4, 1, F1 * 4, 1, gy2, gcol2, P, 0);
                 wgrad_end();
+                if (only_conv2_wgrad) return;
             }
             auto fn = V == 5 ? trunk_fused_bwd_kernel<5> : V == 7 ? trunk_fused_bwd_kernel<7> : trunk_fused_bwd_kernel<9>;
             cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             fn<<<dim3(nblk, G), warps * 32, smem, st>>>(h->d_flat, h->bwd_obs, h->online, a.arg, h->trunk_part, B, C, F1, F2,
                                                        h->cfg.obs_stride, (long long)B * h->cfg.obs_stride, P, h->o_c2w,
                                                        (long long)B * D, gp);
+            stamp(st, 13);
             trunk_bwd_reduce_kernel<<<dim3((K1 * 32 + 96 + 127) / 128, G), 128, 0, st>>>(h->trunk_part, h->grads, nblk, K1, F1, F2, P,
                                                                                        h->o_c1w, h->o_c1b, h->o_c2b);
             return;
@@ -2515,11 +2569,19 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
         const long long P = h->P, gH = (long long)B * H;
         MlpBwdHeads bh;
         float *dhs[2] = {h->d_h, h->d_h2};
+        // critical_first: the data-gradient chain (mlp_fused_bwd -> trunk_fused_bwd -> reduce) is issued BEFORE the weight-gradient
+        // kernels that branch off it, which wait for events marked at the points their inputs are ready.  In a captured graph
+        // the kernels that become ready together are launched in creation order: with the side work first the chain's kernels
+        // started 19 us (after the loss) and 10 us (after mlp_fused_bwd) late (globaltimer stamps, tools/exp_learner_stamps.py)
+        const bool to_trunk0 = h->has_conv && h->fused_trunk_acts && h->trunk_part;
+        const bool cfirst = h->critical_first && g_wg.h && to_trunk0 && (h->V == 5 || h->V == 7 || h->V == 9);
+        if (cfirst) cudaEventRecord(h->ev_mark[0], st);
         for (int k = 0; k < nheads; ++k) {
             const HeadLayout &hd = h->heads[k];
             const int O = hd.out;
             bh.w1[k] = hd.w1; bh.w2[k] = hd.w2; bh.out[k] = O;
             bh.dout[k] = h->d_out[k]; bh.hbuf[k] = h->acts[0].h[k]; bh.dh[k] = dhs[k];
+            if (cfirst) continue;
             cudaStream_t ws = wgrad_begin(st);
             gemm(ws, G, h->d_out[k], bh.hbuf[k], h->grads + hd.w2, nullptr, O, H, B, 1, O, H, 1, H, 1, (long long)B * O, gH, P, 0);
             colsum(ws, G, h->ones, h->d_out[k], h->grads + hd.b2, B, O, (long long)B * O, P);
@@ -2531,7 +2593,7 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
         float *dx = h->has_conv ? h->d_flat : nullptr;
         dim3 grid((B + kMlpTM - 1) / kMlpTM, dx ? (in.din + kMlpTN - 1) / kMlpTN : 1, G);
         const bool to_trunk = h->has_conv && h->fused_trunk_acts && h->trunk_part;
-        if (to_trunk) {  // conv2's im2col only needs the forward pass: issue it now, on a side stream
+        if (to_trunk && !cfirst) {  // conv2's im2col only needs the forward pass: issue it now, on a side stream
             maexp_learner::Acts &a0 = h->acts[0];
             const int Hp = h->Hp, H2 = h->H2, F1 = h->F1;
             cudaStream_t ws = wgrad_begin(st);
@@ -2542,8 +2604,59 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
             wgrad_end();
             h->col2_ready = h->dy2_ready = true;
         }
+        stamp(st, 11);
         mlp_fused_bwd_kernel<<<grid, 256, 0, st>>>(h->online, P, bh, nheads, B, B, in.din, H, dx, vec_w1,
                                                    to_trunk ? h->d_y2 : nullptr, h->H2 * h->H2, 0);
+        stamp(st, 12);
+        if (cfirst) {
+            cudaEventRecord(h->ev_mark[1], st);
+            h->dy2_ready = true;  // the fused MLP backward wrote d_y2 next to d_flat
+            stamp(st, 7);
+            trunk_backward(h, st, /*defer_conv2_wgrad=*/true);
+            stamp(st, 8);
+            // ---- the deferred side work, each behind the point of the chain that produced its input
+            for (int k = 0; k < nheads; ++k) {  // after the loss: second-layer weight / bias gradients
+                const HeadLayout &hd = h->heads[k];
+                const int O = hd.out;
+                cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[0]);
+                gemm(ws, G, h->d_out[k], bh.hbuf[k], h->grads + hd.w2, nullptr, O, H, B, 1, O, H, 1, H, 1, (long long)B * O, gH, P, 0);
+                wgrad_end();
+            }
+            {   // after the loss: conv2's im2col (forward activations only)
+                maexp_learner::Acts &a0 = h->acts[0];
+                const int Hp = h->Hp, H2 = h->H2, F1 = h->F1;
+                cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[0]);
+                im2col_kernel<<<grid1d((long long)B * H2 * H2 * F1 * 4, G), 256, 0, ws>>>(
+                    a0.p, a0.col2, B, F1, H2, H2, (long long)Hp * Hp * F1, 1, (long long)Hp * F1, F1, (long long)B * Hp * Hp * F1,
+                    (long long)B * H2 * H2 * F1 * 4);
+                cudaEventRecord(h->ev_col2, ws);
+                wgrad_end();
+                h->col2_ready = true;
+            }
+            for (int k = 0; k < nheads; ++k) {  // after mlp_fused_bwd: first-layer weight / bias gradients
+                const HeadLayout &hd = h->heads[k];
+                cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[1]);
+                gemm(ws, G, dhs[k], in.x, h->grads + hd.w1, nullptr, H, in.din, B, 1, H, in.x_row, 1, in.din, 1, gH, in.x_g, P, 0);
+                wgrad_end();
+            }
+            {   // after mlp_fused_bwd: every bias gradient of the heads in one launch
+                BiasGradArgs ba = {};
+                int maxc = 0;
+                for (int k = 0; k < nheads; ++k) {
+                    const HeadLayout &hd = h->heads[k];
+                    ba.src[ba.n] = h->d_out[k]; ba.src_g[ba.n] = (long long)B * hd.out; ba.cols[ba.n] = hd.out; ba.dst_off[ba.n] = hd.b2; ++ba.n;
+                    ba.src[ba.n] = dhs[k]; ba.src_g[ba.n] = gH; ba.cols[ba.n] = H; ba.dst_off[ba.n] = hd.b1; ++ba.n;
+                    maxc = hd.out > maxc ? hd.out : maxc;
+                    maxc = H > maxc ? H : maxc;
+                }
+                cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[1]);
+                bias_grads_kernel<<<dim3((maxc + 63) / 64, ba.n, G), 64, 0, ws>>>(ba, h->grads, P, B);
+                wgrad_end();
+            }
+            trunk_backward(h, st, false, /*only_conv2_wgrad=*/true, h->ev_mark[1]);  // after mlp_fused_bwd (d_y2) and the im2col
+            wgrad_close();
+            return;
+        }
         for (int k = 0; k < nheads; ++k) {
             const HeadLayout &hd = h->heads[k];
             cudaStream_t ws = wgrad_begin(st);
@@ -2556,7 +2669,9 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
             mlp_backward(h, st, h->heads[k], in, h->d_out[k], a.h[k], k & 1 ? h->d_h2 : h->d_h, h->has_conv ? h->d_flat : nullptr,
                          k > 0);
     }
+    stamp(st, 7);
     if (h->has_conv) trunk_backward(h, st);
+    stamp(st, 8);
     wgrad_close();
 }
 
@@ -3266,12 +3381,20 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     rc |= lalloc(h, &h->splitk_ws, (size_t)kSplitWorkspaceFloats);
     for (int k = 0; k < kSides; ++k) {
         rc |= lalloc(h, &h->splitk_side[k], (size_t)kSplitWorkspaceFloats);
-        rc |= cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking) != cudaSuccess;
+        {   // MAEXP_SIDE_PRIORITY=low: the weight-gradient / inference branches yield to the data-gradient chain on the main stream
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            const char *pr = getenv("MAEXP_SIDE_PRIORITY");
+            const int prio = (pr && pr[0] == 'l') ? lo : (pr && pr[0] == 'h') ? hi : 0;
+            rc |= cudaStreamCreateWithPriority(&h->side[k], cudaStreamNonBlocking, prio) != cudaSuccess;
+        }
         rc |= cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming) != cudaSuccess;
         rc |= cudaEventCreateWithFlags(&h->ev_w[k], cudaEventDisableTiming) != cudaSuccess;
     }
     rc |= cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess;
     rc |= cudaEventCreateWithFlags(&h->ev_col2, cudaEventDisableTiming) != cudaSuccess;
+    for (int k = 0; k < 2; ++k) rc |= cudaEventCreateWithFlags(&h->ev_mark[k], cudaEventDisableTiming) != cudaSuccess;
+    if (const char *cf = getenv("MAEXP_CRITICAL_FIRST")) h->critical_first = atoi(cf) != 0;
     for (int k = 0; k < 3; ++k) {
         maexp_learner::Acts &a = h->acts[k];
         memset(&a, 0, sizeof(a));
@@ -3429,6 +3552,8 @@ void maexp_learner_destroy(maexp_learner *h) {
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_col2) cudaEventDestroy(h->ev_col2);
+    for (int k = 0; k < 2; ++k)
+        if (h->ev_mark[k]) cudaEventDestroy(h->ev_mark[k]);
     for (void *d : h->allocs) cudaFree(d);
     delete h;
 }
@@ -3614,9 +3739,12 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
     if (!forward_batched(h, st, obs, next_obs, B)) {
         // the training pass is the longest chain: it is issued first (its nodes come first in a captured graph), the side
         // passes fork from the point before it
+        stamp(st, 0);
         cudaEventRecord(h->ev_fork, st);
         forward(h, st, h->online, obs, B, h->acts[0]);
+        stamp(st, 1);
         cudaStream_t s2 = fork_pass(h, st, 0, false);
+        stamp(s2, 2);
         // The distributional nets run two inference passes, target(s') and online(s') (double-DQN action selection), each on its
         // own side stream.  MAEXP_MERGE_INFERENCE_PASSES=1 sends both down ONE branch as grid slices of one trunk launch and one
         // heads launch: under the CUPTI timeline the last of three branches starts ~55 us late and merging looks attractive, but
@@ -3640,9 +3768,12 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         }
         if (!both) {
             forward(h, s2, h->target, next_obs, B, h->acts[2], /*inference=*/true);  // passes 1 and 2 never feed a backward pass
+            stamp(s2, 3);
             if (h->dist) {  // double-DQN action selection by the online net
                 cudaStream_t s1 = fork_pass(h, st, 1, false);
+                stamp(s1, 4);
                 forward(h, s1, h->online, next_obs, B, h->acts[1], /*inference=*/true);
+                stamp(s1, 5);
             }
         }
         join_pass(h, st, 0);
@@ -3665,7 +3796,9 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         else qr_loss_kernel<<<grid, 256, 0, st>>>(p);
     }
     mean_kernel<<<G, 256, 0, st>>>(h->per_sample, loss_out ? loss_out : h->q_tmp, B);
+    stamp(st, 6);
     backward(h, st, obs);
+    stamp(st, 9);
     MAEXP_CUDA_L(cudaGetLastError());
     return 0;
 }
@@ -3724,6 +3857,20 @@ int maexp_learner_grads_iqn(maexp_learner *h, const float *obs, const float *nex
 int maexp_learner_apply(maexp_learner *h, float grad_scale, const uint8_t *active, float *grad_norm_out, void *stream) {
     if (!h) return fail("maexp_learner_apply: null handle");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g_stamps) {  // an eager call prints the stamps of the update before it (e.g. the last graph replay)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        if (cap == cudaStreamCaptureStatusNone) {
+            unsigned long long t[16];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(t, g_stamps, sizeof(t), cudaMemcpyDeviceToHost);
+            const char *name[14] = {"start", "train pass fwd done", "target pass start", "target pass fwd done", "online(s') pass start",
+                                    "online(s') pass fwd done", "loss done", "mlp data-grad chain done", "trunk backward done",
+                                    "all gradients joined", "clip + optimizer done", "mlp_fused_bwd launch", "mlp_fused_bwd done",
+                                    "trunk_fused_bwd done"};
+            for (int i = 0; i < 14; ++i) fprintf(stderr, "  stamp %2d %8.1f us  %s\n", i, (double)((long long)(t[i] - t[0])) * 1e-3, name[i]);
+        }
+    }
     sqnorm_partial_kernel<<<dim3(h->nparts, h->G), 256, 0, st>>>(h->grads, h->partial, h->P, grad_scale);
     if (h->cfg.optimizer == 1) {
         adam_step_kernel<<<(h->G + 63) / 64, 64, 0, st>>>(h->adam_steps, active, h->G);
@@ -3735,6 +3882,7 @@ int maexp_learner_apply(maexp_learner *h, float grad_scale, const uint8_t *activ
                                                             h->cfg.max_norm, h->cfg.learning_rate, h->cfg.alpha,
                                                             h->cfg.one_minus_alpha, h->cfg.eps, active, grad_norm_out);
     }
+    stamp(st, 10);
     MAEXP_CUDA_L(cudaGetLastError());
     return 0;
 }
