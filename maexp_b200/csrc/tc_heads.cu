@@ -607,13 +607,15 @@ __global__ void tc_heads_prepare_kernel(const PrepArgs p) {
     const int g = blockIdx.y;
     const float *src = p.params + (size_t)g * p.P;
     const int n1 = p.nheads * kHidden;
-    const long long w1n = (long long)n1 * p.din;
-    long long total = w1n + n1;
-    for (int h = 0; h < p.nheads; ++h) total += (long long)p.npad[h] * (kHidden + 1);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long j = i;
+    // (32-bit index arithmetic: the panels of one agent are < 2^31 elements -- checked by the host; 64-bit divisions made this
+    // kernel 10 us, on the chain of every forward pass of an update)
+    const int w1n = n1 * p.din;
+    int total = w1n + n1;
+    for (int h = 0; h < p.nheads; ++h) total += p.npad[h] * (kHidden + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int j = i;
         if (j < w1n) {
-            const int r = (int)(j / p.din), k = (int)(j - (long long)r * p.din), h = r / kHidden;
+            const int r = j / p.din, k = j - r * p.din, h = r / kHidden;
             const float v = src[p.w1[h] + (long long)(r - h * kHidden) * p.din + k], hi = tf32_rna(v);
             p.w1hi[(size_t)g * w1n + j] = hi;
             p.w1lo[(size_t)g * w1n + j] = v - hi;
@@ -621,15 +623,15 @@ __global__ void tc_heads_prepare_kernel(const PrepArgs p) {
         }
         j -= w1n;
         if (j < n1) {
-            const int h = (int)j / kHidden;
+            const int h = j / kHidden;
             p.b1cat[(size_t)g * n1 + j] = src[p.b1[h] + (j - h * kHidden)];
             continue;
         }
         j -= n1;
         for (int h = 0; h < p.nheads; ++h) {
-            const long long wn = (long long)p.npad[h] * kHidden;
+            const int wn = p.npad[h] * kHidden;
             if (j < wn) {
-                const int r = (int)(j / kHidden), k = (int)(j - (long long)r * kHidden);
+                const int r = j / kHidden, k = j - r * kHidden;
                 const int rs = (h == 1 && p.perm_A && r < p.out[h]) ? (r % p.perm_A) * p.perm_Z + r / p.perm_A : r;  // source row
                 float v = 0.0f;
                 if (r < p.out[h]) {
@@ -647,7 +649,7 @@ __global__ void tc_heads_prepare_kernel(const PrepArgs p) {
             }
             j -= wn;
             if (j < p.npad[h]) {
-                const int js = (h == 1 && p.perm_A && j < p.out[h]) ? (int)(j % p.perm_A) * p.perm_Z + (int)(j / p.perm_A) : (int)j;
+                const int js = (h == 1 && p.perm_A && j < p.out[h]) ? (j % p.perm_A) * p.perm_Z + j / p.perm_A : j;
                 float b = 0.0f;
                 if (j < p.out[h]) {
                     if (p.mean_Z) {
@@ -682,7 +684,7 @@ namespace {
 // arguments of one pass: panel layout, tensor maps, TMEM plan, epilogue mode; false: shape outside what the kernels handle
 bool plan_pass(int G, const TcHeadsFwd &f, HeadsArgs &a, PrepArgs &p, bool &persistent) {
     if (f.nheads < 1 || f.nheads > 2 || f.H != kHidden || f.din < kBK || f.din % kBK || f.rows < 1 || !f.workspace) return false;
-    if ((reinterpret_cast<uintptr_t>(f.x) & 15) || (f.x_row & 3) || (f.x_g & 3)) return false;
+    if ((reinterpret_cast<uintptr_t>(f.x) & 15) || (f.x_row & 3) || (f.x_g & 3) || f.din > (1 << 20)) return false;
     a = HeadsArgs();
     p = PrepArgs();
     a.nheads = p.nheads = f.nheads;
@@ -790,7 +792,7 @@ bool tc_heads_forward_multi(cudaStream_t st, int G, const TcHeadsFwd *f, int n) 
         }
     }
     if (!set_smem_attr()) return false;
-    for (int q = 0; q < n; ++q) tc_heads_prepare_kernel<<<dim3(64, G), 256, 0, st>>>(p[q]);
+    for (int q = 0; q < n; ++q) tc_heads_prepare_kernel<<<dim3(128, G), 256, 0, st>>>(p[q]);
     tc_heads_kernel<<<dim3((f[0].rows + kBM - 1) / kBM, G, n), kThreads, (size_t)kStages * kStageBytes + 1024, st>>>(aa);
     return cudaGetLastError() == cudaSuccess;
 }
@@ -808,7 +810,7 @@ bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &f) {
     }
     const size_t smem = (size_t)kStages * kStageBytes + 1024;
     if (!set_smem_attr()) return false;
-    tc_heads_prepare_kernel<<<dim3(64, G), 256, 0, st>>>(p);
+    tc_heads_prepare_kernel<<<dim3(128, G), 256, 0, st>>>(p);
     if (persistent) {
         const size_t smem_p = (size_t)kStages * kStageBytes + 1024 + sizeof(float) * kBM * kCPitch;
         static bool attr_p = false;
