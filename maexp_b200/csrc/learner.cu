@@ -1625,6 +1625,95 @@ __global__ void bias_grads_kernel(const BiasGradArgs a, float *grads, long long 
     grads[(size_t)g * P + a.dst_off[t] + c] = (s0 + s1) + (s2 + s3);
 }
 
+// Weight gradients of an update as ONE grouped launch: C[m][n] = sum_k A[k][m] B[k][n] for up to five problems (both operands
+// "K-outer": row = batch sample, the layout d_out / d_h / activations already have), 64 x 64 output tiles, the whole K range in
+// one CTA in ascending order (deterministic, no split-K workspace or reduction launch), register-prefetched 16-row slabs.
+// Replaces the strided split-K GEMM + reduce pairs (2 launches per problem) on the side streams of backward().
+struct WgProblem {
+    const float *A, *B;
+    float *C;
+    long long gA, gB;
+    int M, N, K, lda, ldb, ldc, tiles_n;
+};
+struct WgArgs {
+    WgProblem p[5];
+    int tile0[6];  // prefix sums of the tile counts
+    int n;
+};
+__global__ void __launch_bounds__(256) wgrad_group_kernel(const WgArgs a, long long gC) {
+    __shared__ __align__(16) float As[16][64 + 4];
+    __shared__ __align__(16) float Bs[16][64 + 4];
+    int pi = 0;
+    while (pi + 1 < a.n && (int)blockIdx.x >= a.tile0[pi + 1]) ++pi;
+    const WgProblem &P = a.p[pi];
+    const int t = blockIdx.x - a.tile0[pi], tm = t / P.tiles_n, tn = t - tm * P.tiles_n, g = blockIdx.y;
+    const int m0 = tm * 64, n0 = tn * 64, tid = threadIdx.x;
+    const float *A = P.A + (size_t)g * P.gA, *B = P.B + (size_t)g * P.gB;
+    const int lr = tid >> 4, lc = (tid & 15) * 4;  // this thread's slab element group: row lr, columns lc..lc+3
+    const bool va = (P.lda & 3) == 0 && (P.gA & 3) == 0 && (reinterpret_cast<uintptr_t>(P.A) & 15) == 0;
+    const bool vb = (P.ldb & 3) == 0 && (P.gB & 3) == 0 && (reinterpret_cast<uintptr_t>(P.B) & 15) == 0;
+    auto fetch = [&](const float *src, int ld, int lim, int c0, int k, bool vec) {
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (k < P.K) {
+            const float *s = src + (size_t)k * ld + c0 + lc;
+            if (vec && c0 + lc + 3 < lim) v = *reinterpret_cast<const float4 *>(s);
+            else {
+                if (c0 + lc < lim) v.x = s[0];
+                if (c0 + lc + 1 < lim) v.y = s[1];
+                if (c0 + lc + 2 < lim) v.z = s[2];
+                if (c0 + lc + 3 < lim) v.w = s[3];
+            }
+        }
+        return v;
+    };
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads, a 4 x 4 micro-tile each
+    float4 ra = fetch(A, P.lda, P.M, m0, lr, va), rb = fetch(B, P.ldb, P.N, n0, lr, vb);
+    for (int k0 = 0; k0 < P.K; k0 += 16) {
+        *reinterpret_cast<float4 *>(&As[lr][lc]) = ra;
+        *reinterpret_cast<float4 *>(&Bs[lr][lc]) = rb;
+        __syncthreads();
+        if (k0 + 16 < P.K) {
+            ra = fetch(A, P.lda, P.M, m0, k0 + 16 + lr, va);
+            rb = fetch(B, P.ldb, P.N, n0, k0 + 16 + lr, vb);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *C = P.C + (size_t)g * gC;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= P.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < P.N) C[(size_t)m * P.ldc + n] = acc[i][j];
+        }
+    }
+}
+void wgrad_group(cudaStream_t st, int G, WgArgs &a, long long gC) {
+    a.tile0[0] = 0;
+    for (int i = 0; i < a.n; ++i) {
+        a.p[i].tiles_n = (a.p[i].N + 63) / 64;
+        a.tile0[i + 1] = a.tile0[i] + ((a.p[i].M + 63) / 64) * a.p[i].tiles_n;
+    }
+    wgrad_group_kernel<<<dim3(a.tile0[a.n], G), 256, 0, st>>>(a, gC);
+}
+
 // Weight / bias gradients never feed the data-gradient chain, so inside a backward pass that opts in (g_wg.h set) they
 // are issued on the side streams, in rotation, each behind an event recorded on the main stream at that point.
 struct WGradCtx {
@@ -2624,6 +2713,20 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
             trunk_backward(h, st, /*defer_conv2_wgrad=*/true);
             stamp(st, 8);
             // ---- the deferred side work, each behind the point of the chain that produced its input
+            // MAEXP_WGRAD_GROUPED=1: the weight gradients as two grouped launches without split-K (wgrad_group_kernel).  Measured
+            // SLOWER (224 against 198 us per C51 team update): 224 CTAs with K = 256 .. 1 024 each are long serial chains, the
+            // split-K GEMMs spread the same work over ~4x more CTAs.  Kept as the deterministic single-pass reference.
+            const bool grouped = getenv("MAEXP_WGRAD_GROUPED") != nullptr;
+            if (grouped) {  // after the loss: second-layer weight gradients of all heads, one grouped launch
+                WgArgs wa = {};
+                for (int k = 0; k < nheads; ++k) {
+                    const HeadLayout &hd = h->heads[k];
+                    wa.p[wa.n++] = {h->d_out[k], bh.hbuf[k], h->grads + hd.w2, (long long)B * hd.out, gH, hd.out, H, B, hd.out, H, H, 0};
+                }
+                cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[0]);
+                wgrad_group(ws, G, wa, P);
+                wgrad_end();
+            } else
             for (int k = 0; k < nheads; ++k) {  // after the loss: second-layer weight / bias gradients
                 const HeadLayout &hd = h->heads[k];
                 const int O = hd.out;
@@ -2642,6 +2745,21 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
                 wgrad_end();
                 h->col2_ready = true;
             }
+            if (grouped) {  // after mlp_fused_bwd (d_h, d_y2) and the im2col: first-layer and conv2 weight gradients, one launch
+                WgArgs wa = {};
+                for (int k = 0; k < nheads; ++k) {
+                    const HeadLayout &hd = h->heads[k];
+                    wa.p[wa.n++] = {dhs[k], in.x, h->grads + hd.w1, gH, in.x_g, H, in.din, B, H, (int)in.x_row, in.din, 0};
+                }
+                const int F1 = h->F1, F2 = h->F2, H2 = h->H2, M2 = B * H2 * H2;
+                wa.p[wa.n++] = {h->d_y2, h->acts[0].col2, h->grads + h->o_c2w, (long long)M2 * F2, (long long)M2 * F1 * 4, F2, F1 * 4, M2,
+                                F2, F1 * 4, F1 * 4, 0};
+                cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[1]);
+                cudaStreamWaitEvent(ws, h->ev_col2, 0);
+                h->col2_ready = h->dy2_ready = false;
+                wgrad_group(ws, G, wa, P);
+                wgrad_end();
+            } else
             for (int k = 0; k < nheads; ++k) {  // after mlp_fused_bwd: first-layer weight / bias gradients
                 const HeadLayout &hd = h->heads[k];
                 cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[1]);
@@ -2662,7 +2780,7 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
                 bias_grads_kernel<<<dim3((maxc + 63) / 64, ba.n, G), 64, 0, ws>>>(ba, h->grads, P, B);
                 wgrad_end();
             }
-            trunk_backward(h, st, false, /*only_conv2_wgrad=*/true, h->ev_mark[1]);  // after mlp_fused_bwd (d_y2) and the im2col
+            if (!grouped) trunk_backward(h, st, false, /*only_conv2_wgrad=*/true, h->ev_mark[1]);  // after mlp_fused_bwd (d_y2) and the im2col
             wgrad_close();
             return;
         }
