@@ -57,8 +57,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_trunk_kernel(const __grid_cons
     const int C = TC ? TC : a.C, K1 = C * 4;
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t *a_hi = smem, *a_lo = smem + kSlabs * kASlab;
-    uint8_t *w_hi = smem + 2 * kSlabs * kASlab, *w_lo = w_hi + kSlabs * kWSlab;
-    float *w1t = reinterpret_cast<float *>(w_lo + kSlabs * kWSlab);  // [K1][32] conv1 weight, k-major
+    // conv2's weight slabs: the hi and the lo panel of a slab sit back to back (128 rows), so a_hi x [W_hi; W_lo] is ONE UMMA with
+    // N = 128 (columns 0-63: hi x hi, 64-127: hi x lo) -- an N = 64 UMMA takes the same ~64 cycles as an N = 128 one
+    uint8_t *w_hi = smem + 2 * kSlabs * kASlab, *w_lo = w_hi + kWSlab;  // slab s at + s * 2 * kWSlab
+    float *w1t = reinterpret_cast<float *>(w_hi + 2 * kSlabs * kWSlab);  // [K1][32] conv1 weight, k-major
     float *s_tile = w1t + K1 * 32;  // the tile's 32 observation rows as they sit in HBM ([32][stride]), one bulk copy per tile
     const float *src = a.obs + (size_t)g * a.g_obs;
     const int ntiles = (a.B + kTileObs - 1) / kTileObs;
@@ -82,19 +84,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_trunk_kernel(const __grid_cons
         if ((int)blockIdx.x < ntiles) request_obs(blockIdx.x);
         mbar_expect_tx(&wbar, 2u * kSlabs * kWSlab);
         for (int s = 0; s < kSlabs; ++s) {
-            tma_2d(smem_u32(w_hi + s * kWSlab), &a.tm_w2hi, &wbar, s * kBK, g * kF2);
-            tma_2d(smem_u32(w_lo + s * kWSlab), &a.tm_w2lo, &wbar, s * kBK, g * kF2);
+            tma_2d(smem_u32(w_hi + s * 2 * kWSlab), &a.tm_w2hi, &wbar, s * kBK, g * kF2);
+            tma_2d(smem_u32(w_lo + s * 2 * kWSlab), &a.tm_w2lo, &wbar, s * kBK, g * kF2);
         }
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(64u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = idesc_tf32_m128(kF2);
+    const uint32_t idesc = idesc_tf32_m128(kF2), idesc2 = idesc_tf32_m128(2 * kF2);
     float *dst = a.flat + (size_t)g * a.g_flat;
 
     int it = 0;
@@ -173,13 +175,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_trunk_kernel(const __grid_cons
 #pragma unroll
             for (int s = 0; s < kSlabs; ++s) {
                 const uint32_t aA = smem_u32(a_hi + s * kASlab), aAlo = smem_u32(a_lo + s * kASlab);
-                const uint32_t aW = smem_u32(w_hi + s * kWSlab), aWlo = smem_u32(w_lo + s * kWSlab);
+                const uint32_t aW = smem_u32(w_hi + s * 2 * kWSlab);
 #pragma unroll
                 for (int k = 0; k < kBK / 8; ++k) {
                     const uint32_t ko = (uint32_t)k * 32;
-                    umma_tf32(tmem, smem_desc(aA + ko), smem_desc(aW + ko), idesc, (s > 0 || k > 0) ? 1u : 0u);
-                    umma_tf32(tmem, smem_desc(aAlo + ko), smem_desc(aW + ko), idesc, 1u);
-                    umma_tf32(tmem, smem_desc(aA + ko), smem_desc(aWlo + ko), idesc, 1u);
+                    umma_tf32(tmem, smem_desc(aA + ko), smem_desc(aW + ko), idesc2, (s > 0 || k > 0) ? 1u : 0u);  // hi x [hi; lo]
+                    umma_tf32(tmem, smem_desc(aAlo + ko), smem_desc(aW + ko), idesc, 1u);                       // lo x hi
                 }
             }
             umma_commit(&mbar);
@@ -193,18 +194,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_trunk_kernel(const __grid_cons
             const int row = warp * 32 + lane, b = tile * kTileObs + (row >> 2), pos = row & 3;
 #pragma unroll
             for (int c0 = 0; c0 < kF2; c0 += 16) {
-                uint32_t r[16];
+                uint32_t r[16], r2[16];
                 tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kF2 + c0), r2);
                 if (b < a.B) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) dst[(size_t)b * (kF2 * 4) + (size_t)(c0 + j) * 4 + pos] = __uint_as_float(r[j]) + s_b2[c0 + j];
+                    for (int j = 0; j < 16; ++j)
+                        dst[(size_t)b * (kF2 * 4) + (size_t)(c0 + j) * 4 + pos] = (__uint_as_float(r[j]) + __uint_as_float(r2[j])) + s_b2[c0 + j];
                 }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
 }
 
 __global__ void tc_trunk_prepare_kernel(const float *params, long long P, long long o_c2w, float *hi, float *lo) {
