@@ -1608,21 +1608,33 @@ struct BiasGradArgs {
     long long src_g[4], dst_off[4];
     int cols[4], n;
 };
-__global__ void bias_grads_kernel(const BiasGradArgs a, float *grads, long long P, int rows) {
-    const int g = blockIdx.z, t = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n || c >= a.cols[t]) return;
+__global__ void __launch_bounds__(256) bias_grads_kernel(const BiasGradArgs a, float *grads, long long P, int rows) {
+    // 32 columns x 8 row groups per CTA: row group q sums rows q, q + 8, ... with four interleaved partial sums; the eight
+    // group sums meet in shared memory and are added in the order q = 0..7 (fixed order: deterministic)
+    __shared__ float part[8][33];
+    const int g = blockIdx.z, t = blockIdx.y, lane = threadIdx.x & 31, q = threadIdx.x >> 5, c = blockIdx.x * 32 + lane;
+    if (t >= a.n) return;
     const int stride = a.cols[t];
-    const float *s = a.src[t] + (size_t)g * a.src_g[t] + c;
     float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-    int r = 0;
-    for (; r + 3 < rows; r += 4) {
-        s0 += s[(size_t)r * stride];
-        s1 += s[(size_t)(r + 1) * stride];
-        s2 += s[(size_t)(r + 2) * stride];
-        s3 += s[(size_t)(r + 3) * stride];
+    if (c < stride) {
+        const float *s = a.src[t] + (size_t)g * a.src_g[t] + c;
+        int r = q;
+        for (; r + 24 < rows; r += 32) {
+            s0 += s[(size_t)r * stride];
+            s1 += s[(size_t)(r + 8) * stride];
+            s2 += s[(size_t)(r + 16) * stride];
+            s3 += s[(size_t)(r + 24) * stride];
+        }
+        for (; r < rows; r += 8) s0 += s[(size_t)r * stride];
     }
-    for (; r < rows; ++r) s0 += s[(size_t)r * stride];
-    grads[(size_t)g * P + a.dst_off[t] + c] = (s0 + s1) + (s2 + s3);
+    part[q][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (q == 0 && c < stride) {
+        float sum = part[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) sum += part[k][lane];
+        grads[(size_t)g * P + a.dst_off[t] + c] = sum;
+    }
 }
 
 // Weight gradients of an update as ONE grouped launch: C[m][n] = sum_k A[k][m] B[k][n] for up to five problems (both operands
@@ -2777,7 +2789,7 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
                     maxc = H > maxc ? H : maxc;
                 }
                 cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[1]);
-                bias_grads_kernel<<<dim3((maxc + 63) / 64, ba.n, G), 64, 0, ws>>>(ba, h->grads, P, B);
+                bias_grads_kernel<<<dim3((maxc + 31) / 32, ba.n, G), 256, 0, ws>>>(ba, h->grads, P, B);
                 wgrad_end();
             }
             if (!grouped) trunk_backward(h, st, false, /*only_conv2_wgrad=*/true, h->ev_mark[1]);  // after mlp_fused_bwd (d_y2) and the im2col
