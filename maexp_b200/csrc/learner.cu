@@ -2729,27 +2729,31 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
             // SLOWER (224 against 198 us per C51 team update): 224 CTAs with K = 256 .. 1 024 each are long serial chains, the
             // split-K GEMMs spread the same work over ~4x more CTAs.  Kept as the deterministic single-pass reference.
             const bool grouped = getenv("MAEXP_WGRAD_GROUPED") != nullptr;
+            // when the second-layer weight gradients and the im2col start: 0 = right after the loss (beside mlp_fused_bwd), 1 = after it
+            // (measured: 200 us per C51 team update against 220 us -- the early start wins although it slows mlp_fused_bwd down)
+            static const int late = getenv("MAEXP_WGRAD_LATE") ? atoi(getenv("MAEXP_WGRAD_LATE")) : 0;
+            cudaEvent_t ev_w2 = h->ev_mark[late ? 1 : 0];
             if (grouped) {  // after the loss: second-layer weight gradients of all heads, one grouped launch
                 WgArgs wa = {};
                 for (int k = 0; k < nheads; ++k) {
                     const HeadLayout &hd = h->heads[k];
                     wa.p[wa.n++] = {h->d_out[k], bh.hbuf[k], h->grads + hd.w2, (long long)B * hd.out, gH, hd.out, H, B, hd.out, H, H, 0};
                 }
-                cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[0]);
+                cudaStream_t ws = wgrad_begin_at(st, ev_w2);
                 wgrad_group(ws, G, wa, P);
                 wgrad_end();
             } else
             for (int k = 0; k < nheads; ++k) {  // after the loss: second-layer weight / bias gradients
                 const HeadLayout &hd = h->heads[k];
                 const int O = hd.out;
-                cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[0]);
+                cudaStream_t ws = wgrad_begin_at(st, ev_w2);
                 gemm(ws, G, h->d_out[k], bh.hbuf[k], h->grads + hd.w2, nullptr, O, H, B, 1, O, H, 1, H, 1, (long long)B * O, gH, P, 0);
                 wgrad_end();
             }
             {   // after the loss: conv2's im2col (forward activations only)
                 maexp_learner::Acts &a0 = h->acts[0];
                 const int Hp = h->Hp, H2 = h->H2, F1 = h->F1;
-                cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[0]);
+                cudaStream_t ws = wgrad_begin_at(st, ev_w2);
                 im2col_kernel<<<grid1d((long long)B * H2 * H2 * F1 * 4, G), 256, 0, ws>>>(
                     a0.p, a0.col2, B, F1, H2, H2, (long long)Hp * Hp * F1, 1, (long long)Hp * F1, F1, (long long)B * Hp * Hp * F1,
                     (long long)B * H2 * H2 * F1 * 4);
