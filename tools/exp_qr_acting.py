@@ -1,5 +1,5 @@
 import os, sys, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from maexp_b200.config import baseline_config
 from maexp_b200.core.agents.brains import LearnerGroup
 B, G = 65536, 8
