@@ -486,6 +486,7 @@ def test_large_batch_inference_path_matches_oracle(kind, V, C, B):
     cfg, _ = golden_configs()[kind]
     G = 2
     cfg = cfg.merged_with(batch_size=B, visible_range=V)
+    torch.manual_seed(11)  # fixed initialisation: the three-term TF32 error (3-6e-6 over random nets, tools/exp_tc_accuracy.py) is then the same every run
     g = LearnerGroup(cfg, [C, V, V], 4, G, B)
     gen = torch.Generator().manual_seed(3)
     obs = (torch.rand((G, B, C, V, V), generator=gen) < 0.25).float()
