@@ -1424,6 +1424,7 @@ struct maexp_learner {
     bool tc_heads = true;          // acting batches: both layers of all heads in one TMA-fed tcgen05 kernel (csrc/tc_heads.cu; MAEXP_TC_HEADS=0: GEMM by GEMM)
     bool tc_trunk = true;          // acting batches: conv2 of the trunk as an implicit GEMM on tcgen05 (csrc/tc_trunk.cu; MAEXP_TC_TRUNK=0: CUDA cores)
     float *tc_trunk_ws = nullptr;
+    struct { const float *key; float *ws; } tc_trunk_upd[4] = {};  // the update's passes run concurrently: one panel buffer each
     float *tc_heads_ws = nullptr;  // its pre-split weight panels
     size_t tc_heads_ws_floats = 0;
     // the same kernel for the forward passes of an update (online(s), online(s'), target(s') run concurrently on their own
@@ -1512,6 +1513,18 @@ struct maexp_learner {
 };
 
 namespace {
+
+// Lazily allocated kernel workspaces (weight panels every reader's prepare kernel overwrites completely): NO memset -- cudaMemset
+// runs on the legacy default stream, which does not order against the non-blocking side streams the update's passes run on, and
+// zeroed a panel after its prepare kernel had written it (a first-call race: gradients off by 40 % once in a few runs).
+template <typename T>
+int lalloc_scratch(maexp_learner *h, T **ptr, size_t count) {
+    void *d = nullptr;
+    MAEXP_CUDA_L(cudaMalloc(&d, (count ? count : 1) * sizeof(T)));
+    h->allocs.push_back(d);
+    *ptr = static_cast<T *>(d);
+    return 0;
+}
 
 template <typename T>
 int lalloc(maexp_learner *h, T **ptr, size_t count) {
@@ -2304,19 +2317,43 @@ bool trunk_forward_multi(maexp_learner *h, cudaStream_t st, int n, const float *
     const long long P = h->P, Bmax = h->B, stride = h->cfg.obs_stride;
     if (!h->fused_trunk || F1 > 32 || F2 > 64 || !(V == 5 || V == 7 || V == 9) || n < 1 || n > 3) return false;
     // acting / evaluation batches: conv1 + pooling on the CUDA cores, conv2 as an implicit GEMM on the tensor cores
-    if (g_inference_tc && h->use_tc && h->tc_trunk && n == 1 && !train[0] && B >= 2048 && V == 7 && F1 == 32 && F2 == 64) {
-        if (!h->tc_trunk_ws) {
-            float *ws = nullptr;
-            if (lalloc(h, &ws, tc_trunk_workspace_floats(G)) == 0) h->tc_trunk_ws = ws;
+    // ... and the passes of an update (>= 128 rows; the training pass also keeps the pooled map and the argmax)
+    const bool tc_acting = g_inference_tc && !train[0] && B >= 2048, tc_update = !g_inference_tc && h->tc_mlp && B >= 128 &&
+               (h->cfg.kind == MAEXP_LEARNER_C51 || h->cfg.kind == MAEXP_LEARNER_DQN_CONV_MLP);  // (the quantile-Huber gradients of QR-DQN / IQN amplify the 2e-6 past the gradient bar)
+    if (h->use_tc && h->tc_trunk && n == 1 && (tc_acting || tc_update) && V == 7 && F1 == 32 && F2 == 64) {
+        float *panel = nullptr;
+        if (tc_acting) {
+            if (!h->tc_trunk_ws) {
+                float *ws = nullptr;
+                if (lalloc_scratch(h, &ws, tc_trunk_workspace_floats(G)) == 0) h->tc_trunk_ws = ws;
+            }
+            panel = h->tc_trunk_ws;
+        } else {
+            for (int k = 0; k < 4 && !panel; ++k) {
+                auto &e = h->tc_trunk_upd[k];
+                if (e.key == acts[0]->flat || !e.key) {
+                    if (!e.ws) {
+                        float *ws = nullptr;
+                        if (lalloc_scratch(h, &ws, tc_trunk_workspace_floats(G))) break;
+                        e.ws = ws;
+                    }
+                    e.key = acts[0]->flat;
+                    panel = e.ws;
+                }
+            }
         }
-        if (h->tc_trunk_ws) {
+        if (panel) {
             TcTrunkFwd t = {};
             t.obs = obs[0]; t.params = params[0]; t.flat = acts[0]->flat;
             t.stride = stride; t.g_obs = (long long)B * stride; t.P = P;
             t.o_c1w = h->o_c1w; t.o_c1b = h->o_c1b; t.o_c2w = h->o_c2w; t.o_c2b = h->o_c2b; t.g_flat = Bmax * h->D;
             t.B = B; t.C = C; t.V = V; t.F1 = F1; t.F2 = F2;
-            t.workspace = h->tc_trunk_ws;
-            if (tc_trunk_forward(st, G, t)) return true;
+            t.workspace = panel;
+            if (train[0]) { t.p_out = acts[0]->p; t.arg_out = acts[0]->arg; t.g_p = Bmax * Hp * Hp * F1; }
+            if (tc_trunk_forward(st, G, t)) {
+                if (train[0]) { h->bwd_obs = obs[0]; h->fused_trunk_acts = true; }
+                return true;
+            }
         }
     }
     // the 32 KB of conv2 weights are staged once per CTA: 16 warps per CTA at the update batch sizes, so that the three
@@ -2466,7 +2503,7 @@ bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const flo
         const size_t need = tc_heads_workspace_floats(h->G, nheads, in.din, outs_n);
         if (need > h->tc_heads_ws_floats) {  // first call (or a wider layer): the old panel buffer stays in h->allocs until destroy
             float *ws = nullptr;
-            if (lalloc(h, &ws, need) == 0) { h->tc_heads_ws = ws; h->tc_heads_ws_floats = need; }
+            if (lalloc_scratch(h, &ws, need) == 0) { h->tc_heads_ws = ws; h->tc_heads_ws_floats = need; }
         }
         if (need <= h->tc_heads_ws_floats) {
             TcHeadsFwd t = {};
@@ -2512,7 +2549,7 @@ bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const flo
             auto &e = h->tc_heads_upd[slot];
             if (e.floats < need) {
                 float *ws = nullptr;
-                if (lalloc(h, &ws, need)) { ok = false; break; }
+                if (lalloc_scratch(h, &ws, need)) { ok = false; break; }
                 e.ws = ws; e.floats = need;
             }
             e.key = outs[q][0];

@@ -43,11 +43,14 @@ struct alignas(64) TrunkArgs {
     float *flat;
     long long stride, g_obs, P, o_c1w, o_c1b, o_c2b, g_flat;
     int B, C;
+    float *p_out;      // TRAIN: pooled map [G][.][9][32] (NHWC) and pooling argmax the backward pass reads (group pitch g_p)
+    uint8_t *arg_out;
+    long long g_p;
     long long *dbg;  // MAEXP_TC_TRUNK_DBG: cycle stamps of CTA (0, 0)
 };
 
 // TC > 0: the number of observation channels at compile time (the per-channel cell reads become 128-bit loads at static offsets)
-template <int TC>
+template <int TC, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) tc_trunk_kernel(const __grid_constant__ TrunkArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t wbar, mbar, obar;
@@ -151,9 +154,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_trunk_kernel(const __grid_cons
                     }
                 }
                 float p[kCells];
+                if constexpr (TRAIN) {
+                    // the learner's online(s) pass keeps what the backward pass reads: the pooled map (NHWC) and the pooling argmax
+                    // -- bias added before the comparison, first maximum wins, as F.max_pool2d on the biased conv output
+                    const float bb = s_b1[lane];
 #pragma unroll
-                for (int cell = 0; cell < kCells; ++cell)  // max(x_i) + b == max(x_i + b)
-                    p[cell] = fmaxf(fmaxf(acc[cell][0], acc[cell][1]), fmaxf(acc[cell][2], acc[cell][3])) + s_b1[lane];
+                    for (int cell = 0; cell < kCells; ++cell) {
+                        float best = acc[cell][0] + bb;
+                        int bi = 0;
+                        if (acc[cell][1] + bb > best) { best = acc[cell][1] + bb; bi = 1; }
+                        if (acc[cell][2] + bb > best) { best = acc[cell][2] + bb; bi = 2; }
+                        if (acc[cell][3] + bb > best) { best = acc[cell][3] + bb; bi = 3; }
+                        p[cell] = best;
+                        const size_t pi = (size_t)g * a.g_p + ((size_t)b * kCells + cell) * kF1 + lane;
+                        a.p_out[pi] = best;
+                        a.arg_out[pi] = (uint8_t)bi;
+                    }
+                } else {
+#pragma unroll
+                    for (int cell = 0; cell < kCells; ++cell)  // max(x_i) + b == max(x_i + b)
+                        p[cell] = fmaxf(fmaxf(acc[cell][0], acc[cell][1]), fmaxf(acc[cell][2], acc[cell][3])) + s_b1[lane];
+                }
                 // K = ic * 4 + tap (conv2 weight layout [oc][ic][kh][kw]): lane = ic owns chunk ic of every row of this observation
                 const int slab = lane >> 3, chunk = lane & 7;
 #pragma unroll
@@ -240,12 +261,15 @@ bool tc_trunk_forward(cudaStream_t st, int G, const TcTrunkFwd &f) {
     const size_t smem = 2 * (size_t)kSlabs * kASlab + 2 * (size_t)kSlabs * kWSlab +
                         sizeof(float) * ((size_t)f.C * 4 * 32 + (size_t)kTileObs * f.stride) + 1024;
     if (smem > 227 * 1024) return false;  // (7 channels: 44 KB of observations per tile do not fit next to the operand tiles)
-    auto fn = f.C == 3 ? tc_trunk_kernel<3> : tc_trunk_kernel<0>;
-    static size_t attr[2] = {0, 0};
-    if (smem > attr[f.C == 3]) {
+    const bool train = f.p_out != nullptr && f.arg_out != nullptr;
+    auto fn = train ? (f.C == 3 ? tc_trunk_kernel<3, true> : tc_trunk_kernel<0, true>) : (f.C == 3 ? tc_trunk_kernel<3, false> : tc_trunk_kernel<0, false>);
+    static size_t attr[4] = {0, 0, 0, 0};
+    const int ai = (f.C == 3) + 2 * train;
+    if (smem > attr[ai]) {
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-        attr[f.C == 3] = smem;
+        attr[ai] = smem;
     }
+    a.p_out = f.p_out; a.arg_out = f.arg_out; a.g_p = f.g_p;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

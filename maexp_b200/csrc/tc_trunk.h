@@ -13,6 +13,9 @@ struct TcTrunkFwd {
     long long stride, g_obs, P, o_c1w, o_c1b, o_c2w, o_c2b, g_flat;
     int B, C, V, F1, F2;
     float *workspace;     // tc_trunk_workspace_floats() floats, 16-byte aligned: the pre-split conv2 weight panels
+    float *p_out;         // training pass: pooled map [G][.][9][32] and pooling argmax for the backward pass (group pitch g_p), or nullptr
+    unsigned char *arg_out;
+    long long g_p;
 };
 size_t tc_trunk_workspace_floats(int G);
 // false: shape outside what the kernel handles (visible_range 7, 32 / 64 filters); the caller falls back to the CUDA-core kernel

@@ -75,7 +75,9 @@ def test_all_reduced_update_equals_single_gpu_update_on_global_batch(kind):
     from maexp_b200.core.agents.brains import LearnerGroup
     from oracle.make_golden_learner import configs as golden_configs
     cfg, shape = golden_configs()[kind]
-    G, B, world = 2, 64, 2
+    # B = 128 per rank: the ranks and the global-batch learner then take the same kernels (update batches of >= 128 rows run the
+    # conv2 / MLP-head contractions on the tensor cores with three TF32 terms; 64 + 64 against 128 would compare two arithmetic paths)
+    G, B, world = 2, 128, 2
     C, V = shape[0], shape[1]
     torch.manual_seed(3)
     ranks = [LearnerGroup(cfg.merged_with(batch_size=B), shape, 4, G, B) for _ in range(world)]
