@@ -1429,7 +1429,7 @@ struct maexp_learner {
     size_t tc_heads_ws_floats = 0;
     // the same kernel for the forward passes of an update (online(s), online(s'), target(s') run concurrently on their own
     // streams): one panel buffer per pass, keyed by the pass's output buffer
-    struct { const float *key; float *ws; size_t floats; } tc_heads_upd[4] = {};
+    struct { const float *key; float *ws; size_t floats; } tc_heads_upd[8] = {};
     bool fused_trunk = true;       // one-kernel conv trunk for every local-view pass (MAEXP_FUSED_TRUNK=0: layer by layer)
     const float *bwd_obs = nullptr;  // observations of the last training pass (conv1's im2col in trunk_backward)
     float *trunk_part = nullptr;      // block partials of trunk_fused_bwd_kernel
@@ -2536,14 +2536,46 @@ bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const flo
     // activation handed from the first accumulator to the second contraction inside the SM (csrc/tc_mlp.cu)
     // (not IQN: its quantile-Huber gradients amplify the 2e-6 of the three-term TF32 products past the 1e-4 gradient bar)
     if (h->tc_mlp && h->tc_heads && !h->iqn && !g_inference_tc && in.rows >= 128 && H == 128 && in.din >= 32 && in.din % 32 == 0) {
-        // TMA-fed kernel, all heads of a pass in one CTA per 128-row tile (csrc/tc_heads.cu)
+        // TMA-fed kernel (csrc/tc_heads.cu).  A single pass with two heads (what the update's three streams issue) runs one head
+        // per CTA -- two grid slices, each with its own 128-column first accumulator: an update batch is only two row tiles per
+        // agent, so the kernel's time is one CTA's latency, and a head's 12 K slabs are shorter than both heads' 16
+        // (34 -> 27 us per pass; MAEXP_TC_HEADS_SPLIT=0: both heads in one CTA).  The x slab is loaded and split twice.
+        static const bool split_heads = !(getenv("MAEXP_TC_HEADS_SPLIT") && atoi(getenv("MAEXP_TC_HEADS_SPLIT")) == 0);
+        if (n == 1 && nheads == 2 && split_heads) {
+            bool ok1 = true;
+            TcHeadsFwd ent[2] = {};
+            for (int k = 0; k < 2 && ok1; ++k) {
+                int outs_n[2] = {hds[k].out, 0};
+                const size_t need = tc_heads_workspace_floats(h->G, 1, in.din, outs_n);
+                int slot = -1;
+                for (int j = 0; j < 8 && slot < 0; ++j)
+                    if (h->tc_heads_upd[j].key == outs[0][k] || !h->tc_heads_upd[j].key) slot = j;
+                if (slot < 0) { ok1 = false; break; }
+                auto &e = h->tc_heads_upd[slot];
+                if (e.floats < need) {
+                    float *ws = nullptr;
+                    if (lalloc_scratch(h, &ws, need)) { ok1 = false; break; }
+                    e.ws = ws; e.floats = need;
+                }
+                e.key = outs[0][k];
+                TcHeadsFwd &t = ent[k];
+                t.x = ins[0].x; t.x_row = ins[0].x_row; t.x_g = ins[0].x_g;
+                t.params = params[0]; t.P = P;
+                t.nheads = 1;
+                t.w1[0] = hds[k].w1; t.b1[0] = hds[k].b1; t.w2[0] = hds[k].w2; t.b2[0] = hds[k].b2; t.out[0] = hds[k].out;
+                t.outp[0] = outs[0][k]; t.hbuf[0] = hbufs[0][k];
+                t.rows = ins[0].rows; t.rows_max = ins[0].rows_max; t.din = ins[0].din; t.H = H;
+                t.workspace = e.ws;
+            }
+            if (ok1 && tc_heads_forward_multi(st, h->G, ent, 2)) return true;
+        }
         bool ok = true;
         TcHeadsFwd passes[3] = {};
         for (int q = 0; q < n && ok; ++q) {
             int outs_n[2] = {hds[0].out, nheads > 1 ? hds[1].out : 0};
             const size_t need = tc_heads_workspace_floats(h->G, nheads, in.din, outs_n);
             int slot = -1;
-            for (int k = 0; k < 4 && slot < 0; ++k)
+            for (int k = 0; k < 8 && slot < 0; ++k)
                 if (h->tc_heads_upd[k].key == outs[q][0] || !h->tc_heads_upd[k].key) slot = k;
             if (slot < 0) { ok = false; break; }
             auto &e = h->tc_heads_upd[slot];
