@@ -2539,7 +2539,8 @@ bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const flo
         // TMA-fed kernel (csrc/tc_heads.cu).  A single pass with two heads (what the update's three streams issue) runs one head
         // per CTA -- two grid slices, each with its own 128-column first accumulator: an update batch is only two row tiles per
         // agent, so the kernel's time is one CTA's latency, and a head's 12 K slabs are shorter than both heads' 16
-        // (34 -> 27 us per pass; MAEXP_TC_HEADS_SPLIT=0: both heads in one CTA).  The x slab is loaded and split twice.
+        // (the forward phase of a C51 update ends at 58 instead of 65 us, the update takes 182 instead of 189 us;
+        // MAEXP_TC_HEADS_SPLIT=0: both heads in one CTA).  The x slab is loaded and split twice.
         static const bool split_heads = !(getenv("MAEXP_TC_HEADS_SPLIT") && atoi(getenv("MAEXP_TC_HEADS_SPLIT")) == 0);
         if (n == 1 && nheads == 2 && split_heads) {
             bool ok1 = true;
