@@ -1,6 +1,11 @@
-// TMA-fed, warp-specialised tcgen05 kernel for the acting / evaluation batches (>= 512 rows per agent): the two-layer MLP
-// heads of core/agents/models/mlp.py:28-34 -- fc_V and fc_A of the distributional networks, `mlp` of ConvMLP -- as ONE
-// kernel per forward pass:
+// TMA-fed, warp-specialised tcgen05 kernels for the two-layer MLP heads of core/agents/models/mlp.py:28-34 -- fc_V and fc_A of
+// the distributional networks, `mlp` of ConvMLP -- as ONE kernel per forward pass.  Three entry points of the same pipeline:
+//   tc_heads_kernel          one CTA per 128-row tile; raw head outputs (+ the hidden activation for a backward pass) or the
+//                            fused greedy-value epilogue; up to three passes / heads as grid slices (the update's forward passes)
+//   tc_heads_acting_kernel   persistent form for the acting batches of the 4-action dueling distributional networks: the
+//                            epilogue of tile i overlaps the main loop of tile i + 1 (further down)
+//   quantile-mean collapse   QR-DQN acting: the second layer shrinks to 1 + A rows (plan_pass)
+//
 //
 //     hidden_k = relu(x W1_k^T + b1_k)   (all heads share x: one UMMA with N = heads * 128 columns)
 //     out_k    = hidden_k W2_k^T + b2_k  (the hidden activation goes from tensor memory through bias + ReLU back into shared
@@ -9,7 +14,7 @@
 // Every fp32 product is evaluated as three TF32 terms (a_hi b_hi + a_lo b_hi + a_hi b_lo, a_hi = rna-tf32(a)), which keeps
 // the Q-values inside the learner's 1e-5 parity bar (tests/test_learner_gpu.py large-batch tests).
 //
-// Roles (192 threads, one CTA per 128-row tile and agent, one CTA per SM: it owns all 512 TMEM columns):
+// Roles of tc_heads_kernel (320 threads, one CTA per 128-row tile and agent, one CTA per SM: it owns all 512 TMEM columns):
 //   warp 0      producer: one thread issues the TMA loads (cp.async.bulk.tensor, SWIZZLE_128B boxes of 32 floats x rows) of the
 //               raw fp32 x slab and of the PRE-SPLIT weight slabs (hi / lo panels written once per call by
 //               tc_heads_prepare_kernel, so no thread ever touches a weight) into a two-stage ring, mbarrier expect_tx
@@ -17,7 +22,10 @@
 //               tcgen05.commit, whose mbarrier arrival hands the stage back to the producer
 //   warps 2-5   layer 1: split the x slab into hi / lo in place (shared -> registers -> shared, no global latency on this
 //               path); layer 2: read 32 hidden columns of their TMEM lane quadrant (tcgen05.ld), bias + ReLU, split, store
-//               the swizzled A slab; at the end: the output epilogue (bias, row stores)
+//               the swizzled A slab
+//   warps 2-9   epilogue, two threads per row: accumulators -> shared memory (odd pitch), then either coalesced row stores of the
+//               raw outputs or the dueling combination + expectation (greedy_values_row)
+// Tried and dropped in the persistent kernel: eight operand warps (two threads per row in layer 2) -- 0.63 against 0.61 ms.
 // Stage hand-offs: full[s] (TMA bytes landed) -> conv[s] (operands split, fence.proxy.async) -> MMA -> empty[s] (commit).
 // TMEM: columns [0, heads*128) hold the first accumulator; the widest head's output sits at column 256, the other head's
 // output re-uses the first-processed head's hidden columns once they have been consumed.
