@@ -3,7 +3,8 @@
 // env_step_kernel (env_kernel.cuh) gives every environment one lane for the whole sequential phase, so half of the warp
 // idles there (16 environments per warp) and every agent's window crop sits on one long per-lane chain.  The reference's
 // order dependence is much narrower than that (default_environment.py:153-175, abstract_world.py:39-78):
-//   * moves are sequential in `order`  -> the environment's first lane (the "leader") resolves them, 8 short iterations;
+//   * moves are sequential in `order`  -> every lane derives its agent's rank, target cell and wall test in parallel, then N short
+//     rounds (one mover per environment and round) update the agents bit grid;
 //   * a pickup happens on the agent's own cell, agents never share a cell and a respawned object never lands on an agent
 //     (default_environment.py:134-148), so all N pickup tests are independent -> one test per lane, a ballot collects them;
 //   * respawns draw from one per-environment stream and must not collide with each other -> the leader replays the (rare)
@@ -11,9 +12,10 @@
 //   * agent i observes the objects after pickups / respawns 0..i -> every lane crops the FINAL grid and undoes the logged
 //     events of the agents behind it (pickup cells and respawn cells are disjoint sets, so the order of the undo is free);
 //   * per-agent rewards, done flags, positions and the 147 observation bits are element-wise -> one lane each, coalesced.
-// A warp owns 32 / N environments per work item (4 at N = 8), work items come from an atomic queue (4x more, shorter items
-// than env_step_kernel's groups, so warps drift apart and the stores of one overlap the logic of another), and the
-// expansion phase is the same arithmetic 4-bit -> float4 expansion with 128-bit streaming stores.
+// A warp owns 32 / N environments per work item (4 at N = 8; 4x more, shorter items than env_step_kernel's groups), items are
+// dealt round-robin (an atomic queue -- one same-address fetch per item -- cost 10 us per step and stays behind
+// MAEXP_LANES_QUEUE=1), the next item's state is requested before the current item's stores start, and the expansion phase is
+// the same arithmetic 4-bit -> float4 expansion with 128-bit streaming stores.
 // Shapes: N in {2, 4, 8}, one object type, the three default channels (agents, objects, area), visible_range 5 / 7, no
 // observation noise; everything else (and calls that ask for heat-maps, coordinates or object snapshots) runs
 // env_step_kernel on the same state.  Results are bit-identical to it (tests/test_env_gpu.py runs both).

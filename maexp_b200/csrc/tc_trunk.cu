@@ -1,4 +1,5 @@
-// Conv trunk of the acting / evaluation batches with the second convolution on the 5th-generation tensor cores
+// Conv trunk of the acting / evaluation batches and of the C51 / DQN update passes (TRAIN keeps the pooled map and the pooling
+// argmax for the backward pass) with the second convolution on the 5th-generation tensor cores
 // (core/agents/models/customs/convolution.py: conv 2x2 -> max_pool2d(2, 2) -> conv 2x2 -> flatten; visible_range 7, 32 and
 // 64 filters).  conv2 is 70 % of the trunk's arithmetic and, as an implicit GEMM, a dense contraction:
 //
@@ -9,9 +10,10 @@
 //               conv1 channel, the agent's conv1 weights in shared memory); every lane then writes the four im2col chunks of its
 //               channel (the 2x2 taps under each output position are 4 consecutive K values = one 16-byte chunk), split into
 //               TF32 hi / lo, straight into the K-major SWIZZLE_128B operand tile -- the pooled map never exists in memory
-//   warp 0      one thread issues 48 tcgen05.mma.cta_group::1.kind::tf32 per tile (4 K slabs x 4 K steps x 3 TF32 terms:
-//               a_hi b_hi + a_lo b_hi + a_hi b_lo, fp32-level accuracy) into a 64-column TMEM accumulator and commits to an
-//               mbarrier.  conv2's weights are pre-split hi / lo panels, loaded ONCE per CTA by TMA (eight 8 KB boxes)
+//   warp 0      one thread issues 32 tcgen05.mma.cta_group::1.kind::tf32 per tile (4 K slabs x 4 K steps x {a_hi [b_hi; b_lo] with
+//               N = 128, a_lo b_hi with N = 64}: the three TF32 terms, fp32-level accuracy) into a 128-column TMEM accumulator
+//               (the epilogue adds the two halves) and commits to an mbarrier.  conv2's weights are pre-split hi / lo panels,
+//               loaded ONCE per CTA by TMA (eight 8 KB boxes); the tile's observations arrive by one TMA bulk copy
 //   warps 0-3   epilogue: tcgen05.ld of their TMEM lane quadrant, bias, stores in PyTorch's flatten order (the four output
 //               positions of an observation sit in four neighbouring lanes: 16 contiguous bytes per output channel)
 // The conv warps start the next tile's observations as soon as the MMAs have released the operand tile, while the epilogue
