@@ -719,6 +719,79 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                 default: expand_group<0, EPW>(s_w, dst, lane, p.slot_floats, p.q_str, p.q_tail, p.sub_str, p.sub_tail);
                 }
             } else {
+            bool pairs_done = false;
+            if constexpr (NOISE == MAEXP_NOISE_FLIP) {
+                if (!p.noise_tape) {
+                    // Flip noise with on-chip draws: 16-bit uniforms, EIGHT per Philox4x32-10 call (element k: call k >> 3, word
+                    // (k & 7) >> 1, low half for even k; DESIGN.md RNG specification, oracle noise_draw).  A lane owns a PAIR of
+                    // quads (8 consecutive elements = one call = 32 contiguous output bytes), so the draws cost half the calls of
+                    // the one-word-per-element form (86 -> 43 per agent-step at C = 7, V = 7).
+                    auto u16f = [](uint32_t h) { return __fadd_rn(__uint_as_float(0x3f800000u | (h << 7)), -1.0f); };  // h / 65536, exact
+                    auto flip4 = [&](float (&v)[4], uint32_t w0, uint32_t w1, const QuadNoise &qn) {
+                        const float dr[4] = {u16f(w0 & 0xFFFFu), u16f(w0 >> 16), u16f(w1 & 0xFFFFu), u16f(w1 >> 16)};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {  // flip_observation_noise.py:28-46
+                            float x = __fadd_rn(v[j], qn.pre[j]);
+                            x = __fadd_rn(x, __fmul_rn(dr[j], qn.scale[j]));
+                            x = fabsf(rintf(x));
+                            v[j] = __fadd_rn(x, -qn.pre[j]);
+                        }
+                    };
+                    auto emit_pair = [&](int e, int qp, uint32_t word, int lut_a, int lut_b, const QuadNoise &qa, const QuadNoise &qb,
+                                         bool has_b) {
+                        const int q0 = 2 * qp, sh = (q0 & 7) * 4, off = e * env_stride + q0 * 4;
+                        const float4 oa = s_lut[lut_a + ((word >> sh) & 0xFu)], ob = s_lut[lut_b + ((word >> (sh + 4)) & 0xFu)];
+                        if (dst_rel) {  // merged: the relative key stays clean
+                            store_quad(reinterpret_cast<float4 *>(dst_rel + off), oa);
+                            if (has_b) store_quad(reinterpret_cast<float4 *>(dst_rel + off + 4), ob);
+                        }
+                        float va[4] = {oa.x, oa.y, oa.z, oa.w}, vb[4] = {ob.x, ob.y, ob.z, ob.w};
+                        if (s_active[e] & 2) {
+                            const uint4 w = philox4x32_10(p.seed, p.gid0 + (uint32_t)(env0 + e), p.tick, kStreamNoise, (uint32_t)qp, (uint32_t)i);
+                            flip4(va, w.x, w.y, qa);
+                            flip4(vb, w.z, w.w, qb);
+                        }
+                        store_quad(reinterpret_cast<float4 *>(dst + off), make_float4(va[0], va[1], va[2], va[3]));
+                        if (has_b) store_quad(reinterpret_cast<float4 *>(dst + off + 4), make_float4(vb[0], vb[1], vb[2], vb[3]));
+                    };
+                    const int npairs = (qps + 1) >> 1, nfullp = npairs >> 5, remp = npairs & 31;
+                    for (int c = 0; c < nfullp; ++c) {
+                        const int qp = c * 32 + lane, q0 = 2 * qp;
+                        const bool has_b = q0 + 1 < qps;
+                        const int lut_a = quad_class(q0), lut_b = quad_class(q0 + 1);
+                        const uint32_t *wq = s_w + (q0 >> 3) * EPW;
+                        const QuadNoise qa = quad_noise(q0), qb = quad_noise(q0 + 1);
+                        if (!check) {
+#pragma unroll kUnrollEnvs
+                            for (int e = 0; e < nenv; ++e) emit_pair(e, qp, wq[e], lut_a, lut_b, qa, qb, has_b);
+                        } else {
+                            for (int e = 0; e < nenv; ++e)
+                                if (s_active[e] & 1) emit_pair(e, qp, wq[e], lut_a, lut_b, qa, qb, has_b);
+                        }
+                    }
+                    if (remp) {
+                        int pitch = 1;
+                        while (pitch < remp) pitch <<= 1;
+                        const int r = lane & (pitch - 1), esub = lane / pitch, estep = 32 / pitch;
+                        if (r < remp) {
+                            const int qp = nfullp * 32 + r, q0 = 2 * qp;
+                            const bool has_b = q0 + 1 < qps;
+                            const int lut_a = quad_class(q0), lut_b = quad_class(q0 + 1);
+                            const uint32_t *wq = s_w + (q0 >> 3) * EPW;
+                            const QuadNoise qa = quad_noise(q0), qb = quad_noise(q0 + 1);
+                            if (!check) {
+#pragma unroll kUnrollEnvs
+                                for (int e = esub; e < nenv; e += estep) emit_pair(e, qp, wq[e], lut_a, lut_b, qa, qb, has_b);
+                            } else {
+                                for (int e = esub; e < nenv; e += estep)
+                                    if (s_active[e] & 1) emit_pair(e, qp, wq[e], lut_a, lut_b, qa, qb, has_b);
+                            }
+                        }
+                    }
+                    pairs_done = true;
+                }
+            }
+            if (!pairs_done) {
             // (1) full chunks: lane owns quad q = c*32 + lane of every env → per-lane constants hoisted,
             //     each store instruction covers 512 contiguous bytes of one agent slot
             const int nfull = qps >> 5;
@@ -755,6 +828,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (V == 9 || NOISE != 0) ? 4 
                             if (s_active[e] & 1) emit(e, q, wq[e], sh, lut_off, qn);
                     }
                 }
+            }
             }
             }
         }

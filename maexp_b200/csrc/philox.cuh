@@ -12,7 +12,7 @@ enum Stream : uint32_t {
     kStreamInitPerm = 3,  // default_environment.py:97-98
     kStreamDest = 4,      // three_rooms_map.py:52-55
     kStreamObjects = 5,   // default_environment.py:123-148 during reset
-    kStreamNoise = 6      // noises/*.py, one call per 4 observation elements
+    kStreamNoise = 6      // noises/*.py: gaussian, one call per 4 elements; uniform (flip), 16-bit draws, one call per 8
 };
 
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,

@@ -596,8 +596,14 @@ static float u32_to_unit_float(uint32_t u) { return (float)(u >> 8) * (1.0f / 16
 static float noise_draw(const orc_env *o, int e, uint32_t tick, int i, int k, const float *tape, int gaussian) {
     if (tape) return tape[((size_t)e * o->cfg.num_agents + i) * (size_t)orc_obs_elems(o) + k];
     uint32_t w[4];
+    if (!gaussian) {
+        /* uniform draws (flip noise): 16 bits each, EIGHT per call -- element k: call k >> 3, word (k & 7) >> 1, the low half
+         * for even k; u = h / 65536 exactly (DESIGN.md RNG specification; csrc/env_kernel.cuh emit_pair) */
+        philox4x32_10(o->cfg.seed, genv(o, e), tick, MAEXP_STREAM_NOISE, (uint32_t)(k >> 3), (uint32_t)i, w);
+        const uint32_t word = w[(k & 7) >> 1], h = (k & 1) ? word >> 16 : word & 0xFFFFu;
+        return (float)h * (1.0f / 65536.0f);
+    }
     philox4x32_10(o->cfg.seed, genv(o, e), tick, MAEXP_STREAM_NOISE, (uint32_t)(k >> 2), (uint32_t)i, w);
-    if (!gaussian) return u32_to_unit_float(w[k & 3]);
     /* Box-Muller on the pair (w[2p], w[2p+1]); bit-exact parity is only claimed for taped draws */
     const int p = (k & 3) >> 1;
     const float u1 = ((float)(w[2 * p] >> 8) + 0.5f) * (1.0f / 16777216.0f);

@@ -24,7 +24,7 @@ enum {
     MAEXP_STREAM_INIT_PERM = 3,   /* default_environment.py:97-98                      */
     MAEXP_STREAM_DEST = 4,        /* three_rooms_map.py:52-55                          */
     MAEXP_STREAM_OBJECTS = 5,     /* default_environment.py:123-148 at reset           */
-    MAEXP_STREAM_NOISE = 6        /* noises/*.py, one call per 4 observation elements  */
+    MAEXP_STREAM_NOISE = 6        /* noises/*.py: gaussian, one call per 4 elements; uniform (flip), 16-bit draws, one call per 8 */
 };
 
 static inline void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,

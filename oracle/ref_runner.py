@@ -78,12 +78,15 @@ def philox_actions(n, seed, env, tick):
 
 
 def uniform_field(n_elems, seed, env, tick, agent):
+    """Uniform draws of the flip noise: 16 bits each, eight per Philox call -- element k: call k >> 3, word (k & 7) >> 1, the low
+    half for even k; u = h / 65536 (DESIGN.md RNG specification; oracle/maexp_oracle.c noise_draw)."""
     out = np.empty(n_elems, np.float32)
-    for q in range((n_elems + 3) // 4):
-        w = philox4x32_10(seed, env, tick, STREAM_NOISE, q, agent)
-        for j in range(4):
-            if 4 * q + j < n_elems:
-                out[4 * q + j] = np.float32(w[j] >> 8) * np.float32(1.0 / 16777216.0)
+    for c in range((n_elems + 7) // 8):
+        w = philox4x32_10(seed, env, tick, STREAM_NOISE, c, agent)
+        for j in range(8):
+            if 8 * c + j < n_elems:
+                h = (w[j >> 1] >> 16) if (j & 1) else (w[j >> 1] & 0xFFFF)
+                out[8 * c + j] = np.float32(h) * np.float32(1.0 / 65536.0)
     return out
 
 
