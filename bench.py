@@ -431,12 +431,13 @@ def run_ours(args, rank, local_rank, world):
             "learner": {"metric": "learner_updates_per_sec", "unit": "agent-network updates/s",
                         "value": ku * N / (upd_ms * 1e-3), "ms_per_team_update": upd_ms / ku, "brain": "categorical_dqn",
                         "agents": N, "batch_per_gpu": B, "global_batch": B * world, "steps": ku, "loss": loss,
-                        "note": "replay sample (1 launch) + forward/backward (CUDA graph) + "
+                        "note": "replay sample (1 launch) + forward/backward "
+                                + ("and clip+RMSprop in ONE CUDA graph; " if graphed.single_graph else "(CUDA graph) + ")
                                 + ("" if world == 1 else
                                    "ONE cooperative kernel: gradient reduce-scatter / all-gather over NVLink peer memory + 1/world + "
                                    "clip + RMSprop (maexp_learner_apply_data_parallel); " if graphed.peers is not None else
                                    "NCCL all-reduce of the flat gradient buffer + ")
-                                + ("clip+RMSprop (CUDA graph); " if world == 1 or graphed.peers is None else "")
+                                + ("clip+RMSprop (CUDA graph); " if not graphed.single_graph and graphed.peers is None else "")
                                 + "all 8 agents' networks in grouped launches",
                         "collective": None if world == 1 else ("fused NVLink peer kernel" if graphed.peers is not None else "nccl"),
                         "roofline": learner_roofline(learner_flop, upd_s)},

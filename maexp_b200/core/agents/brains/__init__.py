@@ -363,6 +363,7 @@ class GraphedUpdate:
         self.group, self.batch, self.active, self.dist, self.pg = group, batch, active, dist, process_group
         self.world = dist.get_world_size(process_group) if dist is not None else 1
         self.g_grads = self.g_apply = None
+        self.single_graph = False
         self.calls = 0
         # data parallel on NVLink peers: the gradient buffer moves into symmetric memory and ONE cooperative kernel does the
         # exchange and the optimizer step (maexp_learner_apply_data_parallel); otherwise NCCL all-reduce + apply
@@ -448,13 +449,19 @@ class GraphedUpdate:
         if self.g_grads is None:
             torch.cuda.synchronize(self.group.device)
             self.g_grads = torch.cuda.CUDAGraph()
+            # one GPU: nothing runs between the two halves, so they are ONE graph (no graph boundary before the optimizer)
+            self.single_graph = self.dist is None and os.environ.get("MAEXP_SINGLE_GRAPH", "1") != "0"
             with torch.cuda.graph(self.g_grads):
                 self.group.grads(self.batch)
-            if self.peers is None:
+                if self.single_graph:
+                    self.group.apply(1.0, self.active)
+            if self.peers is None and not self.single_graph:
                 self.g_apply = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.g_apply):
                     self.group.apply(1.0 / self.world, self.active)
         self.g_grads.replay()
+        if self.single_graph:
+            return self.group.loss
         if not self._apply():  # fused: one cooperative launch (exchange over NVLink + clip + RMSprop)
             self._reduce()
             self.g_apply.replay()

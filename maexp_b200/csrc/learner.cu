@@ -35,6 +35,10 @@ int fail(const std::string &msg);  // env.cu
 bool tc_gemm_launch(cudaStream_t st, int G, const float *A, const float *W, const float *bias, float *C, int M, int N, int K,
                     long long lda, long long ldw, long long ldc, long long gA, long long gW, long long gBias, long long gC, int relu,
                     int split);
+// tc_gemm.cu: the weight-gradient products (batch = K, both operands k-outermost) on tcgen05, transposed while staging
+bool tc_gemm_tn_launch(cudaStream_t st, int G, const float *A, const float *B, float *C, int M, int N, int K, long long lda,
+                       long long ldb, long long ldc, long long gA, long long gB, long long gC, float *part, long long part_floats,
+                       int *ksplit_out);
 #define MAEXP_CUDA_L(call)                                                                        \
     do {                                                                                          \
         cudaError_t err__ = (call);                                                               \
@@ -1416,6 +1420,15 @@ struct maexp_learner {
     bool use_tc = true;  // tensor-core GEMMs for large inference batches (MAEXP_TC=0 turns them off)
     bool batched_fwd = false;      // all forward passes of an update as slices of one launch (MAEXP_BATCHED_FWD=1; measured slower than one stream each: 263 vs 234 us)
     bool fused_mlp = true;         // one-kernel MLP heads for the update batches (MAEXP_FUSED_MLP=0: GEMM by GEMM)
+    // MAEXP_TC_WGRAD=1: the weight-gradient GEMMs of >= 128-row update batches on tcgen05 (tc_gemm_tn_kernel).  Opt-in: measured
+    // SLOWER inside the update (184 against 175 us per C51 team update) although its kernels are ~5x shorter -- their 80-100 KB
+    // of shared memory cannot sit beside the three resident CTAs per SM of trunk_fused_bwd_kernel, so they run after the
+    // data-gradient chain instead of beside it (stamps: gradients joined 22 us after the chain instead of 1 us)
+    bool tc_wgrad = false;
+    // MAEXP_MLP_BWD_SPLIT=1: the heads' data-gradient chain as two kernels (dh once per head, then dx) instead of one whose
+    // column tiles each repeat the dout W2 product.  Opt-in: half the flops, but measured slower inside the update (183 against
+    // 175 us) -- the phase is bound by contention with the weight-gradient kernels beside it, not by this kernel's arithmetic
+    bool mlp_bwd_split = false;
     bool tc_mlp = true;            // the MLP heads of >= 128-row update batches on tcgen05 (csrc/tc_mlp.cu; MAEXP_TC_MLP=0: the SIMT kernel).
                                    // First measured slower than the SIMT kernel (45 vs 33 us at B = 256; profiles/r2_tc_mlp_fwd_*.txt): its
                                    // operand staging went through GENERIC stores (the 1024-byte alignment of the dynamic shared memory was
@@ -1457,7 +1470,9 @@ struct maexp_learner {
     float *splitk_side[kSides] = {};
     cudaStream_t side[kSides] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kSides] = {}, ev_w[kSides] = {};
-    cudaEvent_t ev_mark[2] = {};   // backward(): points of the main stream the deferred weight-gradient work waits for
+    cudaEvent_t ev_mark[3] = {}, ev_prep[3] = {};
+    float *mean_dst = nullptr;  // where backward() writes the batch-mean loss (set by the update just before it)
+    bool fork_live = false, prep_branch = true;  // ev_fork was recorded in this update; weight-panel kernels beside the trunk   // backward(): points of the main stream the deferred weight-gradient work waits for
     bool critical_first = true;    // MAEXP_CRITICAL_FIRST=0: weight-gradient kernels are issued where their inputs become ready
     float *d_h2 = nullptr, *d_hrow2 = nullptr;  // second hidden-gradient buffers: weight-gradient GEMMs of head k read
                                                 // theirs on a side stream while head k+1's data gradients are computed
@@ -1564,6 +1579,7 @@ void stamp(cudaStream_t st, int slot) {
     stamp_kernel<<<1, 1, 0, st>>>(g_stamps + slot);
 }
 bool g_inference_tc = false;                             // set by the q_values entry points around their forward pass
+bool g_wgrad_tc = false;                                 // set by backward(): the weight-gradient GEMMs of this update on tcgen05
 constexpr int kAttnMapsBatch = 256;                      // q_values batches up to this size keep their attention maps
 struct InferenceScope {                                  // (every model family: conv heads, transformer projections)
     explicit InferenceScope(bool on) { g_inference_tc = on; }
@@ -1586,6 +1602,19 @@ void gemm(cudaStream_t st, int G, const float *A, const float *Bm, float *C, con
     if (g_inference_tc && M >= 512 && K >= 32 && sak == 1 && sbk == 1 && scn == 1 && !accumulate && !aux &&
         tc_gemm_launch(st, G, A, Bm, bias, C, M, N, K, sam, sbn, scm, gA, gB, gBias, gC, relu, 3))
         return;
+    // weight gradients of an update (C = dY^T X: both operands k-outermost, the batch is K): tensor cores, three TF32 terms
+    if (g_wgrad_tc && sam == 1 && sbn == 1 && scn == 1 && !bias && !relu && !accumulate && !aux && K >= 128 && M >= 32 && N >= 64) {
+        int ks = 1;
+        if (tc_gemm_tn_launch(st, G, A, Bm, C, M, N, K, sak, sbk, scm, gA, gB, gC, g_splitk_ws, g_splitk_ws ? kSplitWorkspaceFloats : 0,
+                              &ks)) {
+            if (ks > 1) {
+                const long long total = (long long)M * N;
+                splitk_reduce_kernel<<<dim3((unsigned)((total + 255) / 256 > 256 ? 256 : (total + 255) / 256), G), 256, 0, st>>>(
+                    a, ks, G, g_splitk_ws);
+            }
+            return;
+        }
+    }
     if (M >= 2048 && sak == 1 && sbk == 1 && (K & 3) == 0 && (sam & 3) == 0 && (gA & 3) == 0 && aligned16(A)) {
         dim3 grid((N + kBigN - 1) / kBigN, (M + kBigM - 1) / kBigM, G);
         gemm_big_kernel<<<grid, 256, 0, st>>>(a);
@@ -2175,12 +2204,14 @@ struct MlpBwdHeads {
 
 __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params, long long P, const MlpBwdHeads hd, int nheads,
                                                             int rows, long long rows_max, int din, int H, float *dx,
-                                                            int vec_w1, float *dx_nhwc, int Q, int accumulate) {
+                                                            int vec_w1, float *dx_nhwc, int Q, int accumulate, int dh_only) {
+    // dh_only: blockIdx.y is the head, the CTA stops after writing dh (the split chain: mlp_dx_kernel then forms dx from dh
+    // without every column tile repeating this product)
     constexpr int TM = kMlpTM, TN = kMlpTN, BK = kMlpBK;
     __shared__ __align__(16) float As[BK][TM + 4];
     __shared__ __align__(16) float Bs[BK][TN + 4];
     __shared__ __align__(16) float Hs[TN][TM + 4];
-    const int g = blockIdx.z, m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+    const int g = blockIdx.z, m0 = blockIdx.x * TM, n0 = dh_only ? 0 : blockIdx.y * TN;
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const float *Wg = params + (size_t)g * P;
     const int am = tid >> 3, ak = (tid & 7) * 4;
@@ -2239,7 +2270,7 @@ __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params,
         }
     };
     const int vec_h = (H & 3) == 0;  // W2 rows are H floats: 16-byte aligned when the tensor is (checked by the host for W1 only)
-    for (int head = 0; head < nheads; ++head) {
+    for (int head = dh_only ? blockIdx.y : 0; head < (dh_only ? (int)blockIdx.y + 1 : nheads); ++head) {
         const int O = head == 0 ? hd.out[0] : hd.out[1];
         const float *dout = (head == 0 ? hd.dout[0] : hd.dout[1]) + (size_t)g * rows_max * O;
         const float *hb = (head == 0 ? hd.hbuf[0] : hd.hbuf[1]) + (size_t)g * rows_max * H;
@@ -2274,12 +2305,12 @@ __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params,
             *reinterpret_cast<float4 *>(&Hs[n][ty * 4]) = make_float4(v[0], v[1], v[2], v[3]);
         }
         __syncthreads();
-        if (blockIdx.y == 0)
+        if (blockIdx.y == 0 || dh_only)
             for (int i = tid; i < TM * TN; i += 256) {
                 const int m = i >> 7, n = i & (TN - 1);
                 if (m0 + m < rows && n < H) dh[(size_t)(m0 + m) * H + n] = Hs[n][m];
             }
-        if (!dx) { __syncthreads(); continue; }
+        if (!dx || dh_only) { __syncthreads(); continue; }
         // ---- dx tile += dh[32][H] W1[H][din]
         fetch_b(W1, H, din, 0, n0, vec_w1);
         for (int k0 = 0; k0 < H; k0 += BK) {
@@ -2290,7 +2321,7 @@ __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params,
             __syncthreads();
         }
     }
-    if (!dx) return;
+    if (!dx || dh_only) return;
     float *dst = dx + (size_t)g * rows_max * din;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -2305,6 +2336,102 @@ __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params,
                 // the same gradient as conv2's NHWC output gradient [m][pos][oc] (flatten order is oc*Q + pos): what the
                 // conv2 weight-gradient GEMM reads
                 if (dx_nhwc) dx_nhwc[(size_t)g * rows_max * din + ((size_t)m * Q + n % Q) * (din / Q) + n / Q] = accx[i][j];
+            }
+        }
+    }
+}
+
+// Second half of the split data-gradient chain: dx[rows][din] = sum over the heads of dh_head[rows][H] W1_head[H][din], dh read
+// back from HBM (written by mlp_fused_bwd_kernel with dh_only).  A CTA owns 32 rows and one 128-column tile; every output is
+// the same fmaf chain (head 0, k ascending, then head 1) as in the one-kernel form, so both give the same bits.
+__global__ void __launch_bounds__(256) mlp_dx_kernel(const float *params, long long P, const MlpBwdHeads hd, int nheads, int rows,
+                                                     long long rows_max, int din, int H, float *dx, int vec_w1, float *dx_nhwc,
+                                                     int Q) {
+    constexpr int TM = kMlpTM, TN = kMlpTN, BK = kMlpBK;
+    __shared__ __align__(16) float As[2][BK][TM + 4];
+    __shared__ __align__(16) float Bs[2][BK][TN + 4];
+    const int g = blockIdx.z, m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const float *Wg = params + (size_t)g * P;
+    const int am = tid >> 3, ak = (tid & 7) * 4;
+    const bool vec_h = (H & 3) == 0 && ((rows_max * H) & 3) == 0;
+    float4 ra, rb[4];
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    const int nkb = (H + BK - 1) / BK, steps = nheads * nkb;
+    auto fetch = [&](int s) {
+        const int head = s / nkb, k0 = (s - head * nkb) * BK;
+        const float *dh = (head == 0 ? hd.dh[0] : hd.dh[1]) + (size_t)g * rows_max * H;
+        const float *W1 = Wg + (head == 0 ? hd.w1[0] : hd.w1[1]);
+        const int m = m0 + am, k = k0 + ak;
+        ra = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (m < rows && k < H) {
+            const float *src = dh + (size_t)m * H + k;
+            if (vec_h && ((reinterpret_cast<uintptr_t>(dh) & 15) == 0) && k + 3 < H) ra = *reinterpret_cast<const float4 *>(src);
+            else {
+                ra.x = src[0];
+                if (k + 1 < H) ra.y = src[1];
+                if (k + 2 < H) ra.z = src[2];
+                if (k + 3 < H) ra.w = src[3];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int idx = tid + r * 256, kk = k0 + (idx >> 5), n = n0 + (idx & 31) * 4;
+            rb[r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (kk < H) {
+                const float *src = W1 + (size_t)kk * din + n;
+                if (vec_w1 && n + 3 < din) rb[r] = *reinterpret_cast<const float4 *>(src);
+                else {
+                    if (n < din) rb[r].x = src[0];
+                    if (n + 1 < din) rb[r].y = src[1];
+                    if (n + 2 < din) rb[r].z = src[2];
+                    if (n + 3 < din) rb[r].w = src[3];
+                }
+            }
+        }
+    };
+    auto store = [&](int buf) {
+        As[buf][ak][am] = ra.x; As[buf][ak + 1][am] = ra.y; As[buf][ak + 2][am] = ra.z; As[buf][ak + 3][am] = ra.w;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int idx = tid + r * 256;
+            *reinterpret_cast<float4 *>(&Bs[buf][idx >> 5][(idx & 31) * 4]) = rb[r];
+        }
+    };
+    fetch(0);
+    store(0);
+    __syncthreads();
+    for (int s = 0; s < steps; ++s) {  // double-buffered tiles: one barrier per K step
+        const int buf = s & 1;
+        if (s + 1 < steps) fetch(s + 1);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (s + 1 < steps) store(buf ^ 1);
+        __syncthreads();
+    }
+    float *dst = dx + (size_t)g * rows_max * din;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= rows) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < din) {
+                dst[(size_t)m * din + n] = acc[i][j];
+                if (dx_nhwc) dx_nhwc[(size_t)g * rows_max * din + ((size_t)m * Q + n % Q) * (din / Q) + n / Q] = acc[i][j];
             }
         }
     }
@@ -2423,7 +2550,9 @@ void trunk_backward(maexp_learner *h, cudaStream_t st, bool defer_conv2_wgrad = 
     if (h->fused_trunk_acts && h->trunk_part) {
         const int V = h->V, warps = 8, K1 = C * 4, D = F2 * H2 * H2;
         const size_t smem = sizeof(float) * ((size_t)F2 * 128 + (size_t)warps * ((D + 3) / 4 * 4 + (C * V * V + 3) / 4 * 4 + K1 * 32 + 96));
-        int nblk = (B + warps * 2 - 1) / (warps * 2);  // two samples per warp
+        // samples per warp (MAEXP_TRUNK_BWD_SPW, default 2): 16 blocks per agent at B = 256
+        static const int spw = getenv("MAEXP_TRUNK_BWD_SPW") ? (atoi(getenv("MAEXP_TRUNK_BWD_SPW")) < 1 ? 1 : atoi(getenv("MAEXP_TRUNK_BWD_SPW"))) : 2;
+        int nblk = (B + warps * spw - 1) / (warps * spw);
         if (nblk > kTrunkBwdBlocks) nblk = kTrunkBwdBlocks;
         if (smem <= 200 * 1024) {
             if (!defer_conv2_wgrad) {   // conv2's weight gradient stays a GEMM, off the critical path
@@ -2568,7 +2697,19 @@ bool mlp_fused_forward_multi(maexp_learner *h, cudaStream_t st, int n, const flo
                 t.rows = ins[0].rows; t.rows_max = ins[0].rows_max; t.din = ins[0].din; t.H = H;
                 t.workspace = e.ws;
             }
-            if (ok1 && tc_heads_forward_multi(st, h->G, ent, 2)) return true;
+            // inside an update the weight-panel kernels of this pass run on a free side stream behind the update's fork point
+            // (beside the pass's trunk): MAEXP_PREP_BRANCH=0 keeps them on the pass's chain
+            TcHeadsPrepBranch pb = {}, *prep = nullptr;
+            if (ok1 && h->fork_live && h->prep_branch) {
+                int pass = 0;
+                for (int q = 0; q < 3; ++q)
+                    if (outs[0][0] == h->acts[q].out[0]) pass = q;
+                pb.stream = h->side[2 + (pass & 1)];
+                pb.after = h->ev_fork;
+                pb.done = h->ev_prep[pass];
+                prep = &pb;
+            }
+            if (ok1 && tc_heads_forward_multi(st, h->G, ent, 2, prep)) return true;
         }
         bool ok = true;
         TcHeadsFwd passes[3] = {};
@@ -2674,7 +2815,7 @@ void mlp_backward(maexp_learner *h, cudaStream_t st, const HeadLayout &hd, const
         const int vec_w1 = (in.din & 3) == 0 && (P & 3) == 0 && (reinterpret_cast<uintptr_t>(h->online + hd.w1) & 15) == 0;
         dim3 grid((rows + kMlpTM - 1) / kMlpTM, dx ? (in.din + kMlpTN - 1) / kMlpTN : 1, G);
         mlp_fused_bwd_kernel<<<grid, 256, 0, st>>>(h->online, P, bh, 1, rows, in.rows_max, in.din, H, dx, vec_w1, nullptr, 1,
-                                                   accumulate_dx);
+                                                   accumulate_dx, 0);
         cudaStream_t ws = wgrad_begin(st);
         gemm(ws, G, dhbuf, in.x, h->grads + hd.w1, nullptr, H, in.din, rows, 1, H, in.x_row, 1, in.din, 1, gH, in.x_g, P, 0);
         colsum(ws, G, h->ones, dhbuf, h->grads + hd.b1, rows, H, gH, P);
@@ -2744,6 +2885,12 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
     else in = {obs, h->cfg.obs_stride, (long long)B * h->cfg.obs_stride, B, B, h->D};
     wgrad_open(h, st);
     const int nheads = (int)h->heads.size(), H = h->H, G = h->G;
+    // C51 / DQN only, like the tensor-core trunk: the 2e-6 of the three-term products is inside their gradient bar
+    struct WgradTcScope {
+        explicit WgradTcScope(bool on) { g_wgrad_tc = on; }
+        ~WgradTcScope() { g_wgrad_tc = false; }
+    } wgrad_tc_scope(h->use_tc && h->tc_wgrad && B >= 128 &&
+                     (h->cfg.kind == MAEXP_LEARNER_C51 || h->cfg.kind == MAEXP_LEARNER_DQN_CONV_MLP));
     if (h->fused_mlp && nheads <= 2 && H <= kMlpTN && in.din <= kMlpMaxIn) {
         // weight gradients on the side streams around ONE kernel for the data-gradient chain of all heads
         const long long P = h->P, gH = (long long)B * H;
@@ -2785,8 +2932,19 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
             h->col2_ready = h->dy2_ready = true;
         }
         stamp(st, 11);
-        mlp_fused_bwd_kernel<<<grid, 256, 0, st>>>(h->online, P, bh, nheads, B, B, in.din, H, dx, vec_w1,
-                                                   to_trunk ? h->d_y2 : nullptr, h->H2 * h->H2, 0);
+        // MAEXP_MLP_BWD_SPLIT=1: dh once per head, then dx from it -- in the one-kernel form every one of the din / 128 column
+        // tiles repeats the dout W2 product (5x at din = 576: more than half of its flops)
+        if (h->mlp_bwd_split && dx && grid.y > 1) {
+            mlp_fused_bwd_kernel<<<dim3(grid.x, nheads, G), 256, 0, st>>>(h->online, P, bh, nheads, B, B, in.din, H, dx, vec_w1, nullptr,
+                                                                         1, 0, 1);
+            if (cfirst) cudaEventRecord(h->ev_mark[2], st);  // dh is ready: the first-layer weight gradients may start
+            mlp_dx_kernel<<<grid, 256, 0, st>>>(h->online, P, bh, nheads, B, B, in.din, H, dx, vec_w1, to_trunk ? h->d_y2 : nullptr,
+                                                h->H2 * h->H2);
+        } else {
+            mlp_fused_bwd_kernel<<<grid, 256, 0, st>>>(h->online, P, bh, nheads, B, B, in.din, H, dx, vec_w1,
+                                                       to_trunk ? h->d_y2 : nullptr, h->H2 * h->H2, 0, 0);
+            if (cfirst) cudaEventRecord(h->ev_mark[2], st);
+        }
         stamp(st, 12);
         if (cfirst) {
             cudaEventRecord(h->ev_mark[1], st);
@@ -2803,6 +2961,16 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
             // (measured: 200 us per C51 team update against 220 us -- the early start wins although it slows mlp_fused_bwd down)
             static const int late = getenv("MAEXP_WGRAD_LATE") ? atoi(getenv("MAEXP_WGRAD_LATE")) : 0;
             cudaEvent_t ev_w2 = h->ev_mark[late ? 1 : 0];
+            // what reads dh only (first-layer weight gradients, bias gradients) starts when the split chain's dh kernel is done
+            // (MAEXP_DH_EARLY=0: after the whole MLP chain, as before the split)
+            static const int dh_early = getenv("MAEXP_DH_EARLY") ? atoi(getenv("MAEXP_DH_EARLY")) : 1;
+            cudaEvent_t ev_dh = h->ev_mark[dh_early ? 2 : 1];
+            if (h->mean_dst) {  // the loss scalar of this update (reads per_sample, written by the loss kernel before ev_mark[0])
+                cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[0]);
+                mean_kernel<<<G, 256, 0, ws>>>(h->per_sample, h->mean_dst, B);
+                wgrad_end();
+                h->mean_dst = nullptr;
+            }
             if (grouped) {  // after the loss: second-layer weight gradients of all heads, one grouped launch
                 WgArgs wa = {};
                 for (int k = 0; k < nheads; ++k) {
@@ -2846,9 +3014,9 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
                 wgrad_group(ws, G, wa, P);
                 wgrad_end();
             } else
-            for (int k = 0; k < nheads; ++k) {  // after mlp_fused_bwd: first-layer weight / bias gradients
+            for (int k = 0; k < nheads; ++k) {  // after dh: first-layer weight / bias gradients
                 const HeadLayout &hd = h->heads[k];
-                cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[1]);
+                cudaStream_t ws = wgrad_begin_at(st, ev_dh);
                 gemm(ws, G, dhs[k], in.x, h->grads + hd.w1, nullptr, H, in.din, B, 1, H, in.x_row, 1, in.din, 1, gH, in.x_g, P, 0);
                 wgrad_end();
             }
@@ -2862,7 +3030,7 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
                     maxc = hd.out > maxc ? hd.out : maxc;
                     maxc = H > maxc ? H : maxc;
                 }
-                cudaStream_t ws = wgrad_begin_at(st, h->ev_mark[1]);
+                cudaStream_t ws = wgrad_begin_at(st, ev_dh);
                 bias_grads_kernel<<<dim3((maxc + 31) / 32, ba.n, G), 256, 0, ws>>>(ba, h->grads, P, B);
                 wgrad_end();
             }
@@ -3349,6 +3517,9 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (const char *fm = getenv("MAEXP_FUSED_MLP")) h->fused_mlp = atoi(fm) != 0;
     if (const char *tm = getenv("MAEXP_TC_MLP")) h->tc_mlp = atoi(tm) != 0;
     if (const char *th = getenv("MAEXP_TC_HEADS")) h->tc_heads = atoi(th) != 0;
+    if (const char *tw = getenv("MAEXP_TC_WGRAD")) h->tc_wgrad = atoi(tw) != 0;
+    if (const char *ms = getenv("MAEXP_MLP_BWD_SPLIT")) h->mlp_bwd_split = atoi(ms) != 0;
+    if (const char *pb = getenv("MAEXP_PREP_BRANCH")) h->prep_branch = atoi(pb) != 0;
     if (const char *tt = getenv("MAEXP_TC_TRUNK")) h->tc_trunk = atoi(tt) != 0;
     if (const char *bf = getenv("MAEXP_BATCHED_FWD")) h->batched_fwd = atoi(bf) != 0;
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
@@ -3606,7 +3777,8 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     }
     rc |= cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess;
     rc |= cudaEventCreateWithFlags(&h->ev_col2, cudaEventDisableTiming) != cudaSuccess;
-    for (int k = 0; k < 2; ++k) rc |= cudaEventCreateWithFlags(&h->ev_mark[k], cudaEventDisableTiming) != cudaSuccess;
+    for (int k = 0; k < 3; ++k) rc |= cudaEventCreateWithFlags(&h->ev_mark[k], cudaEventDisableTiming) != cudaSuccess;
+    for (int k = 0; k < 3; ++k) rc |= cudaEventCreateWithFlags(&h->ev_prep[k], cudaEventDisableTiming) != cudaSuccess;
     if (const char *cf = getenv("MAEXP_CRITICAL_FIRST")) h->critical_first = atoi(cf) != 0;
     for (int k = 0; k < 3; ++k) {
         maexp_learner::Acts &a = h->acts[k];
@@ -3765,8 +3937,10 @@ void maexp_learner_destroy(maexp_learner *h) {
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_col2) cudaEventDestroy(h->ev_col2);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 3; ++k) {
         if (h->ev_mark[k]) cudaEventDestroy(h->ev_mark[k]);
+        if (h->ev_prep[k]) cudaEventDestroy(h->ev_prep[k]);
+    }
     for (void *d : h->allocs) cudaFree(d);
     delete h;
 }
@@ -3954,6 +4128,7 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         // passes fork from the point before it
         stamp(st, 0);
         cudaEventRecord(h->ev_fork, st);
+        h->fork_live = true;
         forward(h, st, h->online, obs, B, h->acts[0]);
         stamp(st, 1);
         cudaStream_t s2 = fork_pass(h, st, 0, false);
@@ -3991,6 +4166,7 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         }
         join_pass(h, st, 0);
         if (h->dist && !both) join_pass(h, st, 1);
+        h->fork_live = false;
     }
     if (!h->dist) {
         dqn_loss_kernel<<<dim3((B + 127) / 128, G), 128, 0, st>>>(h->acts[0].out[0], h->acts[2].out[0], actions, rewards,
@@ -4008,9 +4184,14 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         if (h->cfg.kind == MAEXP_LEARNER_C51) c51_loss_kernel<<<grid, 256, 0, st>>>(p, h->m_scratch);
         else qr_loss_kernel<<<grid, 256, 0, st>>>(p);
     }
-    mean_kernel<<<G, 256, 0, st>>>(h->per_sample, loss_out ? loss_out : h->q_tmp, B);
+    // the batch mean of the loss feeds nothing in the backward pass: backward() issues it on a side stream (off the chain)
+    h->mean_dst = loss_out ? loss_out : h->q_tmp;
     stamp(st, 6);
     backward(h, st, obs);
+    if (h->mean_dst) {
+        mean_kernel<<<G, 256, 0, st>>>(h->per_sample, h->mean_dst, B);
+        h->mean_dst = nullptr;
+    }
     stamp(st, 9);
     MAEXP_CUDA_L(cudaGetLastError());
     return 0;

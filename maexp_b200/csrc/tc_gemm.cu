@@ -171,6 +171,150 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const TcArgs a) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(ncols) : "memory");
 }
 
+
+// ---- weight-gradient GEMMs of the update (the batch is the K dimension): C[M,N] = sum_k A[k][m] * B[k][n], both operands
+// ---- stored k-outermost (A = dY [rows][M], B = X [rows][N]).  The tensor core wants both K-major, so the staging transposes:
+// ---- a thread loads a 4 (k) x 4 (m) block as four 16-byte row pieces and stores four 16-byte K-chunks, one per row of the
+// ---- swizzled tile (lanes of a quarter warp hold the 8 chunks of one row: conflict-free stores, 64-byte global segments).
+// ---- Three TF32 terms per product; split-K slices write dense partial tiles part[slice][g][M][N] for the learner's
+// ---- fixed-order reduction (deterministic, like its CUDA-core split-K GEMM).
+struct TnArgs {
+    const float *A, *B;
+    float *C;  // ksplit == 1: C[m][n] (row stride ldc, group stride gC); else the partial tiles
+    int M, N, K, tileN, ntiles, ksplit, kslice;
+    long long lda, ldb, ldc, gA, gB, gC;
+};
+
+__device__ __forceinline__ void load_block_t(const float *base, long long ld, int col, int limit, bool vec, int k0, int kend,
+                                             float4 (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int k = k0 + i;
+        if (k < kend && col < limit) {
+            const float *src = base + (size_t)k * ld + col;
+            if (vec && col + 3 < limit) v[i] = *reinterpret_cast<const float4 *>(src);
+            else {
+                v[i].x = src[0];
+                if (col + 1 < limit) v[i].y = src[1];
+                if (col + 2 < limit) v[i].z = src[2];
+                if (col + 3 < limit) v[i].w = src[3];
+            }
+        }
+    }
+}
+__device__ __forceinline__ void stage_block_t(uint8_t *hi, uint8_t *lo, int q, int c, const float4 (&v)[4]) {
+    stage_chunk<3>(hi, lo, 4 * q + 0, c, make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
+    stage_chunk<3>(hi, lo, 4 * q + 1, c, make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
+    stage_chunk<3>(hi, lo, 4 * q + 2, c, make_float4(v[0].z, v[1].z, v[2].z, v[3].z));
+    stage_chunk<3>(hi, lo, 4 * q + 3, c, make_float4(v[0].w, v[1].w, v[2].w, v[3].w));
+}
+
+__global__ void __launch_bounds__(kThreads) tc_gemm_tn_kernel(const TnArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = blockIdx.y;
+    const int nt = blockIdx.z % a.ntiles, slice = blockIdx.z / a.ntiles;
+    const int n0t = nt * a.tileN, tileN = min(a.tileN, a.N - n0t), npad = (tileN + 15) / 16 * 16;
+    const int m0 = blockIdx.x * kBM, tileM = min(kBM, a.M - m0);
+    const int kbeg = slice * a.kslice, kend = min(a.K, kbeg + a.kslice);
+    const float *A = a.A + (size_t)g * a.gA + m0, *B = a.B + (size_t)g * a.gB + n0t;
+    const uint32_t a_bytes = kBM * 128, w_bytes = (uint32_t)npad * 128;
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sA = smem, *sAlo = sA + a_bytes, *sW = sA + 2 * a_bytes, *sWlo = sW + w_bytes;
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)npad) ncols <<= 1;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+    const uint32_t idesc = idesc_tf32_m128(npad);
+    const int num_kb = (kend - kbeg + kBK - 1) / kBK;
+    const bool a_vec = (a.lda & 3) == 0 && (a.gA & 3) == 0 && ((uintptr_t)a.A & 15) == 0;
+    const bool b_vec = (a.ldb & 3) == 0 && (a.gB & 3) == 0 && ((uintptr_t)a.B & 15) == 0;
+    // one 4 x 4 block of A per thread (32 row quads x 8 K-chunks), up to two of B (<= 64 row quads x 8 K-chunks)
+    const int c = tid & 7, q = tid >> 3;
+    const int nbq = npad >> 2;  // row quads of the B tile
+    float4 ra[4], rb0[4], rb1[4];
+    auto prefetch = [&](int k0) {
+        load_block_t(A, a.lda, 4 * q, tileM, a_vec, k0 + 4 * c, kend, ra);
+        if (q < nbq) load_block_t(B, a.ldb, 4 * q, tileN, b_vec, k0 + 4 * c, kend, rb0);
+        if (q + 32 < nbq) load_block_t(B, a.ldb, 4 * (q + 32), tileN, b_vec, k0 + 4 * c, kend, rb1);
+    };
+    if (num_kb > 0) prefetch(kbeg);
+    for (int kb = 0; kb < num_kb; ++kb) {
+        if (kb >= 1) mbar_wait(&bar, (kb - 1) & 1);
+        stage_block_t(sA, sAlo, q, c, ra);
+        if (q < nbq) stage_block_t(sW, sWlo, q, c, rb0);
+        if (q + 32 < nbq) stage_block_t(sW, sWlo, q + 32, c, rb1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t aA = smem_u32(sA), aAlo = smem_u32(sAlo), aW = smem_u32(sW), aWlo = smem_u32(sWlo);
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {
+                const uint32_t ko = (uint32_t)k * 32;
+                umma_tf32(tmem_d, smem_desc(aA + ko), smem_desc(aW + ko), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_tf32(tmem_d, smem_desc(aAlo + ko), smem_desc(aW + ko), idesc, 1u);
+                umma_tf32(tmem_d, smem_desc(aA + ko), smem_desc(aWlo + ko), idesc, 1u);
+            }
+            umma_commit(&bar);
+        }
+        if (kb + 1 < num_kb) prefetch(kbeg + (kb + 1) * kBK);
+    }
+    if (num_kb > 0) mbar_wait(&bar, (num_kb - 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // epilogue: warp w reads TMEM lane quadrant w % 4 (rows), warps 0-3 the even 16-column groups, 4-7 the odd ones
+    const int quad = warp & 3, ml = quad * 32 + lane, m = m0 + ml;
+    float *crow;
+    long long ldc;
+    if (a.ksplit > 1) {
+        crow = a.C + (((size_t)slice * gridDim.y + g) * a.M + m) * a.N + n0t;
+        ldc = a.N;
+    } else {
+        crow = a.C + (size_t)g * a.gC + (size_t)m * a.ldc + n0t;
+        ldc = a.ldc;
+    }
+    const bool c_vec = (ldc & 3) == 0 && ((a.ksplit > 1) ? (((size_t)a.M * a.N) & 3) == 0 : (a.gC & 3) == 0) && ((uintptr_t)a.C & 15) == 0;
+    for (int n0 = (warp >> 2) * 16; n0 < npad; n0 += 32) {
+        uint32_t r[16];
+        if (num_kb > 0) tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)n0, r);
+        else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+        if (ml < tileM) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const int n = n0 + j4 * 4;
+                if (c_vec && n + 3 < tileN) {
+                    *reinterpret_cast<float4 *>(crow + n) = make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]),
+                                                                        __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < tileN) crow[n + j] = __uint_as_float(r[j4 * 4 + j]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(ncols) : "memory");
+}
+
 }  // namespace
 
 namespace maexp {
@@ -193,6 +337,41 @@ bool tc_gemm_launch(cudaStream_t st, int G, const float *A, const float *W, cons
     return true;
 }
 
+
+// grouped weight-gradient launch: C[g][M,N] = sum_k A[g][k][m] B[g][k][n].  *ksplit_out > 1: the kernel wrote partial tiles
+// part[slice][g][M][N] into `part` (the caller reduces them in slice order); returns false when the shape is outside what the
+// kernel handles (the caller's CUDA-core GEMM then runs)
+bool tc_gemm_tn_launch(cudaStream_t st, int G, const float *A, const float *B, float *C, int M, int N, int K, long long lda,
+                       long long ldb, long long ldc, long long gA, long long gB, long long gC, float *part, long long part_floats,
+                       int *ksplit_out) {
+    if (N < 16 || M < 16 || K < 64) return false;
+    TnArgs a;
+    a.A = A; a.B = B; a.M = M; a.N = N; a.K = K;
+    a.ntiles = (N + 255) / 256;
+    a.tileN = ((N + a.ntiles - 1) / a.ntiles + 15) / 16 * 16;
+    a.lda = lda; a.ldb = ldb; a.ldc = ldc; a.gA = gA; a.gB = gB; a.gC = gC;
+    // split K into slices of >= 12 slabs when one CTA's chain would be long (the conv2 weight gradient: K = B * positions)
+    int ksplit = 1;
+    if (part && K >= 1024) {
+        ksplit = K / 384;
+        if (ksplit > 8) ksplit = 8;
+        while (ksplit > 1 && (long long)ksplit * G * M * N > part_floats) --ksplit;
+    }
+    a.ksplit = ksplit;
+    a.kslice = ((K + ksplit - 1) / ksplit + kBK - 1) / kBK * kBK;
+    a.C = ksplit > 1 ? part : C;
+    const int npad = (a.tileN + 15) / 16 * 16;
+    const size_t smem = 2 * ((size_t)kBM * 128 + (size_t)npad * 128) + 1024;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kBM * 128 + 256 * 128) + 1024) != cudaSuccess)
+            return false;
+        attr = true;
+    }
+    tc_gemm_tn_kernel<<<dim3((M + kBM - 1) / kBM, G, a.ntiles * ksplit), kThreads, smem, st>>>(a);
+    *ksplit_out = ksplit;
+    return true;
+}
 }  // namespace maexp
 
 extern "C" int maexp_tc_gemm(const float *A, const float *W, const float *bias, float *C, int32_t M, int32_t N, int32_t K,

@@ -787,7 +787,10 @@ bool set_smem_attr() {
 }  // namespace
 
 // the forward passes of an update (same shapes, their own inputs / parameters / outputs) as ONE launch: blockIdx.z = pass
-bool tc_heads_forward_multi(cudaStream_t st, int G, const TcHeadsFwd *f, int n) {
+// prep != nullptr: the weight-panel kernels (which read parameters only) run on prep->stream behind prep->after -- a point of the
+// pass before its trunk -- and the heads kernel waits for them: in a captured update they become a branch beside the trunk
+// instead of 4 us per head on the pass's chain
+bool tc_heads_forward_multi(cudaStream_t st, int G, const TcHeadsFwd *f, int n, const TcHeadsPrepBranch *prep) {
     if (n < 1 || n > 3) return false;
     HeadsArgsN aa = {};
     PrepArgs p[3];
@@ -800,7 +803,14 @@ bool tc_heads_forward_multi(cudaStream_t st, int G, const TcHeadsFwd *f, int n) 
         }
     }
     if (!set_smem_attr()) return false;
-    for (int q = 0; q < n; ++q) tc_heads_prepare_kernel<<<dim3(128, G), 256, 0, st>>>(p[q]);
+    if (prep) {
+        cudaStreamWaitEvent(prep->stream, prep->after, 0);
+        for (int q = 0; q < n; ++q) tc_heads_prepare_kernel<<<dim3(128, G), 256, 0, prep->stream>>>(p[q]);
+        cudaEventRecord(prep->done, prep->stream);
+        cudaStreamWaitEvent(st, prep->done, 0);
+    } else {
+        for (int q = 0; q < n; ++q) tc_heads_prepare_kernel<<<dim3(128, G), 256, 0, st>>>(p[q]);
+    }
     tc_heads_kernel<<<dim3((f[0].rows + kBM - 1) / kBM, G, n), kThreads, (size_t)kStages * kStageBytes + 1024, st>>>(aa);
     return cudaGetLastError() == cudaSuccess;
 }

@@ -32,6 +32,7 @@ size_t tc_heads_workspace_floats(int G, int nheads, int din, const int *out);
 // false: shape outside what the kernel handles (the caller falls back to the per-layer tensor-core GEMMs)
 bool tc_heads_forward(cudaStream_t st, int G, const TcHeadsFwd &a);
 // n <= 3 passes of the same shapes as grid slices of one launch (the forward passes of an update)
-bool tc_heads_forward_multi(cudaStream_t st, int G, const TcHeadsFwd *passes, int n);
+struct TcHeadsPrepBranch { cudaStream_t stream; cudaEvent_t after, done; };  // where the weight-panel kernels run (see tc_heads.cu)
+bool tc_heads_forward_multi(cudaStream_t st, int G, const TcHeadsFwd *passes, int n, const TcHeadsPrepBranch *prep = nullptr);
 
 }  // namespace maexp

@@ -671,6 +671,45 @@ def test_batched_forward_passes_match_streamed(kind, V, C, B, monkeypatch):
     assert float((grads - grads_ref).norm()) <= 1e-6 * float(grads_ref.norm())
 
 
+
+@pytest.mark.parametrize("kind,V,C,B", [("c51", 7, 3, 256), ("dqn_conv_mlp", 7, 3, 300), ("c51", 7, 3, 1100)])
+def test_opt_in_backward_kernels_match_default(kind, V, C, B, monkeypatch):
+    """The two measured-slower, opt-in forms of the backward pass stay correct: MAEXP_MLP_BWD_SPLIT=1 (dh kernel + dx kernel: the
+    same fmaf chains, so the same bits up to the C51 projection's atomics) and MAEXP_TC_WGRAD=1 (weight-gradient GEMMs on tcgen05,
+    operands transposed while staging, three TF32 terms, split-K slices reduced in a fixed order: within 2e-5 per tensor)."""
+    from maexp_b200.core.agents.brains import LearnerGroup
+    cfg, _ = golden_configs()[kind]
+    G = 2
+    cfg = cfg.merged_with(batch_size=B, visible_range=V)
+    torch.manual_seed(31)
+    gen = torch.Generator().manual_seed(9)
+    obs = (torch.rand((G, B, C, V, V), generator=gen) < 0.25).float()
+    nxt = (torch.rand((G, B, C, V, V), generator=gen) < 0.25).float()
+    groups = []
+    for split, tcw in (("0", "0"), ("1", "0"), ("0", "1")):
+        monkeypatch.setenv("MAEXP_MLP_BWD_SPLIT", split)
+        monkeypatch.setenv("MAEXP_TC_WGRAD", tcw)
+        groups.append(LearnerGroup(cfg, [C, V, V], 4, G, B))
+    ref = groups[0]
+    for g in groups[1:]:
+        for a in range(G):
+            g.load_state_dict(a, ref.state_dict(a))
+            g.load_state_dict(a, ref.state_dict(a, which=1), which=1)
+    batch = {"obs": pack(ref, obs), "next_obs": pack(ref, nxt),
+             "actions": torch.randint(0, 4, (G, B), generator=gen).to(torch.int32).cuda(),
+             "rewards": torch.randint(-1, 2, (G, B), generator=gen).float().cuda(),
+             "dones": (torch.rand((G, B), generator=gen) < 0.1).to(torch.uint8).cuda()}
+    ref.grads(batch)
+    want = ref.params(2).cpu()
+    for g, tol in zip(groups[1:], (1e-6, 2e-5)):
+        g.grads(batch)
+        got = g.params(2).cpu()
+        for a in range(G):
+            for name, off, cnt in g.table:
+                e = float((got[a, off:off + cnt] - want[a, off:off + cnt]).norm()) / (float(want[a, off:off + cnt].norm()) + 1e-12)
+                assert e <= tol, (a, name, e, tol)
+
+
 def test_graphed_update_equals_eager_updates():
     """GraphedUpdate (eager first step, then captured CUDA graphs) walks the parameters exactly like
     LearnerGroup.learn on a twin group (QR-DQN: no atomics anywhere, so bit-equal)."""

@@ -1,7 +1,8 @@
 """GPU experiment: phase timeline of the graph-replayed C51 team update WITHOUT a profiler attached (%globaltimer stamps written
 by one-thread kernels at the phase boundaries; MAEXP_LEARNER_STAMPS=1).  CUPTI timelines serialise the update's branches."""
 import os, sys
-os.environ["MAEXP_LEARNER_STAMPS"] = "1"
+if os.environ.get("STAMPS", "1") != "0":  # STAMPS=0: the plain timing, no stamp kernels in the graph
+    os.environ["MAEXP_LEARNER_STAMPS"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from maexp_b200.config import baseline_config
@@ -21,6 +22,8 @@ a.record()
 for _ in range(100):
     gu.step()
 b.record(); torch.cuda.synchronize()
-print("graph-replayed update: %.1f us (with the stamp kernels in the graph)" % (a.elapsed_time(b) * 10))
-g.apply(1.0)  # eager: prints the stamps of the last replay
+stamps = "MAEXP_LEARNER_STAMPS" in os.environ
+print("graph-replayed update: %.1f us (%s the stamp kernels in the graph)" % (a.elapsed_time(b) * 10, "with" if stamps else "without"))
+if stamps:
+    g.apply(1.0)  # eager: prints the stamps of the last replay
 torch.cuda.synchronize()
