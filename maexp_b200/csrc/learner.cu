@@ -1575,7 +1575,11 @@ unsigned long long *g_stamps = nullptr;
 void stamp(cudaStream_t st, int slot) {
     static const bool on = getenv("MAEXP_LEARNER_STAMPS") != nullptr;
     if (!on) return;
-    if (!g_stamps && cudaMalloc(&g_stamps, 64 * sizeof(unsigned long long)) != cudaSuccess) return;
+    if (!g_stamps) {
+        if (cudaMalloc(&g_stamps, 64 * sizeof(unsigned long long)) != cudaSuccess) return;
+        cudaMemset(g_stamps, 0, 64 * sizeof(unsigned long long));
+        cudaDeviceSynchronize();
+    }
     stamp_kernel<<<1, 1, 0, st>>>(g_stamps + slot);
 }
 bool g_inference_tc = false;                             // set by the q_values entry points around their forward pass
@@ -1605,6 +1609,12 @@ void gemm(cudaStream_t st, int G, const float *A, const float *Bm, float *C, con
     // weight gradients of an update (C = dY^T X: both operands k-outermost, the batch is K): tensor cores, three TF32 terms
     if (g_wgrad_tc && sam == 1 && sbn == 1 && scn == 1 && !bias && !relu && !accumulate && !aux && K >= 128 && M >= 32 && N >= 64) {
         int ks = 1;
+        static int dbg_slot = 14;  // MAEXP_LEARNER_STAMPS: when each tensor-core weight-gradient kernel started / ended on its side stream
+        if (dbg_slot >= 38) dbg_slot = 14;
+        const int s0 = dbg_slot;
+        dbg_slot += 2;
+        stamp(st, s0);
+        struct StampAfter { cudaStream_t st; int slot; ~StampAfter() { stamp(st, slot); } } stamp_after{st, s0 + 1};
         if (tc_gemm_tn_launch(st, G, A, Bm, C, M, N, K, sak, sbk, scm, gA, gB, gC, g_splitk_ws, g_splitk_ws ? kSplitWorkspaceFloats : 0,
                               &ks)) {
             if (ks > 1) {
@@ -4255,7 +4265,7 @@ int maexp_learner_apply(maexp_learner *h, float grad_scale, const uint8_t *activ
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cap);
         if (cap == cudaStreamCaptureStatusNone) {
-            unsigned long long t[16];
+            unsigned long long t[40];
             cudaStreamSynchronize(st);
             cudaMemcpy(t, g_stamps, sizeof(t), cudaMemcpyDeviceToHost);
             const char *name[14] = {"start", "train pass fwd done", "target pass start", "target pass fwd done", "online(s') pass start",
@@ -4263,6 +4273,10 @@ int maexp_learner_apply(maexp_learner *h, float grad_scale, const uint8_t *activ
                                     "all gradients joined", "clip + optimizer done", "mlp_fused_bwd launch", "mlp_fused_bwd done",
                                     "trunk_fused_bwd done"};
             for (int i = 0; i < 14; ++i) fprintf(stderr, "  stamp %2d %8.1f us  %s\n", i, (double)((long long)(t[i] - t[0])) * 1e-3, name[i]);
+            for (int i = 14; i < 38; i += 2)
+                if (t[i] > t[0] && t[i + 1] > t[0])
+                    fprintf(stderr, "  stamp %2d %8.1f -> %8.1f us  tensor-core weight-gradient GEMM (+ its split-K reduction)\n", i,
+                            (double)((long long)(t[i] - t[0])) * 1e-3, (double)((long long)(t[i + 1] - t[0])) * 1e-3);
         }
     }
     sqnorm_partial_kernel<<<dim3(h->nparts, h->G), 256, 0, st>>>(h->grads, h->partial, h->P, grad_scale);
