@@ -449,8 +449,13 @@ __device__ __forceinline__ float dueling(const float *v, const float *adv, int A
 // C51 (categorical_dqn_brain.py:51-87).  One warp per (agent, sample); a lane owns atoms lane, lane + 32, ...  The dueling
 // rows of a network are formed once per atom (the same operation order as dueling()), the projection scatters into a
 // per-warp shared-memory row, and every head output is read exactly once.
+// NA = most actions, NT = atoms per lane the instantiation is unrolled for: every warp runs the code once, so the kernel
+// was bound by instruction fetch (ncu: "no instruction" 4.4 of 15 stall cycles per issue, 1 724 instructions per warp of which
+// three quarters were predicated off at 4 actions x 51 atoms, 16.5 us); <4, 2> covers the reference's configurations.  All
+// three networks' rows are loaded up front (one round of global latency instead of three).
+template <int NA, int NT>
 __global__ void __launch_bounds__(256) c51_loss_kernel(const DistArgs p, float *m_scratch) {
-    __shared__ float s_m[8][32 * kMaxAtomsPerLane];
+    __shared__ float s_m[8][32 * NT];
     const int g = blockIdx.y, wid = threadIdx.x >> 5, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= p.B) return;
     (void)m_scratch;
@@ -461,48 +466,53 @@ __global__ void __launch_bounds__(256) c51_loss_kernel(const DistArgs p, float *
     const float *vn = duel ? p.v_n + i * Z : nullptr, *an = p.a_n + i * A * Z;
     const float *vt = duel ? p.v_t + i * Z : nullptr, *at = p.a_t + i * A * Z;
     const int a_taken = p.act[i];
+    const float r = p.rew[i];
     // all action rows of one network for this lane's atoms: v + (adv[a] - mean_a adv), sum over actions in index order
-    auto rows = [&](const float *v, const float *adv, float (&d)[kMaxActions][kMaxAtomsPerLane]) {
+    auto rows = [&](const float *v, const float *adv, float (&d)[NA][NT]) {
 #pragma unroll
-        for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+        for (int t = 0; t < NT; ++t) {
             const int jj = lane + 32 * t;
-            if (jj >= Z) continue;
-            float ad[kMaxActions], sum = 0.0f;
 #pragma unroll
-            for (int k = 0; k < kMaxActions; ++k)
+            for (int k = 0; k < NA; ++k) d[k][t] = 0.0f;
+            if (jj >= Z) continue;
+            float ad[NA], sum = 0.0f;
+#pragma unroll
+            for (int k = 0; k < NA; ++k)
                 if (k < A) { ad[k] = adv[k * Z + jj]; sum = __fadd_rn(sum, ad[k]); }
             if (!v) {
 #pragma unroll
-                for (int k = 0; k < kMaxActions; ++k)
+                for (int k = 0; k < NA; ++k)
                     if (k < A) d[k][t] = ad[k];
             } else {
                 const float mean = __fdiv_rn(sum, (float)A), vj = v[jj];
 #pragma unroll
-                for (int k = 0; k < kMaxActions; ++k)
+                for (int k = 0; k < NA; ++k)
                     if (k < A) d[k][t] = __fadd_rn(vj, __fadd_rn(ad[k], -mean));
             }
         }
     };
-    float sup[kMaxAtomsPerLane];
+    float sup[NT];
 #pragma unroll
-    for (int t = 0; t < kMaxAtomsPerLane; ++t) sup[t] = (lane + 32 * t < Z) ? p.support[lane + 32 * t] : 0.0f;
+    for (int t = 0; t < NT; ++t) sup[t] = (lane + 32 * t < Z) ? p.support[lane + 32 * t] : 0.0f;
 
-    // best action of the ONLINE net on s': argmax_a sum_j softmax(out[a])_j z_j, first maximum wins
-    float dn[kMaxActions][kMaxAtomsPerLane];
+    float dn[NA][NT], dt[NA][NT], ds[NA][NT];
     rows(vn, an, dn);
+    rows(vt, at, dt);
+    rows(vs, as, ds);
+    // best action of the ONLINE net on s': argmax_a sum_j softmax(out[a])_j z_j, first maximum wins
     int best = 0;
     float best_q = 0.0f;
 #pragma unroll
-    for (int a = 0; a < kMaxActions; ++a) {
+    for (int a = 0; a < NA; ++a) {
         if (a >= A) break;
         float mx = -INFINITY;
 #pragma unroll
-        for (int t = 0; t < kMaxAtomsPerLane; ++t)
+        for (int t = 0; t < NT; ++t)
             if (lane + 32 * t < Z) mx = fmaxf(mx, dn[a][t]);
         mx = warp_max(mx);
         float se = 0.0f, sq = 0.0f;
 #pragma unroll
-        for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+        for (int t = 0; t < NT; ++t) {
             if (lane + 32 * t < Z) {
                 const float e = expf(__fadd_rn(dn[a][t], -mx));
                 se = __fadd_rn(se, e);
@@ -514,18 +524,21 @@ __global__ void __launch_bounds__(256) c51_loss_kernel(const DistArgs p, float *
         const float qv = __fdiv_rn(sq, se);
         if (a == 0 || qv > best_q) { best_q = qv; best = a; }
     }
-    // p' = softmax(target(s')[best]): only the best row of the target net is formed
-    float pt[kMaxAtomsPerLane], mx = -INFINITY;
+    // p' = softmax(target(s')[best])
+    float pt[NT], mx = -INFINITY;
 #pragma unroll
-    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+    for (int t = 0; t < NT; ++t) {
         const int jj = lane + 32 * t;
-        pt[t] = jj < Z ? dueling(vt, at, A, Z, best, jj) : -INFINITY;
+        float row = dt[0][t];
+#pragma unroll
+        for (int k = 1; k < NA; ++k) row = (k == best) ? dt[k][t] : row;
+        pt[t] = jj < Z ? row : -INFINITY;
         mx = fmaxf(mx, pt[t]);
     }
     mx = warp_max(mx);
     float se = 0.0f;
 #pragma unroll
-    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+    for (int t = 0; t < NT; ++t) {
         pt[t] = (lane + 32 * t < Z) ? expf(__fadd_rn(pt[t], -mx)) : 0.0f;
         se = __fadd_rn(se, pt[t]);
     }
@@ -534,9 +547,8 @@ __global__ void __launch_bounds__(256) c51_loss_kernel(const DistArgs p, float *
     float *m = s_m[wid];
     for (int jj = lane; jj < Z; jj += 32) m[jj] = 0.0f;
     __syncwarp();
-    const float r = p.rew[i];
 #pragma unroll
-    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+    for (int t = 0; t < NT; ++t) {
         const int jj = lane + 32 * t;
         if (jj >= Z) continue;
         const float prob = __fdiv_rn(pt[t], se);
@@ -551,24 +563,27 @@ __global__ void __launch_bounds__(256) c51_loss_kernel(const DistArgs p, float *
     }
     __syncwarp();
     // log_softmax(online(s)[a_taken]), loss and its gradient
-    float l[kMaxAtomsPerLane];
+    float l[NT];
     mx = -INFINITY;
 #pragma unroll
-    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+    for (int t = 0; t < NT; ++t) {
         const int jj = lane + 32 * t;
-        l[t] = jj < Z ? dueling(vs, as, A, Z, a_taken, jj) : -INFINITY;
+        float row = ds[0][t];
+#pragma unroll
+        for (int k = 1; k < NA; ++k) row = (k == a_taken) ? ds[k][t] : row;
+        l[t] = jj < Z ? row : -INFINITY;
         mx = fmaxf(mx, l[t]);
     }
     mx = warp_max(mx);
     float sum_e = 0.0f;
 #pragma unroll
-    for (int t = 0; t < kMaxAtomsPerLane; ++t)
+    for (int t = 0; t < NT; ++t)
         if (lane + 32 * t < Z) sum_e = __fadd_rn(sum_e, expf(__fadd_rn(l[t], -mx)));
     sum_e = warp_sum(sum_e);
     const float lse = __fadd_rn(mx, logf(sum_e));
     float loss = 0.0f, msum = 0.0f;
 #pragma unroll
-    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+    for (int t = 0; t < NT; ++t) {
         const int jj = lane + 32 * t;
         if (jj < Z) {
             loss = __fadd_rn(loss, __fmul_rn(m[jj], __fadd_rn(l[t], -lse)));
@@ -580,7 +595,7 @@ __global__ void __launch_bounds__(256) c51_loss_kernel(const DistArgs p, float *
     if (lane == 0) p.per_sample[i] = -loss;
     const float invB = __fdiv_rn(1.0f, (float)p.B);
 #pragma unroll
-    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+    for (int t = 0; t < NT; ++t) {
         const int jj = lane + 32 * t;
         if (jj >= Z) continue;
         const float sm = expf(__fadd_rn(l[t], -lse));
@@ -1472,6 +1487,8 @@ struct maexp_learner {
     cudaEvent_t ev_fork = nullptr, ev_join[kSides] = {}, ev_w[kSides] = {};
     cudaEvent_t ev_mark[3] = {}, ev_prep[3] = {};
     float *mean_dst = nullptr;  // where backward() writes the batch-mean loss (set by the update just before it)
+    bool zero_live = false, mlp_bwd_head_par = true;  // ev_fork of THIS update exists until its backward pass is issued
+    cudaEvent_t ev_zero = nullptr;
     bool fork_live = false, prep_branch = true;  // ev_fork was recorded in this update; weight-panel kernels beside the trunk   // backward(): points of the main stream the deferred weight-gradient work waits for
     bool critical_first = true;    // MAEXP_CRITICAL_FIRST=0: weight-gradient kernels are issued where their inputs become ready
     float *d_h2 = nullptr, *d_hrow2 = nullptr;  // second hidden-gradient buffers: weight-gradient GEMMs of head k read
@@ -1575,6 +1592,10 @@ unsigned long long *g_stamps = nullptr;
 void stamp(cudaStream_t st, int slot) {
     static const bool on = getenv("MAEXP_LEARNER_STAMPS") != nullptr;
     if (!on) return;
+    // MAEXP_LEARNER_STAMPS=1: every slot; any other value: a bit mask of the slots to keep (every stamp kernel on the chain costs
+    // ~2.5 us and changes which of the kernels that are ready together starts first, so a sparse mask perturbs the update less)
+    static const unsigned long long mask = strtoull(getenv("MAEXP_LEARNER_STAMPS"), nullptr, 0);
+    if (mask != 1ull && !((mask >> slot) & 1ull)) return;
     if (!g_stamps) {
         if (cudaMalloc(&g_stamps, 64 * sizeof(unsigned long long)) != cudaSuccess) return;
         cudaMemset(g_stamps, 0, 64 * sizeof(unsigned long long));
@@ -2205,6 +2226,11 @@ __global__ void __launch_bounds__(256) mlp_fused_fwd_kernel(long long x_row, lon
 // in registers.  A CTA owns 32 rows and one 128-column tile of dx (blockIdx.y); both weight matrices are read in their
 // PyTorch layout, which is already [k][n] for these two products.  Replaces 2 GEMMs + 2 split-K reductions per head on the
 // critical path of the backward pass.  dx == nullptr: only dh (plain MLP on the observation).
+// three resident CTAs per SM (<= 80 registers): at 127 registers two CTAs fill an SM's register file, the 320 CTAs of a C51
+// update (8 row tiles x 5 column tiles x 8 agents) need a second wave on 296 slots and nothing else fits beside them
+#ifndef MAEXP_MLP_BWD_MINB
+#define MAEXP_MLP_BWD_MINB 3
+#endif
 struct MlpBwdHeads {
     long long w1[2], w2[2];
     int out[2];
@@ -2212,16 +2238,22 @@ struct MlpBwdHeads {
     float *dh[2];
 };
 
-__global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params, long long P, const MlpBwdHeads hd, int nheads,
+__global__ void __launch_bounds__(256, MAEXP_MLP_BWD_MINB) mlp_fused_bwd_kernel(const float *params, long long P, const MlpBwdHeads hd, int nheads,
                                                             int rows, long long rows_max, int din, int H, float *dx,
                                                             int vec_w1, float *dx_nhwc, int Q, int accumulate, int dh_only) {
-    // dh_only: blockIdx.y is the head, the CTA stops after writing dh (the split chain: mlp_dx_kernel then forms dx from dh
+    // dh_only == 1: blockIdx.y is the head, the CTA stops after writing dh (the split chain: mlp_dx_kernel then forms dx from dh
     // without every column tile repeating this product)
+    // dh_only == 2 (heads in parallel): blockIdx.y = head * column tiles + column tile; a CTA walks ONE head's chain and adds its
+    // dx tile into the zeroed dx / dx_nhwc with atomicAdd -- two addends per element (0 + a + b = 0 + b + a exactly), so the
+    // result does not depend on the order the CTAs arrive in
+    const int head_par = dh_only == 2, col_tiles = head_par ? (int)gridDim.y / nheads : (int)gridDim.y;
+    const int my_head = head_par ? (int)blockIdx.y / col_tiles : (int)blockIdx.y, my_tile = head_par ? (int)blockIdx.y % col_tiles : (int)blockIdx.y;
+    if (head_par) dh_only = 0;
     constexpr int TM = kMlpTM, TN = kMlpTN, BK = kMlpBK;
     __shared__ __align__(16) float As[BK][TM + 4];
     __shared__ __align__(16) float Bs[BK][TN + 4];
     __shared__ __align__(16) float Hs[TN][TM + 4];
-    const int g = blockIdx.z, m0 = blockIdx.x * TM, n0 = dh_only ? 0 : blockIdx.y * TN;
+    const int g = blockIdx.z, m0 = blockIdx.x * TM, n0 = dh_only ? 0 : my_tile * TN;
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const float *Wg = params + (size_t)g * P;
     const int am = tid >> 3, ak = (tid & 7) * 4;
@@ -2280,7 +2312,7 @@ __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params,
         }
     };
     const int vec_h = (H & 3) == 0;  // W2 rows are H floats: 16-byte aligned when the tensor is (checked by the host for W1 only)
-    for (int head = dh_only ? blockIdx.y : 0; head < (dh_only ? (int)blockIdx.y + 1 : nheads); ++head) {
+    for (int head = (dh_only || head_par) ? my_head : 0; head < ((dh_only || head_par) ? my_head + 1 : nheads); ++head) {
         const int O = head == 0 ? hd.out[0] : hd.out[1];
         const float *dout = (head == 0 ? hd.dout[0] : hd.dout[1]) + (size_t)g * rows_max * O;
         const float *hb = (head == 0 ? hd.hbuf[0] : hd.hbuf[1]) + (size_t)g * rows_max * H;
@@ -2315,7 +2347,7 @@ __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params,
             *reinterpret_cast<float4 *>(&Hs[n][ty * 4]) = make_float4(v[0], v[1], v[2], v[3]);
         }
         __syncthreads();
-        if (blockIdx.y == 0 || dh_only)
+        if (my_tile == 0 || dh_only)
             for (int i = tid; i < TM * TN; i += 256) {
                 const int m = i >> 7, n = i & (TN - 1);
                 if (m0 + m < rows && n < H) dh[(size_t)(m0 + m) * H + n] = Hs[n][m];
@@ -2341,6 +2373,11 @@ __global__ void __launch_bounds__(256) mlp_fused_bwd_kernel(const float *params,
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
             if (n < din) {
+                if (head_par) {
+                    atomicAdd(&dst[(size_t)m * din + n], accx[i][j]);
+                    if (dx_nhwc) atomicAdd(&dx_nhwc[(size_t)g * rows_max * din + ((size_t)m * Q + n % Q) * (din / Q) + n / Q], accx[i][j]);
+                    continue;
+                }
                 if (accumulate) accx[i][j] = __fadd_rn(dst[(size_t)m * din + n], accx[i][j]);  // dx += (the caller's earlier heads)
                 dst[(size_t)m * din + n] = accx[i][j];
                 // the same gradient as conv2's NHWC output gradient [m][pos][oc] (flatten order is oc*Q + pos): what the
@@ -2944,7 +2981,22 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
         stamp(st, 11);
         // MAEXP_MLP_BWD_SPLIT=1: dh once per head, then dx from it -- in the one-kernel form every one of the din / 128 column
         // tiles repeats the dout W2 product (5x at din = 576: more than half of its flops)
-        if (h->mlp_bwd_split && dx && grid.y > 1) {
+        // heads in parallel (default for two heads inside an update; MAEXP_MLP_BWD_HEADS_PARALLEL=0: one CTA walks both): at
+        // B = 256 the grid is 8 row tiles x 2 column tiles x 8 agents = 128 CTAs of 8 warps, one per SM, so the kernel's time is
+        // one CTA's chain of 18 K steps; with a head per CTA the longer chain is 12 steps and an SM holds two CTAs
+        const bool head_par = h->mlp_bwd_head_par && dx && nheads == 2 && h->zero_live && !h->mlp_bwd_split;
+        if (head_par) {
+            const size_t bytes = sizeof(float) * (size_t)G * B * in.din;
+            cudaStream_t zs = h->side[3];  // zero dx (and its NHWC copy) on a branch behind the update's fork point: off the chain
+            cudaStreamWaitEvent(zs, h->ev_fork, 0);
+            cudaMemsetAsync(dx, 0, bytes, zs);
+            if (to_trunk) cudaMemsetAsync(h->d_y2, 0, bytes, zs);
+            cudaEventRecord(h->ev_zero, zs);
+            cudaStreamWaitEvent(st, h->ev_zero, 0);
+            mlp_fused_bwd_kernel<<<dim3(grid.x, grid.y * nheads, G), 256, 0, st>>>(h->online, P, bh, nheads, B, B, in.din, H, dx, vec_w1,
+                                                                                  to_trunk ? h->d_y2 : nullptr, h->H2 * h->H2, 0, 2);
+            if (cfirst) cudaEventRecord(h->ev_mark[2], st);
+        } else if (h->mlp_bwd_split && dx && grid.y > 1) {
             mlp_fused_bwd_kernel<<<dim3(grid.x, nheads, G), 256, 0, st>>>(h->online, P, bh, nheads, B, B, in.din, H, dx, vec_w1, nullptr,
                                                                          1, 0, 1);
             if (cfirst) cudaEventRecord(h->ev_mark[2], st);  // dh is ready: the first-layer weight gradients may start
@@ -3530,6 +3582,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     if (const char *tw = getenv("MAEXP_TC_WGRAD")) h->tc_wgrad = atoi(tw) != 0;
     if (const char *ms = getenv("MAEXP_MLP_BWD_SPLIT")) h->mlp_bwd_split = atoi(ms) != 0;
     if (const char *pb = getenv("MAEXP_PREP_BRANCH")) h->prep_branch = atoi(pb) != 0;
+    if (const char *hp = getenv("MAEXP_MLP_BWD_HEADS_PARALLEL")) h->mlp_bwd_head_par = atoi(hp) != 0;
     if (const char *tt = getenv("MAEXP_TC_TRUNK")) h->tc_trunk = atoi(tt) != 0;
     if (const char *bf = getenv("MAEXP_BATCHED_FWD")) h->batched_fwd = atoi(bf) != 0;
     h->G = cfg->num_agents; h->B = cfg->batch_size; h->C = cfg->channels; h->V = cfg->visible_range;
@@ -3789,6 +3842,7 @@ int maexp_learner_create(const maexp_learner_cfg *cfg, maexp_learner **out) {
     rc |= cudaEventCreateWithFlags(&h->ev_col2, cudaEventDisableTiming) != cudaSuccess;
     for (int k = 0; k < 3; ++k) rc |= cudaEventCreateWithFlags(&h->ev_mark[k], cudaEventDisableTiming) != cudaSuccess;
     for (int k = 0; k < 3; ++k) rc |= cudaEventCreateWithFlags(&h->ev_prep[k], cudaEventDisableTiming) != cudaSuccess;
+    rc |= cudaEventCreateWithFlags(&h->ev_zero, cudaEventDisableTiming) != cudaSuccess;
     if (const char *cf = getenv("MAEXP_CRITICAL_FIRST")) h->critical_first = atoi(cf) != 0;
     for (int k = 0; k < 3; ++k) {
         maexp_learner::Acts &a = h->acts[k];
@@ -3947,6 +4001,7 @@ void maexp_learner_destroy(maexp_learner *h) {
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_col2) cudaEventDestroy(h->ev_col2);
+    if (h->ev_zero) cudaEventDestroy(h->ev_zero);
     for (int k = 0; k < 3; ++k) {
         if (h->ev_mark[k]) cudaEventDestroy(h->ev_mark[k]);
         if (h->ev_prep[k]) cudaEventDestroy(h->ev_prep[k]);
@@ -4138,7 +4193,7 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         // passes fork from the point before it
         stamp(st, 0);
         cudaEventRecord(h->ev_fork, st);
-        h->fork_live = true;
+        h->fork_live = h->zero_live = true;
         forward(h, st, h->online, obs, B, h->acts[0]);
         stamp(st, 1);
         cudaStream_t s2 = fork_pass(h, st, 0, false);
@@ -4191,13 +4246,17 @@ int maexp_learner_grads(maexp_learner *h, const float *obs, const float *next_ob
         p.B = B; p.A = A; p.Z = Z;
         p.gamma = h->cfg.gamma; p.v_min = h->cfg.v_min; p.v_max = h->cfg.v_max; p.delta_z = h->cfg.delta_z;
         const dim3 grid((B * 32 + 255) / 256, G);
-        if (h->cfg.kind == MAEXP_LEARNER_C51) c51_loss_kernel<<<grid, 256, 0, st>>>(p, h->m_scratch);
+        if (h->cfg.kind == MAEXP_LEARNER_C51) {
+            if (A <= 4 && Z <= 64) c51_loss_kernel<4, 2><<<grid, 256, 0, st>>>(p, h->m_scratch);
+            else c51_loss_kernel<kMaxActions, kMaxAtomsPerLane><<<grid, 256, 0, st>>>(p, h->m_scratch);
+        }
         else qr_loss_kernel<<<grid, 256, 0, st>>>(p);
     }
     // the batch mean of the loss feeds nothing in the backward pass: backward() issues it on a side stream (off the chain)
     h->mean_dst = loss_out ? loss_out : h->q_tmp;
     stamp(st, 6);
     backward(h, st, obs);
+    h->zero_live = false;
     if (h->mean_dst) {
         mean_kernel<<<G, 256, 0, st>>>(h->per_sample, h->mean_dst, B);
         h->mean_dst = nullptr;
@@ -4348,7 +4407,10 @@ static int dist_loss(const char *who, bool c51, const float *out_s, const float 
     p.B = B; p.A = A; p.Z = Z;
     p.gamma = gamma; p.v_min = v_min; p.v_max = v_max; p.delta_z = delta_z;
     const dim3 grid((B * 32 + 255) / 256, G);
-    if (c51) c51_loss_kernel<<<grid, 256, 0, st>>>(p, m);
+    if (c51) {
+        if (p.A <= 4 && p.Z <= 64) c51_loss_kernel<4, 2><<<grid, 256, 0, st>>>(p, m);
+        else c51_loss_kernel<kMaxActions, kMaxAtomsPerLane><<<grid, 256, 0, st>>>(p, m);
+    }
     else qr_loss_kernel<<<grid, 256, 0, st>>>(p);
     mean_kernel<<<G, 256, 0, st>>>(per, loss_out, B);
     MAEXP_CUDA_L(cudaGetLastError());

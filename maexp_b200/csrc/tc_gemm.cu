@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 #include "maexp_b200.h"
@@ -210,7 +211,7 @@ __device__ __forceinline__ void stage_block_t(uint8_t *hi, uint8_t *lo, int q, i
     stage_chunk<3>(hi, lo, 4 * q + 3, c, make_float4(v[0].w, v[1].w, v[2].w, v[3].w));
 }
 
-__global__ void __launch_bounds__(kThreads) tc_gemm_tn_kernel(const TnArgs a) {
+__global__ void __launch_bounds__(kThreads, 3) tc_gemm_tn_kernel(const TnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_smem;
@@ -351,8 +352,15 @@ bool tc_gemm_tn_launch(cudaStream_t st, int G, const float *A, const float *B, f
     a.tileN = ((N + a.ntiles - 1) / a.ntiles + 15) / 16 * 16;
     a.lda = lda; a.ldb = ldb; a.ldc = ldc; a.gA = gA; a.gB = gB; a.gC = gC;
     // split K into slices of >= 12 slabs when one CTA's chain would be long (the conv2 weight gradient: K = B * positions)
+    // MAEXP_TC_WGRAD_SLABS = K slabs (of 32) per CTA: a single-buffered CTA pays a chain of latencies per slab, so the
+    // slices are short and many (default 12 slabs for K >= 1024, no split below)
+    static const int slabs_env = getenv("MAEXP_TC_WGRAD_SLABS") ? atoi(getenv("MAEXP_TC_WGRAD_SLABS")) : 0;
     int ksplit = 1;
-    if (part && K >= 1024) {
+    if (part && slabs_env > 0) {
+        ksplit = (K + 32 * slabs_env - 1) / (32 * slabs_env);
+        if (ksplit > 32) ksplit = 32;
+        while (ksplit > 1 && (long long)ksplit * G * M * N > part_floats) --ksplit;
+    } else if (part && K >= 1024) {
         ksplit = K / 384;
         if (ksplit > 8) ksplit = 8;
         while (ksplit > 1 && (long long)ksplit * G * M * N > part_floats) --ksplit;

@@ -2,7 +2,7 @@
 by one-thread kernels at the phase boundaries; MAEXP_LEARNER_STAMPS=1).  CUPTI timelines serialise the update's branches."""
 import os, sys
 if os.environ.get("STAMPS", "1") != "0":  # STAMPS=0: the plain timing, no stamp kernels in the graph
-    os.environ["MAEXP_LEARNER_STAMPS"] = "1"
+    os.environ["MAEXP_LEARNER_STAMPS"] = os.environ.get("STAMPS", "1")  # "1": all slots; else a bit mask of slots (0x641: start, loss, joined, done)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from maexp_b200.config import baseline_config
