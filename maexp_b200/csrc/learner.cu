@@ -1857,6 +1857,18 @@ void wgrad_close() {  // join the side streams back into the main stream
 // the pooling argmax (bias added before the comparison, first maximum wins: F.max_pool2d on the biased conv output).
 // blockIdx.z selects one of up to three passes of an update (online(s), online(s'), target(s')), so that all of them are one
 // launch and share the SMs instead of queueing behind each other's shared-memory footprint.
+// one warp copies a row of n floats from HBM into shared memory with eight loads in flight per lane (a plain load -> store
+// loop is one global round trip per element)
+__device__ __forceinline__ void warp_copy_row(float *dst, const float *src, int n, int lane) {
+    for (int base = lane; base < n; base += 32 * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (base + 32 * u < n) ? __ldg(src + base + 32 * u) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (base + 32 * u < n) dst[base + 32 * u] = v[u];
+    }
+}
 struct TrunkPasses {
     const float *obs[3], *params[3];
     float *flat[3];
@@ -1882,9 +1894,18 @@ __global__ void __launch_bounds__(512) trunk_fused_fwd_kernel(const __grid_const
     float *s_p = b2 + 64 + warp * (32 * PC + (CVV + 3) / 4 * 4);  // per warp: pooled [ic][PC] (16-byte aligned), then the observation
     float *s_obs = s_p + 32 * PC;
     const float *W = params + (size_t)g * P;
-    for (int i = threadIdx.x; i < F1 * 256; i += blockDim.x) {
-        const int ic = i >> 8, l = (i >> 3) & 31, tap = (i >> 1) & 3, oc = l + 32 * (i & 1);
-        w2t[i] = oc < F2 ? W[o_c2w + ((size_t)oc * F1 + ic) * 4 + tap] : 0.0f;
+    for (int base = threadIdx.x; base < F1 * 256; base += blockDim.x * 16) {  // sixteen loads in flight per thread
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int i = base + u * blockDim.x, ic = i >> 8, l = (i >> 3) & 31, tap = (i >> 1) & 3, oc = l + 32 * (i & 1);
+            v[u] = (i < F1 * 256 && oc < F2) ? __ldg(W + o_c2w + ((size_t)oc * F1 + ic) * 4 + tap) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int i = base + u * blockDim.x;
+            if (i < F1 * 256) w2t[i] = v[u];
+        }
     }
     for (int i = threadIdx.x; i < K1 * 32; i += blockDim.x) {
         const int k = i >> 5, f = i & 31;
@@ -1897,7 +1918,7 @@ __global__ void __launch_bounds__(512) trunk_fused_fwd_kernel(const __grid_const
     const float *src = obs + (size_t)g * gObs;
     float *dst = flat + (size_t)g * gFlat;
     for (int b = blockIdx.x * nwarps + warp; b < B; b += gridDim.x * nwarps) {
-        for (int i = lane; i < CVV; i += 32) s_obs[i] = src[(size_t)b * stride + i];
+        warp_copy_row(s_obs, src + (size_t)b * stride, CVV, lane);
         __syncwarp();
         // conv1 + max-pool, lane = conv1 output channel: the 3x3 input patch of a pooled cell is read once per input
         // channel and feeds the four conv positions under the pooling window
@@ -1990,9 +2011,20 @@ __global__ void __launch_bounds__(256) trunk_fused_bwd_kernel(const float *d_fla
     float *s_obs = s_d + Dp;
     float *gw = s_obs + CVVp;                       // [K1][32] conv1 weight gradient of this warp's samples, then [32] + [64] biases
     const float *W = params + (size_t)g * P;
-    for (int i = threadIdx.x; i < F2 * 128; i += blockDim.x) {
-        const int oc = i >> 7, ic = (i >> 2) & 31, tap = i & 3;
-        w2s[i] = ic < F1 ? W[o_c2w + ((size_t)oc * F1 + ic) * 4 + tap] : 0.0f;
+    // sixteen loads in flight per thread: as a plain load -> store loop this staging was one global round trip per element
+    // (32 in a row per thread), 60 % of the kernel's stall samples (ncu, profiles/r2_bwd_chain_hot_lines.txt)
+    for (int base = threadIdx.x; base < F2 * 128; base += blockDim.x * 16) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int i = base + u * blockDim.x, oc = i >> 7, ic = (i >> 2) & 31, tap = i & 3;
+            v[u] = (i < F2 * 128 && ic < F1) ? __ldg(W + o_c2w + ((size_t)oc * F1 + ic) * 4 + tap) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int i = base + u * blockDim.x;
+            if (i < F2 * 128) w2s[i] = v[u];
+        }
     }
     for (int i = lane; i < K1 * 32 + 96; i += 32) gw[i] = 0.0f;
     __syncthreads();
@@ -2000,8 +2032,12 @@ __global__ void __launch_bounds__(256) trunk_fused_bwd_kernel(const float *d_fla
     for (int b = blockIdx.x * nwarps + warp; b < B; b += gridDim.x * nwarps) {
         const float *dsrc = d_flat + (size_t)g * gFlat + (size_t)b * D;
         const float *osrc = obs + (size_t)g * gObs + (size_t)b * stride;
-        for (int i = lane; i < D; i += 32) s_d[i] = dsrc[i];
-        for (int i = lane; i < CVV; i += 32) s_obs[i] = osrc[i];
+        // the pooling argmax of this sample (read after the conv2 products): loaded now, so that its latency hides behind them
+        int amax[NC];
+#pragma unroll
+        for (int cell = 0; cell < NC; ++cell) amax[cell] = lane < F1 ? arg[(size_t)g * gP + ((size_t)b * NC + cell) * F1 + lane] : 0;
+        warp_copy_row(s_d, dsrc, D, lane);
+        warp_copy_row(s_obs, osrc, CVV, lane);
         __syncwarp();
         float acc[NC];
 #pragma unroll
@@ -2028,7 +2064,7 @@ __global__ void __launch_bounds__(256) trunk_fused_bwd_kernel(const float *d_fla
         int off[NC];
 #pragma unroll
         for (int cell = 0; cell < NC; ++cell) {
-            const int a = lane < F1 ? arg[(size_t)g * gP + ((size_t)b * NC + cell) * F1 + lane] : 0;
+            const int a = amax[cell];
             off[cell] = (2 * (cell / Hp) + (a >> 1)) * V + 2 * (cell % Hp) + (a & 1);
             gb1 += acc[cell];
         }
@@ -4331,7 +4367,9 @@ int maexp_learner_apply(maexp_learner *h, float grad_scale, const uint8_t *activ
                                     "online(s') pass fwd done", "loss done", "mlp data-grad chain done", "trunk backward done",
                                     "all gradients joined", "clip + optimizer done", "mlp_fused_bwd launch", "mlp_fused_bwd done",
                                     "trunk_fused_bwd done"};
-            for (int i = 0; i < 14; ++i) fprintf(stderr, "  stamp %2d %8.1f us  %s\n", i, (double)((long long)(t[i] - t[0])) * 1e-3, name[i]);
+            for (int i = 0; i < 14; ++i)
+                if (t[i] >= t[0])  // (slots outside the mask stay zero)
+                    fprintf(stderr, "  stamp %2d %8.1f us  %s\n", i, (double)((long long)(t[i] - t[0])) * 1e-3, name[i]);
             for (int i = 14; i < 38; i += 2)
                 if (t[i] > t[0] && t[i + 1] > t[0])
                     fprintf(stderr, "  stamp %2d %8.1f -> %8.1f us  tensor-core weight-gradient GEMM (+ its split-K reduction)\n", i,
