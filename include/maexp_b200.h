@@ -325,6 +325,15 @@ int maexp_learner_attention(maexp_learner *learner, int stack, int layer, int ba
 int maexp_tc_gemm(const float *A, const float *W, const float *bias, float *C, int32_t M, int32_t N, int32_t K, int64_t lda,
                   int64_t ldw, int64_t ldc, int32_t relu, int32_t split, void *stream);
 
+/* Tensor-core weight-gradient product of an update (csrc/tc_gemm.cu, tc_gemm_tn_kernel): C[M,N] = sum_k A[k][m] * B[k][n] with
+ * both operands stored k-outermost (A = dY [K rows][lda], B = X [K rows][ldb]) -- grad_weight = dY^T X of nn.Linear
+ * (models/mlp.py:28-34) and of the im2col form of nn.Conv2d (models/convolution.py:44-55); three TF32 terms per product.
+ * K >= 1024 with a partials buffer: split-K slices write dense tiles partials[slice][M][N] (*ksplit_out slices, to be added
+ * in slice order by the caller) instead of C; otherwise *ksplit_out = 1 and C (row stride ldc) holds the result.  The
+ * learner uses it behind MAEXP_TC_WGRAD=1 (opt-in: measured slower than the CUDA-core split-K GEMMs inside an update). */
+int maexp_tc_gemm_tn(const float *A, const float *B, float *C, float *partials, int64_t partials_floats, int32_t M, int32_t N,
+                     int32_t K, int64_t lda, int64_t ldb, int64_t ldc, int32_t *ksplit_out, void *stream);
+
 /* relative / merged models: index-space positions of the observing agent, int8 [G,B,2] for the state batch and for
  * the next-state batch (maexp_batch.pos / next_pos); used by the following grads / q_values calls */
 int maexp_learner_bind_positions(maexp_learner *learner, const int8_t *pos, const int8_t *next_pos);

@@ -110,6 +110,8 @@ SYMBOLS = {
     "maexp_learner_buffer": (C.c_void_p, [C.c_void_p, C.c_int]),
     "maexp_tc_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                 C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "maexp_tc_gemm_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int32), C.c_void_p]),
     "maexp_learner_attention_tokens": (C.c_int, [C.c_void_p, C.c_int]),
     "maexp_learner_attention": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "maexp_learner_bind_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

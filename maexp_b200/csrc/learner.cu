@@ -1441,8 +1441,8 @@ struct maexp_learner {
     // data-gradient chain instead of beside it (stamps: gradients joined 22 us after the chain instead of 1 us)
     bool tc_wgrad = false;
     // MAEXP_MLP_BWD_SPLIT=1: the heads' data-gradient chain as two kernels (dh once per head, then dx) instead of one whose
-    // column tiles each repeat the dout W2 product.  Opt-in: half the flops, but measured slower inside the update (183 against
-    // 175 us) -- the phase is bound by contention with the weight-gradient kernels beside it, not by this kernel's arithmetic
+    // column tiles each repeat the dout W2 product (twice at din = 256).  Opt-in: measured slower inside the update (183 against
+    // 175 us) -- one more launch on the chain, and the dh kernel's 128 CTAs walk the same 8 K steps
     bool mlp_bwd_split = false;
     bool tc_mlp = true;            // the MLP heads of >= 128-row update batches on tcgen05 (csrc/tc_mlp.cu; MAEXP_TC_MLP=0: the SIMT kernel).
                                    // First measured slower than the SIMT kernel (45 vs 33 us at B = 256; profiles/r2_tc_mlp_fwd_*.txt): its
@@ -2262,8 +2262,8 @@ __global__ void __launch_bounds__(256) mlp_fused_fwd_kernel(long long x_row, lon
 // in registers.  A CTA owns 32 rows and one 128-column tile of dx (blockIdx.y); both weight matrices are read in their
 // PyTorch layout, which is already [k][n] for these two products.  Replaces 2 GEMMs + 2 split-K reductions per head on the
 // critical path of the backward pass.  dx == nullptr: only dh (plain MLP on the observation).
-// three resident CTAs per SM (<= 80 registers): at 127 registers two CTAs fill an SM's register file, the 320 CTAs of a C51
-// update (8 row tiles x 5 column tiles x 8 agents) need a second wave on 296 slots and nothing else fits beside them
+// three resident CTAs per SM (<= 80 registers, no spills): at 127 registers two CTAs fill an SM's register file and nothing else
+// (a weight-gradient CTA of the side streams) fits beside them
 #ifndef MAEXP_MLP_BWD_MINB
 #define MAEXP_MLP_BWD_MINB 3
 #endif
@@ -3016,7 +3016,7 @@ void backward(maexp_learner *h, cudaStream_t st, const float *obs) {
         }
         stamp(st, 11);
         // MAEXP_MLP_BWD_SPLIT=1: dh once per head, then dx from it -- in the one-kernel form every one of the din / 128 column
-        // tiles repeats the dout W2 product (5x at din = 576: more than half of its flops)
+        // tiles repeats the dout W2 product (2x at din = 256, the flattened trunk output at V = 7)
         // heads in parallel (default for two heads inside an update; MAEXP_MLP_BWD_HEADS_PARALLEL=0: one CTA walks both): at
         // B = 256 the grid is 8 row tiles x 2 column tiles x 8 agents = 128 CTAs of 8 warps, one per SM, so the kernel's time is
         // one CTA's chain of 18 K steps; with a head per CTA the longer chain is 12 steps and an SM holds two CTAs

@@ -391,3 +391,14 @@ extern "C" int maexp_tc_gemm(const float *A, const float *W, const float *bias, 
     if (cudaGetLastError() != cudaSuccess) return maexp::fail("maexp_tc_gemm: launch failed");
     return 0;
 }
+
+extern "C" int maexp_tc_gemm_tn(const float *A, const float *B, float *C, float *partials, int64_t partials_floats, int32_t M, int32_t N,
+                                int32_t K, int64_t lda, int64_t ldb, int64_t ldc, int32_t *ksplit_out, void *stream) {
+    if (!A || !B || !C) return maexp::fail("maexp_tc_gemm_tn: null argument");
+    int ks = 1;
+    if (!maexp::tc_gemm_tn_launch(static_cast<cudaStream_t>(stream), 1, A, B, C, M, N, K, lda, ldb, ldc, 0, 0, 0, partials, partials_floats, &ks))
+        return maexp::fail("maexp_tc_gemm_tn: unsupported shape (M, N >= 16, K >= 64)");
+    if (cudaGetLastError() != cudaSuccess) return maexp::fail("maexp_tc_gemm_tn: launch failed");
+    if (ksplit_out) *ksplit_out = ks;
+    return 0;
+}

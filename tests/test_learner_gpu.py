@@ -560,6 +560,33 @@ def test_tcgen05_gemm_against_fp64(M, N, K):
                                      M, N, K, K, K, N, 0, 2, None))  # split must be 1 or 3
 
 
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (204, 128, 256), (51, 128, 300), (64, 128, 2304), (128, 576, 1100), (37, 70, 64)])
+def test_tcgen05_weight_gradient_gemm_against_fp64(M, N, K):
+    """maexp_tc_gemm_tn (C = A^T B with the batch as K, operands transposed while staging, three TF32 terms): within 1e-5 of the
+    exact product sum; ragged M / N / K, rows that are not 16-byte aligned (lda = 51, 37), split-K partial tiles for K >= 1024."""
+    import ctypes as C
+    from maexp_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((K, M), generator=gen).cuda()
+    B = torch.randn((K, N), generator=gen).cuda() * 0.1
+    want = A.double().T @ B.double()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    part = torch.full((8 * M * N,), float("nan"), device="cuda")
+    ks = C.c_int32(0)
+    _lib.check(lib.maexp_tc_gemm_tn(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(out.data_ptr()),
+                                    C.c_void_p(part.data_ptr()), part.numel(), M, N, K, M, N, N, C.byref(ks), None))
+    torch.cuda.synchronize()
+    assert (ks.value > 1) == (K >= 1024)
+    got = out if ks.value == 1 else part[: ks.value * M * N].view(ks.value, M, N).sum(0)
+    assert not torch.isnan(got).any()
+    assert float((got.double() - want).abs().max() / want.abs().max()) < 1e-5
+    with pytest.raises(Exception):
+        _lib.check(lib.maexp_tc_gemm_tn(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(out.data_ptr()), None, 0,
+                                        8, N, K, M, N, N, None, None))  # M < 16
+
+
 def test_attention_agent_returns_reference_structures():
     """generate_agents(agent_type=attention): get_action_attns -> (action, [stacked maps per group]) as attention_agent.py:14-22;
     DA6 gives [local, relative], the da3_baseline brain the zero placeholder of da3_brain.py:107-123."""
