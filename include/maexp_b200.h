@@ -224,12 +224,15 @@ typedef struct {
 
 /* maexp_batch.error_flag bits.  NO_VALID: 64 redraws and a 4096-pair walk found only transitions into reset slots (a ring of
  * 2-3 slots whose environments all reset on the same tick), the sampled row is not a transition; INDEX_RANGE: an injected
- * (slot, env) lay outside the ring and was clamped; INDEX_INVALID: an injected pair names a transition into a reset slot.
+ * (slot, env) lay outside the ring and was clamped; INDEX_INVALID: an injected pair names a transition into a reset slot;
+ * NOT_UNIQUE: the ring holds fewer distinct transitions than the batch asks for, a pick repeats.
  * A flagged row carries action 0 instead of the reset slot's -1, so the loss kernels never index out of bounds. */
-enum { MAEXP_REPLAY_ERR_NO_VALID = 1, MAEXP_REPLAY_ERR_INDEX_RANGE = 2, MAEXP_REPLAY_ERR_INDEX_INVALID = 4 };
+enum { MAEXP_REPLAY_ERR_NO_VALID = 1, MAEXP_REPLAY_ERR_INDEX_RANGE = 2, MAEXP_REPLAY_ERR_INDEX_INVALID = 4,
+       MAEXP_REPLAY_ERR_NOT_UNIQUE = 8 /* fewer distinct transitions than samples: the batch repeats one (np.random.choice raises) */ };
 
-/* Uniform sampling of `batch` whole-team transitions (np.random.choice in buffer.py:61; here with
- * replacement — immaterial for batch << S*E) fused with the gather into per-agent batches.
+/* Uniform sampling of `batch` DISTINCT whole-team transitions (np.random.choice(len, batch, replace=False), buffer.py:61:
+ * sequential rejection sampling, sample b draws again while it equals a pick of a lower index; batch > 1024 samples with
+ * replacement) fused with the gather into per-agent batches.
  * indices: optional int32 [B,2] (slot, env) injected picks (NULL: Philox keyed by seed/tick). */
 int maexp_replay_sample(const maexp_replay_view *ring, int32_t batch, uint32_t seed, uint32_t tick,
                         const int32_t *indices, const maexp_batch *out, void *stream);

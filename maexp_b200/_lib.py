@@ -53,7 +53,7 @@ class Batch(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "next_obs", "actions", "rewards", "dones", "picked", "pos", "next_pos", "error_flag",
                                           "obj_rows", "next_obj_rows", "agents", "next_agents", "dest_rows", "next_dest_rows")]
 
-REPLAY_ERR_NO_VALID, REPLAY_ERR_INDEX_RANGE, REPLAY_ERR_INDEX_INVALID = 1, 2, 4
+REPLAY_ERR_NO_VALID, REPLAY_ERR_INDEX_RANGE, REPLAY_ERR_INDEX_INVALID, REPLAY_ERR_NOT_UNIQUE = 1, 2, 4, 8
 
 
 class LearnerCfg(C.Structure):

@@ -89,7 +89,8 @@ class DeviceReplayRing:
         return b
 
     def sample(self, batch, seed=0, tick=0, indices=None):
-        """Fills `batch` (from new_batch) with uniformly sampled transitions; indices: int32 [B,2]."""
+        """Fills `batch` (from new_batch) with uniformly sampled DISTINCT transitions (buffer.py:61, replace=False);
+        indices: int32 [B,2] injected (slot, env) picks."""
         B = batch["actions"].shape[1]
         view = _lib.ReplayView(self.obs.data_ptr(), self.actions.data_ptr(), self.rewards.data_ptr(),
                                self.dones.data_ptr(), self.was_reset.data_ptr(),
@@ -131,7 +132,9 @@ class DeviceReplayRing:
             why = [text for bit, text in ((_lib.REPLAY_ERR_NO_VALID, "no valid transition in the ring (every stored step is "
                                            "followed by a reset: the ring is too short for the episode length)"),
                                           (_lib.REPLAY_ERR_INDEX_RANGE, "an injected (slot, env) pick lies outside the ring"),
-                                          (_lib.REPLAY_ERR_INDEX_INVALID, "an injected pick names a transition into a reset slot"))
+                                          (_lib.REPLAY_ERR_INDEX_INVALID, "an injected pick names a transition into a reset slot"),
+                                          (_lib.REPLAY_ERR_NOT_UNIQUE, "the ring holds fewer distinct transitions than the batch "
+                                           "(np.random.choice(replace=False) raises ValueError here)"))
                    if flag & bit]
             raise _lib.MaexpError("maexp_replay_sample: " + "; ".join(why))
 

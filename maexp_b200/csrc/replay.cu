@@ -3,8 +3,12 @@
 // Replaces ReplayBuffer.sample + RLDataset.__iter__ + DataLoader default collate
 // (core/utils/buffer.py:60-63, core/utils/dataset.py:24-29, abstract_trainer.py:93-97): one launch
 // picks `batch` whole-team transitions and writes the per-agent batches the learner consumes.
-// One warp per (sample, agent): the pick is recomputed per warp (a few Philox calls) so that no
-// second launch or index buffer is needed; rows are moved with 128-bit loads/stores.
+// One warp per (sample, agent); rows are moved with 128-bit loads/stores.  The picks are DISTINCT, as
+// np.random.choice(len, batch, replace=False) in buffer.py:61: every CTA recomputes the whole pick list in shared memory
+// (one Philox call per sample, a duplicate scan of batch^2 / 2 compares spread over the CTA) -- sequential rejection
+// sampling, sample b redraws while it equals a pick of a lower index -- so that no second launch, index buffer or
+// grid-wide barrier is needed and the result depends on (seed, tick) only.  Batches above kUniqueMaxBatch keep the
+// recompute-per-warp path and sample with replacement.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -19,6 +23,8 @@ int fail(const std::string &msg);
 constexpr uint32_t kStreamReplay = 7;
 constexpr int kMaxRedraws = 64;
 constexpr int kMaxProbes = 4096;
+constexpr int kUniqueMaxBatch = 1024;  // distinct picks up to this batch size (the reference's batches are 32 .. 256)
+constexpr int kMaxUniqueRounds = 256;  // redraws of duplicates per launch before the sampler gives up and says so
 
 // state slot of the transition of age `age` (state = head-1-age, next = head-age); false when the next slot is a reset
 __device__ __forceinline__ bool valid_transition(const maexp_replay_view &r, int age, int env, int *slot) {
@@ -28,14 +34,89 @@ __device__ __forceinline__ bool valid_transition(const maexp_replay_view &r, int
     return !r.was_reset[(size_t)((s + 1) % r.num_slots) * r.num_envs + env];
 }
 
+// sample b's next valid transition, continuing its draw sequence at d (d-th Philox draw of the sample: transition age a in
+// [0, count-2] -- state slot = head-1-a, next slot = head-a (mod S) -- and environment); false: neither the redraws nor the
+// fixed walk found a transition
+__device__ bool draw_pick(const maexp_replay_view &r, uint32_t seed, uint32_t tick, int b, uint32_t &d, int &slot, int &env) {
+    bool ok = false;
+    int age = 0;
+    for (; d < (uint32_t)kMaxRedraws && !ok; ++d) {
+        const uint4 w = philox4x32_10(seed, 0x52504C59u /*'RPLY'*/, tick, kStreamReplay, d, (uint32_t)b);
+        age = (int)scale(w.x, (uint32_t)(r.count - 1));
+        env = (int)scale(w.y, (uint32_t)r.num_envs);
+        ok = valid_transition(r, age, env, &slot);
+    }
+    // every redraw hit a transition into a reset slot (tiny rings whose envs reset in lock-step): walk the
+    // (age, env) pairs after the last draw in a fixed order
+    for (int probe = 0; probe < kMaxProbes && !ok; ++probe) {
+        if (++age >= r.count - 1) {
+            age = 0;
+            if (++env >= r.num_envs) env = 0;
+        }
+        ok = valid_transition(r, age, env, &slot);
+    }
+    return ok;
+}
+
 __global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint32_t seed, uint32_t tick,
                                      const int32_t *indices, const maexp_batch out) {
+    extern __shared__ unsigned long long s_key[];  // unique path: [batch] (slot << 32 | env) of every sample, then [batch] draw counters
+    __shared__ int s_first, s_flags;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int N = r.num_agents;
+    const bool unique = !indices && batch <= kUniqueMaxBatch;
+    if (unique) {  // (before the early exit below: every thread of the CTA takes part)
+        uint32_t *s_d = reinterpret_cast<uint32_t *>(s_key + batch);
+        if (threadIdx.x == 0) s_flags = 0;
+        __syncthreads();
+        for (int q = threadIdx.x; q < batch; q += blockDim.x) {
+            uint32_t d = 0;
+            int sl = 0, en = 0;
+            if (draw_pick(r, seed, tick, q, d, sl, en)) s_key[q] = ((unsigned long long)(uint32_t)sl << 32) | (uint32_t)en;
+            else {
+                s_key[q] = ~0ull - (unsigned long long)q;  // no transition in the ring: flagged, never equal to another key
+                atomicOr(&s_flags, MAEXP_REPLAY_ERR_NO_VALID);
+            }
+            s_d[q] = d;
+        }
+        __syncthreads();
+        for (int round = 0; round <= kMaxUniqueRounds; ++round) {
+            if (threadIdx.x == 0) s_first = batch;
+            __syncthreads();
+            for (int q = threadIdx.x; q < batch; q += blockDim.x) {  // the lowest sample that repeats a pick of a lower index
+                const unsigned long long k = s_key[q];
+                bool dup = false;
+                for (int j = 0; j < q && !dup; ++j) dup = s_key[j] == k;
+                if (dup) atomicMin(&s_first, q);
+            }
+            __syncthreads();
+            const int first = s_first;
+            if (first >= batch) break;
+            if (round == kMaxUniqueRounds) {  // fewer distinct transitions than samples (np.random.choice raises here)
+                if (threadIdx.x == 0) s_flags |= MAEXP_REPLAY_ERR_NOT_UNIQUE;
+                __syncthreads();
+                break;
+            }
+            if (threadIdx.x == 0) {  // every sample below `first` is final: `first` draws again
+                uint32_t d = s_d[first];
+                int sl = 0, en = 0;
+                if (draw_pick(r, seed, tick, first, d, sl, en)) s_key[first] = ((unsigned long long)(uint32_t)sl << 32) | (uint32_t)en;
+                s_d[first] = d;
+            }
+            __syncthreads();
+        }
+    }
     if (warp >= batch * N) return;
     const int b = warp / N, agent = warp - b * N;
     int slot = 0, env = 0, flags = 0;
-    if (indices) {
+    if (unique) {
+        const unsigned long long k = s_key[b];
+        flags = s_flags;
+        if ((k >> 32) < (unsigned long long)r.num_slots) {  // (else the no-transition marker: slot 0, env 0, flagged)
+            slot = (int)(k >> 32);
+            env = (int)(uint32_t)k;
+        }
+    } else if (indices) {
         slot = indices[2 * b];
         env = indices[2 * b + 1];
         if (slot < 0 || slot >= r.num_slots || env < 0 || env >= r.num_envs) {  // never read outside the ring
@@ -44,26 +125,9 @@ __global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint3
             env = min(max(env, 0), r.num_envs - 1);
         }
         if (r.was_reset[(size_t)((slot + 1) % r.num_slots) * r.num_envs + env]) flags |= MAEXP_REPLAY_ERR_INDEX_INVALID;
-    } else {
-        // transition age a in [0, count-2]: state slot = head-1-a, next slot = head-a (mod S)
-        bool ok = false;
-        int age = 0;
-        for (uint32_t d = 0; d < (uint32_t)kMaxRedraws && !ok; ++d) {
-            const uint4 w = philox4x32_10(seed, 0x52504C59u /*'RPLY'*/, tick, kStreamReplay, d, (uint32_t)b);
-            age = (int)scale(w.x, (uint32_t)(r.count - 1));
-            env = (int)scale(w.y, (uint32_t)r.num_envs);
-            ok = valid_transition(r, age, env, &slot);
-        }
-        // every redraw hit a transition into a reset slot (tiny rings whose envs reset in lock-step): walk the
-        // (age, env) pairs after the last draw in a fixed order; the N warps of a sample take the same walk
-        for (int probe = 0; probe < kMaxProbes && !ok; ++probe) {
-            if (++age >= r.count - 1) {
-                age = 0;
-                if (++env >= r.num_envs) env = 0;
-            }
-            ok = valid_transition(r, age, env, &slot);
-        }
-        if (!ok) flags |= MAEXP_REPLAY_ERR_NO_VALID;  // the row below is NOT a transition; the caller must not train on it
+    } else {  // batches above kUniqueMaxBatch: the pick recomputed per warp (the N warps of a sample take the same draws)
+        uint32_t d = 0;
+        if (!draw_pick(r, seed, tick, b, d, slot, env)) flags |= MAEXP_REPLAY_ERR_NO_VALID;  // the row below is NOT a transition
     }
     if (flags && lane == 0 && out.error_flag) atomicOr(out.error_flag, flags);
     const int nxt = (slot + 1) % r.num_slots;
@@ -150,8 +214,9 @@ extern "C" int maexp_replay_sample(const maexp_replay_view *ring, int32_t batch,
         !out->next_obs || !out->actions || !out->rewards || !out->dones)
         return fail("maexp_replay_sample: null buffer");
     const int warps = batch * ring->num_agents;
-    replay_sample_kernel<<<(warps * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(*ring, batch, seed, tick,
-                                                                                                 indices, *out);
+    const size_t smem = (!indices && batch <= kUniqueMaxBatch) ? (size_t)batch * 12 : 0;  // keys + draw counters of the unique path
+    replay_sample_kernel<<<(warps * 32 + 255) / 256, 256, smem, static_cast<cudaStream_t>(stream)>>>(*ring, batch, seed, tick,
+                                                                                                    indices, *out);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(std::string("maexp_replay_sample: ") + cudaGetErrorString(e));
     return 0;

@@ -317,6 +317,21 @@ def test_replay_ring_sampling():
     assert torch.equal(batch["picked"].cpu(), p1)
     ring.sample(batch, seed=921, tick=6)
     assert not torch.equal(batch["picked"].cpu(), p1)
+    # (3) without replacement, as np.random.choice(len, B, replace=False) (buffer.py:61): 64 draws from <= 720 transitions repeat
+    # one in ~94 % of the batches when drawn with replacement; every batch here is distinct, and the picks stay uniform
+    seen = torch.zeros((S, E), dtype=torch.int64)
+    batch["error_flag"].zero_()  # (the injected picks of (1) included transitions into reset slots)
+    for tick in range(200):
+        ring.sample(batch, seed=4, tick=tick)
+        p = batch["picked"].cpu().long()
+        assert len({(int(a), int(b)) for a, b in p}) == B, tick
+        seen[p[:, 0], p[:, 1]] += 1
+    ring.check(batch)
+    valid = (was_reset[(torch.arange(S) + 1) % S] == 0)
+    valid[ring.head] = False  # the newest slot has no successor yet
+    assert int(seen[~valid].sum()) == 0
+    freq = seen[valid].double() / (200 * B / int(valid.sum()))
+    assert float(freq.min()) > 0.15 and float(freq.max()) < 2.5 and abs(float(freq.mean()) - 1.0) < 1e-9
 
 
 def test_replay_sampler_flags_a_ring_without_valid_transitions():
@@ -350,6 +365,13 @@ def test_replay_sampler_flags_a_ring_without_valid_transitions():
     ring.commit()
     ring.sample(batch, seed=921, tick=1)
     ring.check(batch)
+    # more samples than distinct transitions (32 here): np.random.choice(replace=False) raises, the sampler flags the batch
+    big = ring.new_batch(48)
+    ring.sample(big, seed=921, tick=2)
+    torch.cuda.synchronize()
+    assert int(big["error_flag"].item()) == _lib.REPLAY_ERR_NOT_UNIQUE
+    with pytest.raises(_lib.MaexpError):
+        ring.check(big)
     # injected picks: out of range (clamped, flagged) and a pick into a reset slot (flagged, action clamped to 0)
     bad = torch.tensor([[7, 0]] + [[(ring.head - 1) % 2, 1]] * (B - 1), dtype=torch.int32).cuda()
     ring.sample(batch, indices=bad)
