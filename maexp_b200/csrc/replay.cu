@@ -60,14 +60,20 @@ __device__ bool draw_pick(const maexp_replay_view &r, uint32_t seed, uint32_t ti
 
 __global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint32_t seed, uint32_t tick,
                                      const int32_t *indices, const maexp_batch out) {
-    extern __shared__ unsigned long long s_key[];  // unique path: [batch] (slot << 32 | env) of every sample, then [batch] draw counters
-    __shared__ int s_first, s_flags;
+    // unique path: [batch] keys (slot << 32 | env) of every sample, [cap] hash table (cap = the power of two >= 2 * batch), [batch]
+    // draw counters
+    extern __shared__ unsigned long long s_key[];
+    __shared__ int s_first, s_flags, s_any;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int N = r.num_agents;
     const bool unique = !indices && batch <= kUniqueMaxBatch;
     if (unique) {  // (before the early exit below: every thread of the CTA takes part)
-        uint32_t *s_d = reinterpret_cast<uint32_t *>(s_key + batch);
-        if (threadIdx.x == 0) s_flags = 0;
+        int cap = 64;
+        while (cap < 2 * batch) cap <<= 1;
+        unsigned long long *s_tab = s_key + batch;
+        uint32_t *s_d = reinterpret_cast<uint32_t *>(s_tab + cap);
+        if (threadIdx.x == 0) s_flags = s_any = 0;
+        for (int q = threadIdx.x; q < cap; q += blockDim.x) s_tab[q] = ~0ull;
         __syncthreads();
         for (int q = threadIdx.x; q < batch; q += blockDim.x) {
             uint32_t d = 0;
@@ -80,7 +86,21 @@ __global__ void replay_sample_kernel(const maexp_replay_view r, int batch, uint3
             s_d[q] = d;
         }
         __syncthreads();
-        for (int round = 0; round <= kMaxUniqueRounds; ++round) {
+        // does any pick repeat?  (whether one does is independent of the insertion order; almost always none does, and the
+        // batch^2 / 2 compares below are skipped)
+        for (int q = threadIdx.x; q < batch; q += blockDim.x) {
+            const unsigned long long k = s_key[q];
+            if ((k >> 32) >= (unsigned long long)r.num_slots) continue;  // (the no-transition marker)
+            uint32_t hsh = ((uint32_t)(k >> 32) * 0x9E3779B1u + (uint32_t)k * 0x85EBCA6Bu) & (uint32_t)(cap - 1);
+            for (;;) {
+                const unsigned long long prev = atomicCAS(&s_tab[hsh], ~0ull, k);
+                if (prev == ~0ull) break;
+                if (prev == k) { s_any = 1; break; }
+                hsh = (hsh + 1) & (uint32_t)(cap - 1);
+            }
+        }
+        __syncthreads();
+        for (int round = 0; s_any && round <= kMaxUniqueRounds; ++round) {
             if (threadIdx.x == 0) s_first = batch;
             __syncthreads();
             for (int q = threadIdx.x; q < batch; q += blockDim.x) {  // the lowest sample that repeats a pick of a lower index
@@ -214,7 +234,12 @@ extern "C" int maexp_replay_sample(const maexp_replay_view *ring, int32_t batch,
         !out->next_obs || !out->actions || !out->rewards || !out->dones)
         return fail("maexp_replay_sample: null buffer");
     const int warps = batch * ring->num_agents;
-    const size_t smem = (!indices && batch <= kUniqueMaxBatch) ? (size_t)batch * 12 : 0;  // keys + draw counters of the unique path
+    size_t smem = 0;  // unique path: keys + hash table + draw counters
+    if (!indices && batch <= kUniqueMaxBatch) {
+        int cap = 64;
+        while (cap < 2 * batch) cap <<= 1;
+        smem = (size_t)batch * 12 + (size_t)cap * 8;
+    }
     replay_sample_kernel<<<(warps * 32 + 255) / 256, 256, smem, static_cast<cudaStream_t>(stream)>>>(*ring, batch, seed, tick,
                                                                                                     indices, *out);
     const cudaError_t e = cudaGetLastError();
