@@ -1,5 +1,8 @@
-import ctypes as C, torch, sys
-sys.path.insert(0, "/root/repo")
+"""GPU experiment: stand-alone time of the tcgen05 weight-gradient GEMM (maexp_tc_gemm_tn, csrc/tc_gemm.cu) per launch, back to
+back, for the shapes of a C51 team update (one agent-network per launch)."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
 from maexp_b200 import _lib
 lib = _lib.load()
 for (M, N, K) in [(204, 128, 256), (128, 256, 256), (64, 128, 384), (128, 256, 64)]:
